@@ -1,0 +1,269 @@
+"""Synthetic GWF model builders: produce exactly the arrays the reference's
+ConnectionsType / GwfNpfType / GwfStoType / BndType would hand to the solver.
+
+DIS connectivity follows src/Model/ModelUtilities/Connections.f90:463-700
+(`disconnections`): node = k*nrow*ncol + i*ncol + j (0-based here), CSR row =
+[diag, up(k-1), back(i-1), left(j-1), right(j+1), front(i+1), down(k+1)],
+upper-triangle connections numbered in (k,i,j) order as right, front, down;
+cl1/cl2 = half cell sizes, hwva = perpendicular width (horizontal) or area
+(vertical), ihc = 1 horizontal / 0 vertical.
+
+All index arrays produced here are 0-based (index_base = 0).
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import ctypes_types as T
+
+
+@dataclass
+class Package:
+    type: int
+    nodelist: np.ndarray
+    b1: np.ndarray
+    b2: np.ndarray = None
+    b3: np.ndarray = None
+    iflowred: int = 0
+    flowred: float = 0.1
+
+    def __post_init__(self):
+        self.nodelist = T.as_i32(self.nodelist)
+        self.b1 = T.as_f64(self.b1)
+        nb = self.nodelist.size
+        self.b2 = T.as_f64(self.b2) if self.b2 is not None else np.zeros(nb)
+        self.b3 = T.as_f64(self.b3) if self.b3 is not None else np.zeros(nb)
+
+    def struct(self):
+        return T.BndPackageStruct(self.type, self.nodelist.size, 0, self.iflowred, self.flowred,
+                                  T.ptr_i32(self.nodelist), T.ptr_f64(self.b1),
+                                  T.ptr_f64(self.b2), T.ptr_f64(self.b3))
+
+
+def package_array(pkgs):
+    arr = (T.BndPackageStruct * max(1, len(pkgs)))()
+    for i, p in enumerate(pkgs):
+        arr[i] = p.struct()
+    return arr
+
+
+@dataclass
+class GwfModel:
+    """Arrays of one GWF model (0-based indices)."""
+
+    nodes: int
+    ia: np.ndarray
+    ja: np.ndarray
+    jas: np.ndarray
+    isym: np.ndarray
+    ihc: np.ndarray
+    cl1: np.ndarray
+    cl2: np.ndarray
+    hwva: np.ndarray
+    top: np.ndarray
+    bot: np.ndarray
+    area: np.ndarray
+    k11: np.ndarray
+    k33: np.ndarray
+    icelltype: np.ndarray
+    strt: np.ndarray
+    ibound: np.ndarray = None
+    ibotnode: np.ndarray = None
+    ss: np.ndarray = None
+    sy: np.ndarray = None
+    iconvert: np.ndarray = None
+    icellavg: int = 0
+    inewton: int = 0
+    inewtonur: int = 0
+    iperched: int = 0
+    ivarcv: int = 0
+    idewatcv: int = 0
+    insto: int = 0
+    istor_coef: int = 0
+    iconf_ss: int = 0
+    iorig_ss: int = 0
+    shape: tuple = None
+    meta: dict = field(default_factory=dict)
+
+    def __post_init__(self):
+        n = self.nodes
+        for name in ("ia", "ja", "jas", "isym", "ihc", "icelltype"):
+            setattr(self, name, T.as_i32(getattr(self, name)))
+        for name in ("cl1", "cl2", "hwva", "top", "bot", "area", "k11", "k33", "strt"):
+            setattr(self, name, T.as_f64(getattr(self, name)))
+        self.ibound = T.as_i32(self.ibound) if self.ibound is not None else np.ones(n, np.int32)
+        self.ibotnode = T.as_i32(self.ibotnode) if self.ibotnode is not None else np.arange(n, dtype=np.int32)
+        self.ss = T.as_f64(self.ss) if self.ss is not None else np.zeros(n)
+        self.sy = T.as_f64(self.sy) if self.sy is not None else np.zeros(n)
+        self.iconvert = T.as_i32(self.iconvert) if self.iconvert is not None else np.zeros(n, np.int32)
+
+    @property
+    def nja(self):
+        return int(self.ja.size)
+
+    @property
+    def njas(self):
+        return int(self.ihc.size)
+
+    def struct(self):
+        s = T.GwfModelStruct()
+        s.index_base = 0
+        s.nodes, s.nja, s.njas = self.nodes, self.nja, self.njas
+        for name in ("ia", "ja", "jas", "isym", "ihc", "ibound", "icelltype", "ibotnode", "iconvert"):
+            setattr(s, name, T.ptr_i32(getattr(self, name)))
+        for name in ("cl1", "cl2", "hwva", "top", "bot", "area", "strt", "k11", "k33", "ss", "sy"):
+            setattr(s, name, T.ptr_f64(getattr(self, name)))
+        for name in ("icellavg", "inewton", "inewtonur", "iperched", "ivarcv", "idewatcv", "insto",
+                     "istor_coef", "iconf_ss", "iorig_ss"):
+            setattr(s, name, int(getattr(self, name)))
+        s.ithickstrt = 0
+        return s
+
+    def node(self, k, i, j):
+        nlay, nrow, ncol = self.shape
+        return (k * nrow + i) * ncol + j
+
+
+def _bcast(v, shape):
+    a = np.asarray(v, dtype=np.float64)
+    return np.ascontiguousarray(np.broadcast_to(a, shape)).reshape(-1)
+
+
+def dis_connectivity(nlay, nrow, ncol):
+    """ia, ja, jas, isym (0-based) and per-direction masks for a full DIS grid."""
+    n = nlay * nrow * ncol
+    nrc = nrow * ncol
+    idx = np.arange(n, dtype=np.int64)
+    k = idx // nrc
+    rem = idx - k * nrc
+    i = rem // ncol
+    j = rem - i * ncol
+    # direction order: up, back, left, right, front, down
+    exist = np.empty((n, 6), dtype=bool)
+    exist[:, 0] = k > 0
+    exist[:, 1] = i > 0
+    exist[:, 2] = j > 0
+    exist[:, 3] = j < ncol - 1
+    exist[:, 4] = i < nrow - 1
+    exist[:, 5] = k < nlay - 1
+    offs = np.array([-nrc, -ncol, -1, 1, ncol, nrc], dtype=np.int64)
+    cnt = 1 + exist.sum(axis=1)
+    ia = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(cnt, out=ia[1:])
+    nja = int(ia[-1])
+    # position of direction d inside its row (1 + number of earlier existing directions)
+    pos_in_row = 1 + np.cumsum(exist, axis=1) - exist  # (n,6)
+    # upper connection numbering
+    hasr, hasf, hasd = exist[:, 3], exist[:, 4], exist[:, 5]
+    ucnt = hasr.astype(np.int64) + hasf + hasd
+    ustart = np.zeros(n, dtype=np.int64)
+    np.cumsum(ucnt[:-1], out=ustart[1:])
+    njas = int(ucnt.sum())
+    # candidate arrays (n,7): col, jas, isym
+    col = np.empty((n, 7), dtype=np.int64)
+    jas = np.empty((n, 7), dtype=np.int64)
+    isym = np.empty((n, 7), dtype=np.int64)
+    mask = np.empty((n, 7), dtype=bool)
+    col[:, 0] = idx
+    jas[:, 0] = -1
+    isym[:, 0] = ia[:-1]
+    mask[:, 0] = True
+    opp = [5, 4, 3, 2, 1, 0]
+    # upper index of the connection leaving cell c in direction right/front/down
+    uidx = {3: ustart, 4: ustart + hasr, 5: ustart + hasr + hasf}
+    for d in range(6):
+        m = idx + offs[d]
+        ok = exist[:, d]
+        msafe = np.where(ok, m, 0)
+        col[:, d + 1] = msafe
+        mask[:, d + 1] = ok
+        isym[:, d + 1] = ia[msafe] + pos_in_row[msafe, opp[d]]
+        if d >= 3:
+            jas[:, d + 1] = uidx[d]
+        else:
+            jas[:, d + 1] = uidx[opp[d]][msafe]
+    ja = col[mask].astype(np.int32)
+    jas_f = jas[mask].astype(np.int32)
+    isym_f = isym[mask].astype(np.int32)
+    return dict(n=n, nja=nja, njas=njas, ia=ia.astype(np.int32), ja=ja, jas=jas_f, isym=isym_f,
+                k=k, i=i, j=j, hasr=hasr, hasf=hasf, hasd=hasd, ustart=ustart)
+
+
+def build_dis_model(nlay, nrow, ncol, delr, delc, top, botm, k11, k33=None, icelltype=0,
+                    strt=0.0, ss=None, sy=None, iconvert=None, **opts):
+    """Full (no idomain holes) DIS model.  `top` scalar/(nrow,ncol); `botm`
+    (nlay,) / (nlay,nrow,ncol) layer bottoms; k11/k33/icelltype/strt scalar or
+    (nlay,nrow,ncol)."""
+    c = dis_connectivity(nlay, nrow, ncol)
+    n = c["n"]
+    shp = (nlay, nrow, ncol)
+    delr = np.broadcast_to(np.asarray(delr, dtype=np.float64), (ncol,)).copy()
+    delc = np.broadcast_to(np.asarray(delc, dtype=np.float64), (nrow,)).copy()
+    botm = np.asarray(botm, dtype=np.float64)
+    if botm.ndim == 1:
+        botm = botm[:, None, None]
+    bot3 = np.broadcast_to(botm, shp)
+    top3 = np.empty(shp)
+    top3[0] = np.broadcast_to(np.asarray(top, dtype=np.float64), (nrow, ncol))
+    if nlay > 1:
+        top3[1:] = bot3[:-1]
+    topv = top3.reshape(-1).copy()
+    botv = np.ascontiguousarray(bot3).reshape(-1).copy()
+    area = np.broadcast_to(delc[:, None] * delr[None, :], shp).reshape(-1).copy()
+    # per upper connection geometry, in (k,i,j) order right, front, down
+    k, i, j = c["k"], c["i"], c["j"]
+    hasr, hasf, hasd, ustart = c["hasr"], c["hasf"], c["hasd"], c["ustart"]
+    njas = c["njas"]
+    ihc = np.empty(njas, dtype=np.int32)
+    cl1 = np.empty(njas)
+    cl2 = np.empty(njas)
+    hwva = np.empty(njas)
+    nrc = nrow * ncol
+    # right
+    s = np.nonzero(hasr)[0]
+    u = ustart[s]
+    ihc[u] = 1
+    cl1[u] = 0.5 * delr[j[s]]
+    cl2[u] = 0.5 * delr[j[s] + 1]
+    hwva[u] = delc[i[s]]
+    # front
+    s = np.nonzero(hasf)[0]
+    u = ustart[s] + hasr[s]
+    ihc[u] = 1
+    cl1[u] = 0.5 * delc[i[s]]
+    cl2[u] = 0.5 * delc[i[s] + 1]
+    hwva[u] = delr[j[s]]
+    # down
+    s = np.nonzero(hasd)[0]
+    u = ustart[s] + hasr[s] + hasf[s]
+    ihc[u] = 0
+    cl1[u] = 0.5 * (topv[s] - botv[s])
+    cl2[u] = 0.5 * (topv[s + nrc] - botv[s + nrc])
+    hwva[u] = delr[j[s]] * delc[i[s]]
+    k11v = _bcast(k11, shp)
+    k33v = _bcast(k33 if k33 is not None else k11, shp)
+    ict = np.ascontiguousarray(np.broadcast_to(np.asarray(icelltype, dtype=np.int32), shp)).reshape(-1)
+    ibot = (np.arange(n, dtype=np.int64) % nrc + (nlay - 1) * nrc).astype(np.int32)
+    m = GwfModel(nodes=n, ia=c["ia"], ja=c["ja"], jas=c["jas"], isym=c["isym"], ihc=ihc, cl1=cl1,
+                 cl2=cl2, hwva=hwva, top=topv, bot=botv, area=area, k11=k11v, k33=k33v,
+                 icelltype=ict, strt=_bcast(strt, shp), ibotnode=ibot,
+                 ss=_bcast(ss, shp) if ss is not None else None,
+                 sy=_bcast(sy, shp) if sy is not None else None,
+                 iconvert=(np.ascontiguousarray(np.broadcast_to(np.asarray(iconvert, dtype=np.int32), shp)).reshape(-1)
+                           if iconvert is not None else None),
+                 shape=shp, **opts)
+    if ss is not None or sy is not None:
+        m.insto = 1
+    return m
+
+
+def tdis_steps(perlen, nstp, tsmult):
+    """Time-step lengths of one stress period (src/Timing/tdis.f90:255-267)."""
+    if tsmult == 1.0:
+        d0 = perlen / nstp
+    else:
+        d0 = perlen * (1.0 - tsmult) / (1.0 - tsmult ** nstp)
+    out = [d0]
+    for _ in range(nstp - 1):
+        out.append(out[-1] * tsmult)
+    return out

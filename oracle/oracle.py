@@ -1,0 +1,198 @@
+"""ctypes wrapper over oracle/liboracle_mf6.so -- TEST INFRASTRUCTURE ONLY.
+
+May be imported from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs; never from modflow6_b200/.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from modflow6_b200 import ctypes_types as T
+from modflow6_b200.grid import package_array
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle_mf6.so")
+    srcs = [os.path.join(_HERE, f) for f in ("ims.c", "gwf_solution.c", "mf6_oracle.h")]
+    srcs.append(os.path.join(_HERE, "..", "include", "mf6gpu_types.h"))
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs if os.path.exists(s)):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+class Summary(C.Structure):
+    _fields_ = [("cap", C.c_int), ("count", C.c_int), ("itinner", T.p_i32), ("dvmax", T.p_f64),
+                ("rmax", T.p_f64), ("locdv", T.p_i32), ("locr", T.p_i32), ("alpha", T.p_f64),
+                ("omega", T.p_f64)]
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        vp = C.c_void_p
+        L.orc_ims_create.restype = vp
+        L.orc_ims_create.argtypes = [C.c_int, C.c_int, T.p_i32, T.p_i32, C.POINTER(T.ImsSettings), T.p_i32]
+        L.orc_ims_destroy.argtypes = [vp]
+        L.orc_ims_apply.restype = C.c_int
+        L.orc_ims_apply.argtypes = [vp, T.p_f64, T.p_f64, T.p_f64, C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(Summary)]
+        L.orc_amux.argtypes = [C.c_int, T.p_f64, T.p_f64, T.p_f64, T.p_i32, T.p_i32]
+        L.orc_ddot.restype = C.c_double
+        L.orc_ddot.argtypes = [C.c_int, T.p_f64, T.p_f64]
+        L.orc_dnrm2.restype = C.c_double
+        L.orc_dnrm2.argtypes = [C.c_int, T.p_f64]
+        L.orc_ilu0_create.restype = vp
+        L.orc_ilu0_create.argtypes = [C.c_int, C.c_int, T.p_i32, T.p_i32]
+        L.orc_ilu0_destroy.argtypes = [vp]
+        L.orc_pcu.restype = C.c_int
+        L.orc_pcu.argtypes = [vp, T.p_f64, T.p_i32, T.p_i32, C.c_double]
+        L.orc_ilu0a.argtypes = [vp, T.p_f64, T.p_f64]
+        L.orc_sln_create.restype = vp
+        L.orc_sln_create.argtypes = [C.POINTER(T.GwfModelStruct), C.POINTER(T.SlnSettings), C.POINTER(T.ImsSettings), T.p_i32]
+        L.orc_sln_destroy.argtypes = [vp]
+        L.orc_sln_set_packages.argtypes = [vp, C.c_int, C.POINTER(T.BndPackageStruct)]
+        L.orc_sln_timestep.restype = C.c_int
+        L.orc_sln_timestep.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(T.StepReport)]
+        L.orc_sln_formulate.argtypes = [vp, C.c_int, C.c_double, C.c_int]
+        for f in ("orc_sln_x", "orc_sln_flowja", "orc_sln_amat", "orc_sln_rhs", "orc_sln_condsat"):
+            getattr(L, f).restype = T.p_f64
+            getattr(L, f).argtypes = [vp]
+        L.orc_sln_timers.argtypes = [vp, T.p_f64]
+        _LIB = L
+    return _LIB
+
+
+class OracleIlu0:
+    """pccrs + pcu + ilu0a on a 0-based diag-first CSR."""
+
+    def __init__(self, ia, ja):
+        self.ia, self.ja = T.as_i32(ia), T.as_i32(ja)
+        self.n = self.ia.size - 1
+        self.h = lib().orc_ilu0_create(self.n, self.ja.size, T.ptr_i32(self.ia), T.ptr_i32(self.ja))
+
+    def factor(self, amat, relax):
+        amat = T.as_f64(amat)
+        return lib().orc_pcu(self.h, T.ptr_f64(amat), T.ptr_i32(self.ia), T.ptr_i32(self.ja), relax)
+
+    def apply(self, r):
+        r = T.as_f64(r)
+        d = np.zeros_like(r)
+        lib().orc_ilu0a(self.h, T.ptr_f64(r), T.ptr_f64(d))
+        return d
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_ilu0_destroy(self.h)
+            self.h = None
+
+
+def amux(ia, ja, a, x):
+    ia, ja, a, x = T.as_i32(ia), T.as_i32(ja), T.as_f64(a), T.as_f64(x)
+    y = np.zeros(ia.size - 1)
+    lib().orc_amux(ia.size - 1, T.ptr_f64(x), T.ptr_f64(y), T.ptr_f64(a), T.ptr_i32(ja), T.ptr_i32(ia))
+    return y
+
+
+class OracleIms:
+    """imslinear_ar + imslinear_ap (ImsLinear.f90:111-339, 617-750)."""
+
+    def __init__(self, ia, ja, settings, perm=None, summary_cap=0):
+        self.ia, self.ja = T.as_i32(ia), T.as_i32(ja)
+        self.n = self.ia.size - 1
+        self.settings = settings
+        self.perm = T.as_i32(perm) if perm is not None else None
+        self.h = lib().orc_ims_create(self.n, self.ja.size, T.ptr_i32(self.ia), T.ptr_i32(self.ja),
+                                      C.byref(settings), T.ptr_i32(self.perm))
+        self.cap = summary_cap
+        if summary_cap:
+            self._arr = dict(itinner=np.zeros(summary_cap, np.int32), dvmax=np.zeros(summary_cap),
+                             rmax=np.zeros(summary_cap), locdv=np.zeros(summary_cap, np.int32),
+                             locr=np.zeros(summary_cap, np.int32), alpha=np.zeros(summary_cap),
+                             omega=np.zeros(summary_cap))
+            a = self._arr
+            self.sum = Summary(summary_cap, 0, T.ptr_i32(a["itinner"]), T.ptr_f64(a["dvmax"]),
+                               T.ptr_f64(a["rmax"]), T.ptr_i32(a["locdv"]), T.ptr_i32(a["locr"]),
+                               T.ptr_f64(a["alpha"]), T.ptr_f64(a["omega"]))
+        else:
+            self.sum = None
+
+    def solve(self, amat, x, rhs, kstp=1, kiter=1):
+        """Solves in place (x updated); returns (innerit, icnvg)."""
+        amat = T.as_f64(amat).copy()
+        rhs = T.as_f64(rhs).copy()
+        assert x.dtype == np.float64 and x.flags.c_contiguous
+        icnvg = C.c_int(0)
+        it = lib().orc_ims_apply(self.h, T.ptr_f64(amat), T.ptr_f64(x), T.ptr_f64(rhs), C.byref(icnvg),
+                                 kstp, kiter, C.byref(self.sum) if self.sum is not None else None)
+        return it, icnvg.value
+
+    def summary(self):
+        c = min(self.sum.count, self.cap)
+        return {k: v[:c].copy() for k, v in self._arr.items()}
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_ims_destroy(self.h)
+            self.h = None
+
+
+class OracleSolution:
+    """NumericalSolution + one GWF model on the CPU."""
+
+    def __init__(self, model, sln, ims, perm=None):
+        self.model = model
+        self._ms = model.struct()
+        self.perm = T.as_i32(perm) if perm is not None else None
+        self.h = lib().orc_sln_create(C.byref(self._ms), C.byref(sln), C.byref(ims), T.ptr_i32(self.perm))
+        self.n = model.nodes
+
+    def set_packages(self, pkgs):
+        arr = package_array(pkgs)
+        lib().orc_sln_set_packages(self.h, len(pkgs), arr)
+
+    def timestep(self, kper=1, kstp=1, delt=1.0, iss=1):
+        rep = T.StepReport()
+        lib().orc_sln_timestep(self.h, kper, kstp, float(delt), int(iss), C.byref(rep))
+        return rep
+
+    def formulate(self, kiter=1, delt=1.0, iss=1):
+        lib().orc_sln_formulate(self.h, kiter, float(delt), int(iss))
+
+    def _view(self, fn, n):
+        p = getattr(lib(), fn)(self.h)
+        return np.ctypeslib.as_array(p, shape=(n,))
+
+    @property
+    def x(self):
+        return self._view("orc_sln_x", self.n)
+
+    @property
+    def flowja(self):
+        return self._view("orc_sln_flowja", self.model.nja)
+
+    @property
+    def amat(self):
+        return self._view("orc_sln_amat", self.model.nja)
+
+    @property
+    def rhs(self):
+        return self._view("orc_sln_rhs", self.n)
+
+    @property
+    def condsat(self):
+        return self._view("orc_sln_condsat", self.model.njas)
+
+    def timers(self):
+        t = np.zeros(2)
+        lib().orc_sln_timers(self.h, T.ptr_f64(t))
+        return t
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_sln_destroy(self.h)
+            self.h = None
