@@ -1,0 +1,149 @@
+/*
+ * mf6gpu.h -- C ABI of libmf6gpu.so: the B200 (sm_100a) implementation of the
+ * MODFLOW 6 per-outer-iteration hot path (GWF formulate + IMS linear solve).
+ *
+ * This is the drop-in boundary.  A Fortran host binds these entry points with
+ * ISO_C_BINDING (see fortran/ and INTEGRATION.md) from three thin types that
+ * extend the reference's own abstract interfaces, exactly the way the PETSc
+ * backend does:
+ *
+ *   GpuMatrixType  extends MatrixBaseType        src/Utilities/Matrix/MatrixBase.f90:9-38
+ *       (pattern: PetscMatrixType, src/Utilities/Matrix/PetscMatrix.F90)
+ *   GpuVectorType  extends VectorBaseType        src/Utilities/Vector/VectorBase.f90:6-20
+ *   GpuSolverType  extends LinearSolverBaseType  src/Solution/LinearSolverBase.f90:17-61
+ *       (pattern: PetscSolverType, src/Solution/PETSc/PetscSolver.F90:82-362)
+ *
+ * and, for the device-resident formulate + outer iteration, from
+ * NumericalSolutionType (src/Solution/NumericalSolution.f90) through the
+ * mf6gpu_solution_* group.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on failure; the message is in
+ *     mf6gpu_last_error().  Non-convergence is NOT an error (cf.
+ *     PetscSolver.F90:346-360).  Nothing throws or exits across the ABI.
+ *   - host arrays are borrowed for the duration of the call; the library owns
+ *     every device buffer.  Structure (ia/ja) is uploaded once at create.
+ *   - index arrays carry their base explicitly (1 = Fortran arrays unchanged).
+ *   - calls are blocking; one handle is used by one host thread at a time.
+ *   - there is NO CPU fallback: without a usable CUDA device every compute
+ *     entry point fails with an error.
+ */
+#ifndef MF6GPU_H
+#define MF6GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "mf6gpu_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MF6GPU_ABI_VERSION 1
+
+typedef struct mf6gpu_matrix mf6gpu_matrix;
+typedef struct mf6gpu_vector mf6gpu_vector;
+typedef struct mf6gpu_solver mf6gpu_solver;
+typedef struct mf6gpu_solution mf6gpu_solution;
+
+/* ---- library ------------------------------------------------------------ */
+int mf6gpu_abi_version(void);
+const char *mf6gpu_last_error(void);
+/* sizeof() of the ABI structs, for binding self-checks: 0 ims_settings,
+ * 1 sln_settings, 2 gwf_model, 3 bnd_package, 4 step_report */
+size_t mf6gpu_sizeof(int which);
+/* select the CUDA device of this process (one process per GPU); -1 keeps the
+ * current device.  Fails if no device is usable. */
+int mf6gpu_init(int device);
+int mf6gpu_device_count(void);
+
+/* ---- MatrixBaseType ------------------------------------------------------
+ * SparseMatrixType%init (SparseMatrix.f90:54-74): CSR pattern, rows stored
+ * diagonal first (Sparse.f90:217-239).  The values live on the device in a
+ * level-sorted SELL-32 layout chosen by `gpu_ordering` (MF6GPU_ORDER_*). */
+int mf6gpu_matrix_create(int32_t n, int32_t nja, const int32_t *ia,
+                         const int32_t *ja, int32_t index_base,
+                         int32_t gpu_ordering, mf6gpu_matrix **out);
+int mf6gpu_matrix_destroy(mf6gpu_matrix *m);
+/* PetscMatrixType%update analogue (PetscMatrix.F90:149-162): push the host
+ * CSR values amat[nja] (original CSR order) to the device. */
+int mf6gpu_matrix_update(mf6gpu_matrix *m, const double *amat);
+/* spm_zero_entries (SparseMatrix.f90:251-260) */
+int mf6gpu_matrix_zero_entries(mf6gpu_matrix *m);
+/* read the device values back in original CSR order (get_aij analogue) */
+int mf6gpu_matrix_get_values(mf6gpu_matrix *m, double *amat);
+/* spm_multiply (SparseMatrix.f90:298-316 -> amux): y = A x, host vectors */
+int mf6gpu_matrix_multiply(mf6gpu_matrix *m, const double *x, double *y);
+/* structure facts: 0 n, 1 nja, 2 number of ILU levels, 3 ordering, 4 SELL slots */
+int64_t mf6gpu_matrix_info(const mf6gpu_matrix *m, int what);
+/* final permutation: perm[new] = old (0-based), length n */
+int mf6gpu_matrix_get_permutation(const mf6gpu_matrix *m, int32_t *perm);
+
+/* ---- VectorBaseType (SeqVector.f90) ---------------------------------------- */
+int mf6gpu_vector_create(int32_t n, mf6gpu_vector **out);
+int mf6gpu_vector_destroy(mf6gpu_vector *v);
+int mf6gpu_vector_set(mf6gpu_vector *v, const double *host);   /* set from host array */
+int mf6gpu_vector_get(const mf6gpu_vector *v, double *host);   /* get_array analogue */
+int mf6gpu_vector_zero_entries(mf6gpu_vector *v);              /* sqv_zero_entries :111-120 */
+int mf6gpu_vector_axpy(mf6gpu_vector *y, double alpha, const mf6gpu_vector *x); /* sqv_axpy :135-148 */
+int mf6gpu_vector_norm2(const mf6gpu_vector *v, double *result);               /* sqv_norm2 :152-164 */
+int mf6gpu_vector_dot(const mf6gpu_vector *a, const mf6gpu_vector *b, double *result); /* ddot */
+
+/* ---- LinearSolverBaseType ------------------------------------------------- */
+/* create_matrix/initialize (LinearSolverBase.f90:31-41): the solver keeps a
+ * reference to `m` (not owned).  summary_capacity = nitermax of
+ * ConvergenceSummaryType (0 = do not record per-iteration data). */
+int mf6gpu_solver_create(mf6gpu_matrix *m, const mf6gpu_ims_settings *settings,
+                         int32_t summary_capacity, mf6gpu_solver **out);
+int mf6gpu_solver_destroy(mf6gpu_solver *s);
+/* solve (LinearSolverBase.f90:43-51) == imslinear_ap (ImsLinear.f90:617-750)
+ * on the device: scale, ILU0/MILU0 factorisation (with the pivot rescue loop),
+ * residual, CG or BiCGSTAB with the IMS stopping rules.  rhs/x are host arrays
+ * of length n in ORIGINAL ordering; x is updated in place.
+ * Outputs: iteration_number (inner iterations), is_converged (ICNVG: 1/0). */
+int mf6gpu_solver_solve(mf6gpu_solver *s, int32_t kiter, int32_t kstp,
+                        const double *rhs, double *x, int32_t *iteration_number,
+                        int32_t *is_converged);
+/* ConvergenceSummaryType side channel: copies min(count, cap) records of the
+ * current time step; loc* are 1-based solution rows (original ordering).
+ * Any output pointer may be NULL.  Returns the number of records. */
+int mf6gpu_solver_get_summary(mf6gpu_solver *s, int32_t cap, int32_t *itinner,
+                              double *dvmax, int32_t *locdv, double *rmax,
+                              int32_t *locr, double *alpha, double *omega);
+/* facts of the last solve: 0 l2norm0, 1 pivot corrections, 2 device seconds in
+ * factorisation, 3 device seconds in the Krylov loop, 4 kernel launches */
+double mf6gpu_solver_stat(const mf6gpu_solver *s, int what);
+/* preconditioner pieces exposed for parity tests (pcu + ilu0a):
+ * factor the current matrix values, apply M^-1 to a host vector */
+int mf6gpu_solver_factor(mf6gpu_solver *s, int32_t *npivot_fixes);
+int mf6gpu_solver_apply_preconditioner(mf6gpu_solver *s, const double *r, double *z);
+
+/* ---- NumericalSolutionType + GWF formulate, device resident --------------- */
+int mf6gpu_solution_create(const mf6gpu_gwf_model *model,
+                           const mf6gpu_sln_settings *sln,
+                           const mf6gpu_ims_settings *ims,
+                           mf6gpu_solution **out);
+int mf6gpu_solution_destroy(mf6gpu_solution *s);
+/* bnd_rp: stress-period data of every package (copied to the device) */
+int mf6gpu_solution_set_packages(mf6gpu_solution *s, int32_t npkg,
+                                 const mf6gpu_bnd_package *pk);
+/* sln_ca: prepareSolve + outer loop of solve(kiter) + finalizeSolve for one
+ * time step (NumericalSolution.f90:1287-1327) */
+int mf6gpu_solution_timestep(mf6gpu_solution *s, int32_t kper, int32_t kstp,
+                             double delt, int32_t iss, mf6gpu_step_report *rep);
+/* sln_buildsystem + the pre-solve fix-ups of sln_ls, no linear solve */
+int mf6gpu_solution_formulate(mf6gpu_solution *s, int32_t kiter, double delt,
+                              int32_t iss);
+int mf6gpu_solution_get_x(mf6gpu_solution *s, double *x);        /* heads, original order */
+int mf6gpu_solution_set_x(mf6gpu_solution *s, const double *x);
+int mf6gpu_solution_get_amat(mf6gpu_solution *s, double *amat);  /* CSR order */
+int mf6gpu_solution_get_rhs(mf6gpu_solution *s, double *rhs);
+int mf6gpu_solution_get_flowja(mf6gpu_solution *s, double *flowja);
+int mf6gpu_solution_get_condsat(mf6gpu_solution *s, double *condsat);
+/* the linear solver owned by the solution (for stats / summary) */
+mf6gpu_solver *mf6gpu_solution_solver(mf6gpu_solution *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

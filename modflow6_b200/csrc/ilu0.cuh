@@ -1,0 +1,13 @@
+// ilu0.cuh -- level-scheduled ILU0/MILU0 (see ilu0.cu)
+#pragma once
+#include "matrix.cuh"
+
+namespace mf6 {
+// one numeric factorisation pass with fixed (delta, ipcflag); *d_failflag is set
+// to 1 by any row whose pivot fails the reference's checks.  Returns launches.
+int ilu0_factor(const mf6gpu_matrix &A, const double *aval, double *lu, double relax,
+                double delta, int ipcflag, int *d_failflag, cudaStream_t s);
+// d = (LU)^-1 rin.  `done` (device flag, may be null) turns the kernels into no-ops.
+int ilu0_apply(const mf6gpu_matrix &A, const double *lu, const double *rin, double *d,
+               const int *done, cudaStream_t s);
+}  // namespace mf6

@@ -1,0 +1,322 @@
+// matrix.cu -- build of the level-sorted SELL-32 system matrix, value upload /
+// download, SpMV (amux) and permutation kernels.
+//
+// Reference behaviour restated here:
+//   SparseMatrixType   src/Utilities/Matrix/SparseMatrix.f90:54-74, 251-260, 298-316
+//   amux               src/Utilities/Libraries/sparsekit/sparsekit.f90:1-59
+//   PetscMatrixType%update (host CSR -> backend)  src/Utilities/Matrix/PetscMatrix.F90:149-162
+#include "matrix.cuh"
+#include "spmv.cuh"
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+namespace mf6 {
+
+std::string &last_error() {
+  static thread_local std::string e;
+  return e;
+}
+
+// ---------------------------------------------------------------- kernels ---
+// y = A x : one thread per row, slots read slice-coalesced.  Loads of a chunk
+// of 8 slots are issued before any use so that each thread keeps up to 24
+// independent loads in flight; the accumulation keeps the row's storage order
+// (diagonal, then ascending) so the result is bit-identical to amux.
+__global__ void __launch_bounds__(kBlock)
+spmv_sell32_kernel(int n, const int *__restrict__ slice_ptr,
+                   const unsigned char *__restrict__ rowlen,
+                   const int *__restrict__ col, const double *__restrict__ val,
+                   const double *__restrict__ x, double *__restrict__ y) {
+  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n;
+       row += gridDim.x * blockDim.x) {
+    const double t = sell_row_dot(row, slice_ptr, rowlen, col, val, x);
+    y[row] = t;
+  }
+}
+
+__global__ void gather_kernel(int n, const int *__restrict__ perm,
+                              const double *__restrict__ in, double *__restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    out[i] = in[perm[i]];
+}
+
+__global__ void scatter_kernel(int n, const int *__restrict__ perm,
+                               const double *__restrict__ in, double *__restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    out[perm[i]] = in[i];
+}
+
+// sell[csr2sell[p]] = csr[p]
+__global__ void csr_to_sell_kernel(int nja, const int *__restrict__ map,
+                                   const double *__restrict__ csr, double *__restrict__ sell) {
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nja; p += gridDim.x * blockDim.x)
+    sell[map[p]] = csr[p];
+}
+
+__global__ void sell_to_csr_kernel(int nja, const int *__restrict__ map,
+                                   const double *__restrict__ sell, double *__restrict__ csr) {
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nja; p += gridDim.x * blockDim.x)
+    csr[p] = sell[map[p]];
+}
+
+void launch_spmv(const mf6gpu_matrix &A, const double *val, const double *x, double *y,
+                 cudaStream_t s) {
+  spmv_sell32_kernel<<<grid_for(A.n), kBlock, 0, s>>>(A.n, A.slice_ptr.p, A.rowlen.p, A.col.p,
+                                                      val, x, y);
+}
+
+void launch_gather(int n, const int *perm, const double *in, double *out, cudaStream_t s) {
+  gather_kernel<<<grid_for(n), kBlock, 0, s>>>(n, perm, in, out);
+}
+
+void launch_scatter(int n, const int *perm, const double *in, double *out, cudaStream_t s) {
+  scatter_kernel<<<grid_for(n), kBlock, 0, s>>>(n, perm, in, out);
+}
+
+// ------------------------------------------------------------- host build ---
+static void build_matrix(mf6gpu_matrix &M, int n, int nja, const int32_t *ia_in,
+                         const int32_t *ja_in, int base, int ordering) {
+  MF6_REQUIRE(n > 0 && nja >= n, "matrix_create: bad dimensions");
+  MF6_REQUIRE(ordering == MF6GPU_ORDER_NATURAL || ordering == MF6GPU_ORDER_MULTICOLOR,
+              "matrix_create: unknown gpu_ordering");
+  M.n = n;
+  M.nja = nja;
+  M.ordering = ordering;
+  std::vector<int> ia(n + 1), ja(nja);
+  for (int i = 0; i <= n; i++) ia[i] = ia_in[i] - base;
+  for (int i = 0; i < nja; i++) ja[i] = ja_in[i] - base;
+  MF6_REQUIRE(ia[0] == 0 && ia[n] == nja, "matrix_create: ia does not span nja (check index_base)");
+  for (int r = 0; r < n; r++) {
+    MF6_REQUIRE(ia[r + 1] > ia[r], "matrix_create: empty row");
+    MF6_REQUIRE(ja[ia[r]] == r, "matrix_create: rows must store the diagonal first (Sparse.f90:217-239)");
+    MF6_REQUIRE(ia[r + 1] - ia[r] <= 255, "matrix_create: more than 255 entries in a row");
+  }
+  // --- elimination order (ordidx[old] = position in the reference-style loop)
+  std::vector<int> ordidx(n);
+  if (ordering == MF6GPU_ORDER_NATURAL) {
+    std::iota(ordidx.begin(), ordidx.end(), 0);
+  } else {
+    // greedy colouring in natural order
+    std::vector<int> color(n, -1);
+    int ncolors = 0;
+    std::vector<unsigned long long> forb;
+    for (int v = 0; v < n; v++) {
+      unsigned long long mask = 0ull;
+      bool big = false;
+      for (int p = ia[v] + 1; p < ia[v + 1]; p++) {
+        int c = color[ja[p]];
+        if (c >= 64) big = true;
+        else if (c >= 0) mask |= (1ull << c);
+      }
+      int c = 0;
+      if (!big) {
+        while (c < 64 && (mask >> c) & 1ull) c++;
+      }
+      if (big || c == 64) {  // rare: fall back to an explicit set
+        std::vector<char> used(ncolors + 2, 0);
+        for (int p = ia[v] + 1; p < ia[v + 1]; p++)
+          if (color[ja[p]] >= 0) used[color[ja[p]]] = 1;
+        c = 0;
+        while (used[c]) c++;
+      }
+      color[v] = c;
+      if (c + 1 > ncolors) ncolors = c + 1;
+    }
+    std::vector<int> cnt(ncolors + 1, 0);
+    for (int v = 0; v < n; v++) cnt[color[v] + 1]++;
+    for (int c = 0; c < ncolors; c++) cnt[c + 1] += cnt[c];
+    for (int v = 0; v < n; v++) ordidx[v] = cnt[color[v]]++;
+  }
+  std::vector<int> byord(n);  // byord[ord] = old
+  for (int v = 0; v < n; v++) byord[ordidx[v]] = v;
+  // --- dependency levels of the lower-triangular solve in that order
+  std::vector<int> level(n, 0);
+  int nlevels = 0;
+  for (int o = 0; o < n; o++) {
+    int v = byord[o];
+    int lv = 0;
+    for (int p = ia[v] + 1; p < ia[v + 1]; p++) {
+      int u = ja[p];
+      if (ordidx[u] < o && level[u] + 1 > lv) lv = level[u] + 1;
+    }
+    level[v] = lv;
+    if (lv + 1 > nlevels) nlevels = lv + 1;
+  }
+  M.nlevels = nlevels;
+  // --- final numbering: stable sort by (level, ordidx)
+  M.level_ptr.assign(nlevels + 1, 0);
+  for (int v = 0; v < n; v++) M.level_ptr[level[v] + 1]++;
+  for (int l = 0; l < nlevels; l++) M.level_ptr[l + 1] += M.level_ptr[l];
+  M.perm.resize(n);
+  M.iperm.resize(n);
+  {
+    std::vector<int> cur(M.level_ptr.begin(), M.level_ptr.end() - 1);
+    for (int o = 0; o < n; o++) {
+      int v = byord[o];
+      int r = cur[level[v]]++;
+      M.perm[r] = v;
+      M.iperm[v] = r;
+    }
+  }
+  // --- SELL-32 structure
+  M.nslices = (n + 31) / 32;
+  std::vector<unsigned char> rowlen(n), nlow(n);
+  std::vector<int> slice_ptr(M.nslices + 1, 0);
+  int maxlen = 0;
+  for (int s = 0; s < M.nslices; s++) {
+    int w = 0;
+    for (int r = s * 32; r < std::min(n, s * 32 + 32); r++) {
+      int v = M.perm[r];
+      int len = ia[v + 1] - ia[v];
+      rowlen[r] = (unsigned char)len;
+      if (len > w) w = len;
+    }
+    long long next = (long long)slice_ptr[s] + 32LL * w;
+    MF6_REQUIRE(next < (long long)INT_MAX, "matrix_create: SELL storage exceeds 2^31 slots");
+    slice_ptr[s + 1] = (int)next;
+    if (w > maxlen) maxlen = w;
+  }
+  M.maxlen = maxlen;
+  M.nslots = slice_ptr[M.nslices];
+  std::vector<int> col((size_t)M.nslots);
+  std::vector<int> csr2sell(nja);
+  std::vector<std::pair<int, int>> tmp;  // (ordidx(col), csr position)
+  for (int r = 0; r < n; r++) {
+    int v = M.perm[r];
+    long long base_slot = (long long)slice_ptr[r >> 5] + (r & 31);
+    int w = (slice_ptr[(r >> 5) + 1] - slice_ptr[r >> 5]) / 32;
+    tmp.clear();
+    for (int p = ia[v] + 1; p < ia[v + 1]; p++) tmp.emplace_back(ordidx[ja[p]], p);
+    std::sort(tmp.begin(), tmp.end());
+    col[base_slot] = r;
+    csr2sell[ia[v]] = (int)base_slot;
+    int lo = 0;
+    for (size_t k = 0; k < tmp.size(); k++) {
+      int p = tmp[k].second;
+      long long slot = base_slot + 32LL * (long long)(k + 1);
+      col[slot] = M.iperm[ja[p]];
+      csr2sell[p] = (int)slot;
+      if (tmp[k].first < ordidx[v]) lo++;
+      MF6_REQUIRE(ja[p] != v, "matrix_create: duplicate diagonal entry");
+      if (k > 0) MF6_REQUIRE(tmp[k].first != tmp[k - 1].first, "matrix_create: duplicate column in a row");
+    }
+    nlow[r] = (unsigned char)lo;
+    for (int k = (int)tmp.size() + 1; k < w; k++) col[base_slot + 32LL * k] = r;  // padding
+  }
+  // padding lanes of the last slice
+  for (int r = n; r < M.nslices * 32; r++) {
+    long long base_slot = (long long)slice_ptr[r >> 5] + (r & 31);
+    int w = (slice_ptr[(r >> 5) + 1] - slice_ptr[r >> 5]) / 32;
+    for (int k = 0; k < w; k++) col[base_slot + 32LL * k] = 0;
+  }
+  // --- upload
+  M.d_perm.upload(M.perm);
+  M.d_iperm.upload(M.iperm);
+  if (ordering == MF6GPU_ORDER_NATURAL && nlevels > 1) {
+    M.d_ord.upload(M.perm);  // elimination index of final row r is its original index
+  }
+  M.slice_ptr.upload(slice_ptr);
+  M.col.upload(col);
+  M.rowlen.upload(rowlen);
+  M.nlow.upload(nlow);
+  M.csr2sell.upload(csr2sell);
+  M.val.alloc_zero((size_t)M.nslots);
+  M.stage.alloc((size_t)nja);
+  M.xs.alloc((size_t)n);
+  M.ys.alloc((size_t)n);
+}
+
+}  // namespace mf6
+
+using namespace mf6;
+
+extern "C" {
+
+int mf6gpu_matrix_create(int32_t n, int32_t nja, const int32_t *ia, const int32_t *ja,
+                         int32_t index_base, int32_t gpu_ordering, mf6gpu_matrix **out) {
+  return guard([&] {
+    MF6_REQUIRE(out && ia && ja, "matrix_create: null argument");
+    int dev;
+    MF6_CK(cudaGetDevice(&dev));
+    auto *M = new mf6gpu_matrix();
+    try {
+      build_matrix(*M, n, nja, ia, ja, index_base, gpu_ordering);
+    } catch (...) {
+      delete M;
+      throw;
+    }
+    *out = M;
+  });
+}
+
+int mf6gpu_matrix_destroy(mf6gpu_matrix *m) {
+  return guard([&] { delete m; });
+}
+
+int mf6gpu_matrix_update(mf6gpu_matrix *m, const double *amat) {
+  return guard([&] {
+    MF6_REQUIRE(m && amat, "matrix_update: null argument");
+    MF6_CK(cudaMemcpyAsync(m->stage.p, amat, sizeof(double) * (size_t)m->nja,
+                           cudaMemcpyHostToDevice, m->stream));
+    csr_to_sell_kernel<<<grid_for(m->nja), kBlock, 0, m->stream>>>(m->nja, m->csr2sell.p,
+                                                                   m->stage.p, m->val.p);
+    MF6_CK(cudaGetLastError());
+    MF6_CK(cudaStreamSynchronize(m->stream));
+  });
+}
+
+int mf6gpu_matrix_zero_entries(mf6gpu_matrix *m) {
+  return guard([&] {
+    MF6_REQUIRE(m, "matrix_zero_entries: null argument");
+    m->val.zero(m->stream);
+    MF6_CK(cudaStreamSynchronize(m->stream));
+  });
+}
+
+int mf6gpu_matrix_get_values(mf6gpu_matrix *m, double *amat) {
+  return guard([&] {
+    MF6_REQUIRE(m && amat, "matrix_get_values: null argument");
+    sell_to_csr_kernel<<<grid_for(m->nja), kBlock, 0, m->stream>>>(m->nja, m->csr2sell.p,
+                                                                   m->val.p, m->stage.p);
+    MF6_CK(cudaGetLastError());
+    m->stage.download(amat, (size_t)m->nja, m->stream);
+  });
+}
+
+int mf6gpu_matrix_multiply(mf6gpu_matrix *m, const double *x, double *y) {
+  return guard([&] {
+    MF6_REQUIRE(m && x && y, "matrix_multiply: null argument");
+    // stage in original order, permute, multiply, permute back
+    mf6::DevBuf<double> tmp;
+    tmp.alloc((size_t)m->n);
+    MF6_CK(cudaMemcpyAsync(tmp.p, x, sizeof(double) * (size_t)m->n, cudaMemcpyHostToDevice, m->stream));
+    launch_gather(m->n, m->d_perm.p, tmp.p, m->xs.p, m->stream);
+    launch_spmv(*m, m->val.p, m->xs.p, m->ys.p, m->stream);
+    launch_scatter(m->n, m->d_perm.p, m->ys.p, tmp.p, m->stream);
+    MF6_CK(cudaGetLastError());
+    tmp.download(y, (size_t)m->n, m->stream);
+  });
+}
+
+int64_t mf6gpu_matrix_info(const mf6gpu_matrix *m, int what) {
+  if (!m) return -1;
+  switch (what) {
+    case 0: return m->n;
+    case 1: return m->nja;
+    case 2: return m->nlevels;
+    case 3: return m->ordering;
+    case 4: return m->nslots;
+    case 5: return m->maxlen;
+  }
+  return -1;
+}
+
+int mf6gpu_matrix_get_permutation(const mf6gpu_matrix *m, int32_t *perm) {
+  return guard([&] {
+    MF6_REQUIRE(m && perm, "matrix_get_permutation: null argument");
+    std::memcpy(perm, m->perm.data(), sizeof(int) * (size_t)m->n);
+  });
+}
+
+}  // extern "C"

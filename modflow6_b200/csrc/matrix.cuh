@@ -1,0 +1,51 @@
+// matrix.cuh -- device-resident system matrix (MatrixBaseType replacement).
+//
+// HBM layout (all arrays in the FINAL numbering = rows sorted by ILU level):
+//   SELL-32: rows are grouped in slices of 32 consecutive rows; slot k of row r
+//   lives at  slice_ptr[r>>5] + 32*k + (r&31)  so that the 32 lanes of a warp
+//   read 256 contiguous bytes of `val` and 128 of `col` per slot.
+//   Slot 0 is the diagonal; slots 1..nlow are the lower (earlier-eliminated)
+//   neighbours, slots nlow+1..rowlen-1 the upper ones, each group ascending in
+//   the reference's elimination order so that per-row arithmetic is performed
+//   in exactly the order of amux / ims_base_pcilu0 / ims_base_ilu0a.
+//   The ILU0/MILU0 factor shares slice_ptr/col/rowlen/nlow and only adds a
+//   second value array (slot 0 = inverse pivot = APC(n)).
+#pragma once
+#include "common.cuh"
+#include "../../include/mf6gpu.h"
+
+struct mf6gpu_matrix {
+  int n = 0, nja = 0;
+  int ordering = 0;
+  int nlevels = 0;
+  int nslices = 0;
+  long long nslots = 0;
+  int maxlen = 0;
+  std::vector<int> perm;       // perm[new] = old
+  std::vector<int> iperm;      // iperm[old] = new
+  std::vector<int> level_ptr;  // [nlevels+1] row ranges in final numbering
+  mf6::DevBuf<int> d_perm, d_iperm;
+  mf6::DevBuf<int> d_ord;      // elimination-order index of each final row (tie-breaks); empty => identity
+  mf6::DevBuf<int> slice_ptr;  // [nslices+1]
+  mf6::DevBuf<int> col;        // [nslots]
+  mf6::DevBuf<double> val;     // [nslots]
+  mf6::DevBuf<unsigned char> rowlen, nlow;  // [n]
+  mf6::DevBuf<int> csr2sell;   // [nja] slot of each original CSR entry
+  mf6::DevBuf<double> stage;   // [nja] H2D/D2H staging of CSR values
+  mf6::DevBuf<double> xs, ys;  // [n] staging vectors for host multiply
+  cudaStream_t stream = 0;
+  const int *ord_ptr() const { return d_ord.n ? d_ord.p : nullptr; }
+};
+
+namespace mf6 {
+
+// y = A x (device vectors in final numbering); optional fused dot partial:
+// if dot_with != nullptr accumulates sum_r dot_with[r]*y[r] into partial[blockIdx]
+void launch_spmv(const mf6gpu_matrix &A, const double *val, const double *x, double *y,
+                 cudaStream_t s);
+// out[new] = in[perm[new]]
+void launch_gather(int n, const int *perm, const double *in, double *out, cudaStream_t s);
+// out[perm[new]] = in[new]
+void launch_scatter(int n, const int *perm, const double *in, double *out, cudaStream_t s);
+
+}  // namespace mf6

@@ -1,0 +1,747 @@
+// solver.cu -- device-resident IMS linear accelerators: PCG and BiCGSTAB with
+// ILU0/MILU0, the IMS stopping rules and the ConvergenceSummary side channel.
+//
+// Restates on the device:
+//   imslinear_ap       src/Solution/LinearMethods/ImsLinear.f90:617-750
+//   ims_base_cg        src/Solution/LinearMethods/ImsLinearBase.f90:30-240
+//   ims_base_bcgs      :249-549        ims_base_pcu      :761-864
+//   ims_base_testcnvg  :1101-1146      ims_base_residual :1291-1312
+//   ims_base_epfact    :1316-1333      ddot / dnrm2  blas1_d.f90:295-333, 387-480
+//   is_close           src/Utilities/MathUtil.f90:45-86
+//
+// The inner loop never synchronises with the host: the recurrence scalars
+// (rho, alpha, beta, omega), the reductions and the convergence decision live
+// in a KState block in HBM; every kernel is a no-op once KState::done is set
+// and the host polls that flag every few iterations.
+// Reductions are deterministic: per-CTA partials in fixed slots, combined in a
+// fixed order by the last CTA to finish (threadfence + ticket).
+#include "solver.cuh"
+#include "spmv.cuh"
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+namespace mf6 {
+
+enum { TK_DOT = 0, TK_SPMV = 1, TK_UPD = 2, TK_NRM = 3 };
+// finalisation modes of the reduction kernels
+enum {
+  FIN_CG_RHO = 0,     // rho = sum ; beta = rho / rho0
+  FIN_CG_ALPHA = 1,   // den = sum + sign(eps) ; alpha = rho / den
+  FIN_BCGS_RHO = 2,   // rho = sum ; beta = (rho/rho0)(alpha0/omega0)
+  FIN_BCGS_ALPHA = 3, // alpha = rho / (sum + sign(eps))
+  FIN_BCGS_OMEGA = 4, // omega = s0 / (s1 + sign(eps))
+  FIN_NRM_MAX = 5,    // scale = max |d|
+  FIN_NRM_SSQ = 6,    // l2norm0 = scale * sqrt(sum (d/scale)^2)
+  FIN_PLAIN = 7       // out = sum
+};
+
+__device__ __forceinline__ double dsign(double a, double b) { return copysign(fabs(a), b); }
+
+__device__ __forceinline__ bool is_close_dev(double a, double b) {
+  if (a == b) return true;
+  const double m = fmax(fabs(a), fabs(b));
+  return fabs(a - b) <= fmax(100.0 * DBL_EPSILON * m, 0.0);
+}
+
+// ims_base_testcnvg, ImsLinearBase.f90:1101-1146
+__device__ __forceinline__ void testcnvg_dev(int opt, int &icnvg, int iiter, double dvmax,
+                                             double rmax, double rmax0, double epfact,
+                                             double dvclose, double rclose) {
+  if (opt == 0) {
+    if (fabs(dvmax) <= dvclose && fabs(rmax) <= rclose) icnvg = 1;
+  } else if (opt == 1) {
+    if (fabs(dvmax) <= dvclose && fabs(rmax) <= rclose) icnvg = (iiter == 1) ? 1 : -1;
+  } else if (opt == 2) {
+    if (fabs(dvmax) <= dvclose || rmax <= rclose)
+      icnvg = 1;
+    else if (rmax <= rmax0 * epfact)
+      icnvg = -1;
+  } else if (opt == 3) {
+    if (fabs(dvmax) <= dvclose)
+      icnvg = 1;
+    else if (rmax <= rmax0 * rclose)
+      icnvg = -1;
+  } else if (opt == 4) {
+    if (fabs(dvmax) <= dvclose && rmax <= rclose)
+      icnvg = 1;
+    else if (rmax <= rmax0 * epfact)
+      icnvg = -1;
+  }
+}
+
+// scalar epilogue of a sum reduction, executed by one thread
+__device__ void finalize_sum(int mode, double s0, double s1, KState *st, double *out) {
+  switch (mode) {
+    case FIN_CG_RHO:
+      st->rho = s0;
+      st->beta = s0 / st->rho0;  // unused on the first iteration
+      break;
+    case FIN_CG_ALPHA: {
+      double den = s0;
+      den = den + dsign(DBL_EPSILON, den);
+      st->alpha = st->rho / den;
+      break;
+    }
+    case FIN_BCGS_RHO:
+      st->rho = s0;
+      st->beta = (s0 / st->rho0) * (st->alpha0 / st->omega0);
+      break;
+    case FIN_BCGS_ALPHA: {
+      double den = s0;
+      den = den + dsign(DBL_EPSILON, den);
+      st->alpha = st->rho / den;
+      break;
+    }
+    case FIN_BCGS_OMEGA: {
+      double den = s1;
+      den = den + dsign(DBL_EPSILON, den);
+      st->omega = s0 / den;
+      break;
+    }
+    case FIN_NRM_MAX:
+      *out = s0;
+      break;
+    case FIN_NRM_SSQ: {
+      const double scale = out[0];
+      st->l2norm0 = (scale == 0.0) ? 0.0 : scale * sqrt(s0);
+      break;
+    }
+    default:
+      *out = s0;
+  }
+}
+
+// combine per-CTA partial sums (1 or 2 interleaved sums) in a fixed order
+template <int NS>
+__device__ __forceinline__ void reduce_partials_and_finalize(int mode, const double *partial,
+                                                             KState *st, double *out, double *sh) {
+  double a0 = 0.0, a1 = 0.0;
+  for (int i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+    a0 += partial[NS * i];
+    if (NS == 2) a1 += partial[NS * i + 1];
+  }
+  a0 = block_sum(a0, sh);
+  if (NS == 2) a1 = block_sum(a1, sh);
+  if (threadIdx.x == 0) finalize_sum(mode, a0, a1, st, out);
+}
+
+// ---- dot product (ddot) ------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+dot_kernel(int n, const double *__restrict__ a, const double *__restrict__ b,
+           double *__restrict__ partial, unsigned int *ticket, KState *st, int mode,
+           double *out, int check_done) {
+  __shared__ double sh[8];
+  __shared__ bool last;
+  if (check_done && st->done) return;
+  double s = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    s += a[i] * b[i];
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+  if (last_block(ticket, &last)) reduce_partials_and_finalize<1>(mode, partial, st, out, sh);
+}
+
+// ---- dnrm2 in two passes (max |d|, then sum (d/scale)^2) ---------------------
+__global__ void __launch_bounds__(kBlock)
+nrm_max_kernel(int n, const double *__restrict__ a, double *__restrict__ partial,
+               unsigned int *ticket, double *out) {
+  __shared__ double sh[8];
+  __shared__ bool last;
+  double m = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    m = fmax(m, fabs(a[i]));
+  m = block_max(m, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = m;
+  if (last_block(ticket, &last)) {
+    double r = 0.0;
+    for (int i = threadIdx.x; i < gridDim.x; i += blockDim.x) r = fmax(r, partial[i]);
+    r = block_max(r, sh);
+    if (threadIdx.x == 0) *out = r;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock)
+nrm_ssq_kernel(int n, const double *__restrict__ a, double *__restrict__ partial,
+               unsigned int *ticket, KState *st, double *scale_io) {
+  __shared__ double sh[8];
+  __shared__ bool last;
+  const double scale = *scale_io;
+  double s = 0.0;
+  if (scale > 0.0)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      const double r = fabs(a[i]) / scale;
+      s += r * r;
+    }
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+  if (last_block(ticket, &last))
+    reduce_partials_and_finalize<1>(FIN_NRM_SSQ, partial, st, scale_io, sh);
+}
+
+// ---- y = A x (+ fused dot products with the freshly computed y) --------------
+// EPI 0: y = A x ; EPI 1: y = b - A x (ims_base_residual)
+// NDOT 0: none ; 1: sum w[row]*y[row] ; 2: sum w[row]*y[row] and sum y[row]^2
+template <int EPI, int NDOT>
+__global__ void __launch_bounds__(kBlock)
+spmv_fused_kernel(int n, const int *__restrict__ slice_ptr,
+                  const unsigned char *__restrict__ rowlen, const int *__restrict__ col,
+                  const double *__restrict__ val, const double *__restrict__ x,
+                  double *__restrict__ y, const double *__restrict__ b,
+                  const double *__restrict__ w, double *__restrict__ partial,
+                  unsigned int *ticket, KState *st, int mode, int check_done) {
+  __shared__ double sh[8];
+  __shared__ bool last;
+  if (check_done && st->done) return;
+  double s0 = 0.0, s1 = 0.0;
+  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
+    double t = sell_row_dot(row, slice_ptr, rowlen, col, val, x);
+    if (EPI == 1) t = b[row] - t;
+    y[row] = t;
+    if (NDOT >= 1) s0 += w[row] * t;
+    if (NDOT == 2) s1 += t * t;
+  }
+  if (NDOT >= 1) {
+    s0 = block_sum(s0, sh);
+    if (NDOT == 2) s1 = block_sum(s1, sh);
+    if (threadIdx.x == 0) {
+      partial[NDOT * blockIdx.x] = s0;
+      if (NDOT == 2) partial[NDOT * blockIdx.x + 1] = s1;
+    }
+    if (last_block(ticket, &last))
+      reduce_partials_and_finalize<(NDOT == 2 ? 2 : 1)>(mode, partial, st, nullptr, sh);
+  }
+}
+
+// ---- vector updates -----------------------------------------------------------
+// CG: P = Z (first) | P = Z + beta P                     ImsLinearBase.f90:118-127
+__global__ void __launch_bounds__(kBlock)
+cg_p_kernel(int n, const double *__restrict__ z, double *__restrict__ p, const KState *st,
+            int first) {
+  if (st->done) return;
+  const double beta = st->beta;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    p[i] = first ? z[i] : z[i] + beta * p[i];
+}
+
+// BCGS: P = D (first) | P = D + beta (P - omega0 V)      ImsLinearBase.f90:346-355
+__global__ void __launch_bounds__(kBlock)
+bcgs_p_kernel(int n, const double *__restrict__ d, const double *__restrict__ v,
+              double *__restrict__ p, const KState *st, int first) {
+  if (st->done) return;
+  const double beta = st->beta, omega0 = st->omega0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    p[i] = first ? d[i] : d[i] + beta * (p[i] - omega0 * v[i]);
+}
+
+// BCGS: Q = D - alpha V                                   ImsLinearBase.f90:380-382
+__global__ void __launch_bounds__(kBlock)
+bcgs_q_kernel(int n, const double *__restrict__ d, const double *__restrict__ v,
+              double *__restrict__ q, const KState *st) {
+  if (st->done) return;
+  const double alpha = st->alpha;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    q[i] = d[i] - alpha * v[i];
+}
+
+struct SummaryPtrs {
+  int *itinner, *locdv, *locr;
+  double *dvmax, *rmax, *alpha, *omega;
+};
+
+// scalar tail of one inner iteration: everything between the update loop and
+// "SAVE CURRENT INNER ITERATES" (ImsLinearBase.f90:183-235 / 480-544)
+__device__ void finalize_iteration(KState *st, double ssq, MaxLoc mx, MaxLoc mr, int bcgs,
+                                   SummaryPtrs sp) {
+  const double l2norm = sqrt(ssq);
+  st->deltax = mx.v;
+  st->rmax = mr.v;
+  st->l2norm = l2norm;
+  st->xloc = mx.idx;
+  st->rloc = mr.idx;
+  st->iter += 1;
+  st->sum_count += 1;
+  const int k = st->sum_count - 1;
+  if (k < st->sum_cap) {
+    sp.itinner[k] = st->iter;
+    sp.dvmax[k] = mx.v;
+    sp.locdv[k] = mx.idx;
+    sp.rmax[k] = mr.v;
+    sp.locr[k] = mr.idx;
+    sp.alpha[k] = st->alpha;
+    sp.omega[k] = bcgs ? st->omega : 0.0;
+  }
+  const int opt = st->icnvgopt;
+  const double rcnvg = (opt == 2 || opt == 3 || opt == 4) ? l2norm : mr.v;
+  int icnvg = st->icnvg;
+  testcnvg_dev(opt, icnvg, st->iter, mx.v, rcnvg, st->l2norm0, st->epfact, st->dvclose,
+               st->rclose);
+  if (rcnvg == 0.0) icnvg = 1;
+  st->icnvg = icnvg;
+  int done = 0;
+  if (icnvg != 0) done = 1;
+  if (!done && is_close_dev(st->rho, st->rho0)) done = 1;
+  if (bcgs) {
+    if (!done && is_close_dev(st->alpha, st->alpha0)) done = 1;
+    if (!done && is_close_dev(st->omega, st->omega0)) done = 1;
+    if (!done && st->rho * st->omega == 0.0) done = 1;
+  } else {
+    if (!done && st->rho == 0.0) done = 1;
+  }
+  if (!done) {
+    st->rho0 = st->rho;
+    st->alpha0 = st->alpha;
+    st->omega0 = st->omega;
+  }
+  st->done = done;
+}
+
+// CG: X += alpha P ; D -= alpha Q ; max|alpha P|, max|D|, sum D^2   :137-183
+// BCGS: X += alpha PHAT + omega QHAT ; D = Q - omega T ; same reductions :429-480
+template <int BCGS>
+__global__ void __launch_bounds__(kBlock)
+update_kernel(int n, double *__restrict__ x, double *__restrict__ d,
+              const double *__restrict__ p, const double *__restrict__ q,
+              const double *__restrict__ qhat, const double *__restrict__ t,
+              const double *__restrict__ dscale, const int *__restrict__ ord,
+              double *__restrict__ partial, MaxLoc *__restrict__ pmx, MaxLoc *__restrict__ pmr,
+              unsigned int *ticket, KState *st, SummaryPtrs sp) {
+  __shared__ double sh[8];
+  __shared__ MaxLoc shm[8];
+  __shared__ bool last;
+  if (st->done) return;
+  const double alpha = st->alpha, omega = st->omega;
+  const int iscl = st->iscl;
+  double ssq = 0.0;
+  MaxLoc mx = maxloc_init(), mr = maxloc_init();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double tv, rv;
+    if (BCGS) {
+      tv = alpha * p[i] + omega * qhat[i];  // p = PHAT here
+      x[i] = x[i] + tv;
+      if (iscl != 0) tv = tv * dscale[i];
+      rv = q[i] - omega * t[i];
+      d[i] = rv;
+      if (iscl != 0) rv = rv / dscale[i];
+    } else {
+      tv = alpha * p[i];
+      x[i] = x[i] + tv;
+      rv = d[i];
+      rv = rv - alpha * q[i];
+      d[i] = rv;
+    }
+    const double atv = fabs(tv), arv = fabs(rv);
+    if (atv >= mx.a && atv > 0.0) maxloc_take(mx, tv, ord ? ord[i] : i, i);
+    if (arv >= mr.a && arv > 0.0) maxloc_take(mr, rv, ord ? ord[i] : i, i);
+    ssq += rv * rv;
+  }
+  ssq = block_sum(ssq, sh);
+  mx = block_maxloc(mx, shm);
+  mr = block_maxloc(mr, shm);
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = ssq;
+    pmx[blockIdx.x] = mx;
+    pmr[blockIdx.x] = mr;
+  }
+  if (last_block(ticket, &last)) {
+    double a = 0.0;
+    MaxLoc gx = maxloc_init(), gr = maxloc_init();
+    for (int i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+      a += partial[i];
+      maxloc_merge(gx, pmx[i]);
+      maxloc_merge(gr, pmr[i]);
+    }
+    a = block_sum(a, sh);
+    gx = block_maxloc(gx, shm);
+    gr = block_maxloc(gr, shm);
+    if (threadIdx.x == 0) finalize_iteration(st, a, gx, gr, BCGS, sp);
+  }
+}
+
+__global__ void copy_kernel(int n, const double *__restrict__ a, double *__restrict__ b) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    b[i] = a[i];
+}
+
+__global__ void init_state_kernel(KState *st, double epfact, double dvclose, double rclose,
+                                  int icnvgopt, int sum_cap, int iscl, int reset_count) {
+  st->rho = st->rho0 = st->alpha = st->alpha0 = st->omega = st->omega0 = st->beta = 0.0;
+  st->epfact = epfact;
+  st->dvclose = dvclose;
+  st->rclose = rclose;
+  st->deltax = st->rmax = st->l2norm = 0.0;
+  st->xloc = st->rloc = -1;
+  st->icnvgopt = icnvgopt;
+  st->icnvg = 0;
+  st->done = 0;
+  st->iter = 0;
+  if (reset_count) st->sum_count = 0;
+  st->sum_cap = sum_cap;
+  st->iscl = iscl;
+}
+
+// ims_base_scale, symmetric diagonal scaling (ISCL = 1) :644-663, 727-752
+__global__ void scale1_vec_kernel(int n, const int *__restrict__ slice_ptr,
+                                  const double *__restrict__ val, double *__restrict__ dscale) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    const long long base = (long long)slice_ptr[r >> 5] + (r & 31);
+    dscale[r] = 1.0 / sqrt(fabs(val[base]));
+  }
+}
+
+__global__ void scale_apply_kernel(int n, const int *__restrict__ slice_ptr,
+                                   const unsigned char *__restrict__ rowlen,
+                                   const int *__restrict__ col, double *__restrict__ val,
+                                   const double *__restrict__ ds, const double *__restrict__ ds2,
+                                   double *__restrict__ x, double *__restrict__ b, int unscale) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    const long long base = (long long)slice_ptr[r >> 5] + (r & 31);
+    const int len = rowlen[r];
+    const double c1 = ds[r];
+    for (int k = 0; k < len; k++) {
+      const long long p = base + 32LL * k;
+      const double c2 = ds2[col[p]];
+      if (!unscale)
+        val[p] = c1 * val[p] * c2;
+      else
+        val[p] = (1.0 / c1) * val[p] * (1.0 / c2);
+    }
+    const double c2 = ds2[r];
+    if (!unscale) {
+      x[r] = x[r] / c2;
+      b[r] = b[r] * c1;
+    } else {
+      x[r] = x[r] * c2;
+      b[r] = b[r] / c1;
+    }
+  }
+}
+
+}  // namespace mf6
+
+using namespace mf6;
+
+// ImsLinearBase.f90:1316-1333 (0.01 / 0.10 are single-precision literals there)
+static double epfact_of(int icnvgopt, int kstp) {
+  if (icnvgopt == 2) return kstp == 1 ? (double)0.01f : (double)0.10f;
+  if (icnvgopt == 4) return 1.0e-4;
+  return 1.0;
+}
+
+// ims_base_pcu, ImsLinearBase.f90:808-858
+int mf6gpu_solver::factor() {
+  int ipcflag = 0, icount = 0;
+  double delta = 0.0;
+  for (;;) {
+    failflag.zero(stream);
+    launches += ilu0_factor(*A, A->val.p, lu.p, s.relax, delta, ipcflag, failflag.p, stream);
+    MF6_CK(cudaGetLastError());
+    MF6_CK(cudaMemcpyAsync(h_flag.p, failflag.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    MF6_CK(cudaStreamSynchronize(stream));
+    ipcflag = h_flag.p[0] ? 1 : 0;
+    if (ipcflag < 1) break;
+    delta = 1.5 * delta + 1.0e-3;
+    ipcflag = 0;
+    if (delta > 0.5) {
+      delta = 0.5;
+      ipcflag = 2;
+    }
+    icount++;
+    if (icount > 10) break;
+  }
+  return icount;
+}
+
+void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_dev, int *iters,
+                                 int *icnvg_out) {
+  const int N = n;
+  const int G = grid_for(N);
+  cudaStream_t S = stream;
+  const bool bcgs = (s.ilinmeth == 2);
+  SummaryPtrs sp{sum_itinner.p, sum_locdv.p, sum_locr.p, sum_dvmax.p, sum_rmax.p, sum_alpha.p, sum_omega.p};
+  launches = 0;
+  MF6_CK(cudaEventRecord(ev[0], S));
+  // -- scale (ImsLinear.f90:645-650)
+  if (s.iscl == 1) {
+    scale1_vec_kernel<<<G, kBlock, 0, S>>>(N, A->slice_ptr.p, A->val.p, dscale.p);
+    copy_kernel<<<G, kBlock, 0, S>>>(N, dscale.p, dscale2.p);
+    scale_apply_kernel<<<G, kBlock, 0, S>>>(N, A->slice_ptr.p, A->rowlen.p, A->col.p, A->val.p,
+                                            dscale.p, dscale2.p, x_dev, b_dev, 0);
+    launches += 3;
+  }
+  // -- preconditioner (ImsLinear.f90:669-673)
+  npivfix = factor();
+  MF6_CK(cudaEventRecord(ev[1], S));
+  // -- initial residual and its norm (ImsLinear.f90:676-699)
+  init_state_kernel<<<1, 1, 0, S>>>(st.p, epfact_of(s.icnvgopt, kstp), s.dvclose, s.rclose,
+                                    s.icnvgopt, sum_cap, s.iscl, kiter == 1 ? 1 : 0);
+  p.zero(S);
+  q.zero(S);
+  z.zero(S);
+  spmv_fused_kernel<1, 0><<<G, kBlock, 0, S>>>(N, A->slice_ptr.p, A->rowlen.p, A->col.p, A->val.p,
+                                               x_dev, d.p, b_dev, nullptr, nullptr, nullptr, st.p, 0, 0);
+  double *scale_slot = partial.p + 3 * kMaxBlocks;  // scratch scalar
+  nrm_max_kernel<<<G, kBlock, 0, S>>>(N, d.p, partial.p, tickets.p + TK_NRM, scale_slot);
+  nrm_ssq_kernel<<<G, kBlock, 0, S>>>(N, d.p, partial.p, tickets.p + TK_NRM, st.p, scale_slot);
+  launches += 4;
+  MF6_CK(cudaGetLastError());
+  MF6_CK(cudaMemcpyAsync(h_st.p, st.p, sizeof(KState), cudaMemcpyDeviceToHost, S));
+  MF6_CK(cudaStreamSynchronize(S));
+  l2norm0 = h_st.p->l2norm0;
+  int itmax = s.iter1;
+  int icnvg = 0;
+  if (l2norm0 == 0.0) {
+    itmax = 0;
+    icnvg = 1;
+  }
+  int innerit = 0;
+  const int *ord = A->ord_ptr();
+  // polling cadence: cheap iterations (small n) are batched deeper
+  const int batch = (N > 2000000) ? 4 : 16;
+  if (itmax > 0) {
+    if (bcgs) copy_kernel<<<G, kBlock, 0, S>>>(N, d.p, dhat.p);
+    int launched = 0;
+    bool finished = false;
+    while (!finished && launched < itmax) {
+      const int nb = std::min(batch, itmax - launched);
+      for (int b = 0; b < nb; b++) {
+        const int iiter = launched + b + 1;
+        const int first = (iiter == 1) ? 1 : 0;
+        if (!bcgs) {
+          launches += ilu0_apply(*A, lu.p, d.p, z.p, &st.p->done, S);
+          dot_kernel<<<G, kBlock, 0, S>>>(N, d.p, z.p, partial.p, tickets.p + TK_DOT, st.p,
+                                          FIN_CG_RHO, nullptr, 1);
+          cg_p_kernel<<<G, kBlock, 0, S>>>(N, z.p, p.p, st.p, first);
+          spmv_fused_kernel<0, 1><<<G, kBlock, 0, S>>>(N, A->slice_ptr.p, A->rowlen.p, A->col.p,
+                                                       A->val.p, p.p, q.p, nullptr, p.p, partial.p,
+                                                       tickets.p + TK_SPMV, st.p, FIN_CG_ALPHA, 1);
+          update_kernel<0><<<G, kBlock, 0, S>>>(N, x_dev, d.p, p.p, q.p, nullptr, nullptr, nullptr,
+                                                ord, partial.p, pmx.p, pmr.p, tickets.p + TK_UPD,
+                                                st.p, sp);
+          launches += 4;
+        } else {
+          dot_kernel<<<G, kBlock, 0, S>>>(N, dhat.p, d.p, partial.p, tickets.p + TK_DOT, st.p,
+                                          FIN_BCGS_RHO, nullptr, 1);
+          bcgs_p_kernel<<<G, kBlock, 0, S>>>(N, d.p, v.p, p.p, st.p, first);
+          launches += ilu0_apply(*A, lu.p, p.p, phat.p, &st.p->done, S);
+          spmv_fused_kernel<0, 1><<<G, kBlock, 0, S>>>(N, A->slice_ptr.p, A->rowlen.p, A->col.p,
+                                                       A->val.p, phat.p, v.p, nullptr, dhat.p,
+                                                       partial.p, tickets.p + TK_SPMV, st.p,
+                                                       FIN_BCGS_ALPHA, 1);
+          bcgs_q_kernel<<<G, kBlock, 0, S>>>(N, d.p, v.p, q.p, st.p);
+          launches += ilu0_apply(*A, lu.p, q.p, qhat.p, &st.p->done, S);
+          spmv_fused_kernel<0, 2><<<G, kBlock, 0, S>>>(N, A->slice_ptr.p, A->rowlen.p, A->col.p,
+                                                       A->val.p, qhat.p, t.p, nullptr, q.p,
+                                                       partial.p, tickets.p + TK_SPMV, st.p,
+                                                       FIN_BCGS_OMEGA, 1);
+          update_kernel<1><<<G, kBlock, 0, S>>>(N, x_dev, d.p, phat.p, q.p, qhat.p, t.p, dscale.p,
+                                                ord, partial.p, pmx.p, pmr.p, tickets.p + TK_UPD,
+                                                st.p, sp);
+          launches += 6;
+        }
+        if (s.north > 0 && ((iiter + 1) % s.north == 0)) {
+          spmv_fused_kernel<1, 0><<<G, kBlock, 0, S>>>(N, A->slice_ptr.p, A->rowlen.p, A->col.p,
+                                                       A->val.p, x_dev, d.p, b_dev, nullptr,
+                                                       nullptr, nullptr, st.p, 0, 1);
+          launches++;
+        }
+      }
+      launched += nb;
+      MF6_CK(cudaGetLastError());
+      MF6_CK(cudaMemcpyAsync(h_st.p, st.p, sizeof(KState), cudaMemcpyDeviceToHost, S));
+      MF6_CK(cudaStreamSynchronize(S));
+      if (h_st.p->done) finished = true;
+    }
+    innerit = h_st.p->iter;
+    icnvg = h_st.p->icnvg;
+  }
+  if (icnvg < 0) icnvg = 0;
+  // -- unscale (ImsLinear.f90:740-745)
+  if (s.iscl == 1) {
+    scale_apply_kernel<<<G, kBlock, 0, S>>>(N, A->slice_ptr.p, A->rowlen.p, A->col.p, A->val.p,
+                                            dscale.p, dscale2.p, x_dev, b_dev, 1);
+    launches++;
+  }
+  MF6_CK(cudaEventRecord(ev[2], S));
+  MF6_CK(cudaEventSynchronize(ev[2]));
+  float ms01 = 0.f, ms12 = 0.f;
+  MF6_CK(cudaEventElapsedTime(&ms01, ev[0], ev[1]));
+  MF6_CK(cudaEventElapsedTime(&ms12, ev[1], ev[2]));
+  t_factor = 1e-3 * ms01;
+  t_krylov = 1e-3 * ms12;
+  *iters = innerit;
+  *icnvg_out = icnvg;
+}
+
+static void check_settings(mf6gpu_ims_settings &s) {
+  // the same spirit as petsc_check_settings (PetscSolver.F90:123-154): options the
+  // backend cannot honour are rejected (ILUT) or downgraded (reordering)
+  MF6_REQUIRE(s.ilinmeth == 1 || s.ilinmeth == 2, "solver: LINEAR_ACCELERATION must be CG (1) or BICGSTAB (2)");
+  MF6_REQUIRE(s.level <= 0 && s.droptol <= 0.0,
+              "solver: ILUT/MILUT (PRECONDITIONER_LEVELS / DROP_TOLERANCE) is not available on the GPU path");
+  MF6_REQUIRE(s.iscl == 0 || s.iscl == 1, "solver: SCALING_METHOD L2NORM is not available on the GPU path");
+  MF6_REQUIRE(s.relax >= 0.0 && s.relax <= 1.0, "solver: RELAXATION_FACTOR must be in [0,1]");
+  MF6_REQUIRE(s.north >= 0, "solver: NUMBER_ORTHOGONALIZATIONS must be >= 0");
+  MF6_REQUIRE(s.iter1 > 0, "solver: INNER_MAXIMUM must be > 0");
+  if (s.iord != 0) s.iord = 0;  // REORDERING_METHOD ignored (own level-sorted ordering)
+}
+
+extern "C" {
+
+int mf6gpu_solver_create(mf6gpu_matrix *m, const mf6gpu_ims_settings *settings,
+                         int32_t summary_capacity, mf6gpu_solver **out) {
+  return guard([&] {
+    MF6_REQUIRE(m && settings && out, "solver_create: null argument");
+    auto *s = new mf6gpu_solver();
+    try {
+      s->A = m;
+      s->s = *settings;
+      check_settings(s->s);
+      s->ipc = (s->s.relax > 0.0) ? 2 : 1;  // ImsLinear.f90:178-185
+      s->n = m->n;
+      s->stream = m->stream;
+      const size_t n = (size_t)m->n;
+      s->lu.alloc_zero((size_t)m->nslots);
+      s->x.alloc_zero(n);
+      s->b.alloc_zero(n);
+      s->d.alloc_zero(n);
+      s->p.alloc_zero(n);
+      s->q.alloc_zero(n);
+      s->z.alloc_zero(n);
+      if (s->s.ilinmeth == 2) {
+        s->t.alloc_zero(n);
+        s->v.alloc_zero(n);
+        s->dhat.alloc_zero(n);
+        s->phat.alloc_zero(n);
+        s->qhat.alloc_zero(n);
+      }
+      if (s->s.iscl != 0) {
+        s->dscale.alloc_zero(n);
+        s->dscale2.alloc_zero(n);
+      }
+      s->hx.alloc(n);
+      s->hb.alloc(n);
+      s->st.alloc_zero(1);
+      s->partial.alloc_zero(4 * (size_t)kMaxBlocks);
+      s->pmx.alloc_zero((size_t)kMaxBlocks);
+      s->pmr.alloc_zero((size_t)kMaxBlocks);
+      s->tickets.alloc_zero(8);
+      s->failflag.alloc_zero(1);
+      s->sum_cap = summary_capacity > 0 ? summary_capacity : 0;
+      const size_t c = (size_t)(s->sum_cap > 0 ? s->sum_cap : 1);
+      s->sum_itinner.alloc_zero(c);
+      s->sum_locdv.alloc_zero(c);
+      s->sum_locr.alloc_zero(c);
+      s->sum_dvmax.alloc_zero(c);
+      s->sum_rmax.alloc_zero(c);
+      s->sum_alpha.alloc_zero(c);
+      s->sum_omega.alloc_zero(c);
+      s->h_st.alloc(1);
+      s->h_flag.alloc(4);
+      for (auto &e : s->ev) MF6_CK(cudaEventCreate(&e));
+    } catch (...) {
+      delete s;
+      throw;
+    }
+    *out = s;
+  });
+}
+
+int mf6gpu_solver_destroy(mf6gpu_solver *s) {
+  return guard([&] {
+    if (!s) return;
+    for (auto &e : s->ev)
+      if (e) cudaEventDestroy(e);
+    delete s;
+  });
+}
+
+int mf6gpu_solver_solve(mf6gpu_solver *s, int32_t kiter, int32_t kstp, const double *rhs,
+                        double *x, int32_t *iteration_number, int32_t *is_converged) {
+  return guard([&] {
+    MF6_REQUIRE(s && rhs && x && iteration_number && is_converged, "solver_solve: null argument");
+    const size_t nb = sizeof(double) * (size_t)s->n;
+    cudaStream_t S = s->stream;
+    MF6_CK(cudaMemcpyAsync(s->hx.p, x, nb, cudaMemcpyHostToDevice, S));
+    MF6_CK(cudaMemcpyAsync(s->hb.p, rhs, nb, cudaMemcpyHostToDevice, S));
+    launch_gather(s->n, s->A->d_perm.p, s->hx.p, s->x.p, S);
+    launch_gather(s->n, s->A->d_perm.p, s->hb.p, s->b.p, S);
+    int it = 0, cv = 0;
+    s->solve_device(kiter, kstp, s->x.p, s->b.p, &it, &cv);
+    launch_scatter(s->n, s->A->d_perm.p, s->x.p, s->hx.p, S);
+    MF6_CK(cudaGetLastError());
+    MF6_CK(cudaMemcpyAsync(x, s->hx.p, nb, cudaMemcpyDeviceToHost, S));
+    MF6_CK(cudaStreamSynchronize(S));
+    *iteration_number = it;
+    *is_converged = cv;
+  });
+}
+
+int mf6gpu_solver_get_summary(mf6gpu_solver *s, int32_t cap, int32_t *itinner, double *dvmax,
+                              int32_t *locdv, double *rmax, int32_t *locr, double *alpha,
+                              double *omega) {
+  int count = 0;
+  int rc = guard([&] {
+    MF6_REQUIRE(s, "solver_get_summary: null argument");
+    MF6_CK(cudaMemcpy(s->h_st.p, s->st.p, sizeof(KState), cudaMemcpyDeviceToHost));
+    count = std::min(std::min(s->h_st.p->sum_count, s->sum_cap), (int)cap);
+    if (count <= 0) {
+      count = 0;
+      return;
+    }
+    const size_t c = (size_t)count;
+    std::vector<int> li(c);
+    if (itinner) s->sum_itinner.download(itinner, c);
+    if (dvmax) s->sum_dvmax.download(dvmax, c);
+    if (rmax) s->sum_rmax.download(rmax, c);
+    if (alpha) s->sum_alpha.download(alpha, c);
+    if (omega) s->sum_omega.download(omega, c);
+    if (locdv) {
+      s->sum_locdv.download(li.data(), c);
+      for (size_t i = 0; i < c; i++) locdv[i] = li[i] >= 0 ? s->A->perm[li[i]] + 1 : 0;
+    }
+    if (locr) {
+      s->sum_locr.download(li.data(), c);
+      for (size_t i = 0; i < c; i++) locr[i] = li[i] >= 0 ? s->A->perm[li[i]] + 1 : 0;
+    }
+  });
+  return rc < 0 ? rc : count;
+}
+
+double mf6gpu_solver_stat(const mf6gpu_solver *s, int what) {
+  if (!s) return -1.0;
+  switch (what) {
+    case 0: return s->l2norm0;
+    case 1: return (double)s->npivfix;
+    case 2: return s->t_factor;
+    case 3: return s->t_krylov;
+    case 4: return (double)s->launches;
+  }
+  return -1.0;
+}
+
+int mf6gpu_solver_factor(mf6gpu_solver *s, int32_t *npivot_fixes) {
+  return guard([&] {
+    MF6_REQUIRE(s, "solver_factor: null argument");
+    int c = s->factor();
+    if (npivot_fixes) *npivot_fixes = c;
+  });
+}
+
+int mf6gpu_solver_apply_preconditioner(mf6gpu_solver *s, const double *r, double *z) {
+  return guard([&] {
+    MF6_REQUIRE(s && r && z, "solver_apply_preconditioner: null argument");
+    const size_t nb = sizeof(double) * (size_t)s->n;
+    cudaStream_t S = s->stream;
+    MF6_CK(cudaMemcpyAsync(s->hb.p, r, nb, cudaMemcpyHostToDevice, S));
+    launch_gather(s->n, s->A->d_perm.p, s->hb.p, s->d.p, S);
+    ilu0_apply(*s->A, s->lu.p, s->d.p, s->z.p, nullptr, S);
+    launch_scatter(s->n, s->A->d_perm.p, s->z.p, s->hx.p, S);
+    MF6_CK(cudaGetLastError());
+    MF6_CK(cudaMemcpyAsync(z, s->hx.p, nb, cudaMemcpyDeviceToHost, S));
+    MF6_CK(cudaStreamSynchronize(S));
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,60 @@
+// solver.cuh -- device-resident IMS linear solver (LinearSolverBaseType replacement)
+#pragma once
+#include "ilu0.cuh"
+
+namespace mf6 {
+
+// Scalars of the Krylov recurrences; lives in device memory, never read by the
+// host inside the inner loop (only `done`/`iter` are polled every few iterations).
+struct KState {
+  double rho, rho0, alpha, alpha0, omega, omega0, beta;
+  double l2norm0, epfact, dvclose, rclose;
+  double deltax, rmax, l2norm;
+  int xloc, rloc;      // device-numbering rows of deltax / rmax
+  int icnvgopt;
+  int icnvg;           // ICNVG of the reference (1, 0, -1)
+  int done;            // inner loop has exited
+  int iter;            // INNERIT
+  int sum_count;       // summary%iter_cnt
+  int sum_cap;
+  int iscl;
+  int pad;
+};
+
+}  // namespace mf6
+
+struct mf6gpu_solver {
+  mf6gpu_matrix *A = nullptr;  // not owned
+  mf6gpu_ims_settings s{};
+  int ipc = 1;
+  cudaStream_t stream = 0;
+  int n = 0;
+  // work vectors (final numbering)
+  mf6::DevBuf<double> lu;                 // factor values (SELL slots)
+  mf6::DevBuf<double> x, b, d, p, q, z;   // CG
+  mf6::DevBuf<double> t, v, dhat, phat, qhat;  // BiCGSTAB
+  mf6::DevBuf<double> dscale, dscale2;
+  mf6::DevBuf<double> hx, hb;             // staging in original numbering
+  mf6::DevBuf<mf6::KState> st;
+  mf6::DevBuf<double> partial;            // [4 * kMaxBlocks]
+  mf6::DevBuf<mf6::MaxLoc> pmx, pmr;      // [kMaxBlocks]
+  mf6::DevBuf<unsigned int> tickets;      // [8]
+  mf6::DevBuf<int> failflag;
+  // summary ring (device), capacity sum_cap
+  int sum_cap = 0;
+  mf6::DevBuf<int> sum_itinner, sum_locdv, sum_locr;
+  mf6::DevBuf<double> sum_dvmax, sum_rmax, sum_alpha, sum_omega;
+  mf6::PinnedBuf<mf6::KState> h_st;
+  mf6::PinnedBuf<int> h_flag;
+  // stats of the last solve
+  double l2norm0 = 0.0;
+  int npivfix = 0;
+  double t_factor = 0.0, t_krylov = 0.0;
+  long long launches = 0;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool values_external = false;  // A values are assembled on the device by the solution
+
+  // device-side entry: x_dev / b_dev already in FINAL numbering on the device.
+  void solve_device(int kiter, int kstp, double *x_dev, double *b_dev, int *iters, int *icnvg);
+  int factor();  // pcu: returns pivot corrections
+};

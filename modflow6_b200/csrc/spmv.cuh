@@ -1,0 +1,37 @@
+// spmv.cuh -- the SELL-32 row product shared by every kernel that needs (A x)_row.
+#pragma once
+#include "common.cuh"
+
+namespace mf6 {
+#ifdef __CUDACC__
+// (A x)_row with the accumulation order of amux (sparsekit.f90:44-57): slot 0
+// (diagonal) first, then the row's remaining entries in storage order.
+// Loads of 8 slots are issued before use to keep many requests in flight.
+__device__ __forceinline__ double sell_row_dot(int row, const int *__restrict__ slice_ptr,
+                                               const unsigned char *__restrict__ rowlen,
+                                               const int *__restrict__ col,
+                                               const double *__restrict__ val,
+                                               const double *__restrict__ x) {
+  const int len = rowlen[row];
+  const long long base = (long long)slice_ptr[row >> 5] + (row & 31);
+  double t = 0.0;
+  for (int k0 = 0; k0 < len; k0 += 8) {
+    double v[8], xv[8];
+    int c[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const bool ok = (k0 + u) < len;
+      const long long p = base + (long long)(k0 + u) * 32;
+      v[u] = ok ? __ldg(val + p) : 0.0;
+      c[u] = ok ? __ldg(col + p) : row;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) xv[u] = x[c[u]];
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+      if ((k0 + u) < len) t = t + v[u] * xv[u];
+  }
+  return t;
+}
+#endif
+}  // namespace mf6

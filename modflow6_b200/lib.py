@@ -1,0 +1,111 @@
+"""Loader for libmf6gpu.so (the C ABI declared in include/mf6gpu.h).
+
+There is no CPU fallback: if the library is missing this module raises, and
+every compute entry point fails when no CUDA device is usable.
+"""
+import ctypes as C
+import os
+
+from . import ctypes_types as T
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmf6gpu.so")
+
+# every symbol include/mf6gpu.h declares (tests/test_abi.py checks the export list)
+SYMBOLS = [
+    "mf6gpu_abi_version", "mf6gpu_last_error", "mf6gpu_sizeof", "mf6gpu_init", "mf6gpu_device_count",
+    "mf6gpu_matrix_create", "mf6gpu_matrix_destroy", "mf6gpu_matrix_update", "mf6gpu_matrix_zero_entries",
+    "mf6gpu_matrix_get_values", "mf6gpu_matrix_multiply", "mf6gpu_matrix_info", "mf6gpu_matrix_get_permutation",
+    "mf6gpu_vector_create", "mf6gpu_vector_destroy", "mf6gpu_vector_set", "mf6gpu_vector_get",
+    "mf6gpu_vector_zero_entries", "mf6gpu_vector_axpy", "mf6gpu_vector_norm2", "mf6gpu_vector_dot",
+    "mf6gpu_solver_create", "mf6gpu_solver_destroy", "mf6gpu_solver_solve", "mf6gpu_solver_get_summary",
+    "mf6gpu_solver_stat", "mf6gpu_solver_factor", "mf6gpu_solver_apply_preconditioner",
+    "mf6gpu_solution_create", "mf6gpu_solution_destroy", "mf6gpu_solution_set_packages",
+    "mf6gpu_solution_timestep", "mf6gpu_solution_formulate", "mf6gpu_solution_get_x",
+    "mf6gpu_solution_set_x", "mf6gpu_solution_get_amat", "mf6gpu_solution_get_rhs",
+    "mf6gpu_solution_get_flowja", "mf6gpu_solution_get_condsat", "mf6gpu_solution_solver",
+]
+
+_lib = None
+
+
+class Mf6GpuError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen libmf6gpu.so and declare the prototypes (no CUDA call is made)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Mf6GpuError(f"{LIB_PATH} not built; run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, vpp = C.c_void_p, C.POINTER(C.c_void_p)
+    i32, f64 = C.c_int32, C.c_double
+    pi32, pf64 = T.p_i32, T.p_f64
+    L.mf6gpu_abi_version.restype = C.c_int
+    L.mf6gpu_last_error.restype = C.c_char_p
+    L.mf6gpu_sizeof.restype = C.c_size_t
+    L.mf6gpu_sizeof.argtypes = [C.c_int]
+    L.mf6gpu_init.argtypes = [C.c_int]
+    L.mf6gpu_matrix_create.argtypes = [i32, i32, pi32, pi32, i32, i32, vpp]
+    L.mf6gpu_matrix_destroy.argtypes = [vp]
+    L.mf6gpu_matrix_update.argtypes = [vp, pf64]
+    L.mf6gpu_matrix_zero_entries.argtypes = [vp]
+    L.mf6gpu_matrix_get_values.argtypes = [vp, pf64]
+    L.mf6gpu_matrix_multiply.argtypes = [vp, pf64, pf64]
+    L.mf6gpu_matrix_info.restype = C.c_int64
+    L.mf6gpu_matrix_info.argtypes = [vp, C.c_int]
+    L.mf6gpu_matrix_get_permutation.argtypes = [vp, pi32]
+    L.mf6gpu_vector_create.argtypes = [i32, vpp]
+    L.mf6gpu_vector_destroy.argtypes = [vp]
+    L.mf6gpu_vector_set.argtypes = [vp, pf64]
+    L.mf6gpu_vector_get.argtypes = [vp, pf64]
+    L.mf6gpu_vector_zero_entries.argtypes = [vp]
+    L.mf6gpu_vector_axpy.argtypes = [vp, f64, vp]
+    L.mf6gpu_vector_norm2.argtypes = [vp, pf64]
+    L.mf6gpu_vector_dot.argtypes = [vp, vp, pf64]
+    L.mf6gpu_solver_create.argtypes = [vp, C.POINTER(T.ImsSettings), i32, vpp]
+    L.mf6gpu_solver_destroy.argtypes = [vp]
+    L.mf6gpu_solver_solve.argtypes = [vp, i32, i32, pf64, pf64, pi32, pi32]
+    L.mf6gpu_solver_get_summary.argtypes = [vp, i32, pi32, pf64, pi32, pf64, pi32, pf64, pf64]
+    L.mf6gpu_solver_stat.restype = f64
+    L.mf6gpu_solver_stat.argtypes = [vp, C.c_int]
+    L.mf6gpu_solver_factor.argtypes = [vp, pi32]
+    L.mf6gpu_solver_apply_preconditioner.argtypes = [vp, pf64, pf64]
+    L.mf6gpu_solution_create.argtypes = [C.POINTER(T.GwfModelStruct), C.POINTER(T.SlnSettings),
+                                         C.POINTER(T.ImsSettings), vpp]
+    L.mf6gpu_solution_destroy.argtypes = [vp]
+    L.mf6gpu_solution_set_packages.argtypes = [vp, i32, C.POINTER(T.BndPackageStruct)]
+    L.mf6gpu_solution_timestep.argtypes = [vp, i32, i32, f64, i32, C.POINTER(T.StepReport)]
+    L.mf6gpu_solution_formulate.argtypes = [vp, i32, f64, i32]
+    for f in ("get_x", "set_x", "get_amat", "get_rhs", "get_flowja", "get_condsat"):
+        getattr(L, "mf6gpu_solution_" + f).argtypes = [vp, pf64]
+    L.mf6gpu_solution_solver.restype = vp
+    L.mf6gpu_solution_solver.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc < 0:
+        raise Mf6GpuError(load().mf6gpu_last_error().decode("utf-8", "replace"))
+    return rc
+
+
+_initialised = False
+
+
+def init(device=-1):
+    """Select the CUDA device (one process per GPU).  Raises without a GPU."""
+    global _initialised
+    check(load().mf6gpu_init(int(device)))
+    _initialised = True
+
+
+def ensure_init():
+    if not _initialised:
+        dev = int(os.environ.get("LOCAL_RANK", "-1")) if "LOCAL_RANK" in os.environ else -1
+        init(dev)

@@ -1,0 +1,69 @@
+"""Shared problem builders for the tests (seeded, sized to run in seconds)."""
+import numpy as np
+
+from modflow6_b200 import ctypes_types as T
+from modflow6_b200.grid import Package, build_dis_model
+
+
+def hetero_dis(nlay, nrow, ncol, seed=1, sigma=1.0, icelltype=0, top=0.0, dz=10.0, delr=100.0,
+               k33_ratio=0.1, strt=44.0, **opts):
+    rng = np.random.default_rng(seed)
+    k = np.exp(rng.normal(np.log(10.0), sigma, size=(nlay, nrow, ncol)))
+    botm = top - dz * np.arange(1, nlay + 1)
+    return build_dis_model(nlay, nrow, ncol, delr, delr, top, botm, k, k33=k33_ratio * k,
+                           icelltype=icelltype, strt=strt, **opts)
+
+
+def chd_west_east(m, hw=48.0, he=40.0):
+    nlay, nrow, ncol = m.shape
+    kk, ii = np.meshgrid(np.arange(nlay), np.arange(nrow), indexing="ij")
+    west = ((kk * nrow + ii) * ncol).reshape(-1)
+    east = west + ncol - 1
+    return Package(T.PKG_CHD, np.concatenate([west, east]),
+                   np.concatenate([np.full(west.size, hw), np.full(east.size, he)]))
+
+
+def well_center(m, q=-1000.0, layer=None):
+    nlay, nrow, ncol = m.shape
+    k = nlay // 2 if layer is None else layer
+    return Package(T.PKG_WEL, [m.node(k, nrow // 2, ncol // 2)], [q])
+
+
+def permute_csr(ia, ja, a, perm):
+    """B = P A P^T, rows stored diagonal first then ascending (what the oracle builds)."""
+    n = ia.size - 1
+    iperm = np.empty(n, np.int64)
+    iperm[perm] = np.arange(n)
+    ia2 = np.zeros(n + 1, np.int32)
+    ja2 = np.empty_like(ja)
+    a2 = np.empty_like(a)
+    pos = 0
+    for r in range(n):
+        o = perm[r]
+        s, e = ia[o], ia[o + 1]
+        cols = iperm[ja[s + 1:e]]
+        order = np.argsort(cols, kind="stable")
+        ja2[pos] = r
+        a2[pos] = a[s]
+        m = e - s - 1
+        ja2[pos + 1:pos + 1 + m] = cols[order]
+        a2[pos + 1:pos + 1 + m] = a[s + 1:e][order]
+        pos += m + 1
+        ia2[r + 1] = pos
+    return ia2, ja2, a2
+
+
+def assembled_system(m, pkgs, ilinmeth=1):
+    """Formulated (amat, rhs, x) of the first outer iteration, from the oracle."""
+    from oracle.oracle import OracleSolution
+    ims = T.ImsSettings.make(ilinmeth=ilinmeth)
+    sln = T.SlnSettings.make()
+    S = OracleSolution(m, sln, ims)
+    S.set_packages(pkgs)
+    # apply chd_ad so that x carries the constant heads
+    x = S.x
+    for p in pkgs:
+        if p.type == T.PKG_CHD:
+            x[p.nodelist] = p.b1
+    S.formulate(kiter=1, delt=1.0, iss=1)
+    return S.amat.copy(), S.rhs.copy(), S.x.copy()
