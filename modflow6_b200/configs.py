@@ -1,0 +1,136 @@
+"""The BASELINE.json workloads as in-memory model definitions.
+
+C1  autotest/test_gwf_npf01_75x75.py (cases npf01a unconfined / npf01b confined)
+C2  synthetic confined steady-state DIS nlay x nrow x ncol (10 x 1000 x 1000 at full size)
+C3  synthetic unconfined transient DIS with NPF Newton-Raphson + STO, BiCGSTAB, DBD under-relaxation
+All generators are seeded; `scale` arguments shrink the grids for tests.
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import ctypes_types as T
+from .grid import Package, build_dis_model, tdis_steps
+
+
+@dataclass
+class Period:
+    perlen: float
+    nstp: int
+    tsmult: float
+    steady: bool
+    packages: list  # full list of packages active in this period
+
+
+@dataclass
+class SimConfig:
+    name: str
+    model: object
+    periods: list
+    sln: T.SlnSettings
+    ims: T.ImsSettings
+    meta: dict = field(default_factory=dict)
+
+
+def _chd_columns(m, hw, he):
+    nlay, nrow, ncol = m.shape
+    kk, ii = np.meshgrid(np.arange(nlay), np.arange(nrow), indexing="ij")
+    west = ((kk * nrow + ii) * ncol).reshape(-1)
+    east = west + ncol - 1
+    return Package(T.PKG_CHD, np.concatenate([west, east]),
+                   np.concatenate([np.full(west.size, hw), np.full(east.size, he)]))
+
+
+def c1_npf01(case="b", gpu_ordering=T.ORDER_NATURAL):
+    """test_gwf_npf01_75x75.py:16-120 -- 1x75x75, lognormal K (seed 9001), CHD 48/40 on the west/east
+    columns, WEL -1000 at (0,38,38) from period 2; periods: 1 d steady, 1000 d / 10 steps x1.5 transient,
+    1 d steady; CG, relaxation_factor 1.0 (MILU0), dvclose 1e-6, rclose 0.01, no under-relaxation."""
+    idx = {"a": 0, "b": 1}[case]
+    top = [100.0, 0.0][idx]
+    laytyp = [1, 0][idx]
+    ss = [0.0, 1.0e-4][idx]
+    sy = [0.1, 0.0][idx]
+    nlay, nrow, ncol = 1, 75, 75
+    delr = 20000.0 / float(nrow)
+    hk = np.random.RandomState(9001).lognormal(5.0, 1.23, (nrow, ncol))
+    m = build_dis_model(nlay, nrow, ncol, delr, delr, top, [-100.0], hk[None], k33=hk[None],
+                        icelltype=laytyp, strt=40.0, ss=ss, sy=sy, iconvert=laytyp)
+    chd = _chd_columns(m, 48.0, 40.0)
+    nc = int((nrow - 1) / 2) + 1
+    wel = Package(T.PKG_WEL, [m.node(0, nc, nc)], [-1000.0])
+    periods = [Period(1.0, 1, 1.0, True, [chd]),
+               Period(1000.0, 10, 1.5, False, [chd, wel]),
+               Period(1.0, 1, 1.0, True, [chd, wel])]
+    ims = T.ImsSettings.make(dvclose=1e-6, rclose=0.01, iter1=300, ilinmeth=1, relax=1.0,
+                             gpu_ordering=gpu_ordering)
+    sln = T.SlnSettings.make(dvclose=1e-6, mxiter=100, nonmeth=0)
+    return SimConfig(f"npf01{case}_75x75", m, periods, sln, ims)
+
+
+def c2_confined(nlay=10, nrow=1000, ncol=1000, gpu_ordering=T.ORDER_MULTICOLOR, inner_maximum=500,
+                outer_maximum=50, seed=20260101):
+    """confined steady state, heterogeneous K = exp(N(ln 10, 1)), k33 = 0.1 k,
+    delr = delc = 100, layer thickness 10, CHD 48 / 40 on the first / last column, WEL -1000 at the centre
+    of the middle layer; CG + ILU0, inner_dvclose 1e-6, inner_rclose 1e-2, outer_dvclose 1e-5."""
+    rng = np.random.default_rng(seed)
+    k = np.exp(rng.normal(np.log(10.0), 1.0, size=(nlay, nrow, ncol)))
+    botm = -10.0 * np.arange(1, nlay + 1)
+    m = build_dis_model(nlay, nrow, ncol, 100.0, 100.0, 0.0, botm, k, k33=0.1 * k, icelltype=0, strt=44.0)
+    chd = _chd_columns(m, 48.0, 40.0)
+    wel = Package(T.PKG_WEL, [m.node(nlay // 2, nrow // 2, ncol // 2)], [-1000.0])
+    periods = [Period(1.0, 1, 1.0, True, [chd, wel])]
+    ims = T.ImsSettings.make(dvclose=1e-6, rclose=1e-2, iter1=inner_maximum, ilinmeth=1, relax=0.0,
+                             gpu_ordering=gpu_ordering)
+    sln = T.SlnSettings.make(dvclose=1e-5, mxiter=outer_maximum, nonmeth=0)
+    return SimConfig(f"c2_confined_{nlay}x{nrow}x{ncol}", m, periods, sln, ims)
+
+
+def c3_newton(nlay=5, nrow=2000, ncol=2000, gpu_ordering=T.ORDER_MULTICOLOR, nwel=100, ntrans=10,
+              seed=20260102, iallowptc=1):
+    """unconfined transient with NEWTON UNDER_RELAXATION + STO.
+    top 50, 5 layers x 10 m, icelltype 1 in the top layer, ss 1e-5, sy 0.15, RCH 1e-3 on top,
+    CHD on both sides, seeded wells (switched on in the transient period); BICGSTAB + ILU0, DBD under-relaxation (MODERATE preset values,
+    NumericalSolution.f90:2644-2655); 1 steady period + `ntrans` transient steps (x1.2)."""
+    rng = np.random.default_rng(seed)
+    k = np.exp(rng.normal(np.log(10.0), 0.5, size=(nlay, nrow, ncol)))
+    top = 50.0
+    botm = top - 10.0 * np.arange(1, nlay + 1)
+    ict = np.zeros((nlay, nrow, ncol), np.int32)
+    ict[0] = 1
+    m = build_dis_model(nlay, nrow, ncol, 100.0, 100.0, top, botm, k, k33=0.1 * k, icelltype=ict,
+                        strt=47.0, ss=1e-5, sy=0.15, iconvert=ict, inewton=1, inewtonur=1)
+    chd = _chd_columns(m, 48.0, 46.0)
+    rch = Package(T.PKG_RCH, np.arange(nrow * ncol), np.full(nrow * ncol, 1e-3))
+    wi = rng.integers(1, nrow - 1, size=nwel)
+    wj = rng.integers(1, ncol - 1, size=nwel)
+    wk = rng.integers(1, nlay, size=nwel) if nlay > 1 else np.zeros(nwel, int)
+    wnodes = np.unique((wk * nrow + wi) * ncol + wj)
+    wel = Package(T.PKG_WEL, wnodes, np.full(wnodes.size, -500.0), iflowred=1, flowred=0.1)
+    periods = [Period(1.0, 1, 1.0, True, [chd, rch]),
+               Period(100.0, ntrans, 1.2, False, [chd, rch, wel])]
+    ims = T.ImsSettings.make(dvclose=1e-5, rclose=1e-1, iter1=100, ilinmeth=2, relax=0.0,
+                             gpu_ordering=gpu_ordering)
+    sln = T.SlnSettings.make(dvclose=1e-4, mxiter=50, nonmeth=3, theta=0.9, akappa=1e-4, gamma=0.0,
+                             amomentum=0.0, iallowptc=iallowptc)
+    return SimConfig(f"c3_newton_{nlay}x{nrow}x{ncol}", m, periods, sln, ims)
+
+
+def run_simulation(solution, cfg, max_steps=None, collect_heads=False):
+    """Mf6DoTimestep loop (src/mf6core.f90:620-660): for every period set the stress data,
+    for every time step call sln_ca.  `solution` is any object with set_packages / timestep / x
+    (GpuNumericalSolution or the oracle).  Returns the list of step reports (as dicts)."""
+    out = []
+    nsteps = 0
+    for kper, per in enumerate(cfg.periods, start=1):
+        solution.set_packages(per.packages)
+        for kstp, delt in enumerate(tdis_steps(per.perlen, per.nstp, per.tsmult), start=1):
+            rep = solution.timestep(kper, kstp, delt, 1 if per.steady else 0)
+            d = rep.as_dict()
+            d.update(kper=kper, kstp=kstp, delt=delt)
+            if collect_heads:
+                d["head"] = np.array(solution.x, copy=True)
+            out.append(d)
+            nsteps += 1
+            if max_steps is not None and nsteps >= max_steps:
+                return out
+    return out

@@ -1,18 +1,1447 @@
-// solution.cu -- placeholder, replaced by the device-resident formulate path
+// solution.cu -- device-resident GWF formulate (NPF / STO / boundary packages),
+// the pre-solve fix-ups and the outer (Picard / Newton) iteration.
+//
+// Restates on the device (one thread per matrix row, "row-gather" form: every
+// row evaluates its own connections, so there are no atomics and the result is
+// deterministic; arithmetic per entry in the reference's order):
+//   NumericalSolution.f90  solve :1482-1837, sln_buildsystem :1941-1991, sln_reset :2389-2396,
+//       sln_ls fix-ups :2434-2573, sln_calc_ptc :2936-2962, sln_calc_residual :2966-2982,
+//       sln_calcdx :2912-2932, sln_underrelax :2989-3114, sln_get_dxmax :3122-3153
+//   gwf.f90  gwf_ad :396-442, gwf_cf :446-462, gwf_fc :466-555, gwf_ptc :625-687, gwf_cq :741-778,
+//       gwf_bd :785-824
+//   gwf-npf.f90  npf_cf :444-470, npf_fc :474-574, npf_fn :578-698, npf_nur :705-741,
+//       npf_cq/qcalc :745-865, calc_condsat :1950-2037
+//   gwf-sto.f90  sto_fc :226-345, sto_fn :353-439, sto_cq :447-564
+//   BoundaryPackage.f90  bnd_fc :453-472, bnd_cq_simrate :583-619 ; gwf-{wel,riv,rch,ghb,drn,chd}.f90
+//   Budget.f90 :259-267, :631-648 ; Sparse.f90 csr_diagsum :262-281
 #include "solver.cuh"
-using namespace mf6;
-extern "C" {
-#define NOTYET(name) return guard([&] { MF6_REQUIRE(false, name ": not implemented yet"); })
-int mf6gpu_solution_create(const mf6gpu_gwf_model *, const mf6gpu_sln_settings *, const mf6gpu_ims_settings *, mf6gpu_solution **) { NOTYET("solution_create"); }
-int mf6gpu_solution_destroy(mf6gpu_solution *) { return 0; }
-int mf6gpu_solution_set_packages(mf6gpu_solution *, int32_t, const mf6gpu_bnd_package *) { NOTYET("solution_set_packages"); }
-int mf6gpu_solution_timestep(mf6gpu_solution *, int32_t, int32_t, double, int32_t, mf6gpu_step_report *) { NOTYET("solution_timestep"); }
-int mf6gpu_solution_formulate(mf6gpu_solution *, int32_t, double, int32_t) { NOTYET("solution_formulate"); }
-int mf6gpu_solution_get_x(mf6gpu_solution *, double *) { NOTYET("solution_get_x"); }
-int mf6gpu_solution_set_x(mf6gpu_solution *, const double *) { NOTYET("solution_set_x"); }
-int mf6gpu_solution_get_amat(mf6gpu_solution *, double *) { NOTYET("solution_get_amat"); }
-int mf6gpu_solution_get_rhs(mf6gpu_solution *, double *) { NOTYET("solution_get_rhs"); }
-int mf6gpu_solution_get_flowja(mf6gpu_solution *, double *) { NOTYET("solution_get_flowja"); }
-int mf6gpu_solution_get_condsat(mf6gpu_solution *, double *) { NOTYET("solution_get_condsat"); }
-mf6gpu_solver *mf6gpu_solution_solver(mf6gpu_solution *) { return nullptr; }
+#include "gwf_device.cuh"
+#include "spmv.cuh"
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+namespace mf6 {
+
+struct ModelOpts {
+  int icellavg, inewton, inewtonur, iperched, ivarcv, idewatcv, insto;
+  int istor_coef, iconf_ss, iorig_ss;
+  int all_confined;  // no convertible cell, no perched, no Newton: cond == condsat
+  double satomega;
+};
+
+// per-cell / per-slot / per-connection device views passed by value to kernels
+struct ModelView {
+  int n;
+  const int *slice_ptr;
+  const unsigned char *rowlen;
+  const int *col;
+  const int *slot_conn;       // (jas << 1) | (neighbour has the higher original index) ; -1 diag/pad
+  const double *slot_condsat;
+  const double *condsat, *cl1, *cl2, *hwva;
+  const int *ihc;
+  const double *top, *bot, *area, *k11, *k33, *ss, *sy;
+  const int *icelltype, *ibound, *iconvert;
+  ModelOpts o;
+};
+
+// conductance of the connection between row r and its neighbour c, evaluated
+// with the argument order of the reference (n = lower original index).
+__device__ __forceinline__ double conn_cond(const ModelView &M, int r, int c, int up, int jas,
+                                            double slot_csat, const double *__restrict__ h,
+                                            const double *__restrict__ sat) {
+  const int n = up ? r : c, m = up ? c : r;
+  const int ihc = M.ihc[jas];
+  if (ihc == 0)
+    return vcond(M.ibound[n], M.ibound[m], M.icelltype[n], M.icelltype[m], M.o.ivarcv,
+                 M.o.idewatcv, slot_csat, h[n], h[m], M.k33[n], M.k33[m], sat[n], sat[m],
+                 M.top[n], M.top[m], M.bot[n], M.bot[m], M.hwva[jas]);
+  return hcond(M.ibound[n], M.ibound[m], M.icelltype[n], M.icelltype[m], M.o.inewton, ihc,
+               M.o.icellavg, slot_csat, h[n], h[m], sat[n], sat[m], M.k11[n], M.k11[m], M.top[n],
+               M.top[m], M.bot[n], M.bot[m], M.cl1[jas], M.cl2[jas], M.hwva[jas]);
 }
+
+// calc_condsat (gwf-npf.f90:1950-2037), upper triangle, no THICKSTRT (sat = 1)
+__global__ void condsat_kernel(int njas, const int *__restrict__ conn_n,
+                               const int *__restrict__ conn_m, ModelView M,
+                               double *__restrict__ condsat) {
+  for (int jj = blockIdx.x * blockDim.x + threadIdx.x; jj < njas; jj += gridDim.x * blockDim.x) {
+    const int n = conn_n[jj], m = conn_m[jj];
+    const int ihc = M.ihc[jj];
+    const double topn = M.top[n], botn = M.bot[n], topm = M.top[m], botm = M.bot[m];
+    double csat;
+    if (ihc == 0)
+      csat = vcond(1, 1, 1, 1, 1, 1, 1.0, botn, botm, M.k33[n], M.k33[m], 1.0, 1.0, topn, topm,
+                   botn, botm, M.hwva[jj]);
+    else
+      csat = hcond(1, 1, 1, 1, 0, ihc, M.o.icellavg, 1.0, topn, topm, 1.0, 1.0, M.k11[n],
+                   M.k11[m], topn, topm, botn, botm, M.cl1[jj], M.cl2[jj], M.hwva[jj]);
+    condsat[jj] = csat;
+  }
+}
+
+__global__ void slot_condsat_kernel(long long nslots, const int *__restrict__ slot_conn,
+                                    const double *__restrict__ condsat,
+                                    double *__restrict__ slot_condsat) {
+  for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < nslots;
+       s += (long long)gridDim.x * blockDim.x) {
+    const int c = slot_conn[s];
+    slot_condsat[s] = (c >= 0) ? condsat[c >> 1] : 0.0;
+  }
+}
+
+// npf_cf (gwf-npf.f90:444-470) + thksat (:775-794)
+__global__ void npf_cf_kernel(ModelView M, const double *__restrict__ h, double *__restrict__ sat) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < M.n; r += gridDim.x * blockDim.x) {
+    if (M.icelltype[r] != 0) {
+      double satn;
+      if (M.ibound[r] == 0) {
+        satn = 0.0;
+      } else {
+        const double hn = h[r];
+        if (hn >= M.top[r])
+          satn = 1.0;
+        else
+          satn = (hn - M.bot[r]) / (M.top[r] - M.bot[r]);
+        if (M.o.inewton != 0) satn = sQuadraticSaturation(M.top[r], M.bot[r], hn, M.o.satomega);
+      }
+      sat[r] = satn;
+    }
+  }
+}
+
+// ---- boundary packages: all bounds of all packages concatenated -------------
+struct BndView {
+  int nb;
+  const unsigned char *type;
+  const unsigned char *flag;  // WEL: iflowred
+  const int *node;            // final numbering
+  const double *b1, *b2, *b3, *fred;
+  double *hcof, *rhs, *simvals, *ratein, *rateout;
+};
+
+// *_cf of WEL/RIV/RCH/GHB/DRN (gwf-wel.f90:296-332, gwf-riv.f90:270-299, gwf-rch.f90:303-353,
+// gwf-ghb.f90:245-265, gwf-drn.f90:340-373 with drndepth = 0); CHD has no cf terms
+__global__ void bnd_cf_kernel(BndView B, ModelView M, const double *__restrict__ x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B.nb; i += gridDim.x * blockDim.x) {
+    const int node = B.node[i];
+    const int ib = M.ibound[node];
+    double hcof = 0.0, rhs = 0.0;
+    switch (B.type[i]) {
+      case MF6GPU_PKG_WEL:
+        if (ib > 0) {
+          double q = B.b1[i];
+          if (B.flag[i] != 0 && q < 0.0 && M.icelltype[node] != 0) {
+            double tp = M.top[node];
+            const double bt = M.bot[node], thick = tp - bt;
+            tp = bt + B.fred[i] * thick;
+            q = q * sQSaturation(tp, bt, x[node]);
+          }
+          rhs = -q;
+        }
+        break;
+      case MF6GPU_PKG_RIV:
+        if (ib > 0) {
+          const double hriv = B.b1[i], criv = B.b2[i], rbot = B.b3[i];
+          if (x[node] <= rbot) {
+            rhs = -criv * (hriv - rbot);
+            hcof = 0.0;
+          } else {
+            rhs = -criv * hriv;
+            hcof = -criv;
+          }
+        }
+        break;
+      case MF6GPU_PKG_RCH:
+        rhs = -B.b1[i] * M.area[node];
+        if (ib <= 0) rhs = 0.0;
+        break;
+      case MF6GPU_PKG_GHB:
+        if (ib > 0) {
+          hcof = -B.b2[i];
+          rhs = -B.b2[i] * B.b1[i];
+        }
+        break;
+      case MF6GPU_PKG_DRN:
+        if (ib > 0) {
+          const double cdrn = B.b2[i], drnbot = B.b1[i];
+          const double fact = (x[node] <= drnbot) ? 0.0 : 1.0;
+          rhs = -fact * cdrn * drnbot;
+          hcof = -fact * cdrn;
+        }
+        break;
+      default:
+        break;
+    }
+    B.hcof[i] = hcof;
+    B.rhs[i] = rhs;
+  }
+}
+
+// bnd_fc / bnd_fn / bnd_cq scatter: one thread per DISTINCT node walks that
+// node's bounds in (package, bound) order -> same accumulation order as the
+// reference's package loop, no atomics.
+// mode 0: bnd_fc (BoundaryPackage.f90:453-472) ; 1: wel_fn (gwf-wel.f90:378-424) ;
+// mode 2: bnd_cq_simrate (:583-619)
+__global__ void bnd_scatter_kernel(int nseg, const int *__restrict__ seg_node,
+                                   const int *__restrict__ seg_ptr, const int *__restrict__ seg_idx,
+                                   BndView B, ModelView M, const double *__restrict__ x,
+                                   double *__restrict__ val, double *__restrict__ rhsv,
+                                   double *__restrict__ flowja, int mode) {
+  for (int sidx = blockIdx.x * blockDim.x + threadIdx.x; sidx < nseg; sidx += gridDim.x * blockDim.x) {
+    const int node = seg_node[sidx];
+    const long long dslot = (long long)M.slice_ptr[node >> 5] + (node & 31);
+    const int ib = M.ibound[node];
+    if (mode == 0) {
+      double diag = val[dslot], r = rhsv[node];
+      for (int e = seg_ptr[sidx]; e < seg_ptr[sidx + 1]; e++) {
+        const int i = seg_idx[e];
+        if (B.type[i] == MF6GPU_PKG_CHD) continue;  // chd_fc is a no-op (gwf-chd.f90:238-246)
+        r = r + B.rhs[i];
+        diag = diag + B.hcof[i];
+      }
+      val[dslot] = diag;
+      rhsv[node] = r;
+    } else if (mode == 1) {
+      if (ib <= 0) continue;
+      double diag = val[dslot], r = rhsv[node];
+      for (int e = seg_ptr[sidx]; e < seg_ptr[sidx + 1]; e++) {
+        const int i = seg_idx[e];
+        if (B.type[i] != MF6GPU_PKG_WEL) continue;
+        if (B.flag[i] != 0 && M.icelltype[node] != 0) {
+          const double q = -B.rhs[i];
+          if (q < 0.0) {
+            double tp = M.top[node];
+            const double bt = M.bot[node], thick = tp - bt;
+            tp = bt + B.fred[i] * thick;
+            double drterm = sQSaturationDerivative(tp, bt, x[node]);
+            drterm = drterm * B.b1[i];
+            diag = diag + drterm;
+            r = r + drterm * x[node];
+          }
+        }
+      }
+      val[dslot] = diag;
+      rhsv[node] = r;
+    } else {
+      double fd = flowja[dslot];
+      for (int e = seg_ptr[sidx]; e < seg_ptr[sidx + 1]; e++) {
+        const int i = seg_idx[e];
+        if (B.type[i] == MF6GPU_PKG_CHD) continue;
+        double rrate = 0.0;
+        if (ib > 0) rrate = B.hcof[i] * x[node] - B.rhs[i];
+        fd = fd + rrate;
+        B.simvals[i] = rrate;
+      }
+      flowja[dslot] = fd;
+    }
+  }
+}
+
+// chd_ad (gwf-chd.f90:175-197): x(node) = head ; xold(node) = x(node)
+__global__ void chd_ad_kernel(BndView B, double *__restrict__ x, double *__restrict__ xold) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B.nb; i += gridDim.x * blockDim.x) {
+    if (B.type[i] != MF6GPU_PKG_CHD) continue;
+    const int node = B.node[i];
+    x[node] = B.b1[i];
+    xold[node] = B.b1[i];
+  }
+}
+
+// chd_rp (gwf-chd.f90:143-155): ibound(node) = -ibcnum
+__global__ void chd_ibound_kernel(BndView B, const int *__restrict__ pkgid, int *__restrict__ ibound) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B.nb; i += gridDim.x * blockDim.x)
+    if (B.type[i] == MF6GPU_PKG_CHD) ibound[B.node[i]] = -(pkgid[i] + 1);
+}
+
+// calc_chd_rate (gwf-chd.f90:264-320)
+__global__ void chd_rate_kernel(BndView B, ModelView M, double *__restrict__ flowja) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B.nb; i += gridDim.x * blockDim.x) {
+    if (B.type[i] != MF6GPU_PKG_CHD) continue;
+    const int node = B.node[i];
+    const long long base = (long long)M.slice_ptr[node >> 5] + (node & 31);
+    const int len = M.rowlen[node];
+    double rate = 0.0, ratein = 0.0, rateout = 0.0;
+    for (int k = 1; k < len; k++) {
+      const double q = flowja[base + 32LL * k];
+      rate = rate - q;
+      const int n2 = M.col[base + 32LL * k];
+      if (M.ibound[n2] > 0) {
+        if (q < 0.0)
+          ratein = ratein - q;
+        else
+          rateout = rateout + q;
+      }
+    }
+    B.rhs[i] = -rate;
+    B.hcof[i] = 0.0;
+    B.simvals[i] = rate;
+    B.ratein[i] = ratein;
+    B.rateout[i] = rateout;
+    flowja[base] = flowja[base] + rate;
+  }
+}
+
+// ---- sln_reset + npf_fc + sto_fc, one thread per row --------------------------
+template <bool CONFINED>
+__global__ void __launch_bounds__(kBlock)
+assemble_rows_kernel(ModelView M, const double *__restrict__ h, const double *__restrict__ hold,
+                     const double *__restrict__ sat, double *__restrict__ val,
+                     double *__restrict__ rhsv, int transient, double tled) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < M.n; r += gridDim.x * blockDim.x) {
+    const int len = M.rowlen[r];
+    const long long base = (long long)M.slice_ptr[r >> 5] + (r & 31);
+    const int ibr = M.ibound[r];
+    double diag = 0.0, rhs = 0.0;
+    for (int k = 1; k < len; k++) {
+      const long long slot = base + 32LL * k;
+      const int c = __ldg(M.col + slot);
+      const double csat = __ldg(M.slot_condsat + slot);
+      double cond;
+      if (CONFINED) {
+        cond = (ibr == 0 || M.ibound[c] == 0) ? 0.0 : csat;
+        val[slot] = cond;
+        diag = diag + (-cond);
+      } else {
+        const int conn = __ldg(M.slot_conn + slot);
+        const int up = conn & 1, jas = conn >> 1;
+        cond = conn_cond(M, r, c, up, jas, csat, h, sat);
+        bool perched = false;
+        if (M.o.iperched != 0 && M.ihc[jas] == 0) {
+          const int m = up ? c : r;  // lower cell of the vertical pair has the higher index
+          if (M.icelltype[m] != 0 && h[m] < M.top[m]) perched = true;
+        }
+        if (perched) {  // gwf-npf.f90:523-540
+          const int n = up ? r : c;
+          if (up) {
+            rhs = rhs - cond * M.bot[n];
+            diag = diag + (-cond);
+            val[slot] = 0.0;
+          } else {
+            val[slot] = cond;
+            rhs = rhs + cond * M.bot[n];
+          }
+        } else {
+          val[slot] = cond;
+          diag = diag + (-cond);
+        }
+      }
+    }
+    // sto_fc (gwf-sto.f90:226-345)
+    if (transient && ibr >= 1) {
+      const double tp = M.top[r], bt = M.bot[r];
+      const int icv = M.iconvert[r];
+      double snold = 1.0, snnew = 1.0;
+      if (icv != 0) {
+        snold = sQuadraticSaturation(tp, bt, hold[r], M.o.satomega);
+        snnew = sQuadraticSaturation(tp, bt, h[r], M.o.satomega);
+      }
+      const double sc1 = SsCapacity(M.o.istor_coef, tp, bt, M.area[r], M.ss[r]);
+      const double rho1 = sc1 * tled;
+      double aterm, rhsterm, rate;
+      SsTerms(icv, M.o.iorig_ss, M.o.iconf_ss, tp, bt, rho1, rho1, snnew, snold, h[r], hold[r],
+              aterm, rhsterm, rate);
+      diag = diag + aterm;
+      rhs = rhs + rhsterm;
+      if (icv != 0) {
+        rhsterm = 0.0;
+        const double sc2 = M.sy[r] * M.area[r];
+        const double rho2 = sc2 * tled;
+        SyTerms(tp, bt, rho2, rho2, snnew, snold, aterm, rhsterm, rate);
+        diag = diag + aterm;
+        rhs = rhs + rhsterm;
+      }
+    }
+    val[base] = diag;
+    rhsv[r] = rhs;
+  }
+}
+
+// ---- npf_fn + sto_fn, one thread per row ----------------------------------------
+__global__ void __launch_bounds__(kBlock)
+newton_rows_kernel(ModelView M, const double *__restrict__ h, double *__restrict__ val,
+                   double *__restrict__ rhsv, int transient, double tled) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < M.n; r += gridDim.x * blockDim.x) {
+    const int len = M.rowlen[r];
+    const long long base = (long long)M.slice_ptr[r >> 5] + (r & 31);
+    const int ibr = M.ibound[r];
+    double diag = val[base], rhs = rhsv[r];
+    for (int k = 1; k < len; k++) {
+      const long long slot = base + 32LL * k;
+      const int c = M.col[slot];
+      const int conn = M.slot_conn[slot];
+      const int up = conn & 1, jas = conn >> 1;
+      const int ihc = M.ihc[jas];
+      if (ihc == 0 && M.o.ivarcv == 0) continue;
+      const int n = up ? r : c, m = up ? c : r;
+      int iups = m;
+      if (h[m] < h[n]) iups = n;
+      const int idn = (iups == n) ? m : n;
+      if (M.icelltype[iups] == 0) continue;
+      double topup = M.top[iups], botup = M.bot[iups];
+      if (ihc == 2) {
+        topup = fmin(M.top[n], M.top[m]);
+        botup = fmax(M.bot[n], M.bot[m]);
+      }
+      const double cond = M.condsat[jas];
+      const double consterm = -cond * (h[iups] - h[idn]);
+      const double derv = sQuadraticSaturationDerivative(topup, botup, h[iups], M.o.satomega);
+      if (iups == n) {
+        const double term = consterm * derv;
+        if (up) {  // this row is n
+          rhs = rhs + term * h[n];
+          diag = diag + term;
+        } else {   // this row is m
+          rhs = rhs - term * h[n];
+          if (ibr > 0) val[slot] = val[slot] + (-term);
+        }
+      } else {
+        const double term = -consterm * derv;
+        if (up) {
+          rhs = rhs + term * h[m];
+          if (ibr > 0) val[slot] = val[slot] + term;
+        } else {
+          rhs = rhs - term * h[m];
+          diag = diag + (-term);
+        }
+      }
+    }
+    // sto_fn (gwf-sto.f90:353-439); the smoothing calls there use the default eps = 1e-6
+    if (transient && M.o.insto && ibr > 0) {
+      const double tp = M.top[r], bt = M.bot[r], tthk = tp - bt, hh = h[r];
+      const double snnew = sQuadraticSaturation(tp, bt, hh, 1.0e-6);
+      const double sc1 = SsCapacity(M.o.istor_coef, tp, bt, M.area[r], M.ss[r]);
+      const double sc2 = M.sy[r] * M.area[r];
+      const double rho1 = sc1 * tled, rho2 = sc2 * tled;
+      if (M.iconvert[r] != 0) {
+        const double derv = sQuadraticSaturationDerivative(tp, bt, hh, 1.0e-6);
+        double drterm;
+        if (M.o.iconf_ss == 0) {
+          if (M.o.iorig_ss == 0)
+            drterm = -rho1 * derv * (hh - bt) + rho1 * tthk * snnew * derv;
+          else
+            drterm = -(rho1 * derv * hh);
+          diag = diag + drterm;
+          rhs = rhs + drterm * hh;
+        }
+        if (snnew < 1.0) {
+          if (snnew > 0.0) {
+            const double rterm = -rho2 * tthk * snnew;
+            drterm = -rho2 * tthk * derv;
+            diag = diag + (drterm + rho2);
+            rhs = rhs - rterm + drterm * hh + rho2 * bt;
+          }
+        }
+      }
+    }
+    val[base] = diag;
+    rhsv[r] = rhs;
+  }
+}
+
+// ---- pre-solve fix-ups of sln_ls (NumericalSolution.f90:2434-2478) -----------
+__global__ void __launch_bounds__(kBlock)
+ls_fixup_kernel(ModelView M, const double *__restrict__ x, double *__restrict__ xtemp,
+                double *__restrict__ val, double *__restrict__ rhsv, int isymmetric) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < M.n; r += gridDim.x * blockDim.x) {
+    const int len = M.rowlen[r];
+    const long long base = (long long)M.slice_ptr[r >> 5] + (r & 31);
+    const double xr = x[r];
+    xtemp[r] = xr;
+    if (M.ibound[r] > 0) {
+      double rhs = rhsv[r];
+      bool touched = false;
+      if (fabs(val[base]) < 1.0e-15) {
+        val[base] = -1.0;
+        rhs = rhs + (-1.0) * xr;
+        touched = true;
+      }
+      if (isymmetric) {
+        for (int k = 1; k < len; k++) {
+          const long long slot = base + 32LL * k;
+          const int c = M.col[slot];
+          if (M.ibound[c] < 0) {
+            rhs = rhs - (val[slot] * x[c]);
+            val[slot] = 0.0;
+            touched = true;
+          }
+        }
+      }
+      if (touched) rhsv[r] = rhs;
+    } else {
+      val[base] = 1.0;
+      for (int k = 1; k < len; k++) val[base + 32LL * k] = 0.0;
+      rhsv[r] = xr;
+    }
+  }
+}
+
+// NB: the reference walks a row in CSR order (ascending column) when it moves
+// constant-head columns to the right-hand side; the slots are in that order too.
+
+// ---- outer-iteration vector kernels ---------------------------------------------
+struct OuterState {
+  double hncg;      // signed largest |x - xtemp|
+  int loc;          // device row
+  int nur_flag;
+  double dxold_max;
+  double ptc_max;   // max |r| / volume
+  double l2;        // sum r^2
+  double rin, rout;
+};
+
+// sln_get_dxmax (:3122-3153)
+__global__ void __launch_bounds__(kBlock)
+dxmax_kernel(int n, const double *__restrict__ x, const double *__restrict__ xtemp,
+             const int *__restrict__ ibound, const int *__restrict__ ord, MaxLoc *__restrict__ pm,
+             unsigned int *ticket, OuterState *os) {
+  __shared__ MaxLoc shm[8];
+  __shared__ bool last;
+  MaxLoc m = maxloc_init();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (ibound[i] < 1) continue;
+    const double hdif = x[i] - xtemp[i];
+    const double a = fabs(hdif);
+    if (a >= m.a && a > 0.0) maxloc_take(m, hdif, ord ? ord[i] : i, i);
+  }
+  m = block_maxloc(m, shm);
+  if (threadIdx.x == 0) pm[blockIdx.x] = m;
+  if (last_block(ticket, &last)) {
+    MaxLoc g = maxloc_init();
+    for (int i = threadIdx.x; i < gridDim.x; i += blockDim.x) maxloc_merge(g, pm[i]);
+    g = block_maxloc(g, shm);
+    if (threadIdx.x == 0) {
+      os->hncg = g.v;
+      os->loc = g.idx;
+    }
+  }
+}
+
+// sln_calcdx (:2912-2932)
+__global__ void calcdx_kernel(int n, const int *__restrict__ ibound, const double *__restrict__ x,
+                              const double *__restrict__ xtemp, double *__restrict__ dx) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    dx[i] = (ibound[i] < 1) ? 0.0 : x[i] - xtemp[i];
+}
+
+// sln_underrelax simple / cooley (:3010-3064): x = xtemp + f * (x - xtemp)
+__global__ void relax_kernel(int n, const int *__restrict__ ibound, double *__restrict__ x,
+                             const double *__restrict__ xtemp, double *__restrict__ dxold, double f) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (ibound[i] < 1) continue;
+    const double delx = x[i] - xtemp[i];
+    dxold[i] = delx;
+    x[i] = xtemp[i] + f * delx;
+  }
+}
+
+// sln_underrelax delta-bar-delta (:3066-3112)
+__global__ void dbd_kernel(int n, const int *__restrict__ ibound, double *__restrict__ x,
+                           const double *__restrict__ xtemp, double *__restrict__ dxold,
+                           double *__restrict__ wsave, double *__restrict__ hchold,
+                           double *__restrict__ deold, int kiter, double theta, double akappa,
+                           double gamma, double amomentum) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (ibound[i] < 1) continue;
+    double delx = x[i] - xtemp[i];
+    double ws = wsave[i], hc = hchold[i], de = deold[i];
+    if (kiter == 1) {
+      ws = 1.0;
+      hc = 1.0e-20;
+      de = 0.0;
+    }
+    double ww;
+    if (de * delx < 0.0)
+      ww = theta * ws;
+    else
+      ww = ws + akappa;
+    if (ww > 1.0) ww = 1.0;
+    wsave[i] = ww;
+    if (kiter == 1)
+      hc = delx;
+    else
+      hc = (1.0 - gamma) * delx + gamma * hc;
+    hchold[i] = hc;
+    deold[i] = delx;
+    dxold[i] = delx;
+    double amom = 0.0;
+    if (kiter > 4) amom = amomentum;
+    delx = delx * ww + amom * hc;
+    x[i] = xtemp[i] + delx;
+  }
+}
+
+// npf_nur (gwf-npf.f90:705-741)
+__global__ void nur_kernel(ModelView M, const int *__restrict__ ibotnode, double *__restrict__ x,
+                           const double *__restrict__ xtemp, double *__restrict__ dx,
+                           OuterState *os) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < M.n; r += gridDim.x * blockDim.x) {
+    if (M.ibound[r] < 1) continue;
+    if (M.icelltype[r] > 0) {
+      const double botm = M.bot[ibotnode[r]];
+      if (x[r] < botm) {
+        os->nur_flag = 1;
+        const double xx = xtemp[r] * (1.0 - 0.9) + botm * 0.9;
+        x[r] = xx;
+        dx[r] = 0.0;
+      }
+    }
+  }
+}
+
+// max |a| (sln_maxval) -> os->dxold_max
+__global__ void __launch_bounds__(kBlock)
+absmax_kernel(int n, const double *__restrict__ a, double *__restrict__ partial,
+              unsigned int *ticket, OuterState *os) {
+  __shared__ double sh[8];
+  __shared__ bool last;
+  double m = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    m = fmax(m, fabs(a[i]));
+  m = block_max(m, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = m;
+  if (last_block(ticket, &last)) {
+    double r = 0.0;
+    for (int i = threadIdx.x; i < gridDim.x; i += blockDim.x) r = fmax(r, partial[i]);
+    r = block_max(r, sh);
+    if (threadIdx.x == 0) os->dxold_max = r;
+  }
+}
+
+// sln_calc_residual (:2966-2982) + gwf_ptc (gwf.f90:625-687) + l2 norm:
+// r = A x - b (0 for inactive) ; max |r| / V ; sum r^2
+__global__ void __launch_bounds__(kBlock)
+ptc_resid_kernel(ModelView M, const double *__restrict__ val, const double *__restrict__ x,
+                 const double *__restrict__ rhsv, double *__restrict__ partial,
+                 unsigned int *ticket, OuterState *os) {
+  __shared__ double sh[8];
+  __shared__ bool last;
+  double mx = 0.0, ssq = 0.0;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < M.n; r += gridDim.x * blockDim.x) {
+    double t = sell_row_dot(r, M.slice_ptr, M.rowlen, M.col, val, x);
+    t = t + (-1.0) * rhsv[r];
+    if (M.ibound[r] < 1) t = 0.0;
+    ssq += t * t;
+    if (M.ibound[r] >= 1) {
+      const double v = M.area[r] * (M.top[r] - M.bot[r]);
+      mx = fmax(mx, fabs(t) / v);
+    }
+  }
+  mx = block_max(mx, sh);
+  ssq = block_sum(ssq, sh);
+  if (threadIdx.x == 0) {
+    partial[2 * blockIdx.x] = mx;
+    partial[2 * blockIdx.x + 1] = ssq;
+  }
+  if (last_block(ticket, &last)) {
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+      a = fmax(a, partial[2 * i]);
+      b += partial[2 * i + 1];
+    }
+    a = block_max(a, sh);
+    b = block_sum(b, sh);
+    if (threadIdx.x == 0) {
+      os->ptc_max = a;
+      os->l2 = b;
+    }
+  }
+}
+
+// PTC terms (:2556-2565): diag -= ptcval ; rhs -= ptcval * x   for active rows
+__global__ void ptc_apply_kernel(ModelView M, double *__restrict__ val, double *__restrict__ rhsv,
+                                 const double *__restrict__ x, double ptcval) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < M.n; r += gridDim.x * blockDim.x) {
+    if (M.ibound[r] > 0) {
+      const long long base = (long long)M.slice_ptr[r >> 5] + (r & 31);
+      val[base] = val[base] + (-ptcval);
+      rhsv[r] = rhsv[r] - ptcval * x[r];
+    }
+  }
+}
+
+// ---- flows: npf_cq/qcalc (gwf-npf.f90:745-865) + sto_cq (gwf-sto.f90:447-564) ----
+__global__ void __launch_bounds__(kBlock)
+flow_rows_kernel(ModelView M, const double *__restrict__ h, const double *__restrict__ hold,
+                 const double *__restrict__ sat, double *__restrict__ flowja,
+                 double *__restrict__ strgss, double *__restrict__ strgsy, int transient,
+                 double tled) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < M.n; r += gridDim.x * blockDim.x) {
+    const int len = M.rowlen[r];
+    const long long base = (long long)M.slice_ptr[r >> 5] + (r & 31);
+    const int ibr = M.ibound[r];
+    for (int k = 1; k < len; k++) {
+      const long long slot = base + 32LL * k;
+      const int c = M.col[slot];
+      const int conn = M.slot_conn[slot];
+      const int up = conn & 1, jas = conn >> 1;
+      const double csat = M.slot_condsat[slot];
+      double cond;
+      if (M.o.all_confined)
+        cond = (ibr == 0 || M.ibound[c] == 0) ? 0.0 : csat;
+      else
+        cond = conn_cond(M, r, c, up, jas, csat, h, sat);
+      const int n = up ? r : c, m = up ? c : r;
+      double hn = h[n], hm = h[m];
+      if (M.o.iperched != 0 && M.ihc[jas] == 0) {
+        // qcalc is called with n < m, so only its "else" branch applies (:855-858)
+        if (M.icelltype[m] != 0)
+          if (hm < M.top[m]) hm = M.bot[n];
+      }
+      const double qnm = cond * (hm - hn);  // flow into n
+      flowja[slot] = up ? qnm : -qnm;
+    }
+    double fd = 0.0, rss = 0.0, rsy = 0.0;
+    if (transient && ibr > 0) {
+      const double tp = M.top[r], bt = M.bot[r];
+      const int icv = M.iconvert[r];
+      double snold = 1.0, snnew = 1.0;
+      if (icv != 0) {
+        snold = sQuadraticSaturation(tp, bt, hold[r], M.o.satomega);
+        snnew = sQuadraticSaturation(tp, bt, h[r], M.o.satomega);
+      }
+      const double sc1 = SsCapacity(M.o.istor_coef, tp, bt, M.area[r], M.ss[r]);
+      const double rho1 = sc1 * tled;
+      double aterm, rhsterm, rate;
+      SsTerms(icv, M.o.iorig_ss, M.o.iconf_ss, tp, bt, rho1, rho1, snnew, snold, h[r], hold[r],
+              aterm, rhsterm, rate);
+      rss = rate;
+      fd = fd + rate;
+      rate = 0.0;
+      if (icv != 0) {
+        const double sc2 = M.sy[r] * M.area[r];
+        const double rho2 = sc2 * tled;
+        SyTerms(tp, bt, rho2, rho2, snnew, snold, aterm, rhsterm, rate);
+      }
+      rsy = rate;
+      fd = fd + rate;
+    }
+    flowja[base] = fd;
+    if (strgss) {
+      strgss[r] = rss;
+      strgsy[r] = rsy;
+    }
+  }
+}
+
+// csr_diagsum (Sparse.f90:262-281)
+__global__ void diagsum_kernel(ModelView M, double *__restrict__ flowja) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < M.n; r += gridDim.x * blockDim.x) {
+    const int len = M.rowlen[r];
+    const long long base = (long long)M.slice_ptr[r >> 5] + (r & 31);
+    double d = flowja[base];
+    for (int k = 1; k < len; k++) d = d + flowja[base + 32LL * k];
+    flowja[base] = d;
+  }
+}
+
+// rate_accumulator (Budget.f90:631-648) over a[i0:i1)
+__global__ void __launch_bounds__(kBlock)
+posneg_kernel(int i0, int i1, const double *__restrict__ a, double *__restrict__ partial,
+              unsigned int *ticket, OuterState *os) {
+  __shared__ double sh[8];
+  __shared__ bool last;
+  double rin = 0.0, rout = 0.0;
+  for (int i = i0 + blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += gridDim.x * blockDim.x) {
+    const double f = a[i];
+    if (f < 0.0)
+      rout = rout - f;
+    else
+      rin = rin + f;
+  }
+  rin = block_sum(rin, sh);
+  rout = block_sum(rout, sh);
+  if (threadIdx.x == 0) {
+    partial[2 * blockIdx.x] = rin;
+    partial[2 * blockIdx.x + 1] = rout;
+  }
+  if (last_block(ticket, &last)) {
+    double a0 = 0.0, b0 = 0.0;
+    for (int i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+      a0 += partial[2 * i];
+      b0 += partial[2 * i + 1];
+    }
+    a0 = block_sum(a0, sh);
+    b0 = block_sum(b0, sh);
+    if (threadIdx.x == 0) {
+      os->rin = a0;
+      os->rout = b0;
+    }
+  }
+}
+
+__global__ void copy_d_kernel(int n, const double *__restrict__ a, double *__restrict__ b) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    b[i] = a[i];
+}
+
+__global__ void copy_i_kernel(int n, const int *__restrict__ a, int *__restrict__ b) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    b[i] = a[i];
+}
+
+}  // namespace mf6
+
+using namespace mf6;
+
+struct PkgRange {
+  int type, i0, i1;
+};
+
+struct mf6gpu_solution {
+  mf6gpu_matrix *A = nullptr;
+  mf6gpu_solver *S = nullptr;
+  int n = 0, nja = 0, njas = 0;
+  ModelOpts o{};
+  mf6gpu_sln_settings ss{};
+  int isymmetric = 0;
+  cudaStream_t stream = 0;
+  DevBuf<double> top, bot, area, k11, k33, ssv, syv;
+  DevBuf<double> x, xold, sat, rhs, xtemp, dxold, wsave, hchold, deold, strgss, strgsy;
+  DevBuf<int> icelltype, ibound, ibound0, iconvert, ibotnode;
+  DevBuf<int> slot_conn;
+  DevBuf<double> slot_condsat, flowja;
+  DevBuf<double> condsat, cl1, cl2, hwva;
+  DevBuf<int> ihc;
+  DevBuf<double> hstage;  // [max(n, nja)] staging in original order
+  // packages (concatenated)
+  int nb = 0, nseg = 0;
+  std::vector<PkgRange> ranges;
+  DevBuf<unsigned char> b_type, b_flag;
+  DevBuf<int> b_node, b_pkg;
+  DevBuf<double> b_b1, b_b2, b_b3, b_fred, b_hcof, b_rhs, b_sim, b_rin, b_rout;
+  DevBuf<int> seg_node, seg_ptr, seg_idx;
+  // scratch
+  DevBuf<double> partial;
+  DevBuf<MaxLoc> pm;
+  DevBuf<unsigned int> tickets;
+  DevBuf<OuterState> os;
+  PinnedBuf<OuterState> h_os;
+  // outer state
+  double relaxold = 1.0, bigchold = 0.0, bigch = 0.0;
+  double ptcdel = 0.0, l2norm0 = 0.0;
+  double delt = 1.0;
+  int iss = 1;
+  int icnvg = 0;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  std::vector<int> h_conn_jas;  // csr position -> jas (original), for get_condsat ordering
+
+  ModelView view() const {
+    ModelView M;
+    M.n = n;
+    M.slice_ptr = A->slice_ptr.p;
+    M.rowlen = A->rowlen.p;
+    M.col = A->col.p;
+    M.slot_conn = slot_conn.p;
+    M.slot_condsat = slot_condsat.p;
+    M.condsat = condsat.p;
+    M.cl1 = cl1.p;
+    M.cl2 = cl2.p;
+    M.hwva = hwva.p;
+    M.ihc = ihc.p;
+    M.top = top.p;
+    M.bot = bot.p;
+    M.area = area.p;
+    M.k11 = k11.p;
+    M.k33 = k33.p;
+    M.ss = ssv.p;
+    M.sy = syv.p;
+    M.icelltype = icelltype.p;
+    M.ibound = ibound.p;
+    M.iconvert = iconvert.p;
+    M.o = o;
+    return M;
+  }
+  BndView bview() const {
+    BndView B;
+    B.nb = nb;
+    B.type = b_type.p;
+    B.flag = b_flag.p;
+    B.node = b_node.p;
+    B.b1 = b_b1.p;
+    B.b2 = b_b2.p;
+    B.b3 = b_b3.p;
+    B.fred = b_fred.p;
+    B.hcof = b_hcof.p;
+    B.rhs = b_rhs.p;
+    B.simvals = b_sim.p;
+    B.ratein = b_rin.p;
+    B.rateout = b_rout.p;
+    return B;
+  }
+  OuterState fetch_os() {
+    MF6_CK(cudaMemcpyAsync(h_os.p, os.p, sizeof(OuterState), cudaMemcpyDeviceToHost, stream));
+    MF6_CK(cudaStreamSynchronize(stream));
+    return *h_os.p;
+  }
+  void buildsystem(int inewton);
+  void calc_ptc(int &iptc, double &ptcf);
+  void ls_fixups(int kiter, int kstp, int kper, int iptc, double ptcf);
+  int solve_outer(int kiter, int kstp, int kper, double &hncg, int &lrch, double &tf, double &tl);
+  void posneg(const double *a, int i0, int i1, double &rin, double &rout);
+};
+
+template <class T>
+static std::vector<T> permuted(const T *src, const std::vector<int> &perm, T dflt) {
+  std::vector<T> out(perm.size(), dflt);
+  if (src)
+    for (size_t r = 0; r < perm.size(); r++) out[r] = src[perm[r]];
+  return out;
+}
+
+// sln_buildsystem (:1941-1991): sln_reset + gwf_cf + gwf_fc [+ Newton terms]
+void mf6gpu_solution::buildsystem(int inewton) {
+  const ModelView M = view();
+  const BndView B = bview();
+  const int G = grid_for(n);
+  const int transient = (iss == 0 && o.insto) ? 1 : 0;
+  const double tled = 1.0 / delt;
+  if (!o.all_confined) npf_cf_kernel<<<G, kBlock, 0, stream>>>(M, x.p, sat.p);
+  if (nb > 0) bnd_cf_kernel<<<grid_for(nb), kBlock, 0, stream>>>(B, M, x.p);
+  if (o.all_confined)
+    assemble_rows_kernel<true><<<G, kBlock, 0, stream>>>(M, x.p, xold.p, sat.p, A->val.p, rhs.p, transient, tled);
+  else
+    assemble_rows_kernel<false><<<G, kBlock, 0, stream>>>(M, x.p, xold.p, sat.p, A->val.p, rhs.p, transient, tled);
+  if (nseg > 0)
+    bnd_scatter_kernel<<<grid_for(nseg), kBlock, 0, stream>>>(nseg, seg_node.p, seg_ptr.p, seg_idx.p, B, M,
+                                                              x.p, A->val.p, rhs.p, flowja.p, 0);
+  if (inewton && o.inewton) {
+    newton_rows_kernel<<<G, kBlock, 0, stream>>>(M, x.p, A->val.p, rhs.p, transient, tled);
+    if (nseg > 0)
+      bnd_scatter_kernel<<<grid_for(nseg), kBlock, 0, stream>>>(nseg, seg_node.p, seg_ptr.p, seg_idx.p, B,
+                                                                M, x.p, A->val.p, rhs.p, flowja.p, 1);
+  }
+  MF6_CK(cudaGetLastError());
+}
+
+// sln_calc_ptc (:2936-2962) + gwf_ptc (gwf.f90:625-687)
+void mf6gpu_solution::calc_ptc(int &iptc, double &ptcf) {
+  iptc = 0;
+  ptcf = 0.0;
+  int iptct = 0;
+  if (iss > 0) iptct = o.inewton;
+  if (iptct > 0) {
+    ptc_resid_kernel<<<grid_for(n), kBlock, 0, stream>>>(view(), A->val.p, x.p, rhs.p, partial.p,
+                                                         tickets.p + 1, os.p);
+    MF6_CK(cudaGetLastError());
+    OuterState h = fetch_os();
+    ptcf = h.ptc_max;
+    if (ptcf == 0.0) ptcf = 1.0 / (delt * 10.0);
+    iptc = 1;
+  }
+}
+
+void mf6gpu_solution::ls_fixups(int kiter, int kstp, int kper, int iptc, double ptcf) {
+  const ModelView M = view();
+  const int G = grid_for(n);
+  ls_fixup_kernel<<<G, kBlock, 0, stream>>>(M, x.p, xtemp.p, A->val.p, rhs.p, isymmetric);
+  MF6_CK(cudaGetLastError());
+  int iallowptc;
+  if (ss.iallowptc < 0)
+    iallowptc = (kper > 1) ? 1 : 0;
+  else
+    iallowptc = ss.iallowptc;
+  int iptct = iptc * iallowptc;
+  double l2norm = 0.0;
+  if (iptct != 0) {
+    ptc_resid_kernel<<<G, kBlock, 0, stream>>>(M, A->val.p, x.p, rhs.p, partial.p, tickets.p + 1, os.p);
+    MF6_CK(cudaGetLastError());
+    l2norm = std::sqrt(fetch_os().l2);
+    if (kiter == 1) {
+      if (kper > 1 || kstp > 1)
+        if (l2norm <= l2norm0) iptc = 0;
+    } else {
+      const double a = l2norm, b = l2norm0;
+      bool same = (a == b) || std::fabs(a - b) <= 100.0 * 2.220446049250313e-16 * std::fmax(std::fabs(a), std::fabs(b));
+      if (same) iptc = 0;
+    }
+  }
+  iptct = iptc * iallowptc;
+  if (iptct != 0) {
+    if (kiter == 1) {
+      ptcdel = 1.0 / ptcf;
+    } else {
+      if (l2norm > 0.0)
+        ptcdel = ptcdel * std::pow(l2norm0 / l2norm, 1.0);
+      else
+        ptcdel = 0.0;
+    }
+    const double ptcval = (ptcdel > 0.0) ? 1.0 / ptcdel : 1.0;
+    ptc_apply_kernel<<<G, kBlock, 0, stream>>>(M, A->val.p, rhs.p, x.p, ptcval);
+    MF6_CK(cudaGetLastError());
+    l2norm0 = l2norm;
+  }
+}
+
+// solve(kiter) (:1482-1837)
+int mf6gpu_solution::solve_outer(int kiter, int kstp, int kper, double &hncg, int &lrch, double &tf,
+                                 double &tl) {
+  const int G = grid_for(n);
+  MF6_CK(cudaEventRecord(ev[0], stream));
+  buildsystem(1);
+  int iptc;
+  double ptcf;
+  calc_ptc(iptc, ptcf);
+  MF6_CK(cudaEventRecord(ev[1], stream));
+  ls_fixups(kiter, kstp, kper, iptc, ptcf);
+  int iter = 0, icnvg_lin = 0;
+  S->solve_device(kiter, kstp, x.p, rhs.p, &iter, &icnvg_lin);
+  MF6_CK(cudaEventRecord(ev[2], stream));
+  dxmax_kernel<<<G, kBlock, 0, stream>>>(n, x.p, xtemp.p, ibound.p, A->ord_ptr(), pm.p, tickets.p, os.p);
+  MF6_CK(cudaGetLastError());
+  OuterState h = fetch_os();
+  float ms0 = 0.f, ms1 = 0.f;
+  MF6_CK(cudaEventElapsedTime(&ms0, ev[0], ev[1]));
+  MF6_CK(cudaEventElapsedTime(&ms1, ev[1], ev[2]));
+  tf += 1e-3 * ms0;
+  tl += 1e-3 * ms1;
+  hncg = h.hncg;
+  lrch = h.loc;
+  icnvg = 0;
+  if (std::fabs(hncg) <= ss.dvclose) icnvg = 1;
+  if (icnvg != 1) {
+    if (ss.nonmeth == 1) {
+      relax_kernel<<<G, kBlock, 0, stream>>>(n, ibound.p, x.p, xtemp.p, dxold.p, ss.gamma);
+    } else if (ss.nonmeth == 2) {
+      double relax;
+      bigch = hncg;
+      if (kiter == 1) {
+        relax = 1.0;
+        relaxold = 1.0;
+        bigchold = hncg;
+      } else {
+        const double es = bigch / (bigchold * relaxold);
+        const double aes = std::fabs(es);
+        if (es < -1.0)
+          relax = 0.5 / aes;
+        else
+          relax = (3.0 + es) / (3.0 + aes);
+      }
+      relaxold = relax;
+      bigchold = (1.0 - ss.gamma) * bigch + ss.gamma * bigchold;
+      if (relax < 1.0) relax_kernel<<<G, kBlock, 0, stream>>>(n, ibound.p, x.p, xtemp.p, dxold.p, relax);
+    } else if (ss.nonmeth == 3) {
+      dbd_kernel<<<G, kBlock, 0, stream>>>(n, ibound.p, x.p, xtemp.p, dxold.p, wsave.p, hchold.p, deold.p,
+                                           kiter, ss.theta, ss.akappa, ss.gamma, ss.amomentum);
+    } else {
+      calcdx_kernel<<<G, kBlock, 0, stream>>>(n, ibound.p, x.p, xtemp.p, dxold.p);
+    }
+    if (o.inewton != 0 && o.inewtonur != 0) {
+      MF6_CK(cudaMemsetAsync(&os.p->nur_flag, 0, sizeof(int), stream));
+      nur_kernel<<<G, kBlock, 0, stream>>>(view(), ibotnode.p, x.p, xtemp.p, dxold.p, os.p);
+      absmax_kernel<<<G, kBlock, 0, stream>>>(n, dxold.p, partial.p, tickets.p + 2, os.p);
+      MF6_CK(cudaGetLastError());
+      OuterState h2 = fetch_os();
+      if (h2.nur_flag != 0) {
+        if (std::fabs(h2.dxold_max) <= ss.dvclose && std::fabs(hncg) <= ss.dvclose) {
+          icnvg = 1;
+          dxmax_kernel<<<G, kBlock, 0, stream>>>(n, x.p, xtemp.p, ibound.p, A->ord_ptr(), pm.p, tickets.p, os.p);
+          OuterState h3 = fetch_os();
+          hncg = h3.hncg;
+          lrch = h3.loc;
+        }
+      }
+    }
+    MF6_CK(cudaGetLastError());
+  }
+  return iter;
+}
+
+void mf6gpu_solution::posneg(const double *a, int i0, int i1, double &rin, double &rout) {
+  rin = rout = 0.0;
+  if (i1 <= i0) return;
+  posneg_kernel<<<grid_for(i1 - i0), kBlock, 0, stream>>>(i0, i1, a, partial.p, tickets.p + 3, os.p);
+  MF6_CK(cudaGetLastError());
+  OuterState h = fetch_os();
+  rin = h.rin;
+  rout = h.rout;
+}
+
+extern "C" {
+
+int mf6gpu_solution_create(const mf6gpu_gwf_model *m, const mf6gpu_sln_settings *sln,
+                           const mf6gpu_ims_settings *ims, mf6gpu_solution **out) {
+  return guard([&] {
+    MF6_REQUIRE(m && sln && ims && out, "solution_create: null argument");
+    MF6_REQUIRE(m->ithickstrt == 0, "solution_create: THICKSTRT is not supported on the GPU path");
+    MF6_REQUIRE(sln->numtrack == 0, "solution_create: BACKTRACKING is not supported on the GPU path");
+    MF6_REQUIRE(m->njas * 2 == m->nja - m->nodes, "solution_create: nja/njas/nodes are inconsistent");
+    MF6_REQUIRE((long long)m->njas < (1LL << 30), "solution_create: too many connections for one GPU");
+    MF6_REQUIRE(!(m->inewton != 0 && ims->ilinmeth == 1),
+                "solution_create: NEWTON needs an asymmetric accelerator (BICGSTAB), cf. NumericalSolution.f90:942-958");
+    auto *s = new mf6gpu_solution();
+    s->n = m->nodes;
+    s->nja = m->nja;
+    s->njas = m->njas;
+    s->ss = *sln;
+    s->isymmetric = (ims->ilinmeth == 1) ? 1 : 0;  // NumericalSolution.f90:914-916
+    if (mf6gpu_matrix_create(m->nodes, m->nja, m->ia, m->ja, m->index_base, ims->gpu_ordering, &s->A) != 0) {
+      const std::string keep = last_error();
+      delete s;
+      throw Error(keep);
+    }
+    try {
+      const int base = m->index_base;
+      const int n = m->nodes, nja = m->nja, njas = m->njas;
+      mf6gpu_matrix *A = s->A;
+      s->stream = A->stream;
+      if (mf6gpu_solver_create(A, ims, 0, &s->S) != 0) throw Error(last_error());
+      const std::vector<int> &perm = A->perm;
+      // options
+      ModelOpts &o = s->o;
+      o.icellavg = m->icellavg;
+      o.inewton = m->inewton;
+      o.inewtonur = m->inewtonur;
+      o.iperched = m->iperched;
+      o.ivarcv = m->ivarcv;
+      o.idewatcv = m->idewatcv;
+      o.insto = m->insto;
+      o.istor_coef = m->istor_coef;
+      o.iconf_ss = m->iconf_ss;
+      o.iorig_ss = m->iorig_ss;
+      o.satomega = (m->inewton > 0) ? 1.0e-6 : 0.0;
+      bool anyconv = false;
+      for (int i = 0; i < n; i++)
+        if (m->icelltype[i] != 0) anyconv = true;
+      o.all_confined = (!anyconv && m->iperched == 0 && m->inewton == 0) ? 1 : 0;
+      // per-cell arrays in final numbering
+      s->top.upload(permuted(m->top, perm, 0.0));
+      s->bot.upload(permuted(m->bot, perm, 0.0));
+      s->area.upload(permuted(m->area, perm, 0.0));
+      s->k11.upload(permuted(m->k11, perm, 0.0));
+      s->k33.upload(permuted(m->k33 ? m->k33 : m->k11, perm, 0.0));
+      s->ssv.upload(permuted(m->ss, perm, 0.0));
+      s->syv.upload(permuted(m->sy, perm, 0.0));
+      s->icelltype.upload(permuted(m->icelltype, perm, 0));
+      s->iconvert.upload(permuted(m->iconvert, perm, 0));
+      s->ibound0.upload(permuted(m->ibound, perm, 1));
+      s->ibound.upload(permuted(m->ibound, perm, 1));
+      {
+        std::vector<int> ib(n);
+        for (int r = 0; r < n; r++) {
+          int o_ = perm[r];
+          int b = m->ibotnode ? m->ibotnode[o_] - base : o_;
+          ib[r] = A->iperm[b];
+        }
+        s->ibotnode.upload(ib);
+      }
+      s->x.upload(permuted(m->strt, perm, 0.0));
+      s->xold.upload(permuted(m->strt, perm, 0.0));
+      {
+        std::vector<double> ones((size_t)n, 1.0);
+        s->sat.upload(ones);
+      }
+      s->rhs.alloc_zero(n);
+      s->xtemp.alloc_zero(n);
+      s->dxold.alloc_zero(n);
+      s->wsave.alloc_zero(n);
+      s->hchold.alloc_zero(n);
+      s->deold.alloc_zero(n);
+      s->strgss.alloc_zero(n);
+      s->strgsy.alloc_zero(n);
+      s->hstage.alloc((size_t)std::max(nja, n));
+      // per-connection arrays (original jas numbering)
+      {
+        std::vector<int> ihc(m->ihc, m->ihc + njas);
+        s->ihc.upload(ihc);
+        s->cl1.upload(std::vector<double>(m->cl1, m->cl1 + njas));
+        s->cl2.upload(std::vector<double>(m->cl2, m->cl2 + njas));
+        s->hwva.upload(std::vector<double>(m->hwva, m->hwva + njas));
+      }
+      // connection endpoints + slot -> connection map
+      std::vector<int> conn_n((size_t)njas, 0), conn_m((size_t)njas, 0);
+      std::vector<int> slot_conn((size_t)A->nslots, -1);
+      std::vector<int> csr2sell((size_t)nja);
+      A->csr2sell.download(csr2sell.data(), (size_t)nja);
+      s->h_conn_jas.assign((size_t)nja, -1);
+      for (int v = 0; v < n; v++) {
+        const int i0 = m->ia[v] - base, i1 = m->ia[v + 1] - base;
+        for (int p = i0 + 1; p < i1; p++) {
+          const int u = m->ja[p] - base;
+          const int jj = m->jas[p] - base;
+          MF6_REQUIRE(jj >= 0 && jj < njas, "solution_create: jas out of range");
+          s->h_conn_jas[p] = jj;
+          const int up = (u > v) ? 1 : 0;
+          if (up) {
+            conn_n[jj] = A->iperm[v];
+            conn_m[jj] = A->iperm[u];
+          }
+          slot_conn[csr2sell[p]] = (jj << 1) | up;
+        }
+      }
+      s->slot_conn.upload(slot_conn);
+      s->condsat.alloc_zero((size_t)std::max(njas, 1));
+      s->slot_condsat.alloc_zero((size_t)A->nslots);
+      s->flowja.alloc_zero((size_t)A->nslots);
+      s->partial.alloc_zero(4 * (size_t)kMaxBlocks);
+      s->pm.alloc_zero((size_t)kMaxBlocks);
+      s->tickets.alloc_zero(8);
+      s->os.alloc_zero(1);
+      s->h_os.alloc(1);
+      for (auto &e : s->ev) MF6_CK(cudaEventCreate(&e));
+      if (njas > 0) {
+        DevBuf<int> dn, dm;
+        dn.upload(conn_n);
+        dm.upload(conn_m);
+        condsat_kernel<<<grid_for(njas), kBlock, 0, s->stream>>>(njas, dn.p, dm.p, s->view(), s->condsat.p);
+        slot_condsat_kernel<<<grid_for(A->nslots), kBlock, 0, s->stream>>>(A->nslots, s->slot_conn.p,
+                                                                           s->condsat.p, s->slot_condsat.p);
+        MF6_CK(cudaGetLastError());
+        MF6_CK(cudaStreamSynchronize(s->stream));
+      }
+    } catch (const std::exception &e) {
+      const std::string keep = e.what();
+      mf6gpu_solution_destroy(s);
+      throw Error(keep);
+    }
+    *out = s;
+  });
+}
+
+int mf6gpu_solution_destroy(mf6gpu_solution *s) {
+  return guard([&] {
+    if (!s) return;
+    if (s->S) mf6gpu_solver_destroy(s->S);
+    if (s->A) mf6gpu_matrix_destroy(s->A);
+    for (auto &e : s->ev)
+      if (e) cudaEventDestroy(e);
+    delete s;
+  });
+}
+
+int mf6gpu_solution_set_packages(mf6gpu_solution *s, int32_t npkg, const mf6gpu_bnd_package *pk) {
+  return guard([&] {
+    MF6_REQUIRE(s && (npkg == 0 || pk), "solution_set_packages: null argument");
+    MF6_REQUIRE(npkg <= MF6GPU_MAX_BUDGET_TERMS - 2, "solution_set_packages: too many packages");
+    int nb = 0;
+    for (int k = 0; k < npkg; k++) nb += pk[k].nbound;
+    std::vector<unsigned char> type(nb), flag(nb);
+    std::vector<int> node(nb), pkg(nb);
+    std::vector<double> b1(nb, 0.0), b2(nb, 0.0), b3(nb, 0.0), fred(nb, 0.0);
+    s->ranges.clear();
+    int g = 0;
+    for (int k = 0; k < npkg; k++) {
+      const mf6gpu_bnd_package &p = pk[k];
+      MF6_REQUIRE(p.type >= MF6GPU_PKG_CHD && p.type <= MF6GPU_PKG_DRN, "solution_set_packages: unknown package type");
+      s->ranges.push_back(PkgRange{p.type, g, g + p.nbound});
+      for (int i = 0; i < p.nbound; i++, g++) {
+        const int nd = p.nodelist[i] - p.index_base;
+        MF6_REQUIRE(nd >= 0 && nd < s->n, "solution_set_packages: node out of range");
+        type[g] = (unsigned char)p.type;
+        flag[g] = (unsigned char)(p.iflowred != 0);
+        fred[g] = p.flowred;
+        node[g] = s->A->iperm[nd];
+        pkg[g] = k;
+        b1[g] = p.b1 ? p.b1[i] : 0.0;
+        b2[g] = p.b2 ? p.b2[i] : 0.0;
+        b3[g] = p.b3 ? p.b3[i] : 0.0;
+      }
+    }
+    s->nb = nb;
+    // segments of equal node, bounds in (package, bound) order inside a segment
+    std::vector<int> order(nb);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return node[a] < node[b]; });
+    std::vector<int> seg_node, seg_ptr;
+    for (int e = 0; e < nb; e++) {
+      if (e == 0 || node[order[e]] != node[order[e - 1]]) {
+        seg_node.push_back(node[order[e]]);
+        seg_ptr.push_back(e);
+      }
+    }
+    seg_ptr.push_back(nb);
+    s->nseg = (int)seg_node.size();
+    const size_t c = (size_t)std::max(nb, 1);
+    auto up = [&](auto &buf, auto &vec) {
+      vec.resize(c);
+      buf.upload(vec);
+    };
+    up(s->b_type, type);
+    up(s->b_flag, flag);
+    up(s->b_node, node);
+    up(s->b_pkg, pkg);
+    up(s->b_b1, b1);
+    up(s->b_b2, b2);
+    up(s->b_b3, b3);
+    up(s->b_fred, fred);
+    s->b_hcof.alloc_zero(c);
+    s->b_rhs.alloc_zero(c);
+    s->b_sim.alloc_zero(c);
+    s->b_rin.alloc_zero(c);
+    s->b_rout.alloc_zero(c);
+    if (seg_node.empty()) seg_node.push_back(0);
+    order.resize(c);
+    s->seg_node.upload(seg_node);
+    s->seg_ptr.upload(seg_ptr);
+    s->seg_idx.upload(order);
+    // ibound: reset to the initial state, then mark constant heads (chd_rp)
+    copy_i_kernel<<<grid_for(s->n), kBlock, 0, s->stream>>>(s->n, s->ibound0.p, s->ibound.p);
+    if (nb > 0)
+      chd_ibound_kernel<<<grid_for(nb), kBlock, 0, s->stream>>>(s->bview(), s->b_pkg.p, s->ibound.p);
+    MF6_CK(cudaGetLastError());
+    MF6_CK(cudaStreamSynchronize(s->stream));
+  });
+}
+
+int mf6gpu_solution_formulate(mf6gpu_solution *s, int32_t kiter, double delt, int32_t iss) {
+  return guard([&] {
+    MF6_REQUIRE(s, "solution_formulate: null argument");
+    s->delt = delt;
+    s->iss = iss;
+    if (s->nb > 0) chd_ad_kernel<<<grid_for(s->nb), kBlock, 0, s->stream>>>(s->bview(), s->x.p, s->xold.p);
+    s->buildsystem(1);
+    int iptc;
+    double ptcf;
+    s->calc_ptc(iptc, ptcf);
+    s->ls_fixups(kiter, 1, 1, iptc, ptcf);
+    MF6_CK(cudaStreamSynchronize(s->stream));
+  });
+}
+
+int mf6gpu_solution_timestep(mf6gpu_solution *s, int32_t kper, int32_t kstp, double delt,
+                             int32_t iss, mf6gpu_step_report *rep) {
+  return guard([&] {
+    MF6_REQUIRE(s, "solution_timestep: null argument");
+    MF6_REQUIRE(iss != 0 || delt > 0.0, "solution_timestep: DELT must be > 0 for a transient step (gwf-sto.f90:263-268)");
+    s->delt = delt;
+    s->iss = iss;
+    const int n = s->n;
+    const int G = grid_for(n);
+    cudaStream_t st = s->stream;
+    // prepareSolve: gwf_ad (xold = x) ; chd_ad
+    copy_d_kernel<<<G, kBlock, 0, st>>>(n, s->x.p, s->xold.p);
+    if (s->nb > 0) chd_ad_kernel<<<grid_for(s->nb), kBlock, 0, st>>>(s->bview(), s->x.p, s->xold.p);
+    MF6_CK(cudaGetLastError());
+    int kiter, inner_total = 0, lrch = -1;
+    double hncg = 0.0, tf = 0.0, tl = 0.0;
+    s->icnvg = 0;
+    for (kiter = 1; kiter <= s->ss.mxiter; kiter++) {
+      inner_total += s->solve_outer(kiter, kstp, kper, hncg, lrch, tf, tl);
+      if (s->icnvg == 1) break;
+    }
+    if (kiter > s->ss.mxiter) kiter = s->ss.mxiter;
+    // finalizeSolve: gwf_cq
+    const ModelView M = s->view();
+    const BndView B = s->bview();
+    const int transient = (iss == 0 && s->o.insto) ? 1 : 0;
+    if (!s->o.all_confined) npf_cf_kernel<<<G, kBlock, 0, st>>>(M, s->x.p, s->sat.p);
+    flow_rows_kernel<<<G, kBlock, 0, st>>>(M, s->x.p, s->xold.p, s->sat.p, s->flowja.p, s->strgss.p,
+                                           s->strgsy.p, transient, 1.0 / delt);
+    if (s->nb > 0) {
+      bnd_cf_kernel<<<grid_for(s->nb), kBlock, 0, st>>>(B, M, s->x.p);
+      bnd_scatter_kernel<<<grid_for(s->nseg), kBlock, 0, st>>>(s->nseg, s->seg_node.p, s->seg_ptr.p,
+                                                               s->seg_idx.p, B, M, s->x.p, s->A->val.p,
+                                                               s->rhs.p, s->flowja.p, 2);
+    }
+    // gwf_bd: csr_diagsum, then the budget entries (chd_bd computes the CHD rates)
+    diagsum_kernel<<<G, kBlock, 0, st>>>(M, s->flowja.p);
+    if (s->nb > 0) chd_rate_kernel<<<grid_for(s->nb), kBlock, 0, st>>>(B, M, s->flowja.p);
+    MF6_CK(cudaGetLastError());
+    if (rep) {
+      std::memset(rep, 0, sizeof(*rep));
+      int nt = 0;
+      double totrin = 0.0, totrot = 0.0, rin, rout, dum;
+      if (s->o.insto) {
+        s->posneg(s->strgss.p, 0, n, rin, rout);
+        rep->term_id[nt] = 100; rep->term_in[nt] = rin; rep->term_out[nt] = rout; nt++;
+        totrin += rin; totrot += rout;
+        s->posneg(s->strgsy.p, 0, n, rin, rout);
+        rep->term_id[nt] = 101; rep->term_in[nt] = rin; rep->term_out[nt] = rout; nt++;
+        totrin += rin; totrot += rout;
+      }
+      for (const PkgRange &r : s->ranges) {
+        if (nt >= MF6GPU_MAX_BUDGET_TERMS) break;
+        if (r.type == MF6GPU_PKG_CHD) {
+          s->posneg(s->b_rin.p, r.i0, r.i1, rin, dum);
+          s->posneg(s->b_rout.p, r.i0, r.i1, rout, dum);
+        } else {
+          s->posneg(s->b_sim.p, r.i0, r.i1, rin, rout);
+        }
+        rep->term_id[nt] = r.type; rep->term_in[nt] = rin; rep->term_out[nt] = rout; nt++;
+        totrin += rin; totrot += rout;
+      }
+      rep->nterms = nt;
+      rep->totrin = totrin;
+      rep->totrot = totrot;
+      const double avgrat = (totrin + totrot) / 2.0;
+      rep->pdiffr = (avgrat != 0.0) ? 100.0 * (totrin - totrot) / avgrat : 0.0;
+      rep->converged = s->icnvg;
+      rep->outer_iterations = kiter;
+      rep->inner_iterations = inner_total;
+      rep->max_dv = hncg;
+      rep->max_dv_loc = lrch >= 0 ? s->A->perm[lrch] + 1 : 0;
+      rep->npivot_fixes = s->S->npivfix;
+      rep->t_formulate = tf;
+      rep->t_linsolve = tl;
+    }
+    MF6_CK(cudaStreamSynchronize(st));
+  });
+}
+
+static void get_cell_vector(mf6gpu_solution *s, const double *dev, double *host) {
+  launch_scatter(s->n, s->A->d_perm.p, dev, s->hstage.p, s->stream);
+  MF6_CK(cudaGetLastError());
+  s->hstage.download(host, (size_t)s->n, s->stream);
+}
+
+int mf6gpu_solution_get_x(mf6gpu_solution *s, double *x) {
+  return guard([&] {
+    MF6_REQUIRE(s && x, "solution_get_x: null argument");
+    get_cell_vector(s, s->x.p, x);
+  });
+}
+
+int mf6gpu_solution_set_x(mf6gpu_solution *s, const double *x) {
+  return guard([&] {
+    MF6_REQUIRE(s && x, "solution_set_x: null argument");
+    MF6_CK(cudaMemcpyAsync(s->hstage.p, x, sizeof(double) * (size_t)s->n, cudaMemcpyHostToDevice, s->stream));
+    launch_gather(s->n, s->A->d_perm.p, s->hstage.p, s->x.p, s->stream);
+    MF6_CK(cudaGetLastError());
+    MF6_CK(cudaStreamSynchronize(s->stream));
+  });
+}
+
+int mf6gpu_solution_get_rhs(mf6gpu_solution *s, double *rhs) {
+  return guard([&] {
+    MF6_REQUIRE(s && rhs, "solution_get_rhs: null argument");
+    get_cell_vector(s, s->rhs.p, rhs);
+  });
+}
+
+int mf6gpu_solution_get_amat(mf6gpu_solution *s, double *amat) {
+  return guard([&] {
+    MF6_REQUIRE(s && amat, "solution_get_amat: null argument");
+    if (mf6gpu_matrix_get_values(s->A, amat) != 0) throw Error(last_error());
+  });
+}
+
+namespace mf6 {
+__global__ void sell_gather_kernel(int nja, const int *__restrict__ map,
+                                   const double *__restrict__ sell, double *__restrict__ csr) {
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nja; p += gridDim.x * blockDim.x)
+    csr[p] = sell[map[p]];
+}
+}  // namespace mf6
+
+int mf6gpu_solution_get_flowja(mf6gpu_solution *s, double *flowja) {
+  return guard([&] {
+    MF6_REQUIRE(s && flowja, "solution_get_flowja: null argument");
+    sell_gather_kernel<<<grid_for(s->nja), kBlock, 0, s->stream>>>(s->nja, s->A->csr2sell.p, s->flowja.p,
+                                                                   s->hstage.p);
+    MF6_CK(cudaGetLastError());
+    s->hstage.download(flowja, (size_t)s->nja, s->stream);
+  });
+}
+
+int mf6gpu_solution_get_condsat(mf6gpu_solution *s, double *condsat) {
+  return guard([&] {
+    MF6_REQUIRE(s && condsat, "solution_get_condsat: null argument");
+    s->condsat.download(condsat, (size_t)s->njas, s->stream);
+  });
+}
+
+mf6gpu_solver *mf6gpu_solution_solver(mf6gpu_solution *s) { return s ? s->S : nullptr; }
+
+}  // extern "C"

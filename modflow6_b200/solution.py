@@ -1,0 +1,89 @@
+"""Host-side mirror of NumericalSolutionType for one GWF model, device resident.
+
+`GpuNumericalSolution` plays the role of src/Solution/NumericalSolution.f90 for
+the path this repo accelerates: the models' formulate (`sln_buildsystem`), the
+pre-solve fix-ups and linear solve (`sln_ls`), the outer Picard/Newton loop
+(`sln_ca` / `solve(kiter)`), and the flow/budget post-processing of
+`finalizeSolve`.  Heads, matrix and right-hand side stay in HBM between calls;
+only stress data go in and heads / the budget report come out.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import ctypes_types as T
+from .grid import package_array
+from .lib import check, ensure_init, load
+
+
+class GpuNumericalSolution:
+    def __init__(self, model, sln_settings, ims_settings):
+        ensure_init()
+        self._L = load()
+        self.model = model
+        self.sln_settings = sln_settings
+        self.ims_settings = ims_settings
+        self._ms = model.struct()
+        self.n = model.nodes
+        self.h = C.c_void_p()
+        check(self._L.mf6gpu_solution_create(C.byref(self._ms), C.byref(sln_settings), C.byref(ims_settings),
+                                             C.byref(self.h)))
+
+    # bnd_rp of every package
+    def set_packages(self, pkgs):
+        self._pkgs = list(pkgs)
+        arr = package_array(self._pkgs)
+        check(self._L.mf6gpu_solution_set_packages(self.h, len(self._pkgs), arr))
+
+    # sln_ca for one time step
+    def timestep(self, kper=1, kstp=1, delt=1.0, iss=1):
+        rep = T.StepReport()
+        check(self._L.mf6gpu_solution_timestep(self.h, int(kper), int(kstp), float(delt), int(iss), C.byref(rep)))
+        return rep
+
+    def formulate(self, kiter=1, delt=1.0, iss=1):
+        check(self._L.mf6gpu_solution_formulate(self.h, int(kiter), float(delt), int(iss)))
+
+    def _get(self, name, size):
+        a = np.empty(size)
+        check(getattr(self._L, "mf6gpu_solution_get_" + name)(self.h, T.ptr_f64(a)))
+        return a
+
+    @property
+    def x(self):
+        return self._get("x", self.n)
+
+    def set_x(self, x):
+        x = T.as_f64(x)
+        assert x.size == self.n
+        check(self._L.mf6gpu_solution_set_x(self.h, T.ptr_f64(x)))
+
+    @property
+    def amat(self):
+        return self._get("amat", self.model.nja)
+
+    @property
+    def rhs(self):
+        return self._get("rhs", self.n)
+
+    @property
+    def flowja(self):
+        return self._get("flowja", self.model.nja)
+
+    @property
+    def condsat(self):
+        return self._get("condsat", self.model.njas)
+
+    def solver_stat(self, what):
+        return self._L.mf6gpu_solver_stat(self._L.mf6gpu_solution_solver(self.h), what)
+
+    def destroy(self):
+        if self.h:
+            self._L.mf6gpu_solution_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
