@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 IMS + GWF-assembly hot path.
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference] [--size nlay,nrow,ncol]
+
+Workload (BASELINE.json configs[1], "C2"): synthetic confined steady-state DIS
+10 x 1000 x 1000 (1.0e7 cells, nja 6.796e7), heterogeneous K, CHD on both sides,
+one well, IMS CG + ILU0.  One "step" = one time step = sln_ca: formulate
+(NPF/CHD/WEL fill of amat/rhs), pre-solve fix-ups, ILU0 factorisation, the CG
+inner iterations, outer convergence loop, flows + budget.
+
+Metric: IMS cell-iterations per second = cells x inner iterations / time.
+  value : K steps with everything resident in HBM, CUDA events on the launching stream
+  e2e   : the same K steps through the host-buffer C ABI calls a host code makes per
+          time step (stress data + initial heads H2D, heads + budget report D2H)
+  roofline : the CSR/SELL SpMV kernel (dominant single kernel), algorithmic bytes / mean
+          launch duration measured with CUDA events inside the timed region
+  cpu_baseline : the C oracle (port of the reference algorithm, 1 core) on a bounded
+          sample of the same workload
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ims_cell_iterations_per_second"
+UNIT = "cell-iter/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", default="10,1000,1000", help="nlay,nrow,ncol of the C2 grid")
+    ap.add_argument("--ordering", default="multicolor", choices=["multicolor", "natural"])
+    ap.add_argument("--cpu-iters", type=int, default=12, help="inner iterations of the CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inner-maximum", type=int, default=500, help="INNER_MAXIMUM of the IMS LINEAR block")
+    ap.add_argument("--outer-maximum", type=int, default=50, help="OUTER_MAXIMUM (1 = short profiling run)")
+    ap.add_argument("--min-warmup", type=int, default=3)
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smax)) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_config(size, ordering, inner_maximum=500, outer_maximum=50):
+    from modflow6_b200 import configs, ctypes_types as T
+    nlay, nrow, ncol = size
+    o = T.ORDER_MULTICOLOR if ordering == "multicolor" else T.ORDER_NATURAL
+    return configs.c2_confined(nlay, nrow, ncol, gpu_ordering=o, inner_maximum=inner_maximum,
+                               outer_maximum=outer_maximum)
+
+
+def algorithmic_bytes(n, nja):
+    """SURVEY.md section 8(d) per-kernel algorithmic bytes (f64 values, i32 indices)."""
+    spmv = 12 * nja + 4 * (n + 1) + 16 * n
+    ilu = 12 * (nja - n) + 8 * n + 4 * (n + 1) + 4 * n + 32 * n
+    return {"spmv": spmv, "ilu0_apply": ilu, "update": 6 * 8 * n, "dot": 2 * 8 * n, "direction": 3 * 8 * n,
+            "cg_iteration": spmv + ilu + 9 * 8 * n}
+
+
+class CpuSample:
+    """Oracle (port of the reference algorithm) on a bounded sample: one outer iteration of the same
+    model capped at `iters` CG iterations.  cell-iter/s counts the linear-solve time only (ILU0
+    factorisation + residual + iterations), the most favourable reading for the CPU."""
+
+    def __init__(self, cfg, iters):
+        from modflow6_b200 import ctypes_types as T
+        from oracle.oracle import OracleSolution
+        ims = T.ImsSettings.make(dvclose=cfg.ims.dvclose, rclose=cfg.ims.rclose, iter1=iters,
+                                 ilinmeth=cfg.ims.ilinmeth, relax=cfg.ims.relax)
+        sln = T.SlnSettings.make(dvclose=cfg.sln.dvclose, mxiter=1)
+        self.cfg = cfg
+        self.O = OracleSolution(cfg.model, sln, ims)
+        self.O.set_packages(cfg.periods[0].packages)
+
+    def run(self):
+        self.O.x[:] = self.cfg.model.strt
+        t0 = time.perf_counter()
+        rep = self.O.timestep(1, 1, 1.0, 1)
+        wall = time.perf_counter() - t0
+        n = self.cfg.model.nodes
+        return {"iters": rep.inner_iterations, "t_linsolve": rep.t_linsolve, "t_formulate": rep.t_formulate,
+                "wall": wall, "value": n * rep.inner_iterations / rep.t_linsolve}
+
+
+def run_reference(args, size):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = build_config(size, "natural")
+    n = cfg.model.nodes
+    iters = args.cpu_iters
+    cs = CpuSample(cfg, iters)
+    vals, times = [], []
+    t_begin = time.perf_counter()
+    warm = args.warmup
+    i = 0
+    while len(vals) < args.steps:
+        s = cs.run()
+        if i >= warm:
+            vals.append(s["value"])
+            times.append(s["t_linsolve"])
+        i += 1
+        if time.perf_counter() - t_begin > 150 and i < warm:
+            warm = i  # keep the whole run within a few minutes on a slow host core
+    value = float(np.mean(vals))
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": warm, "ms_per_step": 1e3 * float(np.mean(times)),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"C2 confined steady-state DIS {size[0]}x{size[1]}x{size[2]}, IMS CG+ILU0",
+                       "cells": n, "nja": cfg.model.nja},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": f"C oracle (port of ImsLinearBase.f90/gwf-npf.f90; the Fortran reference has no "
+                                       f"compiler in this image), 1 outer iteration capped at {iters} CG iterations "
+                                       f"on the full {n}-cell system; linear-solve time only"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    size = tuple(int(v) for v in args.size.split(","))
+    if args.impl == "reference":
+        run_reference(args, size)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from modflow6_b200 import lib
+    from modflow6_b200.solution import GpuNumericalSolution
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    lib.init(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cfg = build_config(size, args.ordering, args.inner_maximum, args.outer_maximum)
+    n, nja = cfg.model.nodes, cfg.model.nja
+    per = cfg.periods[0]
+    G = GpuNumericalSolution(cfg.model, cfg.sln, cfg.ims)
+    G.set_packages(per.packages)
+    strt = np.ascontiguousarray(cfg.model.strt)
+    pinned_x = torch.empty(n, dtype=torch.float64).pin_memory()
+    pinned_strt = torch.from_numpy(strt.copy()).pin_memory()
+    h2d = strt.nbytes + sum(p.nodelist.nbytes + p.b1.nbytes + p.b2.nbytes + p.b3.nbytes for p in per.packages)
+    d2h = n * 8 + C.sizeof(__import__("modflow6_b200.ctypes_types", fromlist=["StepReport"]).StepReport)
+
+    def step_device():
+        G.reset_x()
+        return G.timestep(1, 1, 1.0, 1)
+
+    def step_e2e():
+        # what a host code does per time step through the C ABI with host buffers
+        G.set_packages(per.packages)                                  # stress data  H2D
+        G._L.mf6gpu_solution_set_x(G.h, C.cast(pinned_strt.data_ptr(), C.POINTER(C.c_double)))   # heads H2D
+        rep = G.timestep(1, 1, 1.0, 1)
+        G._L.mf6gpu_solution_get_x(G.h, C.cast(pinned_x.data_ptr(), C.POINTER(C.c_double)))     # heads D2H
+        return rep
+
+    # ---- warm-up
+    for _ in range(max(args.warmup, args.min_warmup)):
+        rep = step_device()
+    # ---- timed: device resident
+    sampler = ClockSampler(local_rank)
+    G.profile(True)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    inner = outer = 0
+    launches = 0
+    t_ls = t_form = 0.0
+    for _ in range(args.steps):
+        rep = step_device()
+        inner += rep.inner_iterations
+        outer += rep.outer_iterations
+        t_ls += rep.t_linsolve
+        t_form += rep.t_formulate
+        launches += int(G.stat(0))
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    prof = G.profile_result()
+    G.profile(False)
+    # ---- timed: end to end through host buffers
+    step_e2e()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    inner_e = 0
+    for _ in range(args.steps):
+        inner_e += step_e2e().inner_iterations
+    e3.record()
+    barrier()
+    ms_e = e2.elapsed_time(e3)
+    heads = G.x
+    converged = rep.converged
+
+    # max over ranks, whole-job aggregate
+    if world > 1:
+        t = torch.tensor([ms, ms_e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e = t.tolist()
+        c = torch.tensor([float(inner), float(inner_e)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        inner_all, inner_e_all = c.tolist()
+    else:
+        inner_all, inner_e_all = float(inner), float(inner_e)
+    value = n * inner_all / (ms * 1e-3)
+    e2e_value = n * inner_e_all / (ms_e * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        ab = algorithmic_bytes(n, nja)
+        kernels = {}
+        for name in ("spmv", "ilu0_apply", "update", "dot", "direction"):
+            tot, cnt = prof[name]
+            if cnt > 0:
+                dur = tot / cnt * 1e-3
+                kernels[name] = {"launch_groups": cnt, "mean_ms": tot / cnt,
+                                 "achieved_gbs": ab[name] / dur / 1e9, "frac": ab[name] / dur / 1e9 / peak}
+        sp = kernels.get("spmv", {"achieved_gbs": 0.0, "frac": 0.0})
+        iter_ms = sum(k["mean_ms"] for k in kernels.values())
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, args.min_warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C2 confined steady-state DIS {size[0]}x{size[1]}x{size[2]}, IMS CG+ILU0 "
+                                   f"({args.ordering} ILU ordering)",
+                       "cells": n, "nja": nja, "l2_policy": "inputs_exceed_l2 (matrix+vectors >> 126 MB)",
+                       "per_gpu": "one full model per GPU (no exchange)" if world > 1 else "single GPU",
+                       "inner_dvclose": cfg.ims.dvclose, "inner_rclose": cfg.ims.rclose,
+                       "inner_maximum": cfg.ims.iter1, "outer_dvclose": cfg.sln.dvclose},
+            "solve": {"outer_iterations_per_step": outer / args.steps, "inner_iterations_per_step": inner / args.steps,
+                      "converged": int(converged), "linear_solve_s_per_step": t_ls / args.steps,
+                      "formulate_s_per_step": t_form / args.steps, "timestep_s": ms * 1e-3 / args.steps,
+                      "head_min": float(heads.min()), "head_max": float(heads.max())},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": ms_e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "spmv_fused_kernel (SELL-32 SpMV + fused p.q)",
+                         "achieved": sp["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": sp["frac"],
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": ab["spmv"],
+                         "cg_iteration": {"algorithmic_bytes": ab["cg_iteration"], "mean_ms": iter_ms,
+                                          "frac": (ab["cg_iteration"] / (iter_ms * 1e-3) / 1e9 / peak) if iter_ms else None},
+                         "kernels": kernels},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            s = CpuSample(build_config(size, "natural"), args.cpu_iters).run()
+            line["cpu_baseline"] = {"value": s["value"], "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": f"C oracle (port; no Fortran compiler in the image), 1 outer iteration "
+                                              f"capped at {s['iters']} CG iterations on the full {n}-cell system, "
+                                              f"linear-solve time only ({s['t_linsolve']:.2f} s)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -113,6 +113,10 @@ int mf6gpu_solver_get_summary(mf6gpu_solver *s, int32_t cap, int32_t *itinner,
 /* facts of the last solve: 0 l2norm0, 1 pivot corrections, 2 device seconds in
  * factorisation, 3 device seconds in the Krylov loop, 4 kernel launches */
 double mf6gpu_solver_stat(const mf6gpu_solver *s, int what);
+/* per-kernel-class device timing (CUDA events on the solver's stream):
+ * classes 0 spmv, 1 ilu0 apply, 2 x/r update, 3 dot, 4 direction update, 5 factorisation */
+int mf6gpu_solver_profile(mf6gpu_solver *s, int32_t enable);
+int mf6gpu_solver_profile_get(mf6gpu_solver *s, int32_t cls, double *total_ms, int64_t *count);
 /* preconditioner pieces exposed for parity tests (pcu + ilu0a):
  * factor the current matrix values, apply M^-1 to a host vector */
 int mf6gpu_solver_factor(mf6gpu_solver *s, int32_t *npivot_fixes);
@@ -136,12 +140,15 @@ int mf6gpu_solution_formulate(mf6gpu_solution *s, int32_t kiter, double delt,
                               int32_t iss);
 int mf6gpu_solution_get_x(mf6gpu_solution *s, double *x);        /* heads, original order */
 int mf6gpu_solution_set_x(mf6gpu_solution *s, const double *x);
+int mf6gpu_solution_reset_x(mf6gpu_solution *s);                 /* x = IC strt, device side */
 int mf6gpu_solution_get_amat(mf6gpu_solution *s, double *amat);  /* CSR order */
 int mf6gpu_solution_get_rhs(mf6gpu_solution *s, double *rhs);
 int mf6gpu_solution_get_flowja(mf6gpu_solution *s, double *flowja);
 int mf6gpu_solution_get_condsat(mf6gpu_solution *s, double *condsat);
 /* the linear solver owned by the solution (for stats / summary) */
 mf6gpu_solver *mf6gpu_solution_solver(mf6gpu_solution *s);
+/* facts: 0 kernel launches of the last time step, 1 ILU levels, 2 SELL slots */
+double mf6gpu_solution_stat(const mf6gpu_solution *s, int what);
 
 #ifdef __cplusplus
 }

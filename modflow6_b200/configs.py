@@ -108,7 +108,7 @@ def c3_newton(nlay=5, nrow=2000, ncol=2000, gpu_ordering=T.ORDER_MULTICOLOR, nwe
     wel = Package(T.PKG_WEL, wnodes, np.full(wnodes.size, -500.0), iflowred=1, flowred=0.1)
     periods = [Period(1.0, 1, 1.0, True, [chd, rch]),
                Period(100.0, ntrans, 1.2, False, [chd, rch, wel])]
-    ims = T.ImsSettings.make(dvclose=1e-5, rclose=1e-1, iter1=100, ilinmeth=2, relax=0.0,
+    ims = T.ImsSettings.make(dvclose=1e-6, rclose=1e-2, iter1=100, ilinmeth=2, relax=0.0,
                              gpu_ordering=gpu_ordering)
     sln = T.SlnSettings.make(dvclose=1e-4, mxiter=50, nonmeth=3, theta=0.9, akappa=1e-4, gamma=0.0,
                              amomentum=0.0, iallowptc=iallowptc)

@@ -799,6 +799,7 @@ struct mf6gpu_solution {
   int isymmetric = 0;
   cudaStream_t stream = 0;
   DevBuf<double> top, bot, area, k11, k33, ssv, syv;
+  DevBuf<double> strt;
   DevBuf<double> x, xold, sat, rhs, xtemp, dxold, wsave, hchold, deold, strgss, strgsy;
   DevBuf<int> icelltype, ibound, ibound0, iconvert, ibotnode;
   DevBuf<int> slot_conn;
@@ -825,6 +826,7 @@ struct mf6gpu_solution {
   double delt = 1.0;
   int iss = 1;
   int icnvg = 0;
+  long long nl = 0;  // kernel launches of the current time step
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   std::vector<int> h_conn_jas;  // csr position -> jas (original), for get_condsat ordering
 
@@ -898,6 +900,8 @@ void mf6gpu_solution::buildsystem(int inewton) {
   const int G = grid_for(n);
   const int transient = (iss == 0 && o.insto) ? 1 : 0;
   const double tled = 1.0 / delt;
+  nl += (o.all_confined ? 0 : 1) + (nb > 0 ? 1 : 0) + 1 + (nseg > 0 ? 1 : 0);
+  if (inewton && o.inewton) nl += 1 + (nseg > 0 ? 1 : 0);
   if (!o.all_confined) npf_cf_kernel<<<G, kBlock, 0, stream>>>(M, x.p, sat.p);
   if (nb > 0) bnd_cf_kernel<<<grid_for(nb), kBlock, 0, stream>>>(B, M, x.p);
   if (o.all_confined)
@@ -923,6 +927,7 @@ void mf6gpu_solution::calc_ptc(int &iptc, double &ptcf) {
   int iptct = 0;
   if (iss > 0) iptct = o.inewton;
   if (iptct > 0) {
+    nl++;
     ptc_resid_kernel<<<grid_for(n), kBlock, 0, stream>>>(view(), A->val.p, x.p, rhs.p, partial.p,
                                                          tickets.p + 1, os.p);
     MF6_CK(cudaGetLastError());
@@ -936,6 +941,7 @@ void mf6gpu_solution::calc_ptc(int &iptc, double &ptcf) {
 void mf6gpu_solution::ls_fixups(int kiter, int kstp, int kper, int iptc, double ptcf) {
   const ModelView M = view();
   const int G = grid_for(n);
+  nl++;
   ls_fixup_kernel<<<G, kBlock, 0, stream>>>(M, x.p, xtemp.p, A->val.p, rhs.p, isymmetric);
   MF6_CK(cudaGetLastError());
   int iallowptc;
@@ -946,6 +952,7 @@ void mf6gpu_solution::ls_fixups(int kiter, int kstp, int kper, int iptc, double 
   int iptct = iptc * iallowptc;
   double l2norm = 0.0;
   if (iptct != 0) {
+    nl++;
     ptc_resid_kernel<<<G, kBlock, 0, stream>>>(M, A->val.p, x.p, rhs.p, partial.p, tickets.p + 1, os.p);
     MF6_CK(cudaGetLastError());
     l2norm = std::sqrt(fetch_os().l2);
@@ -969,6 +976,7 @@ void mf6gpu_solution::ls_fixups(int kiter, int kstp, int kper, int iptc, double 
         ptcdel = 0.0;
     }
     const double ptcval = (ptcdel > 0.0) ? 1.0 / ptcdel : 1.0;
+    nl++;
     ptc_apply_kernel<<<G, kBlock, 0, stream>>>(M, A->val.p, rhs.p, x.p, ptcval);
     MF6_CK(cudaGetLastError());
     l2norm0 = l2norm;
@@ -988,6 +996,7 @@ int mf6gpu_solution::solve_outer(int kiter, int kstp, int kper, double &hncg, in
   ls_fixups(kiter, kstp, kper, iptc, ptcf);
   int iter = 0, icnvg_lin = 0;
   S->solve_device(kiter, kstp, x.p, rhs.p, &iter, &icnvg_lin);
+  nl += S->launches + 1;  // + dxmax
   MF6_CK(cudaEventRecord(ev[2], stream));
   dxmax_kernel<<<G, kBlock, 0, stream>>>(n, x.p, xtemp.p, ibound.p, A->ord_ptr(), pm.p, tickets.p, os.p);
   MF6_CK(cudaGetLastError());
@@ -1002,6 +1011,7 @@ int mf6gpu_solution::solve_outer(int kiter, int kstp, int kper, double &hncg, in
   icnvg = 0;
   if (std::fabs(hncg) <= ss.dvclose) icnvg = 1;
   if (icnvg != 1) {
+    nl += 1 + ((o.inewton != 0 && o.inewtonur != 0) ? 2 : 0);
     if (ss.nonmeth == 1) {
       relax_kernel<<<G, kBlock, 0, stream>>>(n, ibound.p, x.p, xtemp.p, dxold.p, ss.gamma);
     } else if (ss.nonmeth == 2) {
@@ -1127,6 +1137,7 @@ int mf6gpu_solution_create(const mf6gpu_gwf_model *m, const mf6gpu_sln_settings 
         }
         s->ibotnode.upload(ib);
       }
+      s->strt.upload(permuted(m->strt, perm, 0.0));
       s->x.upload(permuted(m->strt, perm, 0.0));
       s->xold.upload(permuted(m->strt, perm, 0.0));
       {
@@ -1310,6 +1321,7 @@ int mf6gpu_solution_timestep(mf6gpu_solution *s, int32_t kper, int32_t kstp, dou
     const int n = s->n;
     const int G = grid_for(n);
     cudaStream_t st = s->stream;
+    s->nl = 2 + 4 + (s->nb > 0 ? 3 : 0);  // prepareSolve + finalizeSolve kernels (budget reductions not counted)
     // prepareSolve: gwf_ad (xold = x) ; chd_ad
     copy_d_kernel<<<G, kBlock, 0, st>>>(n, s->x.p, s->xold.p);
     if (s->nb > 0) chd_ad_kernel<<<grid_for(s->nb), kBlock, 0, st>>>(s->bview(), s->x.p, s->xold.p);
@@ -1403,6 +1415,16 @@ int mf6gpu_solution_set_x(mf6gpu_solution *s, const double *x) {
   });
 }
 
+// heads back to the initial condition (IC strt) without touching the host
+int mf6gpu_solution_reset_x(mf6gpu_solution *s) {
+  return guard([&] {
+    MF6_REQUIRE(s, "solution_reset_x: null argument");
+    copy_d_kernel<<<grid_for(s->n), kBlock, 0, s->stream>>>(s->n, s->strt.p, s->x.p);
+    MF6_CK(cudaGetLastError());
+    MF6_CK(cudaStreamSynchronize(s->stream));
+  });
+}
+
 int mf6gpu_solution_get_rhs(mf6gpu_solution *s, double *rhs) {
   return guard([&] {
     MF6_REQUIRE(s && rhs, "solution_get_rhs: null argument");
@@ -1443,5 +1465,15 @@ int mf6gpu_solution_get_condsat(mf6gpu_solution *s, double *condsat) {
 }
 
 mf6gpu_solver *mf6gpu_solution_solver(mf6gpu_solution *s) { return s ? s->S : nullptr; }
+
+double mf6gpu_solution_stat(const mf6gpu_solution *s, int what) {
+  if (!s) return -1.0;
+  switch (what) {
+    case 0: return (double)s->nl;
+    case 1: return (double)s->A->nlevels;
+    case 2: return (double)s->A->nslots;
+  }
+  return -1.0;
+}
 
 }  // extern "C"

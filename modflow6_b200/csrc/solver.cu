@@ -429,13 +429,44 @@ static double epfact_of(int icnvgopt, int kstp) {
   return 1.0;
 }
 
+void mf6gpu_solver::prof_begin(int cls) {
+  if (!profiling || !prof_on) return;
+  if (ev_used + 2 > ev_pool.size()) {
+    const size_t old = ev_pool.size();
+    ev_pool.resize(old + 1024);
+    for (size_t i = old; i < ev_pool.size(); i++) MF6_CK(cudaEventCreate(&ev_pool[i]));
+  }
+  ev_cls.push_back(cls);
+  MF6_CK(cudaEventRecord(ev_pool[ev_used++], stream));
+}
+
+void mf6gpu_solver::prof_end() {
+  if (!profiling || !prof_on) return;
+  MF6_CK(cudaEventRecord(ev_pool[ev_used++], stream));
+}
+
+void mf6gpu_solver::prof_collect() {
+  if (!profiling) return;
+  MF6_CK(cudaStreamSynchronize(stream));
+  for (size_t k = 0; k < ev_cls.size(); k++) {
+    float ms = 0.f;
+    MF6_CK(cudaEventElapsedTime(&ms, ev_pool[2 * k], ev_pool[2 * k + 1]));
+    prof_ms[ev_cls[k]] += ms;
+    prof_cnt[ev_cls[k]] += 1;
+  }
+  ev_cls.clear();
+  ev_used = 0;
+}
+
 // ims_base_pcu, ImsLinearBase.f90:808-858
 int mf6gpu_solver::factor() {
   int ipcflag = 0, icount = 0;
   double delta = 0.0;
   for (;;) {
     failflag.zero(stream);
+    prof_begin(PC_FACTOR);
     launches += ilu0_factor(*A, A->val.p, lu.p, s.relax, delta, ipcflag, failflag.p, stream);
+    prof_end();
     MF6_CK(cudaGetLastError());
     MF6_CK(cudaMemcpyAsync(h_flag.p, failflag.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
     MF6_CK(cudaStreamSynchronize(stream));
@@ -472,6 +503,7 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
   }
   // -- preconditioner (ImsLinear.f90:669-673)
   npivfix = factor();
+  prof_collect();
   MF6_CK(cudaEventRecord(ev[1], S));
   // -- initial residual and its norm (ImsLinear.f90:676-699)
   init_state_kernel<<<1, 1, 0, S>>>(st.p, epfact_of(s.icnvgopt, kstp), s.dvclose, s.rclose,
@@ -508,33 +540,52 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
       for (int b = 0; b < nb; b++) {
         const int iiter = launched + b + 1;
         const int first = (iiter == 1) ? 1 : 0;
+        prof_on = (b == 0);  // time one iteration per polling batch
         if (!bcgs) {
+          prof_begin(PC_ILU);
           launches += ilu0_apply(*A, lu.p, d.p, z.p, &st.p->done, S);
+          prof_end();
+          prof_begin(PC_DOT);
           dot_kernel<<<G, kBlock, 0, S>>>(N, d.p, z.p, partial.p, tickets.p + TK_DOT, st.p,
                                           FIN_CG_RHO, nullptr, 1);
+          prof_end();
+          prof_begin(PC_PUPD);
           cg_p_kernel<<<G, kBlock, 0, S>>>(N, z.p, p.p, st.p, first);
+          prof_end();
+          prof_begin(PC_SPMV);
           spmv_fused_kernel<0, 1><<<G, kBlock, 0, S>>>(N, A->slice_ptr.p, A->rowlen.p, A->col.p,
                                                        A->val.p, p.p, q.p, nullptr, p.p, partial.p,
                                                        tickets.p + TK_SPMV, st.p, FIN_CG_ALPHA, 1);
+          prof_end();
+          prof_begin(PC_UPD);
           update_kernel<0><<<G, kBlock, 0, S>>>(N, x_dev, d.p, p.p, q.p, nullptr, nullptr, nullptr,
                                                 ord, partial.p, pmx.p, pmr.p, tickets.p + TK_UPD,
                                                 st.p, sp);
+          prof_end();
           launches += 4;
         } else {
           dot_kernel<<<G, kBlock, 0, S>>>(N, dhat.p, d.p, partial.p, tickets.p + TK_DOT, st.p,
                                           FIN_BCGS_RHO, nullptr, 1);
           bcgs_p_kernel<<<G, kBlock, 0, S>>>(N, d.p, v.p, p.p, st.p, first);
+          prof_begin(PC_ILU);
           launches += ilu0_apply(*A, lu.p, p.p, phat.p, &st.p->done, S);
+          prof_end();
+          prof_begin(PC_SPMV);
           spmv_fused_kernel<0, 1><<<G, kBlock, 0, S>>>(N, A->slice_ptr.p, A->rowlen.p, A->col.p,
                                                        A->val.p, phat.p, v.p, nullptr, dhat.p,
                                                        partial.p, tickets.p + TK_SPMV, st.p,
                                                        FIN_BCGS_ALPHA, 1);
+          prof_end();
           bcgs_q_kernel<<<G, kBlock, 0, S>>>(N, d.p, v.p, q.p, st.p);
+          prof_begin(PC_ILU);
           launches += ilu0_apply(*A, lu.p, q.p, qhat.p, &st.p->done, S);
+          prof_end();
+          prof_begin(PC_SPMV);
           spmv_fused_kernel<0, 2><<<G, kBlock, 0, S>>>(N, A->slice_ptr.p, A->rowlen.p, A->col.p,
                                                        A->val.p, qhat.p, t.p, nullptr, q.p,
                                                        partial.p, tickets.p + TK_SPMV, st.p,
                                                        FIN_BCGS_OMEGA, 1);
+          prof_end();
           update_kernel<1><<<G, kBlock, 0, S>>>(N, x_dev, d.p, phat.p, q.p, qhat.p, t.p, dscale.p,
                                                 ord, partial.p, pmx.p, pmr.p, tickets.p + TK_UPD,
                                                 st.p, sp);
@@ -552,6 +603,12 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
       MF6_CK(cudaMemcpyAsync(h_st.p, st.p, sizeof(KState), cudaMemcpyDeviceToHost, S));
       MF6_CK(cudaStreamSynchronize(S));
       if (h_st.p->done) finished = true;
+      prof_on = true;
+      if (profiling) {
+        // the timed iteration is the first of the batch: it executed unless the loop had already ended
+        if (h_st.p->iter - (launched - nb) < 1) ev_cls.clear();
+        prof_collect();
+      }
     }
     innerit = h_st.p->iter;
     icnvg = h_st.p->icnvg;
@@ -653,6 +710,7 @@ int mf6gpu_solver_destroy(mf6gpu_solver *s) {
     if (!s) return;
     for (auto &e : s->ev)
       if (e) cudaEventDestroy(e);
+    for (auto &e : s->ev_pool) cudaEventDestroy(e);
     delete s;
   });
 }
@@ -719,6 +777,27 @@ double mf6gpu_solver_stat(const mf6gpu_solver *s, int what) {
     case 4: return (double)s->launches;
   }
   return -1.0;
+}
+
+int mf6gpu_solver_profile(mf6gpu_solver *s, int32_t enable) {
+  return guard([&] {
+    MF6_REQUIRE(s, "solver_profile: null argument");
+    s->profiling = enable != 0;
+    for (int c = 0; c < mf6gpu_solver::PC_N; c++) {
+      s->prof_ms[c] = 0.0;
+      s->prof_cnt[c] = 0;
+    }
+    s->ev_cls.clear();
+    s->ev_used = 0;
+  });
+}
+
+int mf6gpu_solver_profile_get(mf6gpu_solver *s, int32_t cls, double *total_ms, int64_t *count) {
+  return guard([&] {
+    MF6_REQUIRE(s && cls >= 0 && cls < mf6gpu_solver::PC_N && total_ms && count, "solver_profile_get: bad argument");
+    *total_ms = s->prof_ms[cls];
+    *count = s->prof_cnt[cls];
+  });
 }
 
 int mf6gpu_solver_factor(mf6gpu_solver *s, int32_t *npivot_fixes) {

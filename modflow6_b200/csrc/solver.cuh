@@ -52,7 +52,19 @@ struct mf6gpu_solver {
   double t_factor = 0.0, t_krylov = 0.0;
   long long launches = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  bool values_external = false;  // A values are assembled on the device by the solution
+  // optional per-kernel-class timing with CUDA events on the launching stream
+  // (classes: 0 spmv, 1 ilu apply, 2 x/r update, 3 dot, 4 direction update, 5 factor)
+  enum { PC_SPMV = 0, PC_ILU = 1, PC_UPD = 2, PC_DOT = 3, PC_PUPD = 4, PC_FACTOR = 5, PC_N = 6 };
+  bool profiling = false;
+  bool prof_on = true;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  std::vector<int> ev_cls;
+  double prof_ms[PC_N] = {0, 0, 0, 0, 0, 0};
+  long long prof_cnt[PC_N] = {0, 0, 0, 0, 0, 0};
+  void prof_begin(int cls);
+  void prof_end();
+  void prof_collect();
 
   // device-side entry: x_dev / b_dev already in FINAL numbering on the device.
   void solve_device(int kiter, int kstp, double *x_dev, double *b_dev, int *iters, int *icnvg);

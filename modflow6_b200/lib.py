@@ -20,10 +20,12 @@ SYMBOLS = [
     "mf6gpu_vector_zero_entries", "mf6gpu_vector_axpy", "mf6gpu_vector_norm2", "mf6gpu_vector_dot",
     "mf6gpu_solver_create", "mf6gpu_solver_destroy", "mf6gpu_solver_solve", "mf6gpu_solver_get_summary",
     "mf6gpu_solver_stat", "mf6gpu_solver_factor", "mf6gpu_solver_apply_preconditioner",
+    "mf6gpu_solver_profile", "mf6gpu_solver_profile_get", "mf6gpu_solution_reset_x",
     "mf6gpu_solution_create", "mf6gpu_solution_destroy", "mf6gpu_solution_set_packages",
     "mf6gpu_solution_timestep", "mf6gpu_solution_formulate", "mf6gpu_solution_get_x",
     "mf6gpu_solution_set_x", "mf6gpu_solution_get_amat", "mf6gpu_solution_get_rhs",
     "mf6gpu_solution_get_flowja", "mf6gpu_solution_get_condsat", "mf6gpu_solution_solver",
+    "mf6gpu_solution_stat",
 ]
 
 _lib = None
@@ -73,6 +75,9 @@ def load():
     L.mf6gpu_solver_get_summary.argtypes = [vp, i32, pi32, pf64, pi32, pf64, pi32, pf64, pf64]
     L.mf6gpu_solver_stat.restype = f64
     L.mf6gpu_solver_stat.argtypes = [vp, C.c_int]
+    L.mf6gpu_solver_profile.argtypes = [vp, i32]
+    L.mf6gpu_solver_profile_get.argtypes = [vp, i32, pf64, C.POINTER(C.c_int64)]
+    L.mf6gpu_solution_reset_x.argtypes = [vp]
     L.mf6gpu_solver_factor.argtypes = [vp, pi32]
     L.mf6gpu_solver_apply_preconditioner.argtypes = [vp, pf64, pf64]
     L.mf6gpu_solution_create.argtypes = [C.POINTER(T.GwfModelStruct), C.POINTER(T.SlnSettings),
@@ -83,6 +88,8 @@ def load():
     L.mf6gpu_solution_formulate.argtypes = [vp, i32, f64, i32]
     for f in ("get_x", "set_x", "get_amat", "get_rhs", "get_flowja", "get_condsat"):
         getattr(L, "mf6gpu_solution_" + f).argtypes = [vp, pf64]
+    L.mf6gpu_solution_stat.restype = f64
+    L.mf6gpu_solution_stat.argtypes = [vp, C.c_int]
     L.mf6gpu_solution_solver.restype = vp
     L.mf6gpu_solution_solver.argtypes = [vp]
     _lib = L

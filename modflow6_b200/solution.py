@@ -74,6 +74,29 @@ class GpuNumericalSolution:
     def condsat(self):
         return self._get("condsat", self.model.njas)
 
+    def reset_x(self):
+        """heads back to the IC strt array, device side (no host traffic)"""
+        check(self._L.mf6gpu_solution_reset_x(self.h))
+
+    PROFILE_CLASSES = ("spmv", "ilu0_apply", "update", "dot", "direction", "factor")
+
+    def profile(self, enable=True):
+        check(self._L.mf6gpu_solver_profile(self._L.mf6gpu_solution_solver(self.h), 1 if enable else 0))
+
+    def profile_result(self):
+        """{class: (total_ms, launches)} measured with CUDA events on the solver stream"""
+        out = {}
+        sv = self._L.mf6gpu_solution_solver(self.h)
+        for i, name in enumerate(self.PROFILE_CLASSES):
+            ms, cnt = C.c_double(), C.c_int64()
+            check(self._L.mf6gpu_solver_profile_get(sv, i, C.byref(ms), C.byref(cnt)))
+            out[name] = (ms.value, cnt.value)
+        return out
+
+    def stat(self, what):
+        """0 kernel launches of the last time step, 1 ILU levels, 2 SELL slots"""
+        return self._L.mf6gpu_solution_stat(self.h, what)
+
     def solver_stat(self, what):
         return self._L.mf6gpu_solver_stat(self._L.mf6gpu_solution_solver(self.h), what)
 

