@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <climits>
 #include <stdexcept>
 #include <string>
@@ -104,7 +105,10 @@ struct PinnedBuf {
 };
 
 constexpr int kBlock = 256;
-constexpr int kMaxBlocks = 148 * 8;  // 148 SMs x 8 resident 256-thread CTAs
+// grid cap of the grid-stride kernels: 148 SMs x 8 resident 256-thread CTAs by default
+// (MF6GPU_GRID_CAP overrides it for tuning experiments)
+int max_blocks();
+#define kMaxBlocks (mf6::max_blocks())
 
 inline int grid_for(long long n) {
   long long b = (n + kBlock - 1) / kBlock;

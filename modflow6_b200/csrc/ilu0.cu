@@ -7,6 +7,7 @@
 // The factor shares the matrix's SELL-32 structure (matrix.cuh): slot 0 holds
 // the inverse pivot APC(n), lower slots the L multipliers, upper slots U.
 #include "ilu0.cuh"
+#include <algorithm>
 
 namespace mf6 {
 
@@ -72,68 +73,138 @@ ilu0_factor_level_kernel(int r0, int r1, const int *__restrict__ slice_ptr,
   for (int k = 1; k < len; k++) lu[base + 32LL * k] = w[k];
 }
 
-// forward sweep of one level: d(n) = r(n) - sum_lower APC(j) d(col)
+// ---- triangular solves ---------------------------------------------------------
+// Level-scheduled ims_base_ilu0a with three fusions that remove whole vector passes:
+//  * rows of level 0 have no lower entries, so their forward value is r itself: the
+//    level-0 forward launch is elided and readers take rin[col] for such neighbours;
+//  * rows of the LAST level have no upper entries, so their backward step is only the
+//    multiplication by the inverse pivot: it is fused into their forward launch;
+//  * (CG) rho = r.z is accumulated by the launches that finalise z (IluDot).
+struct IluDot {
+  double *partial;  // this launch's partial slots (one per WARP), nullptr = no dot
+};
+
+// per-warp partial of rho: no block-level barrier, so CTAs retire as soon as their rows are done
+__device__ __forceinline__ void ilu_dot_finish(double s, const IluDot &D) {
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) D.partial[blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5)] = s;
+}
+
+// rho = sum of the per-warp partials of every finalising launch: fixed chunking and order
+// (deterministic); the last CTA to finish combines the per-CTA sums and writes rho, beta
 __global__ void __launch_bounds__(kBlock)
-ilu0_fwd_level_kernel(int r0, int r1, const int *__restrict__ slice_ptr,
+ilu_dot_reduce_kernel(int nslots, const double *__restrict__ partial, double *__restrict__ cta_sums,
+                      unsigned int *ticket, double *rho_out, double *beta_out, const double *rho0,
+                      const int *__restrict__ done) {
+  __shared__ double sh[8];
+  __shared__ bool last;
+  if (done && *done) return;
+  const int chunk = (nslots + gridDim.x - 1) / gridDim.x;
+  const int i0 = blockIdx.x * chunk, i1 = min(nslots, i0 + chunk);
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int i = i0 + threadIdx.x;
+  for (; i + 3 * kBlock < i1; i += 4 * kBlock) {
+    a0 += partial[i];
+    a1 += partial[i + kBlock];
+    a2 += partial[i + 2 * kBlock];
+    a3 += partial[i + 3 * kBlock];
+  }
+  for (; i < i1; i += kBlock) a0 += partial[i];
+  double a = block_sum((a0 + a1) + (a2 + a3), sh);
+  if (threadIdx.x == 0) cta_sums[blockIdx.x] = a;
+  if (last_block(ticket, &last)) {
+    double t = (threadIdx.x < gridDim.x) ? cta_sums[threadIdx.x] : 0.0;
+    t = block_sum(t, sh);
+    if (threadIdx.x == 0) {
+      *rho_out = t;
+      *beta_out = t / *rho0;
+    }
+  }
+}
+
+// forward sweep of one level (l >= 1): d(n) = r(n) - sum_lower APC(j) d(col)
+// FINAL: the level is the last one -> d(n) = (...) * APC(n) is already the result
+template <bool FINAL>
+__global__ void __launch_bounds__(kBlock, 8)
+ilu0_fwd_level_kernel(int r0, int r1, int lvl1_start, const int *__restrict__ slice_ptr,
                       const unsigned char *__restrict__ nlow, const int *__restrict__ col,
                       const double *__restrict__ lu, const double *__restrict__ rin,
-                      double *__restrict__ d, const int *__restrict__ done) {
-  const int r = r0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= r1) return;
+                      double *__restrict__ d, const int *__restrict__ done, IluDot D) {
   if (done && *done) return;
-  const int lo = nlow[r];
-  const long long base = (long long)slice_ptr[r >> 5] + (r & 31);
-  double tv = rin[r];
-  for (int k0 = 1; k0 <= lo; k0 += 4) {
-    double v[4], dv[4];
-    int c[4];
+  double dot = 0.0;
+  const int r = r0 + blockIdx.x * blockDim.x + threadIdx.x;  // one row per thread: every row's loads in flight at once
+  if (r < r1) {
+    const int lo = nlow[r];
+    const long long base = (long long)slice_ptr[r >> 5] + (r & 31);
+    const double rr = rin[r];
+    double tv = rr;
+    for (int k0 = 1; k0 <= lo; k0 += 4) {
+      double v[4], dv[4];
+      int c[4];
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const bool ok = (k0 + u) <= lo;
-      const long long p = base + 32LL * (k0 + u);
-      v[u] = ok ? __ldg(lu + p) : 0.0;
-      c[u] = ok ? __ldg(col + p) : r;
+      for (int u = 0; u < 4; u++) {
+        const bool ok = (k0 + u) <= lo;
+        const long long p = base + 32LL * (k0 + u);
+        v[u] = ok ? __ldg(lu + p) : 0.0;
+        c[u] = ok ? __ldg(col + p) : r;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        dv[u] = 0.0;
+        if ((k0 + u) <= lo) dv[u] = (c[u] < lvl1_start) ? rin[c[u]] : d[c[u]];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if ((k0 + u) <= lo) tv = tv - v[u] * dv[u];
     }
-#pragma unroll
-    for (int u = 0; u < 4; u++) dv[u] = ((k0 + u) <= lo) ? d[c[u]] : 0.0;
-#pragma unroll
-    for (int u = 0; u < 4; u++)
-      if ((k0 + u) <= lo) tv = tv - v[u] * dv[u];
+    if (FINAL) {
+      tv = tv * __ldg(lu + base);
+      dot += rr * tv;
+    }
+    d[r] = tv;
   }
-  d[r] = tv;
+  if (FINAL && D.partial) ilu_dot_finish(dot, D);
 }
 
 // backward sweep of one level: d(n) = (d(n) - sum_upper APC(j) d(col)) * APC(n)
-__global__ void __launch_bounds__(kBlock)
+// LEVEL0: the forward value of the row is rin(n) itself
+template <bool LEVEL0>
+__global__ void __launch_bounds__(kBlock, 8)
 ilu0_bwd_level_kernel(int r0, int r1, const int *__restrict__ slice_ptr,
                       const unsigned char *__restrict__ rowlen,
                       const unsigned char *__restrict__ nlow, const int *__restrict__ col,
-                      const double *__restrict__ lu, double *__restrict__ d,
-                      const int *__restrict__ done) {
-  const int r = r0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= r1) return;
+                      const double *__restrict__ lu, const double *__restrict__ rin,
+                      double *__restrict__ d, const int *__restrict__ done, IluDot D) {
   if (done && *done) return;
-  const int len = rowlen[r], lo = nlow[r];
-  const long long base = (long long)slice_ptr[r >> 5] + (r & 31);
-  double tv = d[r];
-  const double piv = __ldg(lu + base);
-  for (int k0 = lo + 1; k0 < len; k0 += 4) {
-    double v[4], dv[4];
-    int c[4];
+  double dot = 0.0;
+  const int r = r0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < r1) {
+    const int len = rowlen[r], lo = nlow[r];
+    const long long base = (long long)slice_ptr[r >> 5] + (r & 31);
+    const double rr = rin[r];
+    double tv = LEVEL0 ? rr : d[r];
+    const double piv = __ldg(lu + base);
+    for (int k0 = lo + 1; k0 < len; k0 += 4) {
+      double v[4], dv[4];
+      int c[4];
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const bool ok = (k0 + u) < len;
-      const long long p = base + 32LL * (k0 + u);
-      v[u] = ok ? __ldg(lu + p) : 0.0;
-      c[u] = ok ? __ldg(col + p) : r;
+      for (int u = 0; u < 4; u++) {
+        const bool ok = (k0 + u) < len;
+        const long long p = base + 32LL * (k0 + u);
+        v[u] = ok ? __ldg(lu + p) : 0.0;
+        c[u] = ok ? __ldg(col + p) : r;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) dv[u] = ((k0 + u) < len) ? d[c[u]] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if ((k0 + u) < len) tv = tv - v[u] * dv[u];
     }
-#pragma unroll
-    for (int u = 0; u < 4; u++) dv[u] = ((k0 + u) < len) ? d[c[u]] : 0.0;
-#pragma unroll
-    for (int u = 0; u < 4; u++)
-      if ((k0 + u) < len) tv = tv - v[u] * dv[u];
+    tv = tv * piv;
+    d[r] = tv;
+    dot += rr * tv;
   }
-  d[r] = tv * piv;
+  if (D.partial) ilu_dot_finish(dot, D);
 }
 
 int ilu0_factor(const mf6gpu_matrix &A, const double *aval, double *lu, double relax,
@@ -162,20 +233,46 @@ int ilu0_factor(const mf6gpu_matrix &A, const double *aval, double *lu, double r
 }
 
 int ilu0_apply(const mf6gpu_matrix &A, const double *lu, const double *rin, double *d,
-               const int *done, cudaStream_t s) {
+               const int *done, cudaStream_t s, const IluDotArgs *dot) {
   int launches = 0;
-  for (int l = 0; l < A.nlevels; l++) {
+  const int L = A.nlevels;
+  const int lvl1 = (L > 1) ? A.level_ptr[1] : A.n;
+  int slot = 0;  // next free partial slot
+  // forward: levels 1 .. L-1 (level 0 is elided); the last one also finalises its rows
+  for (int l = 1; l < L; l++) {
     const int r0 = A.level_ptr[l], r1 = A.level_ptr[l + 1];
     if (r1 <= r0) continue;
-    ilu0_fwd_level_kernel<<<(r1 - r0 + kBlock - 1) / kBlock, kBlock, 0, s>>>(
-        r0, r1, A.slice_ptr.p, A.nlow.p, A.col.p, lu, rin, d, done);
+    const int g = (r1 - r0 + kBlock - 1) / kBlock;
+    if (l == L - 1) {
+      IluDot D{dot ? dot->partial + slot : nullptr};
+      slot += g * (kBlock / 32);
+      ilu0_fwd_level_kernel<true><<<g, kBlock, 0, s>>>(r0, r1, lvl1, A.slice_ptr.p, A.nlow.p, A.col.p, lu,
+                                                        rin, d, done, D);
+    } else {
+      ilu0_fwd_level_kernel<false><<<g, kBlock, 0, s>>>(r0, r1, lvl1, A.slice_ptr.p, A.nlow.p, A.col.p, lu,
+                                                         rin, d, done, IluDot{nullptr});
+    }
     launches++;
   }
-  for (int l = A.nlevels - 1; l >= 0; l--) {
+  // backward: levels L-2 .. 0 (L == 1: the single level is level 0)
+  for (int l = (L > 1 ? L - 2 : 0); l >= 0; l--) {
     const int r0 = A.level_ptr[l], r1 = A.level_ptr[l + 1];
     if (r1 <= r0) continue;
-    ilu0_bwd_level_kernel<<<(r1 - r0 + kBlock - 1) / kBlock, kBlock, 0, s>>>(
-        r0, r1, A.slice_ptr.p, A.rowlen.p, A.nlow.p, A.col.p, lu, d, done);
+    const int g = (r1 - r0 + kBlock - 1) / kBlock;
+    IluDot D{dot ? dot->partial + slot : nullptr};
+    slot += g * (kBlock / 32);
+    if (l == 0)
+      ilu0_bwd_level_kernel<true><<<g, kBlock, 0, s>>>(r0, r1, A.slice_ptr.p, A.rowlen.p, A.nlow.p, A.col.p,
+                                                        lu, rin, d, done, D);
+    else
+      ilu0_bwd_level_kernel<false><<<g, kBlock, 0, s>>>(r0, r1, A.slice_ptr.p, A.rowlen.p, A.nlow.p, A.col.p,
+                                                         lu, rin, d, done, D);
+    launches++;
+  }
+  if (dot) {
+    const int rb = std::max(1, std::min(148, slot / (4 * kBlock)));
+    ilu_dot_reduce_kernel<<<rb, kBlock, 0, s>>>(slot, dot->partial, dot->cta_sums, dot->ticket, dot->rho_out,
+                                                dot->beta_out, dot->rho0, done);
     launches++;
   }
   return launches;

@@ -7,7 +7,17 @@ namespace mf6 {
 // to 1 by any row whose pivot fails the reference's checks.  Returns launches.
 int ilu0_factor(const mf6gpu_matrix &A, const double *aval, double *lu, double relax,
                 double delta, int ipcflag, int *d_failflag, cudaStream_t s);
+// optional fused rho = rin . d (CG): accumulated by the launches that finalise d
+struct IluDotArgs {
+  double *partial;       // [(n / kBlock + nlevels + 1) * 8] scratch: one slot per WARP of every finalising launch
+  double *cta_sums;      // [256] scratch of the reduce kernel
+  unsigned int *ticket;
+  double *rho_out;       // receives the dot product
+  double *beta_out;      // receives rho / *rho0
+  const double *rho0;
+};
 // d = (LU)^-1 rin.  `done` (device flag, may be null) turns the kernels into no-ops.
+// rin and d must be different arrays.
 int ilu0_apply(const mf6gpu_matrix &A, const double *lu, const double *rin, double *d,
-               const int *done, cudaStream_t s);
+               const int *done, cudaStream_t s, const IluDotArgs *dot = nullptr);
 }  // namespace mf6

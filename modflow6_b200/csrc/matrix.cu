@@ -13,6 +13,15 @@
 
 namespace mf6 {
 
+int max_blocks() {
+  static int v = [] {
+    const char *e = std::getenv("MF6GPU_GRID_CAP");
+    int c = e ? std::atoi(e) : 0;
+    return c > 0 ? c : 148 * 8;
+  }();
+  return v;
+}
+
 std::string &last_error() {
   static thread_local std::string e;
   return e;

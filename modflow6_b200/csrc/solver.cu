@@ -367,6 +367,7 @@ __global__ void copy_kernel(int n, const double *__restrict__ a, double *__restr
 __global__ void init_state_kernel(KState *st, double epfact, double dvclose, double rclose,
                                   int icnvgopt, int sum_cap, int iscl, int reset_count) {
   st->rho = st->rho0 = st->alpha = st->alpha0 = st->omega = st->omega0 = st->beta = 0.0;
+  st->rho_acc = 0.0;
   st->epfact = epfact;
   st->dvclose = dvclose;
   st->rclose = rclose;
@@ -529,6 +530,14 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
   }
   int innerit = 0;
   const int *ord = A->ord_ptr();
+  const bool fuse_dot = (A->nlevels <= 16);
+  IluDotArgs idot;
+  idot.partial = ilu_partial.p;
+  idot.cta_sums = partial.p + 2 * kMaxBlocks;
+  idot.ticket = tickets.p + 4;
+  idot.rho_out = &st.p->rho;
+  idot.beta_out = &st.p->beta;
+  idot.rho0 = &st.p->rho0;
   // polling cadence: cheap iterations (small n) are batched deeper
   const int batch = (N > 2000000) ? 4 : 16;
   if (itmax > 0) {
@@ -543,12 +552,19 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
         prof_on = (b == 0);  // time one iteration per polling batch
         if (!bcgs) {
           prof_begin(PC_ILU);
-          launches += ilu0_apply(*A, lu.p, d.p, z.p, &st.p->done, S);
-          prof_end();
-          prof_begin(PC_DOT);
-          dot_kernel<<<G, kBlock, 0, S>>>(N, d.p, z.p, partial.p, tickets.p + TK_DOT, st.p,
-                                          FIN_CG_RHO, nullptr, 1);
-          prof_end();
+          if (fuse_dot) {
+            // z = M^-1 d with rho = d.z (and beta = rho/rho0) accumulated by the same launches
+            launches += ilu0_apply(*A, lu.p, d.p, z.p, &st.p->done, S, &idot);
+            prof_end();
+          } else {
+            launches += ilu0_apply(*A, lu.p, d.p, z.p, &st.p->done, S);
+            prof_end();
+            prof_begin(PC_DOT);
+            dot_kernel<<<G, kBlock, 0, S>>>(N, d.p, z.p, partial.p, tickets.p + TK_DOT, st.p,
+                                            FIN_CG_RHO, nullptr, 1);
+            prof_end();
+            launches += 1;
+          }
           prof_begin(PC_PUPD);
           cg_p_kernel<<<G, kBlock, 0, S>>>(N, z.p, p.p, st.p, first);
           prof_end();
@@ -562,7 +578,7 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
                                                 ord, partial.p, pmx.p, pmr.p, tickets.p + TK_UPD,
                                                 st.p, sp);
           prof_end();
-          launches += 4;
+          launches += 3;
         } else {
           dot_kernel<<<G, kBlock, 0, S>>>(N, dhat.p, d.p, partial.p, tickets.p + TK_DOT, st.p,
                                           FIN_BCGS_RHO, nullptr, 1);
@@ -681,6 +697,7 @@ int mf6gpu_solver_create(mf6gpu_matrix *m, const mf6gpu_ims_settings *settings,
       s->hb.alloc(n);
       s->st.alloc_zero(1);
       s->partial.alloc_zero(4 * (size_t)kMaxBlocks);
+      s->ilu_partial.alloc_zero((n / kBlock + (size_t)m->nlevels + 2) * (kBlock / 32));
       s->pmx.alloc_zero((size_t)kMaxBlocks);
       s->pmr.alloc_zero((size_t)kMaxBlocks);
       s->tickets.alloc_zero(8);

@@ -8,6 +8,7 @@ namespace mf6 {
 // host inside the inner loop (only `done`/`iter` are polled every few iterations).
 struct KState {
   double rho, rho0, alpha, alpha0, omega, omega0, beta;
+  double rho_acc;      // running r.z of the fused ILU-apply dot (0 between applies)
   double l2norm0, epfact, dvclose, rclose;
   double deltax, rmax, l2norm;
   int xloc, rloc;      // device-numbering rows of deltax / rmax
@@ -37,6 +38,7 @@ struct mf6gpu_solver {
   mf6::DevBuf<double> hx, hb;             // staging in original numbering
   mf6::DevBuf<mf6::KState> st;
   mf6::DevBuf<double> partial;            // [4 * kMaxBlocks]
+  mf6::DevBuf<double> ilu_partial;        // [n / kBlock + 2] fused ILU-apply dot partials
   mf6::DevBuf<mf6::MaxLoc> pmx, pmr;      // [kMaxBlocks]
   mf6::DevBuf<unsigned int> tickets;      // [8]
   mf6::DevBuf<int> failflag;

@@ -179,7 +179,7 @@ def test_exact_initial_guess_and_diagonal_scaling(system):
     it, cv = GpuLinearSolver(A, ims).solve(1, b, xg)
     ito, cvo = OracleIms(m.ia, m.ja, ims).solve(a, xo, b)
     assert cv == 1 and cvo == 1 and abs(it - ito) <= max(8, ito // 5)
-    assert np.abs(xg - xo).max() <= 10 * 1e-8
+    assert np.abs(xg - xo).max() <= 50 * 1e-8   # BiCGSTAB: see test_krylov_matches_oracle
     assert np.allclose(A.get_values(), a, rtol=1e-13)    # unscaled again
 
 
