@@ -45,6 +45,7 @@ typedef struct mf6gpu_matrix mf6gpu_matrix;
 typedef struct mf6gpu_vector mf6gpu_vector;
 typedef struct mf6gpu_solver mf6gpu_solver;
 typedef struct mf6gpu_solution mf6gpu_solution;
+typedef struct mf6gpu_comm mf6gpu_comm;
 
 /* ---- library ------------------------------------------------------------ */
 int mf6gpu_abi_version(void);
@@ -74,6 +75,11 @@ int mf6gpu_matrix_zero_entries(mf6gpu_matrix *m);
 int mf6gpu_matrix_get_values(mf6gpu_matrix *m, double *amat);
 /* spm_multiply (SparseMatrix.f90:298-316 -> amux): y = A x, host vectors */
 int mf6gpu_matrix_multiply(mf6gpu_matrix *m, const double *x, double *y);
+/* split-model variant: n_own rows whose columns may name halo cells n_own..n_ext-1;
+ * global_id[n_ext] (may be NULL) breaks arg-max ties like the unsplit model would */
+int mf6gpu_matrix_create_ext(int32_t n_own, int32_t n_ext, int32_t nja, const int32_t *ia,
+                             const int32_t *ja, int32_t index_base, int32_t gpu_ordering,
+                             const int32_t *global_id, mf6gpu_matrix **out);
 /* structure facts: 0 n, 1 nja, 2 number of ILU levels, 3 ordering, 4 SELL slots */
 int64_t mf6gpu_matrix_info(const mf6gpu_matrix *m, int what);
 /* final permutation: perm[new] = old (0-based), length n */
@@ -122,11 +128,38 @@ int mf6gpu_solver_profile_get(mf6gpu_solver *s, int32_t cls, double *total_ms, i
 int mf6gpu_solver_factor(mf6gpu_solver *s, int32_t *npivot_fixes);
 int mf6gpu_solver_apply_preconditioner(mf6gpu_solver *s, const double *r, double *z);
 
+/* ---- one process per GPU: communicator of the split-model path ------------
+ * replaces MpiRunControl / MpiRouter / PETSc's MPI use for the path in scope
+ * (src/Distributed/MpiRouter.f90:238-343, src/Solution/ParallelSolution.f90:38-246).
+ * Rank 0 calls mf6gpu_comm_unique_id, the 128 bytes are broadcast by the host
+ * launcher (MPI, torch.distributed, ...), every rank calls mf6gpu_comm_create. */
+int mf6gpu_comm_unique_id(void *out128);
+int mf6gpu_comm_create(int32_t nranks, int32_t rank, const void *id128, mf6gpu_comm **out);
+int mf6gpu_comm_destroy(mf6gpu_comm *c);
+int mf6gpu_comm_rank(const mf6gpu_comm *c);
+int mf6gpu_comm_size(const mf6gpu_comm *c);
+
 /* ---- NumericalSolutionType + GWF formulate, device resident --------------- */
 int mf6gpu_solution_create(const mf6gpu_gwf_model *model,
                            const mf6gpu_sln_settings *sln,
                            const mf6gpu_ims_settings *ims,
                            mf6gpu_solution **out);
+/* split-model path (GWF-GWF exchanges / interface model, exg-gwfgwf.f90:363-661,
+ * SpatialModelConnection.f90:306-510): `model` describes this rank's submodel EXTENDED by its
+ * halo cells -- cells 0..n_own-1 are owned, cells n_own..nodes-1 are the neighbour cells named by
+ * the exchanges (their rows hold the diagonal only; exchange connections are ordinary
+ * connections with their own jas / cl1 / cl2 / hwva / ihc).  Neighbour k (rank nbr_rank[k])
+ * receives the owned cells send_idx[send_ptr[k]..send_ptr[k+1]) and fills the halo cells
+ * n_own + recv_ptr[k] .. n_own + recv_ptr[k+1].  global_id[nodes] = cell numbers of the unsplit
+ * model.  Every rank must pass the same list of package types to set_packages (possibly with
+ * zero bounds).  Heads/ibound of halo cells move by NCCL send/recv, Krylov and outer-loop scalars
+ * by small all-gathers; the preconditioner is ILU0/MILU0 of the rank's diagonal block
+ * (block Jacobi, as PetscSolver.F90:251-278). */
+int mf6gpu_solution_create_dist(const mf6gpu_gwf_model *model, const mf6gpu_sln_settings *sln,
+                                const mf6gpu_ims_settings *ims, mf6gpu_comm *comm, int32_t n_own,
+                                int32_t nnbr, const int32_t *nbr_rank, const int32_t *send_ptr,
+                                const int32_t *send_idx, const int32_t *recv_ptr,
+                                const int32_t *global_id, mf6gpu_solution **out);
 int mf6gpu_solution_destroy(mf6gpu_solution *s);
 /* bnd_rp: stress-period data of every package (copied to the device) */
 int mf6gpu_solution_set_packages(mf6gpu_solution *s, int32_t npkg,

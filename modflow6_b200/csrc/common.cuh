@@ -104,6 +104,12 @@ struct PinnedBuf {
   }
 };
 
+// layout of MaxLoc (below) for structs that the host must be able to size
+struct MaxLocPOD {
+  double a, v;
+  int ord, idx;
+};
+
 constexpr int kBlock = 256;
 // grid cap of the grid-stride kernels: 148 SMs x 8 resident 256-thread CTAs by default
 // (MF6GPU_GRID_CAP overrides it for tuning experiments)

@@ -216,16 +216,16 @@ int ilu0_factor(const mf6gpu_matrix &A, const double *aval, double *lu, double r
     if (r1 <= r0) continue;
     const int blocks = (r1 - r0 + 127) / 128;
     if (A.maxlen <= 8)
-      ilu0_factor_level_kernel<8><<<blocks, 128, 0, s>>>(r0, r1, A.slice_ptr.p, A.rowlen.p, A.nlow.p,
+      ilu0_factor_level_kernel<8><<<blocks, 128, 0, s>>>(r0, r1, A.slice_ptr.p, A.rowlen_loc(), A.nlow.p,
                                                          A.col.p, aval, lu, relax, delta, ipcflag, d_failflag);
     else if (A.maxlen <= 16)
-      ilu0_factor_level_kernel<16><<<blocks, 128, 0, s>>>(r0, r1, A.slice_ptr.p, A.rowlen.p, A.nlow.p,
+      ilu0_factor_level_kernel<16><<<blocks, 128, 0, s>>>(r0, r1, A.slice_ptr.p, A.rowlen_loc(), A.nlow.p,
                                                           A.col.p, aval, lu, relax, delta, ipcflag, d_failflag);
     else if (A.maxlen <= 32)
-      ilu0_factor_level_kernel<32><<<blocks, 128, 0, s>>>(r0, r1, A.slice_ptr.p, A.rowlen.p, A.nlow.p,
+      ilu0_factor_level_kernel<32><<<blocks, 128, 0, s>>>(r0, r1, A.slice_ptr.p, A.rowlen_loc(), A.nlow.p,
                                                           A.col.p, aval, lu, relax, delta, ipcflag, d_failflag);
     else
-      ilu0_factor_level_kernel<64><<<blocks, 128, 0, s>>>(r0, r1, A.slice_ptr.p, A.rowlen.p, A.nlow.p,
+      ilu0_factor_level_kernel<64><<<blocks, 128, 0, s>>>(r0, r1, A.slice_ptr.p, A.rowlen_loc(), A.nlow.p,
                                                           A.col.p, aval, lu, relax, delta, ipcflag, d_failflag);
     launches++;
   }
@@ -262,10 +262,10 @@ int ilu0_apply(const mf6gpu_matrix &A, const double *lu, const double *rin, doub
     IluDot D{dot ? dot->partial + slot : nullptr};
     slot += g * (kBlock / 32);
     if (l == 0)
-      ilu0_bwd_level_kernel<true><<<g, kBlock, 0, s>>>(r0, r1, A.slice_ptr.p, A.rowlen.p, A.nlow.p, A.col.p,
+      ilu0_bwd_level_kernel<true><<<g, kBlock, 0, s>>>(r0, r1, A.slice_ptr.p, A.rowlen_loc(), A.nlow.p, A.col.p,
                                                         lu, rin, d, done, D);
     else
-      ilu0_bwd_level_kernel<false><<<g, kBlock, 0, s>>>(r0, r1, A.slice_ptr.p, A.rowlen.p, A.nlow.p, A.col.p,
+      ilu0_bwd_level_kernel<false><<<g, kBlock, 0, s>>>(r0, r1, A.slice_ptr.p, A.rowlen_loc(), A.nlow.p, A.col.p,
                                                          lu, rin, d, done, D);
     launches++;
   }

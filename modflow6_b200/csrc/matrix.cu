@@ -84,12 +84,15 @@ void launch_scatter(int n, const int *perm, const double *in, double *out, cudaS
 }
 
 // ------------------------------------------------------------- host build ---
-static void build_matrix(mf6gpu_matrix &M, int n, int nja, const int32_t *ia_in,
-                         const int32_t *ja_in, int base, int ordering) {
-  MF6_REQUIRE(n > 0 && nja >= n, "matrix_create: bad dimensions");
+// n = owned rows, n_ext >= n = owned + halo columns; gid (optional, [n_ext]) = global ids used
+// for arg-max tie-breaks in the split-model path
+static void build_matrix(mf6gpu_matrix &M, int n, int n_ext, int nja, const int32_t *ia_in,
+                         const int32_t *ja_in, int base, int ordering, const int32_t *gid) {
+  MF6_REQUIRE(n > 0 && nja >= n && n_ext >= n, "matrix_create: bad dimensions");
   MF6_REQUIRE(ordering == MF6GPU_ORDER_NATURAL || ordering == MF6GPU_ORDER_MULTICOLOR,
               "matrix_create: unknown gpu_ordering");
   M.n = n;
+  M.n_ext = n_ext;
   M.nja = nja;
   M.ordering = ordering;
   std::vector<int> ia(n + 1), ja(nja);
@@ -101,6 +104,8 @@ static void build_matrix(mf6gpu_matrix &M, int n, int nja, const int32_t *ia_in,
     MF6_REQUIRE(ja[ia[r]] == r, "matrix_create: rows must store the diagonal first (Sparse.f90:217-239)");
     MF6_REQUIRE(ia[r + 1] - ia[r] <= 255, "matrix_create: more than 255 entries in a row");
   }
+  for (int p = 0; p < nja; p++) MF6_REQUIRE(ja[p] >= 0 && ja[p] < n_ext, "matrix_create: column out of range");
+  auto is_halo = [&](int c) { return c >= n; };
   // --- elimination order (ordidx[old] = position in the reference-style loop)
   std::vector<int> ordidx(n);
   if (ordering == MF6GPU_ORDER_NATURAL) {
@@ -114,6 +119,7 @@ static void build_matrix(mf6gpu_matrix &M, int n, int nja, const int32_t *ia_in,
       unsigned long long mask = 0ull;
       bool big = false;
       for (int p = ia[v] + 1; p < ia[v + 1]; p++) {
+        if (is_halo(ja[p])) continue;
         int c = color[ja[p]];
         if (c >= 64) big = true;
         else if (c >= 0) mask |= (1ull << c);
@@ -125,7 +131,7 @@ static void build_matrix(mf6gpu_matrix &M, int n, int nja, const int32_t *ia_in,
       if (big || c == 64) {  // rare: fall back to an explicit set
         std::vector<char> used(ncolors + 2, 0);
         for (int p = ia[v] + 1; p < ia[v + 1]; p++)
-          if (color[ja[p]] >= 0) used[color[ja[p]]] = 1;
+          if (!is_halo(ja[p]) && color[ja[p]] >= 0) used[color[ja[p]]] = 1;
         c = 0;
         while (used[c]) c++;
       }
@@ -147,6 +153,7 @@ static void build_matrix(mf6gpu_matrix &M, int n, int nja, const int32_t *ia_in,
     int lv = 0;
     for (int p = ia[v] + 1; p < ia[v + 1]; p++) {
       int u = ja[p];
+      if (is_halo(u)) continue;
       if (ordidx[u] < o && level[u] + 1 > lv) lv = level[u] + 1;
     }
     level[v] = lv;
@@ -157,8 +164,9 @@ static void build_matrix(mf6gpu_matrix &M, int n, int nja, const int32_t *ia_in,
   M.level_ptr.assign(nlevels + 1, 0);
   for (int v = 0; v < n; v++) M.level_ptr[level[v] + 1]++;
   for (int l = 0; l < nlevels; l++) M.level_ptr[l + 1] += M.level_ptr[l];
-  M.perm.resize(n);
-  M.iperm.resize(n);
+  M.perm.resize(n_ext);
+  M.iperm.resize(n_ext);
+  for (int h = n; h < n_ext; h++) M.perm[h] = M.iperm[h] = h;  // halo columns keep their place
   {
     std::vector<int> cur(M.level_ptr.begin(), M.level_ptr.end() - 1);
     for (int o = 0; o < n; o++) {
@@ -170,7 +178,7 @@ static void build_matrix(mf6gpu_matrix &M, int n, int nja, const int32_t *ia_in,
   }
   // --- SELL-32 structure
   M.nslices = (n + 31) / 32;
-  std::vector<unsigned char> rowlen(n), nlow(n);
+  std::vector<unsigned char> rowlen(n), nlow(n), rowlen_loc(n);
   std::vector<int> slice_ptr(M.nslices + 1, 0);
   int maxlen = 0;
   for (int s = 0; s < M.nslices; s++) {
@@ -196,21 +204,25 @@ static void build_matrix(mf6gpu_matrix &M, int n, int nja, const int32_t *ia_in,
     long long base_slot = (long long)slice_ptr[r >> 5] + (r & 31);
     int w = (slice_ptr[(r >> 5) + 1] - slice_ptr[r >> 5]) / 32;
     tmp.clear();
-    for (int p = ia[v] + 1; p < ia[v + 1]; p++) tmp.emplace_back(ordidx[ja[p]], p);
+    // local neighbours in elimination order, then halo columns (ascending): halo sorts last
+    for (int p = ia[v] + 1; p < ia[v + 1]; p++)
+      tmp.emplace_back(is_halo(ja[p]) ? (n + ja[p]) : ordidx[ja[p]], p);
     std::sort(tmp.begin(), tmp.end());
     col[base_slot] = r;
     csr2sell[ia[v]] = (int)base_slot;
-    int lo = 0;
+    int lo = 0, nloc = 1;
     for (size_t k = 0; k < tmp.size(); k++) {
       int p = tmp[k].second;
       long long slot = base_slot + 32LL * (long long)(k + 1);
       col[slot] = M.iperm[ja[p]];
       csr2sell[p] = (int)slot;
-      if (tmp[k].first < ordidx[v]) lo++;
+      if (!is_halo(ja[p]) && tmp[k].first < ordidx[v]) lo++;
+      if (!is_halo(ja[p])) nloc++;
       MF6_REQUIRE(ja[p] != v, "matrix_create: duplicate diagonal entry");
       if (k > 0) MF6_REQUIRE(tmp[k].first != tmp[k - 1].first, "matrix_create: duplicate column in a row");
     }
     nlow[r] = (unsigned char)lo;
+    rowlen_loc[r] = (unsigned char)nloc;
     for (int k = (int)tmp.size() + 1; k < w; k++) col[base_slot + 32LL * k] = r;  // padding
   }
   // padding lanes of the last slice
@@ -222,9 +234,15 @@ static void build_matrix(mf6gpu_matrix &M, int n, int nja, const int32_t *ia_in,
   // --- upload
   M.d_perm.upload(M.perm);
   M.d_iperm.upload(M.iperm);
-  if (ordering == MF6GPU_ORDER_NATURAL && nlevels > 1) {
-    M.d_ord.upload(M.perm);  // elimination index of final row r is its original index
+  if (gid) {
+    std::vector<int> o(n);
+    for (int r = 0; r < n; r++) o[r] = gid[M.perm[r]] - base;  // global cell id of final row r
+    M.d_ord.upload(o);
+  } else if (ordering == MF6GPU_ORDER_NATURAL && nlevels > 1) {
+    std::vector<int> o(M.perm.begin(), M.perm.begin() + n);
+    M.d_ord.upload(o);  // elimination index of final row r is its original index
   }
+  if (n_ext > n) M.rowlen_loc_buf.upload(rowlen_loc);
   M.slice_ptr.upload(slice_ptr);
   M.col.upload(col);
   M.rowlen.upload(rowlen);
@@ -232,8 +250,8 @@ static void build_matrix(mf6gpu_matrix &M, int n, int nja, const int32_t *ia_in,
   M.csr2sell.upload(csr2sell);
   M.val.alloc_zero((size_t)M.nslots);
   M.stage.alloc((size_t)nja);
-  M.xs.alloc((size_t)n);
-  M.ys.alloc((size_t)n);
+  M.xs.alloc_zero((size_t)n_ext);
+  M.ys.alloc_zero((size_t)n_ext);
 }
 
 }  // namespace mf6
@@ -250,7 +268,23 @@ int mf6gpu_matrix_create(int32_t n, int32_t nja, const int32_t *ia, const int32_
     MF6_CK(cudaGetDevice(&dev));
     auto *M = new mf6gpu_matrix();
     try {
-      build_matrix(*M, n, nja, ia, ja, index_base, gpu_ordering);
+      build_matrix(*M, n, n, nja, ia, ja, index_base, gpu_ordering, nullptr);
+    } catch (...) {
+      delete M;
+      throw;
+    }
+    *out = M;
+  });
+}
+
+int mf6gpu_matrix_create_ext(int32_t n_own, int32_t n_ext, int32_t nja, const int32_t *ia,
+                             const int32_t *ja, int32_t index_base, int32_t gpu_ordering,
+                             const int32_t *global_id, mf6gpu_matrix **out) {
+  return guard([&] {
+    MF6_REQUIRE(out && ia && ja, "matrix_create_ext: null argument");
+    auto *M = new mf6gpu_matrix();
+    try {
+      build_matrix(*M, n_own, n_ext, nja, ia, ja, index_base, gpu_ordering, global_id);
     } catch (...) {
       delete M;
       throw;
@@ -324,7 +358,7 @@ int64_t mf6gpu_matrix_info(const mf6gpu_matrix *m, int what) {
 int mf6gpu_matrix_get_permutation(const mf6gpu_matrix *m, int32_t *perm) {
   return guard([&] {
     MF6_REQUIRE(m && perm, "matrix_get_permutation: null argument");
-    std::memcpy(perm, m->perm.data(), sizeof(int) * (size_t)m->n);
+    std::memcpy(perm, m->perm.data(), sizeof(int) * (size_t)m->n);  // owned rows
   });
 }
 

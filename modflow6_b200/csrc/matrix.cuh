@@ -15,7 +15,8 @@
 #include "../../include/mf6gpu.h"
 
 struct mf6gpu_matrix {
-  int n = 0, nja = 0;
+  int n = 0, nja = 0;   // n = OWNED rows
+  int n_ext = 0;        // owned + halo columns (== n on a single GPU); vectors have this length
   int ordering = 0;
   int nlevels = 0;
   int nslices = 0;
@@ -30,6 +31,8 @@ struct mf6gpu_matrix {
   mf6::DevBuf<int> col;        // [nslots]
   mf6::DevBuf<double> val;     // [nslots]
   mf6::DevBuf<unsigned char> rowlen, nlow;  // [n]
+  mf6::DevBuf<unsigned char> rowlen_loc_buf; // [n] entries without halo columns (ILU); empty => same as rowlen
+  const unsigned char *rowlen_loc() const { return rowlen_loc_buf.n ? rowlen_loc_buf.p : rowlen.p; }
   mf6::DevBuf<int> csr2sell;   // [nja] slot of each original CSR entry
   mf6::DevBuf<double> stage;   // [nja] H2D/D2H staging of CSR values
   mf6::DevBuf<double> xs, ys;  // [n] staging vectors for host multiply

@@ -482,14 +482,17 @@ ls_fixup_kernel(ModelView M, const double *__restrict__ x, double *__restrict__ 
 // constant-head columns to the right-hand side; the slots are in that order too.
 
 // ---- outer-iteration vector kernels ---------------------------------------------
+// every field is a double so that the record can be all-gathered across ranks as is
 struct OuterState {
   double hncg;      // signed largest |x - xtemp|
-  int loc;          // device row
-  int nur_flag;
+  double loc;       // device row of it (single GPU)
+  double loc_ord;   // tie-break / global cell id of it
+  double nur_flag;
   double dxold_max;
   double ptc_max;   // max |r| / volume
   double l2;        // sum r^2
   double rin, rout;
+  double pad;
 };
 
 // sln_get_dxmax (:3122-3153)
@@ -514,7 +517,8 @@ dxmax_kernel(int n, const double *__restrict__ x, const double *__restrict__ xte
     g = block_maxloc(g, shm);
     if (threadIdx.x == 0) {
       os->hncg = g.v;
-      os->loc = g.idx;
+      os->loc = (double)g.idx;
+      os->loc_ord = (double)g.ord;
     }
   }
 }
@@ -582,7 +586,7 @@ __global__ void nur_kernel(ModelView M, const int *__restrict__ ibotnode, double
     if (M.icelltype[r] > 0) {
       const double botm = M.bot[ibotnode[r]];
       if (x[r] < botm) {
-        os->nur_flag = 1;
+        os->nur_flag = 1.0;
         const double xx = xtemp[r] * (1.0 - 0.9) + botm * 0.9;
         x[r] = xx;
         dx[r] = 0.0;
@@ -777,6 +781,14 @@ __global__ void copy_d_kernel(int n, const double *__restrict__ a, double *__res
     b[i] = a[i];
 }
 
+__global__ void i2d_kernel(int n, const int *__restrict__ a, double *__restrict__ b) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) b[i] = (double)a[i];
+}
+
+__global__ void d2i_kernel(int n, const double *__restrict__ a, int *__restrict__ b) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) b[i] = (int)a[i];
+}
+
 __global__ void copy_i_kernel(int n, const int *__restrict__ a, int *__restrict__ b) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     b[i] = a[i];
@@ -793,7 +805,11 @@ struct PkgRange {
 struct mf6gpu_solution {
   mf6gpu_matrix *A = nullptr;
   mf6gpu_solver *S = nullptr;
-  int n = 0, nja = 0, njas = 0;
+  int n = 0, nja = 0, njas = 0;   // n = owned cells (matrix rows)
+  int n_ext = 0;                  // owned + halo cells
+  mf6::HaloPlan halo;             // split-model path only
+  DevBuf<double> os_all;          // [nranks] gathered OuterState
+  DevBuf<double> ibd_tmp;         // [n_ext] ibound as doubles for the halo exchange
   ModelOpts o{};
   mf6gpu_sln_settings ss{};
   int isymmetric = 0;
@@ -832,7 +848,7 @@ struct mf6gpu_solution {
 
   ModelView view() const {
     ModelView M;
-    M.n = n;
+    M.n = n;  // owned rows
     M.slice_ptr = A->slice_ptr.p;
     M.rowlen = A->rowlen.p;
     M.col = A->col.p;
@@ -873,10 +889,39 @@ struct mf6gpu_solution {
     B.rateout = b_rout.p;
     return B;
   }
+  // local record, or (split-model path) the records of all ranks combined on the host in rank
+  // order: identical on every rank, like the MPI_Allreduce calls of ParallelSolution.f90:54-235
   OuterState fetch_os() {
-    MF6_CK(cudaMemcpyAsync(h_os.p, os.p, sizeof(OuterState), cudaMemcpyDeviceToHost, stream));
+    if (!halo.active()) {
+      MF6_CK(cudaMemcpyAsync(h_os.p, os.p, sizeof(OuterState), cudaMemcpyDeviceToHost, stream));
+      MF6_CK(cudaStreamSynchronize(stream));
+      return *h_os.p;
+    }
+    const int nr = halo.comm->nranks;
+    const size_t cnt = sizeof(OuterState) / sizeof(double);
+    comm_allgather(halo.comm, reinterpret_cast<const double *>(os.p), os_all.p, cnt, stream);
+    MF6_CK(cudaMemcpyAsync(h_os.p, os_all.p, sizeof(OuterState) * (size_t)nr, cudaMemcpyDeviceToHost, stream));
     MF6_CK(cudaStreamSynchronize(stream));
-    return *h_os.p;
+    OuterState g = h_os.p[0];
+    for (int r = 1; r < nr; r++) {
+      const OuterState &y = h_os.p[r];
+      const double ay = std::fabs(y.hncg), ag = std::fabs(g.hncg);
+      if (ay > ag || (ay == ag && ay > 0.0 && y.loc_ord < g.loc_ord)) {
+        g.hncg = y.hncg;
+        g.loc_ord = y.loc_ord;
+      }
+      g.nur_flag = std::fmax(g.nur_flag, y.nur_flag);
+      g.dxold_max = std::fmax(g.dxold_max, y.dxold_max);
+      g.ptc_max = std::fmax(g.ptc_max, y.ptc_max);
+      g.l2 += y.l2;
+      g.rin += y.rin;
+      g.rout += y.rout;
+    }
+    g.loc = g.loc_ord;  // reported as a global cell id
+    return g;
+  }
+  void exchange_x() {
+    if (halo.active()) halo.exchange(x.p, stream);
   }
   void buildsystem(int inewton);
   void calc_ptc(int &iptc, double &ptcf);
@@ -900,9 +945,14 @@ void mf6gpu_solution::buildsystem(int inewton) {
   const int G = grid_for(n);
   const int transient = (iss == 0 && o.insto) ? 1 : 0;
   const double tled = 1.0 / delt;
+  exchange_x();  // halo heads (STG_BFR_EXG_CF synchronisation of the reference)
   nl += (o.all_confined ? 0 : 1) + (nb > 0 ? 1 : 0) + 1 + (nseg > 0 ? 1 : 0);
   if (inewton && o.inewton) nl += 1 + (nseg > 0 ? 1 : 0);
-  if (!o.all_confined) npf_cf_kernel<<<G, kBlock, 0, stream>>>(M, x.p, sat.p);
+  if (!o.all_confined) {
+    ModelView Me = M;
+    Me.n = n_ext;  // saturation of the halo cells too
+    npf_cf_kernel<<<grid_for(n_ext), kBlock, 0, stream>>>(Me, x.p, sat.p);
+  }
   if (nb > 0) bnd_cf_kernel<<<grid_for(nb), kBlock, 0, stream>>>(B, M, x.p);
   if (o.all_confined)
     assemble_rows_kernel<true><<<G, kBlock, 0, stream>>>(M, x.p, xold.p, sat.p, A->val.p, rhs.p, transient, tled);
@@ -1007,7 +1057,7 @@ int mf6gpu_solution::solve_outer(int kiter, int kstp, int kper, double &hncg, in
   tf += 1e-3 * ms0;
   tl += 1e-3 * ms1;
   hncg = h.hncg;
-  lrch = h.loc;
+  lrch = (int)h.loc;
   icnvg = 0;
   if (std::fabs(hncg) <= ss.dvclose) icnvg = 1;
   if (icnvg != 1) {
@@ -1039,18 +1089,18 @@ int mf6gpu_solution::solve_outer(int kiter, int kstp, int kper, double &hncg, in
       calcdx_kernel<<<G, kBlock, 0, stream>>>(n, ibound.p, x.p, xtemp.p, dxold.p);
     }
     if (o.inewton != 0 && o.inewtonur != 0) {
-      MF6_CK(cudaMemsetAsync(&os.p->nur_flag, 0, sizeof(int), stream));
+      MF6_CK(cudaMemsetAsync(&os.p->nur_flag, 0, sizeof(double), stream));
       nur_kernel<<<G, kBlock, 0, stream>>>(view(), ibotnode.p, x.p, xtemp.p, dxold.p, os.p);
       absmax_kernel<<<G, kBlock, 0, stream>>>(n, dxold.p, partial.p, tickets.p + 2, os.p);
       MF6_CK(cudaGetLastError());
       OuterState h2 = fetch_os();
-      if (h2.nur_flag != 0) {
+      if (h2.nur_flag != 0.0) {
         if (std::fabs(h2.dxold_max) <= ss.dvclose && std::fabs(hncg) <= ss.dvclose) {
           icnvg = 1;
           dxmax_kernel<<<G, kBlock, 0, stream>>>(n, x.p, xtemp.p, ibound.p, A->ord_ptr(), pm.p, tickets.p, os.p);
           OuterState h3 = fetch_os();
           hncg = h3.hncg;
-          lrch = h3.loc;
+          lrch = (int)h3.loc;
         }
       }
     }
@@ -1061,8 +1111,8 @@ int mf6gpu_solution::solve_outer(int kiter, int kstp, int kper, double &hncg, in
 
 void mf6gpu_solution::posneg(const double *a, int i0, int i1, double &rin, double &rout) {
   rin = rout = 0.0;
-  if (i1 <= i0) return;
-  posneg_kernel<<<grid_for(i1 - i0), kBlock, 0, stream>>>(i0, i1, a, partial.p, tickets.p + 3, os.p);
+  if (i1 <= i0 && !halo.active()) return;
+  posneg_kernel<<<grid_for(std::max(i1 - i0, 1)), kBlock, 0, stream>>>(i0, i1, a, partial.p, tickets.p + 3, os.p);
   MF6_CK(cudaGetLastError());
   OuterState h = fetch_os();
   rin = h.rin;
@@ -1071,33 +1121,72 @@ void mf6gpu_solution::posneg(const double *a, int i0, int i1, double &rin, doubl
 
 extern "C" {
 
-int mf6gpu_solution_create(const mf6gpu_gwf_model *m, const mf6gpu_sln_settings *sln,
-                           const mf6gpu_ims_settings *ims, mf6gpu_solution **out) {
-  return guard([&] {
+// split-model description of one rank (all arrays in the model's LOCAL numbering / index base)
+struct DistArgs {
+  mf6gpu_comm *comm;
+  int n_own;
+  int nnbr;
+  const int32_t *nbr_rank;   // [nnbr]
+  const int32_t *send_ptr;   // [nnbr+1]
+  const int32_t *send_idx;   // [send_ptr[nnbr]] owned cells whose values neighbour k needs
+  const int32_t *recv_ptr;   // [nnbr+1] ranges inside the halo region (cells n_own + ...)
+  const int32_t *global_id;  // [nodes] global cell id of every local cell (owned + halo)
+};
+
+static void create_solution(const mf6gpu_gwf_model *m, const mf6gpu_sln_settings *sln,
+                            const mf6gpu_ims_settings *ims, const DistArgs *da, mf6gpu_solution **out) {
     MF6_REQUIRE(m && sln && ims && out, "solution_create: null argument");
     MF6_REQUIRE(m->ithickstrt == 0, "solution_create: THICKSTRT is not supported on the GPU path");
     MF6_REQUIRE(sln->numtrack == 0, "solution_create: BACKTRACKING is not supported on the GPU path");
-    MF6_REQUIRE(m->njas * 2 == m->nja - m->nodes, "solution_create: nja/njas/nodes are inconsistent");
+    if (!da) MF6_REQUIRE(m->njas * 2 == m->nja - m->nodes, "solution_create: nja/njas/nodes are inconsistent");
     MF6_REQUIRE((long long)m->njas < (1LL << 30), "solution_create: too many connections for one GPU");
     MF6_REQUIRE(!(m->inewton != 0 && ims->ilinmeth == 1),
                 "solution_create: NEWTON needs an asymmetric accelerator (BICGSTAB), cf. NumericalSolution.f90:942-958");
+    const int n_own = da ? da->n_own : m->nodes;
+    MF6_REQUIRE(n_own > 0 && n_own <= m->nodes, "solution_create: bad number of owned cells");
+    const int nja_own = m->ia[n_own] - m->index_base;  // halo rows (diagonal only) are not matrix rows
     auto *s = new mf6gpu_solution();
-    s->n = m->nodes;
-    s->nja = m->nja;
+    s->n = n_own;
+    s->n_ext = m->nodes;
+    s->nja = nja_own;
     s->njas = m->njas;
     s->ss = *sln;
     s->isymmetric = (ims->ilinmeth == 1) ? 1 : 0;  // NumericalSolution.f90:914-916
-    if (mf6gpu_matrix_create(m->nodes, m->nja, m->ia, m->ja, m->index_base, ims->gpu_ordering, &s->A) != 0) {
+    if (mf6gpu_matrix_create_ext(n_own, m->nodes, nja_own, m->ia, m->ja, m->index_base, ims->gpu_ordering,
+                                 da ? da->global_id : nullptr, &s->A) != 0) {
       const std::string keep = last_error();
       delete s;
       throw Error(keep);
     }
     try {
       const int base = m->index_base;
-      const int n = m->nodes, nja = m->nja, njas = m->njas;
+      const int n = m->nodes, nja = nja_own, njas = m->njas;  // n = extended cell count here
       mf6gpu_matrix *A = s->A;
       s->stream = A->stream;
       if (mf6gpu_solver_create(A, ims, 0, &s->S) != 0) throw Error(last_error());
+      if (da) {
+        mf6::HaloPlan &H = s->halo;
+        H.comm = da->comm;
+        H.n_own = n_own;
+        H.n_halo = n - n_own;
+        H.nbr_rank.assign(da->nbr_rank, da->nbr_rank + da->nnbr);
+        H.send_ptr.assign(da->send_ptr, da->send_ptr + da->nnbr + 1);
+        H.recv_ptr.assign(da->recv_ptr, da->recv_ptr + da->nnbr + 1);
+        MF6_REQUIRE(H.recv_ptr.back() == H.n_halo, "solution_create: recv ranges must cover the halo region");
+        std::vector<int> sidx((size_t)H.send_ptr.back());
+        for (size_t i = 0; i < sidx.size(); i++) {
+          const int c = da->send_idx[i] - base;
+          MF6_REQUIRE(c >= 0 && c < n_own, "solution_create: send_idx must name owned cells");
+          sidx[i] = A->iperm[c];
+        }
+        if (sidx.empty()) sidx.push_back(0);
+        H.send_idx.upload(sidx);
+        H.sendbuf.alloc_zero(sidx.size());
+        s->S->halo = &s->halo;
+        s->os_all.alloc_zero(sizeof(OuterState) / sizeof(double) * (size_t)da->comm->nranks);
+        s->h_os.alloc((size_t)da->comm->nranks);
+        s->ibd_tmp.alloc_zero((size_t)n);
+      }
       const std::vector<int> &perm = A->perm;
       // options
       ModelOpts &o = s->o;
@@ -1167,17 +1256,21 @@ int mf6gpu_solution_create(const mf6gpu_gwf_model *m, const mf6gpu_sln_settings 
       std::vector<int> csr2sell((size_t)nja);
       A->csr2sell.download(csr2sell.data(), (size_t)nja);
       s->h_conn_jas.assign((size_t)nja, -1);
-      for (int v = 0; v < n; v++) {
+      for (int v = 0; v < n_own; v++) {
         const int i0 = m->ia[v] - base, i1 = m->ia[v + 1] - base;
         for (int p = i0 + 1; p < i1; p++) {
           const int u = m->ja[p] - base;
           const int jj = m->jas[p] - base;
           MF6_REQUIRE(jj >= 0 && jj < njas, "solution_create: jas out of range");
           s->h_conn_jas[p] = jj;
-          const int up = (u > v) ? 1 : 0;
+          // argument order of the reference: n = the cell with the lower (GLOBAL) number
+          const int up = da ? ((da->global_id[u] > da->global_id[v]) ? 1 : 0) : ((u > v) ? 1 : 0);
           if (up) {
             conn_n[jj] = A->iperm[v];
             conn_m[jj] = A->iperm[u];
+          } else if (u >= n_own) {  // exchange connection seen only from this side
+            conn_n[jj] = A->iperm[u];
+            conn_m[jj] = A->iperm[v];
           }
           slot_conn[csr2sell[p]] = (jj << 1) | up;
         }
@@ -1190,7 +1283,7 @@ int mf6gpu_solution_create(const mf6gpu_gwf_model *m, const mf6gpu_sln_settings 
       s->pm.alloc_zero((size_t)kMaxBlocks);
       s->tickets.alloc_zero(8);
       s->os.alloc_zero(1);
-      s->h_os.alloc(1);
+      if (!da) s->h_os.alloc(1);
       for (auto &e : s->ev) MF6_CK(cudaEventCreate(&e));
       if (njas > 0) {
         DevBuf<int> dn, dm;
@@ -1208,6 +1301,23 @@ int mf6gpu_solution_create(const mf6gpu_gwf_model *m, const mf6gpu_sln_settings 
       throw Error(keep);
     }
     *out = s;
+}
+
+int mf6gpu_solution_create(const mf6gpu_gwf_model *m, const mf6gpu_sln_settings *sln,
+                           const mf6gpu_ims_settings *ims, mf6gpu_solution **out) {
+  return guard([&] { create_solution(m, sln, ims, nullptr, out); });
+}
+
+int mf6gpu_solution_create_dist(const mf6gpu_gwf_model *m, const mf6gpu_sln_settings *sln,
+                                const mf6gpu_ims_settings *ims, mf6gpu_comm *comm, int32_t n_own,
+                                int32_t nnbr, const int32_t *nbr_rank, const int32_t *send_ptr,
+                                const int32_t *send_idx, const int32_t *recv_ptr,
+                                const int32_t *global_id, mf6gpu_solution **out) {
+  return guard([&] {
+    MF6_REQUIRE(comm && global_id && (nnbr == 0 || (nbr_rank && send_ptr && send_idx && recv_ptr)),
+                "solution_create_dist: null argument");
+    DistArgs da{comm, n_own, nnbr, nbr_rank, send_ptr, send_idx, recv_ptr, global_id};
+    create_solution(m, sln, ims, &da, out);
   });
 }
 
@@ -1291,6 +1401,13 @@ int mf6gpu_solution_set_packages(mf6gpu_solution *s, int32_t npkg, const mf6gpu_
     copy_i_kernel<<<grid_for(s->n), kBlock, 0, s->stream>>>(s->n, s->ibound0.p, s->ibound.p);
     if (nb > 0)
       chd_ibound_kernel<<<grid_for(nb), kBlock, 0, s->stream>>>(s->bview(), s->b_pkg.p, s->ibound.p);
+    if (s->halo.active()) {
+      // ibound of the halo cells (constant heads of the neighbour), cf. VirtualGwfModel.f90:117-122
+      const int nh = s->n_ext - s->n;
+      i2d_kernel<<<grid_for(s->n), kBlock, 0, s->stream>>>(s->n, s->ibound.p, s->ibd_tmp.p);
+      s->halo.exchange(s->ibd_tmp.p, s->stream);
+      if (nh > 0) d2i_kernel<<<grid_for(nh), kBlock, 0, s->stream>>>(nh, s->ibd_tmp.p + s->n, s->ibound.p + s->n);
+    }
     MF6_CK(cudaGetLastError());
     MF6_CK(cudaStreamSynchronize(s->stream));
   });
@@ -1338,7 +1455,12 @@ int mf6gpu_solution_timestep(mf6gpu_solution *s, int32_t kper, int32_t kstp, dou
     const ModelView M = s->view();
     const BndView B = s->bview();
     const int transient = (iss == 0 && s->o.insto) ? 1 : 0;
-    if (!s->o.all_confined) npf_cf_kernel<<<G, kBlock, 0, st>>>(M, s->x.p, s->sat.p);
+    s->exchange_x();
+    if (!s->o.all_confined) {
+      ModelView Me = M;
+      Me.n = s->n_ext;
+      npf_cf_kernel<<<grid_for(s->n_ext), kBlock, 0, st>>>(Me, s->x.p, s->sat.p);
+    }
     flow_rows_kernel<<<G, kBlock, 0, st>>>(M, s->x.p, s->xold.p, s->sat.p, s->flowja.p, s->strgss.p,
                                            s->strgsy.p, transient, 1.0 / delt);
     if (s->nb > 0) {
@@ -1383,7 +1505,7 @@ int mf6gpu_solution_timestep(mf6gpu_solution *s, int32_t kper, int32_t kstp, dou
       rep->outer_iterations = kiter;
       rep->inner_iterations = inner_total;
       rep->max_dv = hncg;
-      rep->max_dv_loc = lrch >= 0 ? s->A->perm[lrch] + 1 : 0;
+      rep->max_dv_loc = lrch >= 0 ? (s->halo.active() ? lrch : s->A->perm[lrch]) + 1 : 0;
       rep->npivot_fixes = s->S->npivfix;
       rep->t_formulate = tf;
       rep->t_linsolve = tl;

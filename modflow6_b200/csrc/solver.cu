@@ -124,7 +124,14 @@ __device__ __forceinline__ void reduce_partials_and_finalize(int mode, const dou
   }
   a0 = block_sum(a0, sh);
   if (NS == 2) a1 = block_sum(a1, sh);
-  if (threadIdx.x == 0) finalize_sum(mode, a0, a1, st, out);
+  if (threadIdx.x == 0) {
+    if (st->dist) {
+      st->red.s[0] = a0;
+      st->red.s[1] = a1;
+    } else {
+      finalize_sum(mode, a0, a1, st, out);
+    }
+  }
 }
 
 // ---- dot product (ddot) ------------------------------------------------------
@@ -146,7 +153,7 @@ dot_kernel(int n, const double *__restrict__ a, const double *__restrict__ b,
 // ---- dnrm2 in two passes (max |d|, then sum (d/scale)^2) ---------------------
 __global__ void __launch_bounds__(kBlock)
 nrm_max_kernel(int n, const double *__restrict__ a, double *__restrict__ partial,
-               unsigned int *ticket, double *out) {
+               unsigned int *ticket, KState *st, double *out) {
   __shared__ double sh[8];
   __shared__ bool last;
   double m = 0.0;
@@ -158,7 +165,12 @@ nrm_max_kernel(int n, const double *__restrict__ a, double *__restrict__ partial
     double r = 0.0;
     for (int i = threadIdx.x; i < gridDim.x; i += blockDim.x) r = fmax(r, partial[i]);
     r = block_max(r, sh);
-    if (threadIdx.x == 0) *out = r;
+    if (threadIdx.x == 0) {
+      if (st->dist)
+        st->red.s[0] = r;
+      else
+        *out = r;
+    }
   }
 }
 
@@ -355,8 +367,45 @@ update_kernel(int n, double *__restrict__ x, double *__restrict__ d,
     a = block_sum(a, sh);
     gx = block_maxloc(gx, shm);
     gr = block_maxloc(gr, shm);
-    if (threadIdx.x == 0) finalize_iteration(st, a, gx, gr, BCGS, sp);
+    if (threadIdx.x == 0) {
+      if (st->dist) {
+        st->red.s[0] = a;
+        st->red.mx = MaxLocPOD{gx.a, gx.v, gx.ord, gx.idx};
+        st->red.mr = MaxLocPOD{gr.a, gr.v, gr.ord, gr.idx};
+      } else {
+        finalize_iteration(st, a, gx, gr, BCGS, sp);
+      }
+    }
   }
+}
+
+enum { FIN_UPDATE = 100 };
+
+// split-model path: combine the gathered per-rank records in rank order (deterministic and
+// identical on every rank) and run the same scalar epilogue the single-GPU kernels run inline
+__global__ void global_finalize_kernel(int mode, const RedRec *__restrict__ all, int nranks,
+                                       KState *st, double *out, int bcgs, SummaryPtrs sp) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const bool krylov = !(mode == FIN_NRM_MAX || mode == FIN_NRM_SSQ);
+  if (krylov && st->done) return;
+  double s0 = 0.0, s1 = 0.0;
+  MaxLoc mx = maxloc_init(), mr = maxloc_init();
+  for (int r = 0; r < nranks; r++) {
+    if (mode == FIN_NRM_MAX) {
+      s0 = fmax(s0, all[r].s[0]);
+    } else {
+      s0 += all[r].s[0];
+      s1 += all[r].s[1];
+    }
+    if (mode == FIN_UPDATE) {
+      maxloc_merge(mx, MaxLoc{all[r].mx.a, all[r].mx.v, all[r].mx.ord, all[r].mx.ord});
+      maxloc_merge(mr, MaxLoc{all[r].mr.a, all[r].mr.v, all[r].mr.ord, all[r].mr.ord});
+    }
+  }
+  if (mode == FIN_UPDATE)
+    finalize_iteration(st, s0, mx, mr, bcgs, sp);  // locations are GLOBAL cell ids here
+  else
+    finalize_sum(mode, s0, s1, st, out);
 }
 
 __global__ void copy_kernel(int n, const double *__restrict__ a, double *__restrict__ b) {
@@ -365,7 +414,8 @@ __global__ void copy_kernel(int n, const double *__restrict__ a, double *__restr
 }
 
 __global__ void init_state_kernel(KState *st, double epfact, double dvclose, double rclose,
-                                  int icnvgopt, int sum_cap, int iscl, int reset_count) {
+                                  int icnvgopt, int sum_cap, int iscl, int reset_count, int dist) {
+  st->dist = dist;
   st->rho = st->rho0 = st->alpha = st->alpha0 = st->omega = st->omega0 = st->beta = 0.0;
   st->rho_acc = 0.0;
   st->epfact = epfact;
@@ -459,6 +509,16 @@ void mf6gpu_solver::prof_collect() {
   ev_used = 0;
 }
 
+void mf6gpu_solver::reduce_finalize(int mode, double *out, int bcgs) {
+  if (!halo || !halo->active()) return;
+  SummaryPtrs sp{sum_itinner.p, sum_locdv.p, sum_locr.p, sum_dvmax.p, sum_rmax.p, sum_alpha.p, sum_omega.p};
+  const size_t cnt = sizeof(RedRec) / sizeof(double);
+  comm_allgather(halo->comm, reinterpret_cast<const double *>(&st.p->red), red_all.p, cnt, stream);
+  global_finalize_kernel<<<1, 1, 0, stream>>>(mode, reinterpret_cast<const RedRec *>(red_all.p),
+                                              halo->comm->nranks, st.p, out, bcgs, sp);
+  launches += 1;
+}
+
 // ims_base_pcu, ImsLinearBase.f90:808-858
 int mf6gpu_solver::factor() {
   int ipcflag = 0, icount = 0;
@@ -491,6 +551,8 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
   const int G = grid_for(N);
   cudaStream_t S = stream;
   const bool bcgs = (s.ilinmeth == 2);
+  const bool dist = halo && halo->active();
+  MF6_REQUIRE(!(dist && s.iscl != 0), "solver: SCALING_METHOD is not available on the split-model path");
   SummaryPtrs sp{sum_itinner.p, sum_locdv.p, sum_locr.p, sum_dvmax.p, sum_rmax.p, sum_alpha.p, sum_omega.p};
   launches = 0;
   MF6_CK(cudaEventRecord(ev[0], S));
@@ -508,15 +570,18 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
   MF6_CK(cudaEventRecord(ev[1], S));
   // -- initial residual and its norm (ImsLinear.f90:676-699)
   init_state_kernel<<<1, 1, 0, S>>>(st.p, epfact_of(s.icnvgopt, kstp), s.dvclose, s.rclose,
-                                    s.icnvgopt, sum_cap, s.iscl, kiter == 1 ? 1 : 0);
+                                    s.icnvgopt, sum_cap, s.iscl, kiter == 1 ? 1 : 0, dist ? 1 : 0);
   p.zero(S);
   q.zero(S);
   z.zero(S);
+  if (dist) halo->exchange(x_dev, S);
   spmv_fused_kernel<1, 0><<<G, kBlock, 0, S>>>(N, A->slice_ptr.p, A->rowlen.p, A->col.p, A->val.p,
                                                x_dev, d.p, b_dev, nullptr, nullptr, nullptr, st.p, 0, 0);
   double *scale_slot = partial.p + 3 * kMaxBlocks;  // scratch scalar
-  nrm_max_kernel<<<G, kBlock, 0, S>>>(N, d.p, partial.p, tickets.p + TK_NRM, scale_slot);
+  nrm_max_kernel<<<G, kBlock, 0, S>>>(N, d.p, partial.p, tickets.p + TK_NRM, st.p, scale_slot);
+  reduce_finalize(FIN_NRM_MAX, scale_slot, 0);
   nrm_ssq_kernel<<<G, kBlock, 0, S>>>(N, d.p, partial.p, tickets.p + TK_NRM, st.p, scale_slot);
+  reduce_finalize(FIN_NRM_SSQ, scale_slot, 0);
   launches += 4;
   MF6_CK(cudaGetLastError());
   MF6_CK(cudaMemcpyAsync(h_st.p, st.p, sizeof(KState), cudaMemcpyDeviceToHost, S));
@@ -535,8 +600,8 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
   idot.partial = ilu_partial.p;
   idot.cta_sums = partial.p + 2 * kMaxBlocks;
   idot.ticket = tickets.p + 4;
-  idot.rho_out = &st.p->rho;
-  idot.beta_out = &st.p->beta;
+  idot.rho_out = dist ? &st.p->red.s[0] : &st.p->rho;
+  idot.beta_out = dist ? &st.p->red.s[1] : &st.p->beta;
   idot.rho0 = &st.p->rho0;
   // polling cadence: cheap iterations (small n) are batched deeper
   const int batch = (N > 2000000) ? 4 : 16;
@@ -555,6 +620,7 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
           if (fuse_dot) {
             // z = M^-1 d with rho = d.z (and beta = rho/rho0) accumulated by the same launches
             launches += ilu0_apply(*A, lu.p, d.p, z.p, &st.p->done, S, &idot);
+            reduce_finalize(FIN_CG_RHO, nullptr, 0);
             prof_end();
           } else {
             launches += ilu0_apply(*A, lu.p, d.p, z.p, &st.p->done, S);
@@ -562,52 +628,63 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
             prof_begin(PC_DOT);
             dot_kernel<<<G, kBlock, 0, S>>>(N, d.p, z.p, partial.p, tickets.p + TK_DOT, st.p,
                                             FIN_CG_RHO, nullptr, 1);
+            reduce_finalize(FIN_CG_RHO, nullptr, 0);
             prof_end();
             launches += 1;
           }
           prof_begin(PC_PUPD);
           cg_p_kernel<<<G, kBlock, 0, S>>>(N, z.p, p.p, st.p, first);
+          if (dist) halo->exchange(p.p, S);
           prof_end();
           prof_begin(PC_SPMV);
           spmv_fused_kernel<0, 1><<<G, kBlock, 0, S>>>(N, A->slice_ptr.p, A->rowlen.p, A->col.p,
                                                        A->val.p, p.p, q.p, nullptr, p.p, partial.p,
                                                        tickets.p + TK_SPMV, st.p, FIN_CG_ALPHA, 1);
+          reduce_finalize(FIN_CG_ALPHA, nullptr, 0);
           prof_end();
           prof_begin(PC_UPD);
           update_kernel<0><<<G, kBlock, 0, S>>>(N, x_dev, d.p, p.p, q.p, nullptr, nullptr, nullptr,
                                                 ord, partial.p, pmx.p, pmr.p, tickets.p + TK_UPD,
                                                 st.p, sp);
+          reduce_finalize(FIN_UPDATE, nullptr, 0);
           prof_end();
           launches += 3;
         } else {
           dot_kernel<<<G, kBlock, 0, S>>>(N, dhat.p, d.p, partial.p, tickets.p + TK_DOT, st.p,
                                           FIN_BCGS_RHO, nullptr, 1);
+          reduce_finalize(FIN_BCGS_RHO, nullptr, 1);
           bcgs_p_kernel<<<G, kBlock, 0, S>>>(N, d.p, v.p, p.p, st.p, first);
           prof_begin(PC_ILU);
           launches += ilu0_apply(*A, lu.p, p.p, phat.p, &st.p->done, S);
+          if (dist) halo->exchange(phat.p, S);
           prof_end();
           prof_begin(PC_SPMV);
           spmv_fused_kernel<0, 1><<<G, kBlock, 0, S>>>(N, A->slice_ptr.p, A->rowlen.p, A->col.p,
                                                        A->val.p, phat.p, v.p, nullptr, dhat.p,
                                                        partial.p, tickets.p + TK_SPMV, st.p,
                                                        FIN_BCGS_ALPHA, 1);
+          reduce_finalize(FIN_BCGS_ALPHA, nullptr, 1);
           prof_end();
           bcgs_q_kernel<<<G, kBlock, 0, S>>>(N, d.p, v.p, q.p, st.p);
           prof_begin(PC_ILU);
           launches += ilu0_apply(*A, lu.p, q.p, qhat.p, &st.p->done, S);
+          if (dist) halo->exchange(qhat.p, S);
           prof_end();
           prof_begin(PC_SPMV);
           spmv_fused_kernel<0, 2><<<G, kBlock, 0, S>>>(N, A->slice_ptr.p, A->rowlen.p, A->col.p,
                                                        A->val.p, qhat.p, t.p, nullptr, q.p,
                                                        partial.p, tickets.p + TK_SPMV, st.p,
                                                        FIN_BCGS_OMEGA, 1);
+          reduce_finalize(FIN_BCGS_OMEGA, nullptr, 1);
           prof_end();
           update_kernel<1><<<G, kBlock, 0, S>>>(N, x_dev, d.p, phat.p, q.p, qhat.p, t.p, dscale.p,
                                                 ord, partial.p, pmx.p, pmr.p, tickets.p + TK_UPD,
                                                 st.p, sp);
+          reduce_finalize(FIN_UPDATE, nullptr, 1);
           launches += 6;
         }
         if (s.north > 0 && ((iiter + 1) % s.north == 0)) {
+          if (dist) halo->exchange(x_dev, S);
           spmv_fused_kernel<1, 0><<<G, kBlock, 0, S>>>(N, A->slice_ptr.p, A->rowlen.p, A->col.p,
                                                        A->val.p, x_dev, d.p, b_dev, nullptr,
                                                        nullptr, nullptr, st.p, 0, 1);
@@ -674,7 +751,7 @@ int mf6gpu_solver_create(mf6gpu_matrix *m, const mf6gpu_ims_settings *settings,
       s->ipc = (s->s.relax > 0.0) ? 2 : 1;  // ImsLinear.f90:178-185
       s->n = m->n;
       s->stream = m->stream;
-      const size_t n = (size_t)m->n;
+      const size_t n = (size_t)m->n_ext;  // vectors carry the halo region behind the owned rows
       s->lu.alloc_zero((size_t)m->nslots);
       s->x.alloc_zero(n);
       s->b.alloc_zero(n);
@@ -702,6 +779,7 @@ int mf6gpu_solver_create(mf6gpu_matrix *m, const mf6gpu_ims_settings *settings,
       s->pmr.alloc_zero((size_t)kMaxBlocks);
       s->tickets.alloc_zero(8);
       s->failflag.alloc_zero(1);
+      s->red_all.alloc_zero(8 * 64);
       s->sum_cap = summary_capacity > 0 ? summary_capacity : 0;
       const size_t c = (size_t)(s->sum_cap > 0 ? s->sum_cap : 1);
       s->sum_itinner.alloc_zero(c);
@@ -774,11 +852,13 @@ int mf6gpu_solver_get_summary(mf6gpu_solver *s, int32_t cap, int32_t *itinner, d
     if (omega) s->sum_omega.download(omega, c);
     if (locdv) {
       s->sum_locdv.download(li.data(), c);
-      for (size_t i = 0; i < c; i++) locdv[i] = li[i] >= 0 ? s->A->perm[li[i]] + 1 : 0;
+      const bool dist = s->halo && s->halo->active();
+      for (size_t i = 0; i < c; i++) locdv[i] = li[i] >= 0 ? (dist ? li[i] : s->A->perm[li[i]]) + 1 : 0;
     }
     if (locr) {
       s->sum_locr.download(li.data(), c);
-      for (size_t i = 0; i < c; i++) locr[i] = li[i] >= 0 ? s->A->perm[li[i]] + 1 : 0;
+      const bool dist = s->halo && s->halo->active();
+      for (size_t i = 0; i < c; i++) locr[i] = li[i] >= 0 ? (dist ? li[i] : s->A->perm[li[i]]) + 1 : 0;
     }
   });
   return rc < 0 ? rc : count;

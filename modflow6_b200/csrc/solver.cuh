@@ -1,8 +1,15 @@
 // solver.cuh -- device-resident IMS linear solver (LinearSolverBaseType replacement)
 #pragma once
 #include "ilu0.cuh"
+#include "comm.cuh"
 
 namespace mf6 {
+
+// one rank's contribution to a reduction of the split-model path (8 doubles)
+struct RedRec {
+  double s[2];
+  MaxLocPOD mx, mr;
+};
 
 // Scalars of the Krylov recurrences; lives in device memory, never read by the
 // host inside the inner loop (only `done`/`iter` are polled every few iterations).
@@ -19,13 +26,17 @@ struct KState {
   int sum_count;       // summary%iter_cnt
   int sum_cap;
   int iscl;
-  int pad;
+  int dist;            // split-model path: reductions are completed by global_finalize_kernel
+  RedRec red;          // this rank's partial result of the reduction in flight
 };
 
 }  // namespace mf6
 
 struct mf6gpu_solver {
   mf6gpu_matrix *A = nullptr;  // not owned
+  mf6::HaloPlan *halo = nullptr;  // not owned; non-null on the split-model path
+  mf6::DevBuf<double> red_all;    // [nranks * 8] gathered RedRec
+  void reduce_finalize(int mode, double *out, int bcgs);  // all-gather + global finalize (no-op on 1 GPU)
   mf6gpu_ims_settings s{};
   int ipc = 1;
   cudaStream_t stream = 0;

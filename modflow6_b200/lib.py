@@ -25,7 +25,8 @@ SYMBOLS = [
     "mf6gpu_solution_timestep", "mf6gpu_solution_formulate", "mf6gpu_solution_get_x",
     "mf6gpu_solution_set_x", "mf6gpu_solution_get_amat", "mf6gpu_solution_get_rhs",
     "mf6gpu_solution_get_flowja", "mf6gpu_solution_get_condsat", "mf6gpu_solution_solver",
-    "mf6gpu_solution_stat",
+    "mf6gpu_solution_stat", "mf6gpu_matrix_create_ext", "mf6gpu_solution_create_dist",
+    "mf6gpu_comm_unique_id", "mf6gpu_comm_create", "mf6gpu_comm_destroy", "mf6gpu_comm_rank", "mf6gpu_comm_size",
 ]
 
 _lib = None
@@ -82,6 +83,15 @@ def load():
     L.mf6gpu_solver_apply_preconditioner.argtypes = [vp, pf64, pf64]
     L.mf6gpu_solution_create.argtypes = [C.POINTER(T.GwfModelStruct), C.POINTER(T.SlnSettings),
                                          C.POINTER(T.ImsSettings), vpp]
+    L.mf6gpu_matrix_create_ext.argtypes = [i32, i32, i32, pi32, pi32, i32, i32, pi32, vpp]
+    L.mf6gpu_comm_unique_id.argtypes = [C.c_void_p]
+    L.mf6gpu_comm_create.argtypes = [i32, i32, C.c_void_p, vpp]
+    L.mf6gpu_comm_destroy.argtypes = [vp]
+    L.mf6gpu_comm_rank.argtypes = [vp]
+    L.mf6gpu_comm_size.argtypes = [vp]
+    L.mf6gpu_solution_create_dist.argtypes = [C.POINTER(T.GwfModelStruct), C.POINTER(T.SlnSettings),
+                                              C.POINTER(T.ImsSettings), vp, i32, i32, pi32, pi32, pi32, pi32,
+                                              pi32, vpp]
     L.mf6gpu_solution_destroy.argtypes = [vp]
     L.mf6gpu_solution_set_packages.argtypes = [vp, i32, C.POINTER(T.BndPackageStruct)]
     L.mf6gpu_solution_timestep.argtypes = [vp, i32, i32, f64, i32, C.POINTER(T.StepReport)]

@@ -799,6 +799,8 @@ static void free_pkgs(orc_solution *S) {
   S->npkg = 0;
 }
 
+void orc_sln_set_blocks(orc_solution *S, const int *block) { orc_ims_set_blocks(S->ims, block); }
+
 void orc_sln_destroy(orc_solution *S) {
   if (!S) return;
   free_pkgs(S);

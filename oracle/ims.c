@@ -540,8 +540,36 @@ orc_imslinear *orc_ims_create(int n, int nja, const int *ia, const int *ja,
   return L;
 }
 
+void orc_ims_set_blocks(orc_imslinear *L, const int *block) {
+  const int n = L->n;
+  const int *ia0 = L->use_perm ? L->iaro : L->ia;
+  const int *ja0 = L->use_perm ? L->jaro : L->ja;
+  L->use_blocks = 1;
+  L->iaf = (int *)malloc(sizeof(int) * (size_t)(n + 1));
+  L->jaf = (int *)malloc(sizeof(int) * (size_t)L->nja);
+  L->fmap = (int *)malloc(sizeof(int) * (size_t)L->nja);
+  L->af = (double *)malloc(sizeof(double) * (size_t)L->nja);
+  int pos = 0;
+  for (int r = 0; r < n; r++) {
+    L->iaf[r] = pos;
+    int br = block[L->use_perm ? L->lorder[r] : r];
+    for (int k = ia0[r]; k < ia0[r + 1]; k++) {
+      int c = ja0[k];
+      int bc = block[L->use_perm ? L->lorder[c] : c];
+      if (bc != br) continue;
+      L->jaf[pos] = c;
+      L->fmap[pos] = k;
+      pos++;
+    }
+  }
+  L->iaf[n] = pos;
+  orc_ilu0_destroy(L->pc);
+  L->pc = orc_ilu0_create(n, pos, L->iaf, L->jaf);
+}
+
 void orc_ims_destroy(orc_imslinear *L) {
   if (!L) return;
+  free(L->iaf); free(L->jaf); free(L->fmap); free(L->af);
   free(L->d); free(L->p); free(L->q); free(L->z); free(L->t); free(L->v);
   free(L->dhat); free(L->phat); free(L->qhat); free(L->dscale); free(L->dscale2);
   free(L->lorder); free(L->iorder); free(L->iaro); free(L->jaro); free(L->aro);
@@ -592,7 +620,13 @@ int orc_ims_apply(orc_imslinear *L, double *amat, double *x, double *rhs,
     x0 = L->xp;
     b0 = L->bp;
   }
-  L->npivfix = orc_pcu(L->pc, a0, ia0, ja0, s->relax);
+  if (L->use_blocks) {
+    const int nf = L->iaf[n];
+    for (int k = 0; k < nf; k++) L->af[k] = a0[L->fmap[k]];
+    L->npivfix = orc_pcu(L->pc, L->af, L->iaf, L->jaf, s->relax);
+  } else {
+    L->npivfix = orc_pcu(L->pc, a0, ia0, ja0, s->relax);
+  }
   if (kiter == 1) {
     L->niterc = 0;
     if (sum) sum->count = 0;

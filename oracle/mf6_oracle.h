@@ -99,12 +99,20 @@ typedef struct {
   double l2norm0, epfact;
   int niterc;
   int npivfix; /* last pcu icount */
+  /* optional block-Jacobi preconditioner (the reference's parallel PC: PCBJACOBI + IMS ILU on
+   * each rank's diagonal block, PetscSolver.F90:251-278): entries whose row and column lie in
+   * different blocks are dropped from the ILU only */
+  int use_blocks;
+  int *iaf, *jaf, *fmap; /* filtered pattern (in the working ordering) + source position */
+  double *af;
 } orc_imslinear;
 
 /* imslinear_ar :111-339 ; perm may be NULL (natural order).  perm[new]=old. */
 orc_imslinear *orc_ims_create(int n, int nja, const int *ia, const int *ja,
                               const mf6gpu_ims_settings *s, const int *perm);
 void orc_ims_destroy(orc_imslinear *L);
+/* block[n] (original numbering) switches the preconditioner to block Jacobi; call right after create */
+void orc_ims_set_blocks(orc_imslinear *L, const int *block);
 /* imslinear_ap :617-750 ; amat/x/rhs in original ordering.  Returns innerit. */
 int orc_ims_apply(orc_imslinear *L, double *amat, double *x, double *rhs,
                   int *icnvg, int kstp, int kiter, orc_summary *sum);
@@ -112,6 +120,7 @@ int orc_ims_apply(orc_imslinear *L, double *amat, double *x, double *rhs,
 /* ---- GWF model + numerical solution (gwf.c, solution.c) ---------------- */
 typedef struct orc_solution orc_solution;
 
+void orc_sln_set_blocks(orc_solution *S, const int *block);
 orc_solution *orc_sln_create(const mf6gpu_gwf_model *m,
                              const mf6gpu_sln_settings *ss,
                              const mf6gpu_ims_settings *ls, const int *perm);

@@ -55,6 +55,8 @@ def lib():
         L.orc_sln_create.restype = vp
         L.orc_sln_create.argtypes = [C.POINTER(T.GwfModelStruct), C.POINTER(T.SlnSettings), C.POINTER(T.ImsSettings), T.p_i32]
         L.orc_sln_destroy.argtypes = [vp]
+        L.orc_sln_set_blocks.argtypes = [vp, T.p_i32]
+        L.orc_ims_set_blocks.argtypes = [vp, T.p_i32]
         L.orc_sln_set_packages.argtypes = [vp, C.c_int, C.POINTER(T.BndPackageStruct)]
         L.orc_sln_timestep.restype = C.c_int
         L.orc_sln_timestep.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(T.StepReport)]
@@ -144,12 +146,16 @@ class OracleIms:
 class OracleSolution:
     """NumericalSolution + one GWF model on the CPU."""
 
-    def __init__(self, model, sln, ims, perm=None):
+    def __init__(self, model, sln, ims, perm=None, blocks=None):
+        """perm: elimination order (perm[new] = old); blocks: block id per cell => block-Jacobi ILU"""
         self.model = model
         self._ms = model.struct()
         self.perm = T.as_i32(perm) if perm is not None else None
         self.h = lib().orc_sln_create(C.byref(self._ms), C.byref(sln), C.byref(ims), T.ptr_i32(self.perm))
         self.n = model.nodes
+        if blocks is not None:
+            self.blocks = T.as_i32(blocks)
+            lib().orc_sln_set_blocks(self.h, T.ptr_i32(self.blocks))
 
     def set_packages(self, pkgs):
         arr = package_array(pkgs)
