@@ -217,15 +217,43 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    cfg = build_config(size, args.ordering, args.inner_maximum, args.outer_maximum)
-    n, nja = cfg.model.nodes, cfg.model.nja
-    per = cfg.periods[0]
-    G = GpuNumericalSolution(cfg.model, cfg.sln, cfg.ims)
-    G.set_packages(per.packages)
-    strt = np.ascontiguousarray(cfg.model.strt)
+    if world == 1:
+        cfg = build_config(size, args.ordering, args.inner_maximum, args.outer_maximum)
+        n, nja = cfg.model.nodes, cfg.model.nja
+        n_total = n
+        pkgs = cfg.periods[0].packages
+        G = GpuNumericalSolution(cfg.model, cfg.sln, cfg.ims)
+        strt = np.ascontiguousarray(cfg.model.strt)
+        ims_s, sln_s = cfg.ims, cfg.sln
+        layout = "single GPU"
+    else:
+        # weak scaling: every rank owns one C2-sized block of a (pr*nrow) x (pc*ncol) grid, coupled through
+        # halo exchange + all-gathered Krylov scalars (split-model path, block-Jacobi ILU0)
+        from modflow6_b200 import ctypes_types as T
+        from modflow6_b200.distributed import (GpuComm, GpuDistributedSolution, GridSpec, build_dis_block,
+                                               global_packages_c2)
+        # blocks are stacked along the rows (the no-flow direction): the constant heads stay 1000 columns
+        # apart, so the conditioning -- and the inner-iteration count -- does not grow with the GPU count
+        pr, pc = world, 1
+        spec = GridSpec(nlay=size[0], nrow=size[1] * pr, ncol=size[2] * pc)
+        sub = build_dis_block(spec, pr, pc, rank)
+        o = T.ORDER_MULTICOLOR if args.ordering == "multicolor" else T.ORDER_NATURAL
+        ims_s = T.ImsSettings.make(dvclose=1e-6, rclose=1e-2, iter1=args.inner_maximum, ilinmeth=1, relax=0.0,
+                                   gpu_ordering=o)
+        sln_s = T.SlnSettings.make(dvclose=1e-5, mxiter=args.outer_maximum, nonmeth=0)
+        comm = GpuComm(rank, world)
+        G = GpuDistributedSolution(sub, sln_s, ims_s, comm)
+        pkgs = global_packages_c2(spec)
+        n = sub.n_own
+        nja = int(sub.model.ia[sub.n_own])
+        n_total = spec.nlay * spec.nrow * spec.ncol
+        strt = np.ascontiguousarray(sub.model.strt[:n])
+        layout = f"{pr}x{pc} blocks of {size[0]}x{size[1]}x{size[2]} cells, global {spec.nlay}x{spec.nrow}x{spec.ncol}"
+    G.set_packages(pkgs)
+    per_pkgs = G._pkgs
     pinned_x = torch.empty(n, dtype=torch.float64).pin_memory()
     pinned_strt = torch.from_numpy(strt.copy()).pin_memory()
-    h2d = strt.nbytes + sum(p.nodelist.nbytes + p.b1.nbytes + p.b2.nbytes + p.b3.nbytes for p in per.packages)
+    h2d = strt.nbytes + sum(p.nodelist.nbytes + p.b1.nbytes + p.b2.nbytes + p.b3.nbytes for p in per_pkgs)
     d2h = n * 8 + C.sizeof(__import__("modflow6_b200.ctypes_types", fromlist=["StepReport"]).StepReport)
 
     def step_device():
@@ -234,7 +262,7 @@ def main():
 
     def step_e2e():
         # what a host code does per time step through the C ABI with host buffers
-        G.set_packages(per.packages)                                  # stress data  H2D
+        G.set_packages(pkgs)                                          # stress data  H2D
         G._L.mf6gpu_solution_set_x(G.h, C.cast(pinned_strt.data_ptr(), C.POINTER(C.c_double)))   # heads H2D
         rep = G.timestep(1, 1, 1.0, 1)
         G._L.mf6gpu_solution_get_x(G.h, C.cast(pinned_x.data_ptr(), C.POINTER(C.c_double)))     # heads D2H
@@ -280,18 +308,13 @@ def main():
     heads = G.x
     converged = rep.converged
 
-    # max over ranks, whole-job aggregate
+    # max over ranks; iteration counts are global (identical on every rank), cells are summed over ranks
     if world > 1:
         t = torch.tensor([ms, ms_e], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e = t.tolist()
-        c = torch.tensor([float(inner), float(inner_e)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        inner_all, inner_e_all = c.tolist()
-    else:
-        inner_all, inner_e_all = float(inner), float(inner_e)
-    value = n * inner_all / (ms * 1e-3)
-    e2e_value = n * inner_e_all / (ms_e * 1e-3)
+    value = n_total * float(inner) / (ms * 1e-3)
+    e2e_value = n_total * float(inner_e) / (ms_e * 1e-3)
 
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -311,15 +334,17 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"C2 confined steady-state DIS {size[0]}x{size[1]}x{size[2]}, IMS CG+ILU0 "
                                    f"({args.ordering} ILU ordering)",
-                       "cells": n, "nja": nja, "l2_policy": "inputs_exceed_l2 (matrix+vectors >> 126 MB)",
-                       "per_gpu": "one full model per GPU (no exchange)" if world > 1 else "single GPU",
-                       "inner_dvclose": cfg.ims.dvclose, "inner_rclose": cfg.ims.rclose,
-                       "inner_maximum": cfg.ims.iter1, "outer_dvclose": cfg.sln.dvclose},
+                       "cells": n_total, "cells_per_gpu": n, "nja_per_gpu": nja,
+                       "l2_policy": "inputs_exceed_l2 (matrix+vectors >> 126 MB)", "layout": layout,
+                       "exchange": "NCCL send/recv halo per SpMV + all-gather of Krylov scalars" if world > 1 else "none",
+                       "inner_dvclose": ims_s.dvclose, "inner_rclose": ims_s.rclose,
+                       "inner_maximum": ims_s.iter1, "outer_dvclose": sln_s.dvclose},
             "solve": {"outer_iterations_per_step": outer / args.steps, "inner_iterations_per_step": inner / args.steps,
                       "converged": int(converged), "linear_solve_s_per_step": t_ls / args.steps,
                       "formulate_s_per_step": t_form / args.steps, "timestep_s": ms * 1e-3 / args.steps,
                       "head_min": float(heads.min()), "head_max": float(heads.max())},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world,
+                    "d2h_bytes_per_step": int(d2h) * world,
                     "ms_per_step": ms_e / args.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "spmv_fused_kernel (SELL-32 SpMV + fused p.q)",
@@ -331,7 +356,7 @@ def main():
                          "kernels": kernels},
             "clocks": clocks,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             s = CpuSample(build_config(size, "natural"), args.cpu_iters).run()
             line["cpu_baseline"] = {"value": s["value"], "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": f"C oracle (port; no Fortran compiler in the image), 1 outer iteration "

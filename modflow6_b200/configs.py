@@ -88,7 +88,7 @@ def c2_confined(nlay=10, nrow=1000, ncol=1000, gpu_ordering=T.ORDER_MULTICOLOR, 
 def c3_newton(nlay=5, nrow=2000, ncol=2000, gpu_ordering=T.ORDER_MULTICOLOR, nwel=100, ntrans=10,
               seed=20260102, iallowptc=1):
     """unconfined transient with NEWTON UNDER_RELAXATION + STO.
-    top 50, 5 layers x 10 m, icelltype 1 in the top layer, ss 1e-5, sy 0.15, RCH 1e-3 on top,
+    top 50, 5 layers x 10 m, icelltype 1 in the top layer, ss 1e-5, sy 0.15, RCH on top (sized for a 1.5 m mound),
     CHD on both sides, seeded wells (switched on in the transient period); BICGSTAB + ILU0, DBD under-relaxation (MODERATE preset values,
     NumericalSolution.f90:2644-2655); 1 steady period + `ntrans` transient steps (x1.2)."""
     rng = np.random.default_rng(seed)
@@ -100,7 +100,9 @@ def c3_newton(nlay=5, nrow=2000, ncol=2000, gpu_ordering=T.ORDER_MULTICOLOR, nwe
     m = build_dis_model(nlay, nrow, ncol, 100.0, 100.0, top, botm, k, k33=0.1 * k, icelltype=ict,
                         strt=47.0, ss=1e-5, sy=0.15, iconvert=ict, inewton=1, inewtonur=1)
     chd = _chd_columns(m, 48.0, 46.0)
-    rch = Package(T.PKG_RCH, np.arange(nrow * ncol), np.full(nrow * ncol, 1e-3))
+    # recharge sized for a ~1.5 m water-table mound between the constant heads: R = 8 T dh / L^2
+    rate = 8.0 * (10.0 * 10.0 * nlay) * 1.5 / float(ncol * 100.0) ** 2
+    rch = Package(T.PKG_RCH, np.arange(nrow * ncol), np.full(nrow * ncol, rate))
     wi = rng.integers(1, nrow - 1, size=nwel)
     wj = rng.integers(1, ncol - 1, size=nwel)
     wk = rng.integers(1, nlay, size=nwel) if nlay > 1 else np.zeros(nwel, int)
@@ -113,6 +115,36 @@ def c3_newton(nlay=5, nrow=2000, ncol=2000, gpu_ordering=T.ORDER_MULTICOLOR, nwe
     sln = T.SlnSettings.make(dvclose=1e-4, mxiter=50, nonmeth=3, theta=0.9, akappa=1e-4, gamma=0.0,
                              amomentum=0.0, iallowptc=iallowptc)
     return SimConfig(f"c3_newton_{nlay}x{nrow}x{ncol}", m, periods, sln, ims)
+
+
+def c4_disv(kind="hexagonal", nlay=5, nr=1000, nc=1000, gpu_ordering=T.ORDER_MULTICOLOR, seed=20260103):
+    """DISV (hexagonal: nr x nc cells per layer; triangular: nr x nc triangles) x nlay
+    layers, confined, heterogeneous K; WEL on 1 %, RIV on 2 % and RCH on 100 % of the top cells (seeded),
+    CHD on the two outer columns of cells; BICGSTAB + ILU0."""
+    from .disv import build_disv_model, hex_cell2d, tri_cell2d
+    c2d = hex_cell2d(nr, nc) if kind == "hexagonal" else tri_cell2d(nr, nc)
+    ncpl = c2d["ncpl"]
+    rng = np.random.default_rng(seed)
+    k = np.exp(rng.normal(np.log(10.0), 0.7, size=(nlay, ncpl)))
+    top = 20.0
+    botm = top - 10.0 * np.arange(1, nlay + 1)
+    m = build_disv_model(nlay, c2d, top, botm, k.reshape(-1), k33=(0.1 * k).reshape(-1), icelltype=0, strt=15.0)
+    cidx = np.arange(ncpl)
+    ccol = cidx % nc
+    west, east = cidx[ccol == 0], cidx[ccol == nc - 1]
+    lay = np.arange(nlay)[:, None] * ncpl
+    chd = Package(T.PKG_CHD, np.concatenate([(lay + west[None, :]).reshape(-1), (lay + east[None, :]).reshape(-1)]),
+                  np.concatenate([np.full(nlay * west.size, 16.0), np.full(nlay * east.size, 14.0)]))
+    inner = cidx[(ccol > 0) & (ccol < nc - 1)]
+    nw, nriv = max(1, inner.size // 100), max(1, inner.size // 50)
+    pick = rng.permutation(inner)
+    wel = Package(T.PKG_WEL, pick[:nw], np.full(nw, -20.0))
+    rv = pick[nw:nw + nriv]
+    riv = Package(T.PKG_RIV, rv, np.full(nriv, 15.5), np.full(nriv, 30.0), np.full(nriv, 13.0))
+    rch = Package(T.PKG_RCH, inner, np.full(inner.size, 2e-4))
+    ims = T.ImsSettings.make(dvclose=1e-7, rclose=1e-3, iter1=300, ilinmeth=2, relax=0.0, gpu_ordering=gpu_ordering)
+    sln = T.SlnSettings.make(dvclose=1e-5, mxiter=50, nonmeth=0)
+    return SimConfig(f"c4_disv_{kind}_{nlay}x{ncpl}", m, [Period(1.0, 1, 1.0, True, [chd, wel, riv, rch])], sln, ims)
 
 
 def run_simulation(solution, cfg, max_steps=None, collect_heads=False):
