@@ -207,6 +207,62 @@ ilu0_bwd_level_kernel(int r0, int r1, const int *__restrict__ slice_ptr,
   if (D.partial) ilu_dot_finish(dot, D);
 }
 
+// ---- two-level (bipartite multicolour) fast path on fixed-width SELL ---------------------------
+// With exactly two levels every off-diagonal of a level-1 row is a lower entry and every
+// off-diagonal of a level-0 row an upper entry, so each sweep is a full-row product without
+// nlow / rowlen / slice_ptr loads.  Padding and halo slots hold lu = 0 and only add -0*finite.
+//   PHASE 0 (rows of level 1):  z = (r - sum_k lu_k r[col_k]) * piv     (forward + its trivial backward)
+//   PHASE 1 (rows of level 0):  z = (r - sum_k lu_k z[col_k]) * piv     (backward; forward value = r)
+template <int W, int PHASE>
+__global__ void __launch_bounds__(kBlock, 8)
+ilu0_two_level_kernel(int r0, int r1, const int *__restrict__ col, const double *__restrict__ lu,
+                      const double *__restrict__ rin, double *__restrict__ d,
+                      const int *__restrict__ done, IluDot D) {
+  if (done && *done) return;
+  double dot = 0.0;
+  const int r = r0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < r1) {
+    const long long base = (long long)(r >> 5) * (32 * W) + (r & 31);
+    double v[W], dv[W];
+    int c[W];
+#pragma unroll
+    for (int u = 0; u < W; u++) {
+      v[u] = __ldg(lu + base + 32 * u);
+      c[u] = __ldg(col + base + 32 * u);
+    }
+    const double rr = rin[r];
+#pragma unroll
+    for (int u = 1; u < W; u++) dv[u] = (PHASE == 0) ? rin[c[u]] : d[c[u]];
+    double tv = rr;
+#pragma unroll
+    for (int u = 1; u < W; u++) tv = tv - v[u] * dv[u];
+    tv = tv * v[0];
+    d[r] = tv;
+    dot = rr * tv;
+  }
+  if (D.partial) ilu_dot_finish(dot, D);
+}
+
+template <int W>
+static int launch_two_level(const mf6gpu_matrix &A, const double *lu, const double *rin, double *d,
+                            const int *done, cudaStream_t s, const IluDotArgs *dot) {
+  const int lvl1 = A.level_ptr[1];
+  const int gA = (A.n - lvl1 + kBlock - 1) / kBlock, gB = (lvl1 + kBlock - 1) / kBlock;
+  IluDot DA{dot ? dot->partial : nullptr};
+  IluDot DB{dot ? dot->partial + gA * (kBlock / 32) : nullptr};
+  ilu0_two_level_kernel<W, 0><<<gA, kBlock, 0, s>>>(lvl1, A.n, A.col.p, lu, rin, d, done, DA);
+  ilu0_two_level_kernel<W, 1><<<gB, kBlock, 0, s>>>(0, lvl1, A.col.p, lu, rin, d, done, DB);
+  int launches = 2;
+  if (dot) {
+    const int slot = (gA + gB) * (kBlock / 32);
+    const int rb = std::max(1, std::min(148, slot / (4 * kBlock)));
+    ilu_dot_reduce_kernel<<<rb, kBlock, 0, s>>>(slot, dot->partial, dot->cta_sums, dot->ticket, dot->rho_out,
+                                                dot->beta_out, dot->rho0, done);
+    launches++;
+  }
+  return launches;
+}
+
 int ilu0_factor(const mf6gpu_matrix &A, const double *aval, double *lu, double relax,
                 double delta, int ipcflag, int *d_failflag, cudaStream_t s) {
   MF6_REQUIRE(A.maxlen <= 64, "ILU0: more than 64 entries in a row is not supported");
@@ -236,6 +292,18 @@ int ilu0_apply(const mf6gpu_matrix &A, const double *lu, const double *rin, doub
                const int *done, cudaStream_t s, const IluDotArgs *dot) {
   int launches = 0;
   const int L = A.nlevels;
+  if (L == 2 && A.level_ptr[1] > 0 && A.level_ptr[1] < A.n) {
+    switch (A.uniform_w) {
+      case 4: return launch_two_level<4>(A, lu, rin, d, done, s, dot);
+      case 5: return launch_two_level<5>(A, lu, rin, d, done, s, dot);
+      case 6: return launch_two_level<6>(A, lu, rin, d, done, s, dot);
+      case 7: return launch_two_level<7>(A, lu, rin, d, done, s, dot);
+      case 8: return launch_two_level<8>(A, lu, rin, d, done, s, dot);
+      case 9: return launch_two_level<9>(A, lu, rin, d, done, s, dot);
+      case 10: return launch_two_level<10>(A, lu, rin, d, done, s, dot);
+      default: break;
+    }
+  }
   const int lvl1 = (L > 1) ? A.level_ptr[1] : A.n;
   int slot = 0;  // next free partial slot
   // forward: levels 1 .. L-1 (level 0 is elided); the last one also finalises its rows

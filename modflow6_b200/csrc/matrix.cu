@@ -181,6 +181,10 @@ static void build_matrix(mf6gpu_matrix &M, int n, int n_ext, int nja, const int3
   std::vector<unsigned char> rowlen(n), nlow(n), rowlen_loc(n);
   std::vector<int> slice_ptr(M.nslices + 1, 0);
   int maxlen = 0;
+  // slice widths: the max row length of each slice, or -- when that costs <= MF6GPU_UNIFORM_PAD_PCT
+  // percent (default 5) extra slots -- the global max for every slice (fixed-width kernels)
+  long long ragged_slots = 0;
+  std::vector<int> sw(M.nslices, 0);
   for (int s = 0; s < M.nslices; s++) {
     int w = 0;
     for (int r = s * 32; r < std::min(n, s * 32 + 32); r++) {
@@ -189,12 +193,29 @@ static void build_matrix(mf6gpu_matrix &M, int n, int n_ext, int nja, const int3
       rowlen[r] = (unsigned char)len;
       if (len > w) w = len;
     }
-    long long next = (long long)slice_ptr[s] + 32LL * w;
-    MF6_REQUIRE(next < (long long)INT_MAX, "matrix_create: SELL storage exceeds 2^31 slots");
-    slice_ptr[s + 1] = (int)next;
+    sw[s] = w;
+    ragged_slots += 32LL * w;
     if (w > maxlen) maxlen = w;
   }
+  {
+    const char *e = std::getenv("MF6GPU_UNIFORM_PAD_PCT");
+    const double pct = e ? std::atof(e) : 5.0;
+    const long long uni_slots = 32LL * maxlen * M.nslices;
+    if ((double)(uni_slots - ragged_slots) <= 0.01 * pct * (double)ragged_slots)
+      for (int s = 0; s < M.nslices; s++) sw[s] = maxlen;
+  }
+  for (int s = 0; s < M.nslices; s++) {
+    long long next = (long long)slice_ptr[s] + 32LL * sw[s];
+    MF6_REQUIRE(next < (long long)INT_MAX, "matrix_create: SELL storage exceeds 2^31 slots");
+    slice_ptr[s + 1] = (int)next;
+  }
   M.maxlen = maxlen;
+  {
+    bool uni = true;
+    for (int sl = 0; sl < M.nslices; sl++)
+      if (slice_ptr[sl + 1] - slice_ptr[sl] != 32 * maxlen) uni = false;
+    M.uniform_w = uni ? maxlen : 0;
+  }
   M.nslots = slice_ptr[M.nslices];
   std::vector<int> col((size_t)M.nslots);
   std::vector<int> csr2sell(nja);

@@ -22,6 +22,7 @@ struct mf6gpu_matrix {
   int nslices = 0;
   long long nslots = 0;
   int maxlen = 0;
+  int uniform_w = 0;           // width shared by every slice (0 = ragged): enables the fixed-width kernels
   std::vector<int> perm;       // perm[new] = old
   std::vector<int> iperm;      // iperm[old] = new
   std::vector<int> level_ptr;  // [nlevels+1] row ranges in final numbering

@@ -226,6 +226,63 @@ spmv_fused_kernel(int n, const int *__restrict__ slice_ptr,
   }
 }
 
+// fixed-width variant (see sell_row_dot_w): no slice_ptr / rowlen loads
+template <int EPI, int NDOT, int W>
+__global__ void __launch_bounds__(kBlock)
+spmv_fused_w_kernel(int n, const int *__restrict__ col, const double *__restrict__ val,
+                    const double *__restrict__ x, double *__restrict__ y,
+                    const double *__restrict__ b, const double *__restrict__ w,
+                    double *__restrict__ partial, unsigned int *ticket, KState *st, int mode,
+                    int check_done) {
+  __shared__ double sh[8];
+  __shared__ bool last;
+  if (check_done && st->done) return;
+  double s0 = 0.0, s1 = 0.0;
+  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
+    double t = sell_row_dot_w<W>(row, col, val, x);
+    if (EPI == 1) t = b[row] - t;
+    y[row] = t;
+    if (NDOT >= 1) s0 += w[row] * t;
+    if (NDOT == 2) s1 += t * t;
+  }
+  if (NDOT >= 1) {
+    s0 = block_sum(s0, sh);
+    if (NDOT == 2) s1 = block_sum(s1, sh);
+    if (threadIdx.x == 0) {
+      partial[NDOT * blockIdx.x] = s0;
+      if (NDOT == 2) partial[NDOT * blockIdx.x + 1] = s1;
+    }
+    if (last_block(ticket, &last))
+      reduce_partials_and_finalize<(NDOT == 2 ? 2 : 1)>(mode, partial, st, nullptr, sh);
+  }
+}
+
+template <int EPI, int NDOT>
+static void launch_spmv_fused(const mf6gpu_matrix &A, int G, cudaStream_t S, const double *x, double *y,
+                              const double *b, const double *w, double *partial, unsigned int *ticket,
+                              KState *st, int mode, int check_done) {
+  const int N = A.n;
+#define MF6_SPMV_W(WW)                                                                              \
+  case WW:                                                                                          \
+    spmv_fused_w_kernel<EPI, NDOT, WW><<<G, kBlock, 0, S>>>(N, A.col.p, A.val.p, x, y, b, w, partial, \
+                                                            ticket, st, mode, check_done);          \
+    return;
+  switch (A.uniform_w) {
+    MF6_SPMV_W(4)
+    MF6_SPMV_W(5)
+    MF6_SPMV_W(6)
+    MF6_SPMV_W(7)
+    MF6_SPMV_W(8)
+    MF6_SPMV_W(9)
+    MF6_SPMV_W(10)
+    default:
+      break;
+  }
+#undef MF6_SPMV_W
+  spmv_fused_kernel<EPI, NDOT><<<G, kBlock, 0, S>>>(N, A.slice_ptr.p, A.rowlen.p, A.col.p, A.val.p, x, y, b,
+                                                    w, partial, ticket, st, mode, check_done);
+}
+
 // ---- vector updates -----------------------------------------------------------
 // CG: P = Z (first) | P = Z + beta P                     ImsLinearBase.f90:118-127
 __global__ void __launch_bounds__(kBlock)
@@ -575,8 +632,7 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
   q.zero(S);
   z.zero(S);
   if (dist) halo->exchange(x_dev, S);
-  spmv_fused_kernel<1, 0><<<G, kBlock, 0, S>>>(N, A->slice_ptr.p, A->rowlen.p, A->col.p, A->val.p,
-                                               x_dev, d.p, b_dev, nullptr, nullptr, nullptr, st.p, 0, 0);
+  launch_spmv_fused<1, 0>(*A, G, S, x_dev, d.p, b_dev, nullptr, nullptr, nullptr, st.p, 0, 0);
   double *scale_slot = partial.p + 3 * kMaxBlocks;  // scratch scalar
   nrm_max_kernel<<<G, kBlock, 0, S>>>(N, d.p, partial.p, tickets.p + TK_NRM, st.p, scale_slot);
   reduce_finalize(FIN_NRM_MAX, scale_slot, 0);
@@ -637,9 +693,8 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
           if (dist) halo->exchange(p.p, S);
           prof_end();
           prof_begin(PC_SPMV);
-          spmv_fused_kernel<0, 1><<<G, kBlock, 0, S>>>(N, A->slice_ptr.p, A->rowlen.p, A->col.p,
-                                                       A->val.p, p.p, q.p, nullptr, p.p, partial.p,
-                                                       tickets.p + TK_SPMV, st.p, FIN_CG_ALPHA, 1);
+          launch_spmv_fused<0, 1>(*A, G, S, p.p, q.p, nullptr, p.p, partial.p, tickets.p + TK_SPMV, st.p,
+                                  FIN_CG_ALPHA, 1);
           reduce_finalize(FIN_CG_ALPHA, nullptr, 0);
           prof_end();
           prof_begin(PC_UPD);
@@ -659,10 +714,8 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
           if (dist) halo->exchange(phat.p, S);
           prof_end();
           prof_begin(PC_SPMV);
-          spmv_fused_kernel<0, 1><<<G, kBlock, 0, S>>>(N, A->slice_ptr.p, A->rowlen.p, A->col.p,
-                                                       A->val.p, phat.p, v.p, nullptr, dhat.p,
-                                                       partial.p, tickets.p + TK_SPMV, st.p,
-                                                       FIN_BCGS_ALPHA, 1);
+          launch_spmv_fused<0, 1>(*A, G, S, phat.p, v.p, nullptr, dhat.p, partial.p, tickets.p + TK_SPMV,
+                                  st.p, FIN_BCGS_ALPHA, 1);
           reduce_finalize(FIN_BCGS_ALPHA, nullptr, 1);
           prof_end();
           bcgs_q_kernel<<<G, kBlock, 0, S>>>(N, d.p, v.p, q.p, st.p);
@@ -671,10 +724,8 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
           if (dist) halo->exchange(qhat.p, S);
           prof_end();
           prof_begin(PC_SPMV);
-          spmv_fused_kernel<0, 2><<<G, kBlock, 0, S>>>(N, A->slice_ptr.p, A->rowlen.p, A->col.p,
-                                                       A->val.p, qhat.p, t.p, nullptr, q.p,
-                                                       partial.p, tickets.p + TK_SPMV, st.p,
-                                                       FIN_BCGS_OMEGA, 1);
+          launch_spmv_fused<0, 2>(*A, G, S, qhat.p, t.p, nullptr, q.p, partial.p, tickets.p + TK_SPMV, st.p,
+                                  FIN_BCGS_OMEGA, 1);
           reduce_finalize(FIN_BCGS_OMEGA, nullptr, 1);
           prof_end();
           update_kernel<1><<<G, kBlock, 0, S>>>(N, x_dev, d.p, phat.p, q.p, qhat.p, t.p, dscale.p,
@@ -685,9 +736,7 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
         }
         if (s.north > 0 && ((iiter + 1) % s.north == 0)) {
           if (dist) halo->exchange(x_dev, S);
-          spmv_fused_kernel<1, 0><<<G, kBlock, 0, S>>>(N, A->slice_ptr.p, A->rowlen.p, A->col.p,
-                                                       A->val.p, x_dev, d.p, b_dev, nullptr,
-                                                       nullptr, nullptr, st.p, 0, 1);
+          launch_spmv_fused<1, 0>(*A, G, S, x_dev, d.p, b_dev, nullptr, nullptr, nullptr, st.p, 0, 1);
           launches++;
         }
       }

@@ -33,5 +33,29 @@ __device__ __forceinline__ double sell_row_dot(int row, const int *__restrict__ 
   }
   return t;
 }
+
+// Uniform-width variant: every SELL slice has the same width W (true for structured DIS grids and
+// regular DISV tilings), so the slot address needs neither slice_ptr nor rowlen and all 2W loads of
+// a row are issued at once.  Padding slots hold val = 0, col = own row: they add +0 at the END of the
+// row sum, so the result is still bit-identical to amux.
+template <int W>
+__device__ __forceinline__ double sell_row_dot_w(int row, const int *__restrict__ col,
+                                                 const double *__restrict__ val,
+                                                 const double *__restrict__ x) {
+  const long long base = (long long)(row >> 5) * (32 * W) + (row & 31);
+  double v[W], xv[W];
+  int c[W];
+#pragma unroll
+  for (int u = 0; u < W; u++) {
+    v[u] = __ldg(val + base + 32 * u);
+    c[u] = __ldg(col + base + 32 * u);
+  }
+#pragma unroll
+  for (int u = 0; u < W; u++) xv[u] = x[c[u]];
+  double t = 0.0;
+#pragma unroll
+  for (int u = 0; u < W; u++) t = t + v[u] * xv[u];
+  return t;
+}
 #endif
 }  // namespace mf6
