@@ -135,6 +135,14 @@ int mf6gpu_solver_apply_preconditioner(mf6gpu_solver *s, const double *r, double
  * launcher (MPI, torch.distributed, ...), every rank calls mf6gpu_comm_create. */
 int mf6gpu_comm_unique_id(void *out128);
 int mf6gpu_comm_create(int32_t nranks, int32_t rank, const void *id128, mf6gpu_comm **out);
+/* optional peer-memory (NVLink / NVSwitch) transport: each rank exports a mailbox (CUDA IPC handle,
+ * 64 bytes; halo_doubles = largest halo message of any rank), the launcher all-gathers the handles,
+ * every rank imports them.  Halo messages and the small all-gathers then move by direct st.global into
+ * the consumer's memory + system-scope flags instead of NCCL calls. */
+int mf6gpu_comm_p2p_export(mf6gpu_comm *c, int64_t halo_doubles, void *handle64);
+int mf6gpu_comm_p2p_import(mf6gpu_comm *c, const void *handles);
+int mf6gpu_comm_p2p_enabled(const mf6gpu_comm *c);
+int mf6gpu_comm_p2p_disable(mf6gpu_comm *c); /* back to NCCL (e.g. when another rank could not map) */
 int mf6gpu_comm_destroy(mf6gpu_comm *c);
 int mf6gpu_comm_rank(const mf6gpu_comm *c);
 int mf6gpu_comm_size(const mf6gpu_comm *c);

@@ -86,7 +86,7 @@ def c2_confined(nlay=10, nrow=1000, ncol=1000, gpu_ordering=T.ORDER_MULTICOLOR, 
 
 
 def c3_newton(nlay=5, nrow=2000, ncol=2000, gpu_ordering=T.ORDER_MULTICOLOR, nwel=100, ntrans=10,
-              seed=20260102, iallowptc=1):
+              seed=20260102, iallowptc=1, inner_maximum=None, outer_maximum=None):
     """unconfined transient with NEWTON UNDER_RELAXATION + STO.
     top 50, 5 layers x 10 m, icelltype 1 in the top layer, ss 1e-5, sy 0.15, RCH on top (sized for a 1.5 m mound),
     CHD on both sides, seeded wells (switched on in the transient period); BICGSTAB + ILU0, DBD under-relaxation (MODERATE preset values,
@@ -110,9 +110,17 @@ def c3_newton(nlay=5, nrow=2000, ncol=2000, gpu_ordering=T.ORDER_MULTICOLOR, nwe
     wel = Package(T.PKG_WEL, wnodes, np.full(wnodes.size, -500.0), iflowred=1, flowred=0.1)
     periods = [Period(1.0, 1, 1.0, True, [chd, rch]),
                Period(100.0, ntrans, 1.2, False, [chd, rch, wel])]
-    ims = T.ImsSettings.make(dvclose=1e-6, rclose=1e-2, iter1=100, ilinmeth=2, relax=0.0,
+    # iteration limits grow with the grid: the steady Newton period of the 2000 x 2000 grid needs
+    # thousands of BiCGSTAB iterations in total
+    big = nrow * ncol >= 250000
+    iter1 = inner_maximum or (4000 if big else 100)
+    mxiter = outer_maximum or 50
+    # INNER_RCLOSE is a per-cell flow residual: with millions of cells it must shrink, or the inner
+    # solver stops long before the water balance closes and the outer loop only inches forward
+    rclose = 1e-5 if big else 1e-2
+    ims = T.ImsSettings.make(dvclose=1e-6, rclose=rclose, iter1=iter1, ilinmeth=2, relax=0.0,
                              gpu_ordering=gpu_ordering)
-    sln = T.SlnSettings.make(dvclose=1e-4, mxiter=50, nonmeth=3, theta=0.9, akappa=1e-4, gamma=0.0,
+    sln = T.SlnSettings.make(dvclose=1e-4, mxiter=mxiter, nonmeth=3, theta=0.9, akappa=1e-4, gamma=0.0,
                              amomentum=0.0, iallowptc=iallowptc)
     return SimConfig(f"c3_newton_{nlay}x{nrow}x{ncol}", m, periods, sln, ims)
 

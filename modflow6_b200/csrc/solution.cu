@@ -1182,6 +1182,20 @@ static void create_solution(const mf6gpu_gwf_model *m, const mf6gpu_sln_settings
         if (sidx.empty()) sidx.push_back(0);
         H.send_idx.upload(sidx);
         H.sendbuf.alloc_zero(sidx.size());
+        {
+          std::vector<int> nr = H.nbr_rank;
+          if (nr.empty()) nr.push_back(0);
+          H.d_nbr_rank.upload(nr);
+          H.d_send_ptr.upload(H.send_ptr);
+          H.d_recv_ptr.upload(H.recv_ptr);
+          H.ticket.alloc_zero(1);
+          if (da->comm->p2p) {
+            for (int k = 0; k < da->nnbr; k++)
+              MF6_REQUIRE((size_t)(H.send_ptr[k + 1] - H.send_ptr[k]) <= da->comm->lay.halo_doubles &&
+                              (size_t)(H.recv_ptr[k + 1] - H.recv_ptr[k]) <= da->comm->lay.halo_doubles,
+                          "solution_create_dist: halo message larger than the peer mailbox");
+          }
+        }
         s->S->halo = &s->halo;
         s->os_all.alloc_zero(sizeof(OuterState) / sizeof(double) * (size_t)da->comm->nranks);
         s->h_os.alloc((size_t)da->comm->nranks);

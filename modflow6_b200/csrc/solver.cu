@@ -440,10 +440,22 @@ enum { FIN_UPDATE = 100 };
 
 // split-model path: combine the gathered per-rank records in rank order (deterministic and
 // identical on every rank) and run the same scalar epilogue the single-GPU kernels run inline
-__global__ void global_finalize_kernel(int mode, const RedRec *__restrict__ all, int nranks,
-                                       KState *st, double *out, int bcgs, SummaryPtrs sp) {
+__global__ void global_finalize_kernel(int mode, const RedRec *__restrict__ all_in, int nranks,
+                                       KState *st, double *out, int bcgs, SummaryPtrs sp, SmallGather sg) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const bool krylov = !(mode == FIN_NRM_MAX || mode == FIN_NRM_SSQ);
+  // peer-memory path: the records are read in place from the mailbox once their flags have arrived
+  // (waited for even when the loop is already done, so that every rank consumes every round)
+  RedRec rec[32];
+  const RedRec *all = all_in;
+  if (sg.base) {
+    for (int r = 0; r < nranks; r++) {
+      const double *src = small_gather_wait(sg, r);
+      double *dst = reinterpret_cast<double *>(&rec[r]);
+      for (int i = 0; i < (int)(sizeof(RedRec) / sizeof(double)); i++) dst[i] = __ldcg(src + i);
+    }
+    all = rec;
+  }
   if (krylov && st->done) return;
   double s0 = 0.0, s1 = 0.0;
   MaxLoc mx = maxloc_init(), mr = maxloc_init();
@@ -570,10 +582,11 @@ void mf6gpu_solver::reduce_finalize(int mode, double *out, int bcgs) {
   if (!halo || !halo->active()) return;
   SummaryPtrs sp{sum_itinner.p, sum_locdv.p, sum_locr.p, sum_dvmax.p, sum_rmax.p, sum_alpha.p, sum_omega.p};
   const size_t cnt = sizeof(RedRec) / sizeof(double);
-  comm_allgather(halo->comm, reinterpret_cast<const double *>(&st.p->red), red_all.p, cnt, stream);
+  SmallGather sg = comm_small_push(halo->comm, reinterpret_cast<const double *>(&st.p->red), cnt, stream);
+  if (!sg.base) comm_allgather(halo->comm, reinterpret_cast<const double *>(&st.p->red), red_all.p, cnt, stream);
   global_finalize_kernel<<<1, 1, 0, stream>>>(mode, reinterpret_cast<const RedRec *>(red_all.p),
-                                              halo->comm->nranks, st.p, out, bcgs, sp);
-  launches += 1;
+                                              halo->comm->nranks, st.p, out, bcgs, sp, sg);
+  launches += 2;
 }
 
 // ims_base_pcu, ImsLinearBase.f90:808-858
@@ -745,6 +758,7 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
       MF6_CK(cudaMemcpyAsync(h_st.p, st.p, sizeof(KState), cudaMemcpyDeviceToHost, S));
       MF6_CK(cudaStreamSynchronize(S));
       if (h_st.p->done) finished = true;
+      if (dist) comm_check(halo->comm);
       prof_on = true;
       if (profiling) {
         // the timed iteration is the first of the batch: it executed unless the loop had already ended

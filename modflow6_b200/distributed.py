@@ -235,6 +235,7 @@ class GpuComm:
         ensure_init()
         self._L = load()
         self.rank, self.nranks = rank, nranks
+        self.p2p = False
         self.h = C.c_void_p()
         if nranks > 1:
             import torch
@@ -251,6 +252,38 @@ class GpuComm:
             check(self._L.mf6gpu_comm_create(nranks, rank, buf, C.byref(self.h)))
         else:
             check(self._L.mf6gpu_comm_create(1, 0, None, C.byref(self.h)))
+
+    def enable_p2p(self, halo_doubles):
+        """Map every rank's mailbox with CUDA IPC so that halo messages and the small all-gathers move by
+        direct peer stores over NVLink instead of NCCL calls (MF6GPU_P2P=0 keeps NCCL).  `halo_doubles`
+        = this rank's largest halo message; the maximum over ranks sizes the mailboxes."""
+        import os
+        if self.nranks == 1 or os.environ.get("MF6GPU_P2P", "1") == "0" or self.p2p:
+            return self.p2p
+        import torch
+        import torch.distributed as dist
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.tensor([int(halo_doubles)], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cap = int(t.item())
+        buf = (C.c_ubyte * 64)()
+        ok = self._L.mf6gpu_comm_p2p_export(self.h, cap, buf) == 0
+        handles = [None] * self.nranks
+        dist.all_gather_object(handles, bytes(buf) if ok else None)
+        if any(h is None for h in handles):
+            return False
+        allh = (C.c_ubyte * (64 * self.nranks)).from_buffer_copy(b"".join(handles))
+        ok = self._L.mf6gpu_comm_p2p_import(self.h, allh) == 0
+        flags = [None] * self.nranks
+        dist.all_gather_object(flags, bool(ok))
+        self.p2p = all(flags)
+        if not self.p2p:
+            self._L.mf6gpu_comm_p2p_disable(self.h)
+        if not self.p2p and self.rank == 0:
+            print("modflow6_b200: CUDA IPC peer mapping unavailable (" +
+                  self._L.mf6gpu_last_error().decode("utf-8", "replace") + "); using NCCL send/recv + all-gather",
+                  flush=True)
+        return self.p2p
 
     def destroy(self):
         if self.h:
@@ -274,6 +307,8 @@ class GpuDistributedSolution:
         self._keep = [T.as_i32(sub.nbr_rank), T.as_i32(sub.send_ptr), T.as_i32(sub.send_idx),
                       T.as_i32(sub.recv_ptr), T.as_i32(sub.global_id)]
         k = self._keep
+        msg = max([0] + list(np.diff(sub.send_ptr)) + list(np.diff(sub.recv_ptr)))
+        comm.enable_p2p(int(msg))
         check(self._L.mf6gpu_solution_create_dist(C.byref(self._ms), C.byref(sln_settings), C.byref(ims_settings),
                                                   comm.h, sub.n_own, k[0].size, T.ptr_i32(k[0]), T.ptr_i32(k[1]),
                                                   T.ptr_i32(k[2]), T.ptr_i32(k[3]), T.ptr_i32(k[4]),

@@ -27,6 +27,7 @@ SYMBOLS = [
     "mf6gpu_solution_get_flowja", "mf6gpu_solution_get_condsat", "mf6gpu_solution_solver",
     "mf6gpu_solution_stat", "mf6gpu_matrix_create_ext", "mf6gpu_solution_create_dist",
     "mf6gpu_comm_unique_id", "mf6gpu_comm_create", "mf6gpu_comm_destroy", "mf6gpu_comm_rank", "mf6gpu_comm_size",
+    "mf6gpu_comm_p2p_export", "mf6gpu_comm_p2p_import", "mf6gpu_comm_p2p_enabled", "mf6gpu_comm_p2p_disable",
 ]
 
 _lib = None
@@ -87,6 +88,10 @@ def load():
     L.mf6gpu_comm_unique_id.argtypes = [C.c_void_p]
     L.mf6gpu_comm_create.argtypes = [i32, i32, C.c_void_p, vpp]
     L.mf6gpu_comm_destroy.argtypes = [vp]
+    L.mf6gpu_comm_p2p_export.argtypes = [vp, C.c_int64, C.c_void_p]
+    L.mf6gpu_comm_p2p_import.argtypes = [vp, C.c_void_p]
+    L.mf6gpu_comm_p2p_enabled.argtypes = [vp]
+    L.mf6gpu_comm_p2p_disable.argtypes = [vp]
     L.mf6gpu_comm_rank.argtypes = [vp]
     L.mf6gpu_comm_size.argtypes = [vp]
     L.mf6gpu_solution_create_dist.argtypes = [C.POINTER(T.GwfModelStruct), C.POINTER(T.SlnSettings),
