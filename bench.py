@@ -113,6 +113,22 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic(prefix):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel whose name starts with `prefix`,
+    from the newest committed ncu summary (profiles/*_traffic.json); None when there is no capture."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    for f in reversed(files):
+        try:
+            d = json.load(open(f))
+        except Exception:
+            continue
+        for k, v in d.items():
+            if k.startswith(prefix):
+                return {"bytes": v, "source": os.path.basename(f), "kernel": k}
+    return None
+
+
 def build_config(size, ordering, inner_maximum=500, outer_maximum=50):
     from modflow6_b200 import configs, ctypes_types as T
     nlay, nrow, ncol = size
@@ -327,6 +343,7 @@ def main():
                 kernels[name] = {"launch_groups": cnt, "mean_ms": tot / cnt,
                                  "achieved_gbs": ab[name] / dur / 1e9, "frac": ab[name] / dur / 1e9 / peak}
         sp = kernels.get("spmv", {"achieved_gbs": 0.0, "frac": 0.0})
+        tr = ncu_traffic("spmv_fused")
         iter_ms = sum(k["mean_ms"] for k in kernels.values())
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -349,7 +366,9 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "spmv_fused_kernel (SELL-32 SpMV + fused p.q)",
                          "achieved": sp["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": sp["frac"],
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": (tr["bytes"] if tr and size == (10, 1000, 1000) else None),
+                         "traffic_source": (f"ncu --set full, {tr['kernel']}, profiles/{tr['source']}" if tr else None),
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ab["spmv"],
                          "cg_iteration": {"algorithmic_bytes": ab["cg_iteration"], "mean_ms": iter_ms,
                                           "frac": (ab["cg_iteration"] / (iter_ms * 1e-3) / 1e9 / peak) if iter_ms else None},

@@ -96,5 +96,12 @@ if krows:
                   f"{d.get('sm__warps_active.avg.pct_of_peak_sustained_active','')} | "
                   f"{d.get('launch__registers_per_thread','')} | {d.get('lts__t_sector_hit_rate.pct','')} |")
     md.append("")
+    import json
+    traffic = {}
+    for d in krows:
+        t = traffic.setdefault(d["kernel"], [])
+        t.append((mb(d, "dram__bytes_read.sum") + mb(d, "dram__bytes_write.sum")) * 1e6)
+    json.dump({k: sum(v) / len(v) for k, v in traffic.items()},
+              open(os.path.join(out_dir, f"{rnd}_traffic.json"), "w"), indent=1)
 open(os.path.join(out_dir, f"{rnd}_summary.md"), "w").write("\n".join(md) + "\n")
 print("\n".join(md))
