@@ -52,7 +52,10 @@ typedef struct mf6gpu_sln_settings {
   double gamma;     /* UNDER_RELAXATION_GAMMA */
   double amomentum; /* UNDER_RELAXATION_MOMENTUM */
   int32_t iallowptc; /* 1 default; 0 = NO_PTC ALL; -1 = NO_PTC FIRST */
-  int32_t numtrack;  /* BACKTRACKING_NUMBER (only 0 supported) */
+  int32_t numtrack;  /* BACKTRACKING_NUMBER */
+  double btol;       /* BACKTRACKING_TOLERANCE */
+  double breduc;     /* BACKTRACKING_REDUCTION_FACTOR */
+  double res_lim;    /* BACKTRACKING_RESIDUAL_LIMIT */
 } mf6gpu_sln_settings;
 
 /* ---- one GWF model: DIS/DISV connectivity + NPF + STO ------------------
@@ -132,6 +135,8 @@ typedef struct mf6gpu_step_report {
   double max_dv;                 /* hncg of the last outer iteration (signed) */
   int32_t max_dv_loc;            /* 1-based node */
   int32_t npivot_fixes;
+  int32_t nbacktracks;           /* backtracking steps taken in this time step */
+  int32_t reserved;
   double totrin, totrot, pdiffr; /* Budget.f90:259-267 */
   double term_in[MF6GPU_MAX_BUDGET_TERMS];
   double term_out[MF6GPU_MAX_BUDGET_TERMS];

@@ -577,6 +577,16 @@ __global__ void dbd_kernel(int n, const int *__restrict__ ibound, double *__rest
   }
 }
 
+// apply_backtracking (NumericalSolution.f90:2828-2842): x = xtemp + breduc (x - xtemp) on active cells
+__global__ void backtrack_kernel(int n, const int *__restrict__ ibound, double *__restrict__ x,
+                                 const double *__restrict__ xtemp, double breduc) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (ibound[i] < 1) continue;
+    const double delx = breduc * (x[i] - xtemp[i]);
+    x[i] = xtemp[i] + delx;
+  }
+}
+
 // npf_nur (gwf-npf.f90:705-741)
 __global__ void nur_kernel(ModelView M, const int *__restrict__ ibotnode, double *__restrict__ x,
                            const double *__restrict__ xtemp, double *__restrict__ dx,
@@ -839,6 +849,8 @@ struct mf6gpu_solution {
   // outer state
   double relaxold = 1.0, bigchold = 0.0, bigch = 0.0;
   double ptcdel = 0.0, l2norm0 = 0.0;
+  double res_prev = 0.0, res_new = 0.0;  // backtracking
+  int nbacktracks = 0;
   double delt = 1.0;
   int iss = 1;
   int icnvg = 0;
@@ -928,6 +940,8 @@ struct mf6gpu_solution {
   void ls_fixups(int kiter, int kstp, int kper, int iptc, double ptcf);
   int solve_outer(int kiter, int kstp, int kper, double &hncg, int &lrch, double &tf, double &tl);
   void posneg(const double *a, int i0, int i1, double &rin, double &rout);
+  double residual_l2();
+  void backtracking(int kiter);
 };
 
 template <class T>
@@ -1033,11 +1047,53 @@ void mf6gpu_solution::ls_fixups(int kiter, int kstp, int kper, int iptc, double 
   }
 }
 
+// sln_l2norm (:2855-2871): || A x - b || with inactive rows zeroed
+double mf6gpu_solution::residual_l2() {
+  exchange_x();
+  nl++;
+  ptc_resid_kernel<<<grid_for(n), kBlock, 0, stream>>>(view(), A->val.p, x.p, rhs.p, partial.p, tickets.p + 1, os.p);
+  MF6_CK(cudaGetLastError());
+  return std::sqrt(fetch_os().l2);
+}
+
+// sln_backtracking (:2680-2776)
+void mf6gpu_solution::backtracking(int kiter) {
+  const int G = grid_for(n);
+  buildsystem(0);
+  if (kiter == 1) {
+    res_prev = residual_l2();
+  } else {
+    res_new = residual_l2();
+  }
+  if (kiter > 1) {
+    if (res_new > res_prev * ss.btol) {
+      for (int nbt = 1; nbt <= ss.numtrack; nbt++) {
+        // get_backtracking_flag (:2790-2822)
+        nl++;
+        dxmax_kernel<<<G, kBlock, 0, stream>>>(n, x.p, xtemp.p, ibound.p, A->ord_ptr(), pm.p, tickets.p, os.p);
+        MF6_CK(cudaGetLastError());
+        const double dx_abs_max = std::fabs(fetch_os().hncg);
+        if (!(ss.breduc * dx_abs_max >= ss.dvclose)) break;
+        nl++;
+        backtrack_kernel<<<G, kBlock, 0, stream>>>(n, ibound.p, x.p, xtemp.p, ss.breduc);
+        nbacktracks++;
+        buildsystem(0);
+        res_new = residual_l2();
+        if (nbt == ss.numtrack) break;
+        if (res_new < res_prev * ss.btol) break;
+        if (res_new < ss.res_lim) break;
+      }
+    }
+    res_prev = res_new;
+  }
+}
+
 // solve(kiter) (:1482-1837)
 int mf6gpu_solution::solve_outer(int kiter, int kstp, int kper, double &hncg, int &lrch, double &tf,
                                  double &tl) {
   const int G = grid_for(n);
   MF6_CK(cudaEventRecord(ev[0], stream));
+  if (ss.numtrack > 0) backtracking(kiter);
   buildsystem(1);
   int iptc;
   double ptcf;
@@ -1137,7 +1193,6 @@ static void create_solution(const mf6gpu_gwf_model *m, const mf6gpu_sln_settings
                             const mf6gpu_ims_settings *ims, const DistArgs *da, mf6gpu_solution **out) {
     MF6_REQUIRE(m && sln && ims && out, "solution_create: null argument");
     MF6_REQUIRE(m->ithickstrt == 0, "solution_create: THICKSTRT is not supported on the GPU path");
-    MF6_REQUIRE(sln->numtrack == 0, "solution_create: BACKTRACKING is not supported on the GPU path");
     if (!da) MF6_REQUIRE(m->njas * 2 == m->nja - m->nodes, "solution_create: nja/njas/nodes are inconsistent");
     MF6_REQUIRE((long long)m->njas < (1LL << 30), "solution_create: too many connections for one GPU");
     MF6_REQUIRE(!(m->inewton != 0 && ims->ilinmeth == 1),
@@ -1460,6 +1515,7 @@ int mf6gpu_solution_timestep(mf6gpu_solution *s, int32_t kper, int32_t kstp, dou
     int kiter, inner_total = 0, lrch = -1;
     double hncg = 0.0, tf = 0.0, tl = 0.0;
     s->icnvg = 0;
+    s->nbacktracks = 0;
     for (kiter = 1; kiter <= s->ss.mxiter; kiter++) {
       inner_total += s->solve_outer(kiter, kstp, kper, hncg, lrch, tf, tl);
       if (s->icnvg == 1) break;
@@ -1521,6 +1577,7 @@ int mf6gpu_solution_timestep(mf6gpu_solution *s, int32_t kper, int32_t kstp, dou
       rep->max_dv = hncg;
       rep->max_dv_loc = lrch >= 0 ? (s->halo.active() ? lrch : s->A->perm[lrch]) + 1 : 0;
       rep->npivot_fixes = s->S->npivfix;
+      rep->nbacktracks = s->nbacktracks;
       rep->t_formulate = tf;
       rep->t_linsolve = tl;
     }

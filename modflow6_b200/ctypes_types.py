@@ -59,12 +59,16 @@ class SlnSettings(C.Structure):
         ("amomentum", c_f64),
         ("iallowptc", c_i32),
         ("numtrack", c_i32),
+        ("btol", c_f64),
+        ("breduc", c_f64),
+        ("res_lim", c_f64),
     ]
 
     @classmethod
     def make(cls, dvclose=1e-5, mxiter=50, nonmeth=0, theta=0.0, akappa=0.0, gamma=0.0,
-             amomentum=0.0, iallowptc=1, numtrack=0):
-        return cls(dvclose, mxiter, nonmeth, theta, akappa, gamma, amomentum, iallowptc, numtrack)
+             amomentum=0.0, iallowptc=1, numtrack=0, btol=1.05, breduc=0.1, res_lim=0.002):
+        return cls(dvclose, mxiter, nonmeth, theta, akappa, gamma, amomentum, iallowptc, numtrack,
+                   btol, breduc, res_lim)
 
 
 class GwfModelStruct(C.Structure):
@@ -131,6 +135,8 @@ class StepReport(C.Structure):
         ("max_dv", c_f64),
         ("max_dv_loc", c_i32),
         ("npivot_fixes", c_i32),
+        ("nbacktracks", c_i32),
+        ("reserved", c_i32),
         ("totrin", c_f64),
         ("totrot", c_f64),
         ("pdiffr", c_f64),
@@ -143,7 +149,7 @@ class StepReport(C.Structure):
 
     def as_dict(self):
         d = {k: getattr(self, k) for k in ("converged", "outer_iterations", "inner_iterations",
-                                           "max_dv", "max_dv_loc", "npivot_fixes", "totrin",
+                                           "max_dv", "max_dv_loc", "npivot_fixes", "nbacktracks", "totrin",
                                            "totrot", "pdiffr", "t_formulate", "t_linsolve")}
         d["terms"] = {PKG_NAMES.get(self.term_id[i], str(self.term_id[i])) + f"#{i}":
                       (self.term_in[i], self.term_out[i]) for i in range(self.nterms)}

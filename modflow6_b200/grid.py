@@ -267,3 +267,60 @@ def tdis_steps(perlen, nstp, tsmult):
     for _ in range(nstp - 1):
         out.append(out[-1] * tsmult)
     return out
+
+
+def merge_models(models, exchanges):
+    """Serial multi-model solution: N GWF models + GWF-GWF exchanges in ONE system matrix, the way
+    sln_connect lays the models out one after the other (NumericalSolution.f90:2336-2381) and gwf_gwf_ac /
+    gwf_gwf_fc add the cross-model terms (exg-gwfgwf.f90:363-411, 488-550).
+
+    `exchanges`: list of dicts(m1=, m2=, nodem1=, nodem2=, ihc=, cl1=, cl2=, hwva=) with 0-based cell ids of the
+    EXCHANGEDATA block.  Returns the merged GwfModel (cell n of model k becomes offset[k] + n) and the offsets.
+    All models must share the NPF / STO options."""
+    offs = np.concatenate([[0], np.cumsum([m.nodes for m in models])]).astype(np.int64)
+    n = int(offs[-1])
+    # upper-triangle connection list of the merged model: (n, m, ihc, cl1, cl2, hwva)
+    rows, cols, ihc, cl1, cl2, hw = [], [], [], [], [], []
+    for k, m in enumerate(models):
+        r = np.repeat(np.arange(m.nodes, dtype=np.int64), np.diff(m.ia))
+        up = m.ja > r
+        j = m.jas[up]
+        rows.append(r[up] + offs[k]); cols.append(m.ja[up].astype(np.int64) + offs[k])
+        ihc.append(m.ihc[j]); cl1.append(m.cl1[j]); cl2.append(m.cl2[j]); hw.append(m.hwva[j])
+    for e in exchanges:
+        a = np.asarray(e["nodem1"], dtype=np.int64) + offs[e["m1"]]
+        b = np.asarray(e["nodem2"], dtype=np.int64) + offs[e["m2"]]
+        swap = a > b
+        rows.append(np.where(swap, b, a)); cols.append(np.where(swap, a, b))
+        ihc.append(np.asarray(e["ihc"], dtype=np.int32))
+        c1, c2 = np.asarray(e["cl1"], dtype=np.float64), np.asarray(e["cl2"], dtype=np.float64)
+        cl1.append(np.where(swap, c2, c1)); cl2.append(np.where(swap, c1, c2))
+        hw.append(np.asarray(e["hwva"], dtype=np.float64))
+    rows, cols = np.concatenate(rows), np.concatenate(cols)
+    ihc, cl1, cl2, hw = np.concatenate(ihc), np.concatenate(cl1), np.concatenate(cl2), np.concatenate(hw)
+    order = np.lexsort((cols, rows))            # (n, ascending m): the filljas numbering
+    rows, cols, ihc, cl1, cl2, hw = rows[order], cols[order], ihc[order], cl1[order], cl2[order], hw[order]
+    njas = rows.size
+    # full CSR: diagonal first, then ascending columns
+    allr = np.concatenate([np.arange(n), rows, cols])
+    allc = np.concatenate([np.arange(n), cols, rows])
+    alljas = np.concatenate([np.full(n, -1), np.arange(njas), np.arange(njas)])
+    isdiag = np.concatenate([np.zeros(n), np.ones(2 * njas)])
+    o2 = np.lexsort((allc, isdiag, allr))
+    ja, jas = allc[o2], alljas[o2]
+    ia = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(np.bincount(allr, minlength=n), out=ia[1:])
+    r2 = allr[o2]
+    key = r2 * n + ja
+    ko = np.argsort(key, kind="stable")
+    isym = ko[np.searchsorted(key[ko], ja * n + r2)]
+    cat = lambda name: np.concatenate([getattr(m, name) for m in models])  # noqa: E731
+    m0 = models[0]
+    return GwfModel(nodes=n, ia=ia, ja=ja, jas=jas, isym=isym, ihc=ihc, cl1=cl1, cl2=cl2, hwva=hw,
+                    top=cat("top"), bot=cat("bot"), area=cat("area"), k11=cat("k11"), k33=cat("k33"),
+                    icelltype=cat("icelltype"), strt=cat("strt"), ibound=cat("ibound"),
+                    ibotnode=np.concatenate([m.ibotnode + offs[k] for k, m in enumerate(models)]),
+                    ss=cat("ss"), sy=cat("sy"), iconvert=cat("iconvert"), icellavg=m0.icellavg,
+                    inewton=m0.inewton, inewtonur=m0.inewtonur, iperched=m0.iperched, ivarcv=m0.ivarcv,
+                    idewatcv=m0.idewatcv, insto=m0.insto, istor_coef=m0.istor_coef, iconf_ss=m0.iconf_ss,
+                    iorig_ss=m0.iorig_ss, shape=None), offs

@@ -60,6 +60,9 @@ struct orc_solution {
   double relaxold, bigchold, bigch;
   /* ptc */
   double ptcdel, l2norm0;
+  /* backtracking */
+  double res_prev, res_new;
+  int nbacktracks;
   int icnvg;
   double t_form, t_ls;
   double delt;
@@ -1061,10 +1064,49 @@ static void get_dxmax(orc_solution *S, double *hncg, int *lrch) {
   *lrch = nb;
 }
 
+/* sln_backtracking :2680-2776 (+ get_backtracking_flag / apply_backtracking :2790-2842) */
+static void backtracking(orc_solution *S, int kiter) {
+  const mf6gpu_sln_settings *c = &S->ss_;
+  buildsystem(S, 0);
+  if (kiter == 1) {
+    S->res_prev = l2norm_resid(S);
+  } else {
+    S->res_new = l2norm_resid(S);
+  }
+  if (kiter > 1) {
+    if (S->res_new > S->res_prev * c->btol) {
+      for (int nb = 1; nb <= c->numtrack; nb++) {
+        /* get_backtracking_flag */
+        double dx_abs_max = 0.0;
+        for (int i = 0; i < S->nodes; i++) {
+          if (S->ibound[i] < 1) continue;
+          double dx_abs = fabs(S->x[i] - S->xtemp[i]);
+          if (dx_abs > dx_abs_max) dx_abs_max = dx_abs;
+        }
+        if (!(c->breduc * dx_abs_max >= c->dvclose)) break;
+        /* apply_backtracking */
+        for (int i = 0; i < S->nodes; i++) {
+          if (S->ibound[i] < 1) continue;
+          double delx = c->breduc * (S->x[i] - S->xtemp[i]);
+          S->x[i] = S->xtemp[i] + delx;
+        }
+        S->nbacktracks++;
+        buildsystem(S, 0);
+        S->res_new = l2norm_resid(S);
+        if (nb == c->numtrack) break;
+        if (S->res_new < S->res_prev * c->btol) break;
+        if (S->res_new < c->res_lim) break;
+      }
+    }
+    S->res_prev = S->res_new;
+  }
+}
+
 /* solve(kiter) :1482-1837 ; returns inner iterations */
 static int solve_outer(orc_solution *S, int kiter, int kstp, int kper,
                        double *hncg, int *lrch) {
   double t0 = now_s();
+  if (S->ss_.numtrack > 0) backtracking(S, kiter);
   buildsystem(S, 1);
   int iptc;
   double ptcf;
@@ -1121,6 +1163,7 @@ int orc_sln_timestep(orc_solution *S, int kper, int kstp, double delt, int iss,
   int kiter, inner_total = 0, lrch = -1;
   double hncg = 0.0;
   S->icnvg = 0;
+  S->nbacktracks = 0;
   for (kiter = 1; kiter <= S->ss_.mxiter; kiter++) {
     inner_total += solve_outer(S, kiter, kstp, kper, &hncg, &lrch);
     if (S->icnvg == 1) break;
@@ -1181,6 +1224,7 @@ int orc_sln_timestep(orc_solution *S, int kper, int kstp, double delt, int iss,
     rep->max_dv = hncg;
     rep->max_dv_loc = lrch + 1;
     rep->npivot_fixes = S->ims->npivfix;
+    rep->nbacktracks = S->nbacktracks;
     rep->t_formulate = S->t_form - tf0;
     rep->t_linsolve = S->t_ls - tl0;
   } else {

@@ -163,3 +163,31 @@ def test_size_independent_properties_medium_grid(gpu):
     assert np.allclose(f[off], -f[m.isym[off]], rtol=0, atol=0)
     resid = f[m.ia[:-1]]                      # after csr_diagsum: residual of every cell's water balance
     assert np.abs(resid).max() <= 10 * cfg.ims.rclose * 50
+
+
+def test_backtracking_parity(gpu):
+    """BACKTRACKING_NUMBER > 0: same backtracking steps, same heads"""
+    cfg = configs.c1_npf01("a", T.ORDER_NATURAL)
+    cfg.sln = T.SlnSettings.make(dvclose=1e-6, mxiter=100, nonmeth=0, numtrack=5, btol=0.3, breduc=0.5, res_lim=1e-9)
+    G, O = _pair(cfg)
+    a = configs.run_simulation(G, cfg, max_steps=3, collect_heads=True)
+    b = configs.run_simulation(O, cfg, max_steps=3, collect_heads=True)
+    assert sum(r["nbacktracks"] for r in b) >= 2
+    for x, y in zip(a, b):
+        assert (x["nbacktracks"], x["outer_iterations"], x["converged"]) == (y["nbacktracks"], y["outer_iterations"], 1)
+        assert np.abs(x["head"] - y["head"]).max() <= 0.5e-6
+
+
+def test_two_models_one_solution(gpu):
+    """test_par_gwf01 literally (two models + GWF-GWF exchange) through the serial multi-model path"""
+    from modflow6_b200.solution import GpuNumericalSolution
+    from tests.test_oracle_known_answers import _two_model_case
+    merged, offs, chd = _two_model_case(5, 5)
+    for ordering in (T.ORDER_NATURAL, T.ORDER_MULTICOLOR):
+        ims = T.ImsSettings.make(dvclose=1e-9, rclose=1e-6, iter1=200, ilinmeth=2, relax=0.97, gpu_ordering=ordering)
+        G = GpuNumericalSolution(merged, T.SlnSettings.make(dvclose=1e-9, mxiter=50), ims)
+        G.set_packages([chd])
+        assert G.timestep().converged == 1
+        h = G.x
+        assert np.allclose(h[:offs[1]].reshape(5, 5, 5), np.arange(1.0, 6.0)[None, None, :], atol=1e-6)
+        assert np.allclose(h[offs[1]:].reshape(5, 5, 5), np.arange(6.0, 11.0)[None, None, :], atol=1e-6)

@@ -5,7 +5,7 @@ import pytest
 
 from modflow6_b200 import configs
 from modflow6_b200 import ctypes_types as T
-from modflow6_b200.grid import Package, build_dis_model, dis_connectivity, tdis_steps
+from modflow6_b200.grid import Package, build_dis_model, dis_connectivity, merge_models, tdis_steps
 from oracle.oracle import OracleIlu0, OracleIms, OracleSolution, amux
 from tests.helpers import assembled_system, chd_west_east, hetero_dis, permute_csr, well_center
 
@@ -183,3 +183,44 @@ def test_packages_riv_ghb_drn_budget_closes():
     assert rep.converged == 1 and abs(rep.pdiffr) < 1e-4
     d = rep.as_dict()["terms"]
     assert len(d) == 4
+
+
+def _two_model_case(nlay, nrow):
+    """autotest/test_par_gwf01.py:20-120 literally: two nlay x nrow x 5 models side by side, joined by a GWF-GWF
+    exchange between column 5 of the left and column 1 of the right model, CHD 1 on the far left, 10 on the far
+    right"""
+    mk = lambda strt: build_dis_model(nlay, nrow, 5, 100.0, 100.0, 0.0, -10.0 * np.arange(1, nlay + 1), 1.0, strt=strt)  # noqa: E731
+    left, right = mk(1.0), mk(10.0)
+    kk, ii = np.meshgrid(np.arange(nlay), np.arange(nrow), indexing="ij")
+    n1 = ((kk * nrow + ii) * 5 + 4).reshape(-1)
+    n2 = ((kk * nrow + ii) * 5 + 0).reshape(-1)
+    ex = dict(m1=0, m2=1, nodem1=n1, nodem2=n2, ihc=np.ones(n1.size, np.int32), cl1=np.full(n1.size, 50.0),
+              cl2=np.full(n1.size, 50.0), hwva=np.full(n1.size, 100.0))
+    merged, offs = merge_models([left, right], [ex])
+    chd = Package(T.PKG_CHD, np.concatenate([n2 + offs[0], n1 + offs[1]]),
+                  np.concatenate([np.full(n2.size, 1.0), np.full(n1.size, 10.0)]))
+    return merged, offs, chd
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (1, 5), (5, 5)])
+def test_par_gwf01_two_models_and_exchange(shape):
+    """the same answer through the serial multi-model path (models merged into one solution matrix)"""
+    merged, offs, chd = _two_model_case(*shape)
+    ims = T.ImsSettings.make(dvclose=1e-9, rclose=1e-6, iter1=100, ilinmeth=2, relax=0.97)
+    S = OracleSolution(merged, T.SlnSettings.make(dvclose=1e-9, mxiter=50), ims)
+    S.set_packages([chd])
+    assert S.timestep().converged == 1
+    h = S.x
+    left = h[:offs[1]].reshape(shape[0], shape[1], 5)
+    right = h[offs[1]:].reshape(shape[0], shape[1], 5)
+    assert np.allclose(left, np.arange(1.0, 6.0)[None, None, :], atol=1e-6)
+    assert np.allclose(right, np.arange(6.0, 11.0)[None, None, :], atol=1e-6)
+
+
+def test_backtracking_is_exercised():
+    """sln_backtracking (NumericalSolution.f90:2680-2842): a tight BACKTRACKING_TOLERANCE forces steps"""
+    cfg = configs.c1_npf01("a")
+    cfg.sln = T.SlnSettings.make(dvclose=1e-6, mxiter=100, nonmeth=0, numtrack=5, btol=0.3, breduc=0.5, res_lim=1e-9)
+    O = OracleSolution(cfg.model, cfg.sln, cfg.ims)
+    reps = configs.run_simulation(O, cfg, max_steps=3)
+    assert all(r["converged"] == 1 for r in reps) and sum(r["nbacktracks"] for r in reps) >= 2
