@@ -188,7 +188,8 @@ int mf6gpu_solution_get_flowja(mf6gpu_solution *s, double *flowja);
 int mf6gpu_solution_get_condsat(mf6gpu_solution *s, double *condsat);
 /* the linear solver owned by the solution (for stats / summary) */
 mf6gpu_solver *mf6gpu_solution_solver(mf6gpu_solution *s);
-/* facts: 0 kernel launches of the last time step, 1 ILU levels, 2 SELL slots */
+/* facts: 0 kernel launches of the last time step, 1 ILU levels, 2 SELL slots,
+ * 3 fraction of stencil-compressed (slice, slot) column groups, 4 fixed SELL width (0 = ragged) */
 double mf6gpu_solution_stat(const mf6gpu_solution *s, int what);
 
 #ifdef __cplusplus

@@ -215,7 +215,8 @@ ilu0_bwd_level_kernel(int r0, int r1, const int *__restrict__ slice_ptr,
 //   PHASE 1 (rows of level 0):  z = (r - sum_k lu_k z[col_k]) * piv     (backward; forward value = r)
 template <int W, int PHASE>
 __global__ void __launch_bounds__(kBlock, 8)
-ilu0_two_level_kernel(int r0, int r1, const int *__restrict__ col, const double *__restrict__ lu,
+ilu0_two_level_kernel(int r0, int r1, int ncols, const int *__restrict__ col,
+                      const int *__restrict__ soff, const double *__restrict__ lu,
                       const double *__restrict__ rin, double *__restrict__ d,
                       const int *__restrict__ done, IluDot D) {
   if (done && *done) return;
@@ -226,9 +227,20 @@ ilu0_two_level_kernel(int r0, int r1, const int *__restrict__ col, const double 
     double v[W], dv[W];
     int c[W];
 #pragma unroll
-    for (int u = 0; u < W; u++) {
-      v[u] = __ldg(lu + base + 32 * u);
-      c[u] = __ldg(col + base + 32 * u);
+    for (int u = 0; u < W; u++) v[u] = __ldg(lu + base + 32 * u);
+    if (soff) {  // stencil-compressed columns (matrix.cuh)
+      const int *so = soff + (r >> 5) * W;
+#pragma unroll
+      for (int u = 1; u < W; u++) {
+        const int o = __ldg(so + u);
+        if (o != INT_MIN)
+          c[u] = min(max(r + o, 0), ncols - 1);
+        else
+          c[u] = __ldg(col + base + 32 * u);
+      }
+    } else {
+#pragma unroll
+      for (int u = 1; u < W; u++) c[u] = __ldg(col + base + 32 * u);
     }
     const double rr = rin[r];
 #pragma unroll
@@ -250,8 +262,9 @@ static int launch_two_level(const mf6gpu_matrix &A, const double *lu, const doub
   const int gA = (A.n - lvl1 + kBlock - 1) / kBlock, gB = (lvl1 + kBlock - 1) / kBlock;
   IluDot DA{dot ? dot->partial : nullptr};
   IluDot DB{dot ? dot->partial + gA * (kBlock / 32) : nullptr};
-  ilu0_two_level_kernel<W, 0><<<gA, kBlock, 0, s>>>(lvl1, A.n, A.col.p, lu, rin, d, done, DA);
-  ilu0_two_level_kernel<W, 1><<<gB, kBlock, 0, s>>>(0, lvl1, A.col.p, lu, rin, d, done, DB);
+  const int *so = A.slot_off.n ? A.slot_off.p : nullptr;
+  ilu0_two_level_kernel<W, 0><<<gA, kBlock, 0, s>>>(lvl1, A.n, A.n_ext, A.col.p, so, lu, rin, d, done, DA);
+  ilu0_two_level_kernel<W, 1><<<gB, kBlock, 0, s>>>(0, lvl1, A.n_ext, A.col.p, so, lu, rin, d, done, DB);
   int launches = 2;
   if (dot) {
     const int slot = (gA + gB) * (kBlock / 32);

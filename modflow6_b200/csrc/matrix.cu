@@ -252,6 +252,33 @@ static void build_matrix(mf6gpu_matrix &M, int n, int n_ext, int nja, const int3
     int w = (slice_ptr[(r >> 5) + 1] - slice_ptr[r >> 5]) / 32;
     for (int k = 0; k < w; k++) col[base_slot + 32LL * k] = 0;
   }
+  // --- stencil compression table (fixed-width layout)
+  if (M.uniform_w > 0 && !std::getenv("MF6GPU_NO_STENCIL")) {
+    const int W = M.uniform_w;
+    std::vector<int> soff((size_t)M.nslices * W, 0);
+    long long hit = 0;
+    for (int sl = 0; sl < M.nslices; sl++) {
+      for (int k = 0; k < W; k++) {
+        bool have = false, uni = true;
+        int off = 0;
+        for (int r = sl * 32; r < std::min(n, sl * 32 + 32); r++) {
+          if (k >= rowlen[r]) continue;  // padding slot: its value is 0, any in-range column will do
+          const int o = col[(size_t)slice_ptr[sl] + 32 * k + (r & 31)] - r;
+          if (!have) {
+            off = o;
+            have = true;
+          } else if (o != off) {
+            uni = false;
+            break;
+          }
+        }
+        soff[(size_t)sl * W + k] = uni ? off : kNoOffset;
+        if (uni) hit++;
+      }
+    }
+    M.slot_off_hit = (double)hit / (double)soff.size();
+    M.slot_off.upload(soff);
+  }
   // --- upload
   M.d_perm.upload(M.perm);
   M.d_iperm.upload(M.iperm);
@@ -372,6 +399,8 @@ int64_t mf6gpu_matrix_info(const mf6gpu_matrix *m, int what) {
     case 3: return m->ordering;
     case 4: return m->nslots;
     case 5: return m->maxlen;
+    case 6: return m->uniform_w;
+    case 7: return (int64_t)(1000.0 * m->slot_off_hit);
   }
   return -1;
 }

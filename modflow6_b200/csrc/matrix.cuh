@@ -34,6 +34,11 @@ struct mf6gpu_matrix {
   mf6::DevBuf<unsigned char> rowlen, nlow;  // [n]
   mf6::DevBuf<unsigned char> rowlen_loc_buf; // [n] entries without halo columns (ILU); empty => same as rowlen
   const unsigned char *rowlen_loc() const { return rowlen_loc_buf.n ? rowlen_loc_buf.p : rowlen.p; }
+  // stencil compression of the column indices (fixed-width layout only): slot_off[s*W + k] = col - row
+  // when that difference is the same for every real entry of slot k in slice s, else kNoOffset ->
+  // the Krylov kernels then skip the 4-byte column loads of that slot for the whole warp
+  mf6::DevBuf<int> slot_off;
+  double slot_off_hit = 0.0;   // fraction of (slice, slot) pairs that are compressed
   mf6::DevBuf<int> csr2sell;   // [nja] slot of each original CSR entry
   mf6::DevBuf<double> stage;   // [nja] H2D/D2H staging of CSR values
   mf6::DevBuf<double> xs, ys;  // [n] staging vectors for host multiply
@@ -42,6 +47,8 @@ struct mf6gpu_matrix {
 };
 
 namespace mf6 {
+
+constexpr int kNoOffset = INT_MIN;
 
 // y = A x (device vectors in final numbering); optional fused dot partial:
 // if dot_with != nullptr accumulates sum_r dot_with[r]*y[r] into partial[blockIdx]

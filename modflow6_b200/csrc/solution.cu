@@ -1665,6 +1665,8 @@ double mf6gpu_solution_stat(const mf6gpu_solution *s, int what) {
     case 0: return (double)s->nl;
     case 1: return (double)s->A->nlevels;
     case 2: return (double)s->A->nslots;
+    case 3: return s->A->slot_off_hit;
+    case 4: return (double)s->A->uniform_w;
   }
   return -1.0;
 }

@@ -229,8 +229,8 @@ spmv_fused_kernel(int n, const int *__restrict__ slice_ptr,
 // fixed-width variant (see sell_row_dot_w): no slice_ptr / rowlen loads
 template <int EPI, int NDOT, int W>
 __global__ void __launch_bounds__(kBlock)
-spmv_fused_w_kernel(int n, const int *__restrict__ col, const double *__restrict__ val,
-                    const double *__restrict__ x, double *__restrict__ y,
+spmv_fused_w_kernel(int n, int ncols, const int *__restrict__ col, const int *__restrict__ soff,
+                    const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y,
                     const double *__restrict__ b, const double *__restrict__ w,
                     double *__restrict__ partial, unsigned int *ticket, KState *st, int mode,
                     int check_done) {
@@ -239,7 +239,7 @@ spmv_fused_w_kernel(int n, const int *__restrict__ col, const double *__restrict
   if (check_done && st->done) return;
   double s0 = 0.0, s1 = 0.0;
   for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
-    double t = sell_row_dot_w<W>(row, col, val, x);
+    double t = sell_row_dot_w<W>(row, col, val, x, soff, ncols);
     if (EPI == 1) t = b[row] - t;
     y[row] = t;
     if (NDOT >= 1) s0 += w[row] * t;
@@ -264,7 +264,9 @@ static void launch_spmv_fused(const mf6gpu_matrix &A, int G, cudaStream_t S, con
   const int N = A.n;
 #define MF6_SPMV_W(WW)                                                                              \
   case WW:                                                                                          \
-    spmv_fused_w_kernel<EPI, NDOT, WW><<<G, kBlock, 0, S>>>(N, A.col.p, A.val.p, x, y, b, w, partial, \
+    spmv_fused_w_kernel<EPI, NDOT, WW><<<G, kBlock, 0, S>>>(N, A.n_ext, A.col.p,                     \
+                                                            A.slot_off.n ? A.slot_off.p : nullptr,  \
+                                                            A.val.p, x, y, b, w, partial,           \
                                                             ticket, st, mode, check_done);          \
     return;
   switch (A.uniform_w) {

@@ -38,17 +38,31 @@ __device__ __forceinline__ double sell_row_dot(int row, const int *__restrict__ 
 // regular DISV tilings), so the slot address needs neither slice_ptr nor rowlen and all 2W loads of
 // a row are issued at once.  Padding slots hold val = 0, col = own row: they add +0 at the END of the
 // row sum, so the result is still bit-identical to amux.
+// soff (may be null): stencil table, see matrix.cuh -- slots whose column is row + constant for the
+// whole slice take the column from the table (one broadcast load per warp) instead of the col array.
 template <int W>
 __device__ __forceinline__ double sell_row_dot_w(int row, const int *__restrict__ col,
                                                  const double *__restrict__ val,
-                                                 const double *__restrict__ x) {
+                                                 const double *__restrict__ x,
+                                                 const int *__restrict__ soff, int ncols) {
   const long long base = (long long)(row >> 5) * (32 * W) + (row & 31);
   double v[W], xv[W];
   int c[W];
 #pragma unroll
-  for (int u = 0; u < W; u++) {
-    v[u] = __ldg(val + base + 32 * u);
-    c[u] = __ldg(col + base + 32 * u);
+  for (int u = 0; u < W; u++) v[u] = __ldg(val + base + 32 * u);
+  if (soff) {
+    const int *so = soff + (row >> 5) * W;
+#pragma unroll
+    for (int u = 0; u < W; u++) {
+      const int o = __ldg(so + u);
+      if (o != INT_MIN)
+        c[u] = min(max(row + o, 0), ncols - 1);
+      else
+        c[u] = __ldg(col + base + 32 * u);
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < W; u++) c[u] = __ldg(col + base + 32 * u);
   }
 #pragma unroll
   for (int u = 0; u < W; u++) xv[u] = x[c[u]];
