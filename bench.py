@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", default="10,1000,1000", help="nlay,nrow,ncol of the C2 grid")
-    ap.add_argument("--ordering", default="multicolor", choices=["multicolor", "natural"])
+    ap.add_argument("--ordering", default="multicolor", choices=["multicolor", "natural", "block"])
     ap.add_argument("--cpu-iters", type=int, default=12, help="inner iterations of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--inner-maximum", type=int, default=500, help="INNER_MAXIMUM of the IMS LINEAR block")
@@ -132,7 +132,7 @@ def ncu_traffic(prefix):
 def build_config(size, ordering, inner_maximum=500, outer_maximum=50):
     from modflow6_b200 import configs, ctypes_types as T
     nlay, nrow, ncol = size
-    o = T.ORDER_MULTICOLOR if ordering == "multicolor" else T.ORDER_NATURAL
+    o = {"multicolor": T.ORDER_MULTICOLOR, "natural": T.ORDER_NATURAL, "block": T.ORDER_BLOCK_MULTICOLOR}[ordering]
     return configs.c2_confined(nlay, nrow, ncol, gpu_ordering=o, inner_maximum=inner_maximum,
                                outer_maximum=outer_maximum)
 
@@ -253,7 +253,8 @@ def main():
         pr, pc = world, 1
         spec = GridSpec(nlay=size[0], nrow=size[1] * pr, ncol=size[2] * pc)
         sub = build_dis_block(spec, pr, pc, rank)
-        o = T.ORDER_MULTICOLOR if args.ordering == "multicolor" else T.ORDER_NATURAL
+        o = {"multicolor": T.ORDER_MULTICOLOR, "natural": T.ORDER_NATURAL,
+             "block": T.ORDER_BLOCK_MULTICOLOR}[args.ordering]
         ims_s = T.ImsSettings.make(dvclose=1e-6, rclose=1e-2, iter1=args.inner_maximum, ilinmeth=1, relax=0.0,
                                    gpu_ordering=o)
         sln_s = T.SlnSettings.make(dvclose=1e-5, mxiter=args.outer_maximum, nonmeth=0)

@@ -80,9 +80,14 @@ int mf6gpu_matrix_multiply(mf6gpu_matrix *m, const double *x, double *y);
 int mf6gpu_matrix_create_ext(int32_t n_own, int32_t n_ext, int32_t nja, const int32_t *ia,
                              const int32_t *ja, int32_t index_base, int32_t gpu_ordering,
                              const int32_t *global_id, mf6gpu_matrix **out);
+/* as above plus block_id[n_own] (may be NULL): the blocks of MF6GPU_ORDER_BLOCK_MULTICOLOR */
+int mf6gpu_matrix_create_blocked(int32_t n_own, int32_t n_ext, int32_t nja, const int32_t *ia,
+                                 const int32_t *ja, int32_t index_base, int32_t gpu_ordering,
+                                 const int32_t *global_id, const int32_t *block_id, mf6gpu_matrix **out);
 /* structure facts: 0 n, 1 nja, 2 number of ILU levels, 3 ordering, 4 SELL slots */
 int64_t mf6gpu_matrix_info(const mf6gpu_matrix *m, int what);
-/* final permutation: perm[new] = old (0-based), length n */
+/* elimination order of the ILU: perm[k] = row (0-based, original numbering) eliminated k-th; this is the
+ * symmetric permutation under which the device ILU0 equals the reference algorithm (NATURAL: identity) */
 int mf6gpu_matrix_get_permutation(const mf6gpu_matrix *m, int32_t *perm);
 
 /* ---- VectorBaseType (SeqVector.f90) ---------------------------------------- */
@@ -186,6 +191,8 @@ int mf6gpu_solution_get_amat(mf6gpu_solution *s, double *amat);  /* CSR order */
 int mf6gpu_solution_get_rhs(mf6gpu_solution *s, double *rhs);
 int mf6gpu_solution_get_flowja(mf6gpu_solution *s, double *flowja);
 int mf6gpu_solution_get_condsat(mf6gpu_solution *s, double *condsat);
+/* elimination order of the owned cells (see mf6gpu_matrix_get_permutation) */
+int mf6gpu_solution_get_permutation(mf6gpu_solution *s, int32_t *perm);
 /* the linear solver owned by the solution (for stats / summary) */
 mf6gpu_solver *mf6gpu_solution_solver(mf6gpu_solution *s);
 /* facts: 0 kernel launches of the last time step, 1 ILU levels, 2 SELL slots,

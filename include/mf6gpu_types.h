@@ -34,13 +34,17 @@ typedef struct mf6gpu_ims_settings {
   /* GPU-path extension (not an .ims keyword; chosen like a PETSc rc option):
    * ordering of the ILU0/MILU0 elimination.
    *   0 = NATURAL    exact reference order, level-scheduled wavefronts
-   *   1 = MULTICOLOR greedy colouring of the matrix graph (few, wide levels) */
+   *   1 = MULTICOLOR greedy colouring of the matrix graph (few, wide levels)
+   *   2 = BLOCK_MULTICOLOR colouring of the vertical cell columns (blocks), natural order inside a
+   *       column: nlay+1 levels, convergence close to NATURAL (the strong vertical couplings are
+   *       eliminated exactly); falls back to 1 when no blocks are known */
   int32_t gpu_ordering;
   int32_t reserved;
 } mf6gpu_ims_settings;
 
 #define MF6GPU_ORDER_NATURAL 0
 #define MF6GPU_ORDER_MULTICOLOR 1
+#define MF6GPU_ORDER_BLOCK_MULTICOLOR 2
 
 /* ---- IMS NONLINEAR block + OPTIONS (NumericalSolution.f90:568-866) ------- */
 typedef struct mf6gpu_sln_settings {

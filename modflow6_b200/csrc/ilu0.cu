@@ -207,6 +207,281 @@ ilu0_bwd_level_kernel(int r0, int r1, const int *__restrict__ slice_ptr,
   if (D.partial) ilu_dot_finish(dot, D);
 }
 
+// ---- fixed-width SELL variants of the level kernels (any number of levels) ---------------------
+// Same arithmetic as ilu0_fwd/bwd_level_kernel; the slot address needs neither slice_ptr nor rowlen
+// (padding slots hold lu = 0) and the columns come from the stencil table where the slice allows it.
+template <int W>
+__device__ __forceinline__ int ilu_col(int r, int u, long long base, const int *__restrict__ col,
+                                       const int *__restrict__ so, int ncols) {
+  if (so) {
+    const int o = __ldg(so + u);
+    if (o != INT_MIN) return min(max(r + o, 0), ncols - 1);
+  }
+  return __ldg(col + base + 32 * u);
+}
+
+template <int W, bool FINAL>
+__global__ void __launch_bounds__(kBlock, 8)
+ilu0_fwd_w_kernel(int r0, int r1, int lvl1_start, int ncols, const unsigned char *__restrict__ nlow,
+                  const int *__restrict__ col, const int *__restrict__ soff,
+                  const double *__restrict__ lu, const double *__restrict__ rin,
+                  double *__restrict__ d, const int *__restrict__ done, IluDot D) {
+  if (done && *done) return;
+  double dot = 0.0;
+  const int r = r0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < r1) {
+    const int lo = nlow[r];
+    const long long base = (long long)(r >> 5) * (32 * W) + (r & 31);
+    const int *so = soff ? soff + (r >> 5) * W : nullptr;
+    double v[W], dv[W];
+#pragma unroll
+    for (int u = 1; u < W; u++) {
+      v[u] = 0.0;
+      dv[u] = 0.0;
+      if (u <= lo) {
+        v[u] = __ldg(lu + base + 32 * u);
+        const int c = ilu_col<W>(r, u, base, col, so, ncols);
+        dv[u] = (c < lvl1_start) ? rin[c] : d[c];
+      }
+    }
+    const double rr = rin[r];
+    double tv = rr;
+#pragma unroll
+    for (int u = 1; u < W; u++)
+      if (u <= lo) tv = tv - v[u] * dv[u];
+    if (FINAL) {
+      tv = tv * __ldg(lu + base);
+      dot = rr * tv;
+    }
+    d[r] = tv;
+  }
+  if (FINAL && D.partial) ilu_dot_finish(dot, D);
+}
+
+template <int W, bool LEVEL0>
+__global__ void __launch_bounds__(kBlock, 8)
+ilu0_bwd_w_kernel(int r0, int r1, int ncols, const unsigned char *__restrict__ nlow,
+                  const int *__restrict__ col, const int *__restrict__ soff,
+                  const double *__restrict__ lu, const double *__restrict__ rin,
+                  double *__restrict__ d, const int *__restrict__ done, IluDot D) {
+  if (done && *done) return;
+  double dot = 0.0;
+  const int r = r0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < r1) {
+    const int lo = nlow[r];
+    const long long base = (long long)(r >> 5) * (32 * W) + (r & 31);
+    const int *so = soff ? soff + (r >> 5) * W : nullptr;
+    double v[W], dv[W];
+    const double piv = __ldg(lu + base);
+#pragma unroll
+    for (int u = 1; u < W; u++) {
+      v[u] = 0.0;
+      dv[u] = 0.0;
+      if (u > lo) {
+        v[u] = __ldg(lu + base + 32 * u);
+        const int c = ilu_col<W>(r, u, base, col, so, ncols);
+        dv[u] = d[c];
+      }
+    }
+    const double rr = rin[r];
+    double tv = LEVEL0 ? rr : d[r];
+#pragma unroll
+    for (int u = 1; u < W; u++)
+      if (u > lo) tv = tv - v[u] * dv[u];
+    tv = tv * piv;
+    d[r] = tv;
+    dot = rr * tv;
+  }
+  if (D.partial) ilu_dot_finish(dot, D);
+}
+
+template <int W>
+static int launch_levels_w(const mf6gpu_matrix &A, const double *lu, const double *rin, double *d,
+                           const int *done, cudaStream_t s, const IluDotArgs *dot) {
+  int launches = 0;
+  const int L = A.nlevels;
+  const int lvl1 = (L > 1) ? A.level_ptr[1] : A.n;
+  const int *so = A.slot_off.n ? A.slot_off.p : nullptr;
+  int slot = 0;
+  for (int l = 1; l < L; l++) {
+    const int r0 = A.level_ptr[l], r1 = A.level_ptr[l + 1];
+    if (r1 <= r0) continue;
+    const int g = (r1 - r0 + kBlock - 1) / kBlock;
+    if (l == L - 1) {
+      IluDot D{dot ? dot->partial + slot : nullptr};
+      slot += g * (kBlock / 32);
+      ilu0_fwd_w_kernel<W, true><<<g, kBlock, 0, s>>>(r0, r1, lvl1, A.n_ext, A.nlow.p, A.col.p, so, lu, rin, d,
+                                                      done, D);
+    } else {
+      ilu0_fwd_w_kernel<W, false><<<g, kBlock, 0, s>>>(r0, r1, lvl1, A.n_ext, A.nlow.p, A.col.p, so, lu, rin, d,
+                                                       done, IluDot{nullptr});
+    }
+    launches++;
+  }
+  for (int l = (L > 1 ? L - 2 : 0); l >= 0; l--) {
+    const int r0 = A.level_ptr[l], r1 = A.level_ptr[l + 1];
+    if (r1 <= r0) continue;
+    const int g = (r1 - r0 + kBlock - 1) / kBlock;
+    IluDot D{dot ? dot->partial + slot : nullptr};
+    slot += g * (kBlock / 32);
+    if (l == 0)
+      ilu0_bwd_w_kernel<W, true><<<g, kBlock, 0, s>>>(r0, r1, A.n_ext, A.nlow.p, A.col.p, so, lu, rin, d, done, D);
+    else
+      ilu0_bwd_w_kernel<W, false><<<g, kBlock, 0, s>>>(r0, r1, A.n_ext, A.nlow.p, A.col.p, so, lu, rin, d, done, D);
+    launches++;
+  }
+  if (dot) {
+    const int rb = std::max(1, std::min(148, slot / (4 * kBlock)));
+    ilu_dot_reduce_kernel<<<rb, kBlock, 0, s>>>(slot, dot->partial, dot->cta_sums, dot->ticket, dot->rho_out,
+                                                dot->beta_out, dot->rho0, done);
+    launches++;
+  }
+  return launches;
+}
+
+// ---- block sweeps (BLOCK_MULTICOLOR on fixed-width SELL) ---------------------------------------
+// One thread owns one block (a vertical cell column) and walks its cells in elimination order, so the
+// whole forward sweep of a colour is ONE launch whatever the number of layers; consecutive threads
+// touch consecutive rows of the same layer (coalesced).  Lower neighbours outside the block belong to
+// earlier colours (finished by earlier launches), upper ones to later colours.  Values of the thread's
+// own block are read back through global memory in program order (same-thread RAW).
+// MODE 0: forward sweep            d(n) = r(n) - sum_lower L d
+// MODE 1: backward sweep           d(n) = (d(n) - sum_upper U d) * piv          (+ rho partial)
+// MODE 2: forward then backward in one pass -- valid for the LAST colour, whose upper entries all lie
+//         inside the block
+template <int W, int MODE, int MAXK>
+__global__ void __launch_bounds__(kBlock)
+ilu0_block_kernel(int nb, int maxk, int ncols, const int *__restrict__ brow,
+                  const unsigned char *__restrict__ nlow, const int *__restrict__ col,
+                  const int *__restrict__ soff, const double *__restrict__ lu,
+                  const double *__restrict__ rin, double *d, const int *__restrict__ done, IluDot D) {
+  if (done && *done) return;
+  double dot = 0.0;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < nb) {
+    // Phase 1 -- everything that does not depend on the block's own recurrence, for all cells of the
+    // block at once (independent loads, issued back to back): row ids, the sums over the neighbours in
+    // OTHER blocks, the multipliers that couple consecutive cells of the block, the inverse pivots.
+    int rk[MAXK];
+    double sk[MAXK];   // forward:  r - sum_{lower, other blocks} L d     backward: fwd - sum_{upper, other blocks} U d
+    double lk[MAXK];   // L multiplier towards the previous cell of the block (0 if none)
+    double uk[MAXK];   // U entry towards the next cell of the block (0 if none)      [MODE 1, 2]
+    double pk[MAXK];   // inverse pivot                                              [MODE 1, 2]
+#pragma unroll
+    for (int k = 0; k < MAXK; k++) rk[k] = (k < maxk) ? __ldg(brow + (size_t)k * nb + q) : -1;
+#pragma unroll
+    for (int k = 0; k < MAXK; k++) {
+      sk[k] = 0.0;
+      lk[k] = 0.0;
+      uk[k] = 0.0;
+      pk[k] = 0.0;
+      const int r = rk[k];
+      if (r < 0) continue;
+      const int rprev = (k > 0) ? rk[k - 1] : -1;
+      const int rnext = (k + 1 < MAXK) ? rk[k + 1] : -1;
+      const int lo = nlow[r];
+      const long long base = (long long)(r >> 5) * (32 * W) + (r & 31);
+      const int *so = soff ? soff + (r >> 5) * W : nullptr;
+      double acc = (MODE == 1) ? d[r] : rin[r];
+      if (MODE != 0) pk[k] = __ldg(lu + base);
+#pragma unroll
+      for (int u = 1; u < W; u++) {
+        const bool lower = (u <= lo);
+        if ((MODE == 0 && !lower) || (MODE == 1 && lower)) continue;
+        const double v = __ldg(lu + base + 32 * u);
+        const int c = ilu_col<W>(r, u, base, col, so, ncols);
+        // a padding slot (v == 0) may carry a stencil column that happens to equal rprev / rnext: it
+        // must not overwrite the real multiplier
+        if (lower) {
+          if (c == rprev) {
+            if (v != 0.0) lk[k] = v;
+          } else
+            acc = acc - v * d[c];
+        } else {
+          if (c == rnext) {
+            if (v != 0.0) uk[k] = v;
+          } else if (MODE == 1)
+            acc = acc - v * d[c];
+          // MODE 2 (last colour): every upper entry lies inside the block, nothing else to subtract
+        }
+      }
+      sk[k] = acc;
+    }
+    // Phase 2 -- the recurrences along the block
+    if (MODE == 0 || MODE == 2) {
+      double prev = 0.0;
+#pragma unroll
+      for (int k = 0; k < MAXK; k++) {
+        if (rk[k] < 0) continue;
+        const double tv = sk[k] - lk[k] * prev;
+        sk[k] = tv;
+        prev = tv;
+        if (MODE == 0) d[rk[k]] = tv;
+      }
+    }
+    if (MODE == 1 || MODE == 2) {
+      double next = 0.0;
+#pragma unroll
+      for (int k = MAXK - 1; k >= 0; k--) {
+        if (rk[k] < 0) continue;
+        const double tv = (sk[k] - uk[k] * next) * pk[k];
+        next = tv;
+        d[rk[k]] = tv;
+        dot += rin[rk[k]] * tv;
+      }
+    }
+  }
+  if (MODE != 0 && D.partial) ilu_dot_finish(dot, D);
+}
+
+template <int W, int MODE>
+static void launch_block_kernel(int g, cudaStream_t s, int nb, int maxk, int ncols, const int *brow,
+                                const unsigned char *nlow, const int *col, const int *so, const double *lu,
+                                const double *rin, double *d, const int *done, IluDot D) {
+  if (maxk <= 4)
+    ilu0_block_kernel<W, MODE, 4><<<g, kBlock, 0, s>>>(nb, maxk, ncols, brow, nlow, col, so, lu, rin, d, done, D);
+  else if (maxk <= 8)
+    ilu0_block_kernel<W, MODE, 8><<<g, kBlock, 0, s>>>(nb, maxk, ncols, brow, nlow, col, so, lu, rin, d, done, D);
+  else if (maxk <= 12)
+    ilu0_block_kernel<W, MODE, 12><<<g, kBlock, 0, s>>>(nb, maxk, ncols, brow, nlow, col, so, lu, rin, d, done, D);
+  else if (maxk <= 16)
+    ilu0_block_kernel<W, MODE, 16><<<g, kBlock, 0, s>>>(nb, maxk, ncols, brow, nlow, col, so, lu, rin, d, done, D);
+  else
+    ilu0_block_kernel<W, MODE, 32><<<g, kBlock, 0, s>>>(nb, maxk, ncols, brow, nlow, col, so, lu, rin, d, done, D);
+}
+
+template <int W>
+static int launch_blocks_w(const mf6gpu_matrix &A, const double *lu, const double *rin, double *d,
+                           const int *done, cudaStream_t s, const IluDotArgs *dot) {
+  const int C = A.blk_ncolors;
+  const int *so = A.slot_off.n ? A.slot_off.p : nullptr;
+  int launches = 0, slot = 0;
+  auto grid = [&](int c) { return (A.blk_nb[c] + kBlock - 1) / kBlock; };
+  for (int c = 0; c < C - 1; c++) {
+    launch_block_kernel<W, 0>(grid(c), s, A.blk_nb[c], A.blk_maxk[c], A.n_ext, A.blk_rows.p + A.blk_off[c], A.nlow.p,
+                              A.col.p, so, lu, rin, d, done, IluDot{nullptr});
+    launches++;
+  }
+  for (int c = C - 1; c >= 0; c--) {
+    IluDot D{dot ? dot->partial + slot : nullptr};
+    slot += grid(c) * (kBlock / 32);
+    if (c == C - 1)
+      launch_block_kernel<W, 2>(grid(c), s, A.blk_nb[c], A.blk_maxk[c], A.n_ext, A.blk_rows.p + A.blk_off[c],
+                                A.nlow.p, A.col.p, so, lu, rin, d, done, D);
+    else
+      launch_block_kernel<W, 1>(grid(c), s, A.blk_nb[c], A.blk_maxk[c], A.n_ext, A.blk_rows.p + A.blk_off[c],
+                                A.nlow.p, A.col.p, so, lu, rin, d, done, D);
+    launches++;
+  }
+  if (dot) {
+    const int rb = std::max(1, std::min(148, slot / (4 * kBlock)));
+    ilu_dot_reduce_kernel<<<rb, kBlock, 0, s>>>(slot, dot->partial, dot->cta_sums, dot->ticket, dot->rho_out,
+                                                dot->beta_out, dot->rho0, done);
+    launches++;
+  }
+  return launches;
+}
+
 // ---- two-level (bipartite multicolour) fast path on fixed-width SELL ---------------------------
 // With exactly two levels every off-diagonal of a level-1 row is a lower entry and every
 // off-diagonal of a level-0 row an upper entry, so each sweep is a full-row product without
@@ -314,6 +589,30 @@ int ilu0_apply(const mf6gpu_matrix &A, const double *lu, const double *rin, doub
       case 8: return launch_two_level<8>(A, lu, rin, d, done, s, dot);
       case 9: return launch_two_level<9>(A, lu, rin, d, done, s, dot);
       case 10: return launch_two_level<10>(A, lu, rin, d, done, s, dot);
+      default: break;
+    }
+  }
+  if (A.blk_ncolors > 0 && A.blk_rows.n > 0 && A.blk_chain_ok && !std::getenv("MF6GPU_NO_BLOCK_SWEEP")) {
+    switch (A.uniform_w) {
+      case 4: return launch_blocks_w<4>(A, lu, rin, d, done, s, dot);
+      case 5: return launch_blocks_w<5>(A, lu, rin, d, done, s, dot);
+      case 6: return launch_blocks_w<6>(A, lu, rin, d, done, s, dot);
+      case 7: return launch_blocks_w<7>(A, lu, rin, d, done, s, dot);
+      case 8: return launch_blocks_w<8>(A, lu, rin, d, done, s, dot);
+      case 9: return launch_blocks_w<9>(A, lu, rin, d, done, s, dot);
+      case 10: return launch_blocks_w<10>(A, lu, rin, d, done, s, dot);
+      default: break;
+    }
+  }
+  if (L <= 64) {  // fixed-width level kernels (few, wide levels); thin natural-order levels keep the generic path
+    switch (A.uniform_w) {
+      case 4: return launch_levels_w<4>(A, lu, rin, d, done, s, dot);
+      case 5: return launch_levels_w<5>(A, lu, rin, d, done, s, dot);
+      case 6: return launch_levels_w<6>(A, lu, rin, d, done, s, dot);
+      case 7: return launch_levels_w<7>(A, lu, rin, d, done, s, dot);
+      case 8: return launch_levels_w<8>(A, lu, rin, d, done, s, dot);
+      case 9: return launch_levels_w<9>(A, lu, rin, d, done, s, dot);
+      case 10: return launch_levels_w<10>(A, lu, rin, d, done, s, dot);
       default: break;
     }
   }

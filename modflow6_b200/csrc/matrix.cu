@@ -87,10 +87,13 @@ void launch_scatter(int n, const int *perm, const double *in, double *out, cudaS
 // n = owned rows, n_ext >= n = owned + halo columns; gid (optional, [n_ext]) = global ids used
 // for arg-max tie-breaks in the split-model path
 static void build_matrix(mf6gpu_matrix &M, int n, int n_ext, int nja, const int32_t *ia_in,
-                         const int32_t *ja_in, int base, int ordering, const int32_t *gid) {
+                         const int32_t *ja_in, int base, int ordering, const int32_t *gid,
+                         const int32_t *block_id = nullptr) {
   MF6_REQUIRE(n > 0 && nja >= n && n_ext >= n, "matrix_create: bad dimensions");
-  MF6_REQUIRE(ordering == MF6GPU_ORDER_NATURAL || ordering == MF6GPU_ORDER_MULTICOLOR,
+  MF6_REQUIRE(ordering == MF6GPU_ORDER_NATURAL || ordering == MF6GPU_ORDER_MULTICOLOR ||
+                  ordering == MF6GPU_ORDER_BLOCK_MULTICOLOR,
               "matrix_create: unknown gpu_ordering");
+  if (ordering == MF6GPU_ORDER_BLOCK_MULTICOLOR && !block_id) ordering = MF6GPU_ORDER_MULTICOLOR;
   M.n = n;
   M.n_ext = n_ext;
   M.nja = nja;
@@ -108,8 +111,64 @@ static void build_matrix(mf6gpu_matrix &M, int n, int n_ext, int nja, const int3
   auto is_halo = [&](int c) { return c >= n; };
   // --- elimination order (ordidx[old] = position in the reference-style loop)
   std::vector<int> ordidx(n);
+  std::vector<int> blk_of, blk_color;  // BLOCK_MULTICOLOR: compact block of every row, colour of every block
+  int blk_count = 0, blk_colors = 0;
   if (ordering == MF6GPU_ORDER_NATURAL) {
     std::iota(ordidx.begin(), ordidx.end(), 0);
+  } else if (ordering == MF6GPU_ORDER_BLOCK_MULTICOLOR) {
+    // Greedy colouring of the QUOTIENT graph of the blocks (e.g. the vertical cell columns of a layered
+    // grid): blocks of one colour are mutually independent, inside a block the reference's natural order is
+    // kept, so the strong intra-block couplings are eliminated exactly like in the reference.
+    // Elimination order = (colour of the block, original index).
+    std::vector<int> bmap(n);  // compact block numbers in order of first appearance
+    int nblk = 0;
+    {
+      std::vector<int> seen;
+      int maxb = 0;
+      for (int v = 0; v < n; v++) maxb = std::max(maxb, (int)block_id[v]);
+      seen.assign((size_t)maxb + 1, -1);
+      for (int v = 0; v < n; v++) {
+        MF6_REQUIRE(block_id[v] >= 0, "matrix_create: negative block id");
+        int &sb = seen[block_id[v]];
+        if (sb < 0) sb = nblk++;
+        bmap[v] = sb;
+      }
+    }
+    std::vector<int> bptr(nblk + 1, 0), bmem(n);
+    for (int v = 0; v < n; v++) bptr[bmap[v] + 1]++;
+    for (int b = 0; b < nblk; b++) bptr[b + 1] += bptr[b];
+    {
+      std::vector<int> cur(bptr.begin(), bptr.end() - 1);
+      for (int v = 0; v < n; v++) bmem[cur[bmap[v]]++] = v;
+    }
+    std::vector<int> bcolor(nblk, -1);
+    int ncolors = 0;
+    for (int b = 0; b < nblk; b++) {
+      unsigned long long mask = 0ull;
+      for (int q = bptr[b]; q < bptr[b + 1]; q++) {
+        const int v = bmem[q];
+        for (int p = ia[v] + 1; p < ia[v + 1]; p++) {
+          if (is_halo(ja[p])) continue;
+          const int nbk = bmap[ja[p]];
+          if (nbk == b) continue;
+          const int c = bcolor[nbk];
+          MF6_REQUIRE(c < 64, "matrix_create: more than 64 block colours");
+          if (c >= 0) mask |= (1ull << c);
+        }
+      }
+      int c = 0;
+      while ((mask >> c) & 1ull) c++;
+      bcolor[b] = c;
+      if (c + 1 > ncolors) ncolors = c + 1;
+    }
+    std::vector<int> cnt(ncolors + 1, 0);
+    for (int v = 0; v < n; v++) cnt[bcolor[bmap[v]] + 1]++;
+    for (int c = 0; c < ncolors; c++) cnt[c + 1] += cnt[c];
+    for (int v = 0; v < n; v++) ordidx[v] = cnt[bcolor[bmap[v]]]++;
+    blk_of = bmap;
+    blk_color = bcolor;
+    blk_count = nblk;
+    blk_colors = ncolors;
   } else {
     // greedy colouring in natural order
     std::vector<int> color(n, -1);
@@ -145,6 +204,7 @@ static void build_matrix(mf6gpu_matrix &M, int n, int n_ext, int nja, const int3
   }
   std::vector<int> byord(n);  // byord[ord] = old
   for (int v = 0; v < n; v++) byord[ordidx[v]] = v;
+  M.elim = byord;
   // --- dependency levels of the lower-triangular solve in that order
   std::vector<int> level(n, 0);
   int nlevels = 0;
@@ -252,6 +312,42 @@ static void build_matrix(mf6gpu_matrix &M, int n, int n_ext, int nja, const int3
     int w = (slice_ptr[(r >> 5) + 1] - slice_ptr[r >> 5]) / 32;
     for (int k = 0; k < w; k++) col[base_slot + 32LL * k] = 0;
   }
+  // --- block tables for the block-sweep triangular solves
+  if (ordering == MF6GPU_ORDER_BLOCK_MULTICOLOR && blk_count > 0) {
+    M.blk_ncolors = blk_colors;
+    std::vector<int> bsize(blk_count, 0), bq(blk_count, 0);
+    for (int v = 0; v < n; v++) bsize[blk_of[v]]++;
+    M.blk_nb.assign(blk_colors, 0);
+    M.blk_maxk.assign(blk_colors, 0);
+    for (int b = 0; b < blk_count; b++) {  // blocks are numbered in order of first appearance
+      const int c = blk_color[b];
+      bq[b] = M.blk_nb[c]++;
+      M.blk_maxk[c] = std::max(M.blk_maxk[c], bsize[b]);
+    }
+    M.blk_off.assign(blk_colors + 1, 0);
+    for (int c = 0; c < blk_colors; c++) M.blk_off[c + 1] = M.blk_off[c] + M.blk_nb[c] * M.blk_maxk[c];
+    std::vector<int> rows((size_t)M.blk_off[blk_colors], -1), fill(blk_count, 0);
+    for (int o = 0; o < n; o++) {  // elimination order: cells of a block appear top to bottom
+      const int v = byord[o], b = blk_of[v], c = blk_color[b];
+      rows[(size_t)M.blk_off[c] + (size_t)fill[b]++ * M.blk_nb[c] + bq[b]] = M.iperm[v];
+    }
+    M.blk_rows.upload(rows);
+    // the block-sweep kernels assume chains: the only intra-block neighbours of the k-th cell are cells k-1, k+1
+    bool chain = true;
+    {
+      std::vector<int> kpos(n, 0), fill2(blk_count, 0);
+      for (int o = 0; o < n; o++) kpos[byord[o]] = fill2[blk_of[byord[o]]]++;
+      for (int v = 0; v < n && chain; v++)
+        for (int p = ia[v] + 1; p < ia[v + 1]; p++) {
+          const int u = ja[p];
+          if (is_halo(u) || blk_of[u] != blk_of[v]) continue;
+          if (std::abs(kpos[u] - kpos[v]) != 1) chain = false;
+        }
+      for (int c = 0; c < blk_colors; c++)
+        if (M.blk_maxk[c] > 32) chain = false;
+    }
+    M.blk_chain_ok = chain;
+  }
   // --- stencil compression table (fixed-width layout)
   if (M.uniform_w > 0 && !std::getenv("MF6GPU_NO_STENCIL")) {
     const int W = M.uniform_w;
@@ -285,6 +381,10 @@ static void build_matrix(mf6gpu_matrix &M, int n, int n_ext, int nja, const int3
   if (gid) {
     std::vector<int> o(n);
     for (int r = 0; r < n; r++) o[r] = gid[M.perm[r]] - base;  // global cell id of final row r
+    M.d_ord.upload(o);
+  } else if (ordering == MF6GPU_ORDER_BLOCK_MULTICOLOR) {
+    std::vector<int> o(n);
+    for (int r = 0; r < n; r++) o[r] = ordidx[M.perm[r]];  // position in the elimination order
     M.d_ord.upload(o);
   } else if (ordering == MF6GPU_ORDER_NATURAL && nlevels > 1) {
     std::vector<int> o(M.perm.begin(), M.perm.begin() + n);
@@ -332,7 +432,23 @@ int mf6gpu_matrix_create_ext(int32_t n_own, int32_t n_ext, int32_t nja, const in
     MF6_REQUIRE(out && ia && ja, "matrix_create_ext: null argument");
     auto *M = new mf6gpu_matrix();
     try {
-      build_matrix(*M, n_own, n_ext, nja, ia, ja, index_base, gpu_ordering, global_id);
+      build_matrix(*M, n_own, n_ext, nja, ia, ja, index_base, gpu_ordering, global_id, nullptr);
+    } catch (...) {
+      delete M;
+      throw;
+    }
+    *out = M;
+  });
+}
+
+int mf6gpu_matrix_create_blocked(int32_t n_own, int32_t n_ext, int32_t nja, const int32_t *ia,
+                                 const int32_t *ja, int32_t index_base, int32_t gpu_ordering,
+                                 const int32_t *global_id, const int32_t *block_id, mf6gpu_matrix **out) {
+  return guard([&] {
+    MF6_REQUIRE(out && ia && ja, "matrix_create_blocked: null argument");
+    auto *M = new mf6gpu_matrix();
+    try {
+      build_matrix(*M, n_own, n_ext, nja, ia, ja, index_base, gpu_ordering, global_id, block_id);
     } catch (...) {
       delete M;
       throw;
@@ -408,7 +524,7 @@ int64_t mf6gpu_matrix_info(const mf6gpu_matrix *m, int what) {
 int mf6gpu_matrix_get_permutation(const mf6gpu_matrix *m, int32_t *perm) {
   return guard([&] {
     MF6_REQUIRE(m && perm, "matrix_get_permutation: null argument");
-    std::memcpy(perm, m->perm.data(), sizeof(int) * (size_t)m->n);  // owned rows
+    std::memcpy(perm, m->elim.data(), sizeof(int) * (size_t)m->n);
   });
 }
 

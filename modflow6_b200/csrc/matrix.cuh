@@ -23,6 +23,7 @@ struct mf6gpu_matrix {
   long long nslots = 0;
   int maxlen = 0;
   int uniform_w = 0;           // width shared by every slice (0 = ragged): enables the fixed-width kernels
+  std::vector<int> elim;       // elimination order of the ILU: elim[k] = original row eliminated k-th
   std::vector<int> perm;       // perm[new] = old
   std::vector<int> iperm;      // iperm[old] = new
   std::vector<int> level_ptr;  // [nlevels+1] row ranges in final numbering
@@ -39,6 +40,13 @@ struct mf6gpu_matrix {
   // the Krylov kernels then skip the 4-byte column loads of that slot for the whole warp
   mf6::DevBuf<int> slot_off;
   double slot_off_hit = 0.0;   // fraction of (slice, slot) pairs that are compressed
+  // BLOCK_MULTICOLOR: the blocks (cell columns) of every colour, for the block-sweep triangular solves:
+  // blk_rows[blk_off[c] + k * blk_nb[c] + q] = final row of the k-th cell (elimination order) of the q-th
+  // block of colour c, or -1 past the end of a short block
+  int blk_ncolors = 0;
+  bool blk_chain_ok = false;   // every block is a chain (cell k couples only to cells k-1 / k+1 of its block, <= 32 cells)
+  std::vector<int> blk_off, blk_nb, blk_maxk;
+  mf6::DevBuf<int> blk_rows;
   mf6::DevBuf<int> csr2sell;   // [nja] slot of each original CSR entry
   mf6::DevBuf<double> stage;   // [nja] H2D/D2H staging of CSR values
   mf6::DevBuf<double> xs, ys;  // [n] staging vectors for host multiply

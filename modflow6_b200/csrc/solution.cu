@@ -1207,8 +1207,25 @@ static void create_solution(const mf6gpu_gwf_model *m, const mf6gpu_sln_settings
     s->njas = m->njas;
     s->ss = *sln;
     s->isymmetric = (ims->ilinmeth == 1) ? 1 : 0;  // NumericalSolution.f90:914-916
-    if (mf6gpu_matrix_create_ext(n_own, m->nodes, nja_own, m->ia, m->ja, m->index_base, ims->gpu_ordering,
-                                 da ? da->global_id : nullptr, &s->A) != 0) {
+    // blocks of the BLOCK_MULTICOLOR ordering: the vertical cell columns (chains of ihc == 0 connections)
+    std::vector<int32_t> block;
+    if (ims->gpu_ordering == MF6GPU_ORDER_BLOCK_MULTICOLOR) {
+      const int base0 = m->index_base;
+      block.resize((size_t)n_own);
+      for (int v = 0; v < n_own; v++) {
+        block[v] = v;
+        for (int p = m->ia[v] - base0 + 1; p < m->ia[v + 1] - base0; p++) {
+          const int u = m->ja[p] - base0;
+          if (u < v && m->ihc[m->jas[p] - base0] == 0) {
+            block[v] = block[u];
+            break;
+          }
+        }
+      }
+    }
+    if (mf6gpu_matrix_create_blocked(n_own, m->nodes, nja_own, m->ia, m->ja, m->index_base, ims->gpu_ordering,
+                                     da ? da->global_id : nullptr, block.empty() ? nullptr : block.data(),
+                                     &s->A) != 0) {
       const std::string keep = last_error();
       delete s;
       throw Error(keep);
@@ -1654,6 +1671,13 @@ int mf6gpu_solution_get_condsat(mf6gpu_solution *s, double *condsat) {
   return guard([&] {
     MF6_REQUIRE(s && condsat, "solution_get_condsat: null argument");
     s->condsat.download(condsat, (size_t)s->njas, s->stream);
+  });
+}
+
+int mf6gpu_solution_get_permutation(mf6gpu_solution *s, int32_t *perm) {
+  return guard([&] {
+    MF6_REQUIRE(s && perm, "solution_get_permutation: null argument");
+    std::memcpy(perm, s->A->elim.data(), sizeof(int) * (size_t)s->n);
   });
 }
 

@@ -17,7 +17,7 @@ MAX_BUDGET_TERMS = 16
 PKG_CHD, PKG_WEL, PKG_RIV, PKG_RCH, PKG_GHB, PKG_DRN = 1, 2, 3, 4, 5, 6
 PKG_NAMES = {1: "CHD", 2: "WEL", 3: "RIV", 4: "RCH", 5: "GHB", 6: "DRN", 100: "STO-SS", 101: "STO-SY"}
 
-ORDER_NATURAL, ORDER_MULTICOLOR = 0, 1
+ORDER_NATURAL, ORDER_MULTICOLOR, ORDER_BLOCK_MULTICOLOR = 0, 1, 2
 
 
 class ImsSettings(C.Structure):

@@ -28,6 +28,7 @@ SYMBOLS = [
     "mf6gpu_solution_stat", "mf6gpu_matrix_create_ext", "mf6gpu_solution_create_dist",
     "mf6gpu_comm_unique_id", "mf6gpu_comm_create", "mf6gpu_comm_destroy", "mf6gpu_comm_rank", "mf6gpu_comm_size",
     "mf6gpu_comm_p2p_export", "mf6gpu_comm_p2p_import", "mf6gpu_comm_p2p_enabled", "mf6gpu_comm_p2p_disable",
+    "mf6gpu_matrix_create_blocked", "mf6gpu_solution_get_permutation",
 ]
 
 _lib = None
@@ -85,6 +86,8 @@ def load():
     L.mf6gpu_solution_create.argtypes = [C.POINTER(T.GwfModelStruct), C.POINTER(T.SlnSettings),
                                          C.POINTER(T.ImsSettings), vpp]
     L.mf6gpu_matrix_create_ext.argtypes = [i32, i32, i32, pi32, pi32, i32, i32, pi32, vpp]
+    L.mf6gpu_matrix_create_blocked.argtypes = [i32, i32, i32, pi32, pi32, i32, i32, pi32, pi32, vpp]
+    L.mf6gpu_solution_get_permutation.argtypes = [vp, pi32]
     L.mf6gpu_comm_unique_id.argtypes = [C.c_void_p]
     L.mf6gpu_comm_create.argtypes = [i32, i32, C.c_void_p, vpp]
     L.mf6gpu_comm_destroy.argtypes = [vp]

@@ -74,6 +74,12 @@ class GpuNumericalSolution:
     def condsat(self):
         return self._get("condsat", self.model.njas)
 
+    def elimination_order(self):
+        """perm[k] = cell eliminated k-th by the ILU (the permutation to hand to the oracle)"""
+        p = np.empty(self.n, np.int32)
+        check(self._L.mf6gpu_solution_get_permutation(self.h, T.ptr_i32(p)))
+        return p
+
     def reset_x(self):
         """heads back to the IC strt array, device side (no host traffic)"""
         check(self._L.mf6gpu_solution_reset_x(self.h))
