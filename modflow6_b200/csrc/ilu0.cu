@@ -7,6 +7,7 @@
 // The factor shares the matrix's SELL-32 structure (matrix.cuh): slot 0 holds
 // the inverse pivot APC(n), lower slots the L multipliers, upper slots U.
 #include "ilu0.cuh"
+#include <type_traits>
 #include <algorithm>
 
 namespace mf6 {
@@ -340,114 +341,158 @@ static int launch_levels_w(const mf6gpu_matrix &A, const double *lu, const doubl
 }
 
 // ---- block sweeps (BLOCK_MULTICOLOR on fixed-width SELL) ---------------------------------------
-// One thread owns one block (a vertical cell column) and walks its cells in elimination order, so the
-// whole forward sweep of a colour is ONE launch whatever the number of layers; consecutive threads
-// touch consecutive rows of the same layer (coalesced).  Lower neighbours outside the block belong to
-// earlier colours (finished by earlier launches), upper ones to later colours.  Values of the thread's
-// own block are read back through global memory in program order (same-thread RAW).
-// MODE 0: forward sweep            d(n) = r(n) - sum_lower L d
-// MODE 1: backward sweep           d(n) = (d(n) - sum_upper U d) * piv          (+ rho partial)
-// MODE 2: forward then backward in one pass -- valid for the LAST colour, whose upper entries all lie
-//         inside the block
-template <int W, int MODE, int MAXK>
+// A block is a vertical cell column whose cells form a chain in elimination order; blocks of one
+// colour are not connected.  The sweep of a colour therefore splits into
+//   gather: for every row of the colour at once (one thread per row, like a level kernel) the products
+//           with the neighbours in OTHER blocks -- earlier colours in the forward sweep, later ones
+//           in the backward sweep -- accumulated into d;
+//   chain:  one thread per block runs the first-order recurrence along its chain, all operands
+//           (d, chain multiplier, pivot, r) loaded up front, consecutive threads touching
+//           consecutive rows of one layer (coalesced);
+// i.e. at most two launches per colour and sweep whatever the number of layers.  The first colour
+// needs no forward gather, the last colour no backward gather and its two chain passes fuse.
+// The chain term is applied after the others, so the summation order differs from the level kernels
+// (rounding only) when the chain neighbour is not the last slot of its half.
+template <int W, bool LOWER>
+__global__ void __launch_bounds__(kBlock, 8)
+ilu0_blk_gather_kernel(int ncell, int ncols, const int *__restrict__ brow,
+                       const unsigned char *__restrict__ bnlow, const unsigned char *__restrict__ bchain,
+                       const int *__restrict__ col, const int *__restrict__ soff,
+                       const double *__restrict__ lu, const double *__restrict__ rin, double *d,
+                       const int *__restrict__ done) {
+  if (done && *done) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ncell) return;
+  const int r = __ldg(brow + t);
+  if (r < 0) return;
+  const int lo = __ldg(bnlow + t);
+  const int ch = __ldg(bchain + t);
+  const int skip = LOWER ? (ch & 15) : (ch >> 4);
+  const long long base = (long long)(r >> 5) * (32 * W) + (r & 31);
+  const int *so = soff ? soff + (r >> 5) * W : nullptr;
+  double acc = LOWER ? rin[r] : d[r];
+  double v[W], dv[W];
+  int o[W];
+#pragma unroll
+  for (int u = 1; u < W; u++) {
+    const bool want = (LOWER == (u <= lo)) && u != skip;
+    v[u] = want ? __ldg(lu + base + 32 * u) : 0.0;
+    o[u] = (soff && want) ? __ldg(so + u) : INT_MIN;
+  }
+#pragma unroll
+  for (int u = 1; u < W; u++) {
+    const bool want = (LOWER == (u <= lo)) && u != skip;
+    int c = min(max(r + o[u], 0), ncols - 1);
+    if (want && o[u] == INT_MIN) c = __ldg(col + base + 32 * u);
+    o[u] = c;
+  }
+#pragma unroll
+  for (int u = 1; u < W; u++) {
+    const bool want = (LOWER == (u <= lo)) && u != skip;
+    dv[u] = want ? d[o[u]] : 0.0;
+  }
+#pragma unroll
+  for (int u = 1; u < W; u++) {
+    const bool want = (LOWER == (u <= lo)) && u != skip;
+    acc = want ? acc - v[u] * dv[u] : acc;
+  }
+  d[r] = acc;
+}
+
+// MODE 0: forward   d(k) = src(k) - L(k,k-1) d(k-1)            src = rin (first colour) or d (gathered)
+// MODE 1: backward  d(k) = (d(k) - U(k,k+1) d(k+1)) * piv(k)   + rho partial
+// MODE 2: both in one pass (last colour, block of at most KC cells)
+template <int MODE, int KC>
 __global__ void __launch_bounds__(kBlock)
-ilu0_block_kernel(int nb, int maxk, int ncols, const int *__restrict__ brow,
-                  const unsigned char *__restrict__ nlow, const int *__restrict__ col,
-                  const int *__restrict__ soff, const double *__restrict__ lu,
-                  const double *__restrict__ rin, double *d, const int *__restrict__ done, IluDot D) {
+ilu0_blk_chain_kernel(int nb, int maxk, int W, bool from_rin, const int *__restrict__ brow,
+                      const unsigned char *__restrict__ bchain, const double *__restrict__ lu,
+                      const double *__restrict__ rin, double *d, const int *__restrict__ done, IluDot D) {
   if (done && *done) return;
   double dot = 0.0;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q < nb) {
-    // Phase 1 -- everything that does not depend on the block's own recurrence, for all cells of the
-    // block at once (independent loads, issued back to back): row ids, the sums over the neighbours in
-    // OTHER blocks, the multipliers that couple consecutive cells of the block, the inverse pivots.
-    int rk[MAXK];
-    double sk[MAXK];   // forward:  r - sum_{lower, other blocks} L d     backward: fwd - sum_{upper, other blocks} U d
-    double lk[MAXK];   // L multiplier towards the previous cell of the block (0 if none)
-    double uk[MAXK];   // U entry towards the next cell of the block (0 if none)      [MODE 1, 2]
-    double pk[MAXK];   // inverse pivot                                              [MODE 1, 2]
+    const int nchunks = (maxk + KC - 1) / KC;
+    double carry = 0.0;  // value of the chain neighbour in the chunk handled before
+    for (int it = 0; it < nchunks; it++) {
+      const int k0 = ((MODE == 1) ? nchunks - 1 - it : it) * KC;
+      int rk[KC], ck[KC];
+      double acc[KC], ml[KC], mu[KC], pk[KC], rr[KC];
 #pragma unroll
-    for (int k = 0; k < MAXK; k++) rk[k] = (k < maxk) ? __ldg(brow + (size_t)k * nb + q) : -1;
+      for (int k = 0; k < KC; k++) {
+        const bool in = (k0 + k < maxk);
+        rk[k] = in ? __ldg(brow + (size_t)(k0 + k) * nb + q) : -1;
+        ck[k] = in ? __ldg(bchain + (size_t)(k0 + k) * nb + q) : 0;
+      }
 #pragma unroll
-    for (int k = 0; k < MAXK; k++) {
-      sk[k] = 0.0;
-      lk[k] = 0.0;
-      uk[k] = 0.0;
-      pk[k] = 0.0;
-      const int r = rk[k];
-      if (r < 0) continue;
-      const int rprev = (k > 0) ? rk[k - 1] : -1;
-      const int rnext = (k + 1 < MAXK) ? rk[k + 1] : -1;
-      const int lo = nlow[r];
-      const long long base = (long long)(r >> 5) * (32 * W) + (r & 31);
-      const int *so = soff ? soff + (r >> 5) * W : nullptr;
-      double acc = (MODE == 1) ? d[r] : rin[r];
-      if (MODE != 0) pk[k] = __ldg(lu + base);
-#pragma unroll
-      for (int u = 1; u < W; u++) {
-        const bool lower = (u <= lo);
-        if ((MODE == 0 && !lower) || (MODE == 1 && lower)) continue;
-        const double v = __ldg(lu + base + 32 * u);
-        const int c = ilu_col<W>(r, u, base, col, so, ncols);
-        // a padding slot (v == 0) may carry a stencil column that happens to equal rprev / rnext: it
-        // must not overwrite the real multiplier
-        if (lower) {
-          if (c == rprev) {
-            if (v != 0.0) lk[k] = v;
-          } else
-            acc = acc - v * d[c];
+      for (int k = 0; k < KC; k++) {
+        const int r = max(rk[k], 0);
+        const bool valid = rk[k] >= 0;
+        const long long base = (long long)(r >> 5) * (32 * W) + (r & 31);
+        const int slo = ck[k] & 15, sup = ck[k] >> 4;
+        if (MODE != 1) {
+          acc[k] = !valid ? 0.0 : (from_rin ? rin[r] : d[r]);
+          ml[k] = (valid && slo) ? __ldg(lu + base + 32 * slo) : 0.0;
         } else {
-          if (c == rnext) {
-            if (v != 0.0) uk[k] = v;
-          } else if (MODE == 1)
-            acc = acc - v * d[c];
-          // MODE 2 (last colour): every upper entry lies inside the block, nothing else to subtract
+          acc[k] = valid ? d[r] : 0.0;
+        }
+        if (MODE != 0) {
+          mu[k] = (valid && sup) ? __ldg(lu + base + 32 * sup) : 0.0;
+          pk[k] = valid ? __ldg(lu + base) : 0.0;
+          rr[k] = (valid && !(MODE == 2 && from_rin)) ? rin[r] : acc[k];
         }
       }
-      sk[k] = acc;
-    }
-    // Phase 2 -- the recurrences along the block
-    if (MODE == 0 || MODE == 2) {
-      double prev = 0.0;
+      if (MODE != 1) {
 #pragma unroll
-      for (int k = 0; k < MAXK; k++) {
-        if (rk[k] < 0) continue;
-        const double tv = sk[k] - lk[k] * prev;
-        sk[k] = tv;
-        prev = tv;
-        if (MODE == 0) d[rk[k]] = tv;
+        for (int k = 0; k < KC; k++)
+          if (rk[k] >= 0) {
+            carry = acc[k] - ml[k] * carry;
+            acc[k] = carry;
+            if (MODE == 0) d[rk[k]] = carry;
+          }
       }
-    }
-    if (MODE == 1 || MODE == 2) {
-      double next = 0.0;
+      if (MODE != 0) {
+        if (MODE == 2) carry = 0.0;
 #pragma unroll
-      for (int k = MAXK - 1; k >= 0; k--) {
-        if (rk[k] < 0) continue;
-        const double tv = (sk[k] - uk[k] * next) * pk[k];
-        next = tv;
-        d[rk[k]] = tv;
-        dot += rin[rk[k]] * tv;
+        for (int k = KC - 1; k >= 0; k--)
+          if (rk[k] >= 0) {
+            carry = (acc[k] - mu[k] * carry) * pk[k];
+            d[rk[k]] = carry;
+            dot += rr[k] * carry;
+          }
       }
     }
   }
   if (MODE != 0 && D.partial) ilu_dot_finish(dot, D);
 }
 
-template <int W, int MODE>
-static void launch_block_kernel(int g, cudaStream_t s, int nb, int maxk, int ncols, const int *brow,
-                                const unsigned char *nlow, const int *col, const int *so, const double *lu,
-                                const double *rin, double *d, const int *done, IluDot D) {
-  if (maxk <= 4)
-    ilu0_block_kernel<W, MODE, 4><<<g, kBlock, 0, s>>>(nb, maxk, ncols, brow, nlow, col, so, lu, rin, d, done, D);
-  else if (maxk <= 8)
-    ilu0_block_kernel<W, MODE, 8><<<g, kBlock, 0, s>>>(nb, maxk, ncols, brow, nlow, col, so, lu, rin, d, done, D);
-  else if (maxk <= 12)
-    ilu0_block_kernel<W, MODE, 12><<<g, kBlock, 0, s>>>(nb, maxk, ncols, brow, nlow, col, so, lu, rin, d, done, D);
-  else if (maxk <= 16)
-    ilu0_block_kernel<W, MODE, 16><<<g, kBlock, 0, s>>>(nb, maxk, ncols, brow, nlow, col, so, lu, rin, d, done, D);
-  else
-    ilu0_block_kernel<W, MODE, 32><<<g, kBlock, 0, s>>>(nb, maxk, ncols, brow, nlow, col, so, lu, rin, d, done, D);
+// rho partials the block sweeps write (one per warp of every finalising launch)
+size_t ilu0_block_dot_slots(const mf6gpu_matrix &A) {
+  size_t n = 0;
+  for (int c = 0; c < A.blk_ncolors; c++) n += (size_t)((A.blk_nb[c] + kBlock - 1) / kBlock) * (kBlock / 32);
+  return n;
+}
+
+static inline int chain_chunk(int maxk) {
+  return maxk <= 4 ? 4 : maxk <= 6 ? 6 : maxk <= 8 ? 8 : maxk <= 10 ? 10 : maxk <= 12 ? 12 : maxk <= 16 ? 16 : 8;
+}
+
+template <int MODE>
+static void launch_chain(const mf6gpu_matrix &A, int c, bool from_rin, const double *lu, const double *rin,
+                         double *d, const int *done, cudaStream_t s, IluDot D) {
+  const int nb = A.blk_nb[c], maxk = A.blk_maxk[c], g = (nb + kBlock - 1) / kBlock, W = A.uniform_w;
+  const int *brow = A.blk_rows.p + A.blk_off[c];
+  const unsigned char *bch = A.blk_chain.p + A.blk_off[c];
+  switch (chain_chunk(maxk)) {
+#define MF6_CHAIN_CASE(KC) \
+  case KC: ilu0_blk_chain_kernel<MODE, KC><<<g, kBlock, 0, s>>>(nb, maxk, W, from_rin, brow, bch, lu, rin, d, done, D); break;
+    MF6_CHAIN_CASE(4)
+    MF6_CHAIN_CASE(6)
+    MF6_CHAIN_CASE(8)
+    MF6_CHAIN_CASE(10)
+    MF6_CHAIN_CASE(12)
+    MF6_CHAIN_CASE(16)
+#undef MF6_CHAIN_CASE
+  }
 }
 
 template <int W>
@@ -456,21 +501,33 @@ static int launch_blocks_w(const mf6gpu_matrix &A, const double *lu, const doubl
   const int C = A.blk_ncolors;
   const int *so = A.slot_off.n ? A.slot_off.p : nullptr;
   int launches = 0, slot = 0;
-  auto grid = [&](int c) { return (A.blk_nb[c] + kBlock - 1) / kBlock; };
-  for (int c = 0; c < C - 1; c++) {
-    launch_block_kernel<W, 0>(grid(c), s, A.blk_nb[c], A.blk_maxk[c], A.n_ext, A.blk_rows.p + A.blk_off[c], A.nlow.p,
-                              A.col.p, so, lu, rin, d, done, IluDot{nullptr});
+  auto gather = [&](auto lower, int c) {
+    const int ncell = A.blk_nb[c] * A.blk_maxk[c];
+    ilu0_blk_gather_kernel<W, decltype(lower)::value><<<(ncell + kBlock - 1) / kBlock, kBlock, 0, s>>>(
+        ncell, A.n_ext, A.blk_rows.p + A.blk_off[c], A.blk_nlow.p + A.blk_off[c], A.blk_chain.p + A.blk_off[c],
+        A.col.p, so, lu, rin, d, done);
+    launches++;
+  };
+  // the last colour's two chain passes fuse when nothing of its U half lies outside the chains and
+  // a block fits one chunk
+  const bool fuse_last = !A.blk_has_upper[C - 1] && A.blk_maxk[C - 1] <= chain_chunk(A.blk_maxk[C - 1]);
+  for (int c = 0; c < C; c++) {
+    if (A.blk_nb[c] == 0) continue;
+    if (A.blk_has_lower[c]) gather(std::true_type{}, c);
+    if (c == C - 1 && fuse_last) break;
+    launch_chain<0>(A, c, !A.blk_has_lower[c], lu, rin, d, done, s, IluDot{nullptr});
     launches++;
   }
   for (int c = C - 1; c >= 0; c--) {
+    if (A.blk_nb[c] == 0) continue;
     IluDot D{dot ? dot->partial + slot : nullptr};
-    slot += grid(c) * (kBlock / 32);
-    if (c == C - 1)
-      launch_block_kernel<W, 2>(grid(c), s, A.blk_nb[c], A.blk_maxk[c], A.n_ext, A.blk_rows.p + A.blk_off[c],
-                                A.nlow.p, A.col.p, so, lu, rin, d, done, D);
-    else
-      launch_block_kernel<W, 1>(grid(c), s, A.blk_nb[c], A.blk_maxk[c], A.n_ext, A.blk_rows.p + A.blk_off[c],
-                                A.nlow.p, A.col.p, so, lu, rin, d, done, D);
+    slot += ((A.blk_nb[c] + kBlock - 1) / kBlock) * (kBlock / 32);
+    if (c == C - 1 && fuse_last) {
+      launch_chain<2>(A, c, !A.blk_has_lower[c], lu, rin, d, done, s, D);
+    } else {
+      if (A.blk_has_upper[c]) gather(std::false_type{}, c);
+      launch_chain<1>(A, c, false, lu, rin, d, done, s, D);
+    }
     launches++;
   }
   if (dot) {

@@ -20,4 +20,6 @@ struct IluDotArgs {
 // rin and d must be different arrays.
 int ilu0_apply(const mf6gpu_matrix &A, const double *lu, const double *rin, double *d,
                const int *done, cudaStream_t s, const IluDotArgs *dot = nullptr);
+// number of rho-partial slots the BLOCK_MULTICOLOR sweeps need (0 without block tables)
+size_t ilu0_block_dot_slots(const mf6gpu_matrix &A);
 }  // namespace mf6

@@ -332,6 +332,39 @@ static void build_matrix(mf6gpu_matrix &M, int n, int n_ext, int nja, const int3
       rows[(size_t)M.blk_off[c] + (size_t)fill[b]++ * M.blk_nb[c] + bq[b]] = M.iperm[v];
     }
     M.blk_rows.upload(rows);
+    bool nibble_ok = false;
+    {
+      // per cell: nlow, and the SELL slots of the entries towards the previous / next cell of the chain
+      // (low / high nibble, 0 = none); per colour: is there any factor entry outside the chains?
+      std::vector<unsigned char> bl(rows.size(), 0), bc(rows.size(), 0);
+      nibble_ok = true;
+      M.blk_has_lower.assign(blk_colors, 0);
+      M.blk_has_upper.assign(blk_colors, 0);
+      for (int c = 0; c < blk_colors; c++) {
+        const size_t nbc = (size_t)M.blk_nb[c];
+        for (size_t i = (size_t)M.blk_off[c]; i < (size_t)M.blk_off[c + 1]; i++) {
+          const int r = rows[i];
+          if (r < 0) continue;
+          bl[i] = nlow[r];
+          const size_t k = (i - (size_t)M.blk_off[c]) / nbc;
+          const int rprev = (k > 0) ? rows[i - nbc] : -1;
+          const int rnext = ((int)k + 1 < M.blk_maxk[c]) ? rows[i + nbc] : -1;
+          int slo = 0, sup = 0;
+          for (int u = 1; u < rowlen_loc[r]; u++) {
+            const int cc = col[(size_t)slice_ptr[r >> 5] + 32 * (size_t)u + (r & 31)];
+            if (u <= nlow[r]) {
+              if (cc == rprev && !slo) slo = u; else M.blk_has_lower[c] = 1;
+            } else {
+              if (cc == rnext && !sup) sup = u; else M.blk_has_upper[c] = 1;
+            }
+          }
+          if (slo > 15 || sup > 15) nibble_ok = false;
+          bc[i] = (unsigned char)(slo | (sup << 4));
+        }
+      }
+      M.blk_nlow.upload(bl);
+      M.blk_chain.upload(bc);
+    }
     // the block-sweep kernels assume chains: the only intra-block neighbours of the k-th cell are cells k-1, k+1
     bool chain = true;
     {
@@ -343,10 +376,8 @@ static void build_matrix(mf6gpu_matrix &M, int n, int n_ext, int nja, const int3
           if (is_halo(u) || blk_of[u] != blk_of[v]) continue;
           if (std::abs(kpos[u] - kpos[v]) != 1) chain = false;
         }
-      for (int c = 0; c < blk_colors; c++)
-        if (M.blk_maxk[c] > 32) chain = false;
     }
-    M.blk_chain_ok = chain;
+    M.blk_chain_ok = chain && nibble_ok;
   }
   // --- stencil compression table (fixed-width layout)
   if (M.uniform_w > 0 && !std::getenv("MF6GPU_NO_STENCIL")) {

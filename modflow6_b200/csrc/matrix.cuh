@@ -44,9 +44,13 @@ struct mf6gpu_matrix {
   // blk_rows[blk_off[c] + k * blk_nb[c] + q] = final row of the k-th cell (elimination order) of the q-th
   // block of colour c, or -1 past the end of a short block
   int blk_ncolors = 0;
-  bool blk_chain_ok = false;   // every block is a chain (cell k couples only to cells k-1 / k+1 of its block, <= 32 cells)
+  bool blk_chain_ok = false;   // every block is a chain: cell k couples only to cells k-1 / k+1 of its block
   std::vector<int> blk_off, blk_nb, blk_maxk;
   mf6::DevBuf<int> blk_rows;
+  mf6::DevBuf<unsigned char> blk_nlow;   // nlow of blk_rows' rows, same layout (saves the sweeps one dependent load)
+  mf6::DevBuf<unsigned char> blk_chain;  // same layout: SELL slot of the entry towards the previous (low nibble) / next
+                                         // (high nibble) cell of the chain, 0 = none
+  std::vector<char> blk_has_lower, blk_has_upper;  // per colour: factor entries outside the chains in the L / U half
   mf6::DevBuf<int> csr2sell;   // [nja] slot of each original CSR entry
   mf6::DevBuf<double> stage;   // [nja] H2D/D2H staging of CSR values
   mf6::DevBuf<double> xs, ys;  // [n] staging vectors for host multiply

@@ -839,7 +839,7 @@ int mf6gpu_solver_create(mf6gpu_matrix *m, const mf6gpu_ims_settings *settings,
       s->hb.alloc(n);
       s->st.alloc_zero(1);
       s->partial.alloc_zero(4 * (size_t)kMaxBlocks);
-      s->ilu_partial.alloc_zero((n / kBlock + (size_t)m->nlevels + 2) * (kBlock / 32));
+      s->ilu_partial.alloc_zero((n / kBlock + (size_t)m->nlevels + 2) * (kBlock / 32) + mf6::ilu0_block_dot_slots(*m));
       s->pmx.alloc_zero((size_t)kMaxBlocks);
       s->pmr.alloc_zero((size_t)kMaxBlocks);
       s->tickets.alloc_zero(8);
