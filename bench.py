@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", default="10,1000,1000", help="nlay,nrow,ncol of the C2 grid")
-    ap.add_argument("--ordering", default="multicolor", choices=["multicolor", "natural", "block"])
+    ap.add_argument("--ordering", default="block", choices=["multicolor", "natural", "block"])
     ap.add_argument("--cpu-iters", type=int, default=12, help="inner iterations of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--inner-maximum", type=int, default=500, help="INNER_MAXIMUM of the IMS LINEAR block")
