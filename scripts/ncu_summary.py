@@ -25,7 +25,7 @@ def short(name):
 
 
 md = [f"# ncu evidence, round {rnd}", "",
-      "Workload: `bench.py` C2 (10x1000x1000, 1e7 cells, nja 6.796e7, multicolour ILU0, f64), B200.", ""]
+      "Workload: `bench.py` C2 (10x1000x1000, 1e7 cells, nja 6.796e7, block-multicolour ILU0 ordering, f64), B200.", ""]
 lf = os.path.join(go, "launches.csv")
 if os.path.exists(lf):
     rows = [r for r in csv.reader(l for l in open(lf) if l.startswith('"'))]
