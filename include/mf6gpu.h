@@ -196,7 +196,8 @@ int mf6gpu_solution_get_permutation(mf6gpu_solution *s, int32_t *perm);
 /* the linear solver owned by the solution (for stats / summary) */
 mf6gpu_solver *mf6gpu_solution_solver(mf6gpu_solution *s);
 /* facts: 0 kernel launches of the last time step, 1 ILU levels, 2 SELL slots,
- * 3 fraction of stencil-compressed (slice, slot) column groups, 4 fixed SELL width (0 = ragged) */
+ * 3 fraction of stencil-compressed (slice, slot) column groups, 4 fixed SELL width (0 = ragged),
+ * 5 colours of the BLOCK_MULTICOLOR sweeps that need no row tables (-1: sweeps not applicable) */
 double mf6gpu_solution_stat(const mf6gpu_solution *s, int what);
 
 #ifdef __cplusplus

@@ -353,21 +353,32 @@ static int launch_levels_w(const mf6gpu_matrix &A, const double *lu, const doubl
 // needs no forward gather, the last colour no backward gather and its two chain passes fuse.
 // The chain term is applied after the others, so the summation order differs from the level kernels
 // (rounding only) when the chain neighbour is not the last slot of its half.
-template <int W, bool LOWER>
+// AFFINE (regular colour, matrix.cuh): grid.y = cell index k along the chain, row = kbase[k] + q
+template <int W, bool LOWER, bool AFFINE>
 __global__ void __launch_bounds__(kBlock, 8)
-ilu0_blk_gather_kernel(int ncell, int ncols, const int *__restrict__ brow,
+ilu0_blk_gather_kernel(int nb, int maxk, int ncols, const int *__restrict__ brow,
                        const unsigned char *__restrict__ bnlow, const unsigned char *__restrict__ bchain,
+                       const int *__restrict__ kbase, const unsigned char *__restrict__ nlow,
                        const int *__restrict__ col, const int *__restrict__ soff,
                        const double *__restrict__ lu, const double *__restrict__ rin, double *d,
                        const int *__restrict__ done) {
   if (done && *done) return;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= ncell) return;
-  const int r = __ldg(brow + t);
-  if (r < 0) return;
-  const int lo = __ldg(bnlow + t);
-  const int ch = __ldg(bchain + t);
-  const int skip = LOWER ? (ch & 15) : (ch >> 4);
+  int r, lo, skip;
+  if (AFFINE) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+    if (q >= nb) return;
+    r = __ldg(kbase + k) + q;
+    lo = __ldg(nlow + r);
+    skip = LOWER ? (k > 0 ? lo : 0) : (k + 1 < maxk ? lo + 1 : 0);
+  } else {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)nb * maxk) return;
+    r = __ldg(brow + t);
+    if (r < 0) return;
+    lo = __ldg(bnlow + t);
+    const int ch = __ldg(bchain + t);
+    skip = LOWER ? (ch & 15) : (ch >> 4);
+  }
   const long long base = (long long)(r >> 5) * (32 * W) + (r & 31);
   const int *so = soff ? soff + (r >> 5) * W : nullptr;
   double acc = LOWER ? rin[r] : d[r];
@@ -402,10 +413,11 @@ ilu0_blk_gather_kernel(int ncell, int ncols, const int *__restrict__ brow,
 // MODE 0: forward   d(k) = src(k) - L(k,k-1) d(k-1)            src = rin (first colour) or d (gathered)
 // MODE 1: backward  d(k) = (d(k) - U(k,k+1) d(k+1)) * piv(k)   + rho partial
 // MODE 2: both in one pass (last colour, block of at most KC cells)
-template <int MODE, int KC>
+template <int MODE, int KC, bool AFFINE>
 __global__ void __launch_bounds__(kBlock)
 ilu0_blk_chain_kernel(int nb, int maxk, int W, bool from_rin, const int *__restrict__ brow,
-                      const unsigned char *__restrict__ bchain, const double *__restrict__ lu,
+                      const unsigned char *__restrict__ bchain, const int *__restrict__ kbase,
+                      const unsigned char *__restrict__ nlow, const double *__restrict__ lu,
                       const double *__restrict__ rin, double *d, const int *__restrict__ done, IluDot D) {
   if (done && *done) return;
   double dot = 0.0;
@@ -420,8 +432,14 @@ ilu0_blk_chain_kernel(int nb, int maxk, int W, bool from_rin, const int *__restr
 #pragma unroll
       for (int k = 0; k < KC; k++) {
         const bool in = (k0 + k < maxk);
-        rk[k] = in ? __ldg(brow + (size_t)(k0 + k) * nb + q) : -1;
-        ck[k] = in ? __ldg(bchain + (size_t)(k0 + k) * nb + q) : 0;
+        if (AFFINE) {
+          rk[k] = in ? __ldg(kbase + k0 + k) + q : -1;
+          const int lo = in ? (int)__ldg(nlow + rk[k]) : 0;
+          ck[k] = !in ? 0 : ((k0 + k > 0 ? lo : 0) | ((k0 + k + 1 < maxk ? lo + 1 : 0) << 4));
+        } else {
+          rk[k] = in ? __ldg(brow + (size_t)(k0 + k) * nb + q) : -1;
+          ck[k] = in ? __ldg(bchain + (size_t)(k0 + k) * nb + q) : 0;
+        }
       }
 #pragma unroll
       for (int k = 0; k < KC; k++) {
@@ -482,9 +500,18 @@ static void launch_chain(const mf6gpu_matrix &A, int c, bool from_rin, const dou
   const int nb = A.blk_nb[c], maxk = A.blk_maxk[c], g = (nb + kBlock - 1) / kBlock, W = A.uniform_w;
   const int *brow = A.blk_rows.p + A.blk_off[c];
   const unsigned char *bch = A.blk_chain.p + A.blk_off[c];
+  const int *kb = A.blk_base.p + A.blk_base_off[c];
+  const bool aff = A.blk_affine[c];
   switch (chain_chunk(maxk)) {
-#define MF6_CHAIN_CASE(KC) \
-  case KC: ilu0_blk_chain_kernel<MODE, KC><<<g, kBlock, 0, s>>>(nb, maxk, W, from_rin, brow, bch, lu, rin, d, done, D); break;
+#define MF6_CHAIN_CASE(KC)                                                                                         \
+  case KC:                                                                                                         \
+    if (aff)                                                                                                       \
+      ilu0_blk_chain_kernel<MODE, KC, true><<<g, kBlock, 0, s>>>(nb, maxk, W, from_rin, brow, bch, kb, A.nlow.p, lu, \
+                                                                 rin, d, done, D);                                 \
+    else                                                                                                           \
+      ilu0_blk_chain_kernel<MODE, KC, false><<<g, kBlock, 0, s>>>(nb, maxk, W, from_rin, brow, bch, kb, A.nlow.p,  \
+                                                                  lu, rin, d, done, D);                            \
+    break;
     MF6_CHAIN_CASE(4)
     MF6_CHAIN_CASE(6)
     MF6_CHAIN_CASE(8)
@@ -502,10 +529,20 @@ static int launch_blocks_w(const mf6gpu_matrix &A, const double *lu, const doubl
   const int *so = A.slot_off.n ? A.slot_off.p : nullptr;
   int launches = 0, slot = 0;
   auto gather = [&](auto lower, int c) {
-    const int ncell = A.blk_nb[c] * A.blk_maxk[c];
-    ilu0_blk_gather_kernel<W, decltype(lower)::value><<<(ncell + kBlock - 1) / kBlock, kBlock, 0, s>>>(
-        ncell, A.n_ext, A.blk_rows.p + A.blk_off[c], A.blk_nlow.p + A.blk_off[c], A.blk_chain.p + A.blk_off[c],
-        A.col.p, so, lu, rin, d, done);
+    constexpr bool LOWER = decltype(lower)::value;
+    const int nb = A.blk_nb[c], maxk = A.blk_maxk[c];
+    const int *brow = A.blk_rows.p + A.blk_off[c];
+    const unsigned char *bnl = A.blk_nlow.p + A.blk_off[c], *bch = A.blk_chain.p + A.blk_off[c];
+    const int *kb = A.blk_base.p + A.blk_base_off[c];
+    if (A.blk_affine[c] && maxk <= 65535) {
+      const dim3 g((nb + kBlock - 1) / kBlock, maxk);
+      ilu0_blk_gather_kernel<W, LOWER, true><<<g, kBlock, 0, s>>>(nb, maxk, A.n_ext, brow, bnl, bch, kb, A.nlow.p,
+                                                                  A.col.p, so, lu, rin, d, done);
+    } else {
+      const long long ncell = (long long)nb * maxk;
+      ilu0_blk_gather_kernel<W, LOWER, false><<<(unsigned)((ncell + kBlock - 1) / kBlock), kBlock, 0, s>>>(
+          nb, maxk, A.n_ext, brow, bnl, bch, kb, A.nlow.p, A.col.p, so, lu, rin, d, done);
+    }
     launches++;
   };
   // the last colour's two chain passes fuse when nothing of its U half lies outside the chains and

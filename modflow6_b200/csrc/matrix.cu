@@ -364,6 +364,30 @@ static void build_matrix(mf6gpu_matrix &M, int n, int n_ext, int nja, const int3
       }
       M.blk_nlow.upload(bl);
       M.blk_chain.upload(bc);
+      // regular colours (structured grids): all blocks full, the k-th cells of consecutive blocks are
+      // consecutive rows, the chain entries are the last lower / first upper slot -> no table loads
+      std::vector<int> base;
+      M.blk_affine.assign(blk_colors, 0);
+      M.blk_base_off.assign(blk_colors + 1, 0);
+      for (int c = 0; c < blk_colors; c++) {
+        const size_t nbc = (size_t)M.blk_nb[c], off = (size_t)M.blk_off[c];
+        bool aff = nbc > 0 && !std::getenv("MF6GPU_NO_AFFINE");
+        for (int k = 0; k < M.blk_maxk[c] && aff; k++) {
+          const int r0 = rows[off + k * nbc];
+          for (size_t q = 0; q < nbc; q++) {
+            const size_t i = off + k * nbc + q;
+            const int want = (k > 0 ? bl[i] : 0) | ((k + 1 < M.blk_maxk[c] ? bl[i] + 1 : 0) << 4);
+            if (r0 < 0 || rows[i] != r0 + (int)q || bc[i] != want) {
+              aff = false;
+              break;
+            }
+          }
+        }
+        M.blk_affine[c] = aff;
+        for (int k = 0; k < M.blk_maxk[c]; k++) base.push_back(nbc ? rows[off + k * nbc] : -1);
+        M.blk_base_off[c + 1] = (int)base.size();
+      }
+      M.blk_base.upload(base);
     }
     // the block-sweep kernels assume chains: the only intra-block neighbours of the k-th cell are cells k-1, k+1
     bool chain = true;

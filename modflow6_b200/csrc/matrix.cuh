@@ -50,6 +50,11 @@ struct mf6gpu_matrix {
   mf6::DevBuf<unsigned char> blk_nlow;   // nlow of blk_rows' rows, same layout (saves the sweeps one dependent load)
   mf6::DevBuf<unsigned char> blk_chain;  // same layout: SELL slot of the entry towards the previous (low nibble) / next
                                          // (high nibble) cell of the chain, 0 = none
+  // regular colours: row of cell k of block q = blk_base[blk_base_off[c] + k] + q and the chain slots are nlow /
+  // nlow + 1, so the sweeps need none of the three tables above
+  std::vector<char> blk_affine;
+  std::vector<int> blk_base_off;
+  mf6::DevBuf<int> blk_base;
   std::vector<char> blk_has_lower, blk_has_upper;  // per colour: factor entries outside the chains in the L / U half
   mf6::DevBuf<int> csr2sell;   // [nja] slot of each original CSR entry
   mf6::DevBuf<double> stage;   // [nja] H2D/D2H staging of CSR values

@@ -1691,6 +1691,11 @@ double mf6gpu_solution_stat(const mf6gpu_solution *s, int what) {
     case 2: return (double)s->A->nslots;
     case 3: return s->A->slot_off_hit;
     case 4: return (double)s->A->uniform_w;
+    case 5: {
+      int na = 0;
+      for (char a : s->A->blk_affine) na += a ? 1 : 0;
+      return s->A->blk_chain_ok ? (double)na : -1.0;
+    }
   }
   return -1.0;
 }

@@ -55,6 +55,7 @@ def test_block_sweep_apply_matches_oracle(gpu, monkeypatch, grid, stencil):
     G, z, zo = _apply_pair(configs.c2_confined(*grid, T.ORDER_BLOCK_MULTICOLOR))
     assert G.stat(4) > 0, "fixed-width layout not engaged"
     assert G.stat(1) == grid[0] + 1            # nlay + 1 dependency levels
+    assert G.stat(5) == 2                      # full columns of a DIS grid: table-free sweeps
     assert np.abs(z - zo).max() <= 4 * np.spacing(np.abs(zo).max())
 
 
@@ -94,3 +95,23 @@ def test_block_sweep_simulation_parity(gpu, monkeypatch, grid):
         assert abs(a["inner_iterations"] - b["inner_iterations"]) <= max(3, b["inner_iterations"] // 10)
         assert np.abs(a["head"] - b["head"]).max() <= 0.1 * cfg.sln.dvclose
         assert abs(a["pdiffr"] - b["pdiffr"]) <= 1e-3
+
+
+@pytest.mark.parametrize("grid", GRIDS[:4])
+def test_block_sweep_table_path(gpu, monkeypatch, grid):
+    """irregular colours (short columns, unstructured layers) address their rows through the block tables;
+    MF6GPU_NO_AFFINE forces that path on a regular grid"""
+    monkeypatch.setenv("MF6GPU_UNIFORM_PAD_PCT", "100")
+    monkeypatch.setenv("MF6GPU_NO_AFFINE", "1")
+    G, z, zo = _apply_pair(configs.c2_confined(*grid, T.ORDER_BLOCK_MULTICOLOR))
+    assert G.stat(5) == 0
+    assert np.abs(z - zo).max() <= 4 * np.spacing(np.abs(zo).max())
+
+
+def test_block_sweep_disv(gpu, monkeypatch):
+    """layered DISV: the columns are still chains, the block graph needs more than two colours"""
+    monkeypatch.setenv("MF6GPU_UNIFORM_PAD_PCT", "100")
+    cfg = configs.c4_disv("hexagonal", 6, 9, 11, T.ORDER_BLOCK_MULTICOLOR)
+    G, z, zo = _apply_pair(cfg)
+    assert G.stat(5) >= 0, "block sweeps not engaged"
+    assert np.abs(z - zo).max() <= 4 * np.spacing(np.abs(zo).max())
