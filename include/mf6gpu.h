@@ -191,6 +191,13 @@ int mf6gpu_solution_get_amat(mf6gpu_solution *s, double *amat);  /* CSR order */
 int mf6gpu_solution_get_rhs(mf6gpu_solution *s, double *rhs);
 int mf6gpu_solution_get_flowja(mf6gpu_solution *s, double *flowja);
 int mf6gpu_solution_get_condsat(mf6gpu_solution *s, double *condsat);
+/* simulated rate of every boundary of the last time step (bnd_cq_simrate, BoundaryPackage.f90:583-619;
+ * calc_chd_rate, gwf-chd.f90:264-320), packages concatenated in set_packages order: what
+ * save_print_model_flows (BoundaryPackage.f90:1753-1900) writes to the budget file.  *count = number
+ * of boundaries; simvals may be NULL to query it */
+int mf6gpu_solution_get_simvals(mf6gpu_solution *s, int32_t cap, double *simvals, int32_t *count);
+/* STO-SS and STO-SY rates per cell of the last time step (sto_cq, gwf-sto.f90:447-564), original order */
+int mf6gpu_solution_get_storage(mf6gpu_solution *s, double *strgss, double *strgsy);
 /* elimination order of the owned cells (see mf6gpu_matrix_get_permutation) */
 int mf6gpu_solution_get_permutation(mf6gpu_solution *s, int32_t *perm);
 /* the linear solver owned by the solution (for stats / summary) */

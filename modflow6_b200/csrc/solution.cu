@@ -1667,6 +1667,27 @@ int mf6gpu_solution_get_flowja(mf6gpu_solution *s, double *flowja) {
   });
 }
 
+int mf6gpu_solution_get_simvals(mf6gpu_solution *s, int32_t cap, double *simvals, int32_t *count) {
+  return guard([&] {
+    MF6_REQUIRE(s && count, "solution_get_simvals: null argument");
+    *count = s->nb;
+    if (simvals && s->nb > 0) {
+      MF6_REQUIRE(cap >= s->nb, "solution_get_simvals: buffer too small");
+      MF6_CK(cudaMemcpyAsync(simvals, s->b_sim.p, sizeof(double) * (size_t)s->nb, cudaMemcpyDeviceToHost, s->stream));
+      MF6_CK(cudaStreamSynchronize(s->stream));
+    }
+  });
+}
+
+int mf6gpu_solution_get_storage(mf6gpu_solution *s, double *strgss, double *strgsy) {
+  return guard([&] {
+    MF6_REQUIRE(s && strgss && strgsy, "solution_get_storage: null argument");
+    MF6_REQUIRE(s->strgss.n > 0, "solution_get_storage: the model has no STO package");
+    get_cell_vector(s, s->strgss.p, strgss);
+    get_cell_vector(s, s->strgsy.p, strgsy);
+  });
+}
+
 int mf6gpu_solution_get_condsat(mf6gpu_solution *s, double *condsat) {
   return guard([&] {
     MF6_REQUIRE(s && condsat, "solution_get_condsat: null argument");

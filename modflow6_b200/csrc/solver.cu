@@ -512,6 +512,80 @@ __global__ void scale1_vec_kernel(int n, const int *__restrict__ slice_ptr,
   }
 }
 
+// ---- SCALING_METHOD L2NORM (ims_base_scale, ImsLinearBase.f90:676-721) -------------------------
+// pass 1: dscale(n) = 1 / ||row n||_2 (1 for an empty row), row scaled in place
+__global__ void scale2_rows_kernel(int n, const int *__restrict__ slice_ptr,
+                                   const unsigned char *__restrict__ rowlen, double *__restrict__ val,
+                                   double *__restrict__ dscale) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    const long long base = (long long)slice_ptr[r >> 5] + (r & 31);
+    const int len = rowlen[r];
+    double c1 = 0.0;
+    for (int k = 0; k < len; k++) {
+      const double a = val[base + 32LL * k];
+      c1 = c1 + a * a;
+    }
+    c1 = sqrt(c1);
+    c1 = (c1 == 0.0) ? 1.0 : 1.0 / c1;
+    dscale[r] = c1;
+    for (int k = 0; k < len; k++) val[base + 32LL * k] = c1 * val[base + 32LL * k];
+  }
+}
+
+// pass 2: dscale2(j) = 1 / ||column j||_2 of the row-scaled matrix.  The entries of column j are the
+// transposed positions of row j's entries (structurally symmetric matrix); they are gathered in
+// ascending row order -- lower neighbours, diagonal, upper neighbours -- like the reference's row loop
+// accumulates them, so no atomics and a fixed summation order.
+__global__ void scale2_cols_kernel(int n, const int *__restrict__ slice_ptr,
+                                   const unsigned char *__restrict__ rowlen,
+                                   const unsigned char *__restrict__ nlow, const int *__restrict__ col,
+                                   const double *__restrict__ val, double *__restrict__ dscale2) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const long long base = (long long)slice_ptr[j >> 5] + (j & 31);
+    const int len = rowlen[j], lo = nlow[j];
+    double c2 = 0.0;
+    for (int k = 1; k <= len; k++) {
+      // visiting order: slots 1..lo, then the diagonal (slot 0), then slots lo+1..len-1
+      const int slot = (k <= lo) ? k : (k == lo + 1 ? 0 : k - 1);
+      double a = 0.0;
+      if (slot == 0) {
+        a = val[base];
+      } else {
+        const int i = col[base + 32LL * slot];
+        if (i < n) {  // (halo columns have no row here)
+          const long long bi = (long long)slice_ptr[i >> 5] + (i & 31);
+          const int leni = rowlen[i];
+          for (int k2 = 1; k2 < leni; k2++)
+            if (col[bi + 32LL * k2] == j) {
+              a = val[bi + 32LL * k2];
+              break;
+            }
+        }
+      }
+      c2 = c2 + a * a;
+    }
+    dscale2[j] = (c2 == 0.0) ? 1.0 : 1.0 / sqrt(c2);
+  }
+}
+
+// pass 3: column scaling of the matrix, then x / dscale2 and b * dscale (ImsLinearBase.f90:712-727)
+__global__ void scale2_apply_kernel(int n, const int *__restrict__ slice_ptr,
+                                    const unsigned char *__restrict__ rowlen, const int *__restrict__ col,
+                                    double *__restrict__ val, const double *__restrict__ ds,
+                                    const double *__restrict__ ds2, double *__restrict__ x,
+                                    double *__restrict__ b) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    const long long base = (long long)slice_ptr[r >> 5] + (r & 31);
+    const int len = rowlen[r];
+    for (int k = 0; k < len; k++) {
+      const long long p = base + 32LL * k;
+      val[p] = ds2[col[p]] * val[p];
+    }
+    x[r] = x[r] / ds2[r];
+    b[r] = b[r] * ds[r];
+  }
+}
+
 __global__ void scale_apply_kernel(int n, const int *__restrict__ slice_ptr,
                                    const unsigned char *__restrict__ rowlen,
                                    const int *__restrict__ col, double *__restrict__ val,
@@ -634,6 +708,13 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
     copy_kernel<<<G, kBlock, 0, S>>>(N, dscale.p, dscale2.p);
     scale_apply_kernel<<<G, kBlock, 0, S>>>(N, A->slice_ptr.p, A->rowlen.p, A->col.p, A->val.p,
                                             dscale.p, dscale2.p, x_dev, b_dev, 0);
+    launches += 3;
+  } else if (s.iscl == 2) {
+    scale2_rows_kernel<<<G, kBlock, 0, S>>>(N, A->slice_ptr.p, A->rowlen.p, A->val.p, dscale.p);
+    scale2_cols_kernel<<<G, kBlock, 0, S>>>(N, A->slice_ptr.p, A->rowlen.p, A->nlow.p, A->col.p, A->val.p,
+                                            dscale2.p);
+    scale2_apply_kernel<<<G, kBlock, 0, S>>>(N, A->slice_ptr.p, A->rowlen.p, A->col.p, A->val.p, dscale.p,
+                                             dscale2.p, x_dev, b_dev);
     launches += 3;
   }
   // -- preconditioner (ImsLinear.f90:669-673)
@@ -773,7 +854,7 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
   }
   if (icnvg < 0) icnvg = 0;
   // -- unscale (ImsLinear.f90:740-745)
-  if (s.iscl == 1) {
+  if (s.iscl != 0) {
     scale_apply_kernel<<<G, kBlock, 0, S>>>(N, A->slice_ptr.p, A->rowlen.p, A->col.p, A->val.p,
                                             dscale.p, dscale2.p, x_dev, b_dev, 1);
     launches++;
@@ -795,7 +876,7 @@ static void check_settings(mf6gpu_ims_settings &s) {
   MF6_REQUIRE(s.ilinmeth == 1 || s.ilinmeth == 2, "solver: LINEAR_ACCELERATION must be CG (1) or BICGSTAB (2)");
   MF6_REQUIRE(s.level <= 0 && s.droptol <= 0.0,
               "solver: ILUT/MILUT (PRECONDITIONER_LEVELS / DROP_TOLERANCE) is not available on the GPU path");
-  MF6_REQUIRE(s.iscl == 0 || s.iscl == 1, "solver: SCALING_METHOD L2NORM is not available on the GPU path");
+  MF6_REQUIRE(s.iscl >= 0 && s.iscl <= 2, "solver: SCALING_METHOD must be NONE (0), DIAGONAL (1) or L2NORM (2)");
   MF6_REQUIRE(s.relax >= 0.0 && s.relax <= 1.0, "solver: RELAXATION_FACTOR must be in [0,1]");
   MF6_REQUIRE(s.north >= 0, "solver: NUMBER_ORTHOGONALIZATIONS must be >= 0");
   MF6_REQUIRE(s.iter1 > 0, "solver: INNER_MAXIMUM must be > 0");

@@ -29,6 +29,7 @@ SYMBOLS = [
     "mf6gpu_comm_unique_id", "mf6gpu_comm_create", "mf6gpu_comm_destroy", "mf6gpu_comm_rank", "mf6gpu_comm_size",
     "mf6gpu_comm_p2p_export", "mf6gpu_comm_p2p_import", "mf6gpu_comm_p2p_enabled", "mf6gpu_comm_p2p_disable",
     "mf6gpu_matrix_create_blocked", "mf6gpu_solution_get_permutation",
+    "mf6gpu_solution_get_simvals", "mf6gpu_solution_get_storage",
 ]
 
 _lib = None
@@ -106,6 +107,8 @@ def load():
     L.mf6gpu_solution_formulate.argtypes = [vp, i32, f64, i32]
     for f in ("get_x", "set_x", "get_amat", "get_rhs", "get_flowja", "get_condsat"):
         getattr(L, "mf6gpu_solution_" + f).argtypes = [vp, pf64]
+    L.mf6gpu_solution_get_simvals.argtypes = [vp, i32, pf64, pi32]
+    L.mf6gpu_solution_get_storage.argtypes = [vp, pf64, pf64]
     L.mf6gpu_solution_stat.restype = f64
     L.mf6gpu_solution_stat.argtypes = [vp, C.c_int]
     L.mf6gpu_solution_solver.restype = vp

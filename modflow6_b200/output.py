@@ -1,0 +1,174 @@
+"""Binary head (.hds) and cell-by-cell budget (.cbc) files in the reference's formats (SURVEY.md section 8f,
+rank 1: the step right after the hot path of every time step).
+
+MODFLOW 6 opens its binary output with ACCESS='STREAM', FORM='UNFORMATTED' (src/Utilities/OpenSpec.f90):
+plain little-endian values back to back, no record markers.  All integers are i32, all reals f64, all
+strings 16 characters, right-justified for the flow-term text.
+
+Writers restate
+  ulasav    src/Utilities/InputOutput.f90:924-940     one layer of a dependent variable
+  ubdsv1    src/Utilities/InputOutput.f90:945-974     full array budget term (IMETH = 1)
+  ubdsv06   src/Utilities/InputOutput.f90:981-1024    list budget term header (IMETH = 6)
+  ubdsvd    src/Utilities/InputOutput.f90:1053-1071   one list entry (node, node2, q)
+as they are driven by record_array (Dis.f90:1401-1485), record_connection_array
+(DiscretizationBase.f90:955-969), sto_save_model_flows (gwf-sto.f90:620-640),
+save_print_model_flows (BoundaryPackage.f90:1753-1900) and gwf_ot_flow (gwf.f90:911-960: STO-SS, STO-SY,
+FLOW-JA-FACE, then the stress packages in package order).
+Readers restate HeadFileReader.f90:88-130 and BudgetFileReader.f90:120-230 and are used by the tests to
+check the writers (round trip + hand-packed records).
+"""
+import struct
+
+import numpy as np
+
+from . import ctypes_types as T
+
+PKG_TEXT = {T.PKG_CHD: "CHD", T.PKG_WEL: "WEL", T.PKG_RIV: "RIV", T.PKG_RCH: "RCH", T.PKG_GHB: "GHB",
+            T.PKG_DRN: "DRN"}
+
+
+def _text16(s, right=True):
+    s = s[:16]
+    return (s.rjust(16) if right else s.ljust(16)).encode("ascii")
+
+
+def grid_shape(shape):
+    """(nlay, nrow, ncol) for DIS; (nlay, ncpl) for DISV is written as (nlay, 1, ncpl) (Disv.f90 mshape)"""
+    if len(shape) == 3:
+        return tuple(int(v) for v in shape)
+    if len(shape) == 2:
+        return int(shape[0]), 1, int(shape[1])
+    return 1, 1, int(shape[0])
+
+
+class HeadFileWriter:
+    def __init__(self, path, shape, text="HEAD"):
+        self.nlay, self.nrow, self.ncol = grid_shape(shape)
+        self.text = _text16(text)
+        self.f = open(path, "wb")
+
+    def write(self, kstp, kper, pertim, totim, head):
+        """one ulasav record per layer"""
+        head = np.ascontiguousarray(head, dtype="<f8").reshape(self.nlay, self.nrow * self.ncol)
+        for k in range(self.nlay):
+            self.f.write(struct.pack("<iidd", kstp, kper, pertim, totim) + self.text
+                         + struct.pack("<iii", self.ncol, self.nrow, k + 1))
+            self.f.write(head[k].tobytes())
+        self.f.flush()
+
+    def close(self):
+        self.f.close()
+
+
+class BudgetFileWriter:
+    def __init__(self, path, shape, model_name):
+        self.nlay, self.nrow, self.ncol = grid_shape(shape)
+        self.model = _text16(model_name.upper(), right=False)
+        self.f = open(path, "wb")
+
+    def _header(self, kstp, kper, text, ncol, nrow, nlay, imeth, delt, pertim, totim):
+        self.f.write(struct.pack("<ii", kstp, kper) + _text16(text) + struct.pack("<iii", ncol, nrow, -nlay))
+        self.f.write(struct.pack("<iddd", imeth, delt, pertim, totim))
+
+    def write_flowja(self, kstp, kper, delt, pertim, totim, flowja):
+        """record_connection_array: ubdsv1 with ncol = nja, nrow = nlay = 1"""
+        flowja = np.ascontiguousarray(flowja, dtype="<f8")
+        self._header(kstp, kper, "FLOW-JA-FACE", flowja.size, 1, 1, 1, delt, pertim, totim)
+        self.f.write(flowja.tobytes())
+
+    def write_array(self, kstp, kper, delt, pertim, totim, text, values):
+        """record_array with idataun < 0 (STO-SS, STO-SY): the whole grid as one IMETH = 1 record"""
+        values = np.ascontiguousarray(values, dtype="<f8")
+        assert values.size == self.nlay * self.nrow * self.ncol
+        self._header(kstp, kper, text, self.ncol, self.nrow, self.nlay, 1, delt, pertim, totim)
+        self.f.write(values.tobytes())
+
+    def write_list(self, kstp, kper, delt, pertim, totim, text, package_name, nodes, q):
+        """save_print_model_flows: IMETH = 6 header, then (node, bound index, rate) per boundary.
+        `nodes` are 0-based cell numbers; entries with node < 0 (inactive) are skipped like node <= 0 there."""
+        nodes = np.asarray(nodes)
+        q = np.asarray(q, dtype=np.float64)
+        keep = nodes >= 0
+        self._header(kstp, kper, text, self.ncol, self.nrow, self.nlay, 6, delt, pertim, totim)
+        self.f.write(self.model + _text16(package_name.upper(), right=False) + self.model
+                     + _text16(package_name.upper(), right=False))
+        self.f.write(struct.pack("<i", 1))                      # naux + 1
+        self.f.write(struct.pack("<i", int(keep.sum())))        # nlist
+        rec = np.empty(int(keep.sum()), dtype=np.dtype([("n", "<i4"), ("n2", "<i4"), ("q", "<f8")]))
+        rec["n"] = nodes[keep] + 1
+        rec["n2"] = np.nonzero(keep)[0] + 1
+        rec["q"] = q[keep]
+        self.f.write(rec.tobytes())
+
+    def write_step(self, kstp, kper, delt, pertim, totim, solution, packages, package_names=None):
+        """everything gwf_ot_flow saves for one time step, taken from a solution object
+        (GpuNumericalSolution or the oracle: flowja, storage_rates, simvals)"""
+        m = solution.model
+        if getattr(m, "insto", 0):
+            ss, sy = solution.storage_rates
+            self.write_array(kstp, kper, delt, pertim, totim, "STO-SS", ss)
+            if m.iconvert is not None and np.any(m.iconvert):      # iusesy (gwf-sto.f90:633-637)
+                self.write_array(kstp, kper, delt, pertim, totim, "STO-SY", sy)
+        self.write_flowja(kstp, kper, delt, pertim, totim, solution.flowja)
+        sim = solution.simvals
+        count = {}
+        for i, p in enumerate(packages):
+            t = PKG_TEXT[p.type]
+            count[t] = count.get(t, 0) + 1
+            name = package_names[i] if package_names else f"{t}-{count[t]}"   # default package names, e.g. CHD-1
+            self.write_list(kstp, kper, delt, pertim, totim, t, name, p.nodelist, sim[i])
+        self.f.flush()
+
+    def close(self):
+        self.f.close()
+
+
+def read_head_file(path):
+    """list of dicts (kstp, kper, pertim, totim, text, ncol, nrow, ilay, data[nrow, ncol])"""
+    out = []
+    with open(path, "rb") as f:
+        while True:
+            h = f.read(52)
+            if len(h) < 52:
+                break
+            kstp, kper, pertim, totim = struct.unpack("<iidd", h[:24])
+            text = h[24:40].decode("ascii")
+            ncol, nrow, ilay = struct.unpack("<iii", h[40:52])
+            data = np.frombuffer(f.read(8 * ncol * nrow), dtype="<f8").reshape(nrow, ncol)
+            out.append(dict(kstp=kstp, kper=kper, pertim=pertim, totim=totim, text=text, ncol=ncol, nrow=nrow,
+                            ilay=ilay, data=data))
+    return out
+
+
+def read_budget_file(path):
+    """list of dicts; IMETH 1: `flow` array (FLOW-JA-FACE: nval = ncol; else ncol*nrow*|nlay|),
+    IMETH 6: names, auxtxt, `node`, `node2`, `q`, `aux`"""
+    out = []
+    with open(path, "rb") as f:
+        while True:
+            h = f.read(36)
+            if len(h) < 36:
+                break
+            kstp, kper = struct.unpack("<ii", h[:8])
+            text = h[8:24].decode("ascii")
+            nval, idum1, idum2 = struct.unpack("<iii", h[24:36])
+            imeth, delt, pertim, totim = struct.unpack("<iddd", f.read(28))
+            r = dict(kstp=kstp, kper=kper, text=text, ncol=nval, nrow=idum1, nlay=idum2, imeth=imeth, delt=delt,
+                     pertim=pertim, totim=totim)
+            if imeth == 1:
+                n = nval if text.strip() == "FLOW-JA-FACE" else nval * idum1 * abs(idum2)
+                r["flow"] = np.frombuffer(f.read(8 * n), dtype="<f8")
+            elif imeth == 6:
+                names = [f.read(16).decode("ascii") for _ in range(4)]
+                r.update(srcmodel=names[0], srcpackage=names[1], dstmodel=names[2], dstpackage=names[3])
+                ndat, = struct.unpack("<i", f.read(4))
+                naux = ndat - 1
+                r["auxtxt"] = [f.read(16).decode("ascii") for _ in range(naux)]
+                nlist, = struct.unpack("<i", f.read(4))
+                dt = np.dtype([("n", "<i4"), ("n2", "<i4"), ("q", "<f8"), ("aux", "<f8", (naux,))])
+                rec = np.frombuffer(f.read(dt.itemsize * nlist), dtype=dt)
+                r.update(node=rec["n"].copy(), node2=rec["n2"].copy(), q=rec["q"].copy(), aux=rec["aux"].copy())
+            else:
+                raise ValueError(f"budget file: IMETH {imeth} is not written by MODFLOW 6")
+            out.append(r)
+    return out

@@ -74,6 +74,26 @@ class GpuNumericalSolution:
     def condsat(self):
         return self._get("condsat", self.model.njas)
 
+    @property
+    def simvals(self):
+        """simulated rate of every boundary of the last time step, one array per package (set_packages order)"""
+        cnt = C.c_int32()
+        check(self._L.mf6gpu_solution_get_simvals(self.h, 0, None, C.byref(cnt)))
+        a = np.empty(max(cnt.value, 1))
+        check(self._L.mf6gpu_solution_get_simvals(self.h, cnt.value, T.ptr_f64(a), C.byref(cnt)))
+        out, i0 = [], 0
+        for p in self._pkgs:
+            out.append(a[i0:i0 + p.nodelist.size].copy())
+            i0 += p.nodelist.size
+        return out
+
+    @property
+    def storage_rates(self):
+        """(STO-SS, STO-SY) rate per cell of the last time step"""
+        ss, sy = np.empty(self.n), np.empty(self.n)
+        check(self._L.mf6gpu_solution_get_storage(self.h, T.ptr_f64(ss), T.ptr_f64(sy)))
+        return ss, sy
+
     def elimination_order(self):
         """perm[k] = cell eliminated k-th by the ILU (the permutation to hand to the oracle)"""
         p = np.empty(self.n, np.int32)

@@ -1239,6 +1239,13 @@ double *orc_sln_flowja(orc_solution *S) { return S->flowja; }
 const double *orc_sln_amat(orc_solution *S) { return S->amat; }
 const double *orc_sln_rhs(orc_solution *S) { return S->rhs; }
 const double *orc_sln_condsat(orc_solution *S) { return S->condsat; }
+/* simulated rates of package k (bnd_cq_simrate / calc_chd_rate) and the STO-SS / STO-SY rates per cell
+ * (sto_cq) of the last time step: what the budget file records hold */
+const double *orc_sln_simvals(orc_solution *S, int k) {
+  return (k >= 0 && k < S->npkg) ? S->pkg[k].simvals : 0;
+}
+const double *orc_sln_strgss(orc_solution *S) { return S->strgss; }
+const double *orc_sln_strgsy(orc_solution *S) { return S->strgsy; }
 void orc_sln_timers(orc_solution *S, double *t2) {
   t2[0] = S->t_form;
   t2[1] = S->t_ls;

@@ -135,6 +135,9 @@ int orc_sln_timestep(orc_solution *S, int kper, int kstp, double delt, int iss,
 /* access to state */
 double *orc_sln_x(orc_solution *S);
 double *orc_sln_flowja(orc_solution *S);
+const double *orc_sln_simvals(orc_solution *S, int k);
+const double *orc_sln_strgss(orc_solution *S);
+const double *orc_sln_strgsy(orc_solution *S);
 const double *orc_sln_amat(orc_solution *S);
 const double *orc_sln_rhs(orc_solution *S);
 const double *orc_sln_condsat(orc_solution *S);

@@ -61,7 +61,10 @@ def lib():
         L.orc_sln_timestep.restype = C.c_int
         L.orc_sln_timestep.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(T.StepReport)]
         L.orc_sln_formulate.argtypes = [vp, C.c_int, C.c_double, C.c_int]
-        for f in ("orc_sln_x", "orc_sln_flowja", "orc_sln_amat", "orc_sln_rhs", "orc_sln_condsat"):
+        L.orc_sln_simvals.restype = T.p_f64
+        L.orc_sln_simvals.argtypes = [vp, C.c_int]
+        for f in ("orc_sln_x", "orc_sln_flowja", "orc_sln_amat", "orc_sln_rhs", "orc_sln_condsat", "orc_sln_strgss",
+                  "orc_sln_strgsy"):
             getattr(L, f).restype = T.p_f64
             getattr(L, f).argtypes = [vp]
         L.orc_sln_timers.argtypes = [vp, T.p_f64]
@@ -158,8 +161,21 @@ class OracleSolution:
             lib().orc_sln_set_blocks(self.h, T.ptr_i32(self.blocks))
 
     def set_packages(self, pkgs):
+        self._pkgs = list(pkgs)
         arr = package_array(pkgs)
         lib().orc_sln_set_packages(self.h, len(pkgs), arr)
+
+    @property
+    def simvals(self):
+        out = []
+        for k, p in enumerate(self._pkgs):
+            n = p.nodelist.size
+            out.append(np.ctypeslib.as_array(lib().orc_sln_simvals(self.h, k), shape=(max(n, 1),))[:n].copy())
+        return out
+
+    @property
+    def storage_rates(self):
+        return self._view("orc_sln_strgss", self.n).copy(), self._view("orc_sln_strgsy", self.n).copy()
 
     def timestep(self, kper=1, kstp=1, delt=1.0, iss=1):
         rep = T.StepReport()

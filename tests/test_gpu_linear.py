@@ -183,6 +183,26 @@ def test_exact_initial_guess_and_diagonal_scaling(system):
     assert np.allclose(A.get_values(), a, rtol=1e-13)    # unscaled again
 
 
+@pytest.mark.parametrize("meth", [1, 2])
+@pytest.mark.parametrize("ordering", [T.ORDER_NATURAL, T.ORDER_MULTICOLOR])
+def test_l2norm_scaling(system, meth, ordering):
+    """SCALING_METHOD L2NORM (ims_base_scale, ISCL = 2, ImsLinearBase.f90:676-721): row norms, then column
+    norms of the row-scaled matrix, gathered in the reference's accumulation order (no atomics)"""
+    from modflow6_b200.linear import GpuLinearSolver, GpuMatrix
+    from oracle.oracle import OracleIms
+    m, a, b, x0 = system
+    ims = T.ImsSettings.make(dvclose=1e-8, rclose=1e-6, iter1=600, ilinmeth=meth, iscl=2, gpu_ordering=ordering)
+    A = GpuMatrix(m.ia, m.ja, 0, ordering)
+    A.update(a)
+    xg, xo = x0.copy(), x0.copy()
+    it, cv = GpuLinearSolver(A, ims).solve(1, b, xg)
+    perm = A.permutation() if ordering != T.ORDER_NATURAL else None
+    ito, cvo = OracleIms(m.ia, m.ja, ims, perm=perm).solve(a, xo, b)
+    assert cv == 1 and cvo == 1 and abs(it - ito) <= max(8, ito // 5)
+    assert np.abs(xg - xo).max() <= (50 if meth == 2 else 0.5) * 1e-8
+    assert np.allclose(A.get_values(), a, rtol=1e-13)    # unscaled again
+
+
 def test_unsupported_options_fail_loudly(system):
     from modflow6_b200.lib import Mf6GpuError
     from modflow6_b200.linear import GpuLinearSolver, GpuMatrix
