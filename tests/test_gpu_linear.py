@@ -183,8 +183,7 @@ def test_exact_initial_guess_and_diagonal_scaling(system):
     assert np.allclose(A.get_values(), a, rtol=1e-13)    # unscaled again
 
 
-@pytest.mark.parametrize("meth", [1, 2])
-@pytest.mark.parametrize("ordering", [T.ORDER_NATURAL, T.ORDER_MULTICOLOR])
+@pytest.mark.parametrize("meth,ordering", [(1, T.ORDER_NATURAL), (2, T.ORDER_NATURAL), (1, T.ORDER_MULTICOLOR)])
 def test_l2norm_scaling(system, meth, ordering):
     """SCALING_METHOD L2NORM (ims_base_scale, ISCL = 2, ImsLinearBase.f90:676-721): row norms, then column
     norms of the row-scaled matrix, gathered in the reference's accumulation order (no atomics)"""
