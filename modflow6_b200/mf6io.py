@@ -1,0 +1,464 @@
+"""Reader for the subset of MODFLOW 6 input files that feeds the accelerated path (SURVEY.md section 8f,
+rank 3): mfsim.nam, TDIS, IMS, GWF name file, DIS, IC, NPF, STO, CHD/WEL/DRN/RIV/GHB/RCH (list based), OC and
+GWF-GWF exchanges -- enough to run FloPy-written models such as the reference's `.mf6minsim/` example through
+`mf6gpu_solution_*` without the Fortran host (which cannot be built in this image).
+
+Format facts restated here (doc/mf6io/mf6ivar/dfn/*.dfn; src/Utilities/BlockParser.f90,
+src/Utilities/ArrayReaders.f90; src/Utilities/Idm/mf6blockfile/*):
+  * free format, case-insensitive keywords, tokens separated by blanks or commas, quotes group a token;
+    `#`, `!` and `//` start a comment line; BEGIN <name> [<number>] ... END <name>
+  * READARRAY control lines: CONSTANT v | INTERNAL [FACTOR f] [IPRN n] + values | OPEN/CLOSE file [FACTOR f]
+    [(BINARY)] [IPRN n]; with LAYERED after the array name there is one control line per layer
+  * list packages: PERIOD <iper> blocks hold `cellid  bound values...`; a period's list stays in force until
+    the next PERIOD block (BoundaryPackage bnd_rp)
+Anything outside the supported subset raises Mf6InputError naming the keyword -- nothing is ignored silently
+except print/format options that do not change results.
+"""
+import os
+import shlex
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import ctypes_types as T
+from .grid import Package, build_dis_model
+
+
+class Mf6InputError(ValueError):
+    pass
+
+
+# ---- block-file tokeniser -----------------------------------------------------------------------
+def _tokens(line):
+    s = line.strip()
+    if not s or s[0] in "#!" or s.startswith("//"):
+        return []
+    lex = shlex.shlex(s.replace(",", " "), posix=True)
+    lex.whitespace_split = True
+    lex.commenters = "#"
+    return list(lex)
+
+
+def read_blocks(path):
+    """-> list of (NAME, number or None, [token lists])"""
+    if not os.path.exists(path):
+        raise Mf6InputError(f"input file not found: {path}")
+    blocks, cur = [], None
+    with open(path) as f:
+        for raw in f:
+            t = _tokens(raw)
+            if not t:
+                continue
+            k = t[0].upper()
+            if k == "BEGIN":
+                if cur is not None:
+                    raise Mf6InputError(f"{path}: BEGIN {t[1]} inside block {cur[0]}")
+                num = int(t[2]) if len(t) > 2 and t[2].lstrip("-").isdigit() else None
+                cur = (t[1].upper(), num, [])
+            elif k == "END":
+                if cur is None or cur[0] != t[1].upper():
+                    raise Mf6InputError(f"{path}: END {t[1]} does not close a block")
+                blocks.append(cur)
+                cur = None
+            elif cur is not None:
+                cur[2].append(t)
+            else:
+                raise Mf6InputError(f"{path}: text outside a block: {raw.strip()}")
+    if cur is not None:
+        raise Mf6InputError(f"{path}: block {cur[0]} is not closed")
+    return blocks
+
+
+def _block(blocks, name, required=True):
+    for b in blocks:
+        if b[0] == name:
+            return b[2]
+    if required:
+        raise Mf6InputError(f"block {name} is missing")
+    return []
+
+
+def _options(lines):
+    return {ln[0].upper(): ln[1:] for ln in lines}
+
+
+# ---- READARRAY ----------------------------------------------------------------------------------
+class _ArrayReader:
+    def __init__(self, lines, base_dir):
+        self.lines, self.pos, self.dir = lines, 0, base_dir
+
+    def more(self):
+        return self.pos < len(self.lines)
+
+    def name_line(self):
+        ln = self.lines[self.pos]
+        self.pos += 1
+        return ln[0].upper(), (len(ln) > 1 and ln[1].upper() == "LAYERED")
+
+    def _one(self, n, dtype):
+        ctl = self.lines[self.pos]
+        self.pos += 1
+        key = ctl[0].upper()
+        conv = float if dtype == np.float64 else (lambda s: int(float(s)))
+        if key == "CONSTANT":
+            return np.full(n, conv(ctl[1]), dtype=dtype)
+        factor = 1.0
+        up = [c.upper() for c in ctl]
+        if "FACTOR" in up:
+            factor = float(ctl[up.index("FACTOR") + 1])
+        if key == "INTERNAL":
+            vals = []
+            while len(vals) < n:
+                if self.pos >= len(self.lines):
+                    raise Mf6InputError("INTERNAL array is shorter than the grid")
+                vals += self.lines[self.pos]
+                self.pos += 1
+            a = np.array([float(v) for v in vals[:n]])
+        elif key == "OPEN/CLOSE":
+            fn = os.path.join(self.dir, ctl[1])
+            if "(BINARY)" in up:
+                raise Mf6InputError("OPEN/CLOSE (BINARY) arrays are not supported")
+            a = np.loadtxt(fn).reshape(-1)[:n].astype(np.float64)
+        else:
+            raise Mf6InputError(f"array control record {ctl[0]} is not supported")
+        a = a * factor
+        return a.astype(dtype) if dtype != np.float64 else a
+
+    def read(self, shape, layered, dtype=np.float64):
+        n = int(np.prod(shape))
+        if layered and len(shape) == 3:
+            per = shape[1] * shape[2]
+            return np.concatenate([self._one(per, dtype) for _ in range(shape[0])])
+        return self._one(n, dtype)
+
+
+def read_griddata(lines, base_dir, spec):
+    """spec: NAME -> (shape, dtype).  -> dict NAME -> flat array"""
+    rd, out = _ArrayReader(lines, base_dir), {}
+    while rd.more():
+        name, layered = rd.name_line()
+        if name not in spec:
+            raise Mf6InputError(f"GRIDDATA array {name} is not supported on the GPU path")
+        shape, dtype = spec[name]
+        out[name] = rd.read(shape, layered, dtype)
+    return out
+
+
+# ---- simulation objects ---------------------------------------------------------------------------
+@dataclass
+class StressPackage:
+    ftype: str
+    name: str
+    periods: dict            # iper (1-based) -> Package or None (empty period block)
+    iflowred: int = 0
+    flowred: float = 0.1
+
+
+@dataclass
+class GwfInput:
+    name: str
+    model: object            # grid.GwfModel
+    shape: tuple
+    packages: list = field(default_factory=list)      # [StressPackage]
+    sto_transient: dict = field(default_factory=dict)  # iper -> bool (True = TRANSIENT)
+    head_file: str = None
+    budget_file: str = None
+    save: dict = field(default_factory=dict)          # iper -> list of (rtype, ocsetting tokens)
+
+
+@dataclass
+class Simulation:
+    base_dir: str
+    nper: int
+    perioddata: list         # [(perlen, nstp, tsmult)]
+    models: list             # [GwfInput]
+    exchanges: list          # dicts for grid.merge_models
+    sln: object
+    ims: object
+    warnings: list = field(default_factory=list)
+
+
+_PKG_TYPE = {"CHD6": T.PKG_CHD, "WEL6": T.PKG_WEL, "RIV6": T.PKG_RIV, "RCH6": T.PKG_RCH, "GHB6": T.PKG_GHB,
+             "DRN6": T.PKG_DRN}
+_PKG_NCOL = {"CHD6": 1, "WEL6": 1, "RIV6": 3, "RCH6": 1, "GHB6": 2, "DRN6": 2}
+
+
+def read_tdis(path):
+    b = read_blocks(path)
+    nper = int(_options(_block(b, "DIMENSIONS"))["NPER"][0])
+    pd = [(float(t[0]), int(t[1]), float(t[2])) for t in _block(b, "PERIODDATA")]
+    if len(pd) != nper:
+        raise Mf6InputError(f"{path}: PERIODDATA has {len(pd)} rows, NPER = {nper}")
+    return nper, pd
+
+
+def read_ims(path, warnings):
+    """IMS options -> (SlnSettings, ImsSettings).  Defaults and the COMPLEXITY presets follow
+    NumericalSolution.f90:568-866 / sln_set_defaults and ImsLinearSettings.f90:120-253 (preset_config)."""
+    b = read_blocks(path)
+    opt = _options(_block(b, "OPTIONS", required=False))
+    nl = _options(_block(b, "NONLINEAR", required=False))
+    li = _options(_block(b, "LINEAR", required=False))
+    cx = (opt.get("COMPLEXITY", ["SIMPLE"])[0]).upper()
+    if cx not in ("SIMPLE", "MODERATE", "COMPLEX"):
+        raise Mf6InputError(f"{path}: unknown COMPLEXITY {cx}")
+    # presets: sln_setouter (NumericalSolution.f90:2623-2671), preset_config (ImsLinearSettings.f90:74-116)
+    ci = ("SIMPLE", "MODERATE", "COMPLEX").index(cx)
+    sln = dict(dvclose=(1e-3, 1e-2, 1e-1)[ci], mxiter=(25, 50, 100)[ci], nonmeth=(0, 3, 3)[ci],
+               theta=(1.0, 0.9, 0.8)[ci], akappa=(0.0, 1e-4, 1e-4)[ci], gamma=(1.0, 0.0, 0.0)[ci], amomentum=0.0,
+               numtrack=(0, 0, 20)[ci], btol=(0.0, 0.0, 1.05)[ci], breduc=(0.0, 0.0, 0.1)[ci],
+               res_lim=(0.0, 0.0, 0.002)[ci])
+    ims = dict(iter1=(50, 100, 500)[ci], ilinmeth=(1, 2, 2)[ci], dvclose=(1e-3, 1e-2, 1e-1)[ci], rclose=1e-1,
+               relax=(0.0, 0.97, 0.0)[ci], level=(0, 0, 5)[ci], droptol=(0.0, 0.0, 1e-4)[ci], north=(0, 0, 2)[ci],
+               iscl=0, iord=0, icnvgopt=0)
+    iallowptc = 1
+    if "NO_PTC" in opt:
+        v = opt["NO_PTC"]
+        iallowptc = -1 if (v and v[0].upper() == "FIRST") else 0
+    ur = {"NONE": 0, "SIMPLE": 1, "COOLEY": 2, "DBD": 3}
+    for k, v in nl.items():
+        if k in ("OUTER_DVCLOSE", "OUTER_HCLOSE"):
+            sln["dvclose"] = float(v[0])
+        elif k == "OUTER_MAXIMUM":
+            sln["mxiter"] = int(v[0])
+        elif k == "UNDER_RELAXATION":
+            sln["nonmeth"] = ur[v[0].upper()]
+        elif k == "UNDER_RELAXATION_THETA":
+            sln["theta"] = float(v[0])
+        elif k == "UNDER_RELAXATION_KAPPA":
+            sln["akappa"] = float(v[0])
+        elif k == "UNDER_RELAXATION_GAMMA":
+            sln["gamma"] = float(v[0])
+        elif k == "UNDER_RELAXATION_MOMENTUM":
+            sln["amomentum"] = float(v[0])
+        elif k == "BACKTRACKING_NUMBER":
+            sln["numtrack"] = int(v[0])
+        elif k == "BACKTRACKING_TOLERANCE":
+            sln["btol"] = float(v[0])
+        elif k == "BACKTRACKING_REDUCTION_FACTOR":
+            sln["breduc"] = float(v[0])
+        elif k == "BACKTRACKING_RESIDUAL_LIMIT":
+            sln["res_lim"] = float(v[0])
+        elif k == "OUTER_RCLOSEBND":
+            warnings.append("OUTER_RCLOSEBND is deprecated and ignored (as in the reference)")
+        else:
+            raise Mf6InputError(f"{path}: NONLINEAR option {k} is not supported")
+    rc = {"STRICT": 1, "L2NORM_RCLOSE": 2, "RELATIVE_RCLOSE": 3, "L2NORM_RELATIVE_RCLOSE": 4}
+    for k, v in li.items():
+        if k == "INNER_MAXIMUM":
+            ims["iter1"] = int(v[0])
+        elif k in ("INNER_DVCLOSE", "INNER_HCLOSE"):
+            ims["dvclose"] = float(v[0])
+        elif k == "INNER_RCLOSE":
+            ims["rclose"] = float(v[0])
+            if len(v) > 1:
+                ims["icnvgopt"] = rc[v[1].upper()]
+        elif k == "LINEAR_ACCELERATION":
+            ims["ilinmeth"] = {"CG": 1, "BICGSTAB": 2}[v[0].upper()]
+        elif k == "RELAXATION_FACTOR":
+            ims["relax"] = float(v[0])
+        elif k == "PRECONDITIONER_LEVELS":
+            ims["level"] = int(v[0])
+        elif k == "PRECONDITIONER_DROP_TOLERANCE":
+            ims["droptol"] = float(v[0])
+        elif k == "NUMBER_ORTHOGONALIZATIONS":
+            ims["north"] = int(v[0])
+        elif k == "SCALING_METHOD":
+            ims["iscl"] = {"NONE": 0, "DIAGONAL": 1, "L2NORM": 2}[v[0].upper()]
+        elif k == "REORDERING_METHOD":
+            ims["iord"] = {"NONE": 0, "RCM": 1, "MD": 2}[v[0].upper()]
+        else:
+            raise Mf6InputError(f"{path}: LINEAR option {k} is not supported")
+    # the policy of petsc_check_settings (PetscSolver.F90:123-154): what the backend cannot honour is
+    # downgraded with a warning the caller can print
+    if ims["level"] > 0 or ims["droptol"] > 0.0:
+        warnings.append("PRECONDITIONER_LEVELS / DROP_TOLERANCE (ILUT) are not available on the GPU path: "
+                        "ILU0/MILU0 is used instead")
+        ims["level"], ims["droptol"] = 0, 0.0
+    if ims["iord"] != 0:
+        warnings.append("REORDERING_METHOD is replaced by the GPU level ordering")
+        ims["iord"] = 0
+    return T.SlnSettings.make(iallowptc=iallowptc, **sln), T.ImsSettings.make(**ims)
+
+
+def _cellid(tokens, shape):
+    if len(shape) == 3:
+        k, i, j = int(tokens[0]) - 1, int(tokens[1]) - 1, int(tokens[2]) - 1
+        if not (0 <= k < shape[0] and 0 <= i < shape[1] and 0 <= j < shape[2]):
+            raise Mf6InputError(f"cellid {tokens[:3]} outside the grid {shape}")
+        return (k * shape[1] + i) * shape[2] + j, 3
+    raise Mf6InputError("only DIS cellids are supported")
+
+
+def read_stress_package(path, ftype, name, shape):
+    b = read_blocks(path)
+    opt = _options(_block(b, "OPTIONS", required=False))
+    naux = len(opt.get("AUXILIARY", opt.get("AUX", [])))
+    for k in opt:
+        if k in ("READASARRAYS", "TS6", "TAS6", "MOVER", "AUXMULTNAME"):
+            raise Mf6InputError(f"{path}: option {k} is not supported on the GPU path")
+    iflowred, flowred = 0, 0.1
+    if "AUTO_FLOW_REDUCE" in opt:
+        iflowred, flowred = 1, float(opt["AUTO_FLOW_REDUCE"][0]) if opt["AUTO_FLOW_REDUCE"] else 0.1
+    ncol = _PKG_NCOL[ftype]
+    periods = {}
+    for nm, num, lines in b:
+        if nm != "PERIOD":
+            continue
+        nodes, vals = [], []
+        for t in lines:
+            node, w = _cellid(t, shape)
+            nodes.append(node)
+            vals.append([float(v) for v in t[w:w + ncol]])
+        if nodes:
+            v = np.array(vals)
+            cols = [v[:, c] if c < ncol else None for c in range(3)]
+            periods[num] = Package(_PKG_TYPE[ftype], np.array(nodes), cols[0], cols[1], cols[2], iflowred=iflowred,
+                                   flowred=flowred)
+        else:
+            periods[num] = None
+    return StressPackage(ftype[:-1], name, periods, iflowred, flowred), naux
+
+
+def read_gwf_model(name, nam_path, base_dir, warnings):
+    b = read_blocks(nam_path)
+    opt = _options(_block(b, "OPTIONS", required=False))
+    inewton = 1 if "NEWTON" in opt else 0
+    inewtonur = 1 if inewton and opt["NEWTON"] and opt["NEWTON"][0].upper() == "UNDER_RELAXATION" else 0
+    files = {}
+    stress = []
+    for t in _block(b, "PACKAGES"):
+        ft = t[0].upper()
+        fn = os.path.join(base_dir, t[1])
+        pn = t[2] if len(t) > 2 else None
+        if ft in _PKG_TYPE:
+            stress.append((ft, fn, pn))
+        elif ft in ("DIS6", "IC6", "NPF6", "STO6", "OC6"):
+            files[ft] = fn
+        else:
+            raise Mf6InputError(f"{nam_path}: package {ft} is outside the GPU path (SURVEY.md section 8)")
+    for need in ("DIS6", "IC6", "NPF6"):
+        if need not in files:
+            raise Mf6InputError(f"{nam_path}: {need} package is required")
+    # DIS
+    d = read_blocks(files["DIS6"])
+    dim = _options(_block(d, "DIMENSIONS"))
+    nlay, nrow, ncol = int(dim["NLAY"][0]), int(dim["NROW"][0]), int(dim["NCOL"][0])
+    shape = (nlay, nrow, ncol)
+    g = read_griddata(_block(d, "GRIDDATA"), base_dir,
+                      {"DELR": ((ncol,), np.float64), "DELC": ((nrow,), np.float64), "TOP": ((nrow, ncol), np.float64),
+                       "BOTM": (shape, np.float64), "IDOMAIN": (shape, np.int32)})
+    # IC / NPF / STO
+    ic = read_griddata(_block(read_blocks(files["IC6"]), "GRIDDATA"), base_dir, {"STRT": (shape, np.float64)})
+    nb = read_blocks(files["NPF6"])
+    nopt = _options(_block(nb, "OPTIONS", required=False))
+    for k in nopt:
+        if k in ("THICKSTRT", "XT3D", "REWET", "TVK6", "K22OVERK", "K33OVERK"):
+            raise Mf6InputError(f"NPF option {k} is not supported on the GPU path")
+    np_ = read_griddata(_block(nb, "GRIDDATA"), base_dir,
+                        {"ICELLTYPE": (shape, np.int32), "K": (shape, np.float64), "K22": (shape, np.float64),
+                         "K33": (shape, np.float64)})
+    if "K22" in np_ and not np.array_equal(np_["K22"], np_["K"]):
+        raise Mf6InputError("NPF K22 anisotropy is not supported on the GPU path")
+    kw = {}
+    avg = {"LOGARITHMIC": 1, "AMT-LMK": 2, "AMT-HMK": 3}
+    if "ALTERNATIVE_CELL_AVERAGING" in nopt:
+        kw["icellavg"] = avg[nopt["ALTERNATIVE_CELL_AVERAGING"][0].upper()]
+    if "PERCHED" in nopt:
+        kw["iperched"] = 1
+    if "VARIABLECV" in nopt:
+        kw["ivarcv"] = 1
+        if nopt["VARIABLECV"] and nopt["VARIABLECV"][0].upper() == "DEWATERED":
+            kw["idewatcv"] = 1
+    sto = {}
+    sto_tr = {}
+    if "STO6" in files:
+        sb = read_blocks(files["STO6"])
+        sopt = _options(_block(sb, "OPTIONS", required=False))
+        sto = read_griddata(_block(sb, "GRIDDATA"), base_dir,
+                            {"ICONVERT": (shape, np.int32), "SS": (shape, np.float64), "SY": (shape, np.float64)})
+        if "STORAGECOEFFICIENT" in sopt:
+            kw["istor_coef"] = 1
+        if "SS_CONFINED_ONLY" in sopt:
+            kw["iconf_ss"] = 1
+        for nm, num, lines in sb:
+            if nm == "PERIOD":
+                key = lines[0][0].upper() if lines else "STEADY-STATE"
+                sto_tr[num] = (key == "TRANSIENT")
+    top = g["TOP"].reshape(nrow, ncol)
+    botm = g["BOTM"].reshape(shape)
+    m = build_dis_model(nlay, nrow, ncol, g["DELR"], g["DELC"], top, botm, np_["K"].reshape(shape),
+                        k33=np_["K33"].reshape(shape) if "K33" in np_ else None,
+                        icelltype=np_["ICELLTYPE"].reshape(shape), strt=ic["STRT"].reshape(shape),
+                        ss=sto["SS"].reshape(shape) if "SS" in sto else None,
+                        sy=sto["SY"].reshape(shape) if "SY" in sto else None,
+                        iconvert=sto["ICONVERT"].reshape(shape) if "ICONVERT" in sto else None,
+                        inewton=inewton, inewtonur=inewtonur, **kw)
+    if "IDOMAIN" in g:
+        if (g["IDOMAIN"] < 0).any():
+            raise Mf6InputError("IDOMAIN < 0 (vertical pass-through cells) is not supported on the GPU path")
+        m.ibound = np.where(g["IDOMAIN"] > 0, 1, 0).astype(np.int32)
+    gi = GwfInput(name=name, model=m, shape=shape, sto_transient=sto_tr)
+    count = {}
+    for ft, fn, pn in stress:
+        count[ft] = count.get(ft, 0) + 1
+        sp, _ = read_stress_package(fn, ft, pn or f"{ft[:-1]}-{count[ft]}", shape)
+        gi.packages.append(sp)
+    if "OC6" in files:
+        ob = read_blocks(files["OC6"])
+        oopt = _block(ob, "OPTIONS", required=False)
+        for t in oopt:
+            if t[0].upper() == "HEAD" and t[1].upper() == "FILEOUT":
+                gi.head_file = os.path.join(base_dir, t[2])
+            elif t[0].upper() == "BUDGET" and t[1].upper() == "FILEOUT":
+                gi.budget_file = os.path.join(base_dir, t[2])
+        for nm, num, lines in ob:
+            if nm == "PERIOD":
+                gi.save[num] = [(t[1].upper(), [x.upper() for x in t[2:]]) for t in lines if t[0].upper() == "SAVE"]
+    return gi
+
+
+def read_exchange(path, m1, m2, shape1, shape2):
+    b = read_blocks(path)
+    opt = _options(_block(b, "OPTIONS", required=False))
+    for k in opt:
+        if k in ("GNC6", "MVR6", "XT3D", "CELL_AVERAGING", "VARIABLECV", "DEWATERED"):
+            raise Mf6InputError(f"{path}: exchange option {k} is not supported on the GPU path")
+    n1, n2, ihc, cl1, cl2, hw = [], [], [], [], [], []
+    for t in _block(b, "EXCHANGEDATA"):
+        a, w = _cellid(t, shape1)
+        c, w2 = _cellid(t[w:], shape2)
+        r = t[w + w2:]
+        n1.append(a); n2.append(c)
+        ihc.append(int(r[0])); cl1.append(float(r[1])); cl2.append(float(r[2])); hw.append(float(r[3]))
+    return dict(m1=m1, m2=m2, nodem1=np.array(n1), nodem2=np.array(n2), ihc=np.array(ihc, dtype=np.int32),
+                cl1=np.array(cl1), cl2=np.array(cl2), hwva=np.array(hw))
+
+
+def read_simulation(sim_dir):
+    """mfsim.nam and everything it names (src/SimulationCreate.f90 order: timing, models, exchanges, solutions)"""
+    sim_dir = os.path.abspath(sim_dir)
+    b = read_blocks(os.path.join(sim_dir, "mfsim.nam"))
+    warnings = []
+    tim = _block(b, "TIMING")
+    nper, pd = read_tdis(os.path.join(sim_dir, tim[0][1]))
+    models, index = [], {}
+    for t in _block(b, "MODELS"):
+        if t[0].upper() != "GWF6":
+            raise Mf6InputError(f"model type {t[0]} is outside the GPU path (GWF6 only)")
+        index[t[2].upper()] = len(models)
+        models.append(read_gwf_model(t[2], os.path.join(sim_dir, t[1]), sim_dir, warnings))
+    exchanges = []
+    for t in _block(b, "EXCHANGES", required=False):
+        if t[0].upper() != "GWF6-GWF6":
+            raise Mf6InputError(f"exchange type {t[0]} is outside the GPU path")
+        i1, i2 = index[t[2].upper()], index[t[3].upper()]
+        exchanges.append(read_exchange(os.path.join(sim_dir, t[1]), i1, i2, models[i1].shape, models[i2].shape))
+    sg = [x for x in b if x[0] == "SOLUTIONGROUP"]
+    if len(sg) != 1 or len(sg[0][2]) != 1 or sg[0][2][0][0].upper() != "IMS6":
+        raise Mf6InputError("exactly one solution group with one IMS6 solution is supported")
+    sl = sg[0][2][0]
+    if sorted(x.upper() for x in sl[2:]) != sorted(index):
+        raise Mf6InputError("every model must belong to the one IMS solution")
+    sln, ims = read_ims(os.path.join(sim_dir, sl[1]), warnings)
+    return Simulation(sim_dir, nper, pd, models, exchanges, sln, ims, warnings)

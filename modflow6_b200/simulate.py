@@ -1,0 +1,139 @@
+"""Run a MODFLOW 6 simulation directory through the accelerated path: the time loop of
+`Mf6DoTimestep` (src/mf6core.f90:620-660) around `mf6gpu_solution_timestep`, with the input subset read by
+`mf6io.py` and heads / budgets written in the reference's binary formats by `output.py`.
+
+    python -m modflow6_b200.simulate <simulation directory> [--ordering block|multicolor|natural]
+
+There is no CPU fallback: without a GPU the solution object cannot be created and the run fails.  (`run` takes
+the solution class as a parameter so that the tests can drive the same reader / time loop / writers with the
+CPU oracle and check them against the reference's known answers.)
+"""
+import argparse
+import json
+import sys
+
+import numpy as np
+
+from . import ctypes_types as T
+from .grid import Package, merge_models, tdis_steps
+from .mf6io import read_simulation
+from .output import BudgetFileWriter, HeadFileWriter
+
+DHNOFLO = 1.0e30   # Constants.f90: head written for cells outside the active domain
+
+
+def _should_save(settings, kstp, nstp):
+    """OC `SAVE <rtype> <ocsetting>`: ALL | FIRST | LAST | FREQUENCY n | STEPS n1 n2 ... (gwf-oc.dfn)"""
+    for s in settings:
+        if not s or s[0] == "ALL":
+            return True
+        if s[0] == "FIRST" and kstp == 1:
+            return True
+        if s[0] == "LAST" and kstp == nstp:
+            return True
+        if s[0] == "FREQUENCY" and int(s[1]) > 0 and kstp % int(s[1]) == 0:
+            return True
+        if s[0] == "STEPS" and kstp in [int(v) for v in s[1:]]:
+            return True
+    return False
+
+
+def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None, solution_class=None):
+    """solution_class(model, sln_settings, ims_settings) -> object with set_packages / timestep / x / flowja /
+    simvals / storage_rates; default GpuNumericalSolution"""
+    sim = read_simulation(sim_dir)
+    log = log or (lambda *a: None)
+    for w in sim.warnings:
+        log("warning:", w)
+    models = [gi.model for gi in sim.models]
+    if len(models) == 1 and not sim.exchanges:
+        model, offs = models[0], np.array([0, models[0].nodes])
+    else:
+        model, offs = merge_models(models, sim.exchanges)
+    sim.ims.gpu_ordering = ordering
+    if solution_class is None:
+        from .solution import GpuNumericalSolution as solution_class
+    S = solution_class(model, sim.sln, sim.ims)
+    writers = []
+    for k, gi in enumerate(sim.models):
+        hw = HeadFileWriter(gi.head_file, gi.shape) if (write_output and gi.head_file) else None
+        bw = None
+        if write_output and gi.budget_file:
+            if len(models) > 1:
+                log(f"warning: {gi.name}: budget files are written for single-model simulations only")
+            else:
+                bw = BudgetFileWriter(gi.budget_file, gi.shape, gi.name)
+        writers.append((hw, bw))
+    current = [[None] * len(gi.packages) for gi in sim.models]     # list in force per package
+    saving = [dict() for _ in sim.models]                          # rtype -> settings in force
+    reports, totim = [], 0.0
+    for kper in range(1, sim.nper + 1):
+        perlen, nstp, tsmult = sim.perioddata[kper - 1]
+        pkgs, owner = [], []
+        for k, gi in enumerate(sim.models):
+            for ip, sp in enumerate(gi.packages):
+                if kper in sp.periods:
+                    current[k][ip] = sp.periods[kper]
+                p = current[k][ip]
+                if p is not None:
+                    pkgs.append(Package(p.type, p.nodelist + int(offs[k]), p.b1, p.b2, p.b3, iflowred=p.iflowred,
+                                        flowred=p.flowred))
+                    owner.append((k, ip))
+            if kper in gi.save:
+                saving[k] = {}
+                for rtype, st in gi.save[kper]:
+                    saving[k].setdefault(rtype, []).append(st)
+        # a model without STO is steady; with STO the period keeps the last STEADY-STATE / TRANSIENT keyword,
+        # TRANSIENT before any PERIOD block (gwf-sto.f90:170-182, 756)
+        iss = 1
+        for gi in sim.models:
+            if gi.model.insto:
+                upto = [p for p in gi.sto_transient if p <= kper]
+                iss = 0 if (not upto or gi.sto_transient[max(upto)]) else 1
+        S.set_packages(pkgs)
+        pertim = 0.0
+        for kstp, delt in enumerate(tdis_steps(perlen, nstp, tsmult), start=1):
+            rep = S.timestep(kper, kstp, delt, iss)
+            pertim += delt
+            totim += delt
+            d = rep.as_dict()
+            d.update(kper=kper, kstp=kstp, delt=delt, totim=totim)
+            reports.append(d)
+            log(f"period {kper} step {kstp}: outer {d['outer_iterations']} inner {d['inner_iterations']} "
+                f"converged {d['converged']} budget discrepancy {d['pdiffr']:.3e} %")
+            x = S.x
+            for k, gi in enumerate(sim.models):
+                hw, bw = writers[k]
+                if hw and _should_save(saving[k].get("HEAD", []), kstp, nstp):
+                    h = x[offs[k]:offs[k] + gi.model.nodes].copy()
+                    h[gi.model.ibound == 0] = DHNOFLO
+                    hw.write(kstp, kper, pertim, totim, h)
+                if bw and _should_save(saving[k].get("BUDGET", []), kstp, nstp):   # single-model simulation
+                    bw.write_step(kstp, kper, delt, pertim, totim, S, pkgs,
+                                  [gi.packages[ip].name for _, ip in owner])
+    for hw, bw in writers:
+        if hw:
+            hw.close()
+        if bw:
+            bw.close()
+    heads = [S.x[offs[k]:offs[k] + gi.model.nodes].reshape(gi.shape) for k, gi in enumerate(sim.models)]
+    return dict(simulation=sim, reports=reports, heads=heads, solution=S)
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description=__doc__.splitlines()[0])
+    ap.add_argument("sim_dir")
+    ap.add_argument("--ordering", default="block", choices=["natural", "multicolor", "block"])
+    a = ap.parse_args(argv)
+    o = {"natural": T.ORDER_NATURAL, "multicolor": T.ORDER_MULTICOLOR, "block": T.ORDER_BLOCK_MULTICOLOR}[a.ordering]
+    out = run(a.sim_dir, o, log=lambda *s: print(*s, file=sys.stderr))
+    ok = all(r["converged"] for r in out["reports"])
+    print(json.dumps({"steps": len(out["reports"]), "converged": bool(ok),
+                      "inner_iterations": int(sum(r["inner_iterations"] for r in out["reports"])),
+                      "head_min": float(min(h.min() for h in out["heads"])),
+                      "head_max": float(max(h.max() for h in out["heads"]))}))
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,125 @@
+"""Writers of small MODFLOW 6 input decks for the reader tests (what FloPy would write; the layout follows
+the reference's `.mf6minsim/` example and doc/mf6io).  Only test infrastructure."""
+import os
+
+import numpy as np
+
+
+def _w(path, text):
+    with open(path, "w") as f:
+        f.write("# written by tests/mf6_inputs.py\n" + text)
+
+
+def _arr(name, a, layered=False):
+    """READARRAY text: CONSTANT when uniform; LAYERED -> one control record per layer (a[k] scalar or 2-D)"""
+    if layered:
+        s = f"  {name} LAYERED\n"
+        for ak in a:
+            ak = np.asarray(ak, dtype=float)
+            if ak.ndim == 0 or np.all(ak == ak.reshape(-1)[0]):
+                s += f"    CONSTANT  {float(ak.reshape(-1)[0])!r}\n"
+            else:
+                s += "    INTERNAL FACTOR 1.0\n" + "\n".join("      " + " ".join(repr(float(v)) for v in row)
+                                                           for row in ak) + "\n"
+        return s
+    a = np.asarray(a)
+    if a.ndim == 0 or np.all(a == a.reshape(-1)[0]):
+        return f"  {name}\n    CONSTANT  {a.reshape(-1)[0]}\n"
+    return f"  {name}\n    INTERNAL FACTOR 1.0 IPRN 0\n" + "\n".join(
+        "      " + " ".join(repr(float(v)) for v in row) for row in a.reshape(-1, a.shape[-1])) + "\n"
+
+
+def write_gwf(d, name, shape, delr, delc, top, botm, k, chd=None, wel=None, icelltype=0, strt=0.0, k33=None,
+              sto=None, oc=True, newton=False, extra_periods=None):
+    """chd / wel: dict iper -> list of ((k,i,j), value) with 1-based cellids"""
+    nlay, nrow, ncol = shape
+    pk = f"  DIS6  {name}.dis  dis\n  IC6  {name}.ic  ic\n  NPF6  {name}.npf  npf\n"
+    _w(os.path.join(d, f"{name}.dis"),
+       f"BEGIN options\nEND options\n\nBEGIN dimensions\n  NLAY {nlay}\n  NROW {nrow}\n  NCOL {ncol}\nEND dimensions\n\n"
+       "BEGIN griddata\n" + _arr("delr", delr) + _arr("delc", delc) + _arr("top", top)
+       + _arr("botm", botm, layered=np.ndim(botm) > 0)
+       + "END griddata\n")
+    _w(os.path.join(d, f"{name}.ic"), "BEGIN griddata\n" + _arr("strt", strt) + "END griddata\n")
+    npf = "BEGIN options\n  SAVE_FLOWS\nEND options\n\nBEGIN griddata\n" + _arr("icelltype", icelltype) \
+        + _arr("k", np.asarray(k, dtype=float).reshape(shape) if np.ndim(k) else k, layered=np.ndim(k) > 0)
+    if k33 is not None:
+        npf += _arr("k33", k33)
+    _w(os.path.join(d, f"{name}.npf"), npf + "END griddata\n")
+    if sto:
+        pk += f"  STO6  {name}.sto  sto\n"
+        s = "BEGIN options\nEND options\n\nBEGIN griddata\n" + _arr("iconvert", sto.get("iconvert", 0)) \
+            + _arr("ss", sto["ss"]) + _arr("sy", sto.get("sy", 0.0)) + "END griddata\n\n"
+        for iper, key in sorted(sto["periods"].items()):
+            s += f"BEGIN period {iper}\n  {key}\nEND period {iper}\n\n"
+        _w(os.path.join(d, f"{name}.sto"), s)
+    for ft, spd in (("CHD", chd), ("WEL", wel)):
+        if not spd:
+            continue
+        pk += f"  {ft}6  {name}.{ft.lower()}  {ft.lower()}_0\n"
+        s = f"BEGIN options\nEND options\n\nBEGIN dimensions\n  MAXBOUND  {max(len(v) for v in spd.values())}\nEND dimensions\n\n"
+        for iper, rows in sorted(spd.items()):
+            s += f"BEGIN period  {iper}\n" + "".join(f"  {c[0]} {c[1]} {c[2]}  {v!r}\n" for c, v in rows) \
+                + f"END period  {iper}\n\n"
+        _w(os.path.join(d, f"{name}.{ft.lower()}"), s)
+    if oc:
+        pk += f"  OC6  {name}.oc  oc\n"
+        _w(os.path.join(d, f"{name}.oc"),
+           f"BEGIN options\n  HEAD FILEOUT {name}.hds\n  BUDGET FILEOUT {name}.cbc\nEND options\n\n"
+           "BEGIN period 1\n  SAVE HEAD ALL\n  SAVE BUDGET LAST\n  PRINT HEAD LAST\nEND period 1\n")
+    _w(os.path.join(d, f"{name}.nam"),
+       "BEGIN options\n" + ("  NEWTON UNDER_RELAXATION\n" if newton else "") + "END options\n\nBEGIN packages\n" + pk
+       + "END packages\n")
+
+
+def write_sim(d, models, perioddata, ims_text, exchanges=()):
+    """models: [name]; exchanges: [(file stem, m1, m2, rows)] with rows = (cellid1, cellid2, ihc, cl1, cl2, hwva)"""
+    _w(os.path.join(d, "sim.tdis"),
+       f"BEGIN options\n  TIME_UNITS days\nEND options\n\nBEGIN dimensions\n  NPER {len(perioddata)}\nEND dimensions\n\n"
+       "BEGIN perioddata\n" + "".join(f"  {p[0]!r}  {p[1]}  {p[2]!r}\n" for p in perioddata) + "END perioddata\n")
+    _w(os.path.join(d, "sim.ims"), ims_text)
+    ex = ""
+    for stem, m1, m2, rows in exchanges:
+        ex += f"  GWF6-GWF6  {stem}.gwfgwf  {m1}  {m2}\n"
+        _w(os.path.join(d, f"{stem}.gwfgwf"),
+           f"BEGIN options\n  AUXILIARY ANGLDEGX CDIST\nEND options\n\nBEGIN dimensions\n  NEXG {len(rows)}\nEND dimensions\n\n"
+           "BEGIN exchangedata\n" + "".join(
+               f"  {a[0]} {a[1]} {a[2]}  {b[0]} {b[1]} {b[2]}  {ihc}  {c1!r}  {c2!r}  {hw!r}  0.0  {c1 + c2!r}\n"
+               for a, b, ihc, c1, c2, hw in rows) + "END exchangedata\n")
+    _w(os.path.join(d, "mfsim.nam"),
+       "BEGIN options\nEND options\n\nBEGIN timing\n  TDIS6  sim.tdis\nEND timing\n\nBEGIN models\n"
+       + "".join(f"  gwf6  {m}.nam  {m}\n" for m in models) + "END models\n\nBEGIN exchanges\n" + ex
+       + "END exchanges\n\nBEGIN solutiongroup  1\n  ims6  sim.ims  " + "  ".join(models) + "\nEND solutiongroup  1\n")
+
+
+IMS_PAR_GWF01 = """BEGIN options
+  PRINT_OPTION  all
+END options
+
+BEGIN nonlinear
+  OUTER_DVCLOSE  1.0E-08
+  OUTER_MAXIMUM  100
+  UNDER_RELAXATION  dbd
+END nonlinear
+
+BEGIN linear
+  INNER_MAXIMUM  300
+  INNER_DVCLOSE  1.0E-08
+  inner_rclose   0.001
+  LINEAR_ACCELERATION  bicgstab
+  RELAXATION_FACTOR    0.97
+END linear
+"""
+
+
+def write_par_gwf01(d, shape):
+    """autotest/test_par_gwf01.py: two models of `shape` side by side, CHD 1.0 on the left edge, 10.0 on the
+    right edge, K = 1, confined; known answer: heads 1, 2, ..., 10 along the columns"""
+    nlay, nrow, ncol = shape
+    botm = [-100.0 * (k + 1) for k in range(nlay)]
+    left = [((k + 1, i + 1, 1), 1.0) for k in range(nlay) for i in range(nrow)]
+    right = [((k + 1, i + 1, ncol), 10.0) for k in range(nlay) for i in range(nrow)]
+    write_gwf(d, "leftmodel", shape, 100.0, 100.0, 0.0, botm, 1.0, chd={1: left})
+    write_gwf(d, "rightmodel", shape, 100.0, 100.0, 0.0, botm, 1.0, chd={1: right})
+    rows = [((k + 1, i + 1, ncol), (k + 1, i + 1, 1), 1, 50.0, 50.0, 100.0) for k in range(nlay) for i in range(nrow)]
+    write_sim(d, ["leftmodel", "rightmodel"], [(1.0, 1, 1.0)], IMS_PAR_GWF01,
+              exchanges=[("sim", "leftmodel", "rightmodel", rows)])

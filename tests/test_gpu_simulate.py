@@ -1,0 +1,54 @@
+"""MODFLOW 6 input decks run end to end on the device (reader -> mf6gpu_solution_* -> .hds / .cbc):
+the reference's known answers and the oracle run of the same deck.  Needs a B200: run with -m gpu."""
+import numpy as np
+import pytest
+
+from modflow6_b200 import ctypes_types as T
+from modflow6_b200 import simulate
+from modflow6_b200.output import read_budget_file, read_head_file
+from tests import mf6_inputs
+from tests.test_mf6io_cpu import oracle_class
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 5), (1, 5, 5), (5, 5, 5)])
+@pytest.mark.parametrize("ordering", [T.ORDER_NATURAL, T.ORDER_BLOCK_MULTICOLOR])
+def test_par_gwf01_on_device(gpu, tmp_path, shape, ordering):
+    """autotest/test_par_gwf01.py:200-212: heads 1..10 across two models coupled by a GWF-GWF exchange"""
+    mf6_inputs.write_par_gwf01(str(tmp_path), shape)
+    out = simulate.run(str(tmp_path), ordering=ordering)
+    assert all(r["converged"] for r in out["reports"])
+    for h, first in zip(out["heads"], (1.0, 6.0)):
+        np.testing.assert_array_almost_equal(h, np.broadcast_to(first + np.arange(5.0), shape))
+
+
+def test_transient_deck_device_vs_oracle(gpu, tmp_path):
+    rng = np.random.default_rng(7)
+    shape = (3, 12, 15)
+    k = np.exp(rng.normal(1.0, 0.8, shape))
+    chd = [((kk + 1, i + 1, 1), 12.0) for kk in range(3) for i in range(12)] + \
+          [((kk + 1, i + 1, 15), 8.0) for kk in range(3) for i in range(12)]
+    sto = dict(iconvert=0, ss=1e-4, sy=0.1, periods={1: "STEADY-STATE", 2: "TRANSIENT"})
+    ims = ("BEGIN nonlinear\n  OUTER_DVCLOSE 1e-6\n  OUTER_MAXIMUM 50\nEND nonlinear\n\n"
+           "BEGIN linear\n  INNER_MAXIMUM 200\n  INNER_DVCLOSE 1e-7\n  INNER_RCLOSE 1e-4\n  LINEAR_ACCELERATION CG\nEND linear\n")
+    for tag in ("gpu", "cpu"):
+        d = tmp_path / tag
+        d.mkdir()
+        mf6_inputs.write_gwf(str(d), "m", shape, 50.0, 40.0, 0.0, [-10.0, -25.0, -45.0], k, chd={1: chd},
+                             wel={2: [((2, 6, 8), -150.0)]}, sto=sto, strt=10.0, k33=0.5)
+        mf6_inputs.write_sim(str(d), ["m"], [(1.0, 1, 1.0), (30.0, 4, 1.3)], ims)
+    g = simulate.run(str(tmp_path / "gpu"), ordering=T.ORDER_NATURAL)
+    c = simulate.run(str(tmp_path / "cpu"), ordering=T.ORDER_NATURAL, solution_class=oracle_class())
+    assert len(g["reports"]) == len(c["reports"]) == 5
+    for a, b in zip(g["reports"], c["reports"]):
+        assert a["converged"] == b["converged"] == 1 and a["outer_iterations"] == b["outer_iterations"]
+        assert abs(a["pdiffr"] - b["pdiffr"]) <= 1e-3
+    assert np.abs(g["heads"][0] - c["heads"][0]).max() <= 0.1 * 1e-6
+    hg, hc = read_head_file(tmp_path / "gpu" / "m.hds"), read_head_file(tmp_path / "cpu" / "m.hds")
+    assert len(hg) == len(hc) == 15
+    bg, bc = read_budget_file(tmp_path / "gpu" / "m.cbc"), read_budget_file(tmp_path / "cpu" / "m.cbc")
+    assert [(r["text"], r["kper"], r["kstp"]) for r in bg] == [(r["text"], r["kper"], r["kstp"]) for r in bc]
+    for a, b in zip(bg, bc):
+        va, vb = (a["flow"], b["flow"]) if a["imeth"] == 1 else (a["q"], b["q"])
+        assert np.allclose(va, vb, rtol=1e-4, atol=1e-5 * max(1.0, np.abs(vb).max()))

@@ -1,0 +1,124 @@
+"""Input reader (modflow6_b200/mf6io.py) + time loop (simulate.py) + binary writers, driven with the CPU
+oracle as the solution class: the reference's own known answers reached from input FILES.
+
+  * autotest/test_par_gwf01.py:200-212 -- two models joined by a GWF-GWF exchange, heads 1..10 (1-D, 2-D, 3-D)
+  * autotest/test_gwf_chd01.py:126-127 -- heads == linspace(1, 0, 100)
+  * a transient deck (STO periods, WEL from period 2, heterogeneous K as INTERNAL arrays, OC) must give exactly
+    the heads of the same model assembled directly with grid.build_dis_model
+"""
+import numpy as np
+import pytest
+
+from modflow6_b200 import ctypes_types as T
+from modflow6_b200 import mf6io, simulate
+from modflow6_b200.grid import Package, build_dis_model, tdis_steps
+from modflow6_b200.output import read_budget_file, read_head_file
+from tests import mf6_inputs
+
+
+def oracle_class():
+    from oracle.oracle import OracleSolution
+    return OracleSolution
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 5), (1, 5, 5), (5, 5, 5)])
+def test_par_gwf01_known_answer(tmp_path, shape):
+    mf6_inputs.write_par_gwf01(str(tmp_path), shape)
+    out = simulate.run(str(tmp_path), ordering=T.ORDER_NATURAL, solution_class=oracle_class())
+    assert all(r["converged"] for r in out["reports"])
+    left, right = out["heads"]
+    for h, first in ((left, 1.0), (right, 6.0)):
+        want = np.broadcast_to(first + np.arange(5.0), shape)
+        np.testing.assert_array_almost_equal(h, want)          # 6 decimals, like the reference test
+    # both head files exist and hold one record per layer
+    recs = read_head_file(tmp_path / "leftmodel.hds")
+    assert len(recs) == shape[0] and recs[0]["ncol"] == 5 and recs[0]["nrow"] == shape[1]
+    np.testing.assert_array_almost_equal(recs[0]["data"][0], [1, 2, 3, 4, 5])
+
+
+def test_chd01_known_answer(tmp_path):
+    ims = ("BEGIN nonlinear\n  OUTER_DVCLOSE 1e-6\n  OUTER_MAXIMUM 100\n  UNDER_RELAXATION NONE\nEND nonlinear\n\n"
+           "BEGIN linear\n  INNER_MAXIMUM 300\n  INNER_DVCLOSE 1e-6\n  INNER_RCLOSE 1e-6\n  LINEAR_ACCELERATION CG\n"
+           "  SCALING_METHOD NONE\n  REORDERING_METHOD NONE\n  RELAXATION_FACTOR 1.0\nEND linear\n")
+    mf6_inputs.write_gwf(str(tmp_path), "gwf", (1, 1, 100), 1.0, 1.0, 1.0, [0.0], 1.0,
+                         chd={1: [((1, 1, 1), 1.0), ((1, 1, 100), 0.0)]}, strt=1.0)
+    mf6_inputs.write_sim(str(tmp_path), ["gwf"], [(5.0, 1, 1.0)], ims)
+    out = simulate.run(str(tmp_path), ordering=T.ORDER_NATURAL, solution_class=oracle_class())
+    assert np.allclose(out["heads"][0].ravel(), np.linspace(1, 0, 100))
+    sim = out["simulation"]
+    assert sim.ims.relax == 1.0 and sim.ims.ilinmeth == 1 and sim.sln.mxiter == 100
+    cbc = read_budget_file(tmp_path / "gwf.cbc")
+    assert [r["text"].strip() for r in cbc] == ["FLOW-JA-FACE", "CHD"]
+    assert cbc[1]["srcmodel"].strip() == "GWF" and cbc[1]["dstpackage"].strip() == "CHD_0"
+    q = cbc[1]["q"]
+    assert np.isclose(q[0], -q[1]) and np.isclose(q[0], 1.0 / 99.0)     # Darcy: K dh/dx * area
+
+
+def test_transient_deck_equals_direct_model(tmp_path):
+    rng = np.random.default_rng(5)
+    shape = (2, 7, 9)
+    k = np.exp(rng.normal(1.0, 0.7, shape))
+    botm = [-10.0, -25.0]
+    chd = [((kk + 1, i + 1, 1), 12.0) for kk in range(2) for i in range(7)] + \
+          [((kk + 1, i + 1, 9), 8.0) for kk in range(2) for i in range(7)]
+    wel = [((2, 4, 5), -150.0)]
+    sto = dict(iconvert=0, ss=1e-4, sy=0.1, periods={1: "STEADY-STATE", 2: "TRANSIENT"})
+    ims = ("BEGIN nonlinear\n  OUTER_DVCLOSE 1e-7\n  OUTER_MAXIMUM 50\nEND nonlinear\n\n"
+           "BEGIN linear\n  INNER_MAXIMUM 100\n  INNER_DVCLOSE 1e-8\n  INNER_RCLOSE 1e-4 STRICT\n"
+           "  LINEAR_ACCELERATION BICGSTAB\nEND linear\n")
+    d = str(tmp_path)
+    mf6_inputs.write_gwf(d, "m", shape, 50.0, 40.0, 0.0, botm, k, chd={1: chd}, wel={2: wel}, sto=sto, strt=10.0,
+                         k33=0.5)
+    mf6_inputs.write_sim(d, ["m"], [(1.0, 1, 1.0), (30.0, 4, 1.3), (10.0, 2, 1.0)], ims)
+    out = simulate.run(d, ordering=T.ORDER_NATURAL, solution_class=oracle_class())
+    assert len(out["reports"]) == 7 and all(r["converged"] for r in out["reports"])
+    sim = out["simulation"]
+    assert sim.ims.icnvgopt == 1 and sim.ims.ilinmeth == 2 and sim.models[0].sto_transient == {1: False, 2: True}
+    # the same model without files
+    m = build_dis_model(2, 7, 9, 50.0, 40.0, 0.0, botm, k, k33=0.5, strt=10.0, ss=1e-4, sy=0.1, iconvert=0)
+    node = lambda c: ((c[0] - 1) * 7 + c[1] - 1) * 9 + c[2] - 1   # noqa: E731
+    pc = Package(T.PKG_CHD, [node(c) for c, _ in chd], [v for _, v in chd])
+    pw = Package(T.PKG_WEL, [node(c) for c, _ in wel], [v for _, v in wel])
+    O = oracle_class()(m, sim.sln, sim.ims)
+    steps = 0
+    for kper, (perlen, nstp, tsm) in enumerate(sim.perioddata, start=1):
+        O.set_packages([pc] if kper == 1 else [pc, pw])
+        for kstp, delt in enumerate(tdis_steps(perlen, nstp, tsm), start=1):
+            O.timestep(kper, kstp, delt, 1 if kper == 1 else 0)
+            steps += 1
+    assert np.array_equal(out["heads"][0].ravel(), O.x)
+    # OC: SAVE HEAD ALL, SAVE BUDGET LAST (period-1 block stays in force)
+    hds = read_head_file(tmp_path / "m.hds")
+    assert len(hds) == 7 * 2 and hds[-1]["kper"] == 3 and np.isclose(hds[-1]["totim"], 41.0)
+    cbc = read_budget_file(tmp_path / "m.cbc")
+    assert sorted({(r["kper"], r["kstp"]) for r in cbc}) == [(1, 1), (2, 4), (3, 2)]
+    assert [r["text"].strip() for r in cbc if r["kper"] == 2] == ["STO-SS", "FLOW-JA-FACE", "CHD", "WEL"]
+
+
+def test_reader_rejects_what_the_path_cannot_honour(tmp_path):
+    d = str(tmp_path)
+    mf6_inputs.write_gwf(d, "m", (1, 2, 2), 1.0, 1.0, 0.0, [-1.0], 1.0, chd={1: [((1, 1, 1), 1.0)]})
+    mf6_inputs.write_sim(d, ["m"], [(1.0, 1, 1.0)], "BEGIN linear\n  PRECONDITIONER_LEVELS 2\nEND linear\n")
+    sim = mf6io.read_simulation(d)
+    assert sim.ims.level == 0 and any("ILUT" in w for w in sim.warnings)      # downgraded with a warning
+    npf = (tmp_path / "m.npf").read_text()
+    (tmp_path / "m.npf").write_text(npf.replace("SAVE_FLOWS", "SAVE_FLOWS\n  XT3D"))
+    with pytest.raises(mf6io.Mf6InputError, match="XT3D"):
+        mf6io.read_simulation(d)
+    (tmp_path / "m.npf").write_text(npf)
+    with open(tmp_path / "m.nam", "w") as f:
+        f.write("BEGIN packages\n  DIS6 m.dis\n  IC6 m.ic\n  NPF6 m.npf\n  LAK6 m.lak\nEND packages\n")
+    with pytest.raises(mf6io.Mf6InputError, match="LAK6"):
+        mf6io.read_simulation(d)
+
+
+def test_array_control_records(tmp_path):
+    p = tmp_path / "a.txt"
+    p.write_text("1 2 3\n4 5 6\n")
+    lines = [["k", "LAYERED"], ["CONSTANT", "2.5"], ["INTERNAL", "FACTOR", "2.0"], ["1", "2", "3"], ["4", "5", "6"],
+             ["icelltype"], ["OPEN/CLOSE", "a.txt", "FACTOR", "1"]]
+    g = mf6io.read_griddata(lines, str(tmp_path), {"K": ((2, 2, 3), np.float64), "ICELLTYPE": ((1, 2, 3), np.int32)})
+    assert g["K"].tolist() == [2.5] * 6 + [2.0, 4.0, 6.0, 8.0, 10.0, 12.0]
+    assert g["ICELLTYPE"].tolist() == [1, 2, 3, 4, 5, 6] and g["ICELLTYPE"].dtype == np.int32
+    assert mf6io._tokens("  SAVE  HEAD, 'my file.hds'  # trailing") == ["SAVE", "HEAD", "my file.hds"]
+    assert mf6io._tokens("! comment") == [] and mf6io._tokens("// c") == []
