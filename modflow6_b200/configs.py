@@ -67,7 +67,7 @@ def c1_npf01(case="b", gpu_ordering=T.ORDER_NATURAL):
     return SimConfig(f"npf01{case}_75x75", m, periods, sln, ims)
 
 
-def c2_confined(nlay=10, nrow=1000, ncol=1000, gpu_ordering=T.ORDER_MULTICOLOR, inner_maximum=500,
+def c2_confined(nlay=10, nrow=1000, ncol=1000, gpu_ordering=T.ORDER_BLOCK_MULTICOLOR, inner_maximum=500,
                 outer_maximum=50, seed=20260101):
     """confined steady state, heterogeneous K = exp(N(ln 10, 1)), k33 = 0.1 k,
     delr = delc = 100, layer thickness 10, CHD 48 / 40 on the first / last column, WEL -1000 at the centre
@@ -85,7 +85,7 @@ def c2_confined(nlay=10, nrow=1000, ncol=1000, gpu_ordering=T.ORDER_MULTICOLOR, 
     return SimConfig(f"c2_confined_{nlay}x{nrow}x{ncol}", m, periods, sln, ims)
 
 
-def c3_newton(nlay=5, nrow=2000, ncol=2000, gpu_ordering=T.ORDER_MULTICOLOR, nwel=100, ntrans=10,
+def c3_newton(nlay=5, nrow=2000, ncol=2000, gpu_ordering=T.ORDER_BLOCK_MULTICOLOR, nwel=100, ntrans=10,
               seed=20260102, iallowptc=1, inner_maximum=None, outer_maximum=None):
     """unconfined transient with NEWTON UNDER_RELAXATION + STO.
     top 50, 5 layers x 10 m, icelltype 1 in the top layer, ss 1e-5, sy 0.15, RCH on top (sized for a 1.5 m mound),
@@ -125,7 +125,7 @@ def c3_newton(nlay=5, nrow=2000, ncol=2000, gpu_ordering=T.ORDER_MULTICOLOR, nwe
     return SimConfig(f"c3_newton_{nlay}x{nrow}x{ncol}", m, periods, sln, ims)
 
 
-def c4_disv(kind="hexagonal", nlay=5, nr=1000, nc=1000, gpu_ordering=T.ORDER_MULTICOLOR, seed=20260103):
+def c4_disv(kind="hexagonal", nlay=5, nr=1000, nc=1000, gpu_ordering=T.ORDER_BLOCK_MULTICOLOR, seed=20260103):
     """DISV (hexagonal: nr x nc cells per layer; triangular: nr x nc triangles) x nlay
     layers, confined, heterogeneous K; WEL on 1 %, RIV on 2 % and RCH on 100 % of the top cells (seeded),
     CHD on the two outer columns of cells; BICGSTAB + ILU0."""

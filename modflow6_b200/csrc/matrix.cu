@@ -242,7 +242,8 @@ static void build_matrix(mf6gpu_matrix &M, int n, int n_ext, int nja, const int3
   std::vector<int> slice_ptr(M.nslices + 1, 0);
   int maxlen = 0;
   // slice widths: the max row length of each slice, or -- when that costs <= MF6GPU_UNIFORM_PAD_PCT
-  // percent (default 5) extra slots -- the global max for every slice (fixed-width kernels)
+  // percent (default 12.5: a 5-layer DIS grid pads 6 %) extra slots -- the global max for every slice
+  // (fixed-width kernels, stencil table, block sweeps)
   long long ragged_slots = 0;
   std::vector<int> sw(M.nslices, 0);
   for (int s = 0; s < M.nslices; s++) {
@@ -259,7 +260,7 @@ static void build_matrix(mf6gpu_matrix &M, int n, int n_ext, int nja, const int3
   }
   {
     const char *e = std::getenv("MF6GPU_UNIFORM_PAD_PCT");
-    const double pct = e ? std::atof(e) : 5.0;
+    const double pct = e ? std::atof(e) : 12.5;
     const long long uni_slots = 32LL * maxlen * M.nslices;
     if ((double)(uni_slots - ragged_slots) <= 0.01 * pct * (double)ragged_slots)
       for (int s = 0; s < M.nslices; s++) sw[s] = maxlen;
