@@ -413,12 +413,41 @@ ilu0_blk_gather_kernel(int nb, int maxk, int ncols, const int *__restrict__ brow
 // MODE 0: forward   d(k) = src(k) - L(k,k-1) d(k-1)            src = rin (first colour) or d (gathered)
 // MODE 1: backward  d(k) = (d(k) - U(k,k+1) d(k+1)) * piv(k)   + rho partial
 // MODE 2: both in one pass (last colour, block of at most KC cells)
-template <int MODE, int KC, bool AFFINE>
-__global__ void __launch_bounds__(kBlock)
-ilu0_blk_chain_kernel(int nb, int maxk, int W, bool from_rin, const int *__restrict__ brow,
+__device__ __forceinline__ double ld_f64(const double *p) {
+  double v;
+  asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ld_nc_f64(const double *p) {
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ld_nc_i32(const int *p) {
+  int v;
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ld_nc_u8(const unsigned char *p) {
+  unsigned int v;
+  asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+  return (int)v;
+}
+
+// ADDR 0: rows and chain slots from the block tables; 1: regular colour, bases from kbase[]; 2: regular
+// colour whose chain fits one chunk of <= 16 cells: bases as kernel parameters (no dependent load at all
+// in front of the operand loads)
+struct ChainBase {
+  int r0[16];
+};
+// FROM_RIN: the forward pass starts from rin (first colour: nothing was gathered into d)
+template <int MODE, int KC, int ADDR, bool FROM_RIN>
+__global__ void __launch_bounds__(kBlock, 2)
+ilu0_blk_chain_kernel(int nb, int maxk, int W, int opaque_zero, const int *__restrict__ brow,
                       const unsigned char *__restrict__ bchain, const int *__restrict__ kbase,
-                      const unsigned char *__restrict__ nlow, const double *__restrict__ lu,
-                      const double *__restrict__ rin, double *d, const int *__restrict__ done, IluDot D) {
+                      const __grid_constant__ ChainBase kb, const unsigned char *__restrict__ nlow,
+                      const double *__restrict__ lu, const double *__restrict__ rin, double *d,
+                      const int *__restrict__ done, IluDot D) {
   if (done && *done) return;
   double dot = 0.0;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -429,53 +458,81 @@ ilu0_blk_chain_kernel(int nb, int maxk, int W, bool from_rin, const int *__restr
       const int k0 = ((MODE == 1) ? nchunks - 1 - it : it) * KC;
       int rk[KC], ck[KC];
       double acc[KC], ml[KC], mu[KC], pk[KC], rr[KC];
+      // Operand loads are volatile asm in program order: the compiler otherwise sinks each load next to
+      // its consumer to save registers, and a consumer between two loads stalls the warp (in-order issue)
+      // -- KC dependent round trips instead of two.  Invalid cells read row 0 and are masked afterwards.
 #pragma unroll
       for (int k = 0; k < KC; k++) {
         const bool in = (k0 + k < maxk);
-        if (AFFINE) {
-          rk[k] = in ? __ldg(kbase + k0 + k) + q : -1;
-          const int lo = in ? (int)__ldg(nlow + rk[k]) : 0;
+        if (ADDR != 0) {
+          rk[k] = !in ? -1 : (ADDR == 2 ? kb.r0[(k0 + k) & 15] : __ldg(kbase + k0 + k)) + q;
+        } else {
+          rk[k] = in ? ld_nc_i32(brow + (size_t)(k0 + k) * nb + q) : -1;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < KC; k++) {
+        const bool in = (k0 + k < maxk);
+        if (ADDR != 0) {
+          const int lo = ld_nc_u8(nlow + max(rk[k], 0));
           ck[k] = !in ? 0 : ((k0 + k > 0 ? lo : 0) | ((k0 + k + 1 < maxk ? lo + 1 : 0) << 4));
         } else {
-          rk[k] = in ? __ldg(brow + (size_t)(k0 + k) * nb + q) : -1;
-          ck[k] = in ? __ldg(bchain + (size_t)(k0 + k) * nb + q) : 0;
+          ck[k] = in ? ld_nc_u8(bchain + (size_t)(k0 + k) * nb + q) : 0;
         }
       }
 #pragma unroll
       for (int k = 0; k < KC; k++) {
         const int r = max(rk[k], 0);
-        const bool valid = rk[k] >= 0;
         const long long base = (long long)(r >> 5) * (32 * W) + (r & 31);
-        const int slo = ck[k] & 15, sup = ck[k] >> 4;
-        if (MODE != 1) {
-          acc[k] = !valid ? 0.0 : (from_rin ? rin[r] : d[r]);
-          ml[k] = (valid && slo) ? __ldg(lu + base + 32 * slo) : 0.0;
-        } else {
-          acc[k] = valid ? d[r] : 0.0;
-        }
+        acc[k] = (MODE != 1 && FROM_RIN) ? ld_nc_f64(rin + r) : ld_f64(d + r);
         if (MODE != 0) {
-          mu[k] = (valid && sup) ? __ldg(lu + base + 32 * sup) : 0.0;
-          pk[k] = valid ? __ldg(lu + base) : 0.0;
-          rr[k] = (valid && !(MODE == 2 && from_rin)) ? rin[r] : acc[k];
+          pk[k] = ld_nc_f64(lu + base);
+          if (!(MODE == 2 && FROM_RIN)) rr[k] = ld_nc_f64(rin + r);   // else acc[k] is r itself
         }
       }
+#pragma unroll
+      for (int k = 0; k < KC; k++) {
+        const int r = max(rk[k], 0);
+        const long long base = (long long)(r >> 5) * (32 * W) + (r & 31);
+        const int slo = ck[k] & 15, sup = ck[k] >> 4;
+        if (MODE != 1) ml[k] = ld_nc_f64(lu + base + 32 * slo);   // slot 0 (the pivot) when there is no chain entry
+        if (MODE != 0) mu[k] = ld_nc_f64(lu + base + 32 * sup);
+      }
+      // the recurrence must not start before the last operand load has been ISSUED: its start value is
+      // made to depend (through `opaque_zero`, always 0) on the values loaded last
+      long long after = 0;
+#pragma unroll
+      for (int k = 0; k < KC; k++) {
+        const bool valid = rk[k] >= 0;
+        const int slo = ck[k] & 15, sup = ck[k] >> 4;
+        if (MODE != 1) after ^= __double_as_longlong(ml[k]);
+        if (MODE != 0) after ^= __double_as_longlong(mu[k]) ^ __double_as_longlong(pk[k]);
+        if (MODE != 0 && !(MODE == 2 && FROM_RIN)) after ^= __double_as_longlong(rr[k]);
+        if (!valid) acc[k] = 0.0;
+        if (MODE != 1 && !(valid && slo)) ml[k] = 0.0;
+        if (MODE != 0 && !(valid && sup)) mu[k] = 0.0;
+      }
+      carry = __longlong_as_double(__double_as_longlong(carry) | (after & (long long)opaque_zero));
+      double fw[KC];  // forward values
       if (MODE != 1) {
 #pragma unroll
-        for (int k = 0; k < KC; k++)
+        for (int k = 0; k < KC; k++) {
+          fw[k] = 0.0;
           if (rk[k] >= 0) {
             carry = acc[k] - ml[k] * carry;
-            acc[k] = carry;
+            fw[k] = carry;
             if (MODE == 0) d[rk[k]] = carry;
           }
+        }
       }
       if (MODE != 0) {
         if (MODE == 2) carry = 0.0;
 #pragma unroll
         for (int k = KC - 1; k >= 0; k--)
           if (rk[k] >= 0) {
-            carry = (acc[k] - mu[k] * carry) * pk[k];
+            carry = ((MODE == 2 ? fw[k] : acc[k]) - mu[k] * carry) * pk[k];
             d[rk[k]] = carry;
-            dot += rr[k] * carry;
+            dot += ((MODE == 2 && FROM_RIN) ? acc[k] : rr[k]) * carry;
           }
       }
     }
@@ -490,35 +547,80 @@ size_t ilu0_block_dot_slots(const mf6gpu_matrix &A) {
   return n;
 }
 
-static inline int chain_chunk(int maxk) {
-  return maxk <= 4 ? 4 : maxk <= 6 ? 6 : maxk <= 8 ? 8 : maxk <= 10 ? 10 : maxk <= 12 ? 12 : maxk <= 16 ? 16 : 8;
+// cells per chunk: the operands of a whole chunk live in registers (2 doubles per cell in MODE 0, 4 in MODE 1,
+// 5 in MODE 2; 128 registers per thread), longer chains run chunk after chunk
+static inline int chain_chunk(int mode, int maxk) {
+  const int cap = (mode == 0) ? 16 : (mode == 1 ? 12 : 10);
+  if (maxk > cap) return 8;
+  return maxk <= 4 ? 4 : maxk <= 6 ? 6 : maxk <= 8 ? 8 : maxk <= 10 ? 10 : maxk <= 12 ? 12 : 16;
+}
+static inline bool chain_fits_one_chunk(int mode, int maxk) { return maxk <= chain_chunk(mode, maxk); }
+
+struct ChainArgs {
+  int g, nb, maxk, W;
+  const int *brow;
+  const unsigned char *bch;
+  const int *kb;
+  ChainBase kbv;
+  const unsigned char *nlow;
+  const double *lu, *rin;
+  double *d;
+  const int *done;
+  IluDot D;
+  cudaStream_t s;
+};
+
+template <int MODE, int KC>
+static void launch_chain_kc(const ChainArgs &a, int addr, bool from_rin) {
+  constexpr int cap = (MODE == 0) ? 16 : (MODE == 1 ? 12 : 10);
+  if constexpr (KC <= cap) {
+    auto go = [&](auto addr_c, auto rin_c) {
+      ilu0_blk_chain_kernel<MODE, KC, decltype(addr_c)::value, decltype(rin_c)::value><<<a.g, kBlock, 0, a.s>>>(
+          a.nb, a.maxk, a.W, 0, a.brow, a.bch, a.kb, a.kbv, a.nlow, a.lu, a.rin, a.d, a.done, a.D);
+    };
+    auto with_addr = [&](auto rin_c) {
+      if (addr == 2)
+        go(std::integral_constant<int, 2>{}, rin_c);
+      else if (addr == 1)
+        go(std::integral_constant<int, 1>{}, rin_c);
+      else
+        go(std::integral_constant<int, 0>{}, rin_c);
+    };
+    if (from_rin && MODE != 1)
+      with_addr(std::bool_constant<(MODE != 1)>{});
+    else
+      with_addr(std::false_type{});
+  }
 }
 
 template <int MODE>
 static void launch_chain(const mf6gpu_matrix &A, int c, bool from_rin, const double *lu, const double *rin,
                          double *d, const int *done, cudaStream_t s, IluDot D) {
-  const int nb = A.blk_nb[c], maxk = A.blk_maxk[c], g = (nb + kBlock - 1) / kBlock, W = A.uniform_w;
-  const int *brow = A.blk_rows.p + A.blk_off[c];
-  const unsigned char *bch = A.blk_chain.p + A.blk_off[c];
-  const int *kb = A.blk_base.p + A.blk_base_off[c];
-  const bool aff = A.blk_affine[c];
-  switch (chain_chunk(maxk)) {
-#define MF6_CHAIN_CASE(KC)                                                                                         \
-  case KC:                                                                                                         \
-    if (aff)                                                                                                       \
-      ilu0_blk_chain_kernel<MODE, KC, true><<<g, kBlock, 0, s>>>(nb, maxk, W, from_rin, brow, bch, kb, A.nlow.p, lu, \
-                                                                 rin, d, done, D);                                 \
-    else                                                                                                           \
-      ilu0_blk_chain_kernel<MODE, KC, false><<<g, kBlock, 0, s>>>(nb, maxk, W, from_rin, brow, bch, kb, A.nlow.p,  \
-                                                                  lu, rin, d, done, D);                            \
-    break;
-    MF6_CHAIN_CASE(4)
-    MF6_CHAIN_CASE(6)
-    MF6_CHAIN_CASE(8)
-    MF6_CHAIN_CASE(10)
-    MF6_CHAIN_CASE(12)
-    MF6_CHAIN_CASE(16)
-#undef MF6_CHAIN_CASE
+  ChainArgs a{};
+  a.nb = A.blk_nb[c];
+  a.maxk = A.blk_maxk[c];
+  a.g = (a.nb + kBlock - 1) / kBlock;
+  a.W = A.uniform_w;
+  a.brow = A.blk_rows.p + A.blk_off[c];
+  a.bch = A.blk_chain.p + A.blk_off[c];
+  a.kb = A.blk_base.p + A.blk_base_off[c];
+  a.nlow = A.nlow.p;
+  a.lu = lu;
+  a.rin = rin;
+  a.d = d;
+  a.done = done;
+  a.D = D;
+  a.s = s;
+  const int addr = !A.blk_affine[c] ? 0 : (a.maxk <= 16 ? 2 : 1);
+  if (addr == 2)
+    for (int k = 0; k < a.maxk; k++) a.kbv.r0[k] = A.blk_base_h[A.blk_base_off[c] + k];
+  switch (chain_chunk(MODE, a.maxk)) {
+    case 4: launch_chain_kc<MODE, 4>(a, addr, from_rin); break;
+    case 6: launch_chain_kc<MODE, 6>(a, addr, from_rin); break;
+    case 8: launch_chain_kc<MODE, 8>(a, addr, from_rin); break;
+    case 10: launch_chain_kc<MODE, 10>(a, addr, from_rin); break;
+    case 12: launch_chain_kc<MODE, 12>(a, addr, from_rin); break;
+    case 16: launch_chain_kc<MODE, 16>(a, addr, from_rin); break;
   }
 }
 
@@ -547,7 +649,7 @@ static int launch_blocks_w(const mf6gpu_matrix &A, const double *lu, const doubl
   };
   // the last colour's two chain passes fuse when nothing of its U half lies outside the chains and
   // a block fits one chunk
-  const bool fuse_last = !A.blk_has_upper[C - 1] && A.blk_maxk[C - 1] <= chain_chunk(A.blk_maxk[C - 1]);
+  const bool fuse_last = !A.blk_has_upper[C - 1] && chain_fits_one_chunk(2, A.blk_maxk[C - 1]);
   for (int c = 0; c < C; c++) {
     if (A.blk_nb[c] == 0) continue;
     if (A.blk_has_lower[c]) gather(std::true_type{}, c);

@@ -389,6 +389,7 @@ static void build_matrix(mf6gpu_matrix &M, int n, int n_ext, int nja, const int3
         M.blk_base_off[c + 1] = (int)base.size();
       }
       M.blk_base.upload(base);
+      M.blk_base_h = base;
     }
     // the block-sweep kernels assume chains: the only intra-block neighbours of the k-th cell are cells k-1, k+1
     bool chain = true;

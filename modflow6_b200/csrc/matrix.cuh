@@ -55,6 +55,7 @@ struct mf6gpu_matrix {
   std::vector<char> blk_affine;
   std::vector<int> blk_base_off;
   mf6::DevBuf<int> blk_base;
+  std::vector<int> blk_base_h;  // host copy (short chains pass their bases as kernel parameters)
   std::vector<char> blk_has_lower, blk_has_upper;  // per colour: factor entries outside the chains in the L / U half
   mf6::DevBuf<int> csr2sell;   // [nja] slot of each original CSR entry
   mf6::DevBuf<double> stage;   // [nja] H2D/D2H staging of CSR values
