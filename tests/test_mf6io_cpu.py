@@ -122,3 +122,25 @@ def test_array_control_records(tmp_path):
     assert g["ICELLTYPE"].tolist() == [1, 2, 3, 4, 5, 6] and g["ICELLTYPE"].dtype == np.int32
     assert mf6io._tokens("  SAVE  HEAD, 'my file.hds'  # trailing") == ["SAVE", "HEAD", "my file.hds"]
     assert mf6io._tokens("! comment") == [] and mf6io._tokens("// c") == []
+
+
+def test_reference_minsim_deck(tmp_path):
+    """the reference's own example deck (`.mf6minsim/`: two convertible 1x1x5 models, GWF-GWF exchange, IMS with
+    ILUT levels -> downgraded): read unchanged from the reference tree when it is present (it is not on the
+    GPU box).  1-D unconfined flow between CHD 1 and CHD 10 over a -100 m bottom: (h + 100)^2 falls on a
+    straight line in x up to the discretisation of the saturated thickness"""
+    import os
+    import shutil
+    src = "/root/reference/.mf6minsim"
+    if not os.path.isdir(src):
+        pytest.skip("reference tree not present")
+    for f in os.listdir(src):
+        shutil.copy(os.path.join(src, f), tmp_path)
+    out = simulate.run(str(tmp_path), ordering=T.ORDER_NATURAL, solution_class=oracle_class())
+    assert any("ILUT" in w for w in out["simulation"].warnings)
+    assert all(r["converged"] for r in out["reports"]) and abs(out["reports"][0]["pdiffr"]) < 1e-5
+    h = np.concatenate([x.ravel() for x in out["heads"]])
+    assert h[0] == 1.0 and h[-1] == 10.0 and np.all(np.diff(h) > 0)
+    t2 = (h + 100.0) ** 2
+    fit = np.polyval(np.polyfit(np.arange(10.0), t2, 1), np.arange(10.0))
+    assert np.abs(t2 - fit).max() / t2.mean() < 2e-4
