@@ -120,3 +120,55 @@ def build_disv_model(nlay, cell2d, top, botm, k11, k33=None, icelltype=0, strt=0
         m.insto = 1
     m.meta["cell2d"] = cell2d["kind"]
     return m
+
+
+def cell2d_from_vertices(vertices, cells):
+    """cell2d dictionary of build_disv_model from a DISV package's VERTICES / CELL2D blocks.
+
+    vertices: (nvert, 2) x, y; cells: list of (xc, yc, [0-based vertex numbers, clockwise]).
+    Restates `disvconnections` + `vertexconnect` (Connections.f90:702-790, 1272-1361) and
+    `DisvGeomType%cprops` (DisvGeom.f90:136-202): two cells are connected when they share an EDGE -- two
+    consecutive vertices, traversed forward in one list and backward in the other (`shared_edge`, :300-333);
+    hwva = edge length, cl = normal distance from the cell centre to the edge line (`distance_normal`,
+    :432-447), area by the shoelace formula about the first vertex (`get_area`, :340-386)."""
+    vertices = np.asarray(vertices, dtype=np.float64)
+    ncpl = len(cells)
+    closed = []
+    for _, _, iv in cells:
+        iv = list(iv)
+        if iv[0] != iv[-1]:
+            iv.append(iv[0])          # the reference closes the polygon when it loads CELL2D
+        closed.append(iv)
+    # directed edge (a, b) -> cell; the neighbour across it owns (b, a)
+    owner = {}
+    for j, iv in enumerate(closed):
+        for a, b in zip(iv[:-1], iv[1:]):
+            owner[(a, b)] = j
+    nbr_l, cl_l, len_l = [], [], []
+    area = np.zeros(ncpl)
+    for j, ((xc, yc, _), iv) in enumerate(zip(cells, closed)):
+        nb, cl, ln = [], [], []
+        for a, b in zip(iv[:-1], iv[1:]):
+            m = owner.get((b, a))
+            if m is None or m == j or m in nb:
+                continue
+            x1, y1 = vertices[a]
+            x2, y2 = vertices[b]
+            d = np.sqrt((x1 - x2) ** 2 + (y1 - y2) ** 2)
+            nb.append(m)
+            ln.append(d)
+            cl.append(abs((x2 - x1) * (y1 - yc) - (x1 - xc) * (y2 - y1)) / d)
+        nbr_l.append(nb); cl_l.append(cl); len_l.append(ln)
+        x = vertices[iv, 0]
+        y = vertices[iv, 1]
+        a1 = np.sum((x[:-1] - x[0]) * (y[1:] - y[0]))
+        a2 = np.sum((x[1:] - x[0]) * (y[:-1] - y[0]))
+        area[j] = 0.5 * abs(a1 - a2)
+    maxnb = max(1, max(len(v) for v in nbr_l))
+    nbr = np.full((ncpl, maxnb), -1, dtype=np.int64)
+    nbr_cl = np.zeros((ncpl, maxnb))
+    nbr_len = np.zeros((ncpl, maxnb))
+    for j in range(ncpl):
+        k = len(nbr_l[j])
+        nbr[j, :k], nbr_cl[j, :k], nbr_len[j, :k] = nbr_l[j], cl_l[j], len_l[j]
+    return dict(ncpl=ncpl, nbr=nbr, nbr_cl=nbr_cl, nbr_len=nbr_len, area=area, kind="vertices")

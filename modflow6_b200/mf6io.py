@@ -1,5 +1,5 @@
 """Reader for the subset of MODFLOW 6 input files that feeds the accelerated path (SURVEY.md section 8f,
-rank 3): mfsim.nam, TDIS, IMS, GWF name file, DIS, IC, NPF, STO, CHD/WEL/DRN/RIV/GHB/RCH (list based), OC and
+rank 3): mfsim.nam, TDIS, IMS, GWF name file, DIS, DISV, IC, NPF, STO, CHD/WEL/DRN/RIV/GHB/RCH (list based), OC and
 GWF-GWF exchanges -- enough to run FloPy-written models such as the reference's `.mf6minsim/` example through
 `mf6gpu_solution_*` without the Fortran host (which cannot be built in this image).
 
@@ -21,6 +21,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import ctypes_types as T
+from .disv import build_disv_model, cell2d_from_vertices
 from .grid import Package, build_dis_model
 
 
@@ -282,6 +283,11 @@ def read_ims(path, warnings):
 
 
 def _cellid(tokens, shape):
+    if len(shape) == 2:       # DISV: (layer, icell2d)
+        k, j = int(tokens[0]) - 1, int(tokens[1]) - 1
+        if not (0 <= k < shape[0] and 0 <= j < shape[1]):
+            raise Mf6InputError(f"cellid {tokens[:2]} outside the grid {shape}")
+        return k * shape[1] + j, 2
     if len(shape) == 3:
         k, i, j = int(tokens[0]) - 1, int(tokens[1]) - 1, int(tokens[2]) - 1
         if not (0 <= k < shape[0] and 0 <= i < shape[1] and 0 <= j < shape[2]):
@@ -333,31 +339,54 @@ def read_gwf_model(name, nam_path, base_dir, warnings):
         pn = t[2] if len(t) > 2 else None
         if ft in _PKG_TYPE:
             stress.append((ft, fn, pn))
-        elif ft in ("DIS6", "IC6", "NPF6", "STO6", "OC6"):
+        elif ft in ("DIS6", "DISV6", "IC6", "NPF6", "STO6", "OC6"):
             files[ft] = fn
         else:
             raise Mf6InputError(f"{nam_path}: package {ft} is outside the GPU path (SURVEY.md section 8)")
-    for need in ("DIS6", "IC6", "NPF6"):
+    for need in ("IC6", "NPF6"):
         if need not in files:
             raise Mf6InputError(f"{nam_path}: {need} package is required")
-    # DIS
-    d = read_blocks(files["DIS6"])
-    dim = _options(_block(d, "DIMENSIONS"))
-    nlay, nrow, ncol = int(dim["NLAY"][0]), int(dim["NROW"][0]), int(dim["NCOL"][0])
-    shape = (nlay, nrow, ncol)
-    g = read_griddata(_block(d, "GRIDDATA"), base_dir,
-                      {"DELR": ((ncol,), np.float64), "DELC": ((nrow,), np.float64), "TOP": ((nrow, ncol), np.float64),
-                       "BOTM": (shape, np.float64), "IDOMAIN": (shape, np.int32)})
+    if ("DIS6" in files) == ("DISV6" in files):
+        raise Mf6InputError(f"{nam_path}: exactly one of DIS6 / DISV6 is required (DISU is outside the GPU path)")
+    cell2d = None
+    if "DIS6" in files:
+        d = read_blocks(files["DIS6"])
+        dim = _options(_block(d, "DIMENSIONS"))
+        nlay, nrow, ncol = int(dim["NLAY"][0]), int(dim["NROW"][0]), int(dim["NCOL"][0])
+        shape = (nlay, nrow, ncol)
+        g = read_griddata(_block(d, "GRIDDATA"), base_dir,
+                          {"DELR": ((ncol,), np.float64), "DELC": ((nrow,), np.float64),
+                           "TOP": ((nrow, ncol), np.float64), "BOTM": (shape, np.float64),
+                           "IDOMAIN": (shape, np.int32)})
+    else:
+        d = read_blocks(files["DISV6"])
+        dim = _options(_block(d, "DIMENSIONS"))
+        nlay, ncpl, nvert = int(dim["NLAY"][0]), int(dim["NCPL"][0]), int(dim["NVERT"][0])
+        shape = (nlay, ncpl)
+        g = read_griddata(_block(d, "GRIDDATA"), base_dir,
+                          {"TOP": ((1, 1, ncpl), np.float64), "BOTM": ((nlay, 1, ncpl), np.float64),
+                           "IDOMAIN": ((nlay, 1, ncpl), np.int32)})
+        verts = np.zeros((nvert, 2))
+        for t in _block(d, "VERTICES"):
+            verts[int(t[0]) - 1] = float(t[1]), float(t[2])
+        cells = [None] * ncpl
+        for t in _block(d, "CELL2D"):
+            nv = int(t[3])
+            cells[int(t[0]) - 1] = (float(t[1]), float(t[2]), [int(v) - 1 for v in t[4:4 + nv]])
+        if any(c is None for c in cells):
+            raise Mf6InputError(f"{files['DISV6']}: CELL2D does not list every cell")
+        cell2d = cell2d_from_vertices(verts, cells)
+    ashape = shape if len(shape) == 3 else (nlay, 1, shape[1])      # READARRAY layout (LAYERED = per layer)
     # IC / NPF / STO
-    ic = read_griddata(_block(read_blocks(files["IC6"]), "GRIDDATA"), base_dir, {"STRT": (shape, np.float64)})
+    ic = read_griddata(_block(read_blocks(files["IC6"]), "GRIDDATA"), base_dir, {"STRT": (ashape, np.float64)})
     nb = read_blocks(files["NPF6"])
     nopt = _options(_block(nb, "OPTIONS", required=False))
     for k in nopt:
         if k in ("THICKSTRT", "XT3D", "REWET", "TVK6", "K22OVERK", "K33OVERK"):
             raise Mf6InputError(f"NPF option {k} is not supported on the GPU path")
     np_ = read_griddata(_block(nb, "GRIDDATA"), base_dir,
-                        {"ICELLTYPE": (shape, np.int32), "K": (shape, np.float64), "K22": (shape, np.float64),
-                         "K33": (shape, np.float64)})
+                        {"ICELLTYPE": (ashape, np.int32), "K": (ashape, np.float64), "K22": (ashape, np.float64),
+                         "K33": (ashape, np.float64)})
     if "K22" in np_ and not np.array_equal(np_["K22"], np_["K"]):
         raise Mf6InputError("NPF K22 anisotropy is not supported on the GPU path")
     kw = {}
@@ -376,7 +405,7 @@ def read_gwf_model(name, nam_path, base_dir, warnings):
         sb = read_blocks(files["STO6"])
         sopt = _options(_block(sb, "OPTIONS", required=False))
         sto = read_griddata(_block(sb, "GRIDDATA"), base_dir,
-                            {"ICONVERT": (shape, np.int32), "SS": (shape, np.float64), "SY": (shape, np.float64)})
+                            {"ICONVERT": (ashape, np.int32), "SS": (ashape, np.float64), "SY": (ashape, np.float64)})
         if "STORAGECOEFFICIENT" in sopt:
             kw["istor_coef"] = 1
         if "SS_CONFINED_ONLY" in sopt:
@@ -385,15 +414,16 @@ def read_gwf_model(name, nam_path, base_dir, warnings):
             if nm == "PERIOD":
                 key = lines[0][0].upper() if lines else "STEADY-STATE"
                 sto_tr[num] = (key == "TRANSIENT")
-    top = g["TOP"].reshape(nrow, ncol)
-    botm = g["BOTM"].reshape(shape)
-    m = build_dis_model(nlay, nrow, ncol, g["DELR"], g["DELC"], top, botm, np_["K"].reshape(shape),
-                        k33=np_["K33"].reshape(shape) if "K33" in np_ else None,
-                        icelltype=np_["ICELLTYPE"].reshape(shape), strt=ic["STRT"].reshape(shape),
-                        ss=sto["SS"].reshape(shape) if "SS" in sto else None,
-                        sy=sto["SY"].reshape(shape) if "SY" in sto else None,
-                        iconvert=sto["ICONVERT"].reshape(shape) if "ICONVERT" in sto else None,
-                        inewton=inewton, inewtonur=inewtonur, **kw)
+    common = dict(k33=np_["K33"] if "K33" in np_ else None, icelltype=np_["ICELLTYPE"], strt=ic["STRT"],
+                  ss=sto.get("SS"), sy=sto.get("SY"), iconvert=sto.get("ICONVERT"), inewton=inewton,
+                  inewtonur=inewtonur, **kw)
+    if cell2d is None:
+        r3 = lambda a: None if a is None else a.reshape(shape)   # noqa: E731
+        common = {k: (r3(v) if isinstance(v, np.ndarray) else v) for k, v in common.items()}
+        m = build_dis_model(nlay, nrow, ncol, g["DELR"], g["DELC"], g["TOP"].reshape(nrow, ncol),
+                            g["BOTM"].reshape(shape), np_["K"].reshape(shape), **common)
+    else:
+        m = build_disv_model(nlay, cell2d, g["TOP"], g["BOTM"].reshape(nlay, shape[1]), np_["K"], **common)
     if "IDOMAIN" in g:
         if (g["IDOMAIN"] < 0).any():
             raise Mf6InputError("IDOMAIN < 0 (vertical pass-through cells) is not supported on the GPU path")

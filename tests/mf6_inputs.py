@@ -29,16 +29,43 @@ def _arr(name, a, layered=False):
         "      " + " ".join(repr(float(v)) for v in row) for row in a.reshape(-1, a.shape[-1])) + "\n"
 
 
-def write_gwf(d, name, shape, delr, delc, top, botm, k, chd=None, wel=None, icelltype=0, strt=0.0, k33=None,
-              sto=None, oc=True, newton=False, extra_periods=None):
-    """chd / wel: dict iper -> list of ((k,i,j), value) with 1-based cellids"""
+def _disv_text(shape, delr, delc, top, botm):
+    """the rectangular grid as a DISV package: vertices row by row from the top-left corner, cells clockwise
+    from their top-left vertex (what flopy's structured-to-vertex conversion writes)"""
     nlay, nrow, ncol = shape
-    pk = f"  DIS6  {name}.dis  dis\n  IC6  {name}.ic  ic\n  NPF6  {name}.npf  npf\n"
-    _w(os.path.join(d, f"{name}.dis"),
-       f"BEGIN options\nEND options\n\nBEGIN dimensions\n  NLAY {nlay}\n  NROW {nrow}\n  NCOL {ncol}\nEND dimensions\n\n"
-       "BEGIN griddata\n" + _arr("delr", delr) + _arr("delc", delc) + _arr("top", top)
-       + _arr("botm", botm, layered=np.ndim(botm) > 0)
-       + "END griddata\n")
+    delr = np.broadcast_to(np.asarray(delr, dtype=float), (ncol,))
+    delc = np.broadcast_to(np.asarray(delc, dtype=float), (nrow,))
+    xe = np.concatenate([[0.0], np.cumsum(delr)])
+    ye = delc.sum() - np.concatenate([[0.0], np.cumsum(delc)])
+    s = (f"BEGIN options\nEND options\n\nBEGIN dimensions\n  NLAY {nlay}\n  NCPL {nrow * ncol}\n"
+         f"  NVERT {(nrow + 1) * (ncol + 1)}\nEND dimensions\n\nBEGIN griddata\n" + _arr("top", top)
+         + _arr("botm", botm, layered=np.ndim(botm) > 0) + "END griddata\n\nBEGIN vertices\n")
+    for i in range(nrow + 1):
+        for j in range(ncol + 1):
+            s += f"  {i * (ncol + 1) + j + 1}  {float(xe[j])!r}  {float(ye[i])!r}\n"
+    s += "END vertices\n\nBEGIN cell2d\n"
+    for i in range(nrow):
+        for j in range(ncol):
+            v = [i * (ncol + 1) + j, i * (ncol + 1) + j + 1, (i + 1) * (ncol + 1) + j + 1, (i + 1) * (ncol + 1) + j]
+            s += (f"  {i * ncol + j + 1}  {float(0.5 * (xe[j] + xe[j + 1]))!r}  {float(0.5 * (ye[i] + ye[i + 1]))!r}  4  "
+                  + "  ".join(str(x + 1) for x in v) + "\n")
+    return s + "END cell2d\n"
+
+
+def write_gwf(d, name, shape, delr, delc, top, botm, k, chd=None, wel=None, icelltype=0, strt=0.0, k33=None,
+              sto=None, oc=True, newton=False, disv=False):
+    """chd / wel: dict iper -> list of ((k,i,j), value) with 1-based cellids.  disv=True writes the same
+    rectangular grid as a DISV package (cellids become layer, icell2d)"""
+    nlay, nrow, ncol = shape
+    pk = f"  DIS{'V' if disv else ''}6  {name}.dis  dis\n  IC6  {name}.ic  ic\n  NPF6  {name}.npf  npf\n"
+    if disv:
+        _w(os.path.join(d, f"{name}.dis"), _disv_text(shape, delr, delc, top, botm))
+    else:
+        _w(os.path.join(d, f"{name}.dis"),
+           f"BEGIN options\nEND options\n\nBEGIN dimensions\n  NLAY {nlay}\n  NROW {nrow}\n  NCOL {ncol}\nEND dimensions\n\n"
+           "BEGIN griddata\n" + _arr("delr", delr) + _arr("delc", delc) + _arr("top", top)
+           + _arr("botm", botm, layered=np.ndim(botm) > 0)
+           + "END griddata\n")
     _w(os.path.join(d, f"{name}.ic"), "BEGIN griddata\n" + _arr("strt", strt) + "END griddata\n")
     npf = "BEGIN options\n  SAVE_FLOWS\nEND options\n\nBEGIN griddata\n" + _arr("icelltype", icelltype) \
         + _arr("k", np.asarray(k, dtype=float).reshape(shape) if np.ndim(k) else k, layered=np.ndim(k) > 0)
@@ -58,7 +85,8 @@ def write_gwf(d, name, shape, delr, delc, top, botm, k, chd=None, wel=None, icel
         pk += f"  {ft}6  {name}.{ft.lower()}  {ft.lower()}_0\n"
         s = f"BEGIN options\nEND options\n\nBEGIN dimensions\n  MAXBOUND  {max(len(v) for v in spd.values())}\nEND dimensions\n\n"
         for iper, rows in sorted(spd.items()):
-            s += f"BEGIN period  {iper}\n" + "".join(f"  {c[0]} {c[1]} {c[2]}  {v!r}\n" for c, v in rows) \
+            cid = (lambda c: f"{c[0]} {(c[1] - 1) * ncol + c[2]}") if disv else (lambda c: f"{c[0]} {c[1]} {c[2]}")
+            s += f"BEGIN period  {iper}\n" + "".join(f"  {cid(c)}  {v!r}\n" for c, v in rows) \
                 + f"END period  {iper}\n\n"
         _w(os.path.join(d, f"{name}.{ft.lower()}"), s)
     if oc:

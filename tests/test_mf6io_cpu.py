@@ -144,3 +144,34 @@ def test_reference_minsim_deck(tmp_path):
     t2 = (h + 100.0) ** 2
     fit = np.polyval(np.polyfit(np.arange(10.0), t2, 1), np.arange(10.0))
     assert np.abs(t2 - fit).max() / t2.mean() < 2e-4
+
+
+def test_disv_deck_of_a_rectangular_grid_equals_the_dis_deck(tmp_path):
+    """VERTICES / CELL2D -> connections (vertexconnect, DisvGeom cprops): the same rectangular grid written as a
+    DISV package must give the DIS connectivity (ia, ja, ihc, cl1, cl2, hwva, area) and therefore the same heads"""
+    rng = np.random.default_rng(11)
+    shape = (3, 5, 6)
+    k = np.exp(rng.normal(0.5, 0.6, shape))
+    delr = np.array([10.0, 20.0, 30.0, 15.0, 25.0, 10.0])
+    delc = np.array([12.0, 8.0, 20.0, 16.0, 10.0])
+    botm = [-5.0, -12.0, -30.0]
+    chd = [((kk + 1, i + 1, 1), 5.0) for kk in range(3) for i in range(5)] + \
+          [((kk + 1, i + 1, 6), 2.0) for kk in range(3) for i in range(5)]
+    wel = [((3, 3, 4), -40.0)]
+    ims = ("BEGIN nonlinear\n  OUTER_DVCLOSE 1e-9\n  OUTER_MAXIMUM 50\nEND nonlinear\n\n"
+           "BEGIN linear\n  INNER_MAXIMUM 200\n  INNER_DVCLOSE 1e-10\n  INNER_RCLOSE 1e-8\n  LINEAR_ACCELERATION CG\nEND linear\n")
+    outs = {}
+    for tag in ("dis", "disv"):
+        d = tmp_path / tag
+        d.mkdir()
+        mf6_inputs.write_gwf(str(d), "m", shape, delr, delc, 0.0, botm, k, chd={1: chd}, wel={1: wel}, strt=3.0,
+                             k33=0.3, disv=(tag == "disv"))
+        mf6_inputs.write_sim(str(d), ["m"], [(1.0, 1, 1.0)], ims)
+        outs[tag] = simulate.run(str(d), ordering=T.ORDER_NATURAL, solution_class=oracle_class())
+    a, b = outs["dis"]["simulation"].models[0].model, outs["disv"]["simulation"].models[0].model
+    assert np.array_equal(a.ia, b.ia) and np.array_equal(a.ja, b.ja) and np.array_equal(a.ihc, b.ihc)
+    for name in ("cl1", "cl2", "hwva", "area", "top", "bot"):
+        assert np.allclose(getattr(a, name), getattr(b, name), rtol=1e-13), name
+    assert np.abs(outs["dis"]["heads"][0].ravel() - outs["disv"]["heads"][0].ravel()).max() < 1e-9
+    recs = read_head_file(tmp_path / "disv" / "m.hds")
+    assert len(recs) == 3 and recs[0]["ncol"] == 30 and recs[0]["nrow"] == 1      # DISV: ncol = ncpl, nrow = 1
