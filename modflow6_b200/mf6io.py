@@ -448,21 +448,26 @@ def read_gwf_model(name, nam_path, base_dir, warnings):
     return gi
 
 
-def read_exchange(path, m1, m2, shape1, shape2):
+def read_exchange(path, m1, m2, shape1, shape2, exg_id=1):
     b = read_blocks(path)
     opt = _options(_block(b, "OPTIONS", required=False))
     for k in opt:
         if k in ("GNC6", "MVR6", "XT3D", "CELL_AVERAGING", "VARIABLECV", "DEWATERED"):
             raise Mf6InputError(f"{path}: exchange option {k} is not supported on the GPU path")
-    n1, n2, ihc, cl1, cl2, hw = [], [], [], [], [], []
+    auxname = [a.upper() for a in opt.get("AUXILIARY", opt.get("AUX", []))]
+    n1, n2, ihc, cl1, cl2, hw, aux = [], [], [], [], [], [], []
     for t in _block(b, "EXCHANGEDATA"):
         a, w = _cellid(t, shape1)
         c, w2 = _cellid(t[w:], shape2)
         r = t[w + w2:]
         n1.append(a); n2.append(c)
         ihc.append(int(r[0])); cl1.append(float(r[1])); cl2.append(float(r[2])); hw.append(float(r[3]))
+        aux.append([float(v) for v in r[4:4 + len(auxname)]])
+    # name as simulation_cr builds it (SimulationCreate.f90:455); SAVE_FLOWS = ipakcb (DisConnExchange.f90:142-146)
     return dict(m1=m1, m2=m2, nodem1=np.array(n1), nodem2=np.array(n2), ihc=np.array(ihc, dtype=np.int32),
-                cl1=np.array(cl1), cl2=np.array(cl2), hwva=np.array(hw))
+                cl1=np.array(cl1), cl2=np.array(cl2), hwva=np.array(hw), name=f"GWF-GWF_{exg_id}",
+                save_flows="SAVE_FLOWS" in opt, auxname=auxname,
+                aux=np.array(aux, dtype=np.float64).reshape(len(n1), len(auxname)))
 
 
 def read_simulation(sim_dir):
@@ -483,7 +488,8 @@ def read_simulation(sim_dir):
         if t[0].upper() != "GWF6-GWF6":
             raise Mf6InputError(f"exchange type {t[0]} is outside the GPU path")
         i1, i2 = index[t[2].upper()], index[t[3].upper()]
-        exchanges.append(read_exchange(os.path.join(sim_dir, t[1]), i1, i2, models[i1].shape, models[i2].shape))
+        exchanges.append(read_exchange(os.path.join(sim_dir, t[1]), i1, i2, models[i1].shape, models[i2].shape,
+                                       exg_id=len(exchanges) + 1))
     sg = [x for x in b if x[0] == "SOLUTIONGROUP"]
     if len(sg) != 1 or len(sg[0][2]) != 1 or sg[0][2][0][0].upper() != "IMS6":
         raise Mf6InputError("exactly one solution group with one IMS6 solution is supported")

@@ -100,6 +100,29 @@ class BudgetFileWriter:
         rec["q"] = q[keep]
         self.f.write(rec.tobytes())
 
+    def write_exchange(self, kstp, kper, delt, pertim, totim, exchange_name, other_model, nodes, other_nodes, q,
+                       auxname=(), aux=None):
+        """gwf_gwf_bdsav_model (exg-gwfgwf.f90:997-1153): FLOW-JA-FACE list between this model and `other_model`,
+        source and destination package = the exchange name, one entry per exchange connection
+        (node here, node there, rate into this model, auxiliary values); 0-based cell numbers in"""
+        nodes, other_nodes = np.asarray(nodes), np.asarray(other_nodes)
+        naux = len(auxname)
+        self._header(kstp, kper, "FLOW-JA-FACE", self.ncol, self.nrow, self.nlay, 6, delt, pertim, totim)
+        self.f.write(self.model + _text16(exchange_name.upper(), right=False)
+                     + _text16(other_model.upper(), right=False) + _text16(exchange_name.upper(), right=False))
+        self.f.write(struct.pack("<i", naux + 1))
+        for a in auxname:
+            self.f.write(_text16(a.upper(), right=False))
+        self.f.write(struct.pack("<i", nodes.size))
+        rec = np.empty(nodes.size, dtype=np.dtype([("n", "<i4"), ("n2", "<i4"), ("q", "<f8"), ("aux", "<f8", (naux,))]))
+        rec["n"] = nodes + 1
+        rec["n2"] = other_nodes + 1
+        rec["q"] = q
+        if naux:
+            rec["aux"] = np.asarray(aux, dtype=np.float64).reshape(nodes.size, naux)
+        self.f.write(rec.tobytes())
+        self.f.flush()
+
     def write_step(self, kstp, kper, delt, pertim, totim, solution, packages, package_names=None):
         """everything gwf_ot_flow saves for one time step, taken from a solution object
         (GpuNumericalSolution or the oracle: flowja, storage_rates, simvals)"""

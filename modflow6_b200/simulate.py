@@ -38,6 +38,46 @@ def _should_save(settings, kstp, nstp):
     return False
 
 
+class _ModelView:
+    """what output.write_step needs for ONE model of a multi-model solution: the model's own FLOW-JA-FACE (the
+    entries of the merged matrix whose row and column both belong to it -- same relative order as the model's
+    own CSR, the diagonal carrying the residual that includes the exchange flows, like gwf_gwf_add_to_flowja),
+    its storage rates and the rates of its own packages"""
+
+    def __init__(self, solution, merged, model, lo, pkg_index):
+        self.s, self.model, self.lo, self.pkg_index = solution, model, int(lo), pkg_index
+        rows = np.repeat(np.arange(merged.nodes), np.diff(merged.ia))
+        hi = self.lo + model.nodes
+        self.pick = np.nonzero((rows >= self.lo) & (rows < hi) & (merged.ja >= self.lo) & (merged.ja < hi))[0]
+        assert self.pick.size == model.nja
+
+    @property
+    def flowja(self):
+        return self.s.flowja[self.pick]
+
+    @property
+    def storage_rates(self):
+        ss, sy = self.s.storage_rates
+        return ss[self.lo:self.lo + self.model.nodes], sy[self.lo:self.lo + self.model.nodes]
+
+    @property
+    def simvals(self):
+        sv = self.s.simvals
+        return [sv[i] for i in self.pkg_index]
+
+
+def _exchange_rates(merged, flowja, offs, e):
+    """simvals of a GWF-GWF exchange = flow into the model-1 cell from the model-2 cell (gwf_gwf_calc_simvals):
+    the FLOW-JA-FACE entry (n1, n2) of the merged system"""
+    a = e["nodem1"] + int(offs[e["m1"]])
+    b = e["nodem2"] + int(offs[e["m2"]])
+    q = np.empty(a.size)
+    for i, (r, c) in enumerate(zip(a, b)):
+        p0, p1 = merged.ia[r], merged.ia[r + 1]
+        q[i] = flowja[p0 + int(np.nonzero(merged.ja[p0:p1] == c)[0][0])]
+    return q
+
+
 def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None, solution_class=None):
     """solution_class(model, sln_settings, ims_settings) -> object with set_packages / timestep / x / flowja /
     simvals / storage_rates; default GpuNumericalSolution"""
@@ -59,10 +99,7 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
         hw = HeadFileWriter(gi.head_file, gi.shape) if (write_output and gi.head_file) else None
         bw = None
         if write_output and gi.budget_file:
-            if len(models) > 1:
-                log(f"warning: {gi.name}: budget files are written for single-model simulations only")
-            else:
-                bw = BudgetFileWriter(gi.budget_file, gi.shape, gi.name)
+            bw = BudgetFileWriter(gi.budget_file, gi.shape, gi.name)
         writers.append((hw, bw))
     current = [[None] * len(gi.packages) for gi in sim.models]     # list in force per package
     saving = [dict() for _ in sim.models]                          # rtype -> settings in force
@@ -108,9 +145,25 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
                     h = x[offs[k]:offs[k] + gi.model.nodes].copy()
                     h[gi.model.ibound == 0] = DHNOFLO
                     hw.write(kstp, kper, pertim, totim, h)
-                if bw and _should_save(saving[k].get("BUDGET", []), kstp, nstp):   # single-model simulation
-                    bw.write_step(kstp, kper, delt, pertim, totim, S, pkgs,
-                                  [gi.packages[ip].name for _, ip in owner])
+                if bw and _should_save(saving[k].get("BUDGET", []), kstp, nstp):
+                    mine = [i for i, (kk, _) in enumerate(owner) if kk == k]
+                    view = S if len(models) == 1 else _ModelView(S, model, gi.model, offs[k], mine)
+                    local = [Package(pkgs[i].type, pkgs[i].nodelist - int(offs[k]), pkgs[i].b1) for i in mine]
+                    bw.write_step(kstp, kper, delt, pertim, totim, view, local,
+                                  [gi.packages[owner[i][1]].name for i in mine])
+            # exchange flows follow the models' own records (exg_ot after model_ot, mf6core.f90:755-771)
+            for e in sim.exchanges:
+                if not e["save_flows"]:
+                    continue
+                q = None
+                for k, other, mine, theirs, sign in ((e["m1"], e["m2"], "nodem1", "nodem2", 1.0),
+                                                     (e["m2"], e["m1"], "nodem2", "nodem1", -1.0)):
+                    bw = writers[k][1]
+                    if bw and _should_save(saving[k].get("BUDGET", []), kstp, nstp):
+                        if q is None:
+                            q = _exchange_rates(model, S.flowja, offs, e)
+                        bw.write_exchange(kstp, kper, delt, pertim, totim, e["name"], sim.models[other].name,
+                                          e[mine], e[theirs], sign * q, e["auxname"], e["aux"])
     for hw, bw in writers:
         if hw:
             hw.close()

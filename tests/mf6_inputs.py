@@ -109,7 +109,7 @@ def write_sim(d, models, perioddata, ims_text, exchanges=()):
     for stem, m1, m2, rows in exchanges:
         ex += f"  GWF6-GWF6  {stem}.gwfgwf  {m1}  {m2}\n"
         _w(os.path.join(d, f"{stem}.gwfgwf"),
-           f"BEGIN options\n  AUXILIARY ANGLDEGX CDIST\nEND options\n\nBEGIN dimensions\n  NEXG {len(rows)}\nEND dimensions\n\n"
+           f"BEGIN options\n  AUXILIARY ANGLDEGX CDIST\n  SAVE_FLOWS\nEND options\n\nBEGIN dimensions\n  NEXG {len(rows)}\nEND dimensions\n\n"
            "BEGIN exchangedata\n" + "".join(
                f"  {a[0]} {a[1]} {a[2]}  {b[0]} {b[1]} {b[2]}  {ihc}  {c1!r}  {c2!r}  {hw!r}  0.0  {c1 + c2!r}\n"
                for a, b, ihc, c1, c2, hw in rows) + "END exchangedata\n")

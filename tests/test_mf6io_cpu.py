@@ -175,3 +175,32 @@ def test_disv_deck_of_a_rectangular_grid_equals_the_dis_deck(tmp_path):
     assert np.abs(outs["dis"]["heads"][0].ravel() - outs["disv"]["heads"][0].ravel()).max() < 1e-9
     recs = read_head_file(tmp_path / "disv" / "m.hds")
     assert len(recs) == 3 and recs[0]["ncol"] == 30 and recs[0]["nrow"] == 1      # DISV: ncol = ncpl, nrow = 1
+
+
+def test_multi_model_budget_files(tmp_path):
+    """per-model .cbc of a two-model simulation: the model's own FLOW-JA-FACE, its packages, then the GWF-GWF
+    exchange flows as a FLOW-JA-FACE list towards the other model (gwf_gwf_bdsav_model); the uniform flow field of
+    par_gwf01 (gradient 1 per 100 m cell, K = 1, face area 100 x 100) carries 100 m3/d per cell face"""
+    shape = (2, 3, 5)
+    mf6_inputs.write_par_gwf01(str(tmp_path), shape)
+    out = simulate.run(str(tmp_path), ordering=T.ORDER_NATURAL, solution_class=oracle_class())
+    left, right = (read_budget_file(tmp_path / f"{m}.cbc") for m in ("leftmodel", "rightmodel"))
+    assert [r["text"].strip() for r in left] == ["FLOW-JA-FACE", "CHD", "FLOW-JA-FACE"]
+    ml = out["simulation"].models[0].model
+    assert left[0]["imeth"] == 1 and left[0]["flow"].size == ml.nja
+    ex_l, ex_r = left[2], right[2]
+    assert ex_l["imeth"] == 6 and ex_l["srcmodel"].strip() == "LEFTMODEL" and ex_l["dstmodel"].strip() == "RIGHTMODEL"
+    assert ex_l["srcpackage"].strip() == ex_l["dstpackage"].strip() == "GWF-GWF_1"
+    assert [a.strip() for a in ex_l["auxtxt"]] == ["ANGLDEGX", "CDIST"] and np.allclose(ex_l["aux"][:, 1], 100.0)
+    # left boundary column 5 <-> right column 1, every layer and row
+    cell = lambda k, i, j: (k * 3 + i) * 5 + j + 1   # noqa: E731
+    assert ex_l["node"].tolist() == [cell(k, i, 4) for k in range(2) for i in range(3)]
+    assert ex_l["node2"].tolist() == [cell(k, i, 0) for k in range(2) for i in range(3)]
+    assert np.allclose(ex_l["q"], 100.0, rtol=1e-6)           # water enters the left model from the right (head 6 > 5)
+    assert np.array_equal(ex_r["node"], ex_l["node2"]) and np.allclose(ex_r["q"], -ex_l["q"])
+    # water balance of the left model: CHD outflow == exchange inflow; each cell's row of FLOW-JA-FACE closes
+    assert np.isclose(left[1]["q"].sum(), -ex_l["q"].sum(), rtol=1e-6)
+    resid = np.add.reduceat(left[0]["flow"], ml.ia[:-1])
+    np.add.at(resid, left[1]["node"] - 1, left[1]["q"])
+    np.add.at(resid, ex_l["node"] - 1, ex_l["q"])
+    assert np.abs(resid).max() < 1e-4
