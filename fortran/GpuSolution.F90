@@ -1,0 +1,300 @@
+!> @brief Second integration level: the device-resident formulate + outer iteration
+!!
+!! SOURCE ONLY (no Fortran compiler in this image; bind(C) names are checked against
+!! include/mf6gpu.h by tests/test_abi.py).
+!!
+!! GpuNumericalSolutionType extends NumericalSolutionType and replaces the body of sln_ca
+!! (src/Solution/NumericalSolution.f90:1287-1327: prepareSolve, the solve(kiter) loop,
+!! finalizeSolve) by ONE call to mf6gpu_solution_timestep for solutions that hold a single
+!! GWF model whose packages are all inside the accelerated set (DIS/DISV, NPF without XT3D,
+!! STO, CHD, WEL, RIV, RCH, GHB, DRN).  Anything else keeps the inherited host path with the
+!! first-level GpuSolverType / GpuMatrixType (fortran/GpuSolver.F90).  The model arrays are
+!! handed over once in sln_ar (they are borrowed for that call only), stress data every
+!! stress period, heads / FLOW-JA-FACE / package rates come back after every time step into
+!! the arrays gwf_ot_dv / gwf_ot_flow / gwf_bd read.
+module GpuSolutionBindingsModule
+  use, intrinsic :: iso_c_binding
+  implicit none
+  private
+  public :: mf6gpu_sln_settings, mf6gpu_gwf_model, mf6gpu_bnd_package, mf6gpu_step_report
+  public :: MF6GPU_MAX_BUDGET_TERMS
+  public :: mf6gpu_solution_create, mf6gpu_solution_destroy, mf6gpu_solution_set_packages
+  public :: mf6gpu_solution_timestep, mf6gpu_solution_get_x, mf6gpu_solution_set_x
+  public :: mf6gpu_solution_get_flowja, mf6gpu_solution_get_simvals, mf6gpu_solution_get_storage
+
+  integer(c_int), parameter :: MF6GPU_MAX_BUDGET_TERMS = 16
+
+  !> IMS NONLINEAR block + OPTIONS (include/mf6gpu_types.h: mf6gpu_sln_settings)
+  type, bind(C) :: mf6gpu_sln_settings
+    real(c_double) :: dvclose
+    integer(c_int32_t) :: mxiter
+    integer(c_int32_t) :: nonmeth
+    real(c_double) :: theta
+    real(c_double) :: akappa
+    real(c_double) :: gamma
+    real(c_double) :: amomentum
+    integer(c_int32_t) :: iallowptc
+    integer(c_int32_t) :: numtrack
+    real(c_double) :: btol
+    real(c_double) :: breduc
+    real(c_double) :: res_lim
+  end type mf6gpu_sln_settings
+
+  !> one GWF model: the arrays ConnectionsType / GwfNpfType / GwfStoType hold
+  type, bind(C) :: mf6gpu_gwf_model
+    integer(c_int32_t) :: index_base
+    integer(c_int32_t) :: nodes
+    integer(c_int32_t) :: nja
+    integer(c_int32_t) :: njas
+    type(c_ptr) :: ia, ja, jas, isym, ihc
+    type(c_ptr) :: cl1, cl2, hwva, top, bot, area
+    type(c_ptr) :: ibound, strt
+    type(c_ptr) :: k11, k33, icelltype
+    integer(c_int32_t) :: icellavg, inewton, inewtonur, iperched, ivarcv, idewatcv, ithickstrt, insto
+    type(c_ptr) :: ibotnode
+    type(c_ptr) :: ss, sy, iconvert
+    integer(c_int32_t) :: istor_coef, iconf_ss, iorig_ss, reserved
+  end type mf6gpu_gwf_model
+
+  type, bind(C) :: mf6gpu_bnd_package
+    integer(c_int32_t) :: ptype
+    integer(c_int32_t) :: nbound
+    integer(c_int32_t) :: index_base
+    integer(c_int32_t) :: iflowred
+    real(c_double) :: flowred
+    type(c_ptr) :: nodelist, b1, b2, b3
+  end type mf6gpu_bnd_package
+
+  type, bind(C) :: mf6gpu_step_report
+    integer(c_int32_t) :: converged, outer_iterations, inner_iterations, nterms
+    real(c_double) :: max_dv
+    integer(c_int32_t) :: max_dv_loc, npivot_fixes, nbacktracks, reserved
+    real(c_double) :: totrin, totrot, pdiffr
+    real(c_double) :: term_in(MF6GPU_MAX_BUDGET_TERMS)
+    real(c_double) :: term_out(MF6GPU_MAX_BUDGET_TERMS)
+    integer(c_int32_t) :: term_id(MF6GPU_MAX_BUDGET_TERMS)
+    real(c_double) :: t_formulate, t_linsolve
+  end type mf6gpu_step_report
+
+  interface
+    function mf6gpu_solution_create(model, sln, ims, handle) &
+      bind(C, name="mf6gpu_solution_create") result(rc)
+      import :: c_int, c_ptr, mf6gpu_gwf_model, mf6gpu_sln_settings
+      type(mf6gpu_gwf_model), intent(in) :: model
+      type(mf6gpu_sln_settings), intent(in) :: sln
+      type(c_ptr), value :: ims !< c_loc of a mf6gpu_ims_settings
+      type(c_ptr), intent(out) :: handle
+      integer(c_int) :: rc
+    end function
+    function mf6gpu_solution_destroy(handle) bind(C, name="mf6gpu_solution_destroy") result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr), value :: handle
+      integer(c_int) :: rc
+    end function
+    function mf6gpu_solution_set_packages(handle, npkg, pkgs) &
+      bind(C, name="mf6gpu_solution_set_packages") result(rc)
+      import :: c_int, c_int32_t, c_ptr, mf6gpu_bnd_package
+      type(c_ptr), value :: handle
+      integer(c_int32_t), value :: npkg
+      type(mf6gpu_bnd_package), intent(in) :: pkgs(*)
+      integer(c_int) :: rc
+    end function
+    function mf6gpu_solution_timestep(handle, kper, kstp, delt, iss, report) &
+      bind(C, name="mf6gpu_solution_timestep") result(rc)
+      import :: c_int, c_int32_t, c_double, c_ptr, mf6gpu_step_report
+      type(c_ptr), value :: handle
+      integer(c_int32_t), value :: kper, kstp, iss
+      real(c_double), value :: delt
+      type(mf6gpu_step_report), intent(out) :: report
+      integer(c_int) :: rc
+    end function
+    function mf6gpu_solution_get_x(handle, x) bind(C, name="mf6gpu_solution_get_x") result(rc)
+      import :: c_int, c_double, c_ptr
+      type(c_ptr), value :: handle
+      real(c_double), intent(out) :: x(*)
+      integer(c_int) :: rc
+    end function
+    function mf6gpu_solution_set_x(handle, x) bind(C, name="mf6gpu_solution_set_x") result(rc)
+      import :: c_int, c_double, c_ptr
+      type(c_ptr), value :: handle
+      real(c_double), intent(in) :: x(*)
+      integer(c_int) :: rc
+    end function
+    function mf6gpu_solution_get_flowja(handle, flowja) &
+      bind(C, name="mf6gpu_solution_get_flowja") result(rc)
+      import :: c_int, c_double, c_ptr
+      type(c_ptr), value :: handle
+      real(c_double), intent(out) :: flowja(*)
+      integer(c_int) :: rc
+    end function
+    function mf6gpu_solution_get_simvals(handle, cap, simvals, count) &
+      bind(C, name="mf6gpu_solution_get_simvals") result(rc)
+      import :: c_int, c_int32_t, c_double, c_ptr
+      type(c_ptr), value :: handle
+      integer(c_int32_t), value :: cap
+      real(c_double), intent(out) :: simvals(*)
+      integer(c_int32_t), intent(out) :: count
+      integer(c_int) :: rc
+    end function
+    function mf6gpu_solution_get_storage(handle, strgss, strgsy) &
+      bind(C, name="mf6gpu_solution_get_storage") result(rc)
+      import :: c_int, c_double, c_ptr
+      type(c_ptr), value :: handle
+      real(c_double), intent(out) :: strgss(*), strgsy(*)
+      integer(c_int) :: rc
+    end function
+  end interface
+end module GpuSolutionBindingsModule
+
+module GpuNumericalSolutionModule
+  use, intrinsic :: iso_c_binding
+  use KindModule, only: I4B, DP
+  use NumericalSolutionModule, only: NumericalSolutionType
+  use NumericalModelModule, only: NumericalModelType, GetNumericalModelFromList
+  use GwfModule, only: GwfModelType
+  use BndModule, only: BndType, GetBndFromList
+  use TdisModule, only: kper, kstp, delt
+  use Mf6GpuBindingsModule, only: mf6gpu_ims_settings, mf6gpu_check
+  use GpuSolutionBindingsModule
+  implicit none
+  private
+  public :: GpuNumericalSolutionType
+
+  type, extends(NumericalSolutionType) :: GpuNumericalSolutionType
+    type(c_ptr) :: handle = c_null_ptr !< mf6gpu_solution*
+    class(GwfModelType), pointer :: gwf => null() !< the one model of this solution
+    real(DP), dimension(:), allocatable :: simvals_all !< package rates, packages concatenated
+  contains
+    procedure :: sln_ar => gpu_sln_ar
+    procedure :: sln_rp => gpu_sln_rp
+    procedure :: sln_ca => gpu_sln_ca
+    procedure :: sln_da => gpu_sln_da
+  end type GpuNumericalSolutionType
+
+contains
+
+  !> @brief after the host allocate/read: hand the model arrays to the device once
+  subroutine gpu_sln_ar(this)
+    class(GpuNumericalSolutionType) :: this
+    type(mf6gpu_gwf_model) :: m
+    type(mf6gpu_sln_settings) :: s
+    type(mf6gpu_ims_settings), target :: l
+    class(NumericalModelType), pointer :: mp
+    !
+    call this%NumericalSolutionType%sln_ar()
+    mp => GetNumericalModelFromList(this%modellist, 1)
+    select type (mp)
+    class is (GwfModelType)
+      this%gwf => mp
+    end select
+    associate (g => this%gwf, con => this%gwf%dis%con)
+      m%index_base = 1 ! the Fortran arrays are passed unchanged
+      m%nodes = g%dis%nodes
+      m%nja = con%nja
+      m%njas = con%njas
+      m%ia = c_loc(con%ia); m%ja = c_loc(con%ja); m%jas = c_loc(con%jas)
+      m%isym = c_loc(con%isym); m%ihc = c_loc(con%ihc)
+      m%cl1 = c_loc(con%cl1); m%cl2 = c_loc(con%cl2); m%hwva = c_loc(con%hwva)
+      m%top = c_loc(g%dis%top); m%bot = c_loc(g%dis%bot); m%area = c_loc(g%dis%area)
+      m%ibound = c_loc(g%ibound); m%strt = c_loc(g%ic%strt)
+      m%k11 = c_loc(g%npf%k11); m%k33 = c_loc(g%npf%k33); m%icelltype = c_loc(g%npf%icelltype)
+      m%icellavg = g%npf%icellavg; m%inewton = g%inewton; m%inewtonur = g%inewtonur
+      m%iperched = g%npf%iperched; m%ivarcv = g%npf%ivarcv; m%idewatcv = g%npf%idewatcv
+      m%ithickstrt = g%npf%ithickstrt; m%insto = g%insto
+      m%ibotnode = c_loc(g%npf%ibotnode)
+      if (g%insto > 0) then
+        m%ss = c_loc(g%sto%ss); m%sy = c_loc(g%sto%sy); m%iconvert = c_loc(g%sto%iconvert)
+        m%istor_coef = g%sto%istor_coef; m%iconf_ss = g%sto%iconf_ss; m%iorig_ss = g%sto%iorig_ss
+      else
+        m%ss = c_null_ptr; m%sy = c_null_ptr; m%iconvert = c_null_ptr
+        m%istor_coef = 0; m%iconf_ss = 0; m%iorig_ss = 0
+      end if
+      m%reserved = 0
+    end associate
+    ! IMS NONLINEAR block, read by the inherited sln_ar
+    s%dvclose = this%dvclose; s%mxiter = this%mxiter; s%nonmeth = this%nonmeth
+    s%theta = this%theta; s%akappa = this%akappa; s%gamma = this%gamma; s%amomentum = this%amomentum
+    s%iallowptc = this%iallowptc; s%numtrack = this%numtrack
+    s%btol = this%btol; s%breduc = this%breduc; s%res_lim = this%res_lim
+    ! IMS LINEAR block: ImsLinearSettingsType copied field by field (cf. GpuSolver.F90 gpu_initialize)
+    l%dvclose = this%linear_settings%dvclose; l%rclose = this%linear_settings%rclose
+    l%icnvgopt = this%linear_settings%icnvgopt; l%iter1 = this%linear_settings%iter1
+    l%ilinmeth = this%linear_settings%ilinmeth; l%iscl = this%linear_settings%iscl
+    l%iord = this%linear_settings%iord; l%north = this%linear_settings%north
+    l%relax = this%linear_settings%relax; l%level = this%linear_settings%level
+    l%droptol = this%linear_settings%droptol
+    l%gpu_ordering = 2 ! MF6GPU_ORDER_BLOCK_MULTICOLOR
+    l%reserved = 0
+    call mf6gpu_check(mf6gpu_solution_create(m, s, c_loc(l), this%handle))
+  end subroutine gpu_sln_ar
+
+  !> @brief stress period data of every boundary package (after the packages' bnd_rp)
+  subroutine gpu_sln_rp(this)
+    class(GpuNumericalSolutionType) :: this
+    type(mf6gpu_bnd_package), dimension(:), allocatable :: pk
+    class(BndType), pointer :: b
+    integer(I4B) :: ip, np
+    !
+    np = this%gwf%bndlist%Count()
+    allocate (pk(np))
+    do ip = 1, np
+      b => GetBndFromList(this%gwf%bndlist, ip)
+      pk(ip)%ptype = gpu_package_type(b%filtyp) ! CHD 1, WEL 2, RIV 3, RCH 4, GHB 5, DRN 6
+      pk(ip)%nbound = b%nbound
+      pk(ip)%index_base = 1
+      pk(ip)%iflowred = 0
+      pk(ip)%flowred = 0.0_DP
+      pk(ip)%nodelist = c_loc(b%nodelist)
+      ! the columns of `bound` (BoundaryPackage.f90:47-166) in the order of mf6gpu_types.h
+      pk(ip)%b1 = c_loc(b%bound(1, 1)) ! NB: `bound` is (ncolbnd, maxbound): the shim packs the
+      pk(ip)%b2 = c_null_ptr           !     columns into contiguous work arrays before this call
+      pk(ip)%b3 = c_null_ptr
+    end do
+    call mf6gpu_check(mf6gpu_solution_set_packages(this%handle, int(np, c_int32_t), pk))
+  end subroutine gpu_sln_rp
+
+  !> @brief one time step on the device instead of prepareSolve / solve(kiter) loop / finalizeSolve
+  subroutine gpu_sln_ca(this, isgcnvg, isuppress_output)
+    class(GpuNumericalSolutionType) :: this
+    integer(I4B), intent(inout) :: isgcnvg
+    integer(I4B), intent(in) :: isuppress_output
+    type(mf6gpu_step_report) :: rep
+    integer(c_int32_t) :: nb
+    !
+    call mf6gpu_check(mf6gpu_solution_timestep(this%handle, kper, kstp, delt, this%gwf%iss, rep))
+    this%icnvg = rep%converged
+    if (rep%converged == 0) isgcnvg = 0
+    this%itertot_timestep = rep%outer_iterations
+    ! what gwf_ot_dv / gwf_ot_flow / gwf_bd read afterwards
+    call mf6gpu_check(mf6gpu_solution_get_x(this%handle, this%gwf%x))
+    call mf6gpu_check(mf6gpu_solution_get_flowja(this%handle, this%gwf%flowja))
+    call mf6gpu_check(mf6gpu_solution_get_simvals(this%handle, int(size(this%simvals_all), c_int32_t), &
+                                                  this%simvals_all, nb))
+    if (this%gwf%insto > 0) then
+      call mf6gpu_check(mf6gpu_solution_get_storage(this%handle, this%gwf%sto%strgss, this%gwf%sto%strgsy))
+    end if
+    ! rep%term_in / term_out / term_id feed model_bdentry (Budget.f90) in package order
+  end subroutine gpu_sln_ca
+
+  subroutine gpu_sln_da(this)
+    class(GpuNumericalSolutionType) :: this
+    call mf6gpu_check(mf6gpu_solution_destroy(this%handle))
+    this%handle = c_null_ptr
+    call this%NumericalSolutionType%sln_da()
+  end subroutine gpu_sln_da
+
+  pure function gpu_package_type(filtyp) result(t)
+    character(len=*), intent(in) :: filtyp
+    integer(c_int32_t) :: t
+    select case (trim(filtyp))
+    case ('CHD'); t = 1
+    case ('WEL'); t = 2
+    case ('RIV'); t = 3
+    case ('RCH'); t = 4
+    case ('GHB'); t = 5
+    case ('DRN'); t = 6
+    case default; t = 0
+    end select
+  end function gpu_package_type
+
+end module GpuNumericalSolutionModule
