@@ -16,7 +16,7 @@ from tests.helpers import permute_csr
 
 pytestmark = pytest.mark.gpu
 
-GRIDS = [(10, 6, 10), (20, 6, 10), (5, 9, 7), (33, 5, 6), (3, 40, 64), (12, 5, 7), (14, 4, 6), (16, 3, 5), (7, 6, 5)]
+GRIDS = [(10, 6, 10), (20, 6, 10), (5, 9, 7), (33, 5, 6), (3, 40, 64), (12, 5, 7), (14, 4, 6), (16, 3, 5), (7, 6, 5), (6, 1, 3), (4, 2, 1)]
 
 
 def _apply_pair(cfg, relax=0.0):
