@@ -215,6 +215,86 @@ def build_dis_block(spec, pr, pc, rank, **opts):
                     recv_ptr=recv_ptr, block=(i0, i1, j0, j1), spec=spec)
 
 
+@dataclass
+class GenericSubModel(SubModel):
+    """submodel cut out of an arbitrary global model by an owner map (extract_submodel)"""
+    g2l_own: np.ndarray = None      # [global nodes] local index of the owned cells, -1 elsewhere
+
+    def local_nodes(self, gnodes):
+        loc = self.g2l_own[np.asarray(gnodes, dtype=np.int64)]
+        mask = loc >= 0
+        return mask, loc[mask].astype(np.int32)
+
+
+def extract_submodel(g, owner, rank, nranks):
+    """The submodel of `rank` from a global (e.g. merge_models) GwfModel and the owner rank of every cell --
+    what `mf6 -p` gets from GWF-GWF exchanges: the rank's own model plus the exchange partners' cells as a
+    halo (SpatialModelConnection.f90:306-510, the interface model), with the synchronisation lists of
+    VirtualGwfModel / MpiRouter.  Same layout rules as build_dis_block: owned cells first in ascending global
+    id, halo cells grouped by owner rank in ascending global id, halo rows diagonal only, per-connection
+    arrays (cl1 = the lower GLOBAL id's side) taken unchanged from the global model."""
+    owner = np.asarray(owner)
+    n = g.nodes
+    ia_g = g.ia.astype(np.int64)
+    own = np.nonzero(owner == rank)[0]
+    n_own = own.size
+    cnt = (ia_g[own + 1] - ia_g[own])
+    ia = np.zeros(n_own + 1, dtype=np.int64)
+    np.cumsum(cnt, out=ia[1:])
+    nja_own = int(ia[-1])
+    within = np.arange(nja_own) - np.repeat(ia[:-1], cnt)
+    pos = np.repeat(ia_g[own], cnt) + within
+    cols = g.ja[pos].astype(np.int64)
+    rows_l = np.repeat(np.arange(n_own), cnt)
+    foreign = owner[cols] != rank
+    halo_g = np.unique(cols[foreign])
+    halo_g = halo_g[np.lexsort((halo_g, owner[halo_g]))]
+    n_halo = halo_g.size
+    n_ext = n_own + n_halo
+    g2l = np.full(n, -1, dtype=np.int64)
+    g2l[own] = np.arange(n_own)
+    g2l_own = g2l.copy()
+    g2l[halo_g] = n_own + np.arange(n_halo)
+    ja = g2l[cols]
+    diag = within == 0
+    jas_old = g.jas[pos].astype(np.int64)
+    uniq, inv = np.unique(jas_old[~diag], return_inverse=True)
+    jas = np.full(nja_own, -1, dtype=np.int64)
+    jas[~diag] = inv
+    ia_full = np.concatenate([ia, nja_own + np.arange(1, n_halo + 1)])
+    ja_full = np.concatenate([ja, n_own + np.arange(n_halo)])
+    jas_full = np.concatenate([jas, np.full(n_halo, -1, dtype=np.int64)])
+    rows = np.concatenate([rows_l, n_own + np.arange(n_halo)]).astype(np.int64)
+    key = rows * n_ext + ja_full
+    order = np.argsort(key, kind="stable")
+    tkey = ja_full * n_ext + rows
+    loc = np.minimum(np.searchsorted(key[order], tkey), key.size - 1)
+    isym = np.where(key[order][loc] == tkey, order[loc], 0)
+    sel = np.concatenate([own, halo_g])
+    ibot = g2l[g.ibotnode[sel]]
+    ibot = np.where(ibot < 0, np.arange(n_ext), ibot)
+    m = GwfModel(nodes=n_ext, ia=ia_full, ja=ja_full, jas=jas_full, isym=isym,
+                 ihc=g.ihc[uniq], cl1=g.cl1[uniq], cl2=g.cl2[uniq], hwva=g.hwva[uniq],
+                 top=g.top[sel], bot=g.bot[sel], area=g.area[sel], k11=g.k11[sel], k33=g.k33[sel],
+                 icelltype=g.icelltype[sel], strt=g.strt[sel], ibound=g.ibound[sel], ibotnode=ibot,
+                 ss=g.ss[sel], sy=g.sy[sel], iconvert=g.iconvert[sel],
+                 icellavg=g.icellavg, inewton=g.inewton, inewtonur=g.inewtonur, iperched=g.iperched,
+                 ivarcv=g.ivarcv, idewatcv=g.idewatcv, insto=g.insto, istor_coef=g.istor_coef,
+                 iconf_ss=g.iconf_ss, iorig_ss=g.iorig_ss, shape=None)
+    howner = owner[halo_g]
+    nbrs = np.unique(howner)
+    recv_ptr = np.concatenate([[0], np.cumsum([(howner == q).sum() for q in nbrs])]).astype(np.int32)
+    send_idx, send_ptr = [], [0]
+    for q in nbrs:
+        face = np.unique(rows_l[owner[cols] == q])       # owned cells next to q's cells, ascending global id
+        send_idx.append(face)
+        send_ptr.append(send_ptr[-1] + face.size)
+    send_idx = np.concatenate(send_idx).astype(np.int32) if send_idx else np.zeros(0, np.int32)
+    return GenericSubModel(rank=rank, nranks=nranks, model=m, n_own=n_own, global_id=sel.astype(np.int32),
+                           nbr_rank=nbrs.astype(np.int32), send_ptr=np.asarray(send_ptr, np.int32),
+                           send_idx=send_idx, recv_ptr=recv_ptr, block=None, spec=None, g2l_own=g2l_own)
+
+
 def global_packages_c2(spec):
     """CHD 48 / 40 on the first / last column, WEL -1000 in the centre of the middle layer (C2 recipe)."""
     kk, ii = np.meshgrid(np.arange(spec.nlay), np.arange(spec.nrow), indexing="ij")

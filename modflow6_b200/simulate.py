@@ -78,9 +78,13 @@ def _exchange_rates(merged, flowja, offs, e):
     return q
 
 
-def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None, solution_class=None):
+def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None, solution_class=None, comm=None):
     """solution_class(model, sln_settings, ims_settings) -> object with set_packages / timestep / x / flowja /
-    simvals / storage_rates; default GpuNumericalSolution"""
+    simvals / storage_rates; default GpuNumericalSolution.
+
+    comm (distributed.GpuComm, one process per GPU): the split-model run of `mf6 -p` -- model k of the
+    simulation lives on rank k, its exchange partners' cells are the halo (distributed.extract_submodel);
+    every rank writes its own model's head file.  The deck must hold exactly one model per rank."""
     sim = read_simulation(sim_dir)
     log = log or (lambda *a: None)
     for w in sim.warnings:
@@ -91,15 +95,28 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
     else:
         model, offs = merge_models(models, sim.exchanges)
     sim.ims.gpu_ordering = ordering
-    if solution_class is None:
-        from .solution import GpuNumericalSolution as solution_class
-    S = solution_class(model, sim.sln, sim.ims)
+    rank = None
+    if comm is not None and comm.nranks > 1:
+        from .distributed import GpuDistributedSolution, extract_submodel
+        if len(models) != comm.nranks:
+            raise ValueError(f"{len(models)} models for {comm.nranks} ranks: the split-model run needs one model per rank")
+        rank = comm.rank
+        owner = np.repeat(np.arange(len(models)), [m.nodes for m in models])
+        S = GpuDistributedSolution(extract_submodel(model, owner, rank, comm.nranks), sim.sln, sim.ims, comm)
+    else:
+        if solution_class is None:
+            from .solution import GpuNumericalSolution as solution_class
+        S = solution_class(model, sim.sln, sim.ims)
     writers = []
     for k, gi in enumerate(sim.models):
-        hw = HeadFileWriter(gi.head_file, gi.shape) if (write_output and gi.head_file) else None
+        mine = rank is None or rank == k
+        hw = HeadFileWriter(gi.head_file, gi.shape) if (write_output and gi.head_file and mine) else None
         bw = None
-        if write_output and gi.budget_file:
-            bw = BudgetFileWriter(gi.budget_file, gi.shape, gi.name)
+        if write_output and gi.budget_file and mine:
+            if rank is not None:
+                log(f"warning: {gi.name}: budget files are not written by the split-model run")
+            else:
+                bw = BudgetFileWriter(gi.budget_file, gi.shape, gi.name)
         writers.append((hw, bw))
     current = [[None] * len(gi.packages) for gi in sim.models]     # list in force per package
     saving = [dict() for _ in sim.models]                          # rtype -> settings in force
@@ -138,11 +155,11 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
             reports.append(d)
             log(f"period {kper} step {kstp}: outer {d['outer_iterations']} inner {d['inner_iterations']} "
                 f"converged {d['converged']} budget discrepancy {d['pdiffr']:.3e} %")
-            x = S.x
+            x = S.x                      # split-model run: the owned cells = this rank's model
             for k, gi in enumerate(sim.models):
                 hw, bw = writers[k]
                 if hw and _should_save(saving[k].get("HEAD", []), kstp, nstp):
-                    h = x[offs[k]:offs[k] + gi.model.nodes].copy()
+                    h = (x if rank is not None else x[offs[k]:offs[k] + gi.model.nodes]).copy()
                     h[gi.model.ibound == 0] = DHNOFLO
                     hw.write(kstp, kper, pertim, totim, h)
                 if bw and _should_save(saving[k].get("BUDGET", []), kstp, nstp):
@@ -169,7 +186,10 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
             hw.close()
         if bw:
             bw.close()
-    heads = [S.x[offs[k]:offs[k] + gi.model.nodes].reshape(gi.shape) for k, gi in enumerate(sim.models)]
+    if rank is not None:
+        heads = [S.x.reshape(sim.models[rank].shape)]
+    else:
+        heads = [S.x[offs[k]:offs[k] + gi.model.nodes].reshape(gi.shape) for k, gi in enumerate(sim.models)]
     return dict(simulation=sim, reports=reports, heads=heads, solution=S)
 
 

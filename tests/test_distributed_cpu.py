@@ -156,3 +156,30 @@ def test_gloo_world2_halo_exchange_and_allgather():
         assert p.exitcode == 0
     assert [r[1] for r in res] == [True, True]
     assert res[0][2] == res[1][2] == SPEC.nlay * SPEC.nrow * SPEC.ncol
+
+
+@pytest.mark.parametrize("pr,pc", [(1, 2), (2, 2), (3, 2)])
+def test_generic_extraction_equals_the_block_builder(pr, pc):
+    """extract_submodel (any global model + owner map: the GWF-GWF exchange route) must cut the same
+    submodels out of the global DIS model as the dedicated block builder"""
+    from modflow6_b200.distributed import block_ranges, extract_submodel
+    g = _global().model
+    rb, cb = block_ranges(SPEC.nrow, pr), block_ranges(SPEC.ncol, pc)
+    k, i, j = np.unravel_index(np.arange(g.nodes), (SPEC.nlay, SPEC.nrow, SPEC.ncol))
+    bi = np.searchsorted(np.array([r[1] for r in rb]), i, side="right")
+    bj = np.searchsorted(np.array([c[1] for c in cb]), j, side="right")
+    owner = bi * pc + bj
+    pk = global_packages_c2(SPEC)
+    for rank in range(pr * pc):
+        a, b = build_dis_block(SPEC, pr, pc, rank), extract_submodel(g, owner, rank, pr * pc)
+        assert a.n_own == b.n_own and np.array_equal(a.global_id, b.global_id)
+        assert np.array_equal(a.nbr_rank, b.nbr_rank) and np.array_equal(a.recv_ptr, b.recv_ptr)
+        assert np.array_equal(a.send_ptr, b.send_ptr) and np.array_equal(a.send_idx, b.send_idx)
+        ta, tb = _conn_table(a), _conn_table(b)
+        assert ta.keys() == tb.keys()
+        for key in ta:
+            assert ta[key] == tb[key], key
+        for name in ("top", "bot", "area", "k11", "k33", "strt", "ibound", "icelltype"):
+            assert np.array_equal(getattr(a.model, name), getattr(b.model, name)), name
+        for pa, pb in zip(a.localize_packages(pk), b.localize_packages(pk)):
+            assert np.array_equal(pa.nodelist, pb.nodelist) and np.array_equal(pa.b1, pb.b1)
