@@ -16,7 +16,9 @@ Metric: IMS cell-iterations per second = cells x inner iterations / time.
   roofline : the CSR/SELL SpMV kernel (dominant single kernel), algorithmic bytes / mean
           launch duration measured with CUDA events inside the timed region
   cpu_baseline : the C oracle (port of the reference algorithm, 1 core) on a bounded
-          sample of the same workload
+          sample of the same workload; the same leg (rank 0, N = 1) also reports `parity`:
+          GPU vs oracle on a reduced C2 -- iteration counts side by side, max |dhead|
+          against the 0.1 x OUTER_DVCLOSE bound, budget discrepancy (never timed)
 """
 import argparse
 import ctypes as C
@@ -143,6 +145,28 @@ def algorithmic_bytes(n, nja):
     ilu = 12 * (nja - n) + 8 * n + 4 * (n + 1) + 4 * n + 32 * n
     return {"spmv": spmv, "ilu0_apply": ilu, "update": 6 * 8 * n, "dot": 2 * 8 * n, "direction": 3 * 8 * n,
             "cg_iteration": spmv + ilu + 9 * 8 * n}
+
+
+def parity_check(ordering, size=(4, 48, 64)):
+    """GPU vs the CPU oracle on a reduced C2 (the oracle finishes in a second), reported beside the timing:
+    iteration counts side by side, max |dhead| against the 0.1 x OUTER_DVCLOSE bound, budget discrepancy.
+    The checker is the oracle; nothing here is timed."""
+    from modflow6_b200 import configs, ctypes_types as T
+    from modflow6_b200.solution import GpuNumericalSolution
+    from oracle.oracle import OracleSolution
+    cfg = build_config(size, ordering)
+    G = GpuNumericalSolution(cfg.model, cfg.sln, cfg.ims)
+    perm = None if cfg.ims.gpu_ordering == T.ORDER_NATURAL else G.elimination_order()
+    O = OracleSolution(cfg.model, cfg.sln, cfg.ims, perm=perm)
+    rg = configs.run_simulation(G, cfg)[0]
+    ro = configs.run_simulation(O, cfg)[0]
+    dh = float(np.abs(G.x - O.x).max())
+    G.destroy()
+    return {"case": f"C2 recipe {size[0]}x{size[1]}x{size[2]}, same ILU ordering in the oracle",
+            "max_abs_dhead": dh, "tolerance": 0.1 * cfg.sln.dvclose, "ok": bool(dh <= 0.1 * cfg.sln.dvclose),
+            "outer_iterations": {"gpu": rg["outer_iterations"], "oracle": ro["outer_iterations"]},
+            "inner_iterations": {"gpu": rg["inner_iterations"], "oracle": ro["inner_iterations"]},
+            "budget_pct_discrepancy": {"gpu": rg["pdiffr"], "oracle": ro["pdiffr"]}}
 
 
 class CpuSample:
@@ -377,6 +401,7 @@ def main():
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:
+            line["parity"] = parity_check(args.ordering)
             s = CpuSample(build_config(size, "natural"), args.cpu_iters).run()
             line["cpu_baseline"] = {"value": s["value"], "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": f"C oracle (port; no Fortran compiler in the image), 1 outer iteration "
