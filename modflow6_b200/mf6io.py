@@ -1,5 +1,6 @@
 """Reader for the subset of MODFLOW 6 input files that feeds the accelerated path (SURVEY.md section 8f,
-rank 3): mfsim.nam, TDIS, IMS, GWF name file, DIS, DISV, IC, NPF, STO, CHD/WEL/DRN/RIV/GHB/RCH (list based), OC and
+rank 3): mfsim.nam, TDIS, IMS, GWF name file, DIS, DISV, IC, NPF, STO, CHD/WEL/DRN/RIV/GHB/RCH lists, array-based
+RCH (READASARRAYS), OC and
 GWF-GWF exchanges -- enough to run FloPy-written models such as the reference's `.mf6minsim/` example through
 `mf6gpu_solution_*` without the Fortran host (which cannot be built in this image).
 
@@ -296,13 +297,37 @@ def _cellid(tokens, shape):
     raise Mf6InputError("only DIS cellids are supported")
 
 
+def _read_rcha(blocks, name, shape):
+    """array-based recharge (gwf-rcha.dfn): PERIOD blocks hold IRCH (layer of every 2-D cell, default 1) and
+    RECHARGE arrays; an array that a block omits keeps its previous values (rch_rp / RchType read_initial_attr).
+    Turned into the equivalent list: one boundary per 2-D cell at (irch, cell)."""
+    ncpl = int(np.prod(shape[1:]))
+    a2 = (1,) + tuple(shape[1:]) if len(shape) == 3 else (1, 1, shape[1])
+    irch = np.ones(ncpl, dtype=np.int32)
+    rech = np.zeros(ncpl)
+    periods = {}
+    for nm, num, lines in blocks:
+        if nm != "PERIOD":
+            continue
+        g = read_griddata(lines, "", {"IRCH": (a2, np.int32), "RECHARGE": (a2, np.float64)})
+        irch = g.get("IRCH", irch)
+        rech = g.get("RECHARGE", rech)
+        if irch.min() < 1 or irch.max() > shape[0]:
+            raise Mf6InputError(f"RCHA {name}: IRCH outside 1..{shape[0]}")
+        nodes = (irch.astype(np.int64) - 1) * ncpl + np.arange(ncpl)
+        periods[num] = Package(T.PKG_RCH, nodes, rech.copy())
+    return StressPackage("RCH", name, periods)
+
+
 def read_stress_package(path, ftype, name, shape):
     b = read_blocks(path)
     opt = _options(_block(b, "OPTIONS", required=False))
     naux = len(opt.get("AUXILIARY", opt.get("AUX", [])))
     for k in opt:
-        if k in ("READASARRAYS", "TS6", "TAS6", "MOVER", "AUXMULTNAME"):
+        if k in ("TS6", "TAS6", "MOVER", "AUXMULTNAME") or (k == "READASARRAYS" and ftype != "RCH6"):
             raise Mf6InputError(f"{path}: option {k} is not supported on the GPU path")
+    if "READASARRAYS" in opt:
+        return _read_rcha(b, name, shape), naux
     iflowred, flowred = 0, 0.1
     if "AUTO_FLOW_REDUCE" in opt:
         iflowred, flowred = 1, float(opt["AUTO_FLOW_REDUCE"][0]) if opt["AUTO_FLOW_REDUCE"] else 0.1

@@ -186,10 +186,11 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
             hw.close()
         if bw:
             bw.close()
+    xf = np.array(S.x, copy=True)      # (a solution class may hand out a view of memory it owns)
     if rank is not None:
-        heads = [S.x.reshape(sim.models[rank].shape)]
+        heads = [xf.reshape(sim.models[rank].shape)]
     else:
-        heads = [S.x[offs[k]:offs[k] + gi.model.nodes].reshape(gi.shape) for k, gi in enumerate(sim.models)]
+        heads = [xf[offs[k]:offs[k] + gi.model.nodes].reshape(gi.shape) for k, gi in enumerate(sim.models)]
     return dict(simulation=sim, reports=reports, heads=heads, solution=S)
 
 

@@ -53,7 +53,7 @@ def _disv_text(shape, delr, delc, top, botm):
 
 
 def write_gwf(d, name, shape, delr, delc, top, botm, k, chd=None, wel=None, icelltype=0, strt=0.0, k33=None,
-              sto=None, oc=True, newton=False, disv=False):
+              sto=None, oc=True, newton=False, disv=False, extra_packages=()):
     """chd / wel: dict iper -> list of ((k,i,j), value) with 1-based cellids.  disv=True writes the same
     rectangular grid as a DISV package (cellids become layer, icell2d)"""
     nlay, nrow, ncol = shape
@@ -89,6 +89,9 @@ def write_gwf(d, name, shape, delr, delc, top, botm, k, chd=None, wel=None, icel
             s += f"BEGIN period  {iper}\n" + "".join(f"  {cid(c)}  {v!r}\n" for c, v in rows) \
                 + f"END period  {iper}\n\n"
         _w(os.path.join(d, f"{name}.{ft.lower()}"), s)
+    for ft, ext, text in extra_packages:          # (ftype, file extension, file text)
+        pk += f"  {ft}  {name}.{ext}  {ext}_0\n"
+        _w(os.path.join(d, f"{name}.{ext}"), text)
     if oc:
         pk += f"  OC6  {name}.oc  oc\n"
         _w(os.path.join(d, f"{name}.oc"),

@@ -204,3 +204,39 @@ def test_multi_model_budget_files(tmp_path):
     np.add.at(resid, left[1]["node"] - 1, left[1]["q"])
     np.add.at(resid, ex_l["node"] - 1, ex_l["q"])
     assert np.abs(resid).max() < 1e-4
+
+
+def test_array_based_recharge_equals_the_list(tmp_path):
+    """RCH with READASARRAYS (IRCH + RECHARGE arrays, omitted arrays keep their values) against the same
+    recharge written as a list; convertible top layer + NEWTON so that recharge drives a water table"""
+    rng = np.random.default_rng(3)
+    shape = (2, 4, 5)
+    rate = rng.uniform(1e-4, 5e-4, (4, 5))
+    irch = np.ones((4, 5), dtype=int)
+    irch[1, 2] = 2
+    chd = [((2, i + 1, 1), 3.0) for i in range(4)]
+    ims = ("BEGIN nonlinear\n  OUTER_DVCLOSE 1e-8\n  OUTER_MAXIMUM 100\nEND nonlinear\n\n"
+           "BEGIN linear\n  INNER_MAXIMUM 100\n  INNER_DVCLOSE 1e-9\n  INNER_RCLOSE 1e-7\n  LINEAR_ACCELERATION BICGSTAB\nEND linear\n")
+    arr = lambda a: "\n".join("      " + " ".join(repr(float(v)) for v in row) for row in a)   # noqa: E731
+    rcha = ("BEGIN options\n  READASARRAYS\nEND options\n\nBEGIN period 1\n  irch\n    INTERNAL FACTOR 1\n" + arr(irch)
+            + "\n  recharge\n    INTERNAL FACTOR 1.0\n" + arr(rate) + "\nEND period 1\n\n"
+            "BEGIN period 2\n  recharge\n    INTERNAL FACTOR 2.0\n" + arr(rate) + "\nEND period 2\n")
+    rows = lambda f: "".join(f"  {irch[i, j]} {i + 1} {j + 1}  {float(f * rate[i, j])!r}\n"   # noqa: E731
+                             for i in range(4) for j in range(5))
+    rchl = ("BEGIN options\nEND options\n\nBEGIN dimensions\n  MAXBOUND 20\nEND dimensions\n\nBEGIN period 1\n" + rows(1.0)
+            + "END period 1\n\nBEGIN period 2\n" + rows(2.0) + "END period 2\n")
+    heads = {}
+    for tag, text in (("arrays", rcha), ("list", rchl)):
+        d = tmp_path / tag
+        d.mkdir()
+        mf6_inputs.write_gwf(str(d), "m", shape, 100.0, 100.0, 10.0, [0.0, -10.0], 2.0, chd={1: chd}, icelltype=1,
+                             strt=5.0, newton=True, extra_packages=[("RCH6", "rch", text)])
+        mf6_inputs.write_sim(str(d), ["m"], [(1.0, 1, 1.0), (1.0, 1, 1.0)], ims)
+        out = simulate.run(str(d), ordering=T.ORDER_NATURAL, solution_class=oracle_class())
+        assert all(r["converged"] for r in out["reports"])
+        heads[tag] = out["heads"][0]
+        cbc = read_budget_file(d / "m.cbc")
+        rch = [r for r in cbc if r["text"].strip() == "RCH"][-1]
+        assert rch["node"].size == 20 and np.isclose(rch["q"].sum(), 2.0 * rate.sum() * 100.0 * 100.0)
+    assert np.array_equal(heads["arrays"], heads["list"])
+    assert heads["list"].max() > 3.0       # recharge mounds the water table above the CHD stage
