@@ -240,3 +240,39 @@ def test_array_based_recharge_equals_the_list(tmp_path):
         assert rch["node"].size == 20 and np.isclose(rch["q"].sum(), 2.0 * rate.sum() * 100.0 * 100.0)
     assert np.array_equal(heads["arrays"], heads["list"])
     assert heads["list"].max() > 3.0       # recharge mounds the water table above the CHD stage
+
+
+def test_riv_ghb_drn_lists(tmp_path):
+    """the head-dependent list packages (stage/cond/rbot, bhead/cond, elev/cond column order of the dfn files),
+    with an AUXILIARY column and BOUNDNAMES that the path ignores, equal the directly built packages"""
+    shape = (1, 6, 7)
+    node = lambda c: ((c[0] - 1) * 6 + c[1] - 1) * 7 + c[2] - 1   # noqa: E731
+    riv = [((1, i + 1, 1), 9.0, 50.0, 7.5) for i in range(6)]
+    ghb = [((1, i + 1, 7), 6.0, 20.0) for i in range(6)]
+    drn = [((1, 3, 4), 6.5, 80.0), ((1, 4, 4), 7.0, 60.0)]
+    fmt = lambda rows, extra="": "".join("  " + " ".join(str(v) for v in r[0]) + "  "   # noqa: E731
+                                         + "  ".join(repr(float(v)) for v in r[1:]) + extra + "\n" for r in rows)
+    hdr = "BEGIN options\n{}END options\n\nBEGIN dimensions\n  MAXBOUND 10\nEND dimensions\n\nBEGIN period 1\n"
+    extra = [("RIV6", "riv", hdr.format("  AUXILIARY conc\n  BOUNDNAMES\n") + fmt(riv, "  1.5  reach_a") + "END period 1\n"),
+             ("GHB6", "ghb", hdr.format("") + fmt(ghb) + "END period 1\n"),
+             ("DRN6", "drn", hdr.format("  PRINT_FLOWS\n") + fmt(drn) + "END period 1\n")]
+    ims = ("BEGIN nonlinear\n  OUTER_DVCLOSE 1e-9\n  OUTER_MAXIMUM 50\nEND nonlinear\n\n"
+           "BEGIN linear\n  INNER_MAXIMUM 100\n  INNER_DVCLOSE 1e-10\n  INNER_RCLOSE 1e-8\n  LINEAR_ACCELERATION BICGSTAB\nEND linear\n")
+    d = str(tmp_path)
+    mf6_inputs.write_gwf(d, "m", shape, 50.0, 50.0, 10.0, [0.0], 3.0, strt=8.0, extra_packages=extra)
+    mf6_inputs.write_sim(d, ["m"], [(1.0, 1, 1.0)], ims)
+    out = simulate.run(d, ordering=T.ORDER_NATURAL, solution_class=oracle_class())
+    sim = out["simulation"]
+    assert [p.ftype for p in sim.models[0].packages] == ["RIV", "GHB", "DRN"]
+    m = build_dis_model(1, 6, 7, 50.0, 50.0, 10.0, [0.0], 3.0, strt=8.0)
+    pk = [Package(T.PKG_RIV, [node(r[0]) for r in riv], [r[1] for r in riv], [r[2] for r in riv], [r[3] for r in riv]),
+          Package(T.PKG_GHB, [node(r[0]) for r in ghb], [r[1] for r in ghb], [r[2] for r in ghb]),
+          Package(T.PKG_DRN, [node(r[0]) for r in drn], [r[1] for r in drn], [r[2] for r in drn])]
+    O = oracle_class()(m, sim.sln, sim.ims)
+    O.set_packages(pk)
+    O.timestep(1, 1, 1.0, 1)
+    assert np.array_equal(out["heads"][0].ravel(), O.x)
+    assert 6.0 < out["heads"][0].min() and out["heads"][0].max() < 9.0
+    cbc = read_budget_file(tmp_path / "m.cbc")
+    assert [r["text"].strip() for r in cbc] == ["FLOW-JA-FACE", "RIV", "GHB", "DRN"]
+    assert cbc[1]["q"].sum() > 0 > cbc[2]["q"].sum() and (cbc[3]["q"] <= 0).all()      # river feeds, GHB / drains take
