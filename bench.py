@@ -401,7 +401,10 @@ def main():
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:
-            line["parity"] = parity_check(args.ordering)
+            try:
+                line["parity"] = parity_check(args.ordering)
+            except Exception as e:   # the side report must not cost the measurement; say so in the line
+                line["parity"] = {"error": f"{type(e).__name__}: {e}"}
             s = CpuSample(build_config(size, "natural"), args.cpu_iters).run()
             line["cpu_baseline"] = {"value": s["value"], "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": f"C oracle (port; no Fortran compiler in the image), 1 outer iteration "
