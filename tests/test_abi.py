@@ -2,6 +2,7 @@
 import ctypes as C
 import os
 import re
+import subprocess
 
 import pytest
 
@@ -60,3 +61,23 @@ def test_fortran_shim_binds_existing_symbols():
             assert m in names, f"{f}: {m} is not declared in include/mf6gpu.h"
             found += 1
     assert found >= 10
+
+
+def _build_c_host(tmp_path):
+    exe = str(tmp_path / "host_cabi")
+    libdir = os.path.join(ROOT, "modflow6_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "host_cabi.c"), "-L" + libdir, "-lmf6gpu",
+                           "-Wl,-rpath," + libdir, "-o", exe])
+    return exe
+
+
+def test_header_is_plain_c_and_a_c_host_links(tmp_path):
+    """include/mf6gpu.h compiles as strict C99 and a C program links against libmf6gpu.so; without a GPU the
+    program stops at mf6gpu_init with the library's error text (exit code 3): no CPU fallback"""
+    import torch
+    exe = _build_c_host(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert "abi 1" in r.stdout
+    if not torch.cuda.is_available():
+        assert r.returncode == 3 and "no usable GPU" in r.stdout

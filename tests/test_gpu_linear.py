@@ -230,3 +230,13 @@ def test_vector_ops(gpu):
     assert np.array_equal(va.get_array(), a + (-2.5) * b)
     va.zero_entries()
     assert va.norm2() == 0.0
+
+
+def test_c_host_program(gpu, tmp_path):
+    """examples/host_cabi.c: a plain C program driving the LinearSolverBase seam of the C ABI solves the
+    test_gwf_chd01 system (heads == linspace(1, 0, 100))"""
+    import subprocess
+    from tests.test_abi import _build_c_host
+    r = subprocess.run([_build_c_host(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "converged 1" in r.stdout
