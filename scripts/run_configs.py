@@ -26,9 +26,9 @@ ORD = {"block": T.ORDER_BLOCK_MULTICOLOR, "multicolor": T.ORDER_MULTICOLOR, "nat
 def mk(name):
     s = scale
     if name == "c1":
-        return configs.c1_npf01("b", T.ORDER_NATURAL)
+        return configs.c1_npf01("b", ORD)
     if name == "c1a":
-        return configs.c1_npf01("a", T.ORDER_NATURAL)
+        return configs.c1_npf01("a", ORD)
     if name == "c2":
         return configs.c2_confined(10, int(1000 * s), int(1000 * s), ORD)
     if name == "c3":
@@ -49,7 +49,7 @@ for name in which:
     reps = configs.run_simulation(G, cfg)
     t3 = time.time()
     h = G.x
-    out = {"config": cfg.name, "ordering": order_name if name not in ("c1", "c1a") else "natural",
+    out = {"config": cfg.name, "ordering": order_name,
            "sweep_affine_colours": int(G.stat(5)), "sell_width": int(G.stat(4)), "cells": cfg.model.nodes, "nja": cfg.model.nja, "ilu_levels": int(G.stat(1)),
            "build_model_s": round(t1 - t0, 2), "gpu_setup_s": round(t2 - t1, 2), "run_s": round(t3 - t2, 3),
            "steps": len(reps), "converged": [r["converged"] for r in reps],
