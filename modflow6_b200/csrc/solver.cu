@@ -23,6 +23,7 @@
 #include <cstring>
 
 namespace mf6 {
+constexpr int kGraphMaxRows = 2000000;  // above this an iteration is GPU-bound: plain launches
 
 enum { TK_DOT = 0, TK_SPMV = 1, TK_UPD = 2, TK_NRM = 3 };
 // finalisation modes of the reduction kernels
@@ -761,74 +762,104 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
     if (bcgs) copy_kernel<<<G, kBlock, 0, S>>>(N, d.p, dhat.p);
     int launched = 0;
     bool finished = false;
+    // one inner iteration = a fixed sequence of launches whose arguments never change (the scalars live in
+    // KState): small systems are launch-bound on the host, so iterations 2.. replay a CUDA graph of the
+    // sequence captured once per solve (not on the split-model path, while profiling, or with NORTH > 0)
+    auto enqueue_iteration = [&](int first) {
+      if (!bcgs) {
+        prof_begin(PC_ILU);
+        if (fuse_dot) {
+          // z = M^-1 d with rho = d.z (and beta = rho/rho0) accumulated by the same launches
+          launches += ilu0_apply(*A, lu.p, d.p, z.p, &st.p->done, S, &idot);
+          reduce_finalize(FIN_CG_RHO, nullptr, 0);
+          prof_end();
+        } else {
+          launches += ilu0_apply(*A, lu.p, d.p, z.p, &st.p->done, S);
+          prof_end();
+          prof_begin(PC_DOT);
+          dot_kernel<<<G, kBlock, 0, S>>>(N, d.p, z.p, partial.p, tickets.p + TK_DOT, st.p,
+                                    FIN_CG_RHO, nullptr, 1);
+          reduce_finalize(FIN_CG_RHO, nullptr, 0);
+          prof_end();
+          launches += 1;
+        }
+        prof_begin(PC_PUPD);
+        cg_p_kernel<<<G, kBlock, 0, S>>>(N, z.p, p.p, st.p, first);
+        if (dist) halo->exchange(p.p, S);
+        prof_end();
+        prof_begin(PC_SPMV);
+        launch_spmv_fused<0, 1>(*A, G, S, p.p, q.p, nullptr, p.p, partial.p, tickets.p + TK_SPMV, st.p,
+                            FIN_CG_ALPHA, 1);
+        reduce_finalize(FIN_CG_ALPHA, nullptr, 0);
+        prof_end();
+        prof_begin(PC_UPD);
+        update_kernel<0><<<G, kBlock, 0, S>>>(N, x_dev, d.p, p.p, q.p, nullptr, nullptr, nullptr,
+                                        ord, partial.p, pmx.p, pmr.p, tickets.p + TK_UPD,
+                                        st.p, sp);
+        reduce_finalize(FIN_UPDATE, nullptr, 0);
+        prof_end();
+        launches += 3;
+      } else {
+        dot_kernel<<<G, kBlock, 0, S>>>(N, dhat.p, d.p, partial.p, tickets.p + TK_DOT, st.p,
+                                  FIN_BCGS_RHO, nullptr, 1);
+        reduce_finalize(FIN_BCGS_RHO, nullptr, 1);
+        bcgs_p_kernel<<<G, kBlock, 0, S>>>(N, d.p, v.p, p.p, st.p, first);
+        prof_begin(PC_ILU);
+        launches += ilu0_apply(*A, lu.p, p.p, phat.p, &st.p->done, S);
+        if (dist) halo->exchange(phat.p, S);
+        prof_end();
+        prof_begin(PC_SPMV);
+        launch_spmv_fused<0, 1>(*A, G, S, phat.p, v.p, nullptr, dhat.p, partial.p, tickets.p + TK_SPMV,
+                            st.p, FIN_BCGS_ALPHA, 1);
+        reduce_finalize(FIN_BCGS_ALPHA, nullptr, 1);
+        prof_end();
+        bcgs_q_kernel<<<G, kBlock, 0, S>>>(N, d.p, v.p, q.p, st.p);
+        prof_begin(PC_ILU);
+        launches += ilu0_apply(*A, lu.p, q.p, qhat.p, &st.p->done, S);
+        if (dist) halo->exchange(qhat.p, S);
+        prof_end();
+        prof_begin(PC_SPMV);
+        launch_spmv_fused<0, 2>(*A, G, S, qhat.p, t.p, nullptr, q.p, partial.p, tickets.p + TK_SPMV, st.p,
+                            FIN_BCGS_OMEGA, 1);
+        reduce_finalize(FIN_BCGS_OMEGA, nullptr, 1);
+        prof_end();
+        update_kernel<1><<<G, kBlock, 0, S>>>(N, x_dev, d.p, phat.p, q.p, qhat.p, t.p, dscale.p,
+                                        ord, partial.p, pmx.p, pmr.p, tickets.p + TK_UPD,
+                                        st.p, sp);
+        reduce_finalize(FIN_UPDATE, nullptr, 1);
+        launches += 6;
+      }
+    };
+    const bool use_graph = !dist && !profiling && s.north == 0 && N <= kGraphMaxRows && itmax > 1 &&
+                           !std::getenv("MF6GPU_NO_GRAPH");
+    cudaGraphExec_t gexec = nullptr;
+    int graph_launches = 0;
     while (!finished && launched < itmax) {
       const int nb = std::min(batch, itmax - launched);
       for (int b = 0; b < nb; b++) {
         const int iiter = launched + b + 1;
-        const int first = (iiter == 1) ? 1 : 0;
         prof_on = (b == 0);  // time one iteration per polling batch
-        if (!bcgs) {
-          prof_begin(PC_ILU);
-          if (fuse_dot) {
-            // z = M^-1 d with rho = d.z (and beta = rho/rho0) accumulated by the same launches
-            launches += ilu0_apply(*A, lu.p, d.p, z.p, &st.p->done, S, &idot);
-            reduce_finalize(FIN_CG_RHO, nullptr, 0);
-            prof_end();
-          } else {
-            launches += ilu0_apply(*A, lu.p, d.p, z.p, &st.p->done, S);
-            prof_end();
-            prof_begin(PC_DOT);
-            dot_kernel<<<G, kBlock, 0, S>>>(N, d.p, z.p, partial.p, tickets.p + TK_DOT, st.p,
-                                            FIN_CG_RHO, nullptr, 1);
-            reduce_finalize(FIN_CG_RHO, nullptr, 0);
-            prof_end();
-            launches += 1;
+        if (use_graph && iiter > 1) {
+          if (!gexec) {
+            cudaGraph_t graph = nullptr;
+            const int before = launches;
+            if (!cap_stream) MF6_CK(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
+            const cudaStream_t work = S;
+            S = cap_stream;  // the launches of enqueue_iteration go to S
+            MF6_CK(cudaStreamBeginCapture(S, cudaStreamCaptureModeThreadLocal));
+            enqueue_iteration(0);
+            const cudaError_t cap_rc = cudaStreamEndCapture(S, &graph);
+            S = work;
+            MF6_CK(cap_rc);
+            graph_launches = launches - before;
+            launches = before;
+            MF6_CK(cudaGraphInstantiate(&gexec, graph, 0));
+            MF6_CK(cudaGraphDestroy(graph));
           }
-          prof_begin(PC_PUPD);
-          cg_p_kernel<<<G, kBlock, 0, S>>>(N, z.p, p.p, st.p, first);
-          if (dist) halo->exchange(p.p, S);
-          prof_end();
-          prof_begin(PC_SPMV);
-          launch_spmv_fused<0, 1>(*A, G, S, p.p, q.p, nullptr, p.p, partial.p, tickets.p + TK_SPMV, st.p,
-                                  FIN_CG_ALPHA, 1);
-          reduce_finalize(FIN_CG_ALPHA, nullptr, 0);
-          prof_end();
-          prof_begin(PC_UPD);
-          update_kernel<0><<<G, kBlock, 0, S>>>(N, x_dev, d.p, p.p, q.p, nullptr, nullptr, nullptr,
-                                                ord, partial.p, pmx.p, pmr.p, tickets.p + TK_UPD,
-                                                st.p, sp);
-          reduce_finalize(FIN_UPDATE, nullptr, 0);
-          prof_end();
-          launches += 3;
+          MF6_CK(cudaGraphLaunch(gexec, S));
+          launches += graph_launches;
         } else {
-          dot_kernel<<<G, kBlock, 0, S>>>(N, dhat.p, d.p, partial.p, tickets.p + TK_DOT, st.p,
-                                          FIN_BCGS_RHO, nullptr, 1);
-          reduce_finalize(FIN_BCGS_RHO, nullptr, 1);
-          bcgs_p_kernel<<<G, kBlock, 0, S>>>(N, d.p, v.p, p.p, st.p, first);
-          prof_begin(PC_ILU);
-          launches += ilu0_apply(*A, lu.p, p.p, phat.p, &st.p->done, S);
-          if (dist) halo->exchange(phat.p, S);
-          prof_end();
-          prof_begin(PC_SPMV);
-          launch_spmv_fused<0, 1>(*A, G, S, phat.p, v.p, nullptr, dhat.p, partial.p, tickets.p + TK_SPMV,
-                                  st.p, FIN_BCGS_ALPHA, 1);
-          reduce_finalize(FIN_BCGS_ALPHA, nullptr, 1);
-          prof_end();
-          bcgs_q_kernel<<<G, kBlock, 0, S>>>(N, d.p, v.p, q.p, st.p);
-          prof_begin(PC_ILU);
-          launches += ilu0_apply(*A, lu.p, q.p, qhat.p, &st.p->done, S);
-          if (dist) halo->exchange(qhat.p, S);
-          prof_end();
-          prof_begin(PC_SPMV);
-          launch_spmv_fused<0, 2>(*A, G, S, qhat.p, t.p, nullptr, q.p, partial.p, tickets.p + TK_SPMV, st.p,
-                                  FIN_BCGS_OMEGA, 1);
-          reduce_finalize(FIN_BCGS_OMEGA, nullptr, 1);
-          prof_end();
-          update_kernel<1><<<G, kBlock, 0, S>>>(N, x_dev, d.p, phat.p, q.p, qhat.p, t.p, dscale.p,
-                                                ord, partial.p, pmx.p, pmr.p, tickets.p + TK_UPD,
-                                                st.p, sp);
-          reduce_finalize(FIN_UPDATE, nullptr, 1);
-          launches += 6;
+          enqueue_iteration(iiter == 1 ? 1 : 0);
         }
         if (s.north > 0 && ((iiter + 1) % s.north == 0)) {
           if (dist) halo->exchange(x_dev, S);
@@ -849,6 +880,7 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
         prof_collect();
       }
     }
+    if (gexec) MF6_CK(cudaGraphExecDestroy(gexec));
     innerit = h_st.p->iter;
     icnvg = h_st.p->icnvg;
   }
@@ -952,6 +984,7 @@ int mf6gpu_solver_destroy(mf6gpu_solver *s) {
     for (auto &e : s->ev)
       if (e) cudaEventDestroy(e);
     for (auto &e : s->ev_pool) cudaEventDestroy(e);
+    if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
     delete s;
   });
 }

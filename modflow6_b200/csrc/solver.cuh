@@ -65,6 +65,7 @@ struct mf6gpu_solver {
   double t_factor = 0.0, t_krylov = 0.0;
   long long launches = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t cap_stream = nullptr;     // capture-only stream of the inner-iteration graph (the work stream is the legacy default stream, which cannot capture)
   // optional per-kernel-class timing with CUDA events on the launching stream
   // (classes: 0 spmv, 1 ilu apply, 2 x/r update, 3 dot, 4 direction update, 5 factor)
   enum { PC_SPMV = 0, PC_ILU = 1, PC_UPD = 2, PC_DOT = 3, PC_PUPD = 4, PC_FACTOR = 5, PC_N = 6 };
