@@ -224,3 +224,44 @@ def test_backtracking_is_exercised():
     O = OracleSolution(cfg.model, cfg.sln, cfg.ims)
     reps = configs.run_simulation(O, cfg, max_steps=3)
     assert all(r["converged"] == 1 for r in reps) and sum(r["nbacktracks"] for r in reps) >= 2
+
+
+def test_ifmod_newton_split_equals_single():
+    """autotest/test_gwf_ifmod_newton.py:346-380 -- the reference's criterion for interface models: a Newton,
+    convertible-cell model split into two models joined by a GWF-GWF exchange gives the heads of the single
+    model (max |dh| < 10 x 1e-9 ... here 1e-8) and a budget that closes (|percent discrepancy| < 1e-5)"""
+    from modflow6_b200.grid import build_dis_model, merge_models
+    rng = np.random.default_rng(21)
+    nlay, nrow, ncol, half = 2, 4, 10, 5
+    k = np.exp(rng.normal(0.0, 0.5, (nlay, nrow, ncol)))
+    opts = dict(k33=None, icelltype=1, strt=6.0, inewton=1, inewtonur=1)
+    single = build_dis_model(nlay, nrow, ncol, 50.0, 50.0, 10.0, [0.0, -10.0], k, **opts)
+    parts = [build_dis_model(nlay, nrow, half, 50.0, 50.0, 10.0, [0.0, -10.0], k[:, :, :half], **opts),
+             build_dis_model(nlay, nrow, ncol - half, 50.0, 50.0, 10.0, [0.0, -10.0], k[:, :, half:], **opts)]
+    node = lambda kk, i, j, nc: (kk * nrow + i) * nc + j   # noqa: E731
+    ki = [(kk, i) for kk in range(nlay) for i in range(nrow)]
+    exg = dict(m1=0, m2=1, nodem1=np.array([node(kk, i, half - 1, half) for kk, i in ki]),
+               nodem2=np.array([node(kk, i, 0, ncol - half) for kk, i in ki]), ihc=np.ones(len(ki), np.int32),
+               cl1=np.full(len(ki), 25.0), cl2=np.full(len(ki), 25.0), hwva=np.full(len(ki), 50.0))
+    merged, offs = merge_models(parts, [exg])
+    # global cell (kk, i, j) -> merged numbering
+    def to_merged(kk, i, j):
+        return node(kk, i, j, half) if j < half else int(offs[1]) + node(kk, i, j - half, ncol - half)
+    chd_cells = [(1, i, 0) for i in range(nrow)]
+    rch_cells = [(0, i, j) for i in range(nrow) for j in range(ncol)]
+    def pkgs(f):
+        return [Package(T.PKG_CHD, [f(*c) for c in chd_cells], np.full(len(chd_cells), 2.0)),
+                Package(T.PKG_RCH, [f(*c) for c in rch_cells], np.full(len(rch_cells), 2e-3))]
+    sln = T.SlnSettings.make(dvclose=1e-10, mxiter=200, nonmeth=3, theta=0.9, akappa=1e-4, iallowptc=0)
+    ims = T.ImsSettings.make(dvclose=1e-11, rclose=1e-9, iter1=200, ilinmeth=2, relax=0.0)
+    A = OracleSolution(single, sln, ims)
+    A.set_packages(pkgs(lambda kk, i, j: node(kk, i, j, ncol)))
+    ra = A.timestep()
+    B = OracleSolution(merged, sln, ims)
+    B.set_packages(pkgs(to_merged))
+    rb = B.timestep()
+    assert ra.converged == 1 and rb.converged == 1
+    hb = np.array([B.x[to_merged(kk, i, j)] for kk in range(nlay) for i in range(nrow) for j in range(ncol)])
+    assert np.abs(A.x - hb).max() < 1e-8
+    assert abs(ra.pdiffr) < 1e-5 and abs(rb.pdiffr) < 1e-5
+    assert A.x.max() > 2.5 and A.x[: nrow * ncol].min() > 0.0   # a real water table in the convertible top layer
