@@ -52,3 +52,12 @@ def test_transient_deck_device_vs_oracle(gpu, tmp_path):
     for a, b in zip(bg, bc):
         va, vb = (a["flow"], b["flow"]) if a["imeth"] == 1 else (a["q"], b["q"])
         assert np.allclose(va, vb, rtol=1e-4, atol=1e-5 * max(1.0, np.abs(vb).max()))
+
+
+@pytest.mark.parametrize("ordering", [T.ORDER_NATURAL, T.ORDER_BLOCK_MULTICOLOR])
+def test_chd02_known_answer_on_device(gpu, tmp_path, ordering):
+    """autotest/test_gwf_chd02.py:72-87: literal heads of a 10-cell unconfined Picard solve"""
+    from tests.test_mf6io_cpu import CHD02_HEADS, write_chd02
+    write_chd02(str(tmp_path))
+    out = simulate.run(str(tmp_path), ordering=ordering)
+    assert np.allclose(CHD02_HEADS, out["heads"][0].ravel())

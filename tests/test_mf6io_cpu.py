@@ -276,3 +276,27 @@ def test_riv_ghb_drn_lists(tmp_path):
     cbc = read_budget_file(tmp_path / "m.cbc")
     assert [r["text"].strip() for r in cbc] == ["FLOW-JA-FACE", "RIV", "GHB", "DRN"]
     assert cbc[1]["q"].sum() > 0 > cbc[2]["q"].sum() and (cbc[3]["q"] <= 0).all()      # river feeds, GHB / drains take
+
+
+CHD02_HEADS = np.array([10.00, 9.57481441, 9.1298034, 8.66189866, 8.16714512, 7.64029169, 7.07409994, 6.45808724,
+                        5.77600498, 5.000])
+
+
+def write_chd02(d):
+    """autotest/test_gwf_chd02.py:14-62: 1 x 1 x 10 convertible cells (top 10, bottom 0, K = 1), CHD 10 and 5 at
+    the ends, IMS `COMPLEXITY SIMPLE`"""
+    mf6_inputs.write_gwf(d, "chd02", (1, 1, 10), 1.0, 1.0, 10.0, [0.0], 1.0,
+                         chd={1: [((1, 1, 1), 10.0), ((1, 1, 10), 5.0)]}, icelltype=1, strt=10.0)
+    mf6_inputs.write_sim(d, ["chd02"], [(1.0, 1, 1.0)], "BEGIN options\n  COMPLEXITY SIMPLE\nEND options\n")
+
+
+def test_chd02_known_answer(tmp_path):
+    """the literal head array of autotest/test_gwf_chd02.py:72-87 (unconfined Picard iteration stopped by the
+    SIMPLE preset's OUTER_DVCLOSE = 1e-3: reproducing it to np.allclose needs the same conductance formulation AND
+    the same iteration path)"""
+    write_chd02(str(tmp_path))
+    out = simulate.run(str(tmp_path), ordering=T.ORDER_NATURAL, solution_class=oracle_class())
+    sim = out["simulation"]
+    assert sim.sln.dvclose == 1e-3 and sim.sln.mxiter == 25 and sim.ims.iter1 == 50 and sim.ims.ilinmeth == 1
+    assert np.allclose(CHD02_HEADS, out["heads"][0].ravel())
+    assert np.abs(CHD02_HEADS - out["heads"][0].ravel()).max() < 1e-8
