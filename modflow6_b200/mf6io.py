@@ -338,6 +338,27 @@ def read_stress_package(path, ftype, name, shape):
             continue
         nodes, vals = [], []
         for t in lines:
+            if t[0].upper() == "OPEN/CLOSE":
+                # the list in an external file (ListReader.f90): text rows like the inline ones, or (BINARY)
+                # records of cellid as i32 followed by the bound and auxiliary columns as f64
+                fn = os.path.join(os.path.dirname(path), t[1])
+                if "(BINARY)" in [x.upper() for x in t[2:]]:
+                    nd = len(shape)
+                    dt = np.dtype([("cellid", "<i4", (nd,)), ("v", "<f8", (ncol + naux,))])
+                    rec = np.fromfile(fn, dtype=dt)
+                    for r in rec:
+                        node, _ = _cellid([str(int(c)) for c in r["cellid"]], shape)
+                        nodes.append(node)
+                        vals.append([float(x) for x in r["v"][:ncol]])
+                else:
+                    with open(fn) as f:
+                        for raw in f:
+                            tt = _tokens(raw)
+                            if tt:
+                                node, w = _cellid(tt, shape)
+                                nodes.append(node)
+                                vals.append([float(v) for v in tt[w:w + ncol]])
+                continue
             node, w = _cellid(t, shape)
             nodes.append(node)
             vals.append([float(v) for v in t[w:w + ncol]])

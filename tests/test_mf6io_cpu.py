@@ -300,3 +300,23 @@ def test_chd02_known_answer(tmp_path):
     assert sim.sln.dvclose == 1e-3 and sim.sln.mxiter == 25 and sim.ims.iter1 == 50 and sim.ims.ilinmeth == 1
     assert np.allclose(CHD02_HEADS, out["heads"][0].ravel())
     assert np.abs(CHD02_HEADS - out["heads"][0].ravel()).max() < 1e-8
+
+
+def test_chd02_binary_list_with_auxiliary(tmp_path):
+    """exactly what autotest/test_gwf_chd02.py is about: the CHD list comes from a BINARY OPEN/CLOSE file that
+    also carries two auxiliary columns; same literal answer"""
+    write_chd02(str(tmp_path))
+    rec = np.zeros(2, dtype=[("cellid", "<i4", (3,)), ("v", "<f8", (3,))])
+    rec["cellid"] = [(1, 1, 1), (1, 1, 10)]
+    rec["v"] = [(10.0, 1.0, 100.0), (5.0, 0.0, 100.0)]          # head, conc, something
+    rec.tofile(tmp_path / "chd.bin")
+    (tmp_path / "chd02.chd").write_text(
+        "BEGIN options\n  AUXILIARY conc something\nEND options\n\nBEGIN dimensions\n  MAXBOUND 2\nEND dimensions\n\n"
+        "BEGIN period 1\n  OPEN/CLOSE chd.bin (BINARY)\nEND period 1\n")
+    out = simulate.run(str(tmp_path), ordering=T.ORDER_NATURAL, solution_class=oracle_class())
+    assert np.allclose(CHD02_HEADS, out["heads"][0].ravel())
+    # and the text flavour of OPEN/CLOSE
+    (tmp_path / "chd.txt").write_text("1 1 1 10.0 1.0 100.0\n1 1 10 5.0 0.0 100.0\n")
+    (tmp_path / "chd02.chd").write_text((tmp_path / "chd02.chd").read_text().replace("chd.bin (BINARY)", "chd.txt"))
+    out = simulate.run(str(tmp_path), ordering=T.ORDER_NATURAL, solution_class=oracle_class())
+    assert np.allclose(CHD02_HEADS, out["heads"][0].ravel())
