@@ -153,6 +153,13 @@ module GpuNumericalSolutionModule
   use NumericalModelModule, only: NumericalModelType, GetNumericalModelFromList
   use GwfModule, only: GwfModelType
   use BndModule, only: BndType, GetBndFromList
+  use ChdModule, only: ChdType
+  use WelModule, only: WelType
+  use RivModule, only: RivType
+  use RchModule, only: RchType
+  use GhbModule, only: GhbType
+  use DrnModule, only: DrnType
+  use SimModule, only: store_error
   use TdisModule, only: kper, kstp, delt
   use Mf6GpuBindingsModule, only: mf6gpu_ims_settings, mf6gpu_check
   use GpuSolutionBindingsModule
@@ -239,16 +246,33 @@ contains
     allocate (pk(np))
     do ip = 1, np
       b => GetBndFromList(this%gwf%bndlist, ip)
-      pk(ip)%ptype = gpu_package_type(b%filtyp) ! CHD 1, WEL 2, RIV 3, RCH 4, GHB 5, DRN 6
       pk(ip)%nbound = b%nbound
       pk(ip)%index_base = 1
       pk(ip)%iflowred = 0
       pk(ip)%flowred = 0.0_DP
       pk(ip)%nodelist = c_loc(b%nodelist)
-      ! the columns of `bound` (BoundaryPackage.f90:47-166) in the order of mf6gpu_types.h
-      pk(ip)%b1 = c_loc(b%bound(1, 1)) ! NB: `bound` is (ncolbnd, maxbound): the shim packs the
-      pk(ip)%b2 = c_null_ptr           !     columns into contiguous work arrays before this call
+      pk(ip)%b2 = c_null_ptr
       pk(ip)%b3 = c_null_ptr
+      ! the packages keep their stress columns as separate contiguous arrays (gwf-chd.f90:26,
+      ! gwf-wel.f90:40, gwf-riv.f90:22-24, gwf-rch.f90:28, gwf-ghb.f90:22-23, gwf-drn.f90:26-27):
+      ! they are passed unchanged, in the column order of mf6gpu_types.h
+      select type (b)
+      type is (ChdType)
+        pk(ip)%ptype = 1; pk(ip)%b1 = c_loc(b%head)
+      type is (WelType)
+        pk(ip)%ptype = 2; pk(ip)%b1 = c_loc(b%q)
+        pk(ip)%iflowred = b%iflowred; pk(ip)%flowred = b%flowred
+      type is (RivType)
+        pk(ip)%ptype = 3; pk(ip)%b1 = c_loc(b%stage); pk(ip)%b2 = c_loc(b%cond); pk(ip)%b3 = c_loc(b%rbot)
+      type is (RchType)
+        pk(ip)%ptype = 4; pk(ip)%b1 = c_loc(b%recharge)
+      type is (GhbType)
+        pk(ip)%ptype = 5; pk(ip)%b1 = c_loc(b%bhead); pk(ip)%b2 = c_loc(b%cond)
+      type is (DrnType)
+        pk(ip)%ptype = 6; pk(ip)%b1 = c_loc(b%elev); pk(ip)%b2 = c_loc(b%cond)
+      class default
+        call store_error('package '//trim(b%packName)//' is outside the GPU path', terminate=.true.)
+      end select
     end do
     call mf6gpu_check(mf6gpu_solution_set_packages(this%handle, int(np, c_int32_t), pk))
   end subroutine gpu_sln_rp
@@ -282,19 +306,5 @@ contains
     this%handle = c_null_ptr
     call this%NumericalSolutionType%sln_da()
   end subroutine gpu_sln_da
-
-  pure function gpu_package_type(filtyp) result(t)
-    character(len=*), intent(in) :: filtyp
-    integer(c_int32_t) :: t
-    select case (trim(filtyp))
-    case ('CHD'); t = 1
-    case ('WEL'); t = 2
-    case ('RIV'); t = 3
-    case ('RCH'); t = 4
-    case ('GHB'); t = 5
-    case ('DRN'); t = 6
-    case default; t = 0
-    end select
-  end function gpu_package_type
 
 end module GpuNumericalSolutionModule
