@@ -51,6 +51,9 @@ def parse_args():
     ap.add_argument("--inner-maximum", type=int, default=500, help="INNER_MAXIMUM of the IMS LINEAR block")
     ap.add_argument("--outer-maximum", type=int, default=50, help="OUTER_MAXIMUM (1 = short profiling run)")
     ap.add_argument("--min-warmup", type=int, default=3)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = one --size block per GPU (default, the driver's scaling run); strong = the ONE "
+                         "--size grid cut into N row blocks (time-to-solution of the 1e7-cell model on N GPUs)")
     return ap.parse_args()
 
 
@@ -275,7 +278,10 @@ def main():
         # blocks are stacked along the rows (the no-flow direction): the constant heads stay 1000 columns
         # apart, so the conditioning -- and the inner-iteration count -- does not grow with the GPU count
         pr, pc = world, 1
-        spec = GridSpec(nlay=size[0], nrow=size[1] * pr, ncol=size[2] * pc)
+        if args.scaling == "strong":
+            spec = GridSpec(nlay=size[0], nrow=size[1], ncol=size[2])
+        else:
+            spec = GridSpec(nlay=size[0], nrow=size[1] * pr, ncol=size[2] * pc)
         sub = build_dis_block(spec, pr, pc, rank)
         o = {"multicolor": T.ORDER_MULTICOLOR, "natural": T.ORDER_NATURAL,
              "block": T.ORDER_BLOCK_MULTICOLOR}[args.ordering]
@@ -289,7 +295,9 @@ def main():
         nja = int(sub.model.ia[sub.n_own])
         n_total = spec.nlay * spec.nrow * spec.ncol
         strt = np.ascontiguousarray(sub.model.strt[:n])
-        layout = f"{pr}x{pc} blocks of {size[0]}x{size[1]}x{size[2]} cells, global {spec.nlay}x{spec.nrow}x{spec.ncol}"
+        i0, i1, j0, j1 = sub.block
+        layout = (f"{pr}x{pc} blocks of {size[0]}x{i1 - i0}x{j1 - j0} cells, global "
+                  f"{spec.nlay}x{spec.nrow}x{spec.ncol}")
     G.set_packages(pkgs)
     per_pkgs = G._pkgs
     pinned_x = torch.empty(n, dtype=torch.float64).pin_memory()
@@ -373,7 +381,8 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, args.min_warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
             "config": {"workload": f"C2 confined steady-state DIS {size[0]}x{size[1]}x{size[2]}, IMS CG+ILU0 "
                                    f"({args.ordering} ILU ordering)",
                        "cells": n_total, "cells_per_gpu": n, "nja_per_gpu": nja,
