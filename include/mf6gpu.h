@@ -196,6 +196,10 @@ int mf6gpu_solution_get_condsat(mf6gpu_solution *s, double *condsat);
  * save_print_model_flows (BoundaryPackage.f90:1753-1900) writes to the budget file.  *count = number
  * of boundaries; simvals may be NULL to query it */
 int mf6gpu_solution_get_simvals(mf6gpu_solution *s, int32_t cap, double *simvals, int32_t *count);
+/* the cell every boundary acted on in the last formulate, 0-based, packages concatenated like get_simvals.  Equal
+ * to the input nodelist except for RCH without FIXED_CELL, whose recharge rch_cf hands down to the highest
+ * active cell (gwf-rch.f90:315-333) -- the node the budget file records */
+int mf6gpu_solution_get_nodes(mf6gpu_solution *s, int32_t cap, int32_t *nodes, int32_t *count);
 /* STO-SS and STO-SY rates per cell of the last time step (sto_cq, gwf-sto.f90:447-564), original order */
 int mf6gpu_solution_get_storage(mf6gpu_solution *s, double *strgss, double *strgsy);
 /* elimination order of the owned cells (see mf6gpu_matrix_get_permutation) */

@@ -120,7 +120,8 @@ typedef struct mf6gpu_bnd_package {
   int32_t type;
   int32_t nbound;
   int32_t index_base;
-  int32_t iflowred;   /* WEL AUTO_FLOW_REDUCE on/off */
+  int32_t iflowred;   /* WEL: AUTO_FLOW_REDUCE on/off.  RCH: FIXED_CELL (0 = recharge goes to the highest active
+                         cell below the listed one, gwf-rch.f90:315-333; 1 = it stays on the listed cell) */
   double flowred;     /* WEL AUTO_FLOW_REDUCE fraction */
   const int32_t *nodelist; /* [nbound] */
   const double *b1;

@@ -92,6 +92,28 @@ __global__ void slot_condsat_kernel(long long nslots, const int *__restrict__ sl
   }
 }
 
+// sgwf_npf_wetdry without rewetting (gwf-npf.f90:2061-2158), the first thing npf_cf does for a model without
+// NEWTON: a convertible cell whose saturated thickness is gone becomes inactive for good (ibound0 keeps it so in
+// later stress periods), its head the dry value; a constant-head cell going dry is fatal (flag)
+__global__ void npf_wd_kernel(ModelView M, double *__restrict__ x, int *__restrict__ ibound,
+                              int *__restrict__ ibound0, int *__restrict__ flag) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < M.n; r += gridDim.x * blockDim.x) {
+    const int ib = ibound[r];
+    if (ib == 0 || M.icelltype[r] == 0) continue;
+    double ttop = M.top[r];
+    if (x[r] < ttop) ttop = x[r];
+    if (ttop - M.bot[r] <= 0.0) {
+      if (ib < 0) {
+        *flag = 1;
+        continue;
+      }
+      x[r] = -1.0e30;  // DHDRY
+      ibound[r] = 0;
+      ibound0[r] = 0;
+    }
+  }
+}
+
 // npf_cf (gwf-npf.f90:444-470) + thksat (:775-794)
 __global__ void npf_cf_kernel(ModelView M, const double *__restrict__ h, double *__restrict__ sat) {
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < M.n; r += gridDim.x * blockDim.x) {
@@ -120,6 +142,8 @@ struct BndView {
   const int *node;            // final numbering
   const double *b1, *b2, *b3, *fred;
   double *hcof, *rhs, *simvals, *ratein, *rateout;
+  int *eff;                   // cell the bound acts on (RCH without FIXED_CELL: the highest active cell)
+  const int *below;           // cell under every cell (final numbering, -1 = bottom), null when no cell can be inactive
 };
 
 // *_cf of WEL/RIV/RCH/GHB/DRN (gwf-wel.f90:296-332, gwf-riv.f90:270-299, gwf-rch.f90:303-353,
@@ -129,6 +153,7 @@ __global__ void bnd_cf_kernel(BndView B, ModelView M, const double *__restrict__
     const int node = B.node[i];
     const int ib = M.ibound[node];
     double hcof = 0.0, rhs = 0.0;
+    int eff = node;
     switch (B.type[i]) {
       case MF6GPU_PKG_WEL:
         if (ib > 0) {
@@ -154,10 +179,23 @@ __global__ void bnd_cf_kernel(BndView B, ModelView M, const double *__restrict__
           }
         }
         break;
-      case MF6GPU_PKG_RCH:
-        rhs = -B.b1[i] * M.area[node];
-        if (ib <= 0) rhs = 0.0;
+      case MF6GPU_PKG_RCH: {
+        // rch_cf (gwf-rch.f90:303-353); flag = FIXED_CELL.  Otherwise an inactive cell hands its recharge down
+        // the column to the first cell that is not inactive (highest_active, DiscretizationBase.f90:1077-1112)
+        int nd = node;
+        if (B.flag[i] == 0 && B.below && ib == 0) {
+          for (;;) {
+            const int b = B.below[nd];
+            if (b < 0) break;
+            nd = b;
+            if (M.ibound[nd] != 0) break;
+          }
+        }
+        eff = nd;
+        rhs = -B.b1[i] * M.area[nd];
+        if (M.ibound[nd] <= 0) rhs = 0.0;
         break;
+      }
       case MF6GPU_PKG_GHB:
         if (ib > 0) {
           hcof = -B.b2[i];
@@ -177,6 +215,7 @@ __global__ void bnd_cf_kernel(BndView B, ModelView M, const double *__restrict__
     }
     B.hcof[i] = hcof;
     B.rhs[i] = rhs;
+    B.eff[i] = eff;
   }
 }
 
@@ -199,6 +238,7 @@ __global__ void bnd_scatter_kernel(int nseg, const int *__restrict__ seg_node,
       for (int e = seg_ptr[sidx]; e < seg_ptr[sidx + 1]; e++) {
         const int i = seg_idx[e];
         if (B.type[i] == MF6GPU_PKG_CHD) continue;  // chd_fc is a no-op (gwf-chd.f90:238-246)
+        if (B.eff[i] != node) continue;              // recharge handed down the column: rch_moved_kernel
         r = r + B.rhs[i];
         diag = diag + B.hcof[i];
       }
@@ -230,12 +270,32 @@ __global__ void bnd_scatter_kernel(int nseg, const int *__restrict__ seg_node,
       for (int e = seg_ptr[sidx]; e < seg_ptr[sidx + 1]; e++) {
         const int i = seg_idx[e];
         if (B.type[i] == MF6GPU_PKG_CHD) continue;
+        if (B.eff[i] != node) continue;
         double rrate = 0.0;
         if (ib > 0) rrate = B.hcof[i] * x[node] - B.rhs[i];
         fd = fd + rrate;
         B.simvals[i] = rrate;
       }
       flowja[dslot] = fd;
+    }
+  }
+}
+
+// recharge that rch_cf handed down to another cell than the listed one (rare: dry or inactive top cells): its
+// rhs / rate goes to the row of the cell it acts on.  hcof of RCH is 0.  Distinct columns give distinct targets;
+// bounds of several RCH packages meeting in one cell are summed with atomicAdd.
+// mode 0: bnd_fc ; mode 2: bnd_cq_simrate
+__global__ void rch_moved_kernel(BndView B, ModelView M, double *__restrict__ rhsv, double *__restrict__ flowja,
+                                 int mode) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B.nb; i += gridDim.x * blockDim.x) {
+    const int nd = B.eff[i];
+    if (B.type[i] != MF6GPU_PKG_RCH || nd == B.node[i]) continue;
+    if (mode == 0) {
+      atomicAdd(&rhsv[nd], B.rhs[i]);
+    } else {
+      const double rrate = (M.ibound[nd] > 0) ? -B.rhs[i] : 0.0;
+      atomicAdd(&flowja[(long long)M.slice_ptr[nd >> 5] + (nd & 31)], rrate);
+      B.simvals[i] = rrate;
     }
   }
 }
@@ -828,6 +888,11 @@ struct mf6gpu_solution {
   DevBuf<double> strt;
   DevBuf<double> x, xold, sat, rhs, xtemp, dxold, wsave, hchold, deold, strgss, strgsy;
   DevBuf<int> icelltype, ibound, ibound0, iconvert, ibotnode;
+  DevBuf<int> below;     // cell under every cell (final numbering); only when a cell can be inactive
+  DevBuf<int> b_eff;     // [nb] cell every bound acts on
+  DevBuf<int> wd_flag;   // [1] a constant-head cell went dry
+  bool do_wd = false;    // npf wet/dry conversion applies (no NEWTON, convertible cells, single process)
+  bool moving_rch = false;  // some RCH package without FIXED_CELL and cells that can be inactive
   DevBuf<int> slot_conn;
   DevBuf<double> slot_condsat, flowja;
   DevBuf<double> condsat, cl1, cl2, hwva;
@@ -899,6 +964,8 @@ struct mf6gpu_solution {
     B.simvals = b_sim.p;
     B.ratein = b_rin.p;
     B.rateout = b_rout.p;
+    B.eff = b_eff.p;
+    B.below = below.n ? below.p : nullptr;
     return B;
   }
   // local record, or (split-model path) the records of all ranks combined on the host in rank
@@ -963,6 +1030,10 @@ void mf6gpu_solution::buildsystem(int inewton) {
   nl += (o.all_confined ? 0 : 1) + (nb > 0 ? 1 : 0) + 1 + (nseg > 0 ? 1 : 0);
   if (inewton && o.inewton) nl += 1 + (nseg > 0 ? 1 : 0);
   if (!o.all_confined) {
+    if (do_wd) {
+      npf_wd_kernel<<<grid_for(n), kBlock, 0, stream>>>(M, x.p, ibound.p, ibound0.p, wd_flag.p);
+      nl++;
+    }
     ModelView Me = M;
     Me.n = n_ext;  // saturation of the halo cells too
     npf_cf_kernel<<<grid_for(n_ext), kBlock, 0, stream>>>(Me, x.p, sat.p);
@@ -975,6 +1046,10 @@ void mf6gpu_solution::buildsystem(int inewton) {
   if (nseg > 0)
     bnd_scatter_kernel<<<grid_for(nseg), kBlock, 0, stream>>>(nseg, seg_node.p, seg_ptr.p, seg_idx.p, B, M,
                                                               x.p, A->val.p, rhs.p, flowja.p, 0);
+  if (moving_rch) {
+    rch_moved_kernel<<<grid_for(nb), kBlock, 0, stream>>>(B, M, rhs.p, flowja.p, 0);
+    nl++;
+  }
   if (inewton && o.inewton) {
     newton_rows_kernel<<<G, kBlock, 0, stream>>>(M, x.p, A->val.p, rhs.p, transient, tled);
     if (nseg > 0)
@@ -1291,6 +1366,26 @@ static void create_solution(const mf6gpu_gwf_model *m, const mf6gpu_sln_settings
       for (int i = 0; i < n; i++)
         if (m->icelltype[i] != 0) anyconv = true;
       o.all_confined = (!anyconv && m->iperched == 0 && m->inewton == 0) ? 1 : 0;
+      // cells can become / be inactive: wet-dry conversion (no NEWTON, convertible cells; not on the split-model
+      // path, where ibound of the halo is exchanged once per stress period) or IDOMAIN holes.  Recharge then needs
+      // the cell under every cell (highest_active walks the m > n vertical connections)
+      s->do_wd = (m->inewton == 0) && anyconv && !da;
+      s->wd_flag.alloc_zero(1);
+      bool anyinactive = false;
+      for (int i = 0; i < n_own; i++)
+        if (m->ibound && m->ibound[i] == 0) anyinactive = true;
+      if ((s->do_wd || anyinactive) && !da) {
+        std::vector<int> bel((size_t)n_own, -1);
+        for (int v = 0; v < n_own; v++)
+          for (int p = m->ia[v] - base + 1; p < m->ia[v + 1] - base; p++) {
+            const int u = m->ja[p] - base;
+            if (u > v && u < n_own && m->ihc[m->jas[p] - base] == 0) {
+              bel[(size_t)A->iperm[v]] = A->iperm[u];
+              break;
+            }
+          }
+        s->below.upload(bel);
+      }
       // per-cell arrays in final numbering
       s->top.upload(permuted(m->top, perm, 0.0));
       s->bot.upload(permuted(m->bot, perm, 0.0));
@@ -1473,6 +1568,11 @@ int mf6gpu_solution_set_packages(mf6gpu_solution *s, int32_t npkg, const mf6gpu_
     up(s->b_b2, b2);
     up(s->b_b3, b3);
     up(s->b_fred, fred);
+    s->b_eff.upload(node);   // until the first bnd_cf: every bound acts on its listed cell
+    s->moving_rch = false;
+    for (int k = 0; k < npkg; k++)
+      if (pk[k].type == MF6GPU_PKG_RCH && pk[k].iflowred == 0 && pk[k].nbound > 0 && s->below.n > 0)
+        s->moving_rch = true;
     s->b_hcof.alloc_zero(c);
     s->b_rhs.alloc_zero(c);
     s->b_sim.alloc_zero(c);
@@ -1555,6 +1655,7 @@ int mf6gpu_solution_timestep(mf6gpu_solution *s, int32_t kper, int32_t kstp, dou
       bnd_scatter_kernel<<<grid_for(s->nseg), kBlock, 0, st>>>(s->nseg, s->seg_node.p, s->seg_ptr.p,
                                                                s->seg_idx.p, B, M, s->x.p, s->A->val.p,
                                                                s->rhs.p, s->flowja.p, 2);
+      if (s->moving_rch) rch_moved_kernel<<<grid_for(s->nb), kBlock, 0, st>>>(B, M, s->rhs.p, s->flowja.p, 2);
     }
     // gwf_bd: csr_diagsum, then the budget entries (chd_bd computes the CHD rates)
     diagsum_kernel<<<G, kBlock, 0, st>>>(M, s->flowja.p);
@@ -1599,6 +1700,11 @@ int mf6gpu_solution_timestep(mf6gpu_solution *s, int32_t kper, int32_t kstp, dou
       rep->t_linsolve = tl;
     }
     MF6_CK(cudaStreamSynchronize(st));
+    if (s->do_wd) {
+      int dry = 0;
+      MF6_CK(cudaMemcpy(&dry, s->wd_flag.p, sizeof(int), cudaMemcpyDeviceToHost));
+      MF6_REQUIRE(dry == 0, "CONSTANT-HEAD CELL WENT DRY -- SIMULATION ABORTED (gwf-npf.f90:2137-2146)");
+    }
   });
 }
 
@@ -1675,6 +1781,20 @@ int mf6gpu_solution_get_simvals(mf6gpu_solution *s, int32_t cap, double *simvals
       MF6_REQUIRE(cap >= s->nb, "solution_get_simvals: buffer too small");
       MF6_CK(cudaMemcpyAsync(simvals, s->b_sim.p, sizeof(double) * (size_t)s->nb, cudaMemcpyDeviceToHost, s->stream));
       MF6_CK(cudaStreamSynchronize(s->stream));
+    }
+  });
+}
+
+int mf6gpu_solution_get_nodes(mf6gpu_solution *s, int32_t cap, int32_t *nodes, int32_t *count) {
+  return guard([&] {
+    MF6_REQUIRE(s && count, "solution_get_nodes: null argument");
+    *count = s->nb;
+    if (nodes && s->nb > 0) {
+      MF6_REQUIRE(cap >= s->nb, "solution_get_nodes: buffer too small");
+      std::vector<int> eff((size_t)s->nb);
+      MF6_CK(cudaMemcpyAsync(eff.data(), s->b_eff.p, sizeof(int) * (size_t)s->nb, cudaMemcpyDeviceToHost, s->stream));
+      MF6_CK(cudaStreamSynchronize(s->stream));
+      for (int i = 0; i < s->nb; i++) nodes[i] = s->A->perm[eff[(size_t)i]];
     }
   });
 }

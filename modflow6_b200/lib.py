@@ -29,7 +29,7 @@ SYMBOLS = [
     "mf6gpu_comm_unique_id", "mf6gpu_comm_create", "mf6gpu_comm_destroy", "mf6gpu_comm_rank", "mf6gpu_comm_size",
     "mf6gpu_comm_p2p_export", "mf6gpu_comm_p2p_import", "mf6gpu_comm_p2p_enabled", "mf6gpu_comm_p2p_disable",
     "mf6gpu_matrix_create_blocked", "mf6gpu_solution_get_permutation",
-    "mf6gpu_solution_get_simvals", "mf6gpu_solution_get_storage",
+    "mf6gpu_solution_get_simvals", "mf6gpu_solution_get_storage", "mf6gpu_solution_get_nodes",
 ]
 
 _lib = None
@@ -109,6 +109,7 @@ def load():
         getattr(L, "mf6gpu_solution_" + f).argtypes = [vp, pf64]
     L.mf6gpu_solution_get_simvals.argtypes = [vp, i32, pf64, pi32]
     L.mf6gpu_solution_get_storage.argtypes = [vp, pf64, pf64]
+    L.mf6gpu_solution_get_nodes.argtypes = [vp, i32, pi32, pi32]
     L.mf6gpu_solution_stat.restype = f64
     L.mf6gpu_solution_stat.argtypes = [vp, C.c_int]
     L.mf6gpu_solution_solver.restype = vp

@@ -297,7 +297,7 @@ def _cellid(tokens, shape):
     raise Mf6InputError("only DIS cellids are supported")
 
 
-def _read_rcha(blocks, name, shape):
+def _read_rcha(blocks, name, shape, fixed_cell=0):
     """array-based recharge (gwf-rcha.dfn): PERIOD blocks hold IRCH (layer of every 2-D cell, default 1) and
     RECHARGE arrays; an array that a block omits keeps its previous values (rch_rp / RchType read_initial_attr).
     Turned into the equivalent list: one boundary per 2-D cell at (irch, cell)."""
@@ -315,8 +315,8 @@ def _read_rcha(blocks, name, shape):
         if irch.min() < 1 or irch.max() > shape[0]:
             raise Mf6InputError(f"RCHA {name}: IRCH outside 1..{shape[0]}")
         nodes = (irch.astype(np.int64) - 1) * ncpl + np.arange(ncpl)
-        periods[num] = Package(T.PKG_RCH, nodes, rech.copy())
-    return StressPackage("RCH", name, periods)
+        periods[num] = Package(T.PKG_RCH, nodes, rech.copy(), iflowred=fixed_cell)
+    return StressPackage("RCH", name, periods, fixed_cell)
 
 
 def read_stress_package(path, ftype, name, shape):
@@ -326,9 +326,10 @@ def read_stress_package(path, ftype, name, shape):
     for k in opt:
         if k in ("TS6", "TAS6", "MOVER", "AUXMULTNAME") or (k == "READASARRAYS" and ftype != "RCH6"):
             raise Mf6InputError(f"{path}: option {k} is not supported on the GPU path")
+    fixed_cell = 1 if (ftype == "RCH6" and "FIXED_CELL" in opt) else 0    # carried in Package.iflowred for RCH
     if "READASARRAYS" in opt:
-        return _read_rcha(b, name, shape), naux
-    iflowred, flowred = 0, 0.1
+        return _read_rcha(b, name, shape, fixed_cell), naux
+    iflowred, flowred = fixed_cell, 0.1
     if "AUTO_FLOW_REDUCE" in opt:
         iflowred, flowred = 1, float(opt["AUTO_FLOW_REDUCE"][0]) if opt["AUTO_FLOW_REDUCE"] else 0.1
     ncol = _PKG_NCOL[ftype]

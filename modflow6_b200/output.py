@@ -134,12 +134,13 @@ class BudgetFileWriter:
                 self.write_array(kstp, kper, delt, pertim, totim, "STO-SY", sy)
         self.write_flowja(kstp, kper, delt, pertim, totim, solution.flowja)
         sim = solution.simvals
+        eff = getattr(solution, "effective_nodes", None)     # RCH: rch_cf resets nodelist to the highest active cell
         count = {}
         for i, p in enumerate(packages):
             t = PKG_TEXT[p.type]
             count[t] = count.get(t, 0) + 1
             name = package_names[i] if package_names else f"{t}-{count[t]}"   # default package names, e.g. CHD-1
-            self.write_list(kstp, kper, delt, pertim, totim, t, name, p.nodelist, sim[i])
+            self.write_list(kstp, kper, delt, pertim, totim, t, name, p.nodelist if eff is None else eff[i], sim[i])
         self.f.flush()
 
     def close(self):

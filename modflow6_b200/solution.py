@@ -88,6 +88,19 @@ class GpuNumericalSolution:
         return out
 
     @property
+    def effective_nodes(self):
+        """0-based cell every boundary acted on, one array per package (RCH: the highest active cell)"""
+        cnt = C.c_int32()
+        check(self._L.mf6gpu_solution_get_nodes(self.h, 0, None, C.byref(cnt)))
+        a = np.empty(max(cnt.value, 1), np.int32)
+        check(self._L.mf6gpu_solution_get_nodes(self.h, cnt.value, T.ptr_i32(a), C.byref(cnt)))
+        out, i0 = [], 0
+        for p in self._pkgs:
+            out.append(a[i0:i0 + p.nodelist.size].copy())
+            i0 += p.nodelist.size
+        return out
+
+    @property
     def storage_rates(self):
         """(STO-SS, STO-SY) rate per cell of the last time step"""
         ss, sy = np.empty(self.n), np.empty(self.n)

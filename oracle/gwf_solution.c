@@ -36,7 +36,8 @@
 typedef struct {
   int type, nbound, iflowred;
   double flowred;
-  int *nodelist;
+  int *nodelist;  /* the cell each bound acts on (RCH: reset to the highest active cell by rch_cf) */
+  int *nodetop;   /* RCH without FIXED_CELL: the cell of the input list (nodesontop, gwf-rch.f90:283-297) */
   double *b1, *b2, *b3;
   double *hcof, *rhs, *simvals, *ratein, *rateout;
 } pkg_t;
@@ -56,6 +57,7 @@ struct orc_solution {
   mf6gpu_sln_settings ss_;
   orc_imslinear *ims;
   int isymmetric;
+  int dry_chd; /* a constant-head cell went dry (fatal in the reference) */
   /* cooley */
   double relaxold, bigchold, bigch;
   /* ptc */
@@ -258,7 +260,28 @@ static void calc_condsat(orc_solution *S) {
   }
 }
 
+/* sgwf_npf_wetdry without rewetting (gwf-npf.f90:2061-2158): a convertible cell whose saturated thickness
+ * is gone becomes inactive for good, its head the dry value; a constant head going dry is fatal there */
+#define DHDRY (-1.0e30)
+static void npf_wd(orc_solution *S) {
+  for (int n = 0; n < S->nodes; n++) {
+    if (S->ibound[n] == 0 || S->icelltype[n] == 0) continue;
+    double ttop = S->top[n];
+    if (S->x[n] < ttop) ttop = S->x[n];
+    if (ttop - S->bot[n] <= 0.0) {
+      if (S->ibound[n] < 0) {
+        S->dry_chd = 1;
+        continue;
+      }
+      S->x[n] = DHDRY;
+      S->ibound[n] = 0;
+      S->ibound0[n] = 0; /* stays dry in later stress periods (no rewetting) */
+    }
+  }
+}
+
 static void npf_cf(orc_solution *S) {
+  if (!S->inewton) npf_wd(S); /* npf_cf :454-457 */
   for (int n = 0; n < S->nodes; n++) {
     if (S->icelltype[n] != 0) {
       double satn = (S->ibound[n] == 0) ? 0.0 : thksat(S, n, S->x[n]);
@@ -553,6 +576,24 @@ static void sto_cq(orc_solution *S) {
 }
 
 /* ---------------- boundary packages --------------------------------------- */
+/* DiscretizationBase.f90:1077-1112: walk down the vertical connections (m > n, ihc == 0) to the first
+ * cell that is not inactive, or to the bottom cell */
+static int highest_active(const orc_solution *S, int n) {
+  for (;;) {
+    int below = -1;
+    for (int ii = S->ia[n] + 1; ii < S->ia[n + 1]; ii++) {
+      int m = S->ja[ii];
+      if (S->ihc[S->jas[ii]] == 0 && m > n) {
+        below = m;
+        break;
+      }
+    }
+    if (below < 0) return n; /* bottom cell */
+    n = below;
+    if (S->ibound[n] != 0) return n;
+  }
+}
+
 static void bnd_cf(orc_solution *S, pkg_t *p) {
   for (int i = 0; i < p->nbound; i++) {
     int node = p->nodelist[i];
@@ -594,7 +635,12 @@ static void bnd_cf(orc_solution *S, pkg_t *p) {
       }
       break;
     }
-    case MF6GPU_PKG_RCH: /* gwf-rch.f90:303-353, fixed_cell list input */
+    case MF6GPU_PKG_RCH: /* gwf-rch.f90:303-353; iflowred carries FIXED_CELL for this package type */
+      if (p->iflowred == 0) {
+        node = p->nodetop[i];
+        if (S->ibound[node] == 0) node = highest_active(S, node);
+        p->nodelist[i] = node;
+      }
       p->hcof[i] = 0.0;
       p->rhs[i] = -p->b1[i] * S->area[node];
       if (S->ibound[node] <= 0) p->rhs[i] = 0.0;
@@ -794,7 +840,7 @@ orc_solution *orc_sln_create(const mf6gpu_gwf_model *m,
 static void free_pkgs(orc_solution *S) {
   for (int k = 0; k < S->npkg; k++) {
     pkg_t *p = &S->pkg[k];
-    free(p->nodelist); free(p->b1); free(p->b2); free(p->b3); free(p->hcof);
+    free(p->nodelist); free(p->nodetop); free(p->b1); free(p->b2); free(p->b3); free(p->hcof);
     free(p->rhs); free(p->simvals); free(p->ratein); free(p->rateout);
   }
   free(S->pkg);
@@ -832,6 +878,7 @@ void orc_sln_set_packages(orc_solution *S, int npkg, const mf6gpu_bnd_package *p
     p->iflowred = pk[k].iflowred;
     p->flowred = pk[k].flowred;
     p->nodelist = dup_idx(pk[k].nodelist, nb, pk[k].index_base);
+    p->nodetop = dup_idx(pk[k].nodelist, nb, pk[k].index_base);
     p->b1 = dup_d(pk[k].b1, nb);
     p->b2 = dup_d(pk[k].b2, nb);
     p->b3 = dup_d(pk[k].b3, nb);
@@ -1244,6 +1291,8 @@ const double *orc_sln_condsat(orc_solution *S) { return S->condsat; }
 const double *orc_sln_simvals(orc_solution *S, int k) {
   return (k >= 0 && k < S->npkg) ? S->pkg[k].simvals : 0;
 }
+const int *orc_sln_nodes(orc_solution *S, int k) { return (k >= 0 && k < S->npkg) ? S->pkg[k].nodelist : 0; }
+int orc_sln_dry_chd(const orc_solution *S) { return S->dry_chd; }
 const double *orc_sln_strgss(orc_solution *S) { return S->strgss; }
 const double *orc_sln_strgsy(orc_solution *S) { return S->strgsy; }
 void orc_sln_timers(orc_solution *S, double *t2) {

@@ -136,6 +136,10 @@ int orc_sln_timestep(orc_solution *S, int kper, int kstp, double delt, int iss,
 double *orc_sln_x(orc_solution *S);
 double *orc_sln_flowja(orc_solution *S);
 const double *orc_sln_simvals(orc_solution *S, int k);
+/* the cell every bound of package k acts on (0-based; RCH: the highest active cell, gwf-rch.f90:327-333) */
+const int *orc_sln_nodes(orc_solution *S, int k);
+/* 1 once a constant-head cell went dry (the reference aborts the simulation there) */
+int orc_sln_dry_chd(const orc_solution *S);
 const double *orc_sln_strgss(orc_solution *S);
 const double *orc_sln_strgsy(orc_solution *S);
 const double *orc_sln_amat(orc_solution *S);

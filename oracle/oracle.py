@@ -63,6 +63,9 @@ def lib():
         L.orc_sln_formulate.argtypes = [vp, C.c_int, C.c_double, C.c_int]
         L.orc_sln_simvals.restype = T.p_f64
         L.orc_sln_simvals.argtypes = [vp, C.c_int]
+        L.orc_sln_nodes.restype = T.p_i32
+        L.orc_sln_nodes.argtypes = [vp, C.c_int]
+        L.orc_sln_dry_chd.argtypes = [vp]
         for f in ("orc_sln_x", "orc_sln_flowja", "orc_sln_amat", "orc_sln_rhs", "orc_sln_condsat", "orc_sln_strgss",
                   "orc_sln_strgsy"):
             getattr(L, f).restype = T.p_f64
@@ -180,7 +183,18 @@ class OracleSolution:
     def timestep(self, kper=1, kstp=1, delt=1.0, iss=1):
         rep = T.StepReport()
         lib().orc_sln_timestep(self.h, kper, kstp, float(delt), int(iss), C.byref(rep))
+        if lib().orc_sln_dry_chd(self.h):
+            raise RuntimeError("CONSTANT-HEAD CELL WENT DRY -- SIMULATION ABORTED (gwf-npf.f90:2137-2146)")
         return rep
+
+    @property
+    def effective_nodes(self):
+        """0-based cell every bound acts on, one array per package (RCH: the highest active cell)"""
+        out = []
+        for k, p in enumerate(self._pkgs):
+            n = p.nodelist.size
+            out.append(np.ctypeslib.as_array(lib().orc_sln_nodes(self.h, k), shape=(max(n, 1),))[:n].copy())
+        return out
 
     def formulate(self, kiter=1, delt=1.0, iss=1):
         lib().orc_sln_formulate(self.h, kiter, float(delt), int(iss))

@@ -61,3 +61,23 @@ def test_chd02_known_answer_on_device(gpu, tmp_path, ordering):
     write_chd02(str(tmp_path))
     out = simulate.run(str(tmp_path), ordering=ordering)
     assert np.allclose(CHD02_HEADS, out["heads"][0].ravel())
+
+
+@pytest.mark.parametrize("irch", [None, [1, 1, 1, 1, 1], [2, 2, 1, 2, 2]])
+def test_rch01_on_device(gpu, tmp_path, irch):
+    """autotest/test_gwf_rch01.py:124-130 on the device: the top layer dries up in the first formulate
+    (npf wet/dry conversion), recharge is handed down to the highest active cell, the budget file lists the
+    cells the recharge acted on"""
+    from tests.test_mf6io_cpu import write_rch01
+    for tag in ("gpu", "cpu"):
+        (tmp_path / tag).mkdir()
+        write_rch01(str(tmp_path / tag), irch)
+    g = simulate.run(str(tmp_path / "gpu"), ordering=T.ORDER_NATURAL)
+    c = simulate.run(str(tmp_path / "cpu"), ordering=T.ORDER_NATURAL, solution_class=oracle_class())
+    assert g["reports"][0]["converged"] == 1
+    rec = [r for r in read_budget_file(tmp_path / "gpu" / "rch.cbc") if r["text"].strip() == "RCH"][0]
+    assert rec["node"].tolist() == [6, 7, 3, 9, 10] and rec["node2"].tolist() == [1, 2, 3, 4, 5]
+    assert np.allclose(rec["q"], [0.0, 0.1, 0.1, 0.1, 0.0])
+    hg, hc = g["heads"][0].ravel(), c["heads"][0].ravel()
+    assert (hg[[0, 1, 3, 4]] == -1.0e30).all() and np.abs(hg - hc).max() <= 1e-8
+    assert g["reports"][0]["outer_iterations"] == c["reports"][0]["outer_iterations"]

@@ -320,3 +320,38 @@ def test_chd02_binary_list_with_auxiliary(tmp_path):
     (tmp_path / "chd02.chd").write_text((tmp_path / "chd02.chd").read_text().replace("chd.bin (BINARY)", "chd.txt"))
     out = simulate.run(str(tmp_path), ordering=T.ORDER_NATURAL, solution_class=oracle_class())
     assert np.allclose(CHD02_HEADS, out["heads"][0].ravel())
+
+
+RCH01_IMS = ("BEGIN nonlinear\n  OUTER_DVCLOSE 1e-9\n  OUTER_MAXIMUM 100\n  UNDER_RELAXATION DBD\nEND nonlinear\n\n"
+             "BEGIN linear\n  INNER_MAXIMUM 300\n  INNER_DVCLOSE 1e-9\n  INNER_RCLOSE 1e-3\n  LINEAR_ACCELERATION BICGSTAB\n"
+             "  SCALING_METHOD NONE\n  REORDERING_METHOD NONE\n  RELAXATION_FACTOR 0.97\nEND linear\n")
+
+
+def write_rch01(d, irch):
+    """autotest/test_gwf_rch01.py:21-120: 2 layers x 5 columns of convertible cells, the top layer dry except its
+    middle cell (starting head 25 under a layer bottom of 50), array-based recharge 0.1 on the top layer"""
+    strt = np.array([[[25.0, 25.0, 75.0, 25.0, 25.0]], [[25.0, 25.0, 75.0, 25.0, 25.0]]])
+    per = "BEGIN period 1\n"
+    if irch is not None:
+        per += "  irch\n    INTERNAL FACTOR 1\n      " + " ".join(str(v) for v in irch) + "\n"
+    per += "  recharge\n    CONSTANT 0.1\nEND period 1\n"
+    mf6_inputs.write_gwf(d, "rch", (2, 1, 5), 1.0, 1.0, 100.0, [50.0, 0.0], 1.0, icelltype=1, strt=strt,
+                         chd={1: [((2, 1, 1), 25.0), ((2, 1, 5), 25.0)]}, sto=dict(ss=1e-5, sy=0.1, periods={}),
+                         extra_packages=[("RCH6", "rcha", "BEGIN options\n  READASARRAYS\nEND options\n\n" + per)])
+    mf6_inputs.write_sim(d, ["rch"], [(0.01, 1, 1.0)], RCH01_IMS)
+
+
+@pytest.mark.parametrize("irch", [None, [1, 1, 1, 1, 1], [2, 2, 1, 2, 2]])
+def test_rch01_recharge_reaches_the_highest_active_cell(tmp_path, irch):
+    """autotest/test_gwf_rch01.py:124-130: the RCH budget records -- recharge listed on dry top cells is applied
+    to the cell below (node 7, 9), stays on the wet middle cell (node 3) and is dropped on the constant heads
+    (nodes 6, 10): needs the wet/dry conversion of npf_cf and rch_cf's highest_active"""
+    write_rch01(str(tmp_path), irch)
+    out = simulate.run(str(tmp_path), ordering=T.ORDER_NATURAL, solution_class=oracle_class())
+    assert out["reports"][0]["converged"] == 1
+    rec = [r for r in read_budget_file(tmp_path / "rch.cbc") if r["text"].strip() == "RCH"][0]
+    assert rec["node"].tolist() == [6, 7, 3, 9, 10] and rec["node2"].tolist() == [1, 2, 3, 4, 5]
+    assert np.allclose(rec["q"], [0.0, 0.1, 0.1, 0.1, 0.0])
+    hds = read_head_file(tmp_path / "rch.hds")
+    assert (hds[0]["data"].ravel()[[0, 1, 3, 4]] == -1.0e30).all()      # the dry cells carry HDRY
+    assert hds[0]["data"].ravel()[2] > 50.0
