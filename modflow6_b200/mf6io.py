@@ -471,8 +471,6 @@ def read_gwf_model(name, nam_path, base_dir, warnings):
                             g["BOTM"].reshape(shape), np_["K"].reshape(shape), **common)
     else:
         m = build_disv_model(nlay, cell2d, g["TOP"], g["BOTM"].reshape(nlay, shape[1]), np_["K"], **common)
-    if "REWET" in nopt:
-        raise Mf6InputError("NPF option REWET is not supported on the GPU path (cells that dry stay dry)")
     if "IDOMAIN" in g:
         if (g["IDOMAIN"] < 0).any():
             raise Mf6InputError("IDOMAIN < 0 (vertical pass-through cells) is not supported on the GPU path")
