@@ -3,7 +3,7 @@ rank 1: the step right after the hot path of every time step).
 
 MODFLOW 6 opens its binary output with ACCESS='STREAM', FORM='UNFORMATTED' (src/Utilities/OpenSpec.f90):
 plain little-endian values back to back, no record markers.  All integers are i32, all reals f64, all
-strings 16 characters, right-justified for the flow-term text.
+strings 16 characters: right-justified literals for the flow terms, the left-justified variable name for heads.
 
 Writers restate
   ulasav    src/Utilities/InputOutput.f90:924-940     one layer of a dependent variable
@@ -44,7 +44,10 @@ def grid_shape(shape):
 class HeadFileWriter:
     def __init__(self, path, shape, text="HEAD"):
         self.nlay, self.nrow, self.ncol = grid_shape(shape)
-        self.text = _text16(text)
+        # OutputControlData keeps the variable name in a character(len=16) (`this%cname = cname`,
+        # OutputControlData.f90:22,162): LEFT-justified, unlike the right-justified literals of the budget terms
+        # (checked against the reference's own autotest/data/ex-gwf-bump/results.hds.cmp)
+        self.text = _text16(text, right=False)
         self.f = open(path, "wb")
 
     def write(self, kstp, kper, pertim, totim, head):

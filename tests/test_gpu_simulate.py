@@ -81,3 +81,19 @@ def test_rch01_on_device(gpu, tmp_path, irch):
     hg, hc = g["heads"][0].ravel(), c["heads"][0].ravel()
     assert (hg[[0, 1, 3, 4]] == -1.0e30).all() and np.abs(hg - hc).max() <= 1e-8
     assert g["reports"][0]["outer_iterations"] == c["reports"][0]["outer_iterations"]
+
+
+def test_ex_gwf_bump_on_device(gpu):
+    """the head file MODFLOW 6 itself wrote for autotest/test_gwf_newton_under_relaxation.py (tests/golden):
+    Newton-Raphson + Newton under-relaxation + BiCGSTAB on the device against the reference's own output,
+    with the reference test's criterion np.allclose(base_heads, heads)"""
+    import os
+    from modflow6_b200.solution import GpuNumericalSolution
+    from tests.test_oracle_known_answers import BUMP, bump_case
+    base = read_head_file(os.path.join(BUMP, "results.hds.cmp"))[0]["data"]
+    m, chd, sln, ims = bump_case()
+    G = GpuNumericalSolution(m, sln, ims)
+    G.set_packages([chd])
+    rep = G.timestep(1, 1, 1.0, 1)
+    assert rep.converged == 1
+    assert np.allclose(base, G.x.reshape(51, 51))

@@ -1,5 +1,7 @@
 """Pins the CPU oracle to the reference's own known-answer tests and to
 invariants of the formulation.  Runs on CPU."""
+import os
+
 import numpy as np
 import pytest
 
@@ -265,3 +267,37 @@ def test_ifmod_newton_split_equals_single():
     assert np.abs(A.x - hb).max() < 1e-8
     assert abs(ra.pdiffr) < 1e-5 and abs(rb.pdiffr) < 1e-5
     assert A.x.max() > 2.5 and A.x[: nrow * ncol].min() > 0.0   # a real water table in the convertible top layer
+
+
+BUMP = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ex-gwf-bump")
+
+
+def bump_case():
+    """autotest/test_gwf_newton_under_relaxation.py:9-101 (ex-gwf-bump): 51 x 51 convertible cells over a bumpy
+    bottom, CHD 7.5 / 2.5 on the west / east columns, NEWTON UNDER_RELAXATION, IMS defaults (SIMPLE) with BICGSTAB,
+    OUTER_DVCLOSE 1e-8, OUTER_MAXIMUM 75, INNER 100 / 1e-9 / 1e-3, NO_PTC ALL"""
+    from modflow6_b200.grid import build_dis_model
+    botm = np.loadtxt(os.path.join(BUMP, "bottom.txt")).reshape(1, 51, 51)
+    m = build_dis_model(1, 51, 51, 100.0 / 51, 100.0 / 51, 25.0, botm, 1.0, icelltype=1, strt=7.5, inewton=1,
+                        inewtonur=1)
+    chd = Package(T.PKG_CHD, [i * 51 for i in range(51)] + [i * 51 + 50 for i in range(51)], [7.5] * 51 + [2.5] * 51)
+    sln = T.SlnSettings.make(dvclose=1e-8, mxiter=75, nonmeth=0, theta=1.0, akappa=0.0, gamma=1.0, amomentum=0.0,
+                             iallowptc=0, numtrack=0, btol=0.0, breduc=0.0, res_lim=0.0)
+    ims = T.ImsSettings.make(dvclose=1e-9, rclose=1e-3, iter1=100, ilinmeth=2, relax=0.0)
+    return m, chd, sln, ims
+
+
+def test_ex_gwf_bump_reference_heads():
+    """the head file MODFLOW 6 itself wrote for this model (tests/golden/README.md): Newton-Raphson terms
+    (npf_fn), Newton under-relaxation (npf_nur), quadratic saturation smoothing, BiCGSTAB + ILU0 -- the oracle
+    lands on the reference's heads (max |dh| 2e-8), the bar of the reference test being np.allclose"""
+    from modflow6_b200.output import read_head_file
+    base = read_head_file(os.path.join(BUMP, "results.hds.cmp"))
+    assert len(base) == 1 and base[0]["text"] == "HEAD            " and (base[0]["nrow"], base[0]["ncol"]) == (51, 51)
+    m, chd, sln, ims = bump_case()
+    O = OracleSolution(m, sln, ims)
+    O.set_packages([chd])
+    rep = O.timestep(1, 1, 1.0, 1)
+    assert rep.converged == 1
+    assert np.allclose(base[0]["data"], O.x.reshape(51, 51))
+    assert np.abs(base[0]["data"] - O.x.reshape(51, 51)).max() < 1e-6

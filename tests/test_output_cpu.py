@@ -20,11 +20,11 @@ def test_head_record_bytes(tmp_path):
     w.close()
     want = b""
     for k in range(2):
-        want += struct.pack("<iidd", 3, 2, 1.5, 11.5) + b"            HEAD" + struct.pack("<iii", 3, 2, k + 1)
+        want += struct.pack("<iidd", 3, 2, 1.5, 11.5) + b"HEAD            " + struct.pack("<iii", 3, 2, k + 1)
         want += struct.pack("<6d", *h[6 * k:6 * k + 6])
     assert p.read_bytes() == want
     recs = read_head_file(p)
-    assert [r["ilay"] for r in recs] == [1, 2] and recs[1]["text"] == "            HEAD"
+    assert [r["ilay"] for r in recs] == [1, 2] and recs[1]["text"] == "HEAD            "
     assert np.array_equal(np.concatenate([r["data"].ravel() for r in recs]), h)
 
 
