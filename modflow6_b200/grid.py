@@ -324,3 +324,57 @@ def merge_models(models, exchanges):
                     inewton=m0.inewton, inewtonur=m0.inewtonur, iperched=m0.iperched, ivarcv=m0.ivarcv,
                     idewatcv=m0.idewatcv, insto=m0.insto, istor_coef=m0.istor_coef, iconf_ss=m0.iconf_ss,
                     iorig_ss=m0.iorig_ss, shape=None), offs
+
+
+def build_disu_model(iac, ja, ihc, cl12, hwva, top, bot, area, k11, k33=None, icelltype=0, strt=0.0, ss=None,
+                     sy=None, iconvert=None, **opts):
+    """Unstructured (DISU) model from the CONNECTIONDATA block as the user writes it (gwf-disu.dfn): `iac` entries
+    per cell, `ja` with the cell itself first (0-based here), and `ihc`, `cl12`, `hwva` per ja entry.
+    Follows `disuconnections` + `con_finalize` (Connections.f90:803-960, 245-330): the symmetric arrays take
+    ihc / hwva from the upper-triangle entry, cl1 = cl12 at (n, m), cl2 = cl12 at (m, n).  Rows are stored
+    diagonal first, then ascending columns (the solution-matrix layout); ibotnode = the last cell of the chain of
+    vertical (ihc == 0, m > n) connections below a cell."""
+    iac = np.asarray(iac, dtype=np.int64)
+    n = iac.size
+    ia_in = np.concatenate([[0], np.cumsum(iac)])
+    ja = np.abs(np.asarray(ja, dtype=np.int64))
+    ihc, cl12, hwva = np.asarray(ihc, dtype=np.int32), np.asarray(cl12, dtype=np.float64), np.asarray(hwva, np.float64)
+    rows = np.repeat(np.arange(n, dtype=np.int64), iac)
+    if not np.array_equal(ja[ia_in[:-1]], np.arange(n)):
+        raise ValueError("DISU: the first ja entry of every cell must be the cell itself")
+    isdiag = np.zeros(ja.size, dtype=np.int64)
+    isdiag[ia_in[:-1]] = -1                              # sorts the diagonal first
+    order = np.lexsort((ja, isdiag, rows))
+    ja_s, ihc_e, cl_e, hw_e = ja[order], ihc[order], cl12[order], hwva[order]
+    key = rows * n + ja_s                                # rows is unchanged by a within-row sort
+    ko = np.argsort(key, kind="stable")
+    tkey = ja_s * n + rows
+    loc = np.minimum(np.searchsorted(key[ko], tkey), key.size - 1)
+    if not np.array_equal(key[ko][loc], tkey):
+        raise ValueError("DISU: the connection list is not symmetric")
+    isym = ko[loc]
+    upper = ja_s > rows
+    njas = int(upper.sum())
+    jas = np.full(ja_s.size, -1, dtype=np.int64)
+    jas[upper] = np.arange(njas)
+    lower = ja_s < rows
+    jas[lower] = jas[isym[lower]]
+    if not np.allclose(hw_e[upper], hw_e[isym[upper]]) or not np.array_equal(ihc_e[upper], ihc_e[isym[upper]]):
+        raise ValueError("DISU: ihc / hwva differ between the two directions of a connection")
+    # bottom of every vertical chain
+    below = np.full(n, -1, dtype=np.int64)
+    vert = upper & (ihc_e == 0)
+    below[rows[vert][::-1]] = ja_s[vert][::-1]           # the first (lowest-numbered) vertical neighbour below wins
+    ibot = np.arange(n, dtype=np.int64)
+    for c in range(n - 1, -1, -1):
+        if below[c] >= 0:
+            ibot[c] = ibot[below[c]]
+    bc = lambda v, dt=np.float64: np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=dt), (n,))).copy()  # noqa: E731
+    m = GwfModel(nodes=n, ia=ia_in, ja=ja_s, jas=jas, isym=isym, ihc=ihc_e[upper], cl1=cl_e[upper],
+                 cl2=cl_e[isym[upper]], hwva=hw_e[upper], top=bc(top), bot=bc(bot), area=bc(area), k11=bc(k11),
+                 k33=bc(k33 if k33 is not None else k11), icelltype=bc(icelltype, np.int32), strt=bc(strt),
+                 ibotnode=ibot.astype(np.int32), ss=None if ss is None else bc(ss), sy=None if sy is None else bc(sy),
+                 iconvert=None if iconvert is None else bc(iconvert, np.int32), shape=(n,), **opts)
+    if ss is not None or sy is not None:
+        m.insto = 1
+    return m

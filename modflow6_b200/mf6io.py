@@ -1,5 +1,5 @@
 """Reader for the subset of MODFLOW 6 input files that feeds the accelerated path (SURVEY.md section 8f,
-rank 3): mfsim.nam, TDIS, IMS, GWF name file, DIS, DISV, IC, NPF, STO, CHD/WEL/DRN/RIV/GHB/RCH lists, array-based
+rank 3): mfsim.nam, TDIS, IMS, GWF name file, DIS, DISV, DISU, IC, NPF, STO, CHD/WEL/DRN/RIV/GHB/RCH lists, array-based
 RCH (READASARRAYS), OC and
 GWF-GWF exchanges -- enough to run FloPy-written models such as the reference's `.mf6minsim/` example through
 `mf6gpu_solution_*` without the Fortran host (which cannot be built in this image).
@@ -23,7 +23,7 @@ import numpy as np
 
 from . import ctypes_types as T
 from .disv import build_disv_model, cell2d_from_vertices
-from .grid import Package, build_dis_model
+from .grid import Package, build_dis_model, build_disu_model
 
 
 class Mf6InputError(ValueError):
@@ -284,6 +284,11 @@ def read_ims(path, warnings):
 
 
 def _cellid(tokens, shape):
+    if len(shape) == 1:       # DISU: node
+        nd = int(tokens[0]) - 1
+        if not 0 <= nd < shape[0]:
+            raise Mf6InputError(f"cellid {tokens[0]} outside the grid of {shape[0]} nodes")
+        return nd, 1
     if len(shape) == 2:       # DISV: (layer, icell2d)
         k, j = int(tokens[0]) - 1, int(tokens[1]) - 1
         if not (0 <= k < shape[0] and 0 <= j < shape[1]):
@@ -386,17 +391,32 @@ def read_gwf_model(name, nam_path, base_dir, warnings):
         pn = t[2] if len(t) > 2 else None
         if ft in _PKG_TYPE:
             stress.append((ft, fn, pn))
-        elif ft in ("DIS6", "DISV6", "IC6", "NPF6", "STO6", "OC6"):
+        elif ft in ("DIS6", "DISV6", "DISU6", "IC6", "NPF6", "STO6", "OC6"):
             files[ft] = fn
         else:
             raise Mf6InputError(f"{nam_path}: package {ft} is outside the GPU path (SURVEY.md section 8)")
     for need in ("IC6", "NPF6"):
         if need not in files:
             raise Mf6InputError(f"{nam_path}: {need} package is required")
-    if ("DIS6" in files) == ("DISV6" in files):
-        raise Mf6InputError(f"{nam_path}: exactly one of DIS6 / DISV6 is required (DISU is outside the GPU path)")
+    if sum(k in files for k in ("DIS6", "DISV6", "DISU6")) != 1:
+        raise Mf6InputError(f"{nam_path}: exactly one of DIS6 / DISV6 / DISU6 is required")
     cell2d = None
-    if "DIS6" in files:
+    disu = None
+    if "DISU6" in files:
+        d = read_blocks(files["DISU6"])
+        dim = _options(_block(d, "DIMENSIONS"))
+        nodes, nja = int(dim["NODES"][0]), int(dim["NJA"][0])
+        nlay, shape = 1, (nodes,)
+        g = read_griddata(_block(d, "GRIDDATA"), base_dir,
+                          {"TOP": ((nodes,), np.float64), "BOT": ((nodes,), np.float64), "AREA": ((nodes,), np.float64),
+                           "IDOMAIN": ((nodes,), np.int32)})
+        disu = read_griddata(_block(d, "CONNECTIONDATA"), base_dir,
+                             {"IAC": ((nodes,), np.int32), "JA": ((nja,), np.int32), "IHC": ((nja,), np.int32),
+                              "CL12": ((nja,), np.float64), "HWVA": ((nja,), np.float64),
+                              "ANGLDEGX": ((nja,), np.float64)})
+        if int(disu["IAC"].sum()) != nja:
+            raise Mf6InputError(f"{files['DISU6']}: sum(IAC) != NJA")
+    elif "DIS6" in files:
         d = read_blocks(files["DIS6"])
         dim = _options(_block(d, "DIMENSIONS"))
         nlay, nrow, ncol = int(dim["NLAY"][0]), int(dim["NROW"][0]), int(dim["NCOL"][0])
@@ -423,7 +443,8 @@ def read_gwf_model(name, nam_path, base_dir, warnings):
         if any(c is None for c in cells):
             raise Mf6InputError(f"{files['DISV6']}: CELL2D does not list every cell")
         cell2d = cell2d_from_vertices(verts, cells)
-    ashape = shape if len(shape) == 3 else (nlay, 1, shape[1])      # READARRAY layout (LAYERED = per layer)
+    # READARRAY layout (LAYERED = one control record per layer)
+    ashape = shape if len(shape) == 3 else ((nlay, 1, shape[1]) if len(shape) == 2 else shape)
     # IC / NPF / STO
     ic = read_griddata(_block(read_blocks(files["IC6"]), "GRIDDATA"), base_dir, {"STRT": (ashape, np.float64)})
     nb = read_blocks(files["NPF6"])
@@ -464,7 +485,10 @@ def read_gwf_model(name, nam_path, base_dir, warnings):
     common = dict(k33=np_["K33"] if "K33" in np_ else None, icelltype=np_["ICELLTYPE"], strt=ic["STRT"],
                   ss=sto.get("SS"), sy=sto.get("SY"), iconvert=sto.get("ICONVERT"), inewton=inewton,
                   inewtonur=inewtonur, **kw)
-    if cell2d is None:
+    if disu is not None:
+        m = build_disu_model(disu["IAC"], np.abs(disu["JA"]) - 1, disu["IHC"], disu["CL12"], disu["HWVA"], g["TOP"],
+                             g["BOT"], g["AREA"], np_["K"], **common)
+    elif cell2d is None:
         r3 = lambda a: None if a is None else a.reshape(shape)   # noqa: E731
         common = {k: (r3(v) if isinstance(v, np.ndarray) else v) for k, v in common.items()}
         m = build_dis_model(nlay, nrow, ncol, g["DELR"], g["DELC"], g["TOP"].reshape(nrow, ncol),

@@ -52,13 +52,55 @@ def _disv_text(shape, delr, delc, top, botm):
     return s + "END cell2d\n"
 
 
+def _disu_text(shape, delr, delc, top, botm):
+    """the rectangular grid as a DISU package: per-node top / bot / area and the CONNECTIONDATA arrays (iac, ja with
+    the cell itself first, ihc, cl12, hwva) in the row order up, back, left, right, front, down"""
+    nlay, nrow, ncol = shape
+    delr = np.broadcast_to(np.asarray(delr, dtype=float), (ncol,))
+    delc = np.broadcast_to(np.asarray(delc, dtype=float), (nrow,))
+    bot = np.broadcast_to(np.asarray(botm, dtype=float)[:, None, None], shape)
+    tp = np.concatenate([np.broadcast_to(np.asarray(top, dtype=float), (1, nrow, ncol)), bot[:-1]])
+    node = lambda k, i, j: (k * nrow + i) * ncol + j   # noqa: E731
+    iac, ja, ihc, cl12, hw = [], [], [], [], []
+    for k in range(nlay):
+        for i in range(nrow):
+            for j in range(ncol):
+                e = [(node(k, i, j), 0, 0.0, 0.0)]
+                dz = 0.5 * (tp[k, i, j] - bot[k, i, j])
+                if k > 0:
+                    e.append((node(k - 1, i, j), 0, dz, delr[j] * delc[i]))
+                if i > 0:
+                    e.append((node(k, i - 1, j), 1, 0.5 * delc[i], delr[j]))
+                if j > 0:
+                    e.append((node(k, i, j - 1), 1, 0.5 * delr[j], delc[i]))
+                if j < ncol - 1:
+                    e.append((node(k, i, j + 1), 1, 0.5 * delr[j], delc[i]))
+                if i < nrow - 1:
+                    e.append((node(k, i + 1, j), 1, 0.5 * delc[i], delr[j]))
+                if k < nlay - 1:
+                    e.append((node(k + 1, i, j), 0, dz, delr[j] * delc[i]))
+                iac.append(len(e))
+                for m, h, c, w in e:
+                    ja.append(m + 1); ihc.append(h); cl12.append(c); hw.append(w)
+    n = nlay * nrow * ncol
+    one = lambda name, a, f=repr: f"  {name}\n    INTERNAL FACTOR 1\n      " + " ".join(f(v) for v in a) + "\n"   # noqa: E731
+    area = np.broadcast_to(delc[:, None] * delr[None, :], shape)
+    return (f"BEGIN options\nEND options\n\nBEGIN dimensions\n  NODES {n}\n  NJA {len(ja)}\nEND dimensions\n\n"
+            "BEGIN griddata\n" + one("top", [float(v) for v in tp.ravel()]) + one("bot", [float(v) for v in bot.ravel()])
+            + one("area", [float(v) for v in area.ravel()]) + "END griddata\n\nBEGIN connectiondata\n"
+            + one("iac", iac, str) + one("ja", ja, str) + one("ihc", ihc, str) + one("cl12", [float(v) for v in cl12])
+            + one("hwva", [float(v) for v in hw]) + "END connectiondata\n")
+
+
 def write_gwf(d, name, shape, delr, delc, top, botm, k, chd=None, wel=None, icelltype=0, strt=0.0, k33=None,
-              sto=None, oc=True, newton=False, disv=False, extra_packages=()):
+              sto=None, oc=True, newton=False, disv=False, extra_packages=(), disu=False):
     """chd / wel: dict iper -> list of ((k,i,j), value) with 1-based cellids.  disv=True writes the same
     rectangular grid as a DISV package (cellids become layer, icell2d)"""
     nlay, nrow, ncol = shape
-    pk = f"  DIS{'V' if disv else ''}6  {name}.dis  dis\n  IC6  {name}.ic  ic\n  NPF6  {name}.npf  npf\n"
-    if disv:
+    pk = f"  DIS{'V' if disv else ('U' if disu else '')}6  {name}.dis  dis\n  IC6  {name}.ic  ic\n  NPF6  {name}.npf  npf\n"
+    if disu:
+        _w(os.path.join(d, f"{name}.dis"), _disu_text(shape, delr, delc, top, botm))
+    elif disv:
         _w(os.path.join(d, f"{name}.dis"), _disv_text(shape, delr, delc, top, botm))
     else:
         _w(os.path.join(d, f"{name}.dis"),
@@ -68,7 +110,7 @@ def write_gwf(d, name, shape, delr, delc, top, botm, k, chd=None, wel=None, icel
            + "END griddata\n")
     _w(os.path.join(d, f"{name}.ic"), "BEGIN griddata\n" + _arr("strt", strt) + "END griddata\n")
     npf = "BEGIN options\n  SAVE_FLOWS\nEND options\n\nBEGIN griddata\n" + _arr("icelltype", icelltype) \
-        + _arr("k", np.asarray(k, dtype=float).reshape(shape) if np.ndim(k) else k, layered=np.ndim(k) > 0)
+        + _arr("k", np.asarray(k, dtype=float).reshape(shape) if np.ndim(k) else k, layered=np.ndim(k) > 0 and not disu)
     if k33 is not None:
         npf += _arr("k33", k33)
     _w(os.path.join(d, f"{name}.npf"), npf + "END griddata\n")
@@ -86,6 +128,8 @@ def write_gwf(d, name, shape, delr, delc, top, botm, k, chd=None, wel=None, icel
         s = f"BEGIN options\nEND options\n\nBEGIN dimensions\n  MAXBOUND  {max(len(v) for v in spd.values())}\nEND dimensions\n\n"
         for iper, rows in sorted(spd.items()):
             cid = (lambda c: f"{c[0]} {(c[1] - 1) * ncol + c[2]}") if disv else (lambda c: f"{c[0]} {c[1]} {c[2]}")
+            if disu:
+                cid = lambda c: f"{((c[0] - 1) * nrow + c[1] - 1) * ncol + c[2]}"   # noqa: E731
             s += f"BEGIN period  {iper}\n" + "".join(f"  {cid(c)}  {v!r}\n" for c, v in rows) \
                 + f"END period  {iper}\n\n"
         _w(os.path.join(d, f"{name}.{ft.lower()}"), s)

@@ -146,7 +146,7 @@ def test_reference_minsim_deck(tmp_path):
     assert np.abs(t2 - fit).max() / t2.mean() < 2e-4
 
 
-def test_disv_deck_of_a_rectangular_grid_equals_the_dis_deck(tmp_path):
+def test_disv_and_disu_decks_of_a_rectangular_grid_equal_the_dis_deck(tmp_path):
     """VERTICES / CELL2D -> connections (vertexconnect, DisvGeom cprops): the same rectangular grid written as a
     DISV package must give the DIS connectivity (ia, ja, ihc, cl1, cl2, hwva, area) and therefore the same heads"""
     rng = np.random.default_rng(11)
@@ -161,11 +161,11 @@ def test_disv_deck_of_a_rectangular_grid_equals_the_dis_deck(tmp_path):
     ims = ("BEGIN nonlinear\n  OUTER_DVCLOSE 1e-9\n  OUTER_MAXIMUM 50\nEND nonlinear\n\n"
            "BEGIN linear\n  INNER_MAXIMUM 200\n  INNER_DVCLOSE 1e-10\n  INNER_RCLOSE 1e-8\n  LINEAR_ACCELERATION CG\nEND linear\n")
     outs = {}
-    for tag in ("dis", "disv"):
+    for tag in ("dis", "disv", "disu"):
         d = tmp_path / tag
         d.mkdir()
         mf6_inputs.write_gwf(str(d), "m", shape, delr, delc, 0.0, botm, k, chd={1: chd}, wel={1: wel}, strt=3.0,
-                             k33=0.3, disv=(tag == "disv"))
+                             k33=0.3, disv=(tag == "disv"), disu=(tag == "disu"))
         mf6_inputs.write_sim(str(d), ["m"], [(1.0, 1, 1.0)], ims)
         outs[tag] = simulate.run(str(d), ordering=T.ORDER_NATURAL, solution_class=oracle_class())
     a, b = outs["dis"]["simulation"].models[0].model, outs["disv"]["simulation"].models[0].model
@@ -175,6 +175,15 @@ def test_disv_deck_of_a_rectangular_grid_equals_the_dis_deck(tmp_path):
     assert np.abs(outs["dis"]["heads"][0].ravel() - outs["disv"]["heads"][0].ravel()).max() < 1e-9
     recs = read_head_file(tmp_path / "disv" / "m.hds")
     assert len(recs) == 3 and recs[0]["ncol"] == 30 and recs[0]["nrow"] == 1      # DISV: ncol = ncpl, nrow = 1
+    # and the DISU deck (CONNECTIONDATA: iac, ja, ihc, cl12, hwva -> disuconnections + con_finalize)
+    c = outs["disu"]["simulation"].models[0].model
+    assert np.array_equal(a.ia, c.ia) and np.array_equal(a.ja, c.ja) and np.array_equal(a.ihc, c.ihc)
+    for name in ("cl1", "cl2", "hwva", "area", "top", "bot"):
+        assert np.allclose(getattr(a, name), getattr(c, name), rtol=1e-13), name
+    assert np.array_equal(a.ibotnode, c.ibotnode)
+    assert np.abs(outs["dis"]["heads"][0].ravel() - outs["disu"]["heads"][0].ravel()).max() < 1e-9
+    recs = read_head_file(tmp_path / "disu" / "m.hds")
+    assert len(recs) == 1 and recs[0]["ncol"] == 90 and recs[0]["nrow"] == 1      # DISU: one record of all nodes
 
 
 def test_multi_model_budget_files(tmp_path):
