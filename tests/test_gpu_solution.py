@@ -18,7 +18,6 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def _pair(cfg):
-    from modflow6_b200.linear import GpuMatrix
     from modflow6_b200.solution import GpuNumericalSolution
     from oracle.oracle import OracleSolution
     G = GpuNumericalSolution(cfg.model, cfg.sln, cfg.ims)
