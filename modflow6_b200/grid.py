@@ -378,3 +378,61 @@ def build_disu_model(iac, ja, ihc, cl12, hwva, top, bot, area, k11, k33=None, ic
     if ss is not None or sy is not None:
         m.insto = 1
     return m
+
+
+def build_dis_model_idomain(nlay, nrow, ncol, delr, delc, top, botm, idomain, k11, k33=None, icelltype=0, strt=0.0,
+                            ss=None, sy=None, iconvert=None, **opts):
+    """DIS model with an IDOMAIN array, numbered like the reference numbers it: only cells with idomain > 0 exist
+    (reduced node numbers in user order), idomain == 0 removes a cell, idomain < 0 makes it a vertical pass-through
+    -- the cells above and below it are connected directly with their own half thicknesses (`disconnections`,
+    Connections.f90:463-700: the vertical search `do kk = k+1, nlay ... if (mr >= 0) exit`).
+    `model.meta` carries nodeuser (reduced -> user) and nodereduced (user -> reduced, -1 where no cell exists)."""
+    shp = (nlay, nrow, ncol)
+    nrc = nrow * ncol
+    idom = np.asarray(idomain).reshape(shp)
+    delr = np.broadcast_to(np.asarray(delr, dtype=np.float64), (ncol,))
+    delc = np.broadcast_to(np.asarray(delc, dtype=np.float64), (nrow,))
+    botm = np.asarray(botm, dtype=np.float64)
+    bot3 = np.broadcast_to(botm[:, None, None] if botm.ndim == 1 else botm.reshape(shp), shp)
+    top3 = np.concatenate([np.broadcast_to(np.asarray(top, dtype=np.float64), (1, nrow, ncol)), bot3[:-1]])
+    area3 = np.broadcast_to(delc[:, None] * delr[None, :], shp)
+    active = idom > 0
+    nodeuser = np.nonzero(active.reshape(-1))[0]
+    n = nodeuser.size
+    nodereduced = np.full(nlay * nrc, -1, dtype=np.int64)
+    nodereduced[nodeuser] = np.arange(n)
+    # layer of the next cell below / above that is not a pass-through (idomain >= 0), -1 if none
+    below = np.full(shp, -1, dtype=np.int64)
+    above = np.full(shp, -1, dtype=np.int64)
+    for k in range(nlay - 2, -1, -1):
+        below[k] = np.where(idom[k + 1] >= 0, k + 1, below[k + 1])
+    for k in range(1, nlay):
+        above[k] = np.where(idom[k - 1] >= 0, k - 1, above[k - 1])
+    ku, iu, ju = np.unravel_index(nodeuser, shp)
+    half = 0.5 * (top3 - bot3)
+    ent = [[] for _ in range(7)]        # per direction: (valid, user node of the neighbour, ihc, cl12 of THIS side, hwva)
+    def add(valid, mk, mi, mj, ihc, cl, hw):
+        mk, mi, mj = np.where(valid, mk, 0), np.where(valid, mi, 0), np.where(valid, mj, 0)
+        valid = valid & (idom[mk, mi, mj] > 0)
+        return valid, (mk * nrow + mi) * ncol + mj, ihc, cl, hw
+    dirs = [add(above[ku, iu, ju] >= 0, above[ku, iu, ju], iu, ju, 0, half[ku, iu, ju], area3[ku, iu, ju]),
+            add(iu > 0, ku, iu - 1, ju, 1, 0.5 * delc[iu], delr[ju]),
+            add(ju > 0, ku, iu, ju - 1, 1, 0.5 * delr[ju], delc[iu]),
+            add(ju < ncol - 1, ku, iu, ju + 1, 1, 0.5 * delr[ju], delc[iu]),
+            add(iu < nrow - 1, ku, iu + 1, ju, 1, 0.5 * delc[iu], delr[ju]),
+            add(below[ku, iu, ju] >= 0, below[ku, iu, ju], iu, ju, 0, half[ku, iu, ju], area3[ku, iu, ju])]
+    valid = np.stack([np.ones(n, bool)] + [d[0] for d in dirs], axis=1)
+    cols = np.stack([np.arange(n)] + [nodereduced[d[1]] for d in dirs], axis=1)
+    ihc = np.stack([np.zeros(n, np.int32)] + [np.full(n, d[2], np.int32) for d in dirs], axis=1)
+    cl12 = np.stack([np.zeros(n)] + [np.broadcast_to(d[3], (n,)) for d in dirs], axis=1)
+    hwva = np.stack([np.zeros(n)] + [np.broadcast_to(d[4], (n,)) for d in dirs], axis=1)
+    pick = lambda a: np.ascontiguousarray(np.broadcast_to(np.asarray(a), shp)).reshape(-1)[nodeuser]   # noqa: E731
+    m = build_disu_model(valid.sum(axis=1), cols[valid], ihc[valid], cl12[valid], hwva[valid],
+                         top3.reshape(-1)[nodeuser], bot3.reshape(-1)[nodeuser], area3.reshape(-1)[nodeuser], pick(k11),
+                         k33=None if k33 is None else pick(k33), icelltype=pick(icelltype), strt=pick(strt),
+                         ss=None if ss is None else pick(ss), sy=None if sy is None else pick(sy),
+                         iconvert=None if iconvert is None else pick(iconvert), **opts)
+    m.shape = shp
+    m.meta["nodeuser"] = nodeuser
+    m.meta["nodereduced"] = nodereduced
+    return m

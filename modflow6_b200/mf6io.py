@@ -23,7 +23,7 @@ import numpy as np
 
 from . import ctypes_types as T
 from .disv import build_disv_model, cell2d_from_vertices
-from .grid import Package, build_dis_model, build_disu_model
+from .grid import Package, build_dis_model, build_dis_model_idomain, build_disu_model
 
 
 class Mf6InputError(ValueError):
@@ -166,6 +166,12 @@ class GwfInput:
     head_file: str = None
     budget_file: str = None
     save: dict = field(default_factory=dict)          # iper -> list of (rtype, ocsetting tokens)
+    nodeuser: np.ndarray = None       # DIS with IDOMAIN <= 0 cells: reduced -> user node (model.nodes entries)
+    nodereduced: np.ndarray = None    # user -> reduced node, -1 where no cell exists
+
+    @property
+    def nodesuser(self):
+        return int(np.prod(self.shape))
 
 
 @dataclass
@@ -491,19 +497,37 @@ def read_gwf_model(name, nam_path, base_dir, warnings):
     elif cell2d is None:
         r3 = lambda a: None if a is None else a.reshape(shape)   # noqa: E731
         common = {k: (r3(v) if isinstance(v, np.ndarray) else v) for k, v in common.items()}
-        m = build_dis_model(nlay, nrow, ncol, g["DELR"], g["DELC"], g["TOP"].reshape(nrow, ncol),
-                            g["BOTM"].reshape(shape), np_["K"].reshape(shape), **common)
+        if "IDOMAIN" in g and (g["IDOMAIN"] <= 0).any():
+            # reduced node numbering + vertical pass-through cells, like the reference numbers the grid
+            m = build_dis_model_idomain(nlay, nrow, ncol, g["DELR"], g["DELC"], g["TOP"].reshape(nrow, ncol),
+                                        g["BOTM"].reshape(shape), g.pop("IDOMAIN").reshape(shape),
+                                        np_["K"].reshape(shape), **common)
+        else:
+            m = build_dis_model(nlay, nrow, ncol, g["DELR"], g["DELC"], g["TOP"].reshape(nrow, ncol),
+                                g["BOTM"].reshape(shape), np_["K"].reshape(shape), **common)
     else:
         m = build_disv_model(nlay, cell2d, g["TOP"], g["BOTM"].reshape(nlay, shape[1]), np_["K"], **common)
     if "IDOMAIN" in g:
         if (g["IDOMAIN"] < 0).any():
             raise Mf6InputError("IDOMAIN < 0 (vertical pass-through cells) is not supported on the GPU path")
         m.ibound = np.where(g["IDOMAIN"] > 0, 1, 0).astype(np.int32)
-    gi = GwfInput(name=name, model=m, shape=shape, sto_transient=sto_tr)
+    gi = GwfInput(name=name, model=m, shape=shape, sto_transient=sto_tr, nodeuser=m.meta.get("nodeuser"),
+                  nodereduced=m.meta.get("nodereduced"))
     count = {}
     for ft, fn, pn in stress:
         count[ft] = count.get(ft, 0) + 1
         sp, _ = read_stress_package(fn, ft, pn or f"{ft[:-1]}-{count[ft]}", shape)
+        if gi.nodereduced is not None:          # user cellids -> reduced nodes; boundaries in removed cells are dropped
+            for iper, p in sp.periods.items():
+                if p is None:
+                    continue
+                red = gi.nodereduced[p.nodelist]
+                keep = red >= 0
+                if not keep.all():
+                    warnings.append(f"{name}: {sp.name} period {iper}: {int((~keep).sum())} boundaries lie in cells "
+                                    "that IDOMAIN removes and are ignored")
+                sp.periods[iper] = Package(p.type, red[keep], p.b1[keep], p.b2[keep], p.b3[keep],
+                                           iflowred=p.iflowred, flowred=p.flowred)
         gi.packages.append(sp)
     if "OC6" in files:
         ob = read_blocks(files["OC6"])
@@ -559,8 +583,15 @@ def read_simulation(sim_dir):
         if t[0].upper() != "GWF6-GWF6":
             raise Mf6InputError(f"exchange type {t[0]} is outside the GPU path")
         i1, i2 = index[t[2].upper()], index[t[3].upper()]
-        exchanges.append(read_exchange(os.path.join(sim_dir, t[1]), i1, i2, models[i1].shape, models[i2].shape,
-                                       exg_id=len(exchanges) + 1))
+        e = read_exchange(os.path.join(sim_dir, t[1]), i1, i2, models[i1].shape, models[i2].shape,
+                          exg_id=len(exchanges) + 1)
+        e["usernodem1"], e["usernodem2"] = e["nodem1"], e["nodem2"]
+        for key, gi in (("nodem1", models[i1]), ("nodem2", models[i2])):
+            if gi.nodereduced is not None:
+                e[key] = gi.nodereduced[e[key]]
+                if (e[key] < 0).any():
+                    raise Mf6InputError(f"{t[1]}: an exchange connects a cell that IDOMAIN removes from {gi.name}")
+        exchanges.append(e)
     sg = [x for x in b if x[0] == "SOLUTIONGROUP"]
     if len(sg) != 1 or len(sg[0][2]) != 1 or sg[0][2][0][0].upper() != "IMS6":
         raise Mf6InputError("exactly one solution group with one IMS6 solution is supported")

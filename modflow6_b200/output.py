@@ -126,12 +126,17 @@ class BudgetFileWriter:
         self.f.write(rec.tobytes())
         self.f.flush()
 
-    def write_step(self, kstp, kper, delt, pertim, totim, solution, packages, package_names=None):
+    def write_step(self, kstp, kper, delt, pertim, totim, solution, packages, package_names=None, nodeuser=None):
         """everything gwf_ot_flow saves for one time step, taken from a solution object
-        (GpuNumericalSolution or the oracle: flowja, storage_rates, simvals)"""
+        (GpuNumericalSolution or the oracle: flowja, storage_rates, simvals).  nodeuser: reduced -> user node of
+        a grid with IDOMAIN holes -- list records carry USER node numbers, arrays are expanded to the user grid"""
         m = solution.model
         if getattr(m, "insto", 0):
             ss, sy = solution.storage_rates
+            if nodeuser is not None:          # record_array fills the removed cells with 0 (dinact of sto_save_model_flows)
+                full = np.zeros((2, self.nlay * self.nrow * self.ncol))
+                full[0, nodeuser], full[1, nodeuser] = ss, sy
+                ss, sy = full
             self.write_array(kstp, kper, delt, pertim, totim, "STO-SS", ss)
             if m.iconvert is not None and np.any(m.iconvert):      # iusesy (gwf-sto.f90:633-637)
                 self.write_array(kstp, kper, delt, pertim, totim, "STO-SY", sy)
@@ -143,7 +148,9 @@ class BudgetFileWriter:
             t = PKG_TEXT[p.type]
             count[t] = count.get(t, 0) + 1
             name = package_names[i] if package_names else f"{t}-{count[t]}"   # default package names, e.g. CHD-1
-            self.write_list(kstp, kper, delt, pertim, totim, t, name, p.nodelist if eff is None else eff[i], sim[i])
+            nodes = p.nodelist if eff is None else eff[i]
+            self.write_list(kstp, kper, delt, pertim, totim, t, name, nodes if nodeuser is None else nodeuser[nodes],
+                            sim[i])
         self.f.flush()
 
     def close(self):

@@ -78,6 +78,15 @@ def _exchange_rates(merged, flowja, offs, e):
     return q
 
 
+def _user_grid(gi, h):
+    """heads of the model's cells on the user grid: cells that IDOMAIN removes carry 1e30 (record_array, dinact)"""
+    if gi.nodeuser is None:
+        return h
+    full = np.full(gi.nodesuser, DHNOFLO)
+    full[gi.nodeuser] = h
+    return full
+
+
 def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None, solution_class=None, comm=None):
     """solution_class(model, sln_settings, ims_settings) -> object with set_packages / timestep / x / flowja /
     simvals / storage_rates; default GpuNumericalSolution.
@@ -161,13 +170,13 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
                 if hw and _should_save(saving[k].get("HEAD", []), kstp, nstp):
                     h = (x if rank is not None else x[offs[k]:offs[k] + gi.model.nodes]).copy()
                     h[gi.model.ibound == 0] = DHNOFLO
-                    hw.write(kstp, kper, pertim, totim, h)
+                    hw.write(kstp, kper, pertim, totim, _user_grid(gi, h))
                 if bw and _should_save(saving[k].get("BUDGET", []), kstp, nstp):
                     mine = [i for i, (kk, _) in enumerate(owner) if kk == k]
                     view = S if len(models) == 1 else _ModelView(S, model, gi.model, offs[k], mine)
                     local = [Package(pkgs[i].type, pkgs[i].nodelist - int(offs[k]), pkgs[i].b1) for i in mine]
                     bw.write_step(kstp, kper, delt, pertim, totim, view, local,
-                                  [gi.packages[owner[i][1]].name for i in mine])
+                                  [gi.packages[owner[i][1]].name for i in mine], nodeuser=gi.nodeuser)
             # exchange flows follow the models' own records (exg_ot after model_ot, mf6core.f90:755-771)
             for e in sim.exchanges:
                 if not e["save_flows"]:
@@ -180,7 +189,7 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
                         if q is None:
                             q = _exchange_rates(model, S.flowja, offs, e)
                         bw.write_exchange(kstp, kper, delt, pertim, totim, e["name"], sim.models[other].name,
-                                          e[mine], e[theirs], sign * q, e["auxname"], e["aux"])
+                                          e["user" + mine], e["user" + theirs], sign * q, e["auxname"], e["aux"])
     for hw, bw in writers:
         if hw:
             hw.close()
@@ -188,9 +197,10 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
             bw.close()
     xf = np.array(S.x, copy=True)      # (a solution class may hand out a view of memory it owns)
     if rank is not None:
-        heads = [xf.reshape(sim.models[rank].shape)]
+        heads = [_user_grid(sim.models[rank], xf).reshape(sim.models[rank].shape)]
     else:
-        heads = [xf[offs[k]:offs[k] + gi.model.nodes].reshape(gi.shape) for k, gi in enumerate(sim.models)]
+        heads = [_user_grid(gi, xf[offs[k]:offs[k] + gi.model.nodes]).reshape(gi.shape)
+                 for k, gi in enumerate(sim.models)]
     return dict(simulation=sim, reports=reports, heads=heads, solution=S)
 
 

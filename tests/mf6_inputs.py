@@ -93,7 +93,7 @@ def _disu_text(shape, delr, delc, top, botm):
 
 
 def write_gwf(d, name, shape, delr, delc, top, botm, k, chd=None, wel=None, icelltype=0, strt=0.0, k33=None,
-              sto=None, oc=True, newton=False, disv=False, extra_packages=(), disu=False):
+              sto=None, oc=True, newton=False, disv=False, extra_packages=(), disu=False, idomain=None):
     """chd / wel: dict iper -> list of ((k,i,j), value) with 1-based cellids.  disv=True writes the same
     rectangular grid as a DISV package (cellids become layer, icell2d)"""
     nlay, nrow, ncol = shape
@@ -107,6 +107,7 @@ def write_gwf(d, name, shape, delr, delc, top, botm, k, chd=None, wel=None, icel
            f"BEGIN options\nEND options\n\nBEGIN dimensions\n  NLAY {nlay}\n  NROW {nrow}\n  NCOL {ncol}\nEND dimensions\n\n"
            "BEGIN griddata\n" + _arr("delr", delr) + _arr("delc", delc) + _arr("top", top)
            + _arr("botm", botm, layered=np.ndim(botm) > 0)
+           + ("" if idomain is None else _arr("idomain", np.asarray(idomain, dtype=float), layered=True))
            + "END griddata\n")
     _w(os.path.join(d, f"{name}.ic"), "BEGIN griddata\n" + _arr("strt", strt) + "END griddata\n")
     npf = "BEGIN options\n  SAVE_FLOWS\nEND options\n\nBEGIN griddata\n" + _arr("icelltype", icelltype) \

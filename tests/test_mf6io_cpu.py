@@ -364,3 +364,49 @@ def test_rch01_recharge_reaches_the_highest_active_cell(tmp_path, irch):
     hds = read_head_file(tmp_path / "rch.hds")
     assert (hds[0]["data"].ravel()[[0, 1, 3, 4]] == -1.0e30).all()      # the dry cells carry HDRY
     assert hds[0]["data"].ravel()[2] > 50.0
+
+
+def test_idomain_reduced_numbering_and_pass_through(tmp_path):
+    """IDOMAIN like the reference treats it (disconnections, Connections.f90:463-700): cells with idomain <= 0 do
+    not exist (reduced node numbers), idomain < 0 connects the cells above and below it directly.  A confined
+    3-layer model whose whole middle layer is a pass-through equals the 2-layer model made of its outer layers;
+    a hole (idomain == 0) shows up as 1e30 in the head file, list records keep USER node numbers."""
+    rng = np.random.default_rng(8)
+    nrow, ncol = 5, 6
+    k3 = np.exp(rng.normal(0.3, 0.5, (3, nrow, ncol)))
+    ims = ("BEGIN nonlinear\n  OUTER_DVCLOSE 1e-10\n  OUTER_MAXIMUM 50\nEND nonlinear\n\n"
+           "BEGIN linear\n  INNER_MAXIMUM 200\n  INNER_DVCLOSE 1e-11\n  INNER_RCLOSE 1e-9\n  LINEAR_ACCELERATION CG\nEND linear\n")
+    idom = np.ones((3, nrow, ncol), dtype=int)
+    idom[1] = -1
+    idom[0, 2, 3] = 0                                      # a hole in the top layer
+    chd3 = [((kk, i + 1, 1), 5.0) for kk in (1, 3) for i in range(nrow)] + \
+           [((kk, i + 1, ncol), 2.0) for kk in (1, 3) for i in range(nrow)]
+    wel3 = [((3, 3, 3), -30.0), ((1, 3, 4), -10.0)]        # the second one sits in the hole: ignored with a warning
+    a = tmp_path / "three"
+    a.mkdir()
+    mf6_inputs.write_gwf(str(a), "m", (3, nrow, ncol), 20.0, 25.0, 0.0, [-4.0, -10.0, -18.0], k3, chd={1: chd3},
+                         wel={1: wel3}, strt=3.0, k33=0.2, idomain=idom)
+    mf6_inputs.write_sim(str(a), ["m"], [(1.0, 1, 1.0)], ims)
+    oa = simulate.run(str(a), ordering=T.ORDER_NATURAL, solution_class=oracle_class())
+    assert any("IDOMAIN removes" in w for w in oa["simulation"].warnings)
+    gi = oa["simulation"].models[0]
+    assert gi.model.nodes == 2 * nrow * ncol - 1 and gi.nodeuser.size == gi.model.nodes
+    # the equivalent 2-layer model: thicknesses 4 and 8, same K per layer, the hole as idomain 0 again
+    b = tmp_path / "two"
+    b.mkdir()
+    idom2 = np.ones((2, nrow, ncol), dtype=int)
+    idom2[0, 2, 3] = 0
+    chd2 = [((1 if c[0] == 1 else 2, c[1], c[2]), v) for c, v in chd3]
+    mf6_inputs.write_gwf(str(b), "m", (2, nrow, ncol), 20.0, 25.0, 0.0, [-4.0, -12.0], k3[[0, 2]], chd={1: chd2},
+                         wel={1: [((2, 3, 3), -30.0)]}, strt=3.0, k33=0.2, idomain=idom2)
+    mf6_inputs.write_sim(str(b), ["m"], [(1.0, 1, 1.0)], ims)
+    ob = simulate.run(str(b), ordering=T.ORDER_NATURAL, solution_class=oracle_class())
+    ha, hb = oa["heads"][0], ob["heads"][0]
+    assert np.array_equal(ha[0], hb[0]) and np.array_equal(ha[2], hb[1])         # identical systems
+    assert (ha[1] == 1.0e30).all() and ha[0, 2, 3] == 1.0e30 and ha[0].min() > 1.9
+    hds = read_head_file(a / "m.hds")
+    assert len(hds) == 3 and (hds[1]["data"] == 1.0e30).all() and hds[0]["data"][2, 3] == 1.0e30
+    cbc = read_budget_file(a / "m.cbc")
+    fja, wel = cbc[0], [r for r in cbc if r["text"].strip() == "WEL"][0]
+    assert fja["flow"].size == gi.model.nja                                     # the reduced connectivity
+    assert wel["node"].tolist() == [(2 * nrow + 2) * ncol + 3] and np.isclose(wel["q"][0], -30.0)   # USER node
