@@ -193,6 +193,8 @@ _PKG_NCOL = {"CHD6": 1, "WEL6": 1, "RIV6": 3, "RCH6": 1, "GHB6": 2, "DRN6": 2}
 
 def read_tdis(path):
     b = read_blocks(path)
+    if "ATS6" in _options(_block(b, "OPTIONS", required=False)):
+        raise Mf6InputError(f"{path}: adaptive time stepping (ATS6) is not supported on the GPU path")
     nper = int(_options(_block(b, "DIMENSIONS"))["NPER"][0])
     pd = [(float(t[0]), int(t[1]), float(t[2])) for t in _block(b, "PERIODDATA")]
     if len(pd) != nper:
