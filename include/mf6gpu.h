@@ -89,6 +89,12 @@ int64_t mf6gpu_matrix_info(const mf6gpu_matrix *m, int what);
 /* elimination order of the ILU: perm[k] = row (0-based, original numbering) eliminated k-th; this is the
  * symmetric permutation under which the device ILU0 equals the reference algorithm (NATURAL: identity) */
 int mf6gpu_matrix_get_permutation(const mf6gpu_matrix *m, int32_t *perm);
+/* HOST ONLY (needs no device): the elimination order mf6gpu_matrix_create[_blocked] would choose for this
+ * pattern, perm[k] = row eliminated k-th.  block_id may be NULL: MF6GPU_ORDER_BLOCK_MULTICOLOR then derives
+ * chains from the pattern (dominant far stride = the vertical cell columns of a DIS / DISV numbering).
+ * Lets a CPU checker run the reference algorithm on the identically permuted system anywhere. */
+int mf6gpu_ordering_compute(int32_t n, int32_t n_ext, int32_t nja, const int32_t *ia, const int32_t *ja,
+                            int32_t index_base, int32_t gpu_ordering, const int32_t *block_id, int32_t *perm);
 
 /* ---- VectorBaseType (SeqVector.f90) ---------------------------------------- */
 int mf6gpu_vector_create(int32_t n, mf6gpu_vector **out);
@@ -204,6 +210,8 @@ int mf6gpu_solution_get_nodes(mf6gpu_solution *s, int32_t cap, int32_t *nodes, i
 int mf6gpu_solution_get_storage(mf6gpu_solution *s, double *strgss, double *strgsy);
 /* elimination order of the owned cells (see mf6gpu_matrix_get_permutation) */
 int mf6gpu_solution_get_permutation(mf6gpu_solution *s, int32_t *perm);
+/* HOST ONLY: the elimination order mf6gpu_solution_create would use for this model (no device needed) */
+int mf6gpu_model_elimination_order(const mf6gpu_gwf_model *m, int32_t gpu_ordering, int32_t *perm);
 /* the linear solver owned by the solution (for stats / summary) */
 mf6gpu_solver *mf6gpu_solution_solver(mf6gpu_solution *s);
 /* facts: 0 kernel launches of the last time step, 1 ILU levels, 2 SELL slots,

@@ -84,35 +84,64 @@ void launch_scatter(int n, const int *perm, const double *in, double *out, cudaS
 }
 
 // ------------------------------------------------------------- host build ---
-// n = owned rows, n_ext >= n = owned + halo columns; gid (optional, [n_ext]) = global ids used
-// for arg-max tie-breaks in the split-model path
-static void build_matrix(mf6gpu_matrix &M, int n, int n_ext, int nja, const int32_t *ia_in,
-                         const int32_t *ja_in, int base, int ordering, const int32_t *gid,
-                         const int32_t *block_id = nullptr) {
-  MF6_REQUIRE(n > 0 && nja >= n && n_ext >= n, "matrix_create: bad dimensions");
-  MF6_REQUIRE(ordering == MF6GPU_ORDER_NATURAL || ordering == MF6GPU_ORDER_MULTICOLOR ||
-                  ordering == MF6GPU_ORDER_BLOCK_MULTICOLOR,
-              "matrix_create: unknown gpu_ordering");
-  if (ordering == MF6GPU_ORDER_BLOCK_MULTICOLOR && !block_id) ordering = MF6GPU_ORDER_MULTICOLOR;
-  M.n = n;
-  M.n_ext = n_ext;
-  M.nja = nja;
-  M.ordering = ordering;
-  std::vector<int> ia(n + 1), ja(nja);
-  for (int i = 0; i <= n; i++) ia[i] = ia_in[i] - base;
-  for (int i = 0; i < nja; i++) ja[i] = ja_in[i] - base;
-  MF6_REQUIRE(ia[0] == 0 && ia[n] == nja, "matrix_create: ia does not span nja (check index_base)");
-  for (int r = 0; r < n; r++) {
-    MF6_REQUIRE(ia[r + 1] > ia[r], "matrix_create: empty row");
-    MF6_REQUIRE(ja[ia[r]] == r, "matrix_create: rows must store the diagonal first (Sparse.f90:217-239)");
-    MF6_REQUIRE(ia[r + 1] - ia[r] <= 255, "matrix_create: more than 255 entries in a row");
+// Blocks for BLOCK_MULTICOLOR when the caller of the LinearSolverBase seam gives none (it only has the
+// sparsity pattern): chains along the dominant far stride of the pattern.  In the reference's DIS / DISV
+// numbering the LAST entry of a row is the cell below (offset nrow*ncol resp. ncpl, the same for every
+// row above the bottom layer), so the most frequent "last upper offset" S recovers the vertical cell
+// columns; on a single-layer grid it recovers the grid lines.  Cells v and v+S are chained when they are
+// connected; any partition into such chains is a valid block set (blocks are only required to be chains).
+// Returns an empty vector when fewer than a quarter of the rows can be chained.
+static std::vector<int32_t> derive_chain_blocks(int n, const std::vector<int> &ia, const std::vector<int> &ja) {
+  std::vector<int> off(n, 0);
+  std::vector<int> offs;
+  offs.reserve(n);
+  for (int v = 0; v < n; v++) {
+    int best = 0;
+    for (int p = ia[v] + 1; p < ia[v + 1]; p++)
+      if (ja[p] < n && ja[p] - v > best) best = ja[p] - v;
+    off[v] = best;
+    if (best > 0) offs.push_back(best);
   }
-  for (int p = 0; p < nja; p++) MF6_REQUIRE(ja[p] >= 0 && ja[p] < n_ext, "matrix_create: column out of range");
-  auto is_halo = [&](int c) { return c >= n; };
-  // --- elimination order (ordidx[old] = position in the reference-style loop)
-  std::vector<int> ordidx(n);
-  std::vector<int> blk_of, blk_color;  // BLOCK_MULTICOLOR: compact block of every row, colour of every block
+  if (offs.empty()) return {};
+  std::sort(offs.begin(), offs.end());
+  int S = 0;
+  size_t bestc = 0;
+  for (size_t i = 0; i < offs.size();) {
+    size_t j = i;
+    while (j < offs.size() && offs[j] == offs[i]) j++;
+    if (j - i > bestc || (j - i == bestc && offs[i] > S)) {
+      bestc = j - i;
+      S = offs[i];
+    }
+    i = j;
+  }
+  if (S <= 0 || bestc * 4 < (size_t)n) return {};
+  std::vector<int32_t> block(n);
+  for (int v = 0; v < n; v++) {
+    block[v] = v;
+    const int u = v - S;
+    if (u >= 0 && off[u] == S) block[v] = block[u];  // u's last entry is v: chained
+  }
+  return block;
+}
+
+// Elimination order of the ILU for one of the gpu_ordering choices (host only, no device work):
+// ordidx[old] = position in the reference-style elimination loop.  BLOCK_MULTICOLOR also returns the
+// compact block of every row and the colour of every block.
+struct ElimOrder {
+  std::vector<int> ordidx;
+  std::vector<int> blk_of, blk_color;
   int blk_count = 0, blk_colors = 0;
+};
+
+static ElimOrder compute_elimination(int n, const std::vector<int> &ia, const std::vector<int> &ja, int ordering,
+                                     const int32_t *block_id) {
+  ElimOrder E;
+  std::vector<int> &ordidx = E.ordidx;
+  ordidx.resize(n);
+  std::vector<int> &blk_of = E.blk_of, &blk_color = E.blk_color;
+  int &blk_count = E.blk_count, &blk_colors = E.blk_colors;
+  auto is_halo = [&](int c) { return c >= n; };
   if (ordering == MF6GPU_ORDER_NATURAL) {
     std::iota(ordidx.begin(), ordidx.end(), 0);
   } else if (ordering == MF6GPU_ORDER_BLOCK_MULTICOLOR) {
@@ -202,6 +231,47 @@ static void build_matrix(mf6gpu_matrix &M, int n, int n_ext, int nja, const int3
     for (int c = 0; c < ncolors; c++) cnt[c + 1] += cnt[c];
     for (int v = 0; v < n; v++) ordidx[v] = cnt[color[v]]++;
   }
+  return E;
+}
+
+
+// n = owned rows, n_ext >= n = owned + halo columns; gid (optional, [n_ext]) = global ids used
+// for arg-max tie-breaks in the split-model path
+static void build_matrix(mf6gpu_matrix &M, int n, int n_ext, int nja, const int32_t *ia_in,
+                         const int32_t *ja_in, int base, int ordering, const int32_t *gid,
+                         const int32_t *block_id = nullptr) {
+  MF6_REQUIRE(n > 0 && nja >= n && n_ext >= n, "matrix_create: bad dimensions");
+  MF6_REQUIRE(ordering == MF6GPU_ORDER_NATURAL || ordering == MF6GPU_ORDER_MULTICOLOR ||
+                  ordering == MF6GPU_ORDER_BLOCK_MULTICOLOR,
+              "matrix_create: unknown gpu_ordering");
+  M.n = n;
+  M.n_ext = n_ext;
+  M.nja = nja;
+  M.ordering = ordering;
+  std::vector<int> ia(n + 1), ja(nja);
+  for (int i = 0; i <= n; i++) ia[i] = ia_in[i] - base;
+  for (int i = 0; i < nja; i++) ja[i] = ja_in[i] - base;
+  MF6_REQUIRE(ia[0] == 0 && ia[n] == nja, "matrix_create: ia does not span nja (check index_base)");
+  for (int r = 0; r < n; r++) {
+    MF6_REQUIRE(ia[r + 1] > ia[r], "matrix_create: empty row");
+    MF6_REQUIRE(ja[ia[r]] == r, "matrix_create: rows must store the diagonal first (Sparse.f90:217-239)");
+    MF6_REQUIRE(ia[r + 1] - ia[r] <= 255, "matrix_create: more than 255 entries in a row");
+  }
+  for (int p = 0; p < nja; p++) MF6_REQUIRE(ja[p] >= 0 && ja[p] < n_ext, "matrix_create: column out of range");
+  auto is_halo = [&](int c) { return c >= n; };
+  std::vector<int32_t> derived;
+  if (ordering == MF6GPU_ORDER_BLOCK_MULTICOLOR && !block_id) {
+    derived = derive_chain_blocks(n, ia, ja);
+    if (derived.empty())
+      ordering = MF6GPU_ORDER_MULTICOLOR;
+    else
+      block_id = derived.data();
+  }
+  M.ordering = ordering;
+  ElimOrder E = compute_elimination(n, ia, ja, ordering, block_id);
+  std::vector<int> &ordidx = E.ordidx;
+  std::vector<int> &blk_of = E.blk_of, &blk_color = E.blk_color;
+  const int blk_count = E.blk_count, blk_colors = E.blk_colors;
   std::vector<int> byord(n);  // byord[ord] = old
   for (int v = 0; v < n; v++) byord[ordidx[v]] = v;
   M.elim = byord;
@@ -511,6 +581,30 @@ int mf6gpu_matrix_create_blocked(int32_t n_own, int32_t n_ext, int32_t nja, cons
       throw;
     }
     *out = M;
+  });
+}
+
+// Host-only (no device needed): the elimination order build_matrix would choose for this pattern,
+// perm[k] = original row eliminated k-th.  Lets a CPU checker apply the reference algorithm to the
+// same symmetrically permuted system without a GPU (oracle runs at full size, tests/golden/).
+int mf6gpu_ordering_compute(int32_t n, int32_t n_ext, int32_t nja, const int32_t *ia_in, const int32_t *ja_in,
+                            int32_t index_base, int32_t gpu_ordering, const int32_t *block_id, int32_t *perm) {
+  return guard([&] {
+    MF6_REQUIRE(ia_in && ja_in && perm && n > 0 && nja >= n && n_ext >= n, "ordering_compute: bad argument");
+    std::vector<int> ia(n + 1), ja(nja);
+    for (int i = 0; i <= n; i++) ia[i] = ia_in[i] - index_base;
+    for (int i = 0; i < nja; i++) ja[i] = ja_in[i] - index_base;
+    int ordering = gpu_ordering;
+    std::vector<int32_t> derived;
+    if (ordering == MF6GPU_ORDER_BLOCK_MULTICOLOR && !block_id) {
+      derived = derive_chain_blocks(n, ia, ja);
+      if (derived.empty())
+        ordering = MF6GPU_ORDER_MULTICOLOR;
+      else
+        block_id = derived.data();
+    }
+    ElimOrder E = compute_elimination(n, ia, ja, ordering, block_id);
+    for (int v = 0; v < n; v++) perm[E.ordidx[v]] = v;
   });
 }
 

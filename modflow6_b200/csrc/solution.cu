@@ -1264,6 +1264,23 @@ struct DistArgs {
   const int32_t *global_id;  // [nodes] global cell id of every local cell (owned + halo)
 };
 
+// blocks of the BLOCK_MULTICOLOR ordering: the vertical cell columns (chains of ihc == 0 connections)
+static std::vector<int32_t> model_column_blocks(const mf6gpu_gwf_model *m, int n_own) {
+  const int base0 = m->index_base;
+  std::vector<int32_t> block((size_t)n_own);
+  for (int v = 0; v < n_own; v++) {
+    block[v] = v;
+    for (int p = m->ia[v] - base0 + 1; p < m->ia[v + 1] - base0; p++) {
+      const int u = m->ja[p] - base0;
+      if (u < v && m->ihc[m->jas[p] - base0] == 0) {
+        block[v] = block[u];
+        break;
+      }
+    }
+  }
+  return block;
+}
+
 static void create_solution(const mf6gpu_gwf_model *m, const mf6gpu_sln_settings *sln,
                             const mf6gpu_ims_settings *ims, const DistArgs *da, mf6gpu_solution **out) {
     MF6_REQUIRE(m && sln && ims && out, "solution_create: null argument");
@@ -1282,22 +1299,8 @@ static void create_solution(const mf6gpu_gwf_model *m, const mf6gpu_sln_settings
     s->njas = m->njas;
     s->ss = *sln;
     s->isymmetric = (ims->ilinmeth == 1) ? 1 : 0;  // NumericalSolution.f90:914-916
-    // blocks of the BLOCK_MULTICOLOR ordering: the vertical cell columns (chains of ihc == 0 connections)
     std::vector<int32_t> block;
-    if (ims->gpu_ordering == MF6GPU_ORDER_BLOCK_MULTICOLOR) {
-      const int base0 = m->index_base;
-      block.resize((size_t)n_own);
-      for (int v = 0; v < n_own; v++) {
-        block[v] = v;
-        for (int p = m->ia[v] - base0 + 1; p < m->ia[v + 1] - base0; p++) {
-          const int u = m->ja[p] - base0;
-          if (u < v && m->ihc[m->jas[p] - base0] == 0) {
-            block[v] = block[u];
-            break;
-          }
-        }
-      }
-    }
+    if (ims->gpu_ordering == MF6GPU_ORDER_BLOCK_MULTICOLOR) block = model_column_blocks(m, n_own);
     if (mf6gpu_matrix_create_blocked(n_own, m->nodes, nja_own, m->ia, m->ja, m->index_base, ims->gpu_ordering,
                                      da ? da->global_id : nullptr, block.empty() ? nullptr : block.data(),
                                      &s->A) != 0) {
@@ -1819,6 +1822,19 @@ int mf6gpu_solution_get_permutation(mf6gpu_solution *s, int32_t *perm) {
   return guard([&] {
     MF6_REQUIRE(s && perm, "solution_get_permutation: null argument");
     std::memcpy(perm, s->A->elim.data(), sizeof(int) * (size_t)s->n);
+  });
+}
+
+// Host-only: the elimination order mf6gpu_solution_create would use for this model (perm[k] = cell
+// eliminated k-th); needs no device, so a CPU checker can be run on the same permuted system anywhere.
+int mf6gpu_model_elimination_order(const mf6gpu_gwf_model *m, int32_t gpu_ordering, int32_t *perm) {
+  return guard([&] {
+    MF6_REQUIRE(m && perm, "model_elimination_order: null argument");
+    std::vector<int32_t> block;
+    if (gpu_ordering == MF6GPU_ORDER_BLOCK_MULTICOLOR) block = model_column_blocks(m, m->nodes);
+    if (mf6gpu_ordering_compute(m->nodes, m->nodes, m->nja, m->ia, m->ja, m->index_base, gpu_ordering,
+                                block.empty() ? nullptr : block.data(), perm) != 0)
+      throw Error(last_error());
   });
 }
 

@@ -30,6 +30,7 @@ SYMBOLS = [
     "mf6gpu_comm_p2p_export", "mf6gpu_comm_p2p_import", "mf6gpu_comm_p2p_enabled", "mf6gpu_comm_p2p_disable",
     "mf6gpu_matrix_create_blocked", "mf6gpu_solution_get_permutation",
     "mf6gpu_solution_get_simvals", "mf6gpu_solution_get_storage", "mf6gpu_solution_get_nodes",
+    "mf6gpu_ordering_compute", "mf6gpu_model_elimination_order",
 ]
 
 _lib = None
@@ -89,6 +90,8 @@ def load():
     L.mf6gpu_matrix_create_ext.argtypes = [i32, i32, i32, pi32, pi32, i32, i32, pi32, vpp]
     L.mf6gpu_matrix_create_blocked.argtypes = [i32, i32, i32, pi32, pi32, i32, i32, pi32, pi32, vpp]
     L.mf6gpu_solution_get_permutation.argtypes = [vp, pi32]
+    L.mf6gpu_ordering_compute.argtypes = [i32, i32, i32, pi32, pi32, i32, i32, pi32, pi32]
+    L.mf6gpu_model_elimination_order.argtypes = [C.POINTER(T.GwfModelStruct), i32, pi32]
     L.mf6gpu_comm_unique_id.argtypes = [C.c_void_p]
     L.mf6gpu_comm_create.argtypes = [i32, i32, C.c_void_p, vpp]
     L.mf6gpu_comm_destroy.argtypes = [vp]
@@ -122,6 +125,15 @@ def check(rc):
     if rc < 0:
         raise Mf6GpuError(load().mf6gpu_last_error().decode("utf-8", "replace"))
     return rc
+
+
+def model_elimination_order(model, gpu_ordering):
+    """Host-only: perm[k] = cell eliminated k-th by the device ILU for this model and ordering (no GPU needed)."""
+    import numpy as np
+    ms = model.struct()
+    perm = np.empty(model.nodes, np.int32)
+    check(load().mf6gpu_model_elimination_order(C.byref(ms), int(gpu_ordering), T.ptr_i32(perm)))
+    return perm
 
 
 _initialised = False
