@@ -46,7 +46,12 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", default="10,1000,1000", help="nlay,nrow,ncol of the C2 grid")
     ap.add_argument("--ordering", default="block", choices=["multicolor", "natural", "block"])
-    ap.add_argument("--cpu-iters", type=int, default=12, help="inner iterations of the CPU sample")
+    ap.add_argument("--cpu-iters", type=int, default=None,
+                    help="CG iterations of the CPU sample (default 40 for the cpu_baseline leg, 100 for --impl reference)")
+    ap.add_argument("--blocks", default=None, help="N > 1: PRxPC block layout of the split model (default Nx1)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity blocks (profiling runs)")
+    ap.add_argument("--parity-max-cells", type=float, default=9e7,
+                    help="N > 1: the unsplit model is solved on rank 0 for the parity block up to this many cells")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--inner-maximum", type=int, default=500, help="INNER_MAXIMUM of the IMS LINEAR block")
     ap.add_argument("--outer-maximum", type=int, default=50, help="OUTER_MAXIMUM (1 = short profiling run)")
@@ -197,13 +202,29 @@ class CpuSample:
                 "wall": wall, "value": n * rep.inner_iterations / rep.t_linsolve}
 
 
+def reference_full_solve(size):
+    """The reference algorithm (natural ordering) run to convergence on the full workload: iteration counts,
+    budget and 1-core linear-solve seconds, recorded when the fixture was made (tests/golden/make_golden_full.py;
+    a 15-20 minute run, so it is not repeated inside the bench)."""
+    if tuple(size) != (10, 1000, 1000):
+        return None
+    from oracle import golden
+    g = golden.load("c2_full_natural")
+    if g is None:
+        return None
+    st = g["meta"]["steps"][-1]
+    return {"source": g["file"], "outer_iterations": st["outer_iterations"], "inner_iterations": st["inner_iterations"],
+            "pdiffr": st["pdiffr"], "linear_solve_s_1core": st["t_linsolve"], "formulate_s_1core": st["t_formulate"],
+            "host": "build container (not the GPU box)"}
+
+
 def run_reference(args, size):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cfg = build_config(size, "natural")
     n = cfg.model.nodes
-    iters = args.cpu_iters
+    iters = args.cpu_iters or 100
     cs = CpuSample(cfg, iters)
     vals, times = [], []
     t_begin = time.perf_counter()
@@ -229,7 +250,107 @@ def run_reference(args, size):
                                        f"compiler in this image), 1 outer iteration capped at {iters} CG iterations "
                                        f"on the full {n}-cell system; linear-solve time only"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    full = reference_full_solve(size)
+    if full:
+        line["full_solve"] = full
     print(json.dumps(line), flush=True)
+
+
+def exchange_desc(G, world):
+    if world == 1:
+        return "none"
+    if G.solver_stat(5) > 0:
+        return ("fused peer-memory exchange over NVLink (CUDA IPC mailboxes): the last CTA of the producing kernel "
+                "pushes halo cells / reduction records, the consuming kernels wait on flags; 1 extra launch per "
+                "iteration")
+    if G.comm.p2p:
+        return "peer-memory mailboxes (CUDA IPC): push + pull kernels per halo, push + finalize per reduction"
+    return "NCCL send/recv halo per SpMV + all-gather of Krylov scalars"
+
+
+def seam_e2e(G, cfg, steps, heads_ref):
+    """e2e through the LinearSolverBase seam with HOST buffers: amat / rhs of the formulated system come back to
+    the host once (untimed: in the reference they are assembled there), then every outer iteration calls
+    mf6gpu_matrix_update(amat) + mf6gpu_solver_solve(rhs, x) like PetscSolver%solve does; the outer loop stops on
+    max |dx| <= OUTER_DVCLOSE like sln_get_dxmax."""
+    import torch
+    from modflow6_b200 import ctypes_types as T
+    from modflow6_b200.linear import GpuLinearSolver, GpuMatrix
+    m = cfg.model
+    G.reset_x()
+    G.formulate(1, 1.0, 1)
+    amat, rhs, x0 = G.amat, G.rhs, G.x
+    A = GpuMatrix(m.ia, m.ja, 0, T.ORDER_BLOCK_MULTICOLOR)       # block ids derived from the pattern
+    S = GpuLinearSolver(A, cfg.ims)
+    n = m.nodes
+
+    def one_step():
+        x = x0.copy()
+        inner = 0
+        for kiter in range(1, cfg.sln.mxiter + 1):
+            xold = x.copy()
+            A.update(amat)
+            it, cv = S.solve(kiter, rhs, x)
+            inner += it
+            if np.abs(x - xold).max() <= cfg.sln.dvclose:
+                return x, inner, kiter
+        return x, inner, cfg.sln.mxiter
+
+    one_step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    inner = outer = 0
+    for _ in range(steps):
+        x, it, ko = one_step()
+        inner += it
+        outer += ko
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    out = {"value": n * inner / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+           "outer_iterations_per_step": outer / steps, "inner_iterations_per_step": inner / steps,
+           "h2d_bytes_per_step": int((amat.nbytes + 2 * rhs.nbytes) * outer / steps),
+           "d2h_bytes_per_step": int(rhs.nbytes * outer / steps),
+           "ilu_levels": A.nlevels, "max_abs_dhead_vs_solution_path": float(np.abs(x - heads_ref).max()),
+           "calls": "mf6gpu_matrix_update + mf6gpu_solver_solve per outer iteration, pageable numpy buffers"}
+    S.destroy()
+    A.destroy()
+    return out
+
+
+def split_parity(G, sub, spec, heads, rep, ims_s, sln_s, pkgs, rank, world, args):
+    """N > 1: the heads of the split solve against the SAME global model solved unsplit on one GPU (rank 0) with the
+    same settings -- what autotest/test_par_*.py do with `mf6 -p` vs serial.  Returns the parity block (rank 0)."""
+    import torch
+    import torch.distributed as dist
+    from modflow6_b200.distributed import build_dis_block
+    from modflow6_b200.solution import GpuNumericalSolution
+    n_glob = spec.nlay * spec.nrow * spec.ncol
+    if n_glob > args.parity_max_cells:
+        return {"skipped": f"{n_glob} cells > --parity-max-cells"}
+    xg = torch.zeros(n_glob, dtype=torch.float64, device="cuda")
+    xg[torch.from_numpy(sub.global_id[:sub.n_own].astype(np.int64)).cuda()] = torch.from_numpy(heads).cuda()
+    dist.all_reduce(xg)
+    out = None
+    if rank == 0:
+        t0 = time.perf_counter()
+        g = build_dis_block(spec, 1, 1, 0)
+        S1 = GpuNumericalSolution(g.model, sln_s, ims_s)
+        S1.set_packages(pkgs)
+        r1 = S1.timestep(1, 1, 1.0, 1)
+        x1 = S1.x
+        dh = np.abs(xg.cpu().numpy() - x1)
+        out = {"case": f"{world}-rank split solve vs the unsplit {spec.nlay}x{spec.nrow}x{spec.ncol} model on one GPU",
+               "max_abs_dhead": float(dh.max()), "tolerance": 0.1 * sln_s.dvclose,
+               "ok": bool(dh.max() <= 0.1 * sln_s.dvclose and abs(rep.pdiffr - r1.pdiffr) <= 1e-3),
+               "outer_iterations": {"split": rep.outer_iterations, "unsplit": r1.outer_iterations},
+               "inner_iterations": {"split": rep.inner_iterations, "unsplit": r1.inner_iterations},
+               "budget_pct_discrepancy": {"split": rep.pdiffr, "unsplit": r1.pdiffr},
+               "unsplit_timestep_s": r1.t_linsolve + r1.t_formulate, "wall_s": time.perf_counter() - t0}
+        S1.destroy()
+    dist.barrier()
+    return out
 
 
 def main():
@@ -278,6 +399,10 @@ def main():
         # blocks are stacked along the rows (the no-flow direction): the constant heads stay 1000 columns
         # apart, so the conditioning -- and the inner-iteration count -- does not grow with the GPU count
         pr, pc = world, 1
+        if args.blocks:
+            pr, pc = (int(v) for v in args.blocks.lower().split("x"))
+            if pr * pc != world:
+                raise SystemExit(f"bench.py: --blocks {args.blocks} needs {pr * pc} ranks, got {world}")
         if args.scaling == "strong":
             spec = GridSpec(nlay=size[0], nrow=size[1], ncol=size[2])
         else:
@@ -356,6 +481,22 @@ def main():
     ms_e = e2.elapsed_time(e3)
     heads = G.x
     converged = rep.converged
+    pdiffr, totrin, totrot = rep.pdiffr, rep.totrin, rep.totrot
+
+    # ---- N = 1: the LinearSolverBase-level call sequence (LinearSolverBase.f90:43-51, PetscSolver.F90:304-362):
+    # per outer iteration the host hands over its CSR amat (mf6gpu_matrix_update) and rhs / x arrays
+    # (mf6gpu_solver_solve) and gets x back; the block ordering is derived from the sparsity pattern alone
+    seam = None
+    if world == 1 and not args.no_parity:
+        try:
+            seam = seam_e2e(G, cfg, args.steps, heads)
+        except Exception as e:
+            seam = {"error": f"{type(e).__name__}: {e}"}
+
+    # ---- N > 1: correctness of the split solve = heads against the unsplit model solved on ONE GPU
+    parity_n = None
+    if world > 1 and not args.no_parity:
+        parity_n = split_parity(G, sub, spec, heads, rep, ims_s, sln_s, pkgs, rank, world, args)
 
     # max over ranks; iteration counts are global (identical on every rank), cells are summed over ranks
     if world > 1:
@@ -387,13 +528,15 @@ def main():
                                    f"({args.ordering} ILU ordering)",
                        "cells": n_total, "cells_per_gpu": n, "nja_per_gpu": nja,
                        "l2_policy": "inputs_exceed_l2 (matrix+vectors >> 126 MB)", "layout": layout,
-                       "exchange": "NCCL send/recv halo per SpMV + all-gather of Krylov scalars" if world > 1 else "none",
+                       "exchange": exchange_desc(G, world),
                        "inner_dvclose": ims_s.dvclose, "inner_rclose": ims_s.rclose,
                        "inner_maximum": ims_s.iter1, "outer_dvclose": sln_s.dvclose},
             "solve": {"outer_iterations_per_step": outer / args.steps, "inner_iterations_per_step": inner / args.steps,
                       "converged": int(converged), "linear_solve_s_per_step": t_ls / args.steps,
                       "formulate_s_per_step": t_form / args.steps, "timestep_s": ms * 1e-3 / args.steps,
-                      "head_min": float(heads.min()), "head_max": float(heads.max())},
+                      "time_to_solution_s": ms * 1e-3 / args.steps, "pdiffr": pdiffr, "totrin": totrin,
+                      "totrot": totrot, "head_min": float(heads.min()), "head_max": float(heads.max()),
+                      "timed_with_kernel_class_events": True},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world,
                     "d2h_bytes_per_step": int(d2h) * world,
                     "ms_per_step": ms_e / args.steps},
@@ -409,12 +552,39 @@ def main():
                          "kernels": kernels},
             "clocks": clocks,
         }
-        if not args.no_cpu_baseline and world == 1:
+        if world > 1:
+            line["p2p"] = bool(G.comm.p2p)
+            line["fused_exchange"] = bool(G.solver_stat(5) > 0)
+            if parity_n is not None:
+                line["parity"] = parity_n
+        if seam is not None:
+            line["e2e_linear_solver"] = seam
+        if world == 1 and not args.no_parity:
+            # the BENCHMARKED solve against the full-size oracle fixture (same ILU ordering), plus the small-grid
+            # run against a live oracle
             try:
-                line["parity"] = parity_check(args.ordering)
+                from oracle import golden
+                full = golden.compare_heads(f"c2_full_{args.ordering}", heads, sln_s.dvclose) \
+                    if size == (10, 1000, 1000) else None
+                if full is not None and "oracle" in full:
+                    full["case"] = "the benchmarked 10x1000x1000 solve vs the oracle on the same permuted system"
+                    full["outer_iterations"] = {"gpu": outer / args.steps, "oracle": full["oracle"]["outer_iterations"]}
+                    full["inner_iterations"] = {"gpu": inner / args.steps, "oracle": full["oracle"]["inner_iterations"]}
+                    full["budget_pct_discrepancy"] = {"gpu": pdiffr, "oracle": full["oracle"]["pdiffr"]}
+                    full["ok"] = bool(full["ok"] and abs(pdiffr - full["oracle"]["pdiffr"]) <= 1e-3)
+                    ref = reference_full_solve(size)
+                    if ref:
+                        full["reference_natural_order"] = ref
+                        line["solve"]["time_to_solution_ratio_vs_1core_reference"] = \
+                            ref["linear_solve_s_1core"] / (t_ls / args.steps)
+                    line["parity"] = full
+                    line["parity_small"] = parity_check(args.ordering)
+                else:
+                    line["parity"] = parity_check(args.ordering)
             except Exception as e:   # the side report must not cost the measurement; say so in the line
                 line["parity"] = {"error": f"{type(e).__name__}: {e}"}
-            s = CpuSample(build_config(size, "natural"), args.cpu_iters).run()
+        if not args.no_cpu_baseline and world == 1:
+            s = CpuSample(build_config(size, "natural"), args.cpu_iters or 40).run()
             line["cpu_baseline"] = {"value": s["value"], "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": f"C oracle (port; no Fortran compiler in the image), 1 outer iteration "
                                               f"capped at {s['iters']} CG iterations on the full {n}-cell system, "

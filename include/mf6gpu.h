@@ -128,7 +128,8 @@ int mf6gpu_solver_get_summary(mf6gpu_solver *s, int32_t cap, int32_t *itinner,
                               double *dvmax, int32_t *locdv, double *rmax,
                               int32_t *locr, double *alpha, double *omega);
 /* facts of the last solve: 0 l2norm0, 1 pivot corrections, 2 device seconds in
- * factorisation, 3 device seconds in the Krylov loop, 4 kernel launches */
+ * factorisation, 3 device seconds in the Krylov loop, 4 kernel launches, 5 split-model path: 1 when the
+ * fused peer-memory exchange (in-kernel pushes / waits over NVLink) was used, 0 for the NCCL transport */
 double mf6gpu_solver_stat(const mf6gpu_solver *s, int what);
 /* per-kernel-class device timing (CUDA events on the solver's stream):
  * classes 0 spmv, 1 ilu0 apply, 2 x/r update, 3 dot, 4 direction update, 5 factorisation */

@@ -199,8 +199,48 @@ void comm_check(mf6gpu_comm *c) {
   MF6_REQUIRE(e == 0, "comm: a peer-memory wait timed out (another rank stopped or fell out of step)");
 }
 
+DistRound comm_round(mf6gpu_comm *c) {
+  DistRound R{};
+  if (!c || !c->p2p) return R;
+  const unsigned long long seq = ++c->small_seq;
+  const int parity = (int)(seq & 1ull);
+  const P2PLayout &L = c->lay;
+  R.push = DistPush{c->d_peer.p, c->nranks, L.small_off(parity, c->rank), (int)L.small_doubles, seq};
+  R.pull = SmallGather{c->mailbox + L.small_off(parity, 0), L.small_slot(), (int)L.small_doubles, seq,
+                       c->d_err.p, c->nranks};
+  return R;
+}
+
+// stand-alone producer of a fused halo round (the same device code the fused producers run in their last CTA)
+__global__ void __launch_bounds__(kBlock) halo_push_kernel(HaloPush P, const double *__restrict__ vec) {
+  halo_push_all(P, vec);
+}
+
+void HaloPlan::round(HaloPush &push, HaloSrc &src) {
+  const int nnbr = (int)nbr_rank.size();
+  const unsigned long long seq = ++comm->halo_seq;
+  const int parity = (int)(seq & 1ull);
+  const P2PLayout &L = comm->lay;
+  push = HaloPush{comm->d_peer.p, nnbr, d_nbr_rank.p, d_send_ptr.p, send_idx.p, L.halo_off(parity, comm->rank),
+                  (int)L.halo_doubles, seq, ticket.p};
+  src = HaloSrc{};
+  src.nnbr = nnbr;
+  src.n_own = n_own;
+  for (int k = 0; k <= nnbr; k++) src.recv_ptr[k] = recv_ptr[k];
+  for (int k = 0; k < nnbr; k++)
+    src.msg[k] = reinterpret_cast<const double *>(comm->mailbox + L.halo_off(parity, nbr_rank[k]));
+  src.cap = (int)L.halo_doubles;
+  src.seq = seq;
+  src.err = comm->d_err.p;
+  src.slice_halo = slice_halo.p;
+}
+
+void HaloPlan::push_now(const HaloPush &push, const double *vec, cudaStream_t s) {
+  halo_push_kernel<<<1, kBlock, 0, s>>>(push, vec);
+}
+
 SmallGather comm_small_push(mf6gpu_comm *c, const double *in, size_t count, cudaStream_t s) {
-  SmallGather g{nullptr, 0, 0, 0, nullptr};
+  SmallGather g{nullptr, 0, 0, 0, nullptr, 0};
   if (!c || !c->p2p || count > c->lay.small_doubles) return g;
   const unsigned long long seq = ++c->small_seq;
   const int parity = (int)(seq & 1ull);
@@ -212,6 +252,7 @@ SmallGather comm_small_push(mf6gpu_comm *c, const double *in, size_t count, cuda
   g.cap = (int)L.small_doubles;
   g.seq = seq;
   g.err = c->d_err.p;
+  g.nranks = c->nranks;
   return g;
 }
 

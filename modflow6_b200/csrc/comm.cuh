@@ -44,6 +44,61 @@ struct mf6gpu_comm {
 
 namespace mf6 {
 
+// Peer-memory small all-gather split in two: the push is issued here, the consumer kernel waits for
+// the flags itself and reads the records in place (no pull kernel, no staging copy).
+struct SmallGather {
+  const char *base;          // first record of this parity in the own mailbox (nullptr: not the p2p path)
+  size_t slot;               // byte stride between the records of consecutive ranks
+  int cap;                   // doubles before the flag word
+  unsigned long long seq;
+  int *err;
+  int nranks;
+};
+SmallGather comm_small_push(mf6gpu_comm *c, const double *in, size_t count, cudaStream_t s);
+
+// One reduction round of the fused peer-memory path: no launch of its own.  The LAST CTA of the kernel that
+// produces this rank's partial result stores the 8-double record into every peer's mailbox (DistPush) and
+// every CTA of the kernel that consumes the result waits for the nranks records in its own mailbox and
+// combines them in rank order (SmallGather) -- bit-identical scalars on every rank, no finalize launch.
+struct DistPush {
+  char *const *peer;         // device table of the mapped mailboxes; nullptr = not the fused path
+  int nranks;
+  size_t off;                // byte offset of this rank's record of this round inside every mailbox
+  int cap;
+  unsigned long long seq;
+};
+struct DistRound {
+  DistPush push;
+  SmallGather pull;
+};
+DistRound comm_round(mf6gpu_comm *c);   // allocates the next sequence number (host side only)
+
+// Halo exchange of the fused path.  Producer side (HaloPush): the last CTA of the kernel that finalises the
+// vector gathers the send cells into the neighbours' mailboxes and publishes the flags.  Consumer side
+// (HaloSrc): the SpMV reads halo columns straight out of the own mailbox; rows of slices that touch a halo
+// column are deferred to the end of the kernel and wait for the flags there, so the exchange overlaps the
+// interior rows (replaces MatMult's VecScatterBegin/End overlap, PetscMatrix.F90:108-113).
+constexpr int kMaxHaloNbr = 8;
+struct HaloPush {
+  char *const *peer;         // nullptr = nothing to push
+  int nnbr;
+  const int *nbr_rank, *send_ptr, *send_idx;
+  size_t off;                // byte offset of this rank's message slot of this round in the peers' mailboxes
+  int cap;
+  unsigned long long seq;
+  unsigned int *ticket;
+};
+struct HaloSrc {
+  int nnbr;                  // 0 = halo columns live behind the owned entries of the vector (legacy layout)
+  int n_own;
+  int recv_ptr[kMaxHaloNbr + 1];
+  const double *msg[kMaxHaloNbr];              // neighbour k's message of this round in the own mailbox
+  int cap;
+  unsigned long long seq;
+  int *err;
+  const unsigned char *slice_halo;             // [nslices] 1 = the slice has a row with a halo column
+};
+
 // halo pattern of one solution on one rank
 struct HaloPlan {
   mf6gpu_comm *comm = nullptr;
@@ -53,35 +108,87 @@ struct HaloPlan {
   DevBuf<int> d_nbr_rank, d_send_ptr, d_recv_ptr; // device copies for the peer-memory kernels
   DevBuf<unsigned int> ticket;
   DevBuf<double> sendbuf;
+  DevBuf<unsigned char> slice_halo;               // [nslices] slices with halo columns (fused SpMV)
   bool active() const { return comm != nullptr && comm->nranks > 1; }
+  // fused peer-memory path available (mailboxes mapped, few enough neighbours)?
+  bool fused() const {
+    return active() && comm->p2p && !nbr_rank.empty() && (int)nbr_rank.size() <= kMaxHaloNbr && slice_halo.n > 0;
+  }
   // vec[n_own + recv range of neighbour k] <- neighbour k's owned values
   void exchange(double *vec, cudaStream_t s);
+  // fused path: one round = (producer argument, consumer argument); `push_now` launches the stand-alone
+  // push kernel for producers that cannot carry the push themselves (ILU sweeps, residual)
+  void round(HaloPush &push, HaloSrc &src);
+  void push_now(const HaloPush &push, const double *vec, cudaStream_t s);
 };
-
-// Peer-memory small all-gather split in two: the push is issued here, the consumer kernel waits for
-// the flags itself and reads the records in place (no pull kernel, no staging copy).
-struct SmallGather {
-  const char *base;          // first record of this parity in the own mailbox (nullptr: not the p2p path)
-  size_t slot;               // byte stride between the records of consecutive ranks
-  int cap;                   // doubles before the flag word
-  unsigned long long seq;
-  int *err;
-};
-SmallGather comm_small_push(mf6gpu_comm *c, const double *in, size_t count, cudaStream_t s);
 
 #ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// spin until *flag >= seq; gives up (and raises *err) after ~2^27 polls so a dead peer cannot hang the GPU
+__device__ __forceinline__ bool wait_seq(const unsigned long long *flag, unsigned long long seq, int *err) {
+  for (unsigned int spin = 0; spin < (1u << 27); spin++) {
+    if (ld_acquire_sys_u64(flag) >= seq) return true;
+    __nanosleep(20);
+  }
+  *err = 1;
+  return false;
+}
 // device side of SmallGather: block until rank r's record of this round has landed, return it
 __device__ __forceinline__ const double *small_gather_wait(const SmallGather &g, int r) {
   const double *src = reinterpret_cast<const double *>(g.base + (size_t)r * g.slot);
-  const unsigned long long *flag = reinterpret_cast<const unsigned long long *>(src + g.cap);
-  for (unsigned int spin = 0; spin < (1u << 27); spin++) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
-    if (v >= g.seq) return src;
-    __nanosleep(20);
-  }
-  *g.err = 1;
+  wait_seq(reinterpret_cast<const unsigned long long *>(src + g.cap), g.seq, g.err);
   return src;
+}
+// producer side of a fused round: lanes 0..nranks-1 of the first warp store the record (8 doubles, written by
+// this CTA before the call and made visible with __syncthreads) into the peers' mailboxes + the flag
+__device__ __forceinline__ void dist_push_record(const DistPush &P, const double *rec8) {
+  const int q = threadIdx.x;
+  if (q < P.nranks) {
+    double *dst = reinterpret_cast<double *>(P.peer[q] + P.off);
+#pragma unroll
+    for (int i = 0; i < 8; i++) dst[i] = rec8[i];
+    __threadfence_system();
+    st_release_sys_u64(reinterpret_cast<unsigned long long *>(dst + P.cap), P.seq);
+  }
+}
+// value of halo column c (>= n_own) from the mailbox
+__device__ __forceinline__ double halo_load(const HaloSrc &H, int c) {
+  const int j = c - H.n_own;
+  int k = 0;
+#pragma unroll
+  for (int u = 1; u < kMaxHaloNbr; u++)
+    if (u < H.nnbr && j >= H.recv_ptr[u]) k = u;
+  return __ldcg(H.msg[k] + (j - H.recv_ptr[k]));
+}
+// all threads of the CTA: wait until every neighbour's message of this round has landed
+__device__ __forceinline__ void halo_wait(const HaloSrc &H) {
+  if (threadIdx.x < H.nnbr)
+    wait_seq(reinterpret_cast<const unsigned long long *>(H.msg[threadIdx.x] + H.cap), H.seq, H.err);
+  __syncthreads();
+}
+// last CTA of the producing kernel (all its threads; the vector is complete and fenced): push the send cells
+__device__ __forceinline__ void halo_push_all(const HaloPush &P, const double *vec) {
+  const int total = P.send_ptr[P.nnbr];
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    int k = 0;
+    while (i >= P.send_ptr[k + 1]) k++;
+    double *dst = reinterpret_cast<double *>(P.peer[P.nbr_rank[k]] + P.off);
+    dst[i - P.send_ptr[k]] = __ldcg(vec + P.send_idx[i]);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < P.nnbr) {
+    __threadfence_system();
+    double *dst = reinterpret_cast<double *>(P.peer[P.nbr_rank[threadIdx.x]] + P.off);
+    st_release_sys_u64(reinterpret_cast<unsigned long long *>(dst + P.cap), P.seq);
+  }
 }
 #endif
 

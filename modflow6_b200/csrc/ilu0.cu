@@ -96,7 +96,7 @@ __device__ __forceinline__ void ilu_dot_finish(double s, const IluDot &D) {
 __global__ void __launch_bounds__(kBlock)
 ilu_dot_reduce_kernel(int nslots, const double *__restrict__ partial, double *__restrict__ cta_sums,
                       unsigned int *ticket, double *rho_out, double *beta_out, const double *rho0,
-                      const int *__restrict__ done) {
+                      const int *__restrict__ done, DistPush push) {
   __shared__ double sh[8];
   __shared__ bool last;
   if (done && *done) return;
@@ -116,7 +116,11 @@ ilu_dot_reduce_kernel(int nslots, const double *__restrict__ partial, double *__
   if (last_block(ticket, &last)) {
     double t = (threadIdx.x < gridDim.x) ? cta_sums[threadIdx.x] : 0.0;
     t = block_sum(t, sh);
-    if (threadIdx.x == 0) {
+    if (push.peer) {
+      if (threadIdx.x < 8) sh[threadIdx.x] = (threadIdx.x == 0) ? t : 0.0;
+      __syncthreads();
+      dist_push_record(push, sh);
+    } else if (threadIdx.x == 0) {
       *rho_out = t;
       *beta_out = t / *rho0;
     }
@@ -334,7 +338,7 @@ static int launch_levels_w(const mf6gpu_matrix &A, const double *lu, const doubl
   if (dot) {
     const int rb = std::max(1, std::min(148, slot / (4 * kBlock)));
     ilu_dot_reduce_kernel<<<rb, kBlock, 0, s>>>(slot, dot->partial, dot->cta_sums, dot->ticket, dot->rho_out,
-                                                dot->beta_out, dot->rho0, done);
+                                                dot->beta_out, dot->rho0, done, dot->push);
     launches++;
   }
   return launches;
@@ -672,7 +676,7 @@ static int launch_blocks_w(const mf6gpu_matrix &A, const double *lu, const doubl
   if (dot) {
     const int rb = std::max(1, std::min(148, slot / (4 * kBlock)));
     ilu_dot_reduce_kernel<<<rb, kBlock, 0, s>>>(slot, dot->partial, dot->cta_sums, dot->ticket, dot->rho_out,
-                                                dot->beta_out, dot->rho0, done);
+                                                dot->beta_out, dot->rho0, done, dot->push);
     launches++;
   }
   return launches;
@@ -741,7 +745,7 @@ static int launch_two_level(const mf6gpu_matrix &A, const double *lu, const doub
     const int slot = (gA + gB) * (kBlock / 32);
     const int rb = std::max(1, std::min(148, slot / (4 * kBlock)));
     ilu_dot_reduce_kernel<<<rb, kBlock, 0, s>>>(slot, dot->partial, dot->cta_sums, dot->ticket, dot->rho_out,
-                                                dot->beta_out, dot->rho0, done);
+                                                dot->beta_out, dot->rho0, done, dot->push);
     launches++;
   }
   return launches;
@@ -848,7 +852,7 @@ int ilu0_apply(const mf6gpu_matrix &A, const double *lu, const double *rin, doub
   if (dot) {
     const int rb = std::max(1, std::min(148, slot / (4 * kBlock)));
     ilu_dot_reduce_kernel<<<rb, kBlock, 0, s>>>(slot, dot->partial, dot->cta_sums, dot->ticket, dot->rho_out,
-                                                dot->beta_out, dot->rho0, done);
+                                                dot->beta_out, dot->rho0, done, dot->push);
     launches++;
   }
   return launches;

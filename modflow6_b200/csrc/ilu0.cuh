@@ -1,6 +1,7 @@
 // ilu0.cuh -- level-scheduled ILU0/MILU0 (see ilu0.cu)
 #pragma once
 #include "matrix.cuh"
+#include "comm.cuh"
 
 namespace mf6 {
 // one numeric factorisation pass with fixed (delta, ipcflag); *d_failflag is set
@@ -15,6 +16,7 @@ struct IluDotArgs {
   double *rho_out;       // receives the dot product
   double *beta_out;      // receives rho / *rho0
   const double *rho0;
+  DistPush push{};       // fused split-model path: the rank's partial rho goes straight to the peers' mailboxes
 };
 // d = (LU)^-1 rin.  `done` (device flag, may be null) turns the kernels into no-ops.
 // rin and d must be different arrays.

@@ -1346,6 +1346,17 @@ static void create_solution(const mf6gpu_gwf_model *m, const mf6gpu_sln_settings
                           "solution_create_dist: halo message larger than the peer mailbox");
           }
         }
+        {
+          // slices with a halo column: their rows wait for the neighbours' messages inside the fused SpMV
+          std::vector<unsigned char> sh((size_t)A->nslices, 0);
+          for (int v = 0; v < n_own; v++)
+            for (int p = m->ia[v] - base + 1; p < m->ia[v + 1] - base; p++)
+              if (m->ja[p] - base >= n_own) {
+                sh[(size_t)(A->iperm[v] >> 5)] = 1;
+                break;
+              }
+          H.slice_halo.upload(sh);
+        }
         s->S->halo = &s->halo;
         s->os_all.alloc_zero(sizeof(OuterState) / sizeof(double) * (size_t)da->comm->nranks);
         s->h_os.alloc((size_t)da->comm->nranks);

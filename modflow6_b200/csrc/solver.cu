@@ -114,10 +114,13 @@ __device__ void finalize_sum(int mode, double s0, double s1, KState *st, double 
   }
 }
 
-// combine per-CTA partial sums (1 or 2 interleaved sums) in a fixed order
+// combine per-CTA partial sums (1 or 2 interleaved sums) in a fixed order.  Called by every thread of the
+// last CTA.  Split-model path: the rank's partial goes to the peers (fused round: stored into their
+// mailboxes right here; NCCL fallback: parked in st->red for the all-gather that follows).
 template <int NS>
 __device__ __forceinline__ void reduce_partials_and_finalize(int mode, const double *partial,
-                                                             KState *st, double *out, double *sh) {
+                                                             KState *st, double *out, double *sh,
+                                                             const DistPush &push) {
   double a0 = 0.0, a1 = 0.0;
   for (int i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
     a0 += partial[NS * i];
@@ -125,6 +128,12 @@ __device__ __forceinline__ void reduce_partials_and_finalize(int mode, const dou
   }
   a0 = block_sum(a0, sh);
   if (NS == 2) a1 = block_sum(a1, sh);
+  if (push.peer) {
+    if (threadIdx.x < 8) sh[threadIdx.x] = (threadIdx.x == 0) ? a0 : (threadIdx.x == 1 ? a1 : 0.0);
+    __syncthreads();
+    dist_push_record(push, sh);
+    return;
+  }
   if (threadIdx.x == 0) {
     if (st->dist) {
       st->red.s[0] = a0;
@@ -135,11 +144,34 @@ __device__ __forceinline__ void reduce_partials_and_finalize(int mode, const dou
   }
 }
 
+// Consumer side of a fused round (every CTA): lanes 0..nranks-1 of the first warp wait for one record each,
+// the sums are then combined in rank order (identical on every CTA and every rank); sc[0..1] = the two sums.
+__device__ __forceinline__ void dist_combine(const SmallGather &g, double *sc) {
+  if (threadIdx.x < 32) {
+    double v0 = 0.0, v1 = 0.0;
+    if ((int)threadIdx.x < g.nranks) {
+      const double *src = small_gather_wait(g, threadIdx.x);
+      v0 = __ldcg(src);
+      v1 = __ldcg(src + 1);
+    }
+    double s0 = 0.0, s1 = 0.0;
+    for (int r = 0; r < g.nranks; r++) {
+      s0 += __shfl_sync(0xffffffffu, v0, r);
+      s1 += __shfl_sync(0xffffffffu, v1, r);
+    }
+    if (threadIdx.x == 0) {
+      sc[0] = s0;
+      sc[1] = s1;
+    }
+  }
+  __syncthreads();
+}
+
 // ---- dot product (ddot) ------------------------------------------------------
 __global__ void __launch_bounds__(kBlock)
 dot_kernel(int n, const double *__restrict__ a, const double *__restrict__ b,
            double *__restrict__ partial, unsigned int *ticket, KState *st, int mode,
-           double *out, int check_done) {
+           double *out, int check_done, DistPush push) {
   __shared__ double sh[8];
   __shared__ bool last;
   if (check_done && st->done) return;
@@ -148,7 +180,7 @@ dot_kernel(int n, const double *__restrict__ a, const double *__restrict__ b,
     s += a[i] * b[i];
   s = block_sum(s, sh);
   if (threadIdx.x == 0) partial[blockIdx.x] = s;
-  if (last_block(ticket, &last)) reduce_partials_and_finalize<1>(mode, partial, st, out, sh);
+  if (last_block(ticket, &last)) reduce_partials_and_finalize<1>(mode, partial, st, out, sh, push);
 }
 
 // ---- dnrm2 in two passes (max |d|, then sum (d/scale)^2) ---------------------
@@ -190,12 +222,28 @@ nrm_ssq_kernel(int n, const double *__restrict__ a, double *__restrict__ partial
   s = block_sum(s, sh);
   if (threadIdx.x == 0) partial[blockIdx.x] = s;
   if (last_block(ticket, &last))
-    reduce_partials_and_finalize<1>(FIN_NRM_SSQ, partial, st, scale_io, sh);
+    reduce_partials_and_finalize<1>(FIN_NRM_SSQ, partial, st, scale_io, sh, DistPush{});
 }
 
 // ---- y = A x (+ fused dot products with the freshly computed y) --------------
 // EPI 0: y = A x ; EPI 1: y = b - A x (ims_base_residual)
 // NDOT 0: none ; 1: sum w[row]*y[row] ; 2: sum w[row]*y[row] and sum y[row]^2
+// Fused split-model path (H.nnbr > 0): halo columns are read from the peer-memory mailbox; rows of slices
+// that touch one are deferred behind the interior rows and wait for the neighbours' flags there.
+// (A x)_row for such a row, same slot order as sell_row_dot / sell_row_dot_w
+__device__ __forceinline__ double sell_row_dot_halo(int row, long long base, int len, const int *__restrict__ col,
+                                                    const double *__restrict__ val, const double *__restrict__ x,
+                                                    const HaloSrc &H) {
+  double t = 0.0;
+  for (int k = 0; k < len; k++) {
+    const long long p = base + 32LL * k;
+    const int c = __ldg(col + p);
+    const double xv = (c < H.n_own) ? x[c] : halo_load(H, c);
+    t = t + __ldg(val + p) * xv;
+  }
+  return t;
+}
+
 template <int EPI, int NDOT>
 __global__ void __launch_bounds__(kBlock)
 spmv_fused_kernel(int n, const int *__restrict__ slice_ptr,
@@ -203,17 +251,34 @@ spmv_fused_kernel(int n, const int *__restrict__ slice_ptr,
                   const double *__restrict__ val, const double *__restrict__ x,
                   double *__restrict__ y, const double *__restrict__ b,
                   const double *__restrict__ w, double *__restrict__ partial,
-                  unsigned int *ticket, KState *st, int mode, int check_done) {
+                  unsigned int *ticket, KState *st, int mode, int check_done,
+                  const __grid_constant__ HaloSrc H, DistPush push) {
   __shared__ double sh[8];
   __shared__ bool last;
   if (check_done && st->done) return;
   double s0 = 0.0, s1 = 0.0;
+  int deferred = 0;
   for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
+    if (H.nnbr > 0 && H.slice_halo[row >> 5]) {
+      deferred = 1;
+      continue;
+    }
     double t = sell_row_dot(row, slice_ptr, rowlen, col, val, x);
     if (EPI == 1) t = b[row] - t;
     y[row] = t;
     if (NDOT >= 1) s0 += w[row] * t;
     if (NDOT == 2) s1 += t * t;
+  }
+  if (H.nnbr > 0 && __syncthreads_or(deferred)) {
+    halo_wait(H);
+    for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
+      if (!H.slice_halo[row >> 5]) continue;
+      double t = sell_row_dot_halo(row, (long long)slice_ptr[row >> 5] + (row & 31), rowlen[row], col, val, x, H);
+      if (EPI == 1) t = b[row] - t;
+      y[row] = t;
+      if (NDOT >= 1) s0 += w[row] * t;
+      if (NDOT == 2) s1 += t * t;
+    }
   }
   if (NDOT >= 1) {
     s0 = block_sum(s0, sh);
@@ -223,7 +288,7 @@ spmv_fused_kernel(int n, const int *__restrict__ slice_ptr,
       if (NDOT == 2) partial[NDOT * blockIdx.x + 1] = s1;
     }
     if (last_block(ticket, &last))
-      reduce_partials_and_finalize<(NDOT == 2 ? 2 : 1)>(mode, partial, st, nullptr, sh);
+      reduce_partials_and_finalize<(NDOT == 2 ? 2 : 1)>(mode, partial, st, nullptr, sh, push);
   }
 }
 
@@ -234,17 +299,33 @@ spmv_fused_w_kernel(int n, int ncols, const int *__restrict__ col, const int *__
                     const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y,
                     const double *__restrict__ b, const double *__restrict__ w,
                     double *__restrict__ partial, unsigned int *ticket, KState *st, int mode,
-                    int check_done) {
+                    int check_done, const __grid_constant__ HaloSrc H, DistPush push) {
   __shared__ double sh[8];
   __shared__ bool last;
   if (check_done && st->done) return;
   double s0 = 0.0, s1 = 0.0;
+  int deferred = 0;
   for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
+    if (H.nnbr > 0 && H.slice_halo[row >> 5]) {
+      deferred = 1;
+      continue;
+    }
     double t = sell_row_dot_w<W>(row, col, val, x, soff, ncols);
     if (EPI == 1) t = b[row] - t;
     y[row] = t;
     if (NDOT >= 1) s0 += w[row] * t;
     if (NDOT == 2) s1 += t * t;
+  }
+  if (H.nnbr > 0 && __syncthreads_or(deferred)) {
+    halo_wait(H);
+    for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
+      if (!H.slice_halo[row >> 5]) continue;
+      double t = sell_row_dot_halo(row, (long long)(row >> 5) * (32 * W) + (row & 31), W, col, val, x, H);
+      if (EPI == 1) t = b[row] - t;
+      y[row] = t;
+      if (NDOT >= 1) s0 += w[row] * t;
+      if (NDOT == 2) s1 += t * t;
+    }
   }
   if (NDOT >= 1) {
     s0 = block_sum(s0, sh);
@@ -254,21 +335,22 @@ spmv_fused_w_kernel(int n, int ncols, const int *__restrict__ col, const int *__
       if (NDOT == 2) partial[NDOT * blockIdx.x + 1] = s1;
     }
     if (last_block(ticket, &last))
-      reduce_partials_and_finalize<(NDOT == 2 ? 2 : 1)>(mode, partial, st, nullptr, sh);
+      reduce_partials_and_finalize<(NDOT == 2 ? 2 : 1)>(mode, partial, st, nullptr, sh, push);
   }
 }
 
 template <int EPI, int NDOT>
 static void launch_spmv_fused(const mf6gpu_matrix &A, int G, cudaStream_t S, const double *x, double *y,
                               const double *b, const double *w, double *partial, unsigned int *ticket,
-                              KState *st, int mode, int check_done) {
+                              KState *st, int mode, int check_done, const HaloSrc &H = HaloSrc{},
+                              const DistPush &push = DistPush{}) {
   const int N = A.n;
 #define MF6_SPMV_W(WW)                                                                              \
   case WW:                                                                                          \
     spmv_fused_w_kernel<EPI, NDOT, WW><<<G, kBlock, 0, S>>>(N, A.n_ext, A.col.p,                     \
                                                             A.slot_off.n ? A.slot_off.p : nullptr,  \
                                                             A.val.p, x, y, b, w, partial,           \
-                                                            ticket, st, mode, check_done);          \
+                                                            ticket, st, mode, check_done, H, push); \
     return;
   switch (A.uniform_w) {
     MF6_SPMV_W(4)
@@ -283,26 +365,51 @@ static void launch_spmv_fused(const mf6gpu_matrix &A, int G, cudaStream_t S, con
   }
 #undef MF6_SPMV_W
   spmv_fused_kernel<EPI, NDOT><<<G, kBlock, 0, S>>>(N, A.slice_ptr.p, A.rowlen.p, A.col.p, A.val.p, x, y, b,
-                                                    w, partial, ticket, st, mode, check_done);
+                                                    w, partial, ticket, st, mode, check_done, H, push);
 }
 
 // ---- vector updates -----------------------------------------------------------
 // CG: P = Z (first) | P = Z + beta P                     ImsLinearBase.f90:118-127
+// Fused split-model path: consumes the rho round (every CTA combines the ranks' records itself) and its last
+// CTA pushes the halo cells of the new P to the neighbours.
 __global__ void __launch_bounds__(kBlock)
-cg_p_kernel(int n, const double *__restrict__ z, double *__restrict__ p, const KState *st,
-            int first) {
+cg_p_kernel(int n, const double *__restrict__ z, double *__restrict__ p, KState *st,
+            int first, SmallGather pull, HaloPush hp) {
+  __shared__ double sc[2];
+  __shared__ bool last;
   if (st->done) return;
-  const double beta = st->beta;
+  double beta = st->beta;
+  if (pull.base) {
+    dist_combine(pull, sc);
+    const double rho = sc[0];
+    beta = rho / st->rho0;  // unused on the first iteration
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      st->rho = rho;
+      st->beta = beta;
+    }
+  }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     p[i] = first ? z[i] : z[i] + beta * p[i];
+  if (hp.peer && last_block(hp.ticket, &last)) halo_push_all(hp, p);
 }
 
 // BCGS: P = D (first) | P = D + beta (P - omega0 V)      ImsLinearBase.f90:346-355
 __global__ void __launch_bounds__(kBlock)
 bcgs_p_kernel(int n, const double *__restrict__ d, const double *__restrict__ v,
-              double *__restrict__ p, const KState *st, int first) {
+              double *__restrict__ p, KState *st, int first, SmallGather pull) {
+  __shared__ double sc[2];
   if (st->done) return;
-  const double beta = st->beta, omega0 = st->omega0;
+  double beta = st->beta;
+  const double omega0 = st->omega0;
+  if (pull.base) {
+    dist_combine(pull, sc);
+    const double rho = sc[0];
+    beta = (rho / st->rho0) * (st->alpha0 / omega0);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      st->rho = rho;
+      st->beta = beta;
+    }
+  }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     p[i] = first ? d[i] : d[i] + beta * (p[i] - omega0 * v[i]);
 }
@@ -310,9 +417,17 @@ bcgs_p_kernel(int n, const double *__restrict__ d, const double *__restrict__ v,
 // BCGS: Q = D - alpha V                                   ImsLinearBase.f90:380-382
 __global__ void __launch_bounds__(kBlock)
 bcgs_q_kernel(int n, const double *__restrict__ d, const double *__restrict__ v,
-              double *__restrict__ q, const KState *st) {
+              double *__restrict__ q, KState *st, SmallGather pull) {
+  __shared__ double sc[2];
   if (st->done) return;
-  const double alpha = st->alpha;
+  double alpha = st->alpha;
+  if (pull.base) {
+    dist_combine(pull, sc);
+    double den = sc[0];
+    den = den + dsign(DBL_EPSILON, den);
+    alpha = st->rho / den;
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->alpha = alpha;
+  }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     q[i] = d[i] - alpha * v[i];
 }
@@ -378,12 +493,29 @@ update_kernel(int n, double *__restrict__ x, double *__restrict__ d,
               const double *__restrict__ qhat, const double *__restrict__ t,
               const double *__restrict__ dscale, const int *__restrict__ ord,
               double *__restrict__ partial, MaxLoc *__restrict__ pmx, MaxLoc *__restrict__ pmr,
-              unsigned int *ticket, KState *st, SummaryPtrs sp) {
+              unsigned int *ticket, KState *st, SummaryPtrs sp, SmallGather pull, DistPush push) {
   __shared__ double sh[8];
   __shared__ MaxLoc shm[8];
   __shared__ bool last;
+  __shared__ RedRec shrec;
   if (st->done) return;
-  const double alpha = st->alpha, omega = st->omega;
+  double alpha = st->alpha, omega = st->omega;
+  if (pull.base) {
+    // fused split-model path: this kernel consumes the round of the SpMV that precedes it
+    dist_combine(pull, sh);
+    if (BCGS) {
+      double den = sh[1];
+      den = den + dsign(DBL_EPSILON, den);
+      omega = sh[0] / den;
+      if (blockIdx.x == 0 && threadIdx.x == 0) st->omega = omega;
+    } else {
+      double den = sh[0];
+      den = den + dsign(DBL_EPSILON, den);
+      alpha = st->rho / den;
+      if (blockIdx.x == 0 && threadIdx.x == 0) st->alpha = alpha;
+    }
+    __syncthreads();
+  }
   const int iscl = st->iscl;
   double ssq = 0.0;
   MaxLoc mx = maxloc_init(), mr = maxloc_init();
@@ -428,13 +560,22 @@ update_kernel(int n, double *__restrict__ x, double *__restrict__ d,
     gx = block_maxloc(gx, shm);
     gr = block_maxloc(gr, shm);
     if (threadIdx.x == 0) {
-      if (st->dist) {
+      if (push.peer) {
+        shrec.s[0] = a;
+        shrec.s[1] = 0.0;
+        shrec.mx = MaxLocPOD{gx.a, gx.v, gx.ord, gx.idx};
+        shrec.mr = MaxLocPOD{gr.a, gr.v, gr.ord, gr.idx};
+      } else if (st->dist) {
         st->red.s[0] = a;
         st->red.mx = MaxLocPOD{gx.a, gx.v, gx.ord, gx.idx};
         st->red.mr = MaxLocPOD{gr.a, gr.v, gr.ord, gr.idx};
       } else {
         finalize_iteration(st, a, gx, gr, BCGS, sp);
       }
+    }
+    if (push.peer) {
+      __syncthreads();
+      dist_push_record(push, reinterpret_cast<const double *>(&shrec));
     }
   }
 }
@@ -445,21 +586,22 @@ enum { FIN_UPDATE = 100 };
 // identical on every rank) and run the same scalar epilogue the single-GPU kernels run inline
 __global__ void global_finalize_kernel(int mode, const RedRec *__restrict__ all_in, int nranks,
                                        KState *st, double *out, int bcgs, SummaryPtrs sp, SmallGather sg) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  const bool krylov = !(mode == FIN_NRM_MAX || mode == FIN_NRM_SSQ);
-  // peer-memory path: the records are read in place from the mailbox once their flags have arrived
-  // (waited for even when the loop is already done, so that every rank consumes every round)
-  RedRec rec[32];
+  // launched with one warp.  Peer-memory path: lane r waits for rank r's flag and copies the record out of
+  // the mailbox (waited for even when the loop is already done, so that every rank consumes every round)
+  __shared__ RedRec rec[32];
   const RedRec *all = all_in;
+  const bool krylov = !(mode == FIN_NRM_MAX || mode == FIN_NRM_SSQ);
+  if (krylov && st->done) return;  // every rank takes the same decision: nobody pushed, nobody waits
   if (sg.base) {
-    for (int r = 0; r < nranks; r++) {
-      const double *src = small_gather_wait(sg, r);
-      double *dst = reinterpret_cast<double *>(&rec[r]);
+    if ((int)threadIdx.x < nranks) {
+      const double *src = small_gather_wait(sg, threadIdx.x);
+      double *dst = reinterpret_cast<double *>(&rec[threadIdx.x]);
       for (int i = 0; i < (int)(sizeof(RedRec) / sizeof(double)); i++) dst[i] = __ldcg(src + i);
     }
+    __syncwarp();
     all = rec;
   }
-  if (krylov && st->done) return;
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double s0 = 0.0, s1 = 0.0;
   MaxLoc mx = maxloc_init(), mr = maxloc_init();
   for (int r = 0; r < nranks; r++) {
@@ -661,7 +803,7 @@ void mf6gpu_solver::reduce_finalize(int mode, double *out, int bcgs) {
   const size_t cnt = sizeof(RedRec) / sizeof(double);
   SmallGather sg = comm_small_push(halo->comm, reinterpret_cast<const double *>(&st.p->red), cnt, stream);
   if (!sg.base) comm_allgather(halo->comm, reinterpret_cast<const double *>(&st.p->red), red_all.p, cnt, stream);
-  global_finalize_kernel<<<1, 1, 0, stream>>>(mode, reinterpret_cast<const RedRec *>(red_all.p),
+  global_finalize_kernel<<<1, 32, 0, stream>>>(mode, reinterpret_cast<const RedRec *>(red_all.p),
                                               halo->comm->nranks, st.p, out, bcgs, sp, sg);
   launches += 2;
 }
@@ -765,68 +907,112 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
     // one inner iteration = a fixed sequence of launches whose arguments never change (the scalars live in
     // KState): small systems are launch-bound on the host, so iterations 2.. replay a CUDA graph of the
     // sequence captured once per solve (not on the split-model path, while profiling, or with NORTH > 0)
+    // Split-model path, two transports.  Fused (peer mailboxes mapped): the partial result of every reduction
+    // is stored into the peers' mailboxes by the last CTA of the kernel that produces it and combined by every
+    // CTA of the kernel that consumes it; the halo of the search direction is pushed by the last CTA of the
+    // kernel that writes it and read in place by the SpMV, whose boundary rows wait while the interior runs.
+    // One extra launch per iteration (the scalar tail of the update).  Fallback (NCCL): pack + send/recv,
+    // all-gather + finalize launch after every reduction.
+    const bool fused = dist && halo->fused() && !std::getenv("MF6GPU_NO_FUSED_EXCHANGE");
+    fused_exchange = fused;
+    auto round = [&]() { return fused ? comm_round(halo->comm) : DistRound{}; };
+    auto finalize_update = [&](const DistRound &r, int bc) {
+      if (fused) {
+        global_finalize_kernel<<<1, 32, 0, S>>>(FIN_UPDATE, nullptr, halo->comm->nranks, st.p, nullptr, bc, sp,
+                                                r.pull);
+        launches += 1;
+      } else {
+        reduce_finalize(FIN_UPDATE, nullptr, bc);
+      }
+    };
+    // halo of `vec` for the SpMV that follows; `carried` = the producer kernel pushes it itself
+    auto halo_round = [&](HaloPush &hp, HaloSrc &hs, const double *vec, bool carried) {
+      hp = HaloPush{};
+      hs = HaloSrc{};
+      if (!dist) return;
+      if (fused) {
+        halo->round(hp, hs);
+        if (!carried) {
+          halo->push_now(hp, vec, S);
+          launches += 1;
+        }
+      } else {
+        halo->exchange(const_cast<double *>(vec), S);
+      }
+    };
     auto enqueue_iteration = [&](int first) {
+      HaloPush hp;
+      HaloSrc hs;
       if (!bcgs) {
+        const DistRound r1 = round();
         prof_begin(PC_ILU);
         if (fuse_dot) {
           // z = M^-1 d with rho = d.z (and beta = rho/rho0) accumulated by the same launches
+          idot.push = r1.push;
           launches += ilu0_apply(*A, lu.p, d.p, z.p, &st.p->done, S, &idot);
-          reduce_finalize(FIN_CG_RHO, nullptr, 0);
+          if (!fused) reduce_finalize(FIN_CG_RHO, nullptr, 0);
           prof_end();
         } else {
           launches += ilu0_apply(*A, lu.p, d.p, z.p, &st.p->done, S);
           prof_end();
           prof_begin(PC_DOT);
           dot_kernel<<<G, kBlock, 0, S>>>(N, d.p, z.p, partial.p, tickets.p + TK_DOT, st.p,
-                                    FIN_CG_RHO, nullptr, 1);
-          reduce_finalize(FIN_CG_RHO, nullptr, 0);
+                                    FIN_CG_RHO, nullptr, 1, r1.push);
+          if (!fused) reduce_finalize(FIN_CG_RHO, nullptr, 0);
           prof_end();
           launches += 1;
         }
         prof_begin(PC_PUPD);
-        cg_p_kernel<<<G, kBlock, 0, S>>>(N, z.p, p.p, st.p, first);
-        if (dist) halo->exchange(p.p, S);
+        if (fused) halo->round(hp, hs); else { hp = HaloPush{}; hs = HaloSrc{}; }
+        cg_p_kernel<<<G, kBlock, 0, S>>>(N, z.p, p.p, st.p, first, r1.pull, hp);
+        if (dist && !fused) halo->exchange(p.p, S);
         prof_end();
+        const DistRound r2 = round();
         prof_begin(PC_SPMV);
         launch_spmv_fused<0, 1>(*A, G, S, p.p, q.p, nullptr, p.p, partial.p, tickets.p + TK_SPMV, st.p,
-                            FIN_CG_ALPHA, 1);
-        reduce_finalize(FIN_CG_ALPHA, nullptr, 0);
+                            FIN_CG_ALPHA, 1, hs, r2.push);
+        if (!fused) reduce_finalize(FIN_CG_ALPHA, nullptr, 0);
         prof_end();
+        const DistRound r3 = round();
         prof_begin(PC_UPD);
         update_kernel<0><<<G, kBlock, 0, S>>>(N, x_dev, d.p, p.p, q.p, nullptr, nullptr, nullptr,
                                         ord, partial.p, pmx.p, pmr.p, tickets.p + TK_UPD,
-                                        st.p, sp);
-        reduce_finalize(FIN_UPDATE, nullptr, 0);
+                                        st.p, sp, r2.pull, r3.push);
+        finalize_update(r3, 0);
         prof_end();
         launches += 3;
       } else {
+        const DistRound r1 = round();
         dot_kernel<<<G, kBlock, 0, S>>>(N, dhat.p, d.p, partial.p, tickets.p + TK_DOT, st.p,
-                                  FIN_BCGS_RHO, nullptr, 1);
-        reduce_finalize(FIN_BCGS_RHO, nullptr, 1);
-        bcgs_p_kernel<<<G, kBlock, 0, S>>>(N, d.p, v.p, p.p, st.p, first);
+                                  FIN_BCGS_RHO, nullptr, 1, r1.push);
+        if (!fused) reduce_finalize(FIN_BCGS_RHO, nullptr, 1);
+        bcgs_p_kernel<<<G, kBlock, 0, S>>>(N, d.p, v.p, p.p, st.p, first, r1.pull);
         prof_begin(PC_ILU);
         launches += ilu0_apply(*A, lu.p, p.p, phat.p, &st.p->done, S);
-        if (dist) halo->exchange(phat.p, S);
+        halo_round(hp, hs, phat.p, false);
         prof_end();
+        const DistRound r2 = round();
         prof_begin(PC_SPMV);
         launch_spmv_fused<0, 1>(*A, G, S, phat.p, v.p, nullptr, dhat.p, partial.p, tickets.p + TK_SPMV,
-                            st.p, FIN_BCGS_ALPHA, 1);
-        reduce_finalize(FIN_BCGS_ALPHA, nullptr, 1);
+                            st.p, FIN_BCGS_ALPHA, 1, hs, r2.push);
+        if (!fused) reduce_finalize(FIN_BCGS_ALPHA, nullptr, 1);
         prof_end();
-        bcgs_q_kernel<<<G, kBlock, 0, S>>>(N, d.p, v.p, q.p, st.p);
+        bcgs_q_kernel<<<G, kBlock, 0, S>>>(N, d.p, v.p, q.p, st.p, r2.pull);
         prof_begin(PC_ILU);
         launches += ilu0_apply(*A, lu.p, q.p, qhat.p, &st.p->done, S);
-        if (dist) halo->exchange(qhat.p, S);
+        halo_round(hp, hs, qhat.p, false);
         prof_end();
+        const DistRound r3 = round();
         prof_begin(PC_SPMV);
         launch_spmv_fused<0, 2>(*A, G, S, qhat.p, t.p, nullptr, q.p, partial.p, tickets.p + TK_SPMV, st.p,
-                            FIN_BCGS_OMEGA, 1);
-        reduce_finalize(FIN_BCGS_OMEGA, nullptr, 1);
+                            FIN_BCGS_OMEGA, 1, hs, r3.push);
+        if (!fused) reduce_finalize(FIN_BCGS_OMEGA, nullptr, 1);
         prof_end();
+        const DistRound r4 = round();
         update_kernel<1><<<G, kBlock, 0, S>>>(N, x_dev, d.p, phat.p, q.p, qhat.p, t.p, dscale.p,
                                         ord, partial.p, pmx.p, pmr.p, tickets.p + TK_UPD,
-                                        st.p, sp);
-        reduce_finalize(FIN_UPDATE, nullptr, 1);
+                                        st.p, sp, r3.pull, r4.push);
+        finalize_update(r4, 1);
         launches += 6;
       }
     };
@@ -1051,6 +1237,7 @@ double mf6gpu_solver_stat(const mf6gpu_solver *s, int what) {
     case 2: return s->t_factor;
     case 3: return s->t_krylov;
     case 4: return (double)s->launches;
+    case 5: return s->fused_exchange ? 1.0 : 0.0;
   }
   return -1.0;
 }

@@ -64,6 +64,7 @@ struct mf6gpu_solver {
   int npivfix = 0;
   double t_factor = 0.0, t_krylov = 0.0;
   long long launches = 0;
+  bool fused_exchange = false;  // last solve used the fused peer-memory exchange (split-model path)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaStream_t cap_stream = nullptr;     // capture-only stream of the inner-iteration graph (the work stream is the legacy default stream, which cannot capture)
   // optional per-kernel-class timing with CUDA events on the launching stream

@@ -415,6 +415,9 @@ class GpuDistributedSolution:
     def stat(self, what):
         return self._L.mf6gpu_solution_stat(self.h, what)
 
+    def solver_stat(self, what):
+        return self._L.mf6gpu_solver_stat(self._L.mf6gpu_solution_solver(self.h), what)
+
     def profile(self, enable=True):
         check(self._L.mf6gpu_solver_profile(self._L.mf6gpu_solution_solver(self.h), 1 if enable else 0))
 

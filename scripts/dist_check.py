@@ -27,7 +27,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     spec = GridSpec(nlay=nlay, nrow=nrow, ncol=ncol, seed=11)
     sub = build_dis_block(spec, pr, pc, rank)
-    ims = T.ImsSettings.make(dvclose=1e-8, rclose=1e-5, iter1=400, ilinmeth=meth, relax=0.0, gpu_ordering=ordering)
+    ims = T.ImsSettings.make(dvclose=1e-9, rclose=1e-6, iter1=600, ilinmeth=meth, relax=0.0, gpu_ordering=ordering)
     sln = T.SlnSettings.make(dvclose=1e-7, mxiter=30)
     comm = GpuComm(rank, world)
     G = GpuDistributedSolution(sub, sln, ims, comm)
@@ -48,7 +48,7 @@ def main():
         for r in range(world):
             s = build_dis_block(spec, pr, pc, r)
             blocks[s.global_id[:s.n_own]] = r
-        o_ims = T.ImsSettings.make(dvclose=1e-8, rclose=1e-5, iter1=400, ilinmeth=meth, relax=0.0)
+        o_ims = T.ImsSettings.make(dvclose=1e-9, rclose=1e-6, iter1=600, ilinmeth=meth, relax=0.0)
         O = OracleSolution(g.model, sln, o_ims, blocks=blocks if ordering == 0 else None)
         O.set_packages(pk)
         ro = O.timestep(1, 1, 1.0, 1)
@@ -58,10 +58,10 @@ def main():
               f"oracle(block-Jacobi) {ro.outer_iterations}/{ro.inner_iterations} cv {ro.converged} | max|dh| {dh:.3e} | "
               f"budget in {rep.totrin:.6e}/{ro.totrin:.6e} pdiff {rep.pdiffr:.3e}/{ro.pdiffr:.3e} "
               f"maxdv loc {rep.max_dv_loc}/{ro.max_dv_loc}", flush=True)
-        tol = (0.5 if meth == 1 else 5.0) * sln.dvclose   # BiCGSTAB amplifies reduction-order rounding
+        tol = 0.1 * sln.dvclose   # north_star bar; the inner closure sits two decades below OUTER_DVCLOSE
         ok = rep.converged == 1 and dh <= tol and abs(rep.pdiffr - ro.pdiffr) < 1e-3
         if ordering == 0 and meth == 1:
-            ok = ok and rep.outer_iterations == ro.outer_iterations and abs(rep.inner_iterations - ro.inner_iterations) <= 2
+            ok = ok and rep.outer_iterations == ro.outer_iterations and abs(rep.inner_iterations - ro.inner_iterations) <= 3
         print("DIST_CHECK", "PASS" if ok else "FAIL", flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)

@@ -107,14 +107,16 @@ def test_pivot_rescue_loop(gpu, factor, relax, expected):
 @pytest.mark.parametrize("meth,relax,north", [(1, 0.0, 0), (1, 0.97, 0), (2, 0.0, 0), (2, 0.97, 2), (1, 0.0, 5)])
 def test_krylov_matches_oracle(system, ordering, meth, relax, north):
     """ims_base_cg / ims_base_bcgs: same stopping rules, same iteration path.
-    Tolerance: CG within 0.5 x INNER_DVCLOSE of the oracle with equal iteration counts (the reductions differ
-    only in rounding).  BiCGSTAB amplifies that rounding (its two runs may stop a few iterations apart), so it
-    is held to 10 x INNER_DVCLOSE; both must sit within 20 x INNER_DVCLOSE of a tightly converged solve."""
+    Tolerance (north_star): max |dx| <= 0.1 x DV, where DV = 1e-7 plays the OUTER_DVCLOSE these inner settings
+    would serve; the inner closure sits two decades below it (INNER_DVCLOSE = 0.01 x DV, the usual practice), so
+    that the only difference between the two runs -- the rounding of the parallel reductions, which BiCGSTAB
+    amplifies until its two runs stop a few iterations apart -- stays far below the bound."""
     from modflow6_b200.linear import GpuLinearSolver, GpuMatrix
     from oracle.oracle import OracleIms
     m, a, b, x0 = system
-    dvclose = 1e-7
-    ims = T.ImsSettings.make(dvclose=dvclose, rclose=1e-5, iter1=600, ilinmeth=meth, relax=relax, north=north,
+    DV = 1e-7
+    dvclose = 0.01 * DV
+    ims = T.ImsSettings.make(dvclose=dvclose, rclose=1e-7, iter1=600, ilinmeth=meth, relax=relax, north=north,
                              gpu_ordering=ordering)
     A = GpuMatrix(m.ia, m.ja, 0, ordering)
     A.update(a)
@@ -129,12 +131,11 @@ def test_krylov_matches_oracle(system, ordering, meth, relax, north):
     tight = T.ImsSettings.make(dvclose=1e-12, rclose=1e-9, iter1=2000, ilinmeth=1, relax=0.0)
     xt = x0.copy()
     assert OracleIms(m.ia, m.ja, tight).solve(a, xt, b)[1] == 1
-    assert np.abs(xg - xt).max() <= 20 * dvclose and np.abs(xo - xt).max() <= 20 * dvclose
+    assert np.abs(xg - xt).max() <= 0.1 * DV and np.abs(xo - xt).max() <= 0.1 * DV
+    assert np.abs(xg - xo).max() <= 0.1 * DV
     if meth == 1:
-        assert np.abs(xg - xo).max() <= 0.5 * dvclose
         assert abs(it - ito) <= 1
     else:
-        assert np.abs(xg - xo).max() <= 10 * dvclose
         assert abs(it - ito) <= max(4, ito // 10)
     # ConvergenceSummary side channel: first iterations agree in value and location
     sg, so = S.convergence_summary(), O.summary()
