@@ -5,6 +5,7 @@ no GPU is needed to make these).
     python tests/golden/make_golden_full.py c2 block      # 10 x 1000 x 1000, ~20 min on one core
     python tests/golden/make_golden_full.py c2 natural    # the reference's own ordering (iteration counts)
     python tests/golden/make_golden_full.py c3 block 1    # 5 x 2000 x 2000 Newton, first time step only
+    python tests/golden/make_golden_full.py c2 natural --tight   # inner closure x 0.1 / x 0.01 (cross-ordering parity)
 
 Writes
   tests/golden/<cfg>_full_<ordering>.npz   (committed, small): every STRIDE-th head, sums of heads over blocks of
@@ -41,10 +42,12 @@ def summarize(heads):
 
 
 def main():
-    which = sys.argv[1]
-    ordering = sys.argv[2]
-    max_steps = int(sys.argv[3]) if len(sys.argv) > 3 else None
-    size = tuple(int(v) for v in sys.argv[4].split(",")) if len(sys.argv) > 4 else None
+    tight = "--tight" in sys.argv      # INNER_DVCLOSE x 0.1, INNER_RCLOSE x 0.01: closure slack out of the comparison
+    argv = [a for a in sys.argv if a != "--tight"]
+    which = argv[1]
+    ordering = argv[2]
+    max_steps = int(argv[3]) if len(argv) > 3 and argv[3] != "-" else None
+    size = tuple(int(v) for v in argv[4].split(",")) if len(argv) > 4 else None
     o = {"block": T.ORDER_BLOCK_MULTICOLOR, "natural": T.ORDER_NATURAL, "multicolor": T.ORDER_MULTICOLOR}[ordering]
     if which == "c2":
         cfg = configs.c2_confined(*(size or (10, 1000, 1000)), gpu_ordering=o)
@@ -52,6 +55,10 @@ def main():
         cfg = configs.c3_newton(*(size or (5, 2000, 2000)), gpu_ordering=o)
     else:
         raise SystemExit("config must be c2 or c3")
+    if tight:
+        cfg.ims.dvclose *= 0.1
+        cfg.ims.rclose *= 0.01
+        cfg.ims.iter1 = max(cfg.ims.iter1, 1000)
     perm = None if o == T.ORDER_NATURAL else lib.model_elimination_order(cfg.model, o)
     t0 = time.perf_counter()
     O = OracleSolution(cfg.model, cfg.sln, cfg.ims, perm=perm)
@@ -59,11 +66,14 @@ def main():
     wall = time.perf_counter() - t0
     heads = np.array(O.x, copy=True)
     tag = f"{which}_full_{ordering}" if size is None else f"{which}_{'x'.join(map(str, size))}_{ordering}"
+    if tight:
+        tag += "_tight"
     os.makedirs(os.path.join(HERE, "_big"), exist_ok=True)
     np.save(os.path.join(HERE, "_big", tag + "_heads.npy"), heads)
     s = summarize(heads)
     meta = {"config": cfg.name, "ordering": ordering, "cells": int(cfg.model.nodes), "nja": int(cfg.model.nja),
-            "stride": STRIDE, "block": BLOCK, "sha256": s["sha256"], "oracle_wall_s": wall, "steps": reps,
+            "stride": STRIDE, "block": BLOCK, "inner_dvclose": cfg.ims.dvclose, "inner_rclose": cfg.ims.rclose,
+            "inner_maximum": cfg.ims.iter1, "outer_dvclose": cfg.sln.dvclose, "sha256": s["sha256"], "oracle_wall_s": wall, "steps": reps,
             "made_by": "tests/golden/make_golden_full.py " + " ".join(sys.argv[1:])}
     np.savez_compressed(os.path.join(HERE, tag + ".npz"), sample=s["sample"], block_sums=s["block_sums"],
                         meta=np.array(json.dumps(meta)))

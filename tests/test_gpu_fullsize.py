@@ -1,0 +1,66 @@
+"""Parity at the FULL size of the BASELINE configs: the device solve against the committed oracle fixtures
+(tests/golden/*_full_*.npz, made on the CPU by tests/golden/make_golden_full.py with the elimination order the
+device uses).  north_star bar: max |dhead| <= 0.1 x OUTER_DVCLOSE, budget percent discrepancy within 1e-3."""
+import numpy as np
+import pytest
+
+from modflow6_b200 import configs, ctypes_types as T, lib
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(cfg, max_steps=None):
+    from modflow6_b200.solution import GpuNumericalSolution
+    G = GpuNumericalSolution(cfg.model, cfg.sln, cfg.ims)
+    assert np.array_equal(G.elimination_order(), lib.model_elimination_order(cfg.model, cfg.ims.gpu_ordering))
+    reps = configs.run_simulation(G, cfg, max_steps=max_steps)
+    x = G.x
+    G.destroy()
+    return reps, x
+
+
+def test_c2_full_size_against_oracle_fixture(gpu):
+    """BASELINE config 2 (10 x 1000 x 1000, CG + ILU0, block ordering): 1e7 heads against the oracle's"""
+    from oracle import golden
+    if golden.load("c2_full_block") is None:
+        pytest.skip("fixture missing")
+    cfg = configs.c2_confined()
+    reps, x = _run(cfg)
+    c = golden.compare_heads("c2_full_block", x, cfg.sln.dvclose)
+    assert reps[0]["converged"] == 1
+    assert c["max_abs_dhead"] <= 0.1 * cfg.sln.dvclose, c
+    if "max_abs_dblocksum" in c:
+        assert c["max_abs_dblocksum"] <= 1000 * 0.1 * cfg.sln.dvclose
+    assert abs(reps[0]["pdiffr"] - c["oracle"]["pdiffr"]) <= 1e-3
+    assert reps[0]["outer_iterations"] == c["oracle"]["outer_iterations"]
+    assert abs(reps[0]["inner_iterations"] - c["oracle"]["inner_iterations"]) <= c["oracle"]["inner_iterations"] // 20
+
+
+def test_c2_full_size_cross_ordering_tight_closure(gpu):
+    """with the closure slack taken out (inner closure x 0.1 / x 0.01) the device's block ordering agrees with the
+    reference's NATURAL ordering as well: the orderings differ in convergence path, not in the answer"""
+    from oracle import golden
+    if golden.load("c2_full_natural_tight") is None:
+        pytest.skip("fixture missing")
+    cfg = configs.c2_confined()
+    cfg.ims.dvclose *= 0.1
+    cfg.ims.rclose *= 0.01
+    cfg.ims.iter1 = 1000
+    reps, x = _run(cfg)
+    c = golden.compare_heads("c2_full_natural_tight", x, cfg.sln.dvclose)
+    assert reps[0]["converged"] == 1
+    assert c["max_abs_dhead"] <= 0.1 * cfg.sln.dvclose, c
+    assert abs(reps[0]["pdiffr"] - c["oracle"]["pdiffr"]) <= 1e-3
+
+
+def test_c3_full_size_first_step_against_oracle_fixture(gpu):
+    """BASELINE config 3 (5 x 2000 x 2000 Newton + STO, BiCGSTAB, DBD): the steady first step, 2e7 heads"""
+    from oracle import golden
+    if golden.load("c3_full_block") is None:
+        pytest.skip("fixture missing")
+    cfg = configs.c3_newton()
+    reps, x = _run(cfg, max_steps=1)
+    c = golden.compare_heads("c3_full_block", x, cfg.sln.dvclose)
+    assert reps[0]["converged"] == 1
+    assert c["max_abs_dhead"] <= 0.1 * cfg.sln.dvclose, c
+    assert abs(reps[0]["pdiffr"] - c["oracle"]["pdiffr"]) <= 1e-3
