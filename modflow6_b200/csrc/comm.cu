@@ -81,9 +81,9 @@ __device__ __forceinline__ unsigned long long ld_flag(const unsigned long long *
 }
 // spin until *flag >= seq; gives up (and raises *err) after ~2^27 polls so a dead peer cannot hang the GPU
 __device__ __forceinline__ bool wait_flag(const unsigned long long *flag, unsigned long long seq, int *err) {
-  for (unsigned int spin = 0; spin < (1u << 27); spin++) {
+  for (unsigned int spin = 0; spin < (1u << 23); spin++) {
     if (ld_flag(flag) >= seq) return true;
-    __nanosleep(20);
+    __nanosleep(spin < 4096 ? 20 : 1000);
   }
   *err = 1;
   return false;
@@ -211,9 +211,12 @@ DistRound comm_round(mf6gpu_comm *c) {
   return R;
 }
 
-// stand-alone producer of a fused halo round (the same device code the fused producers run in their last CTA)
+// stand-alone producer of a fused halo round (producers that cannot carry the push themselves): a few CTAs
+// push, the last one to finish publishes the flags
 __global__ void __launch_bounds__(kBlock) halo_push_kernel(HaloPush P, const double *__restrict__ vec) {
+  __shared__ bool last;
   halo_push_all(P, vec);
+  if (last_block_all(P.ticket, &last)) halo_publish(P);
 }
 
 void HaloPlan::round(HaloPush &push, HaloSrc &src) {
@@ -222,7 +225,7 @@ void HaloPlan::round(HaloPush &push, HaloSrc &src) {
   const int parity = (int)(seq & 1ull);
   const P2PLayout &L = comm->lay;
   push = HaloPush{comm->d_peer.p, nnbr, d_nbr_rank.p, d_send_ptr.p, send_idx.p, L.halo_off(parity, comm->rank),
-                  (int)L.halo_doubles, seq, ticket.p};
+                  (int)L.halo_doubles, seq, ticket.p, own_grid, cta_ptr.p, cta_ent.p};
   src = HaloSrc{};
   src.nnbr = nnbr;
   src.n_own = n_own;
@@ -236,7 +239,8 @@ void HaloPlan::round(HaloPush &push, HaloSrc &src) {
 }
 
 void HaloPlan::push_now(const HaloPush &push, const double *vec, cudaStream_t s) {
-  halo_push_kernel<<<1, kBlock, 0, s>>>(push, vec);
+  const int g = std::max(1, std::min(64, (send_ptr.back() + kBlock - 1) / kBlock));
+  halo_push_kernel<<<g, kBlock, 0, s>>>(push, vec);
 }
 
 SmallGather comm_small_push(mf6gpu_comm *c, const double *in, size_t count, cudaStream_t s) {

@@ -87,6 +87,11 @@ struct HaloPush {
   int cap;
   unsigned long long seq;
   unsigned int *ticket;
+  // send entries grouped by the CTA that computes their source row in a `grid`-CTA grid-stride kernel of kBlock
+  // threads (row r belongs to CTA (r / kBlock) % grid): every CTA pushes its own entries, the last one to
+  // finish publishes the flags.  grid == 0: no grouping, the last CTA pushes everything.
+  int grid;
+  const int *cta_ptr, *cta_ent;
 };
 struct HaloSrc {
   int nnbr;                  // 0 = halo columns live behind the owned entries of the vector (legacy layout)
@@ -109,6 +114,8 @@ struct HaloPlan {
   DevBuf<unsigned int> ticket;
   DevBuf<double> sendbuf;
   DevBuf<unsigned char> slice_halo;               // [nslices] slices with halo columns (fused SpMV)
+  int own_grid = 0;                               // grid the ownership lists below were built for
+  DevBuf<int> cta_ptr, cta_ent;                   // send entries grouped by owning CTA (see HaloPush)
   bool active() const { return comm != nullptr && comm->nranks > 1; }
   // fused peer-memory path available (mailboxes mapped, few enough neighbours)?
   bool fused() const {
@@ -131,11 +138,12 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-// spin until *flag >= seq; gives up (and raises *err) after ~2^27 polls so a dead peer cannot hang the GPU
+// spin until *flag >= seq; gives up (and raises *err) after ~10 s so that a dead or out-of-step peer cannot
+// hang the GPU (legitimate waits are microseconds, host-side launch skew between ranks milliseconds)
 __device__ __forceinline__ bool wait_seq(const unsigned long long *flag, unsigned long long seq, int *err) {
-  for (unsigned int spin = 0; spin < (1u << 27); spin++) {
+  for (unsigned int spin = 0; spin < (1u << 23); spin++) {
     if (ld_acquire_sys_u64(flag) >= seq) return true;
-    __nanosleep(20);
+    __nanosleep(spin < 4096 ? 20 : 1000);
   }
   *err = 1;
   return false;
@@ -173,22 +181,56 @@ __device__ __forceinline__ void halo_wait(const HaloSrc &H) {
     wait_seq(reinterpret_cast<const unsigned long long *>(H.msg[threadIdx.x] + H.cap), H.seq, H.err);
   __syncthreads();
 }
-// last CTA of the producing kernel (all its threads; the vector is complete and fenced): push the send cells
-__device__ __forceinline__ void halo_push_all(const HaloPush &P, const double *vec) {
-  const int total = P.send_ptr[P.nnbr];
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    int k = 0;
-    while (i >= P.send_ptr[k + 1]) k++;
-    double *dst = reinterpret_cast<double *>(P.peer[P.nbr_rank[k]] + P.off);
-    dst[i - P.send_ptr[k]] = __ldcg(vec + P.send_idx[i]);
-  }
+// "last CTA done" for kernels in which EVERY thread has made stores that the last CTA (or a peer GPU) must
+// see: fence by every thread, barrier, then the ticket.  Returns true in all threads of the last CTA.
+__device__ __forceinline__ bool last_block_all(unsigned int *counter, bool *sh_flag) {
   __threadfence_system();
   __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicInc(counter, gridDim.x - 1);
+    *sh_flag = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  const bool f = *sh_flag;
+  if (f) __threadfence_system();
+  return f;
+}
+__device__ __forceinline__ void halo_push_entry(const HaloPush &P, const double *vec, int i) {
+  int k = 0;
+  while (i >= P.send_ptr[k + 1]) k++;
+  double *dst = reinterpret_cast<double *>(P.peer[P.nbr_rank[k]] + P.off);
+  dst[i - P.send_ptr[k]] = __ldcg(vec + P.send_idx[i]);
+}
+__device__ __forceinline__ void halo_publish(const HaloPush &P) {
   if (threadIdx.x < P.nnbr) {
-    __threadfence_system();
     double *dst = reinterpret_cast<double *>(P.peer[P.nbr_rank[threadIdx.x]] + P.off);
     st_release_sys_u64(reinterpret_cast<unsigned long long *>(dst + P.cap), P.seq);
   }
+}
+// Tail of a kernel that has just written `vec` (every thread of every CTA calls it, after its last store to vec):
+// each CTA pushes the send cells whose rows it computed itself, the last CTA to finish publishes the flags.
+__device__ __forceinline__ void halo_push_tail(const HaloPush &P, const double *vec, bool *sh_flag) {
+  const bool owned = (P.grid == (int)gridDim.x);
+  if (owned) {
+    __syncthreads();  // the CTA's own stores to vec are visible to all its threads
+    for (int e = P.cta_ptr[blockIdx.x] + threadIdx.x; e < P.cta_ptr[blockIdx.x + 1]; e += blockDim.x)
+      halo_push_entry(P, vec, P.cta_ent[e]);
+  }
+  if (last_block_all(P.ticket, sh_flag)) {
+    if (!owned) {
+      const int total = P.send_ptr[P.nnbr];
+      for (int i = threadIdx.x; i < total; i += blockDim.x) halo_push_entry(P, vec, i);
+      __threadfence_system();
+      __syncthreads();
+    }
+    halo_publish(P);
+  }
+}
+// stand-alone producer: one CTA pushes everything (vec complete before the launch)
+__device__ __forceinline__ void halo_push_all(const HaloPush &P, const double *vec) {
+  const int total = P.send_ptr[P.nnbr];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+    halo_push_entry(P, vec, i);
 }
 #endif
 

@@ -79,6 +79,37 @@ __device__ __forceinline__ double sQSaturationDerivative(double top, double bot,
   return 0.0;
 }
 
+// the same two functions with explicit c1 / c2 (DRN passes -1, 2: gwf-drn.f90:563, 451-452)
+__device__ __forceinline__ double sQSaturationC(double top, double bot, double x, double c1, double c2) {
+  const double w = x - bot, b = top - bot, s = w / b;
+  const double cof1 = c1 / (b * b * b), cof2 = c2 / (b * b);
+  if (s < 0.0) return 0.0;
+  if (s < 1.0) return cof1 * (w * w * w) + cof2 * (w * w);
+  return 1.0;
+}
+
+__device__ __forceinline__ double sQSaturationDerivativeC(double top, double bot, double x, double c1,
+                                                          double c2) {
+  const double w = x - bot, b = top - bot, s = w / b;
+  const double cof1 = c1 * 3.0 / (b * b * b), cof2 = c2 * 2.0 / (b * b);
+  if (s < 0.0) return 0.0;
+  if (s < 1.0) return cof1 * (w * w) + cof2 * w;
+  return 0.0;
+}
+
+// get_drain_elevations (gwf-drn.f90:501-530): elev = b1, drndepth = the DDRN auxiliary value (0 = none)
+__device__ __forceinline__ void drain_elevations(double drnelev, double drndepth, double &drntop,
+                                                 double &drnbot) {
+  if (drndepth != 0.0) {
+    const double elev = drnelev + drndepth;
+    drntop = fmax(elev, drnelev);
+    drnbot = fmin(elev, drnelev);
+  } else {
+    drntop = drnelev;
+    drnbot = drnelev;
+  }
+}
+
 __device__ __forceinline__ double logmean(double d1, double d2) {
   const double drat = d2 / d1;
   if (drat <= 0.995 || drat >= 1.005) return (d2 - d1) / log(drat);

@@ -88,7 +88,7 @@ struct IluDot {
 // per-warp partial of rho: no block-level barrier, so CTAs retire as soon as their rows are done
 __device__ __forceinline__ void ilu_dot_finish(double s, const IluDot &D) {
   s = warp_sum(s);
-  if ((threadIdx.x & 31) == 0) D.partial[blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5)] = s;
+  if ((threadIdx.x & 31) == 0) D.partial[(blockIdx.x * blockDim.x + threadIdx.x) >> 5] = s;
 }
 
 // rho = sum of the per-warp partials of every finalising launch: fixed chunking and order
@@ -560,6 +560,18 @@ static inline int chain_chunk(int mode, int maxk) {
 }
 static inline bool chain_fits_one_chunk(int mode, int maxk) { return maxk <= chain_chunk(mode, maxk); }
 
+// CTA size of the chain kernels.  They hold a whole column's operands in registers (25 % occupancy), and all warps of
+// a CTA move through load -> recurrence -> store in step; small CTAs stagger those phases across the SM and shrink
+// the last partial wave (MF6GPU_CHAIN_BLOCK overrides for tuning)
+static int chain_block() {
+  static int v = [] {
+    const char *e = std::getenv("MF6GPU_CHAIN_BLOCK");
+    const int c = e ? std::atoi(e) : 0;
+    return (c == 32 || c == 64 || c == 128 || c == 256) ? c : 64;
+  }();
+  return v;
+}
+
 struct ChainArgs {
   int g, nb, maxk, W;
   const int *brow;
@@ -579,7 +591,7 @@ static void launch_chain_kc(const ChainArgs &a, int addr, bool from_rin) {
   constexpr int cap = (MODE == 0) ? 16 : (MODE == 1 ? 12 : 10);
   if constexpr (KC <= cap) {
     auto go = [&](auto addr_c, auto rin_c) {
-      ilu0_blk_chain_kernel<MODE, KC, decltype(addr_c)::value, decltype(rin_c)::value><<<a.g, kBlock, 0, a.s>>>(
+      ilu0_blk_chain_kernel<MODE, KC, decltype(addr_c)::value, decltype(rin_c)::value><<<a.g, chain_block(), 0, a.s>>>(
           a.nb, a.maxk, a.W, 0, a.brow, a.bch, a.kb, a.kbv, a.nlow, a.lu, a.rin, a.d, a.done, a.D);
     };
     auto with_addr = [&](auto rin_c) {
@@ -603,7 +615,7 @@ static void launch_chain(const mf6gpu_matrix &A, int c, bool from_rin, const dou
   ChainArgs a{};
   a.nb = A.blk_nb[c];
   a.maxk = A.blk_maxk[c];
-  a.g = (a.nb + kBlock - 1) / kBlock;
+  a.g = (a.nb + chain_block() - 1) / chain_block();
   a.W = A.uniform_w;
   a.brow = A.blk_rows.p + A.blk_off[c];
   a.bch = A.blk_chain.p + A.blk_off[c];

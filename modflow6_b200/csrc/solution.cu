@@ -147,7 +147,7 @@ struct BndView {
 };
 
 // *_cf of WEL/RIV/RCH/GHB/DRN (gwf-wel.f90:296-332, gwf-riv.f90:270-299, gwf-rch.f90:303-353,
-// gwf-ghb.f90:245-265, gwf-drn.f90:340-373 with drndepth = 0); CHD has no cf terms
+// gwf-ghb.f90:245-265, gwf-drn.f90:340-373 incl. the drainage-depth scaling); CHD has no cf terms
 __global__ void bnd_cf_kernel(BndView B, ModelView M, const double *__restrict__ x) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B.nb; i += gridDim.x * blockDim.x) {
     const int node = B.node[i];
@@ -203,9 +203,20 @@ __global__ void bnd_cf_kernel(BndView B, ModelView M, const double *__restrict__
         }
         break;
       case MF6GPU_PKG_DRN:
+        // drn_cf + get_drain_factor (gwf-drn.f90:340-373, 534-574): b3 = drainage depth (DDRN auxiliary), flag =
+        // DEV_CUBIC_SCALING
         if (ib > 0) {
-          const double cdrn = B.b2[i], drnbot = B.b1[i];
-          const double fact = (x[node] <= drnbot) ? 0.0 : 1.0;
+          const double cdrn = B.b2[i], drndepth = B.b3[i];
+          double drntop, drnbot, fact;
+          drain_elevations(B.b1[i], drndepth, drntop, drnbot);
+          if (drndepth != 0.0) {
+            if (B.flag[i] != 0)
+              fact = sQSaturationC(drntop, drnbot, x[node], -1.0, 2.0);
+            else
+              fact = sQuadraticSaturation(drntop, drnbot, x[node], 0.0);
+          } else {
+            fact = (x[node] <= drnbot) ? 0.0 : 1.0;
+          }
           rhs = -fact * cdrn * drnbot;
           hcof = -fact * cdrn;
         }
@@ -222,7 +233,7 @@ __global__ void bnd_cf_kernel(BndView B, ModelView M, const double *__restrict__
 // bnd_fc / bnd_fn / bnd_cq scatter: one thread per DISTINCT node walks that
 // node's bounds in (package, bound) order -> same accumulation order as the
 // reference's package loop, no atomics.
-// mode 0: bnd_fc (BoundaryPackage.f90:453-472) ; 1: wel_fn (gwf-wel.f90:378-424) ;
+// mode 0: bnd_fc (BoundaryPackage.f90:453-472) ; 1: wel_fn (gwf-wel.f90:378-424) + drn_fn (gwf-drn.f90:420-470) ;
 // mode 2: bnd_cq_simrate (:583-619)
 __global__ void bnd_scatter_kernel(int nseg, const int *__restrict__ seg_node,
                                    const int *__restrict__ seg_ptr, const int *__restrict__ seg_idx,
@@ -249,6 +260,18 @@ __global__ void bnd_scatter_kernel(int nseg, const int *__restrict__ seg_node,
       double diag = val[dslot], r = rhsv[node];
       for (int e = seg_ptr[sidx]; e < seg_ptr[sidx + 1]; e++) {
         const int i = seg_idx[e];
+        if (B.type[i] == MF6GPU_PKG_DRN) {  // drn_fn (gwf-drn.f90:420-470)
+          const double drndepth = B.b3[i];
+          if (drndepth != 0.0) {
+            double drntop, drnbot;
+            drain_elevations(B.b1[i], drndepth, drntop, drnbot);
+            double drterm = sQSaturationDerivativeC(drntop, drnbot, x[node], -1.0, 2.0);
+            drterm = drterm * B.b2[i] * (drnbot - x[node]);
+            diag = diag + drterm;
+            r = r + drterm * x[node];
+          }
+          continue;
+        }
         if (B.type[i] != MF6GPU_PKG_WEL) continue;
         if (B.flag[i] != 0 && M.icelltype[node] != 0) {
           const double q = -B.rhs[i];
@@ -1356,6 +1379,19 @@ static void create_solution(const mf6gpu_gwf_model *m, const mf6gpu_sln_settings
                 break;
               }
           H.slice_halo.upload(sh);
+          // send entries grouped by the CTA that computes their row in the vector-update kernels
+          const int G = grid_for(n_own);
+          std::vector<int> ent(sidx.size()), cp((size_t)G + 1, 0);
+          const int nsend = H.send_ptr.back();
+          for (int i = 0; i < nsend; i++) cp[(size_t)((sidx[i] / kBlock) % G) + 1]++;
+          for (int b = 0; b < G; b++) cp[b + 1] += cp[b];
+          {
+            std::vector<int> cur(cp.begin(), cp.end() - 1);
+            for (int i = 0; i < nsend; i++) ent[(size_t)cur[(sidx[i] / kBlock) % G]++] = i;
+          }
+          H.cta_ptr.upload(cp);
+          H.cta_ent.upload(ent);
+          H.own_grid = G;
         }
         s->S->halo = &s->halo;
         s->os_all.alloc_zero(sizeof(OuterState) / sizeof(double) * (size_t)da->comm->nranks);

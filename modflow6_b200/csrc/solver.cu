@@ -129,7 +129,11 @@ __device__ __forceinline__ void reduce_partials_and_finalize(int mode, const dou
   a0 = block_sum(a0, sh);
   if (NS == 2) a1 = block_sum(a1, sh);
   if (push.peer) {
-    if (threadIdx.x < 8) sh[threadIdx.x] = (threadIdx.x == 0) ? a0 : (threadIdx.x == 1 ? a1 : 0.0);
+    if (threadIdx.x == 0) {  // block_sum leaves its result in thread 0 only
+      sh[0] = a0;
+      sh[1] = a1;
+      for (int i = 2; i < 8; i++) sh[i] = 0.0;
+    }
     __syncthreads();
     dist_push_record(push, sh);
     return;
@@ -244,6 +248,27 @@ __device__ __forceinline__ double sell_row_dot_halo(int row, long long base, int
   return t;
 }
 
+// fixed-width layout: all loads of the row issued up front like sell_row_dot_w
+template <int W>
+__device__ __forceinline__ double sell_row_dot_w_halo(int row, const int *__restrict__ col,
+                                                      const double *__restrict__ val, const double *__restrict__ x,
+                                                      const HaloSrc &H) {
+  const long long base = (long long)(row >> 5) * (32 * W) + (row & 31);
+  double v[W], xv[W];
+  int c[W];
+#pragma unroll
+  for (int u = 0; u < W; u++) {
+    v[u] = __ldg(val + base + 32 * u);
+    c[u] = __ldg(col + base + 32 * u);
+  }
+#pragma unroll
+  for (int u = 0; u < W; u++) xv[u] = (c[u] < H.n_own) ? x[c[u]] : halo_load(H, c[u]);
+  double t = 0.0;
+#pragma unroll
+  for (int u = 0; u < W; u++) t = t + v[u] * xv[u];
+  return t;
+}
+
 template <int EPI, int NDOT>
 __global__ void __launch_bounds__(kBlock)
 spmv_fused_kernel(int n, const int *__restrict__ slice_ptr,
@@ -320,7 +345,7 @@ spmv_fused_w_kernel(int n, int ncols, const int *__restrict__ col, const int *__
     halo_wait(H);
     for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
       if (!H.slice_halo[row >> 5]) continue;
-      double t = sell_row_dot_halo(row, (long long)(row >> 5) * (32 * W) + (row & 31), W, col, val, x, H);
+      double t = sell_row_dot_w_halo<W>(row, col, val, x, H);
       if (EPI == 1) t = b[row] - t;
       y[row] = t;
       if (NDOT >= 1) s0 += w[row] * t;
@@ -390,7 +415,7 @@ cg_p_kernel(int n, const double *__restrict__ z, double *__restrict__ p, KState 
   }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     p[i] = first ? z[i] : z[i] + beta * p[i];
-  if (hp.peer && last_block(hp.ticket, &last)) halo_push_all(hp, p);
+  if (hp.peer) halo_push_tail(hp, p, &last);
 }
 
 // BCGS: P = D (first) | P = D + beta (P - omega0 V)      ImsLinearBase.f90:346-355
@@ -486,7 +511,8 @@ __device__ void finalize_iteration(KState *st, double ssq, MaxLoc mx, MaxLoc mr,
 
 // CG: X += alpha P ; D -= alpha Q ; max|alpha P|, max|D|, sum D^2   :137-183
 // BCGS: X += alpha PHAT + omega QHAT ; D = Q - omega T ; same reductions :429-480
-template <int BCGS>
+// VEC2: 128-bit loads / stores (two rows per access; needs 16-byte aligned vectors), two accesses in flight
+template <int BCGS, int VEC2>
 __global__ void __launch_bounds__(kBlock)
 update_kernel(int n, double *__restrict__ x, double *__restrict__ d,
               const double *__restrict__ p, const double *__restrict__ q,
@@ -519,26 +545,85 @@ update_kernel(int n, double *__restrict__ x, double *__restrict__ d,
   const int iscl = st->iscl;
   double ssq = 0.0;
   MaxLoc mx = maxloc_init(), mr = maxloc_init();
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  // one row: the reference's update of X and D plus the three reductions, in the reference's operation order
+  auto row = [&](int i, double xi, double di, double pi, double qi, double qh, double ti, double sc,
+                 double &xo, double &dout) {
     double tv, rv;
     if (BCGS) {
-      tv = alpha * p[i] + omega * qhat[i];  // p = PHAT here
-      x[i] = x[i] + tv;
-      if (iscl != 0) tv = tv * dscale[i];
-      rv = q[i] - omega * t[i];
-      d[i] = rv;
-      if (iscl != 0) rv = rv / dscale[i];
+      tv = alpha * pi + omega * qh;  // p = PHAT here
+      xo = xi + tv;
+      if (iscl != 0) tv = tv * sc;
+      rv = qi - omega * ti;
+      dout = rv;
+      if (iscl != 0) rv = rv / sc;
     } else {
-      tv = alpha * p[i];
-      x[i] = x[i] + tv;
-      rv = d[i];
-      rv = rv - alpha * q[i];
-      d[i] = rv;
+      tv = alpha * pi;
+      xo = xi + tv;
+      rv = di;
+      rv = rv - alpha * qi;
+      dout = rv;
     }
     const double atv = fabs(tv), arv = fabs(rv);
     if (atv >= mx.a && atv > 0.0) maxloc_take(mx, tv, ord ? ord[i] : i, i);
     if (arv >= mr.a && arv > 0.0) maxloc_take(mr, rv, ord ? ord[i] : i, i);
     ssq += rv * rv;
+  };
+  if (VEC2) {
+    const int n2 = n >> 1;
+    double2 *x2 = reinterpret_cast<double2 *>(x), *d2 = reinterpret_cast<double2 *>(d);
+    const double2 *p2 = reinterpret_cast<const double2 *>(p), *q2 = reinterpret_cast<const double2 *>(q);
+    const double2 *qh2 = reinterpret_cast<const double2 *>(qhat), *t2 = reinterpret_cast<const double2 *>(t);
+    const double2 *s2 = reinterpret_cast<const double2 *>(dscale);
+    const int stride = gridDim.x * blockDim.x;
+    const double2 zero2 = make_double2(0.0, 0.0), one2 = make_double2(1.0, 1.0);
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n2; j += 2 * stride) {
+      const int j1 = j + stride;
+      const bool two = j1 < n2;
+      // all loads of both accesses first
+      double2 X0 = x2[j], P0 = p2[j], Q0 = q2[j];
+      double2 D0 = BCGS ? zero2 : d2[j];
+      double2 H0 = BCGS ? qh2[j] : zero2, T0 = BCGS ? t2[j] : zero2;
+      double2 S0 = (BCGS && iscl != 0) ? s2[j] : one2;
+      double2 X1 = zero2, P1 = zero2, Q1 = zero2, D1 = zero2, H1 = zero2, T1 = zero2, S1 = one2;
+      if (two) {
+        X1 = x2[j1];
+        P1 = p2[j1];
+        Q1 = q2[j1];
+        if (!BCGS) D1 = d2[j1];
+        if (BCGS) {
+          H1 = qh2[j1];
+          T1 = t2[j1];
+          if (iscl != 0) S1 = s2[j1];
+        }
+      }
+      double2 XO, DO;
+      row(2 * j, X0.x, D0.x, P0.x, Q0.x, H0.x, T0.x, S0.x, XO.x, DO.x);
+      row(2 * j + 1, X0.y, D0.y, P0.y, Q0.y, H0.y, T0.y, S0.y, XO.y, DO.y);
+      x2[j] = XO;
+      d2[j] = DO;
+      if (two) {
+        row(2 * j1, X1.x, D1.x, P1.x, Q1.x, H1.x, T1.x, S1.x, XO.x, DO.x);
+        row(2 * j1 + 1, X1.y, D1.y, P1.y, Q1.y, H1.y, T1.y, S1.y, XO.y, DO.y);
+        x2[j1] = XO;
+        d2[j1] = DO;
+      }
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+      const int i = n - 1;
+      double xo, dout;
+      row(i, x[i], BCGS ? 0.0 : d[i], p[i], q[i], BCGS ? qhat[i] : 0.0, BCGS ? t[i] : 0.0,
+          (BCGS && iscl != 0) ? dscale[i] : 1.0, xo, dout);
+      x[i] = xo;
+      d[i] = dout;
+    }
+  } else {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      double xo, dout;
+      row(i, x[i], BCGS ? 0.0 : d[i], p[i], q[i], BCGS ? qhat[i] : 0.0, BCGS ? t[i] : 0.0,
+          (BCGS && iscl != 0) ? dscale[i] : 1.0, xo, dout);
+      x[i] = xo;
+      d[i] = dout;
+    }
   }
   ssq = block_sum(ssq, sh);
   mx = block_maxloc(mx, shm);
@@ -940,6 +1025,8 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
         halo->exchange(const_cast<double *>(vec), S);
       }
     };
+    // 128-bit vector accesses in the update kernel need 16-byte aligned vectors (cudaMalloc gives 256)
+    const bool vec2 = ((reinterpret_cast<uintptr_t>(x_dev) & 15) == 0) && !std::getenv("MF6GPU_UPDATE_SCALAR");
     auto enqueue_iteration = [&](int first) {
       HaloPush hp;
       HaloSrc hs;
@@ -975,9 +1062,14 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
         prof_end();
         const DistRound r3 = round();
         prof_begin(PC_UPD);
-        update_kernel<0><<<G, kBlock, 0, S>>>(N, x_dev, d.p, p.p, q.p, nullptr, nullptr, nullptr,
-                                        ord, partial.p, pmx.p, pmr.p, tickets.p + TK_UPD,
-                                        st.p, sp, r2.pull, r3.push);
+        if (vec2)
+          update_kernel<0, 1><<<G, kBlock, 0, S>>>(N, x_dev, d.p, p.p, q.p, nullptr, nullptr, nullptr,
+                                             ord, partial.p, pmx.p, pmr.p, tickets.p + TK_UPD,
+                                             st.p, sp, r2.pull, r3.push);
+        else
+          update_kernel<0, 0><<<G, kBlock, 0, S>>>(N, x_dev, d.p, p.p, q.p, nullptr, nullptr, nullptr,
+                                             ord, partial.p, pmx.p, pmr.p, tickets.p + TK_UPD,
+                                             st.p, sp, r2.pull, r3.push);
         finalize_update(r3, 0);
         prof_end();
         launches += 3;
@@ -1009,9 +1101,14 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
         if (!fused) reduce_finalize(FIN_BCGS_OMEGA, nullptr, 1);
         prof_end();
         const DistRound r4 = round();
-        update_kernel<1><<<G, kBlock, 0, S>>>(N, x_dev, d.p, phat.p, q.p, qhat.p, t.p, dscale.p,
-                                        ord, partial.p, pmx.p, pmr.p, tickets.p + TK_UPD,
-                                        st.p, sp, r3.pull, r4.push);
+        if (vec2)
+          update_kernel<1, 1><<<G, kBlock, 0, S>>>(N, x_dev, d.p, phat.p, q.p, qhat.p, t.p, dscale.p,
+                                             ord, partial.p, pmx.p, pmr.p, tickets.p + TK_UPD,
+                                             st.p, sp, r3.pull, r4.push);
+        else
+          update_kernel<1, 0><<<G, kBlock, 0, S>>>(N, x_dev, d.p, phat.p, q.p, qhat.p, t.p, dscale.p,
+                                             ord, partial.p, pmx.p, pmr.p, tickets.p + TK_UPD,
+                                             st.p, sp, r3.pull, r4.push);
         finalize_update(r4, 1);
         launches += 6;
       }

@@ -143,6 +143,35 @@ static double sQSaturationDerivative(double top, double bot, double x) {
   return 0.0;
 }
 
+/* the same two functions with explicit c1 / c2 (SmoothingFunctions.f90:412-516; DRN passes -1, 2) */
+static double sQSaturationC(double top, double bot, double x, double c1, double c2) {
+  double w = x - bot, b = top - bot, s = w / b;
+  double cof1 = c1 / (b * b * b), cof2 = c2 / (b * b);
+  if (s < 0.0) return 0.0;
+  if (s < 1.0) return cof1 * (w * w * w) + cof2 * (w * w);
+  return 1.0;
+}
+
+static double sQSaturationDerivativeC(double top, double bot, double x, double c1, double c2) {
+  double w = x - bot, b = top - bot, s = w / b;
+  double cof1 = c1 * 3.0 / (b * b * b), cof2 = c2 * 2.0 / (b * b);
+  if (s < 0.0) return 0.0;
+  if (s < 1.0) return cof1 * (w * w) + cof2 * w;
+  return 0.0;
+}
+
+/* get_drain_elevations, gwf-drn.f90:501-530 (b1 = elev, b3 = the DDRN auxiliary value, 0 = none) */
+static void drain_elevations(double drnelev, double drndepth, double *drntop, double *drnbot) {
+  if (drndepth != 0.0) {
+    double elev = drnelev + drndepth;
+    *drntop = elev > drnelev ? elev : drnelev;
+    *drnbot = elev < drnelev ? elev : drnelev;
+  } else {
+    *drntop = drnelev;
+    *drnbot = drnelev;
+  }
+}
+
 /* ---------------- GwfConductanceUtils.f90 -------------------------------- */
 static double logmean(double d1, double d2) {
   double drat = d2 / d1;
@@ -654,14 +683,22 @@ static void bnd_cf(orc_solution *S, pkg_t *p) {
       p->hcof[i] = -p->b2[i];
       p->rhs[i] = -p->b2[i] * p->b1[i];
       break;
-    case MF6GPU_PKG_DRN: { /* gwf-drn.f90:340-373, drndepth = 0 */
+    case MF6GPU_PKG_DRN: { /* drn_cf + get_drain_factor, gwf-drn.f90:340-373, 534-574 */
       if (S->ibound[node] <= 0) {
         p->hcof[i] = 0.0;
         p->rhs[i] = 0.0;
         break;
       }
-      double cdrn = p->b2[i], drnbot = p->b1[i];
-      double fact = (S->x[node] <= drnbot) ? 0.0 : 1.0;
+      double cdrn = p->b2[i], drndepth = p->b3[i], drntop, drnbot, fact;
+      drain_elevations(p->b1[i], drndepth, &drntop, &drnbot);
+      if (drndepth != 0.0) {
+        if (p->iflowred != 0) /* DEV_CUBIC_SCALING */
+          fact = sQSaturationC(drntop, drnbot, S->x[node], -1.0, 2.0);
+        else
+          fact = sQuadraticSaturation(drntop, drnbot, S->x[node], 0.0);
+      } else {
+        fact = (S->x[node] <= drnbot) ? 0.0 : 1.0;
+      }
       p->rhs[i] = -fact * cdrn * drnbot;
       p->hcof[i] = -fact * cdrn;
       break;
@@ -680,8 +717,23 @@ static void bnd_fc(orc_solution *S, pkg_t *p) {
   }
 }
 
-/* gwf-wel.f90:378-424 */
+/* gwf-wel.f90:378-424, gwf-drn.f90:420-470 */
 static void bnd_fn(orc_solution *S, pkg_t *p) {
+  if (p->type == MF6GPU_PKG_DRN) {
+    for (int i = 0; i < p->nbound; i++) {
+      int node = p->nodelist[i];
+      if (S->ibound[node] <= 0) continue;
+      double cdrn = p->b2[i], xnew = S->x[node], drndepth = p->b3[i], drntop, drnbot;
+      drain_elevations(p->b1[i], drndepth, &drntop, &drnbot);
+      if (drndepth != 0.0) {
+        double drterm = sQSaturationDerivativeC(drntop, drnbot, xnew, -1.0, 2.0);
+        drterm = drterm * cdrn * (drnbot - xnew);
+        S->amat[S->ia[node]] += drterm;
+        S->rhs[node] = S->rhs[node] + drterm * xnew;
+      }
+    }
+    return;
+  }
   if (p->type != MF6GPU_PKG_WEL) return;
   for (int i = 0; i < p->nbound; i++) {
     int node = p->nodelist[i];
