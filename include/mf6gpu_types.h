@@ -104,6 +104,17 @@ typedef struct mf6gpu_gwf_model {
   int32_t iconf_ss;   /* SS_CONFINED_ONLY */
   int32_t iorig_ss;   /* 1 = original (pre 6.2.1) ss formulation */
   int32_t reserved;
+  /* NPF anisotropy (gwf-npf.f90 hy_eff :2280-2355, HGeoUtil.f90 hyeff :29-108).  All NULL = isotropic in the
+   * plane (K22 = K).  k22 [nodes]; angle1/2/3 [nodes] in RADIANS (the deck's degrees x pi/180); conn_nx / conn_ny
+   * [njas] = x, y components of the unit normal of every connection pointing from its lower- to its
+   * higher-numbered cell (DIS: exactly (1,0) or (0,-1), Dis.f90:1039-1085; DISV/DISU: cos / sin of ANGLDEGX,
+   * Disv.f90:979-1018); needed when k22 or angle1 is given */
+  const double *k22;
+  const double *angle1;
+  const double *angle2;
+  const double *angle3;
+  const double *conn_nx;
+  const double *conn_ny;
 } mf6gpu_gwf_model;
 
 /* ---- stress packages (BoundaryPackage.f90:47-166) ------------------------ */

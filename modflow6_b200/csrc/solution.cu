@@ -44,6 +44,7 @@ struct ModelView {
   const int *ihc;
   const double *top, *bot, *area, *k11, *k33, *ss, *sy;
   const int *icelltype, *ibound, *iconvert;
+  const double *hyc;  // [2*njas] hy_eff of the lower- / higher-numbered cell along the connection; null = k11 / k33
   ModelOpts o;
 };
 
@@ -56,11 +57,13 @@ __device__ __forceinline__ double conn_cond(const ModelView &M, int r, int c, in
   const int ihc = M.ihc[jas];
   if (ihc == 0)
     return vcond(M.ibound[n], M.ibound[m], M.icelltype[n], M.icelltype[m], M.o.ivarcv,
-                 M.o.idewatcv, slot_csat, h[n], h[m], M.k33[n], M.k33[m], sat[n], sat[m],
-                 M.top[n], M.top[m], M.bot[n], M.bot[m], M.hwva[jas]);
+                 M.o.idewatcv, slot_csat, h[n], h[m], M.hyc ? M.hyc[2 * jas] : M.k33[n],
+                 M.hyc ? M.hyc[2 * jas + 1] : M.k33[m], sat[n], sat[m], M.top[n], M.top[m], M.bot[n], M.bot[m],
+                 M.hwva[jas]);
   return hcond(M.ibound[n], M.ibound[m], M.icelltype[n], M.icelltype[m], M.o.inewton, ihc,
-               M.o.icellavg, slot_csat, h[n], h[m], sat[n], sat[m], M.k11[n], M.k11[m], M.top[n],
-               M.top[m], M.bot[n], M.bot[m], M.cl1[jas], M.cl2[jas], M.hwva[jas]);
+               M.o.icellavg, slot_csat, h[n], h[m], sat[n], sat[m], M.hyc ? M.hyc[2 * jas] : M.k11[n],
+               M.hyc ? M.hyc[2 * jas + 1] : M.k11[m], M.top[n], M.top[m], M.bot[n], M.bot[m], M.cl1[jas],
+               M.cl2[jas], M.hwva[jas]);
 }
 
 // calc_condsat (gwf-npf.f90:1950-2037), upper triangle, no THICKSTRT (sat = 1)
@@ -73,11 +76,12 @@ __global__ void condsat_kernel(int njas, const int *__restrict__ conn_n,
     const double topn = M.top[n], botn = M.bot[n], topm = M.top[m], botm = M.bot[m];
     double csat;
     if (ihc == 0)
-      csat = vcond(1, 1, 1, 1, 1, 1, 1.0, botn, botm, M.k33[n], M.k33[m], 1.0, 1.0, topn, topm,
-                   botn, botm, M.hwva[jj]);
+      csat = vcond(1, 1, 1, 1, 1, 1, 1.0, botn, botm, M.hyc ? M.hyc[2 * jj] : M.k33[n],
+                   M.hyc ? M.hyc[2 * jj + 1] : M.k33[m], 1.0, 1.0, topn, topm, botn, botm, M.hwva[jj]);
     else
-      csat = hcond(1, 1, 1, 1, 0, ihc, M.o.icellavg, 1.0, topn, topm, 1.0, 1.0, M.k11[n],
-                   M.k11[m], topn, topm, botn, botm, M.cl1[jj], M.cl2[jj], M.hwva[jj]);
+      csat = hcond(1, 1, 1, 1, 0, ihc, M.o.icellavg, 1.0, topn, topm, 1.0, 1.0,
+                   M.hyc ? M.hyc[2 * jj] : M.k11[n], M.hyc ? M.hyc[2 * jj + 1] : M.k11[m], topn, topm, botn, botm,
+                   M.cl1[jj], M.cl2[jj], M.hwva[jj]);
     condsat[jj] = csat;
   }
 }
@@ -908,6 +912,7 @@ struct mf6gpu_solution {
   int isymmetric = 0;
   cudaStream_t stream = 0;
   DevBuf<double> top, bot, area, k11, k33, ssv, syv;
+  DevBuf<double> hyc;            // NPF anisotropy: see ModelView::hyc (empty = isotropic in the plane)
   DevBuf<double> strt;
   DevBuf<double> x, xold, sat, rhs, xtemp, dxold, wsave, hchold, deold, strgss, strgsy;
   DevBuf<int> icelltype, ibound, ibound0, iconvert, ibotnode;
@@ -964,6 +969,7 @@ struct mf6gpu_solution {
     M.area = area.p;
     M.k11 = k11.p;
     M.k33 = k33.p;
+    M.hyc = hyc.n ? hyc.p : nullptr;
     M.ss = ssv.p;
     M.sy = syv.p;
     M.icelltype = icelltype.p;
@@ -1287,6 +1293,59 @@ struct DistArgs {
   const int32_t *global_id;  // [nodes] global cell id of every local cell (owned + halo)
 };
 
+// hyeff (src/Utilities/HGeoUtil.f90:29-108, iavgmeth = 0 -- the only value the reference sets) and hy_eff
+// (gwf-npf.f90:2280-2355), evaluated once on the host per connection side: the effective conductivity of a cell
+// along a connection depends only on static data (K11, K22, K33, the rotation angles, the connection normal)
+static double hyeff_host(double k11, double k22, double k33, double ang1, double ang2, double ang3, double vg1,
+                         double vg2, double vg3) {
+  const double s1 = std::sin(ang1), c1 = std::cos(ang1), s2 = std::sin(ang2), c2 = std::cos(ang2);
+  const double s3 = std::sin(ang3), c3 = std::cos(ang3);
+  const double r11 = c1 * c2, r12 = c1 * s2 * s3 - s1 * c3, r13 = -c1 * s2 * c3 - s1 * s3;
+  const double r21 = s1 * c2, r22 = s1 * s2 * s3 + c1 * c3, r23 = -s1 * s2 * c3 + c1 * s3;
+  const double r31 = s2, r32 = -c2 * s3, r33 = c2 * c3;
+  const double ve1 = r11 * vg1 + r21 * vg2 + r31 * vg3;
+  const double ve2 = r12 * vg1 + r22 * vg2 + r32 * vg3;
+  const double ve3 = r13 * vg1 + r23 * vg2 + r33 * vg3;
+  double dnum = 1.0, d1 = ve1 * ve1, d2 = ve2 * ve2, d3 = ve3 * ve3;
+  if (ve1 != 0.0) {
+    dnum = dnum * k11;
+    d2 = d2 * k11;
+    d3 = d3 * k11;
+  }
+  if (ve2 != 0.0) {
+    dnum = dnum * k22;
+    d1 = d1 * k22;
+    d3 = d3 * k22;
+  }
+  if (ve3 != 0.0) {
+    dnum = dnum * k33;
+    d1 = d1 * k33;
+    d2 = d2 * k33;
+  }
+  const double denom = d1 + d2 + d3;
+  return denom > 0.0 ? dnum / denom : 0.0;
+}
+
+static double hy_eff_host(const mf6gpu_gwf_model *md, int n, int ihc, double vg1, double vg2, double vg3) {
+  const double hy11 = md->k11[n], hy22 = md->k22 ? md->k22[n] : md->k11[n];
+  const double hy33 = md->k33 ? md->k33[n] : md->k11[n];
+  if (ihc == 0) {
+    if (!md->angle2) return hy33;
+    return hyeff_host(hy11, hy22, hy33, md->angle1 ? md->angle1[n] : 0.0, md->angle2[n],
+                      md->angle3 ? md->angle3[n] : 0.0, vg1, vg2, vg3);
+  }
+  if (!md->k22) return hy11;
+  double a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  if (md->angle1) {
+    a1 = md->angle1[n];
+    if (md->angle2) {
+      a2 = md->angle2[n];
+      if (md->angle3) a3 = md->angle3[n];
+    }
+  }
+  return hyeff_host(hy11, hy22, hy33, a1, a2, a3, vg1, vg2, vg3);
+}
+
 // blocks of the BLOCK_MULTICOLOR ordering: the vertical cell columns (chains of ihc == 0 connections)
 static std::vector<int32_t> model_column_blocks(const mf6gpu_gwf_model *m, int n_own) {
   const int base0 = m->index_base;
@@ -1507,6 +1566,24 @@ static void create_solution(const mf6gpu_gwf_model *m, const mf6gpu_sln_settings
         }
       }
       s->slot_conn.upload(slot_conn);
+      if (m->k22 || m->angle1 || m->angle2) {
+        MF6_REQUIRE(!da, "solution_create: K22 / rotation angles are not available on the split-model path");
+        MF6_REQUIRE(!(m->k22 || m->angle1) || (m->conn_nx && m->conn_ny),
+                    "solution_create: K22 / ANGLE1 need the connection normals conn_nx / conn_ny");
+        std::vector<double> hy(2 * (size_t)std::max(njas, 1), 0.0);
+        for (int v = 0; v < n_own; v++)
+          for (int p = m->ia[v] - base + 1; p < m->ia[v + 1] - base; p++) {
+            const int u = m->ja[p] - base;
+            if (u < v) continue;
+            const int jj = m->jas[p] - base, hc = m->ihc[jj];
+            const double nx = (hc != 0 && m->conn_nx) ? m->conn_nx[jj] : 0.0;
+            const double ny = (hc != 0 && m->conn_ny) ? m->conn_ny[jj] : 0.0;
+            // connection_normal: seen from the cell itself; u lies below v for a vertical connection
+            hy[2 * (size_t)jj] = hy_eff_host(m, v, hc, nx, ny, hc == 0 ? -1.0 : 0.0);
+            hy[2 * (size_t)jj + 1] = hy_eff_host(m, u, hc, -nx, -ny, hc == 0 ? 1.0 : 0.0);
+          }
+        s->hyc.upload(hy);
+      }
       s->condsat.alloc_zero((size_t)std::max(njas, 1));
       s->slot_condsat.alloc_zero((size_t)A->nslots);
       s->flowja.alloc_zero((size_t)A->nslots);

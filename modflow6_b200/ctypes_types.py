@@ -109,6 +109,12 @@ class GwfModelStruct(C.Structure):
         ("iconf_ss", c_i32),
         ("iorig_ss", c_i32),
         ("reserved", c_i32),
+        ("k22", p_f64),
+        ("angle1", p_f64),
+        ("angle2", p_f64),
+        ("angle3", p_f64),
+        ("conn_nx", p_f64),
+        ("conn_ny", p_f64),
     ]
 
 

@@ -84,6 +84,14 @@ class GwfModel:
     iorig_ss: int = 0
     shape: tuple = None
     meta: dict = field(default_factory=dict)
+    # NPF anisotropy (all None = K22 == K, no rotation): k22 [nodes], angle1/2/3 [nodes] in radians, and the unit
+    # normal of every connection from its lower- to its higher-numbered cell
+    k22: np.ndarray = None
+    angle1: np.ndarray = None
+    angle2: np.ndarray = None
+    angle3: np.ndarray = None
+    conn_nx: np.ndarray = None
+    conn_ny: np.ndarray = None
 
     def __post_init__(self):
         n = self.nodes
@@ -96,6 +104,11 @@ class GwfModel:
         self.ss = T.as_f64(self.ss) if self.ss is not None else np.zeros(n)
         self.sy = T.as_f64(self.sy) if self.sy is not None else np.zeros(n)
         self.iconvert = T.as_i32(self.iconvert) if self.iconvert is not None else np.zeros(n, np.int32)
+        for name in ("k22", "angle1", "angle2", "angle3", "conn_nx", "conn_ny"):
+            v = getattr(self, name)
+            if v is not None:
+                size = self.ihc.size if name.startswith("conn_") else n
+                setattr(self, name, T.as_f64(np.broadcast_to(np.asarray(v, dtype=np.float64), (size,)).copy()))
 
     @property
     def nja(self):
@@ -117,6 +130,10 @@ class GwfModel:
                      "istor_coef", "iconf_ss", "iorig_ss"):
             setattr(s, name, int(getattr(self, name)))
         s.ithickstrt = 0
+        for name in ("k22", "angle1", "angle2", "angle3", "conn_nx", "conn_ny"):
+            v = getattr(self, name)
+            if v is not None:
+                setattr(s, name, T.ptr_f64(v))
         return s
 
     def node(self, k, i, j):
@@ -244,6 +261,18 @@ def build_dis_model(nlay, nrow, ncol, delr, delc, top, botm, k11, k33=None, icel
     k33v = _bcast(k33 if k33 is not None else k11, shp)
     ict = np.ascontiguousarray(np.broadcast_to(np.asarray(icelltype, dtype=np.int32), shp)).reshape(-1)
     ibot = (np.arange(n, dtype=np.int64) % nrc + (nlay - 1) * nrc).astype(np.int32)
+    # anisotropy: per-cell arrays + the connection normals of DisType%connection_normal (Dis.f90:1039-1085):
+    # towards the next column (1, 0), towards the next row ("front") (0, -1), vertical (0, 0)
+    for name in ("k22", "angle1", "angle2", "angle3"):
+        if opts.get(name) is not None:
+            opts[name] = _bcast(opts[name], shp)
+    if opts.get("k22") is not None or opts.get("angle1") is not None:
+        nx, ny = np.zeros(njas), np.zeros(njas)
+        sr = np.nonzero(hasr)[0]
+        nx[ustart[sr]] = 1.0
+        sf = np.nonzero(hasf)[0]
+        ny[ustart[sf] + hasr[sf]] = -1.0
+        opts["conn_nx"], opts["conn_ny"] = nx, ny
     m = GwfModel(nodes=n, ia=c["ia"], ja=c["ja"], jas=c["jas"], isym=c["isym"], ihc=ihc, cl1=cl1,
                  cl2=cl2, hwva=hwva, top=topv, bot=botv, area=area, k11=k11v, k33=k33v,
                  icelltype=ict, strt=_bcast(strt, shp), ibotnode=ibot,

@@ -310,7 +310,7 @@ def _cellid(tokens, shape):
     raise Mf6InputError("only DIS cellids are supported")
 
 
-def _read_rcha(blocks, name, shape, fixed_cell=0):
+def _read_rcha(blocks, name, shape, fixed_cell=0, base_dir=""):
     """array-based recharge (gwf-rcha.dfn): PERIOD blocks hold IRCH (layer of every 2-D cell, default 1) and
     RECHARGE arrays; an array that a block omits keeps its previous values (rch_rp / RchType read_initial_attr).
     Turned into the equivalent list: one boundary per 2-D cell at (irch, cell)."""
@@ -322,7 +322,7 @@ def _read_rcha(blocks, name, shape, fixed_cell=0):
     for nm, num, lines in blocks:
         if nm != "PERIOD":
             continue
-        g = read_griddata(lines, "", {"IRCH": (a2, np.int32), "RECHARGE": (a2, np.float64)})
+        g = read_griddata(lines, base_dir, {"IRCH": (a2, np.int32), "RECHARGE": (a2, np.float64)})
         irch = g.get("IRCH", irch)
         rech = g.get("RECHARGE", rech)
         if irch.min() < 1 or irch.max() > shape[0]:
@@ -332,20 +332,32 @@ def _read_rcha(blocks, name, shape, fixed_cell=0):
     return StressPackage("RCH", name, periods, fixed_cell)
 
 
-def read_stress_package(path, ftype, name, shape):
+def read_stress_package(path, ftype, name, shape, inewton=0):
     b = read_blocks(path)
     opt = _options(_block(b, "OPTIONS", required=False))
-    naux = len(opt.get("AUXILIARY", opt.get("AUX", [])))
+    auxnames = [a.upper() for a in opt.get("AUXILIARY", opt.get("AUX", []))]
+    naux = len(auxnames)
     for k in opt:
         if k in ("TS6", "TAS6", "MOVER", "AUXMULTNAME") or (k == "READASARRAYS" and ftype != "RCH6"):
             raise Mf6InputError(f"{path}: option {k} is not supported on the GPU path")
     fixed_cell = 1 if (ftype == "RCH6" and "FIXED_CELL" in opt) else 0    # carried in Package.iflowred for RCH
     if "READASARRAYS" in opt:
-        return _read_rcha(b, name, shape, fixed_cell), naux
+        return _read_rcha(b, name, shape, fixed_cell, os.path.dirname(path)), naux
     iflowred, flowred = fixed_cell, 0.1
     if "AUTO_FLOW_REDUCE" in opt:
         iflowred, flowred = 1, float(opt["AUTO_FLOW_REDUCE"][0]) if opt["AUTO_FLOW_REDUCE"] else 0.1
     ncol = _PKG_NCOL[ftype]
+    # DRN: AUXDEPTHNAME names the auxiliary column that holds the drainage depth (carried in b3); the discharge
+    # scaling is cubic under NEWTON or with DEV_CUBIC_SCALING (carried in Package.iflowred), gwf-drn.f90:127-135, 203-231
+    depth_col = None
+    if ftype == "DRN6":
+        iflowred = 1 if (inewton or "DEV_CUBIC_SCALING" in opt) else 0
+        if "AUXDEPTHNAME" in opt:
+            nm_d = opt["AUXDEPTHNAME"][0].upper()
+            if nm_d not in auxnames:
+                raise Mf6InputError(f"{path}: AUXDEPTHNAME {nm_d} is not one of the AUXILIARY variables")
+            depth_col = ncol + auxnames.index(nm_d)
+    nread = ncol + (naux if depth_col is not None else 0)
     periods = {}
     for nm, num, lines in b:
         if nm != "PERIOD":
@@ -363,7 +375,7 @@ def read_stress_package(path, ftype, name, shape):
                     for r in rec:
                         node, _ = _cellid([str(int(c)) for c in r["cellid"]], shape)
                         nodes.append(node)
-                        vals.append([float(x) for x in r["v"][:ncol]])
+                        vals.append([float(x) for x in r["v"][:nread]])
                 else:
                     with open(fn) as f:
                         for raw in f:
@@ -371,14 +383,16 @@ def read_stress_package(path, ftype, name, shape):
                             if tt:
                                 node, w = _cellid(tt, shape)
                                 nodes.append(node)
-                                vals.append([float(v) for v in tt[w:w + ncol]])
+                                vals.append([float(v) for v in tt[w:w + nread]])
                 continue
             node, w = _cellid(t, shape)
             nodes.append(node)
-            vals.append([float(v) for v in t[w:w + ncol]])
+            vals.append([float(v) for v in t[w:w + nread]])
         if nodes:
             v = np.array(vals)
             cols = [v[:, c] if c < ncol else None for c in range(3)]
+            if depth_col is not None:
+                cols[2] = v[:, depth_col]
             periods[num] = Package(_PKG_TYPE[ftype], np.array(nodes), cols[0], cols[1], cols[2], iflowred=iflowred,
                                    flowred=flowred)
         else:
@@ -458,14 +472,31 @@ def read_gwf_model(name, nam_path, base_dir, warnings):
     nb = read_blocks(files["NPF6"])
     nopt = _options(_block(nb, "OPTIONS", required=False))
     for k in nopt:
-        if k in ("THICKSTRT", "XT3D", "REWET", "TVK6", "K22OVERK", "K33OVERK"):
+        if k in ("THICKSTRT", "XT3D", "REWET", "TVK6"):
             raise Mf6InputError(f"NPF option {k} is not supported on the GPU path")
     np_ = read_griddata(_block(nb, "GRIDDATA"), base_dir,
                         {"ICELLTYPE": (ashape, np.int32), "K": (ashape, np.float64), "K22": (ashape, np.float64),
-                         "K33": (ashape, np.float64)})
-    if "K22" in np_ and not np.array_equal(np_["K22"], np_["K"]):
-        raise Mf6InputError("NPF K22 anisotropy is not supported on the GPU path")
+                         "K33": (ashape, np.float64), "ANGLE1": (ashape, np.float64), "ANGLE2": (ashape, np.float64),
+                         "ANGLE3": (ashape, np.float64)})
+    # K22OVERK / K33OVERK: the arrays hold ratios (gwf-npf.f90 prepcheck: k22 = k22 * k11, k33 = k33 * k11)
+    if "K22OVERK" in nopt and "K22" in np_:
+        np_["K22"] = np_["K22"] * np_["K"]
+    if "K33OVERK" in nopt and "K33" in np_:
+        np_["K33"] = np_["K33"] * np_["K"]
     kw = {}
+    aniso = ("K22" in np_ and not np.array_equal(np_["K22"], np_["K"])) or any(a in np_ for a in ("ANGLE1", "ANGLE2", "ANGLE3"))
+    if aniso:
+        # hy_eff (gwf-npf.f90:2280-2355); angles are given in degrees and stored in radians (:1213-1239)
+        if disu is not None or cell2d is not None or ("IDOMAIN" in g and (g["IDOMAIN"] <= 0).any()):
+            raise Mf6InputError("NPF K22 / ANGLE anisotropy is supported on full DIS grids only on the GPU path")
+        if "ANGLE2" in np_ and "ANGLE1" not in np_:
+            raise Mf6InputError("NPF: ANGLE2 needs ANGLE1 (gwf-npf.f90 prepcheck)")
+        if "ANGLE3" in np_ and "ANGLE2" not in np_:
+            raise Mf6InputError("NPF: ANGLE3 needs ANGLE1 and ANGLE2 (gwf-npf.f90 prepcheck)")
+        kw["k22"] = (np_["K22"] if "K22" in np_ else np_["K"]).reshape(shape)
+        for a in ("ANGLE1", "ANGLE2", "ANGLE3"):
+            if a in np_:
+                kw[a.lower()] = (np_[a] * (np.arctan(1.0) / 45.0)).reshape(shape)   # DPIO180, Constants.f90:130
     avg = {"LOGARITHMIC": 1, "AMT-LMK": 2, "AMT-HMK": 3}
     if "ALTERNATIVE_CELL_AVERAGING" in nopt:
         kw["icellavg"] = avg[nopt["ALTERNATIVE_CELL_AVERAGING"][0].upper()]
@@ -518,7 +549,7 @@ def read_gwf_model(name, nam_path, base_dir, warnings):
     count = {}
     for ft, fn, pn in stress:
         count[ft] = count.get(ft, 0) + 1
-        sp, _ = read_stress_package(fn, ft, pn or f"{ft[:-1]}-{count[ft]}", shape)
+        sp, _ = read_stress_package(fn, ft, pn or f"{ft[:-1]}-{count[ft]}", shape, inewton)
         if gi.nodereduced is not None:          # user cellids -> reduced nodes; boundaries in removed cells are dropped
             for iper, p in sp.periods.items():
                 if p is None:

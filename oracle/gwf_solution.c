@@ -46,6 +46,7 @@ struct orc_solution {
   int nodes, nja, njas;
   int *ia, *ja, *jas, *isym, *ihc;
   double *cl1, *cl2, *hwva, *top, *bot, *area, *k11, *k33, *ss, *sy;
+  double *hyc; /* [2*njas] effective K of the lower / higher cell along every connection (hy_eff), NULL = k11 / k33 */
   int *icelltype, *ibound0, *ibound, *ibotnode, *iconvert;
   int icellavg, inewton, inewtonur, iperched, ivarcv, idewatcv, insto;
   int istor_coef, iconf_ss, iorig_ss;
@@ -266,6 +267,75 @@ static double thksat(const orc_solution *S, int n, double hn) {
   return t;
 }
 
+/* hyeff, src/Utilities/HGeoUtil.f90:29-108 (iavgmeth = 0, the only value the reference ever sets) */
+static double hyeff(double k11, double k22, double k33, double ang1, double ang2, double ang3, double vg1,
+                    double vg2, double vg3) {
+  double s1 = sin(ang1), c1 = cos(ang1), s2 = sin(ang2), c2 = cos(ang2), s3 = sin(ang3), c3 = cos(ang3);
+  double r11 = c1 * c2, r12 = c1 * s2 * s3 - s1 * c3, r13 = -c1 * s2 * c3 - s1 * s3;
+  double r21 = s1 * c2, r22 = s1 * s2 * s3 + c1 * c3, r23 = -s1 * s2 * c3 + c1 * s3;
+  double r31 = s2, r32 = -c2 * s3, r33 = c2 * c3;
+  double ve1 = r11 * vg1 + r21 * vg2 + r31 * vg3;
+  double ve2 = r12 * vg1 + r22 * vg2 + r32 * vg3;
+  double ve3 = r13 * vg1 + r23 * vg2 + r33 * vg3;
+  double K = 0.0, dnum = 1.0, d1 = ve1 * ve1, d2 = ve2 * ve2, d3 = ve3 * ve3;
+  if (ve1 != 0.0) {
+    dnum = dnum * k11;
+    d2 = d2 * k11;
+    d3 = d3 * k11;
+  }
+  if (ve2 != 0.0) {
+    dnum = dnum * k22;
+    d1 = d1 * k22;
+    d3 = d3 * k22;
+  }
+  if (ve3 != 0.0) {
+    dnum = dnum * k33;
+    d1 = d1 * k33;
+    d2 = d2 * k33;
+  }
+  double denom = d1 + d2 + d3;
+  if (denom > 0.0) K = dnum / denom;
+  return K;
+}
+
+/* hy_eff, gwf-npf.f90:2280-2355: effective K of cell n along its connection to m (vg = normal seen from n) */
+static double hy_eff(const mf6gpu_gwf_model *md, const double *k33, int n, int ihc, double vg1, double vg2,
+                     double vg3) {
+  double hy11 = md->k11[n], hy22 = md->k22 ? md->k22[n] : md->k11[n], hy33 = k33[n];
+  if (ihc == 0) {
+    if (!md->angle2) return hy33;
+    return hyeff(hy11, hy22, hy33, md->angle1 ? md->angle1[n] : 0.0, md->angle2[n], md->angle3 ? md->angle3[n] : 0.0,
+                 vg1, vg2, vg3);
+  }
+  if (!md->k22) return hy11;
+  double a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  if (md->angle1) {
+    a1 = md->angle1[n];
+    if (md->angle2) {
+      a2 = md->angle2[n];
+      if (md->angle3) a3 = md->angle3[n];
+    }
+  }
+  return hyeff(hy11, hy22, hy33, a1, a2, a3, vg1, vg2, vg3);
+}
+
+/* K of the two cells of every connection along it (only with K22 / rotation angles) */
+static void calc_hyc(orc_solution *S, const mf6gpu_gwf_model *md) {
+  S->hyc = NULL;
+  if (!md->k22 && !md->angle1 && !md->angle2) return;
+  S->hyc = (double *)calloc(2 * (size_t)(S->njas ? S->njas : 1), sizeof(double));
+  for (int n = 0; n < S->nodes; n++)
+    for (int ii = S->ia[n] + 1; ii < S->ia[n + 1]; ii++) {
+      int m = S->ja[ii];
+      if (m < n) continue;
+      int jj = S->jas[ii], ihc = S->ihc[jj];
+      double nx = (ihc != 0 && md->conn_nx) ? md->conn_nx[jj] : 0.0, ny = (ihc != 0 && md->conn_ny) ? md->conn_ny[jj] : 0.0;
+      /* connection_normal: from n towards m; vertical: m below n => -1 seen from n, +1 seen from m */
+      S->hyc[2 * jj] = hy_eff(md, S->k33, n, ihc, nx, ny, ihc == 0 ? -1.0 : 0.0);
+      S->hyc[2 * jj + 1] = hy_eff(md, S->k33, m, ihc, -nx, -ny, ihc == 0 ? 1.0 : 0.0);
+    }
+}
+
 /* gwf-npf.f90:1950-2037 with upperOnly = .true., no THICKSTRT (sat = 1) */
 static void calc_condsat(orc_solution *S) {
   for (int n = 0; n < S->nodes; n++) {
@@ -277,12 +347,12 @@ static void calc_condsat(orc_solution *S) {
       double topn = S->top[n], botn = S->bot[n], topm = S->top[m], botm = S->bot[m];
       double csat;
       if (ihc == 0) {
-        csat = vcond(1, 1, 1, 1, 0, 1, 1, 1.0, botn, botm, S->k33[n], S->k33[m], 1.0,
-                     1.0, topn, topm, botn, botm, S->hwva[jj]);
+        csat = vcond(1, 1, 1, 1, 0, 1, 1, 1.0, botn, botm, S->hyc ? S->hyc[2 * jj] : S->k33[n],
+                     S->hyc ? S->hyc[2 * jj + 1] : S->k33[m], 1.0, 1.0, topn, topm, botn, botm, S->hwva[jj]);
       } else {
         csat = hcond(1, 1, 1, 1, 0, ihc, S->icellavg, 1.0, topn, topm, 1.0, 1.0,
-                     S->k11[n], S->k11[m], topn, topm, botn, botm, S->cl1[jj],
-                     S->cl2[jj], S->hwva[jj]);
+                     S->hyc ? S->hyc[2 * jj] : S->k11[n], S->hyc ? S->hyc[2 * jj + 1] : S->k11[m], topn, topm,
+                     botn, botm, S->cl1[jj], S->cl2[jj], S->hwva[jj]);
       }
       S->condsat[jj] = csat;
     }
@@ -326,11 +396,12 @@ static double conn_cond(const orc_solution *S, int n, int m, int ii, double hn,
   if (ihc == 0)
     return vcond(S->ibound[n], S->ibound[m], S->icelltype[n], S->icelltype[m],
                  S->inewton, S->ivarcv, S->idewatcv, S->condsat[jj], hn, hm,
-                 S->k33[n], S->k33[m], S->sat[n], S->sat[m], S->top[n], S->top[m],
-                 S->bot[n], S->bot[m], S->hwva[jj]);
+                 S->hyc ? S->hyc[2 * jj + (n > m)] : S->k33[n], S->hyc ? S->hyc[2 * jj + (m > n)] : S->k33[m],
+                 S->sat[n], S->sat[m], S->top[n], S->top[m], S->bot[n], S->bot[m], S->hwva[jj]);
   return hcond(S->ibound[n], S->ibound[m], S->icelltype[n], S->icelltype[m],
                S->inewton, ihc, S->icellavg, S->condsat[jj], hn, hm, S->sat[n],
-               S->sat[m], S->k11[n], S->k11[m], S->top[n], S->top[m], S->bot[n],
+               S->sat[m], S->hyc ? S->hyc[2 * jj + (n > m)] : S->k11[n],
+               S->hyc ? S->hyc[2 * jj + (m > n)] : S->k11[m], S->top[n], S->top[m], S->bot[n],
                S->bot[m], S->cl1[jj], S->cl2[jj], S->hwva[jj]);
 }
 
@@ -885,6 +956,7 @@ orc_solution *orc_sln_create(const mf6gpu_gwf_model *m,
   S->ss_ = *ss;
   S->ims = orc_ims_create(S->nodes, S->nja, S->ia, S->ja, ls, perm);
   S->isymmetric = (ls->ilinmeth == 1) ? 1 : 0; /* NumericalSolution.f90:914-916 */
+  calc_hyc(S, m);
   calc_condsat(S);
   return S;
 }
@@ -907,7 +979,7 @@ void orc_sln_destroy(orc_solution *S) {
   free_pkgs(S);
   free(S->ia); free(S->ja); free(S->jas); free(S->isym); free(S->ihc);
   free(S->cl1); free(S->cl2); free(S->hwva); free(S->top); free(S->bot);
-  free(S->area); free(S->k11); free(S->k33); free(S->ss); free(S->sy);
+  free(S->area); free(S->k11); free(S->k33); free(S->ss); free(S->sy); free(S->hyc);
   free(S->icelltype); free(S->iconvert); free(S->ibound0); free(S->ibound);
   free(S->ibotnode); free(S->x); free(S->xold); free(S->sat); free(S->condsat);
   free(S->amat); free(S->rhs); free(S->xtemp); free(S->dxold); free(S->wsave);

@@ -42,8 +42,9 @@ def summarize(heads):
 
 
 def main():
-    tight = "--tight" in sys.argv      # INNER_DVCLOSE x 0.1, INNER_RCLOSE x 0.01: closure slack out of the comparison
-    argv = [a for a in sys.argv if a != "--tight"]
+    # --tight: INNER_DVCLOSE x 0.1, INNER_RCLOSE x 0.01; --tight2: x 0.01, x 0.001 (closure slack out of the comparison)
+    tight = 2 if "--tight2" in sys.argv else (1 if "--tight" in sys.argv else 0)
+    argv = [a for a in sys.argv if a not in ("--tight", "--tight2")]
     which = argv[1]
     ordering = argv[2]
     max_steps = int(argv[3]) if len(argv) > 3 and argv[3] != "-" else None
@@ -56,8 +57,8 @@ def main():
     else:
         raise SystemExit("config must be c2 or c3")
     if tight:
-        cfg.ims.dvclose *= 0.1
-        cfg.ims.rclose *= 0.01
+        cfg.ims.dvclose *= 0.1 ** tight
+        cfg.ims.rclose *= 0.01 * 0.1 ** (tight - 1)
         cfg.ims.iter1 = max(cfg.ims.iter1, 1000)
     perm = None if o == T.ORDER_NATURAL else lib.model_elimination_order(cfg.model, o)
     t0 = time.perf_counter()
@@ -67,7 +68,7 @@ def main():
     heads = np.array(O.x, copy=True)
     tag = f"{which}_full_{ordering}" if size is None else f"{which}_{'x'.join(map(str, size))}_{ordering}"
     if tight:
-        tag += "_tight"
+        tag += "_tight" + ("2" if tight == 2 else "")
     os.makedirs(os.path.join(HERE, "_big"), exist_ok=True)
     np.save(os.path.join(HERE, "_big", tag + "_heads.npy"), heads)
     s = summarize(heads)

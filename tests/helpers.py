@@ -67,3 +67,34 @@ def assembled_system(m, pkgs, ilinmeth=1):
             x[p.nodelist] = p.b1
     S.formulate(kiter=1, delt=1.0, iss=1)
     return S.amat.copy(), S.rhs.copy(), S.x.copy()
+
+
+def drn_ddrn01_case(newton):
+    """autotest/test_gwf_drn_ddrn01.py:17-118 literally: 1 x 1 x 100 unconfined strip (xlen 1000, K 10, sy 0.1,
+    ss 1e-5), parabolic initial heads 9 -> 1, one drain in the last cell with elevation 0, conductance
+    kh*delc*ddrn/(delr/2) and DRAINAGE DEPTH ddrn = 1 (AUXDEPTHNAME); 100 transient steps x 1.1 over 100 days;
+    BICGSTAB, outer_dvclose 1e-6, inner_dvclose 1e-9, rclose 0.01 STRICT.  Case b adds NEWTON (cubic scaling,
+    drn_fn terms).  Returns (SimConfig, analytic drain discharge as a function of the drain cell's head)."""
+    from modflow6_b200 import configs
+    ncol, xlen = 100, 1000.0
+    delr, delc = xlen / ncol, 1.0
+    kh, h0, h1 = 10.0, 9.0, 1.0
+    delev, ddrn = 0.0, h1
+    dcond = kh * delc * ddrn / (0.5 * delr)
+    x = np.arange(0, xlen - delr / 2, delr)
+    strt = np.sqrt(h0 ** 2 + x * (h1 ** 2 - h0 ** 2) / (xlen - delr))
+    m = build_dis_model(1, 1, ncol, delr, delc, 10.0, [0.0], kh, icelltype=1, strt=strt.reshape(1, 1, ncol),
+                        ss=1e-5, sy=0.1, iconvert=1, inewton=1 if newton else 0)
+    drn = Package(T.PKG_DRN, [ncol - 1], [delev], [dcond], [ddrn], iflowred=1 if newton else 0)
+    ims = T.ImsSettings.make(dvclose=1e-9, rclose=0.01, icnvgopt=1, iter1=200, ilinmeth=2)
+    sln = T.SlnSettings.make(dvclose=1e-6, mxiter=200)
+    cfg = configs.SimConfig("drn_ddrn01" + ("b" if newton else "a"), m,
+                            [configs.Period(100.0, 100, 1.1, False, [drn])], sln, ims)
+
+    def analytic(h):
+        xd = np.asarray(h) - delev
+        sat = xd / ddrn
+        f = (-1.0 / ddrn ** 3) * xd ** 3 + (2.0 / ddrn ** 2) * xd ** 2 if newton else sat.copy()
+        f = np.where(sat < 0, 0.0, np.where(sat > 1, 1.0, f))
+        return f * dcond * (delev - np.asarray(h))
+    return cfg, analytic

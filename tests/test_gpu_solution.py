@@ -230,3 +230,70 @@ def test_binary_output_files_match_oracle(gpu, tmp_path, which):
             assert np.array_equal(a["node"], b["node"]) and np.array_equal(a["node2"], b["node2"])
             assert np.allclose(a["q"], b["q"], rtol=1e-4, atol=1e-5 * max(1.0, np.abs(b["q"]).max()))
     check_water_balance(cfg, hg, bg)
+
+
+@pytest.mark.parametrize("newton", [False, True])
+def test_drn_drainage_depth_on_device(gpu, newton):
+    """autotest/test_gwf_drn_ddrn01.py on the device: drainage-depth scaling of drn_cf (linear / cubic) and the
+    Newton terms of drn_fn; heads equal the oracle's and the reference's own criterion (discharge == analytic
+    scaling of the drain cell's head, 1e-6) holds for every time step"""
+    from modflow6_b200.grid import tdis_steps
+    from tests.helpers import drn_ddrn01_case
+    cfg, analytic = drn_ddrn01_case(newton)
+    G, O = _pair(cfg)
+    G.set_packages(cfg.periods[0].packages)
+    O.set_packages(cfg.periods[0].packages)
+    for kstp, delt in enumerate(tdis_steps(100.0, 100, 1.1), start=1):
+        rg, ro = G.timestep(1, kstp, delt, 0), O.timestep(1, kstp, delt, 0)
+        assert rg.converged == 1 and ro.converged == 1
+        hg = G.x
+        assert np.abs(hg - O.x).max() <= 0.1 * cfg.sln.dvclose
+        assert abs(G.simvals[0][0] - analytic(hg[-1:])[0]) < 1e-6
+        assert abs(rg.pdiffr - ro.pdiffr) <= 1e-3
+
+
+def test_npf05_anisotropy_on_device(gpu):
+    """autotest/test_gwf_npf05_anisotropy.py:127-141: the literal head array, on the device"""
+    from modflow6_b200.solution import GpuNumericalSolution
+    from tests.test_oracle_known_answers import NPF05_ANSWER, npf05_model
+    m, pk, sln, ims = npf05_model(k22=0.5)
+    G = GpuNumericalSolution(m, sln, ims)
+    G.set_packages(pk)
+    assert G.timestep().converged == 1
+    assert np.allclose(G.x, NPF05_ANSWER)
+
+
+@pytest.mark.parametrize("ordering", [T.ORDER_NATURAL, T.ORDER_BLOCK_MULTICOLOR])
+@pytest.mark.parametrize("angles", [0, 1, 3])
+def test_k22_rotated_anisotropy_parity(gpu, ordering, angles):
+    """hy_eff / hyeff (gwf-npf.f90:2280-2355, HGeoUtil.f90:29-108) with heterogeneous K11, K22, K33 and 0, 1 or 3
+    rotation angles: condsat and the assembled system equal the oracle bit for bit, heads within 0.1 x OUTER_DVCLOSE"""
+    rng = np.random.default_rng(12)
+    shp = (3, 14, 17)
+    k = np.exp(rng.normal(np.log(10.0), 0.8, size=shp))
+    opts = dict(k22=k * rng.uniform(0.05, 0.9, size=shp))
+    if angles >= 1:
+        opts["angle1"] = rng.uniform(-np.pi, np.pi, size=shp)
+    if angles >= 3:
+        opts["angle2"] = rng.uniform(-0.4, 0.4, size=shp)
+        opts["angle3"] = rng.uniform(-0.4, 0.4, size=shp)
+    from modflow6_b200.grid import build_dis_model
+    from tests.helpers import chd_west_east, well_center
+    m = build_dis_model(*shp, 100.0, 100.0, 0.0, -10.0 * np.arange(1, 4), k, k33=0.1 * k, icelltype=0, strt=44.0, **opts)
+    cfg = configs.SimConfig("aniso", m, [configs.Period(1.0, 1, 1.0, True, [chd_west_east(m), well_center(m)])],
+                            T.SlnSettings.make(dvclose=1e-7, mxiter=50),
+                            T.ImsSettings.make(dvclose=1e-9, rclose=1e-6, iter1=400, ilinmeth=2, gpu_ordering=ordering))
+    G, O = _pair(cfg)
+    assert np.array_equal(G.condsat, O.condsat)
+    a = configs.run_simulation(G, cfg, collect_heads=True)[0]
+    b = configs.run_simulation(O, cfg, collect_heads=True)[0]
+    assert a["converged"] == 1 and b["converged"] == 1
+    assert np.abs(a["head"] - b["head"]).max() <= 0.1 * cfg.sln.dvclose
+    assert abs(a["pdiffr"] - b["pdiffr"]) <= 1e-3
+    # anisotropy matters here: the isotropic model has different heads
+    m0 = build_dis_model(*shp, 100.0, 100.0, 0.0, -10.0 * np.arange(1, 4), k, k33=0.1 * k, icelltype=0, strt=44.0)
+    from oracle.oracle import OracleSolution
+    O0 = OracleSolution(m0, cfg.sln, cfg.ims)
+    O0.set_packages(cfg.periods[0].packages)
+    O0.timestep()
+    assert np.abs(O0.x - b["head"]).max() > 1e-3

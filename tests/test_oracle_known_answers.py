@@ -301,3 +301,84 @@ def test_ex_gwf_bump_reference_heads():
     assert rep.converged == 1
     assert np.allclose(base[0]["data"], O.x.reshape(51, 51))
     assert np.abs(base[0]["data"] - O.x.reshape(51, 51)).max() < 1e-6
+
+
+@pytest.mark.parametrize("newton", [False, True])
+def test_drn_ddrn01_discharge_scaling(newton):
+    """autotest/test_gwf_drn_ddrn01.py:120-190 -- the reference's own criterion: the simulated drain discharge of
+    every time step equals the analytic scaling (linear for Picard, cubic under NEWTON) of the drain cell's head
+    to 1e-6 (drainage depth, get_drain_factor and drn_fn, gwf-drn.f90:420-574)"""
+    from modflow6_b200 import configs
+    from tests.helpers import drn_ddrn01_case
+    cfg, analytic = drn_ddrn01_case(newton)
+    S = OracleSolution(cfg.model, cfg.sln, cfg.ims)
+    S.set_packages(cfg.periods[0].packages)
+    from modflow6_b200.grid import tdis_steps
+    heads, q = [], []
+    for kstp, delt in enumerate(tdis_steps(100.0, 100, 1.1), start=1):
+        rep = S.timestep(1, kstp, delt, 0)
+        assert rep.converged == 1
+        heads.append(S.x[-1])
+        q.append(S.simvals[0][0])
+    heads, q = np.array(heads), np.array(q)
+    assert np.abs(q - analytic(heads)).max() < 1e-6
+    assert q.min() < -1e-3 and 0.0 < heads[-1] < 1.0    # the drain works inside its scaling range
+
+
+NPF05_ANSWER = np.array([100.0, 100.00031999, 100.00055998, 100.00071997, 100.00079997,
+                         109.99960002, 109.99964002, 109.99972002, 109.99984001, 110.0])
+
+
+def npf05_model(**aniso):
+    """autotest/test_gwf_npf05_anisotropy.py:16-118: 2 x 1 x 5, top 100, botm 50 / 0, K 5, K22 0.5, K33 0.05 (given
+    as K22OVERK / K33OVERK ratios there), CHD 100 at (1,1,1) and 110 at (2,1,5), recharge 0.01"""
+    m = build_dis_model(2, 1, 5, 1.0, 1.0, 100.0, [50.0, 0.0], 5.0, k33=0.05, icelltype=0, strt=100.0, **aniso)
+    pk = [Package(T.PKG_CHD, [0, 9], [100.0, 110.0]), Package(T.PKG_RCH, np.arange(5), np.full(5, 0.01))]
+    ims = T.ImsSettings.make(dvclose=1e-9, rclose=1e-3, iter1=300, ilinmeth=2, relax=0.97)
+    sln = T.SlnSettings.make(dvclose=1e-9, mxiter=100, nonmeth=3, theta=0.7, akappa=0.1, gamma=0.2, amomentum=0.001)
+    return m, pk, sln, ims
+
+
+def test_npf05_anisotropy_literal_heads():
+    """autotest/test_gwf_npf05_anisotropy.py:127-141 -- the literal head array; with one row every horizontal
+    connection runs along x, so hy_eff must return K11 whatever K22 is (hyeff, HGeoUtil.f90:29-108)"""
+    m, pk, sln, ims = npf05_model(k22=0.5)
+    S = OracleSolution(m, sln, ims)
+    S.set_packages(pk)
+    assert S.timestep().converged == 1
+    assert np.allclose(S.x, NPF05_ANSWER)
+
+
+def _strip(axis, k11, k22=None, angle1=None, n=12):
+    """confined strip of n cells along x (axis 0) or y (axis 1) between CHD 10 and 0: returns the heads"""
+    shape = (1, 1, n) if axis == 0 else (1, n, 1)
+    rng = np.random.default_rng(4)
+    kk = k11 * np.exp(rng.normal(0.0, 0.5, size=shape))
+    opts = {}
+    if k22 is not None:
+        opts["k22"] = k22 * np.exp(rng.normal(0.0, 0.5, size=shape))
+    if angle1 is not None:
+        opts["angle1"] = angle1
+    m = build_dis_model(*shape, 10.0, 10.0, 0.0, [-5.0], kk, strt=5.0, **opts)
+    S = OracleSolution(m, T.SlnSettings.make(dvclose=1e-10, mxiter=50),
+                       T.ImsSettings.make(dvclose=1e-11, rclose=1e-9, iter1=100, ilinmeth=2))
+    S.set_packages([Package(T.PKG_CHD, [0, n - 1], [10.0, 0.0])])
+    assert S.timestep().converged == 1
+    return S.x.copy(), kk, opts.get("k22")
+
+
+def test_hy_eff_directional_conductivity():
+    """hy_eff (gwf-npf.f90:2280-2355): flow along y sees K22, along x K11; ANGLE1 = 90 degrees swaps them"""
+    hy_ref, kk, k22 = _strip(1, 3.0, k22=0.7)
+    # the same strip with K11 := that K22 field and no anisotropy
+    m = build_dis_model(1, 12, 1, 10.0, 10.0, 0.0, [-5.0], k22, strt=5.0)
+    S = OracleSolution(m, T.SlnSettings.make(dvclose=1e-10, mxiter=50),
+                       T.ImsSettings.make(dvclose=1e-11, rclose=1e-9, iter1=100, ilinmeth=2))
+    S.set_packages([Package(T.PKG_CHD, [0, 11], [10.0, 0.0])])
+    S.timestep()
+    assert np.array_equal(hy_ref, S.x)                    # exactly K22: the unit normal is exactly (0, -1)
+    hx, _, _ = _strip(0, 3.0, k22=0.7)                    # along x K22 is invisible
+    hx0, _, _ = _strip(0, 3.0)
+    assert np.array_equal(hx, hx0)
+    hrot, _, _ = _strip(0, 3.0, k22=0.7, angle1=np.arctan(1.0) * 2.0)   # ellipse turned by 90 degrees: x sees K22
+    assert np.allclose(hrot, hy_ref, rtol=0, atol=1e-9)
