@@ -19,7 +19,7 @@ module GpuMatrixModule
 
   type, public, extends(SparseMatrixType) :: GpuMatrixType
     type(c_ptr) :: handle = c_null_ptr !< mf6gpu_matrix*
-    integer(I4B) :: gpu_ordering = 1 !< MF6GPU_ORDER_MULTICOLOR
+    integer(I4B) :: gpu_ordering = 2 !< MF6GPU_ORDER_BLOCK_MULTICOLOR: the cell columns are found from the pattern
   contains
     procedure :: init => gpum_init
     procedure :: destroy => gpum_destroy

@@ -85,6 +85,9 @@ contains
     s%reserved = 0
     call mf6gpu_check(mf6gpu_solver_create(this%matrix%handle, s, &
                                            int(this%nitermax, c_int32_t), this%handle))
+    ! per-model records: model_bounds = CONVMODSTART (NumericalSolution.f90:409-416), 1-based
+    call mf6gpu_check(mf6gpu_solver_set_models(this%handle, int(convergence_summary%convnmod, c_int32_t), &
+                                               convergence_summary%model_bounds, 1_c_int32_t))
   end subroutine gpu_initialize
 
   !> @brief cf. petsc_solve (PetscSolver.F90:304-362)
@@ -106,13 +109,16 @@ contains
     this%iteration_number = it
     this%is_converged = cv
 
-    ! ConvergenceSummaryType side channel (ImsLinearBase.f90:186-197); single-model layout
+    ! ConvergenceSummaryType side channel (ImsLinearBase.f90:186-197): itinner, then the per-model records
+    ! convdvmax(nmod, niter) ... exactly in the layout the device keeps them (model index fastest)
     if (cnvg_summary%nitermax > 1) then
       nrec = mf6gpu_solver_get_summary(this%handle, int(cnvg_summary%nitermax, c_int32_t), &
-                                       cnvg_summary%itinner, cnvg_summary%convdvmax(1, :), &
-                                       cnvg_summary%convlocdv(1, :), cnvg_summary%convrmax(1, :), &
-                                       cnvg_summary%convlocr(1, :), cnvg_summary%convdvmax(1, :), &
-                                       cnvg_summary%convrmax(1, :))
+                                       c_loc(cnvg_summary%itinner), c_null_ptr, c_null_ptr, c_null_ptr, &
+                                       c_null_ptr, c_null_ptr, c_null_ptr)
+      call mf6gpu_check(nrec)
+      nrec = mf6gpu_solver_get_model_summary(this%handle, int(cnvg_summary%nitermax, c_int32_t), &
+                                             cnvg_summary%convdvmax, cnvg_summary%convlocdv, &
+                                             cnvg_summary%convrmax, cnvg_summary%convlocr)
       call mf6gpu_check(nrec)
       cnvg_summary%iter_cnt = nrec
     end if

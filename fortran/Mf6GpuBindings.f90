@@ -15,6 +15,7 @@ module Mf6GpuBindingsModule
   public :: mf6gpu_matrix_multiply
   public :: mf6gpu_solver_create, mf6gpu_solver_destroy, mf6gpu_solver_solve
   public :: mf6gpu_solver_get_summary, mf6gpu_solver_stat
+  public :: mf6gpu_solver_set_models, mf6gpu_solver_get_model_summary
   public :: mf6gpu_check
 
   !> ImsLinearSettingsType as plain data (ImsLinearSettings.f90:13-32)
@@ -94,14 +95,32 @@ module Mf6GpuBindingsModule
       integer(c_int32_t), intent(out) :: iteration_number, is_converged
       integer(c_int) :: rc
     end function
+    !> every array argument may be c_null_ptr (not wanted); pass c_loc(array) otherwise
     function mf6gpu_solver_get_summary(handle, cap, itinner, dvmax, locdv, rmax, locr, &
                                        alpha, omega) &
       bind(C, name="mf6gpu_solver_get_summary") result(rc)
+      import :: c_int, c_int32_t, c_ptr
+      type(c_ptr), value :: handle
+      integer(c_int32_t), value :: cap
+      type(c_ptr), value :: itinner, dvmax, locdv, rmax, locr, alpha, omega
+      integer(c_int) :: rc
+    end function
+    function mf6gpu_solver_set_models(handle, nmod, convmodstart, index_base) &
+      bind(C, name="mf6gpu_solver_set_models") result(rc)
+      import :: c_int, c_int32_t, c_ptr
+      type(c_ptr), value :: handle
+      integer(c_int32_t), value :: nmod, index_base
+      integer(c_int32_t), intent(in) :: convmodstart(*)
+      integer(c_int) :: rc
+    end function
+    !> convdvmax(nmod, niter) etc. are filled in place (model index fastest = Fortran column order)
+    function mf6gpu_solver_get_model_summary(handle, cap, convdvmax, convlocdv, convrmax, convlocr) &
+      bind(C, name="mf6gpu_solver_get_model_summary") result(rc)
       import :: c_int, c_int32_t, c_ptr, c_double
       type(c_ptr), value :: handle
       integer(c_int32_t), value :: cap
-      integer(c_int32_t), intent(inout) :: itinner(*), locdv(*), locr(*)
-      real(c_double), intent(inout) :: dvmax(*), rmax(*), alpha(*), omega(*)
+      real(c_double), intent(inout) :: convdvmax(*), convrmax(*)
+      integer(c_int32_t), intent(inout) :: convlocdv(*), convlocr(*)
       integer(c_int) :: rc
     end function
     function mf6gpu_solver_stat(handle, what) bind(C, name="mf6gpu_solver_stat") result(v)

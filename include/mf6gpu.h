@@ -127,6 +127,13 @@ int mf6gpu_solver_solve(mf6gpu_solver *s, int32_t kiter, int32_t kstp,
 int mf6gpu_solver_get_summary(mf6gpu_solver *s, int32_t cap, int32_t *itinner,
                               double *dvmax, int32_t *locdv, double *rmax,
                               int32_t *locr, double *alpha, double *omega);
+/* Per-model ConvergenceSummary (ImsLinearBase.f90:143-197, ConvergenceSummary.f90): convmodstart [nmod + 1] =
+ * first row of every model (NumericalSolution.f90:409-416 builds it the same way), then the records come back
+ * laid out like convdvmax(nmod, niter) / convlocdv / convrmax / convlocr (model index fastest; locations are
+ * 1-based rows, 0 = none).  get_model_summary returns the number of iterations recorded (< 0 on error). */
+int mf6gpu_solver_set_models(mf6gpu_solver *s, int32_t nmod, const int32_t *convmodstart, int32_t index_base);
+int mf6gpu_solver_get_model_summary(mf6gpu_solver *s, int32_t cap, double *convdvmax, int32_t *convlocdv,
+                                    double *convrmax, int32_t *convlocr);
 /* facts of the last solve: 0 l2norm0, 1 pivot corrections, 2 device seconds in
  * factorisation, 3 device seconds in the Krylov loop, 4 kernel launches, 5 split-model path: 1 when the
  * fused peer-memory exchange (in-kernel pushes / waits over NVLink) was used, 0 for the NCCL transport */

@@ -667,6 +667,63 @@ update_kernel(int n, double *__restrict__ x, double *__restrict__ d,
 
 enum { FIN_UPDATE = 100 };
 
+// Per-model maxima of the iteration the update kernel has just finished (ImsLinearBase.f90:143-176, 186-197):
+// grid.y = model.  dx and the residual are recomputed from the same operands (alpha, omega are final, P / PHAT /
+// QHAT untouched until the next iteration, D holds the new residual), so the values are the ones the update
+// kernel saw.  Record index = summary%iter_cnt - 1, filled once per iteration; a no-op rerun after the loop has
+// ended rewrites the same record with the same values.
+__global__ void __launch_bounds__(kBlock)
+model_summary_kernel(int n, int nmod, const int *__restrict__ modid, const double *__restrict__ d,
+                     const double *__restrict__ p, const double *__restrict__ qhat,
+                     const double *__restrict__ dscale, const int *__restrict__ ord, const KState *st, int bcgs,
+                     MaxLoc *__restrict__ pmx, MaxLoc *__restrict__ pmr, unsigned int *tickets,
+                     double *__restrict__ odv, int *__restrict__ olocdv, double *__restrict__ orm,
+                     int *__restrict__ olocr) {
+  __shared__ MaxLoc shm[8];
+  __shared__ bool last;
+  const int im = blockIdx.y;
+  const double alpha = st->alpha, omega = st->omega;
+  const int iscl = st->iscl;
+  MaxLoc mx = maxloc_init(), mr = maxloc_init();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (modid[i] != im) continue;
+    double tv = bcgs ? alpha * p[i] + omega * qhat[i] : alpha * p[i];
+    double rv = d[i];
+    if (bcgs && iscl != 0) {
+      tv = tv * dscale[i];
+      rv = rv / dscale[i];
+    }
+    const double atv = fabs(tv), arv = fabs(rv);
+    if (atv >= mx.a && atv > 0.0) maxloc_take(mx, tv, ord ? ord[i] : i, i);
+    if (arv >= mr.a && arv > 0.0) maxloc_take(mr, rv, ord ? ord[i] : i, i);
+  }
+  mx = block_maxloc(mx, shm);
+  mr = block_maxloc(mr, shm);
+  if (threadIdx.x == 0) {
+    pmx[(size_t)im * gridDim.x + blockIdx.x] = mx;
+    pmr[(size_t)im * gridDim.x + blockIdx.x] = mr;
+  }
+  if (last_block(tickets + im, &last)) {
+    MaxLoc gx = maxloc_init(), gr = maxloc_init();
+    for (int i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+      maxloc_merge(gx, pmx[(size_t)im * gridDim.x + i]);
+      maxloc_merge(gr, pmr[(size_t)im * gridDim.x + i]);
+    }
+    gx = block_maxloc(gx, shm);
+    gr = block_maxloc(gr, shm);
+    if (threadIdx.x == 0) {
+      const int k = st->sum_count - 1;
+      if (k >= 0 && k < st->sum_cap) {
+        const size_t q = (size_t)k * nmod + im;
+        odv[q] = gx.v;
+        olocdv[q] = gx.idx;
+        orm[q] = gr.v;
+        olocr[q] = gr.idx;
+      }
+    }
+  }
+}
+
 // split-model path: combine the gathered per-rank records in rank order (deterministic and
 // identical on every rank) and run the same scalar epilogue the single-GPU kernels run inline
 __global__ void global_finalize_kernel(int mode, const RedRec *__restrict__ all_in, int nranks,
@@ -1027,6 +1084,13 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
     };
     // 128-bit vector accesses in the update kernel need 16-byte aligned vectors (cudaMalloc gives 256)
     const bool vec2 = ((reinterpret_cast<uintptr_t>(x_dev) & 15) == 0) && !std::getenv("MF6GPU_UPDATE_SCALAR");
+    auto model_summary = [&](int bc) {
+      if (nmod <= 1 || sum_cap <= 0 || dist) return;
+      model_summary_kernel<<<dim3(G, nmod), kBlock, 0, S>>>(
+          N, nmod, modid.p, d.p, bc ? phat.p : p.p, bc ? qhat.p : nullptr, dscale.p, ord, st.p, bc, mpmx.p, mpmr.p,
+          mtickets.p, msum_dvmax.p, msum_locdv.p, msum_rmax.p, msum_locr.p);
+      launches += 1;
+    };
     auto enqueue_iteration = [&](int first) {
       HaloPush hp;
       HaloSrc hs;
@@ -1071,6 +1135,7 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
                                              ord, partial.p, pmx.p, pmr.p, tickets.p + TK_UPD,
                                              st.p, sp, r2.pull, r3.push);
         finalize_update(r3, 0);
+        model_summary(0);
         prof_end();
         launches += 3;
       } else {
@@ -1110,6 +1175,7 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
                                              ord, partial.p, pmx.p, pmr.p, tickets.p + TK_UPD,
                                              st.p, sp, r3.pull, r4.push);
         finalize_update(r4, 1);
+        model_summary(1);
         launches += 6;
       }
     };
@@ -1321,6 +1387,74 @@ int mf6gpu_solver_get_summary(mf6gpu_solver *s, int32_t cap, int32_t *itinner, d
       s->sum_locr.download(li.data(), c);
       const bool dist = s->halo && s->halo->active();
       for (size_t i = 0; i < c; i++) locr[i] = li[i] >= 0 ? (dist ? li[i] : s->A->perm[li[i]]) + 1 : 0;
+    }
+  });
+  return rc < 0 ? rc : count;
+}
+
+// convmodstart [nmod + 1]: first row of every model in the solution's row numbering, ascending, last = n
+int mf6gpu_solver_set_models(mf6gpu_solver *s, int32_t nmod, const int32_t *convmodstart, int32_t index_base) {
+  return guard([&] {
+    MF6_REQUIRE(s && convmodstart && nmod >= 1 && nmod <= 1024, "solver_set_models: bad argument");
+    MF6_REQUIRE(convmodstart[0] - index_base == 0 && convmodstart[nmod] - index_base == s->n,
+                "solver_set_models: convmodstart must span all rows");
+    std::vector<int> mid((size_t)s->n);
+    for (int im = 0; im < nmod; im++) {
+      MF6_REQUIRE(convmodstart[im + 1] >= convmodstart[im], "solver_set_models: convmodstart must ascend");
+      for (int r = convmodstart[im] - index_base; r < convmodstart[im + 1] - index_base; r++)
+        mid[(size_t)s->A->iperm[r]] = im;
+    }
+    s->nmod = nmod;
+    s->modid.upload(mid);
+    const size_t c = (size_t)std::max(s->sum_cap, 1) * (size_t)nmod;
+    s->msum_dvmax.alloc_zero(c);
+    s->msum_rmax.alloc_zero(c);
+    s->msum_locdv.alloc_zero(c);
+    s->msum_locr.alloc_zero(c);
+    s->mpmx.alloc_zero((size_t)nmod * (size_t)kMaxBlocks);
+    s->mpmr.alloc_zero((size_t)nmod * (size_t)kMaxBlocks);
+    s->mtickets.alloc_zero((size_t)nmod);
+  });
+}
+
+// per-model records of the iterations recorded so far: arrays [cap * nmod] laid out like the Fortran
+// convdvmax(nmod, niter) (model index fastest); locations 1-based original rows, 0 = none.  Returns the count.
+int mf6gpu_solver_get_model_summary(mf6gpu_solver *s, int32_t cap, double *convdvmax, int32_t *convlocdv,
+                                    double *convrmax, int32_t *convlocr) {
+  int count = 0;
+  int rc = guard([&] {
+    MF6_REQUIRE(s && s->nmod >= 1, "solver_get_model_summary: call mf6gpu_solver_set_models first");
+    MF6_CK(cudaMemcpy(s->h_st.p, s->st.p, sizeof(KState), cudaMemcpyDeviceToHost));
+    count = std::min(std::min(s->h_st.p->sum_count, s->sum_cap), (int)cap);
+    if (count <= 0) {
+      count = 0;
+      return;
+    }
+    const size_t c = (size_t)count * (size_t)s->nmod;
+    if (s->nmod == 1) {  // one model: its records are the solution-wide ones
+      std::vector<int> li((size_t)count);
+      if (convdvmax) s->sum_dvmax.download(convdvmax, (size_t)count);
+      if (convrmax) s->sum_rmax.download(convrmax, (size_t)count);
+      if (convlocdv) {
+        s->sum_locdv.download(li.data(), (size_t)count);
+        for (int i = 0; i < count; i++) convlocdv[i] = li[i] >= 0 ? s->A->perm[li[i]] + 1 : 0;
+      }
+      if (convlocr) {
+        s->sum_locr.download(li.data(), (size_t)count);
+        for (int i = 0; i < count; i++) convlocr[i] = li[i] >= 0 ? s->A->perm[li[i]] + 1 : 0;
+      }
+      return;
+    }
+    std::vector<int> li(c);
+    if (convdvmax) s->msum_dvmax.download(convdvmax, c);
+    if (convrmax) s->msum_rmax.download(convrmax, c);
+    if (convlocdv) {
+      s->msum_locdv.download(li.data(), c);
+      for (size_t i = 0; i < c; i++) convlocdv[i] = li[i] >= 0 ? s->A->perm[li[i]] + 1 : 0;
+    }
+    if (convlocr) {
+      s->msum_locr.download(li.data(), c);
+      for (size_t i = 0; i < c; i++) convlocr[i] = li[i] >= 0 ? s->A->perm[li[i]] + 1 : 0;
     }
   });
   return rc < 0 ? rc : count;

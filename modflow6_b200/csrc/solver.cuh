@@ -57,6 +57,13 @@ struct mf6gpu_solver {
   int sum_cap = 0;
   mf6::DevBuf<int> sum_itinner, sum_locdv, sum_locr;
   mf6::DevBuf<double> sum_dvmax, sum_rmax, sum_alpha, sum_omega;
+  // per-model records (ConvergenceSummaryType convdvmax(im, n) ...): optional, mf6gpu_solver_set_models
+  int nmod = 0;
+  mf6::DevBuf<int> modid;                 // [n] model of every final row
+  mf6::DevBuf<double> msum_dvmax, msum_rmax;   // [sum_cap * nmod], model index fastest
+  mf6::DevBuf<int> msum_locdv, msum_locr;
+  mf6::DevBuf<mf6::MaxLoc> mpmx, mpmr;    // [nmod * kMaxBlocks]
+  mf6::DevBuf<unsigned int> mtickets;     // [nmod]
   mf6::PinnedBuf<mf6::KState> h_st;
   mf6::PinnedBuf<int> h_flag;
   // stats of the last solve

@@ -31,6 +31,7 @@ SYMBOLS = [
     "mf6gpu_matrix_create_blocked", "mf6gpu_solution_get_permutation",
     "mf6gpu_solution_get_simvals", "mf6gpu_solution_get_storage", "mf6gpu_solution_get_nodes",
     "mf6gpu_ordering_compute", "mf6gpu_model_elimination_order",
+    "mf6gpu_solver_set_models", "mf6gpu_solver_get_model_summary",
 ]
 
 _lib = None
@@ -78,6 +79,8 @@ def load():
     L.mf6gpu_solver_destroy.argtypes = [vp]
     L.mf6gpu_solver_solve.argtypes = [vp, i32, i32, pf64, pf64, pi32, pi32]
     L.mf6gpu_solver_get_summary.argtypes = [vp, i32, pi32, pf64, pi32, pf64, pi32, pf64, pf64]
+    L.mf6gpu_solver_set_models.argtypes = [vp, i32, pi32, i32]
+    L.mf6gpu_solver_get_model_summary.argtypes = [vp, i32, pf64, pi32, pf64, pi32]
     L.mf6gpu_solver_stat.restype = f64
     L.mf6gpu_solver_stat.argtypes = [vp, C.c_int]
     L.mf6gpu_solver_profile.argtypes = [vp, i32]

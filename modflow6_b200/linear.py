@@ -166,6 +166,22 @@ class GpuLinearSolver:
                                                     T.ptr_f64(a["omega"])))
         return {k: v[:c] for k, v in a.items()}
 
+    def set_models(self, convmodstart):
+        """per-model records: convmodstart = 0-based first row of every model, then n (NumericalSolution.f90:409-416)"""
+        cms = T.as_i32(convmodstart)
+        self.nmod = cms.size - 1
+        check(self._L.mf6gpu_solver_set_models(self.h, self.nmod, T.ptr_i32(cms), 0))
+
+    def model_summary(self):
+        """{convdvmax, convlocdv, convrmax, convlocr}: arrays [iterations, nmod] (locations 1-based, 0 = none)"""
+        cap = max(self.nitermax, 1)
+        a = dict(convdvmax=np.zeros(cap * self.nmod), convlocdv=np.zeros(cap * self.nmod, np.int32),
+                 convrmax=np.zeros(cap * self.nmod), convlocr=np.zeros(cap * self.nmod, np.int32))
+        c = check(self._L.mf6gpu_solver_get_model_summary(self.h, cap, T.ptr_f64(a["convdvmax"]),
+                                                          T.ptr_i32(a["convlocdv"]), T.ptr_f64(a["convrmax"]),
+                                                          T.ptr_i32(a["convlocr"])))
+        return {k: v[:c * self.nmod].reshape(c, self.nmod) for k, v in a.items()}
+
     def stat(self, what):
         return self._L.mf6gpu_solver_stat(self.h, what)
 

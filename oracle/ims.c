@@ -341,7 +341,51 @@ static void sum_record(orc_summary *s, int iiter, double dv, int locdv, double r
   }
 }
 
-/* ImsLinearBase.f90:30-240 (single model: CONVNMOD = 1) */
+/* per-model maxima of one inner iteration (ImsLinearBase.f90:143-176): the same strict ">" rule per model */
+typedef struct {
+  int nmod;
+  const int *modid, *lorder;
+  double dv[64], r[64];
+  int locdv[64], locr[64];
+} modtrack;
+
+static void mt_begin(modtrack *t, const orc_summary *sum, const orc_imslinear *L) {
+  t->nmod = (sum && sum->nmod > 0 && sum->nmod <= 64 && sum->modid) ? sum->nmod : 0;
+  t->modid = sum ? sum->modid : NULL;
+  t->lorder = L->use_perm ? L->lorder : NULL;
+  for (int im = 0; im < t->nmod; im++) {
+    t->dv[im] = t->r[im] = 0.0;
+    t->locdv[im] = t->locr[im] = -1;
+  }
+}
+
+static void mt_row(modtrack *t, int i, double tv, double rv) {
+  if (!t->nmod) return;
+  const int o = t->lorder ? t->lorder[i] : i, im = t->modid[o];
+  if (fabs(tv) > fabs(t->dv[im])) {
+    t->dv[im] = tv;
+    t->locdv[im] = o;
+  }
+  if (fabs(rv) > fabs(t->r[im])) {
+    t->r[im] = rv;
+    t->locr[im] = o;
+  }
+}
+
+static void mt_record(const modtrack *t, orc_summary *s) {
+  if (!s || !t->nmod) return;
+  const int k = s->count;
+  if (s->cap > 0 && k <= s->cap)
+    for (int im = 0; im < t->nmod; im++) {
+      const size_t q = (size_t)(k - 1) * (size_t)t->nmod + (size_t)im;
+      s->mdvmax[q] = t->dv[im];
+      s->mlocdv[q] = t->locdv[im];
+      s->mrmax[q] = t->r[im];
+      s->mlocr[q] = t->locr[im];
+    }
+}
+
+/* ImsLinearBase.f90:30-240 */
 static int ims_cg(orc_imslinear *L, int *icnvg, int itmax, const int *ia,
                   const int *ja, const double *a, double *x, double *b,
                   orc_summary *sum) {
@@ -367,8 +411,11 @@ static int ims_cg(orc_imslinear *L, int *icnvg, int itmax, const int *ia,
     alpha = rho / denominator;
     double deltax = 0.0, rmax = 0.0, l2norm = 0.0;
     int xloc = -1, rloc = -1;
+    modtrack mt;
+    mt_begin(&mt, sum, L);
     for (int i = 0; i < n; i++) {
       double tv = alpha * p[i];
+      const double dvi = tv;
       x[i] = x[i] + tv;
       if (fabs(tv) > fabs(deltax)) {
         deltax = tv;
@@ -381,10 +428,12 @@ static int ims_cg(orc_imslinear *L, int *icnvg, int itmax, const int *ia,
         rmax = tv;
         rloc = i;
       }
+      mt_row(&mt, i, dvi, tv);
       l2norm = l2norm + tv * tv;
     }
     l2norm = sqrt(l2norm);
     sum_record(sum, iiter, deltax, xloc, rmax, rloc, alpha, 0.0);
+    mt_record(&mt, sum);
     double rcnvg = (s->icnvgopt == 2 || s->icnvgopt == 3 || s->icnvgopt == 4) ? l2norm : rmax;
     orc_testcnvg(s->icnvgopt, icnvg, innerit, deltax, rcnvg, L->l2norm0,
                  L->epfact, s->dvclose, s->rclose);
@@ -439,10 +488,13 @@ static int ims_bcgs(orc_imslinear *L, int *icnvg, int itmax, const int *ia,
     omega = numerator / denominator;
     double deltax = 0.0, rmax = 0.0, l2norm = 0.0;
     int xloc = -1, rloc = -1;
+    modtrack mt;
+    mt_begin(&mt, sum, L);
     for (int i = 0; i < n; i++) {
       double tv = alpha * phat[i] + omega * qhat[i];
       x[i] = x[i] + tv;
       if (iscl != 0) tv = tv * dscale[i];
+      const double dvi = tv;
       if (fabs(tv) > fabs(deltax)) {
         deltax = tv;
         xloc = i;
@@ -454,10 +506,12 @@ static int ims_bcgs(orc_imslinear *L, int *icnvg, int itmax, const int *ia,
         rmax = tv;
         rloc = i;
       }
+      mt_row(&mt, i, dvi, tv);
       l2norm = l2norm + tv * tv;
     }
     l2norm = sqrt(l2norm);
     sum_record(sum, iiter, deltax, xloc, rmax, rloc, alpha, omega);
+    mt_record(&mt, sum);
     double rcnvg = (s->icnvgopt == 2 || s->icnvgopt == 3 || s->icnvgopt == 4) ? l2norm : rmax;
     orc_testcnvg(s->icnvgopt, icnvg, innerit, deltax, rcnvg, L->l2norm0,
                  L->epfact, s->dvclose, s->rclose);

@@ -79,6 +79,14 @@ typedef struct {
   int *locr;
   double *alpha;
   double *omega;
+  /* per-model records (ConvergenceSummaryType convdvmax(im, n) ..., ImsLinearBase.f90:143-197): optional.
+   * nmod models; modid[row] = model of every ORIGINAL row; arrays [cap * nmod], model index fastest */
+  int nmod;
+  const int *modid;
+  double *mdvmax;
+  double *mrmax;
+  int *mlocdv;   /* 0-based original row, -1 = none */
+  int *mlocr;
 } orc_summary;
 
 typedef struct {

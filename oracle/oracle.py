@@ -28,7 +28,8 @@ def build(force=False):
 class Summary(C.Structure):
     _fields_ = [("cap", C.c_int), ("count", C.c_int), ("itinner", T.p_i32), ("dvmax", T.p_f64),
                 ("rmax", T.p_f64), ("locdv", T.p_i32), ("locr", T.p_i32), ("alpha", T.p_f64),
-                ("omega", T.p_f64)]
+                ("omega", T.p_f64), ("nmod", C.c_int), ("modid", T.p_i32), ("mdvmax", T.p_f64),
+                ("mrmax", T.p_f64), ("mlocdv", T.p_i32), ("mlocr", T.p_i32)]
 
 
 def lib():
@@ -109,7 +110,8 @@ def amux(ia, ja, a, x):
 class OracleIms:
     """imslinear_ar + imslinear_ap (ImsLinear.f90:111-339, 617-750)."""
 
-    def __init__(self, ia, ja, settings, perm=None, summary_cap=0):
+    def __init__(self, ia, ja, settings, perm=None, summary_cap=0, convmodstart=None):
+        """convmodstart (0-based first row of every model + n): per-model records like ConvergenceSummaryType"""
         self.ia, self.ja = T.as_i32(ia), T.as_i32(ja)
         self.n = self.ia.size - 1
         self.settings = settings
@@ -126,6 +128,17 @@ class OracleIms:
             self.sum = Summary(summary_cap, 0, T.ptr_i32(a["itinner"]), T.ptr_f64(a["dvmax"]),
                                T.ptr_f64(a["rmax"]), T.ptr_i32(a["locdv"]), T.ptr_i32(a["locr"]),
                                T.ptr_f64(a["alpha"]), T.ptr_f64(a["omega"]))
+            self.nmod = 0
+            if convmodstart is not None:
+                cms = np.asarray(convmodstart, dtype=np.int64)
+                self.nmod = cms.size - 1
+                self._modid = T.as_i32(np.repeat(np.arange(self.nmod), np.diff(cms)))
+                c = summary_cap * self.nmod
+                a.update(mdvmax=np.zeros(c), mrmax=np.zeros(c), mlocdv=np.zeros(c, np.int32), mlocr=np.zeros(c, np.int32))
+                self.sum.nmod = self.nmod
+                self.sum.modid = T.ptr_i32(self._modid)
+                self.sum.mdvmax, self.sum.mrmax = T.ptr_f64(a["mdvmax"]), T.ptr_f64(a["mrmax"])
+                self.sum.mlocdv, self.sum.mlocr = T.ptr_i32(a["mlocdv"]), T.ptr_i32(a["mlocr"])
         else:
             self.sum = None
 
@@ -141,7 +154,10 @@ class OracleIms:
 
     def summary(self):
         c = min(self.sum.count, self.cap)
-        return {k: v[:c].copy() for k, v in self._arr.items()}
+        out = {}
+        for k, v in self._arr.items():
+            out[k] = v[:c * self.nmod].reshape(c, self.nmod).copy() if k.startswith("m") else v[:c].copy()
+        return out
 
     def __del__(self):
         if getattr(self, "h", None):

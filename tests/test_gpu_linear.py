@@ -241,3 +241,42 @@ def test_c_host_program(gpu, tmp_path):
     r = subprocess.run([_build_c_host(tmp_path)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "converged 1" in r.stdout
+
+
+@pytest.mark.parametrize("ordering", [T.ORDER_NATURAL, T.ORDER_MULTICOLOR, T.ORDER_BLOCK_MULTICOLOR])
+@pytest.mark.parametrize("meth", [1, 2])
+def test_per_model_convergence_summary(system, ordering, meth):
+    """ConvergenceSummaryType per model (ImsLinearBase.f90:143-197, NumericalSolution.f90:409-416): the rows are
+    cut into three "models" by CONVMODSTART; dvmax / rmax and their locations per model and inner iteration equal
+    the oracle's, and their overall maximum is the solution-wide record"""
+    from modflow6_b200.linear import GpuLinearSolver, GpuMatrix
+    from oracle.oracle import OracleIms
+    m, a, b, x0 = system
+    n = m.nodes
+    cms = np.array([0, 700, 1500, n])
+    ims = T.ImsSettings.make(dvclose=1e-9, rclose=1e-7, iter1=600, ilinmeth=meth, gpu_ordering=ordering)
+    A = GpuMatrix(m.ia, m.ja, 0, ordering)
+    A.update(a)
+    S = GpuLinearSolver(A, ims, nitermax=700)
+    S.set_models(cms)
+    xg = x0.copy()
+    it, cv = S.solve(1, b, xg)
+    O = OracleIms(m.ia, m.ja, ims, perm=None if ordering == T.ORDER_NATURAL else A.permutation(), summary_cap=700,
+                  convmodstart=cms)
+    xo = x0.copy()
+    ito, cvo = O.solve(a, xo, b)
+    assert cv == 1 and cvo == 1
+    sg, so, ms = S.convergence_summary(), O.summary(), S.model_summary()
+    k = min(8, it, ito)
+    assert ms["convdvmax"].shape == (it, 3)
+    assert np.allclose(ms["convdvmax"][:k], so["mdvmax"][:k], rtol=1e-6, atol=1e-13)
+    assert np.allclose(ms["convrmax"][:k], so["mrmax"][:k], rtol=1e-6, atol=1e-13)
+    assert np.array_equal(ms["convlocdv"][:k], so["mlocdv"][:k] + 1)
+    assert np.array_equal(ms["convlocr"][:k], so["mlocr"][:k] + 1)
+    # every location lies inside its model; the largest per-model value is the solution-wide one
+    for im in range(3):
+        loc = ms["convlocdv"][:, im]
+        assert np.all((loc > cms[im]) & (loc <= cms[im + 1]))
+    big = np.abs(ms["convdvmax"]).argmax(axis=1)
+    assert np.array_equal(ms["convdvmax"][np.arange(it), big], sg["dvmax"][:it])
+    assert np.array_equal(ms["convlocdv"][np.arange(it), big], sg["locdv"][:it])
