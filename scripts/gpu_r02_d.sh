@@ -2,7 +2,7 @@
 # round 2, GPU call D (2 GPUs): split-model tests with the fused exchange (per-CTA halo push), N=2 weak fused vs
 # unfused, N=2 strong, new single-GPU tests (DRN depth, K22 anisotropy)
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_solution.py tests/test_gpu_linear.py -m gpu -q -x -k "drn or npf05 or k22 or krylov" > gpurun_out/r02d_pytest1.log 2>&1; echo "rc=$?" >> gpurun_out/r02d_pytest1.log
+timeout 600 python -m pytest tests/test_gpu_solution.py tests/test_gpu_linear.py -m gpu -q -x -k "drn or npf05 or k22 or krylov or per_model" > gpurun_out/r02d_pytest1.log 2>&1; echo "rc=$?" >> gpurun_out/r02d_pytest1.log
 tail -6 gpurun_out/r02d_pytest1.log
 timeout 900 python -m pytest tests/test_gpu_distributed.py -m gpu -q > gpurun_out/r02d_pytest_dist.log 2>&1; echo "rc=$?" >> gpurun_out/r02d_pytest_dist.log
 tail -6 gpurun_out/r02d_pytest_dist.log
