@@ -950,8 +950,20 @@ void mf6gpu_solver::reduce_finalize(int mode, double *out, int bcgs) {
   launches += 2;
 }
 
+int mf6gpu_solver::precond(const double *rin, double *dd, const mf6::IluDotArgs *dot) {
+  if (ilut) return ilut->apply(rin, dd, &st.p->done, stream);
+  return ilu0_apply(*A, lu.p, rin, dd, &st.p->done, stream, dot);
+}
+
 // ims_base_pcu, ImsLinearBase.f90:808-858
 int mf6gpu_solver::factor() {
+  if (ilut) {  // ILUT / MILUT: sequential factorisation on the host, see ilut.cuh
+    prof_begin(PC_FACTOR);
+    const int c = ilut->factor(*A, A->val.p, s.relax, stream);
+    prof_end();
+    launches += 1;
+    return c;
+  }
   int ipcflag = 0, icount = 0;
   double delta = 0.0;
   for (;;) {
@@ -1032,7 +1044,7 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
   }
   int innerit = 0;
   const int *ord = A->ord_ptr();
-  const bool fuse_dot = (A->nlevels <= 16);
+  const bool fuse_dot = (A->nlevels <= 16) && !ilut;
   IluDotArgs idot;
   idot.partial = ilu_partial.p;
   idot.cta_sums = partial.p + 2 * kMaxBlocks;
@@ -1100,11 +1112,11 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
         if (fuse_dot) {
           // z = M^-1 d with rho = d.z (and beta = rho/rho0) accumulated by the same launches
           idot.push = r1.push;
-          launches += ilu0_apply(*A, lu.p, d.p, z.p, &st.p->done, S, &idot);
+          launches += precond(d.p, z.p, &idot);
           if (!fused) reduce_finalize(FIN_CG_RHO, nullptr, 0);
           prof_end();
         } else {
-          launches += ilu0_apply(*A, lu.p, d.p, z.p, &st.p->done, S);
+          launches += precond(d.p, z.p);
           prof_end();
           prof_begin(PC_DOT);
           dot_kernel<<<G, kBlock, 0, S>>>(N, d.p, z.p, partial.p, tickets.p + TK_DOT, st.p,
@@ -1145,7 +1157,7 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
         if (!fused) reduce_finalize(FIN_BCGS_RHO, nullptr, 1);
         bcgs_p_kernel<<<G, kBlock, 0, S>>>(N, d.p, v.p, p.p, st.p, first, r1.pull);
         prof_begin(PC_ILU);
-        launches += ilu0_apply(*A, lu.p, p.p, phat.p, &st.p->done, S);
+        launches += precond(p.p, phat.p);
         halo_round(hp, hs, phat.p, false);
         prof_end();
         const DistRound r2 = round();
@@ -1156,7 +1168,7 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
         prof_end();
         bcgs_q_kernel<<<G, kBlock, 0, S>>>(N, d.p, v.p, q.p, st.p, r2.pull);
         prof_begin(PC_ILU);
-        launches += ilu0_apply(*A, lu.p, q.p, qhat.p, &st.p->done, S);
+        launches += precond(q.p, qhat.p);
         halo_round(hp, hs, qhat.p, false);
         prof_end();
         const DistRound r3 = round();
@@ -1255,8 +1267,7 @@ static void check_settings(mf6gpu_ims_settings &s) {
   // the same spirit as petsc_check_settings (PetscSolver.F90:123-154): options the
   // backend cannot honour are rejected (ILUT) or downgraded (reordering)
   MF6_REQUIRE(s.ilinmeth == 1 || s.ilinmeth == 2, "solver: LINEAR_ACCELERATION must be CG (1) or BICGSTAB (2)");
-  MF6_REQUIRE(s.level <= 0 && s.droptol <= 0.0,
-              "solver: ILUT/MILUT (PRECONDITIONER_LEVELS / DROP_TOLERANCE) is not available on the GPU path");
+  MF6_REQUIRE(s.level >= 0 && s.droptol >= 0.0, "solver: PRECONDITIONER_LEVELS / DROP_TOLERANCE must be >= 0");
   MF6_REQUIRE(s.iscl >= 0 && s.iscl <= 2, "solver: SCALING_METHOD must be NONE (0), DIAGONAL (1) or L2NORM (2)");
   MF6_REQUIRE(s.relax >= 0.0 && s.relax <= 1.0, "solver: RELAXATION_FACTOR must be in [0,1]");
   MF6_REQUIRE(s.north >= 0, "solver: NUMBER_ORTHOGONALIZATIONS must be >= 0");
@@ -1275,11 +1286,17 @@ int mf6gpu_solver_create(mf6gpu_matrix *m, const mf6gpu_ims_settings *settings,
       s->A = m;
       s->s = *settings;
       check_settings(s->s);
-      s->ipc = (s->s.relax > 0.0) ? 2 : 1;  // ImsLinear.f90:178-185
+      // ImsLinear.f90:178-185: LEVEL > 0 or DROPTOL > 0 selects ILUT, RELAX > 0 the modified variants
+      s->ipc = ((s->s.level > 0 || s->s.droptol > 0.0) ? 3 : 1) + ((s->s.relax > 0.0) ? 1 : 0);
       s->n = m->n;
       s->stream = m->stream;
       const size_t n = (size_t)m->n_ext;  // vectors carry the halo region behind the owned rows
-      s->lu.alloc_zero((size_t)m->nslots);
+      if (s->ipc >= 3) {
+        s->ilut.reset(new mf6::IlutPlan());
+        s->ilut->build(*m, s->s.level, s->s.droptol);
+      } else {
+        s->lu.alloc_zero((size_t)m->nslots);
+      }
       s->x.alloc_zero(n);
       s->b.alloc_zero(n);
       s->d.alloc_zero(n);
@@ -1509,7 +1526,10 @@ int mf6gpu_solver_apply_preconditioner(mf6gpu_solver *s, const double *r, double
     cudaStream_t S = s->stream;
     MF6_CK(cudaMemcpyAsync(s->hb.p, r, nb, cudaMemcpyHostToDevice, S));
     launch_gather(s->n, s->A->d_perm.p, s->hb.p, s->d.p, S);
-    ilu0_apply(*s->A, s->lu.p, s->d.p, s->z.p, nullptr, S);
+    if (s->ilut)
+      s->ilut->apply(s->d.p, s->z.p, nullptr, S);
+    else
+      ilu0_apply(*s->A, s->lu.p, s->d.p, s->z.p, nullptr, S);
     launch_scatter(s->n, s->A->d_perm.p, s->z.p, s->hx.p, S);
     MF6_CK(cudaGetLastError());
     MF6_CK(cudaMemcpyAsync(z, s->hx.p, nb, cudaMemcpyDeviceToHost, S));

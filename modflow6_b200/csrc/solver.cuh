@@ -1,6 +1,8 @@
 // solver.cuh -- device-resident IMS linear solver (LinearSolverBaseType replacement)
 #pragma once
 #include "ilu0.cuh"
+#include "ilut.cuh"
+#include <memory>
 #include "comm.cuh"
 
 namespace mf6 {
@@ -38,7 +40,10 @@ struct mf6gpu_solver {
   mf6::DevBuf<double> red_all;    // [nranks * 8] gathered RedRec
   void reduce_finalize(int mode, double *out, int bcgs);  // all-gather + global finalize (no-op on 1 GPU)
   mf6gpu_ims_settings s{};
-  int ipc = 1;
+  int ipc = 1;                            // 1 ILU0, 2 MILU0, 3 ILUT, 4 MILUT (ImsLinear.f90:178-185)
+  std::unique_ptr<mf6::IlutPlan> ilut;    // IPC 3 / 4
+  // z = M^-1 r with the active preconditioner; `dot` (fused rho) only with ILU0 / MILU0
+  int precond(const double *rin, double *d, const mf6::IluDotArgs *dot = nullptr);
   cudaStream_t stream = 0;
   int n = 0;
   // work vectors (final numbering)

@@ -281,10 +281,6 @@ def read_ims(path, warnings):
             raise Mf6InputError(f"{path}: LINEAR option {k} is not supported")
     # the policy of petsc_check_settings (PetscSolver.F90:123-154): what the backend cannot honour is
     # downgraded with a warning the caller can print
-    if ims["level"] > 0 or ims["droptol"] > 0.0:
-        warnings.append("PRECONDITIONER_LEVELS / DROP_TOLERANCE (ILUT) are not available on the GPU path: "
-                        "ILU0/MILU0 is used instead")
-        ims["level"], ims["droptol"] = 0, 0.0
     if ims["iord"] != 0:
         warnings.append("REORDERING_METHOD is replaced by the GPU level ordering")
         ims["iord"] = 0

@@ -385,6 +385,14 @@ static void mt_record(const modtrack *t, orc_summary *s) {
     }
 }
 
+/* APPLY PRECONDITIONER (ImsLinearBase.f90:104-114): ILU0 / MILU0 or ILUT / MILUT */
+static void precond(const orc_imslinear *L, const double *r, double *z) {
+  if (L->pct)
+    orc_lusol(L->pct, r, z);
+  else
+    orc_ilu0a(L->pc, r, z);
+}
+
 /* ImsLinearBase.f90:30-240 */
 static int ims_cg(orc_imslinear *L, int *icnvg, int itmax, const int *ia,
                   const int *ja, const double *a, double *x, double *b,
@@ -397,7 +405,7 @@ static int ims_cg(orc_imslinear *L, int *icnvg, int itmax, const int *ia,
   for (int iiter = 1; iiter <= itmax; iiter++) {
     innerit++;
     if (sum) sum->count++;
-    orc_ilu0a(L->pc, d, z);
+    precond(L, d, z);
     rho = orc_ddot(n, d, z);
     if (iiter == 1) {
       for (int i = 0; i < n; i++) p[i] = z[i];
@@ -474,13 +482,13 @@ static int ims_bcgs(orc_imslinear *L, int *icnvg, int itmax, const int *ia,
       beta = (rho / rho0) * (alpha0 / omega0);
       for (int i = 0; i < n; i++) p[i] = d[i] + beta * (p[i] - omega0 * v[i]);
     }
-    orc_ilu0a(L->pc, p, phat);
+    precond(L, p, phat);
     orc_amux(n, phat, v, a, ja, ia);
     double denominator = orc_ddot(n, dhat, v);
     denominator = denominator + dsign(DPREC, denominator);
     alpha = rho / denominator;
     for (int i = 0; i < n; i++) q[i] = d[i] - alpha * v[i];
-    orc_ilu0a(L->pc, q, qhat);
+    precond(L, q, qhat);
     orc_amux(n, qhat, t, a, ja, ia);
     double numerator = orc_ddot(n, t, q);
     denominator = orc_ddot(n, t, t);
@@ -591,6 +599,9 @@ orc_imslinear *orc_ims_create(int n, int nja, const int *ia, const int *ja,
   } else {
     L->pc = orc_ilu0_create(n, nja, ia, ja);
   }
+  /* ImsLinear.f90:178-185: LEVEL > 0 or DROPTOL > 0 selects ILUT (MILUT with RELAX > 0) */
+  if (L->s.level > 0 || L->s.droptol > 0.0)
+    L->pct = orc_ilut_create(n, nja, L->use_perm ? L->iaro : ia, L->s.level);
   return L;
 }
 
@@ -619,10 +630,15 @@ void orc_ims_set_blocks(orc_imslinear *L, const int *block) {
   L->iaf[n] = pos;
   orc_ilu0_destroy(L->pc);
   L->pc = orc_ilu0_create(n, pos, L->iaf, L->jaf);
+  if (L->pct) {
+    orc_ilut_destroy(L->pct);
+    L->pct = orc_ilut_create(n, pos, L->iaf, L->s.level);
+  }
 }
 
 void orc_ims_destroy(orc_imslinear *L) {
   if (!L) return;
+  orc_ilut_destroy(L->pct);
   free(L->iaf); free(L->jaf); free(L->fmap); free(L->af);
   free(L->d); free(L->p); free(L->q); free(L->z); free(L->t); free(L->v);
   free(L->dhat); free(L->phat); free(L->qhat); free(L->dscale); free(L->dscale2);
@@ -677,7 +693,12 @@ int orc_ims_apply(orc_imslinear *L, double *amat, double *x, double *rhs,
   if (L->use_blocks) {
     const int nf = L->iaf[n];
     for (int k = 0; k < nf; k++) L->af[k] = a0[L->fmap[k]];
-    L->npivfix = orc_pcu(L->pc, L->af, L->iaf, L->jaf, s->relax);
+    if (L->pct)
+      L->npivfix = orc_pcu_ilut(L->pct, L->af, L->iaf, L->jaf, s->level, s->droptol, s->relax, &L->ilut_ierr);
+    else
+      L->npivfix = orc_pcu(L->pc, L->af, L->iaf, L->jaf, s->relax);
+  } else if (L->pct) {
+    L->npivfix = orc_pcu_ilut(L->pct, a0, ia0, ja0, s->level, s->droptol, s->relax, &L->ilut_ierr);
   } else {
     L->npivfix = orc_pcu(L->pc, a0, ia0, ja0, s->relax);
   }

@@ -69,6 +69,23 @@ void orc_scale(int iopt, int iscl, int n, const int *ia, const int *ja,
                double *dscale2);
 
 /* per-inner-iteration record (ConvergenceSummary.f90:13-34, 1 model) */
+/* ILUT / MILUT (SPARSKIT2 ilut.f90 as vendored and modified by the reference), see ilut.c */
+typedef struct {
+  int n, iwk;
+  double *alu; /* [iwk+1] MSR values, 1-based: 1..n inverse pivots, n+2.. L and U rows */
+  int *jlu;    /* [iwk+1] 1..n+1 row pointers, then columns (1-based) */
+  int *ju;     /* [n+1] start of the U part of every row */
+  double *w;
+  int *jw;
+} orc_ilut;
+orc_ilut *orc_ilut_create(int n, int nja, const int *ia, int lfil);
+void orc_ilut_destroy(orc_ilut *p);
+int orc_ilut_factor(orc_ilut *P, const double *a, const int *ja, const int *ia, int lfil, double droptol,
+                    double relax, int *izero, double delta);
+int orc_pcu_ilut(orc_ilut *P, const double *amat, const int *ia, const int *ja, int lfil, double droptol,
+                 double relax, int *ierr_out);
+void orc_lusol(const orc_ilut *P, const double *y, double *x);
+
 typedef struct {
   int cap;     /* capacity of the arrays below (0 = do not record) */
   int count;   /* iter_cnt */
@@ -101,6 +118,8 @@ typedef struct {
   int *iaro, *jaro;
   double *aro;
   orc_ilu0 *pc;
+  orc_ilut *pct; /* IPC 3/4 (PRECONDITIONER_LEVELS > 0 or DROP_TOLERANCE > 0, ImsLinear.f90:178-185) */
+  int ilut_ierr;
   double *d, *p, *q, *z, *t, *v, *dhat, *phat, *qhat;
   double *dscale, *dscale2;
   double *xp, *bp; /* permuted x / rhs */

@@ -18,7 +18,7 @@ _LIB = None
 
 def build(force=False):
     so = os.path.join(_HERE, "liboracle_mf6.so")
-    srcs = [os.path.join(_HERE, f) for f in ("ims.c", "gwf_solution.c", "mf6_oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("ims.c", "ilut.c", "gwf_solution.c", "mf6_oracle.h")]
     srcs.append(os.path.join(_HERE, "..", "include", "mf6gpu_types.h"))
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs if os.path.exists(s)):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
@@ -53,6 +53,12 @@ def lib():
         L.orc_pcu.restype = C.c_int
         L.orc_pcu.argtypes = [vp, T.p_f64, T.p_i32, T.p_i32, C.c_double]
         L.orc_ilu0a.argtypes = [vp, T.p_f64, T.p_f64]
+        L.orc_ilut_create.restype = vp
+        L.orc_ilut_create.argtypes = [C.c_int, C.c_int, T.p_i32, C.c_int]
+        L.orc_ilut_destroy.argtypes = [vp]
+        L.orc_pcu_ilut.restype = C.c_int
+        L.orc_pcu_ilut.argtypes = [vp, T.p_f64, T.p_i32, T.p_i32, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_int)]
+        L.orc_lusol.argtypes = [vp, T.p_f64, T.p_f64]
         L.orc_sln_create.restype = vp
         L.orc_sln_create.argtypes = [C.POINTER(T.GwfModelStruct), C.POINTER(T.SlnSettings), C.POINTER(T.ImsSettings), T.p_i32]
         L.orc_sln_destroy.argtypes = [vp]
@@ -97,6 +103,37 @@ class OracleIlu0:
     def __del__(self):
         if getattr(self, "h", None):
             lib().orc_ilu0_destroy(self.h)
+            self.h = None
+
+
+class OracleIlut:
+    """ilut + the pcu delta loop + lusol (sparskit2/ilut.f90, ImsLinearBase.f90:761-864) on a 0-based CSR whose
+    rows store the diagonal first, then ascending columns"""
+
+    def __init__(self, ia, ja, level, droptol):
+        self.ia, self.ja = T.as_i32(ia), T.as_i32(ja)
+        self.n = self.ia.size - 1
+        self.level, self.droptol = int(level), float(droptol)
+        self.h = lib().orc_ilut_create(self.n, self.ja.size, T.ptr_i32(self.ia), self.level)
+
+    def factor(self, amat, relax):
+        amat = T.as_f64(amat)
+        ierr = C.c_int(0)
+        ic = lib().orc_pcu_ilut(self.h, T.ptr_f64(amat), T.ptr_i32(self.ia), T.ptr_i32(self.ja), self.level,
+                                self.droptol, float(relax), C.byref(ierr))
+        if ierr.value != 0:
+            raise RuntimeError(f"ILUT ierr = {ierr.value}")
+        return ic
+
+    def apply(self, r):
+        r = T.as_f64(r)
+        d = np.zeros_like(r)
+        lib().orc_lusol(self.h, T.ptr_f64(r), T.ptr_f64(d))
+        return d
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_ilut_destroy(self.h)
             self.h = None
 
 

@@ -280,3 +280,51 @@ def test_per_model_convergence_summary(system, ordering, meth):
     big = np.abs(ms["convdvmax"]).argmax(axis=1)
     assert np.array_equal(ms["convdvmax"][np.arange(it), big], sg["dvmax"][:it])
     assert np.array_equal(ms["convlocdv"][np.arange(it), big], sg["locdv"][:it])
+
+
+@pytest.mark.parametrize("ordering", [T.ORDER_NATURAL, T.ORDER_MULTICOLOR, T.ORDER_BLOCK_MULTICOLOR])
+@pytest.mark.parametrize("level,droptol,relax", [(5, 1e-4, 0.0), (3, 1e-3, 0.97), (0, 1e-3, 0.0), (7, 0.0, 0.0)])
+def test_ilut_factor_and_apply_bitexact(system, ordering, level, droptol, relax):
+    """ILUT / MILUT (IPC 3/4, sparskit2/ilut.f90): the factor the library computes (host, sequential) and the
+    device level-scheduled lusol equal the oracle bit for bit on the identically permuted system"""
+    from modflow6_b200.linear import GpuLinearSolver, GpuMatrix
+    from oracle.oracle import OracleIlut
+    m, a, b, x0 = system
+    A = GpuMatrix(m.ia, m.ja, 0, ordering)
+    A.update(a)
+    S = GpuLinearSolver(A, T.ImsSettings.make(relax=relax, level=level, droptol=droptol, gpu_ordering=ordering))
+    nfix = S.factor()
+    perm = A.permutation()
+    ia2, ja2, a2 = permute_csr(m.ia, m.ja, a, perm)
+    O = OracleIlut(ia2, ja2, level, droptol)
+    assert O.factor(a2, relax) == nfix
+    r = np.random.default_rng(5).normal(size=m.nodes)
+    z = S.apply_preconditioner(r)
+    zo = np.empty_like(r)
+    zo[perm] = O.apply(r[perm])
+    assert np.array_equal(z, zo)
+
+
+@pytest.mark.parametrize("ordering", [T.ORDER_NATURAL, T.ORDER_BLOCK_MULTICOLOR])
+def test_ilut_bicgstab_matches_oracle(system, ordering):
+    """the COMPLEX preset of the reference (LEVEL 5, DROPTOL 1e-4, BICGSTAB, NORTH 2; ImsLinearSettings.f90:103-113)"""
+    from modflow6_b200.linear import GpuLinearSolver, GpuMatrix
+    from oracle.oracle import OracleIms
+    m, a, b, x0 = system
+    ims = T.ImsSettings.make(dvclose=1e-9, rclose=1e-7, iter1=500, ilinmeth=2, level=5, droptol=1e-4, north=2,
+                             gpu_ordering=ordering)
+    A = GpuMatrix(m.ia, m.ja, 0, ordering)
+    A.update(a)
+    S = GpuLinearSolver(A, ims)
+    xg = x0.copy()
+    it, cv = S.solve(1, b, xg)
+    O = OracleIms(m.ia, m.ja, ims, perm=None if ordering == T.ORDER_NATURAL else A.permutation())
+    xo = x0.copy()
+    ito, cvo = O.solve(a, xo, b)
+    assert cv == 1 and cvo == 1
+    assert np.abs(xg - xo).max() <= 0.1 * 1e-7
+    assert abs(it - ito) <= max(2, ito // 10)
+    ims0 = T.ImsSettings.make(dvclose=1e-9, rclose=1e-7, iter1=500, ilinmeth=2, gpu_ordering=ordering)
+    x1 = x0.copy()
+    it0, _ = GpuLinearSolver(A, ims0).solve(1, b, x1)
+    assert it < it0

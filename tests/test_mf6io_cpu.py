@@ -100,7 +100,7 @@ def test_reader_rejects_what_the_path_cannot_honour(tmp_path):
     mf6_inputs.write_gwf(d, "m", (1, 2, 2), 1.0, 1.0, 0.0, [-1.0], 1.0, chd={1: [((1, 1, 1), 1.0)]})
     mf6_inputs.write_sim(d, ["m"], [(1.0, 1, 1.0)], "BEGIN linear\n  PRECONDITIONER_LEVELS 2\nEND linear\n")
     sim = mf6io.read_simulation(d)
-    assert sim.ims.level == 0 and any("ILUT" in w for w in sim.warnings)      # downgraded with a warning
+    assert sim.ims.level == 2 and not any("ILUT" in w for w in sim.warnings)      # ILUT is honoured (IPC 3)
     npf = (tmp_path / "m.npf").read_text()
     (tmp_path / "m.npf").write_text(npf.replace("SAVE_FLOWS", "SAVE_FLOWS\n  XT3D"))
     with pytest.raises(mf6io.Mf6InputError, match="XT3D"):

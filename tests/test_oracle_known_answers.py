@@ -382,3 +382,55 @@ def test_hy_eff_directional_conductivity():
     assert np.array_equal(hx, hx0)
     hrot, _, _ = _strip(0, 3.0, k22=0.7, angle1=np.arctan(1.0) * 2.0)   # ellipse turned by 90 degrees: x sees K22
     assert np.allclose(hrot, hy_ref, rtol=0, atol=1e-9)
+
+
+def test_ilut_known_answers():
+    """sparskit2/ilut.f90:48-548 restated (oracle/ilut.c), pinned by what the algorithm must do by construction:
+    (1) with no dropping (droptol 0, lfil = n) ILUT is the complete LU factorisation: lusol solves exactly;
+    (2) on a tridiagonal matrix there is no fill, so ILUT(lfil >= 1, 0) equals ILU0 -- values and apply;
+    (3) MILUT (relax > 0) still solves the system;
+    (4) the COMPLEX preset of the reference (LEVEL 5, DROPTOL 1e-4, BICGSTAB; ImsLinearSettings.f90:103-113) converges
+        in far fewer iterations than ILU0 on the same system."""
+    import scipy.sparse as sp
+    from oracle.oracle import OracleIlu0, OracleIlut, OracleIms
+    from tests.helpers import assembled_system, chd_west_east, hetero_dis, well_center
+    m = hetero_dis(2, 9, 11, seed=3)
+    a, b, x0 = assembled_system(m, [chd_west_east(m), well_center(m)])
+    n = m.nodes
+    A = sp.csr_matrix((a, m.ja, m.ia), shape=(n, n))
+    r = np.random.default_rng(0).normal(size=n)
+    P = OracleIlut(m.ia, m.ja, n, 0.0)
+    assert P.factor(a, 0.0) == 0
+    z = P.apply(r)
+    assert np.abs(A @ z - r).max() <= 1e-9 * np.abs(r).max()
+    # tridiagonal
+    nt = 40
+    ia = np.zeros(nt + 1, np.int32)
+    ja, av = [], []
+    rng = np.random.default_rng(1)
+    for i in range(nt):
+        ja.append(i)
+        av.append(4.0 + rng.random())
+        for j in (i - 1, i + 1):
+            if 0 <= j < nt:
+                ja.append(j)
+                av.append(-1.0 - 0.3 * rng.random())
+        ia[i + 1] = len(ja)
+    ja, av = np.array(ja, np.int32), np.array(av)
+    rt = rng.normal(size=nt)
+    Pt, P0 = OracleIlut(ia, ja, 3, 0.0), OracleIlu0(ia, ja)
+    assert Pt.factor(av, 0.0) == 0 and P0.factor(av, 0.0) == 0
+    assert np.array_equal(Pt.apply(rt), P0.apply(rt))
+    # MILUT (relax > 0: the dropped terms go to the pivot, ilut.f90:365) still solves the system
+    sm = T.ImsSettings.make(dvclose=1e-9, rclose=1e-7, iter1=500, ilinmeth=2, level=2, droptol=1e-3, relax=0.97)
+    xm = x0.copy()
+    assert OracleIms(m.ia, m.ja, sm).solve(a, xm, b)[1] == 1
+    assert np.abs(A @ xm - b).max() < 1e-6
+    # COMPLEX preset
+    s5 = T.ImsSettings.make(dvclose=1e-9, rclose=1e-7, iter1=500, ilinmeth=2, level=5, droptol=1e-4)
+    s0 = T.ImsSettings.make(dvclose=1e-9, rclose=1e-7, iter1=500, ilinmeth=2)
+    x5, xz = x0.copy(), x0.copy()
+    it5, cv5 = OracleIms(m.ia, m.ja, s5).solve(a, x5, b)
+    it0, cv0 = OracleIms(m.ia, m.ja, s0).solve(a, xz, b)
+    assert cv5 == 1 and cv0 == 1 and it5 < it0
+    assert np.abs(x5 - xz).max() < 1e-7
