@@ -236,6 +236,9 @@ void HaloPlan::round(HaloPush &push, HaloSrc &src) {
   src.seq = seq;
   src.err = comm->d_err.p;
   src.slice_halo = slice_halo.p;
+  src.grid = own_grid;
+  src.def_ptr = def_ptr.p;
+  src.def_row = def_row.p;
 }
 
 void HaloPlan::push_now(const HaloPush &push, const double *vec, cudaStream_t s) {

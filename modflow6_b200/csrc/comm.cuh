@@ -102,6 +102,9 @@ struct HaloSrc {
   unsigned long long seq;
   int *err;
   const unsigned char *slice_halo;             // [nslices] 1 = the slice has a row with a halo column
+  // rows with halo columns grouped by the CTA that owns them in a `grid`-CTA grid-stride kernel (see HaloPush)
+  int grid;
+  const int *def_ptr, *def_row;
 };
 
 // halo pattern of one solution on one rank
@@ -116,6 +119,7 @@ struct HaloPlan {
   DevBuf<unsigned char> slice_halo;               // [nslices] slices with halo columns (fused SpMV)
   int own_grid = 0;                               // grid the ownership lists below were built for
   DevBuf<int> cta_ptr, cta_ent;                   // send entries grouped by owning CTA (see HaloPush)
+  DevBuf<int> def_ptr, def_row;                   // rows with halo columns grouped by owning CTA (see HaloSrc)
   bool active() const { return comm != nullptr && comm->nranks > 1; }
   // fused peer-memory path available (mailboxes mapped, few enough neighbours)?
   bool fused() const {
@@ -175,6 +179,13 @@ __device__ __forceinline__ double halo_load(const HaloSrc &H, int c) {
     if (u < H.nnbr && j >= H.recv_ptr[u]) k = u;
   return __ldcg(H.msg[k] + (j - H.recv_ptr[k]));
 }
+// have all neighbours' messages of this round landed already?  (one thread, no waiting)
+__device__ __forceinline__ bool halo_arrived(const HaloSrc &H) {
+  bool ok = true;
+  for (int k = 0; k < H.nnbr; k++)
+    ok = ok && ld_acquire_sys_u64(reinterpret_cast<const unsigned long long *>(H.msg[k] + H.cap)) >= H.seq;
+  return ok;
+}
 // all threads of the CTA: wait until every neighbour's message of this round has landed
 __device__ __forceinline__ void halo_wait(const HaloSrc &H) {
   if (threadIdx.x < H.nnbr)
@@ -209,14 +220,30 @@ __device__ __forceinline__ void halo_publish(const HaloPush &P) {
 }
 // Tail of a kernel that has just written `vec` (every thread of every CTA calls it, after its last store to vec):
 // each CTA pushes the send cells whose rows it computed itself, the last CTA to finish publishes the flags.
+// Only threads that stored into a peer's memory pay for a system-scope fence.
 __device__ __forceinline__ void halo_push_tail(const HaloPush &P, const double *vec, bool *sh_flag) {
   const bool owned = (P.grid == (int)gridDim.x);
   if (owned) {
-    __syncthreads();  // the CTA's own stores to vec are visible to all its threads
-    for (int e = P.cta_ptr[blockIdx.x] + threadIdx.x; e < P.cta_ptr[blockIdx.x + 1]; e += blockDim.x)
-      halo_push_entry(P, vec, P.cta_ent[e]);
+    const int e0 = P.cta_ptr[blockIdx.x], e1 = P.cta_ptr[blockIdx.x + 1];
+    if (e1 > e0) {
+      __syncthreads();  // the CTA's own stores to vec are visible to all its threads
+      bool pushed = false;
+      for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+        halo_push_entry(P, vec, P.cta_ent[e]);
+        pushed = true;
+      }
+      if (pushed) __threadfence_system();
+    }
   }
-  if (last_block_all(P.ticket, sh_flag)) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicInc(P.ticket, gridDim.x - 1);
+    *sh_flag = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (*sh_flag) {
+    __threadfence_system();
     if (!owned) {
       const int total = P.send_ptr[P.nnbr];
       for (int i = threadIdx.x; i < total; i += blockDim.x) halo_push_entry(P, vec, i);

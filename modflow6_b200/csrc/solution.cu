@@ -1451,6 +1451,32 @@ static void create_solution(const mf6gpu_gwf_model *m, const mf6gpu_sln_settings
           H.cta_ptr.upload(cp);
           H.cta_ent.upload(ent);
           H.own_grid = G;
+          // chunks (kBlock rows) with halo-touching slices, grouped the same way, for the deferred pass of the
+          // fused SpMV: entry [chunk][t] = the row thread t handles (the same thread as in the one-pass mode, so
+          // that both modes accumulate identical per-thread sums) or -1
+          std::vector<int> dp((size_t)G + 1, 0), dr;
+          const int nchunk = (n_own + kBlock - 1) / kBlock;
+          std::vector<char> cflag((size_t)nchunk, 0);
+          for (int r = 0; r < n_own; r++)
+            if (sh[(size_t)(r >> 5)]) cflag[(size_t)(r / kBlock)] = 1;
+          for (int c = 0; c < nchunk; c++)
+            if (cflag[c]) dp[(size_t)(c % G) + 1] += kBlock;
+          for (int b = 0; b < G; b++) dp[b + 1] += dp[b];
+          dr.assign((size_t)std::max(dp[G], 1), -1);
+          {
+            std::vector<int> cur(dp.begin(), dp.end() - 1);
+            for (int c = 0; c < nchunk; c++) {
+              if (!cflag[c]) continue;
+              const int b = c % G;
+              for (int t = 0; t < kBlock; t++) {
+                const int r = c * kBlock + t;
+                if (r < n_own && sh[(size_t)(r >> 5)]) dr[(size_t)cur[b] + t] = r;
+              }
+              cur[b] += kBlock;
+            }
+          }
+          H.def_ptr.upload(dp);
+          H.def_row.upload(dr);
         }
         s->S->halo = &s->halo;
         s->os_all.alloc_zero(sizeof(OuterState) / sizeof(double) * (size_t)da->comm->nranks);

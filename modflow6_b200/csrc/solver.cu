@@ -281,29 +281,43 @@ spmv_fused_kernel(int n, const int *__restrict__ slice_ptr,
   __shared__ double sh[8];
   __shared__ bool last;
   if (check_done && st->done) return;
-  double s0 = 0.0, s1 = 0.0;
-  int deferred = 0;
+  double s0 = 0.0, s1 = 0.0, h0 = 0.0, h1 = 0.0;  // interior rows / rows that read halo columns
   for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
-    if (H.nnbr > 0 && H.slice_halo[row >> 5]) {
-      deferred = 1;
-      continue;
-    }
+    if (H.nnbr > 0 && H.slice_halo[row >> 5]) continue;  // deferred: waits for the neighbours below
     double t = sell_row_dot(row, slice_ptr, rowlen, col, val, x);
     if (EPI == 1) t = b[row] - t;
     y[row] = t;
     if (NDOT >= 1) s0 += w[row] * t;
     if (NDOT == 2) s1 += t * t;
   }
-  if (H.nnbr > 0 && __syncthreads_or(deferred)) {
-    halo_wait(H);
-    for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
-      if (!H.slice_halo[row >> 5]) continue;
-      double t = sell_row_dot_halo(row, (long long)slice_ptr[row >> 5] + (row & 31), rowlen[row], col, val, x, H);
-      if (EPI == 1) t = b[row] - t;
-      y[row] = t;
-      if (NDOT >= 1) s0 += w[row] * t;
-      if (NDOT == 2) s1 += t * t;
+  if (H.nnbr > 0) {
+    const bool listed = (H.grid == (int)gridDim.x);
+    const int e0 = listed ? H.def_ptr[blockIdx.x] : 0, e1 = listed ? H.def_ptr[blockIdx.x + 1] : 1;
+    if (e1 > e0) {
+      halo_wait(H);
+      if (listed) {
+        for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+          const int row = H.def_row[e];
+          if (row < 0) continue;
+          double t = sell_row_dot_halo(row, (long long)slice_ptr[row >> 5] + (row & 31), rowlen[row], col, val, x, H);
+          if (EPI == 1) t = b[row] - t;
+          y[row] = t;
+          if (NDOT >= 1) h0 += w[row] * t;
+          if (NDOT == 2) h1 += t * t;
+        }
+      } else {
+        for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
+          if (!H.slice_halo[row >> 5]) continue;
+          double t = sell_row_dot_halo(row, (long long)slice_ptr[row >> 5] + (row & 31), rowlen[row], col, val, x, H);
+          if (EPI == 1) t = b[row] - t;
+          y[row] = t;
+          if (NDOT >= 1) h0 += w[row] * t;
+          if (NDOT == 2) h1 += t * t;
+        }
+      }
     }
+    s0 += h0;
+    s1 += h1;
   }
   if (NDOT >= 1) {
     s0 = block_sum(s0, sh);
@@ -328,11 +342,25 @@ spmv_fused_w_kernel(int n, int ncols, const int *__restrict__ col, const int *__
   __shared__ double sh[8];
   __shared__ bool last;
   if (check_done && st->done) return;
-  double s0 = 0.0, s1 = 0.0;
-  int deferred = 0;
+  double s0 = 0.0, s1 = 0.0, h0 = 0.0, h1 = 0.0;  // interior rows / rows that read halo columns
+  // Fused split-model path: when the neighbours' messages are already there (the usual case: they are pushed by
+  // the kernel that precedes this one on every rank) every row is handled in the one pass; otherwise the rows
+  // that read halo columns are left for the end of the CTA that owns them and wait there.  Both modes give a
+  // thread the same rows and keep the two partial sums apart, so the result does not depend on the timing.
+  __shared__ int arrived;
+  if (H.nnbr > 0) {
+    if (threadIdx.x == 0) arrived = halo_arrived(H) ? 1 : 0;
+    __syncthreads();
+  }
+  const bool inline_halo = H.nnbr > 0 && arrived != 0;
   for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
     if (H.nnbr > 0 && H.slice_halo[row >> 5]) {
-      deferred = 1;
+      if (!inline_halo) continue;
+      double t = sell_row_dot_w_halo<W>(row, col, val, x, H);
+      if (EPI == 1) t = b[row] - t;
+      y[row] = t;
+      if (NDOT >= 1) h0 += w[row] * t;
+      if (NDOT == 2) h1 += t * t;
       continue;
     }
     double t = sell_row_dot_w<W>(row, col, val, x, soff, ncols);
@@ -341,17 +369,35 @@ spmv_fused_w_kernel(int n, int ncols, const int *__restrict__ col, const int *__
     if (NDOT >= 1) s0 += w[row] * t;
     if (NDOT == 2) s1 += t * t;
   }
-  if (H.nnbr > 0 && __syncthreads_or(deferred)) {
-    halo_wait(H);
-    for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
-      if (!H.slice_halo[row >> 5]) continue;
-      double t = sell_row_dot_w_halo<W>(row, col, val, x, H);
-      if (EPI == 1) t = b[row] - t;
-      y[row] = t;
-      if (NDOT >= 1) s0 += w[row] * t;
-      if (NDOT == 2) s1 += t * t;
+  if (H.nnbr > 0 && !inline_halo) {
+    const bool listed = (H.grid == (int)gridDim.x);
+    const int e0 = listed ? H.def_ptr[blockIdx.x] : 0, e1 = listed ? H.def_ptr[blockIdx.x + 1] : 1;
+    if (e1 > e0) {
+      halo_wait(H);
+      if (listed) {
+        for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+          const int row = H.def_row[e];
+          if (row < 0) continue;
+          double t = sell_row_dot_w_halo<W>(row, col, val, x, H);
+          if (EPI == 1) t = b[row] - t;
+          y[row] = t;
+          if (NDOT >= 1) h0 += w[row] * t;
+          if (NDOT == 2) h1 += t * t;
+        }
+      } else {
+        for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
+          if (!H.slice_halo[row >> 5]) continue;
+          double t = sell_row_dot_w_halo<W>(row, col, val, x, H);
+          if (EPI == 1) t = b[row] - t;
+          y[row] = t;
+          if (NDOT >= 1) h0 += w[row] * t;
+          if (NDOT == 2) h1 += t * t;
+        }
+      }
     }
   }
+  s0 += h0;
+  s1 += h1;
   if (NDOT >= 1) {
     s0 = block_sum(s0, sh);
     if (NDOT == 2) s1 = block_sum(s1, sh);
