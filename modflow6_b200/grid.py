@@ -345,6 +345,16 @@ def merge_models(models, exchanges):
     isym = ko[np.searchsorted(key[ko], ja * n + r2)]
     cat = lambda name: np.concatenate([getattr(m, name) for m in models])  # noqa: E731
     m0 = models[0]
+    # The merged system carries ONE set of NPF / STO options; the reference keeps them per model.  Models that
+    # differ would be solved with model 0's options (silently wrong heads), so refuse them.
+    for name in ("icellavg", "inewton", "inewtonur", "iperched", "ivarcv", "idewatcv", "insto", "istor_coef",
+                 "iconf_ss", "iorig_ss"):
+        vals = {int(getattr(m, name)) for m in models}
+        if len(vals) > 1:
+            raise ValueError(f"merge_models: the models differ in option `{name}` ({sorted(vals)}); one solution "
+                             "matrix on the GPU path needs the same NPF / STO options in every model")
+    if any(getattr(m, a) is not None for m in models for a in ("k22", "angle1", "angle2", "angle3")):
+        raise ValueError("merge_models: K22 / ANGLE anisotropy is not supported in multi-model solutions")
     return GwfModel(nodes=n, ia=ia, ja=ja, jas=jas, isym=isym, ihc=ihc, cl1=cl1, cl2=cl2, hwva=hw,
                     top=cat("top"), bot=cat("bot"), area=cat("area"), k11=cat("k11"), k33=cat("k33"),
                     icelltype=cat("icelltype"), strt=cat("strt"), ibound=cat("ibound"),

@@ -102,7 +102,11 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
     if len(models) == 1 and not sim.exchanges:
         model, offs = models[0], np.array([0, models[0].nodes])
     else:
-        model, offs = merge_models(models, sim.exchanges)
+        try:
+            model, offs = merge_models(models, sim.exchanges)
+        except ValueError as e:
+            from .mf6io import Mf6InputError
+            raise Mf6InputError(str(e)) from None
     sim.ims.gpu_ordering = ordering
     rank = None
     if comm is not None and comm.nranks > 1:
@@ -148,11 +152,15 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
                     saving[k].setdefault(rtype, []).append(st)
         # a model without STO is steady; with STO the period keeps the last STEADY-STATE / TRANSIENT keyword,
         # TRANSIENT before any PERIOD block (gwf-sto.f90:170-182, 756)
-        iss = 1
+        iss_of = []
         for gi in sim.models:
             if gi.model.insto:
                 upto = [p for p in gi.sto_transient if p <= kper]
-                iss = 0 if (not upto or gi.sto_transient[max(upto)]) else 1
+                iss_of.append(0 if (not upto or gi.sto_transient[max(upto)]) else 1)
+        if len(set(iss_of)) > 1:     # one solution matrix carries one steady / transient state (see merge_models)
+            from .mf6io import Mf6InputError
+            raise Mf6InputError(f"period {kper}: the models of the solution disagree on STEADY-STATE / TRANSIENT")
+        iss = iss_of[0] if iss_of else 1
         S.set_packages(pkgs)
         pertim = 0.0
         for kstp, delt in enumerate(tdis_steps(perlen, nstp, tsmult), start=1):

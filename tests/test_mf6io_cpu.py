@@ -410,3 +410,15 @@ def test_idomain_reduced_numbering_and_pass_through(tmp_path):
     fja, wel = cbc[0], [r for r in cbc if r["text"].strip() == "WEL"][0]
     assert fja["flow"].size == gi.model.nja                                     # the reduced connectivity
     assert wel["node"].tolist() == [(2 * nrow + 2) * ncol + 3] and np.isclose(wel["q"][0], -30.0)   # USER node
+
+
+def test_models_with_different_options_are_refused(tmp_path):
+    """a two-model solution shares one set of NPF / STO options on the GPU path: models that differ (here NEWTON
+    in one of them) must be refused, not silently solved with the first model's options"""
+    from modflow6_b200.grid import build_dis_model, merge_models
+    a = build_dis_model(1, 1, 5, 1.0, 1.0, 0.0, [-1.0], 1.0)
+    b = build_dis_model(1, 1, 5, 1.0, 1.0, 0.0, [-1.0], 1.0, icelltype=1, inewton=1)
+    ex = dict(m1=0, m2=1, nodem1=[4], nodem2=[0], ihc=[1], cl1=[0.5], cl2=[0.5], hwva=[1.0])
+    with pytest.raises(ValueError, match="inewton"):
+        merge_models([a, b], [ex])
+    merge_models([a, a], [ex])
