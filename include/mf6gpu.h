@@ -57,6 +57,10 @@ size_t mf6gpu_sizeof(int which);
  * current device.  Fails if no device is usable. */
 int mf6gpu_init(int device);
 int mf6gpu_device_count(void);
+/* Page-lock / release a host array that stays allocated across calls (the solution's amat, rhs, x): the host <->
+ * device copies of mf6gpu_matrix_update / mf6gpu_solver_solve then run at full PCIe rate.  Optional. */
+int mf6gpu_host_register(void *ptr, size_t bytes);
+int mf6gpu_host_unregister(void *ptr);
 
 /* ---- MatrixBaseType ------------------------------------------------------
  * SparseMatrixType%init (SparseMatrix.f90:54-74): CSR pattern, rows stored

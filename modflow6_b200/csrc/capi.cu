@@ -59,6 +59,23 @@ size_t mf6gpu_sizeof(int which) {
   return 0;
 }
 
+// Page-lock a host array the caller keeps for the whole simulation (the Fortran amat / rhs / x arrays of
+// NumericalSolution: NumericalSolution.f90:415-430), so that the per-outer-iteration copies of
+// mf6gpu_matrix_update / mf6gpu_solver_solve run at full PCIe rate instead of through a pageable staging copy.
+int mf6gpu_host_register(void *ptr, size_t bytes) {
+  return guard([&] {
+    MF6_REQUIRE(ptr && bytes > 0, "host_register: null argument");
+    MF6_CK(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  });
+}
+
+int mf6gpu_host_unregister(void *ptr) {
+  return guard([&] {
+    MF6_REQUIRE(ptr, "host_unregister: null argument");
+    MF6_CK(cudaHostUnregister(ptr));
+  });
+}
+
 int mf6gpu_device_count(void) {
   int c = 0;
   if (cudaGetDeviceCount(&c) != cudaSuccess) {

@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <nvtx3/nvToolsExt.h>
 #include <cstring>
 #include <numeric>
 
@@ -1192,20 +1193,30 @@ void mf6gpu_solution::backtracking(int kiter) {
   }
 }
 
-// solve(kiter) (:1482-1837)
+// solve(kiter) (:1482-1837).  The two NVTX ranges carry the names of the reference's own profiler sections
+// ("Formulate", "Linear solve": NumericalSolution.f90:1581-1601), so a timeline lines up with its listing.
 int mf6gpu_solution::solve_outer(int kiter, int kstp, int kper, double &hncg, int &lrch, double &tf,
                                  double &tl) {
   const int G = grid_for(n);
   MF6_CK(cudaEventRecord(ev[0], stream));
+  nvtxRangePushA("Formulate");
   if (ss.numtrack > 0) backtracking(kiter);
   buildsystem(1);
   int iptc;
   double ptcf;
   calc_ptc(iptc, ptcf);
+  nvtxRangePop();
   MF6_CK(cudaEventRecord(ev[1], stream));
+  nvtxRangePushA("Linear solve");
   ls_fixups(kiter, kstp, kper, iptc, ptcf);
   int iter = 0, icnvg_lin = 0;
-  S->solve_device(kiter, kstp, x.p, rhs.p, &iter, &icnvg_lin);
+  try {
+    S->solve_device(kiter, kstp, x.p, rhs.p, &iter, &icnvg_lin);
+  } catch (...) {
+    nvtxRangePop();
+    throw;
+  }
+  nvtxRangePop();
   nl += S->launches + 1;  // + dxmax
   MF6_CK(cudaEventRecord(ev[2], stream));
   dxmax_kernel<<<G, kBlock, 0, stream>>>(n, x.p, xtemp.p, ibound.p, A->ord_ptr(), pm.p, tickets.p, os.p);

@@ -32,6 +32,7 @@ SYMBOLS = [
     "mf6gpu_solution_get_simvals", "mf6gpu_solution_get_storage", "mf6gpu_solution_get_nodes",
     "mf6gpu_ordering_compute", "mf6gpu_model_elimination_order",
     "mf6gpu_solver_set_models", "mf6gpu_solver_get_model_summary",
+    "mf6gpu_host_register", "mf6gpu_host_unregister",
 ]
 
 _lib = None
@@ -58,6 +59,8 @@ def load():
     L.mf6gpu_sizeof.restype = C.c_size_t
     L.mf6gpu_sizeof.argtypes = [C.c_int]
     L.mf6gpu_init.argtypes = [C.c_int]
+    L.mf6gpu_host_register.argtypes = [C.c_void_p, C.c_size_t]
+    L.mf6gpu_host_unregister.argtypes = [C.c_void_p]
     L.mf6gpu_matrix_create.argtypes = [i32, i32, pi32, pi32, i32, i32, vpp]
     L.mf6gpu_matrix_destroy.argtypes = [vp]
     L.mf6gpu_matrix_update.argtypes = [vp, pf64]
