@@ -53,7 +53,11 @@ def parse_args():
     ap.add_argument("--parity-max-cells", type=float, default=9e7,
                     help="N > 1: the unsplit model is solved on rank 0 for the parity block up to this many cells")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inner-maximum", type=int, default=500, help="INNER_MAXIMUM of the IMS LINEAR block")
+    ap.add_argument("--inner-maximum", type=int, default=None, help="INNER_MAXIMUM of the IMS LINEAR block")
+    ap.add_argument("--closure", default="tight", choices=["tight", "survey"],
+                    help="inner closure of C2 (modflow6_b200/configs.py C2_CLOSURE): tight = INNER_DVCLOSE 1e-7, "
+                         "INNER_RCLOSE 1e-4, INNER_MAXIMUM 1000 (default: the closure at which the 0.1 x OUTER_DVCLOSE "
+                         "parity bar holds at full size); survey = 1e-6 / 1e-2 / 500")
     ap.add_argument("--outer-maximum", type=int, default=50, help="OUTER_MAXIMUM (1 = short profiling run)")
     ap.add_argument("--min-warmup", type=int, default=3)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
@@ -139,12 +143,19 @@ def ncu_traffic(prefix):
     return None
 
 
-def build_config(size, ordering, inner_maximum=500, outer_maximum=50):
+CLOSURE = "tight"      # set from --closure in main()
+
+
+def build_config(size, ordering, inner_maximum=None, outer_maximum=50):
     from modflow6_b200 import configs, ctypes_types as T
     nlay, nrow, ncol = size
     o = {"multicolor": T.ORDER_MULTICOLOR, "natural": T.ORDER_NATURAL, "block": T.ORDER_BLOCK_MULTICOLOR}[ordering]
     return configs.c2_confined(nlay, nrow, ncol, gpu_ordering=o, inner_maximum=inner_maximum,
-                               outer_maximum=outer_maximum)
+                               outer_maximum=outer_maximum, closure=CLOSURE)
+
+
+def fixture_tag(ordering):
+    return f"c2_full_{ordering}" + ("_tight" if CLOSURE == "tight" else "")
 
 
 def algorithmic_bytes(n, nja):
@@ -209,7 +220,7 @@ def reference_full_solve(size):
     if tuple(size) != (10, 1000, 1000):
         return None
     from oracle import golden
-    g = golden.load("c2_full_natural")
+    g = golden.load(fixture_tag("natural"))
     if g is None:
         return None
     st = g["meta"]["steps"][-1]
@@ -364,6 +375,8 @@ def split_parity(G, sub, spec, heads, rep, ims_s, sln_s, pkgs, rank, world, args
 
 def main():
     args = parse_args()
+    global CLOSURE
+    CLOSURE = args.closure
     size = tuple(int(v) for v in args.size.split(","))
     if args.impl == "reference":
         run_reference(args, size)
@@ -419,7 +432,9 @@ def main():
         sub = build_dis_block(spec, pr, pc, rank)
         o = {"multicolor": T.ORDER_MULTICOLOR, "natural": T.ORDER_NATURAL,
              "block": T.ORDER_BLOCK_MULTICOLOR}[args.ordering]
-        ims_s = T.ImsSettings.make(dvclose=1e-6, rclose=1e-2, iter1=args.inner_maximum, ilinmeth=1, relax=0.0,
+        from modflow6_b200.configs import C2_CLOSURE
+        idv, irc, itmax = C2_CLOSURE[args.closure]
+        ims_s = T.ImsSettings.make(dvclose=idv, rclose=irc, iter1=args.inner_maximum or itmax, ilinmeth=1, relax=0.0,
                                    gpu_ordering=o)
         sln_s = T.SlnSettings.make(dvclose=1e-5, mxiter=args.outer_maximum, nonmeth=0)
         comm = GpuComm(rank, world)
@@ -538,7 +553,7 @@ def main():
                        "cells": n_total, "cells_per_gpu": n, "nja_per_gpu": nja,
                        "l2_policy": "inputs_exceed_l2 (matrix+vectors >> 126 MB)", "layout": layout,
                        "exchange": exchange_desc(G, world),
-                       "inner_dvclose": ims_s.dvclose, "inner_rclose": ims_s.rclose,
+                       "closure": args.closure, "inner_dvclose": ims_s.dvclose, "inner_rclose": ims_s.rclose,
                        "inner_maximum": ims_s.iter1, "outer_dvclose": sln_s.dvclose},
             "solve": {"outer_iterations_per_step": outer / args.steps, "inner_iterations_per_step": inner / args.steps,
                       "converged": int(converged), "linear_solve_s_per_step": t_ls / args.steps,
@@ -573,7 +588,7 @@ def main():
             # run against a live oracle
             try:
                 from oracle import golden
-                full = golden.compare_heads(f"c2_full_{args.ordering}", heads, sln_s.dvclose) \
+                full = golden.compare_heads(fixture_tag(args.ordering), heads, sln_s.dvclose) \
                     if size == (10, 1000, 1000) else None
                 if full is not None and "oracle" in full:
                     full["case"] = "the benchmarked 10x1000x1000 solve vs the oracle on the same permuted system"

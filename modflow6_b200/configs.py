@@ -67,11 +67,22 @@ def c1_npf01(case="b", gpu_ordering=T.ORDER_NATURAL):
     return SimConfig(f"npf01{case}_75x75", m, periods, sln, ims)
 
 
-def c2_confined(nlay=10, nrow=1000, ncol=1000, gpu_ordering=T.ORDER_BLOCK_MULTICOLOR, inner_maximum=500,
-                outer_maximum=50, seed=20260101):
+# Inner closure of C2.  "survey" = the values SURVEY.md section 8(d) names (INNER_DVCLOSE 1e-6, INNER_RCLOSE 1e-2,
+# INNER_MAXIMUM 500): only a decade below OUTER_DVCLOSE 1e-5, and on the ill-conditioned 1e7-cell system the CG
+# step-size test then stops 1e-4 away from the converged heads -- two correct implementations that differ only in
+# the rounding of their dot products end 9e-6 apart (measured: device vs oracle on the same permuted system).
+# "tight" = INNER_DVCLOSE 1e-7, INNER_RCLOSE 1e-4, INNER_MAXIMUM 1000: the closure at which the north-star parity
+# bar (0.1 x OUTER_DVCLOSE) is meaningful; device vs oracle 4.5e-7 at full size.  bench.py times "tight".
+C2_CLOSURE = {"survey": (1e-6, 1e-2, 500), "tight": (1e-7, 1e-4, 1000)}
+
+
+def c2_confined(nlay=10, nrow=1000, ncol=1000, gpu_ordering=T.ORDER_BLOCK_MULTICOLOR, inner_maximum=None,
+                outer_maximum=50, seed=20260101, closure="survey"):
     """confined steady state, heterogeneous K = exp(N(ln 10, 1)), k33 = 0.1 k,
     delr = delc = 100, layer thickness 10, CHD 48 / 40 on the first / last column, WEL -1000 at the centre
-    of the middle layer; CG + ILU0, inner_dvclose 1e-6, inner_rclose 1e-2, outer_dvclose 1e-5."""
+    of the middle layer; CG + ILU0, outer_dvclose 1e-5, inner closure per `closure` (C2_CLOSURE)."""
+    inner_dvclose, inner_rclose, itmax = C2_CLOSURE[closure]
+    inner_maximum = inner_maximum or itmax
     rng = np.random.default_rng(seed)
     k = np.exp(rng.normal(np.log(10.0), 1.0, size=(nlay, nrow, ncol)))
     botm = -10.0 * np.arange(1, nlay + 1)
@@ -79,10 +90,10 @@ def c2_confined(nlay=10, nrow=1000, ncol=1000, gpu_ordering=T.ORDER_BLOCK_MULTIC
     chd = _chd_columns(m, 48.0, 40.0)
     wel = Package(T.PKG_WEL, [m.node(nlay // 2, nrow // 2, ncol // 2)], [-1000.0])
     periods = [Period(1.0, 1, 1.0, True, [chd, wel])]
-    ims = T.ImsSettings.make(dvclose=1e-6, rclose=1e-2, iter1=inner_maximum, ilinmeth=1, relax=0.0,
+    ims = T.ImsSettings.make(dvclose=inner_dvclose, rclose=inner_rclose, iter1=inner_maximum, ilinmeth=1, relax=0.0,
                              gpu_ordering=gpu_ordering)
     sln = T.SlnSettings.make(dvclose=1e-5, mxiter=outer_maximum, nonmeth=0)
-    return SimConfig(f"c2_confined_{nlay}x{nrow}x{ncol}", m, periods, sln, ims)
+    return SimConfig(f"c2_confined_{nlay}x{nrow}x{ncol}", m, periods, sln, ims, meta={"closure": closure})
 
 
 def c3_newton(nlay=5, nrow=2000, ncol=2000, gpu_ordering=T.ORDER_BLOCK_MULTICOLOR, nwel=100, ntrans=10,

@@ -23,7 +23,14 @@
 #include <cstring>
 
 namespace mf6 {
-constexpr int kGraphMaxRows = 2000000;  // above this an iteration is GPU-bound: plain launches
+// above this many rows an iteration is GPU-bound: plain launches (MF6GPU_GRAPH_MAX_ROWS overrides, for tuning)
+static int graph_max_rows() {
+  static int v = [] {
+    const char *e = std::getenv("MF6GPU_GRAPH_MAX_ROWS");
+    return e ? std::atoi(e) : 2000000;
+  }();
+  return v;
+}
 
 enum { TK_DOT = 0, TK_SPMV = 1, TK_UPD = 2, TK_NRM = 3 };
 // finalisation modes of the reduction kernels
@@ -996,9 +1003,9 @@ void mf6gpu_solver::reduce_finalize(int mode, double *out, int bcgs) {
   launches += 2;
 }
 
-int mf6gpu_solver::precond(const double *rin, double *dd, const mf6::IluDotArgs *dot) {
-  if (ilut) return ilut->apply(rin, dd, &st.p->done, stream);
-  return ilu0_apply(*A, lu.p, rin, dd, &st.p->done, stream, dot);
+int mf6gpu_solver::precond(const double *rin, double *dd, cudaStream_t S, const mf6::IluDotArgs *dot) {
+  if (ilut) return ilut->apply(rin, dd, &st.p->done, S);
+  return ilu0_apply(*A, lu.p, rin, dd, &st.p->done, S, dot);
 }
 
 // ims_base_pcu, ImsLinearBase.f90:808-858
@@ -1158,11 +1165,11 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
         if (fuse_dot) {
           // z = M^-1 d with rho = d.z (and beta = rho/rho0) accumulated by the same launches
           idot.push = r1.push;
-          launches += precond(d.p, z.p, &idot);
+          launches += precond(d.p, z.p, S, &idot);
           if (!fused) reduce_finalize(FIN_CG_RHO, nullptr, 0);
           prof_end();
         } else {
-          launches += precond(d.p, z.p);
+          launches += precond(d.p, z.p, S);
           prof_end();
           prof_begin(PC_DOT);
           dot_kernel<<<G, kBlock, 0, S>>>(N, d.p, z.p, partial.p, tickets.p + TK_DOT, st.p,
@@ -1203,7 +1210,7 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
         if (!fused) reduce_finalize(FIN_BCGS_RHO, nullptr, 1);
         bcgs_p_kernel<<<G, kBlock, 0, S>>>(N, d.p, v.p, p.p, st.p, first, r1.pull);
         prof_begin(PC_ILU);
-        launches += precond(p.p, phat.p);
+        launches += precond(p.p, phat.p, S);
         halo_round(hp, hs, phat.p, false);
         prof_end();
         const DistRound r2 = round();
@@ -1214,7 +1221,7 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
         prof_end();
         bcgs_q_kernel<<<G, kBlock, 0, S>>>(N, d.p, v.p, q.p, st.p, r2.pull);
         prof_begin(PC_ILU);
-        launches += precond(q.p, qhat.p);
+        launches += precond(q.p, qhat.p, S);
         halo_round(hp, hs, qhat.p, false);
         prof_end();
         const DistRound r3 = round();
@@ -1237,7 +1244,7 @@ void mf6gpu_solver::solve_device(int kiter, int kstp, double *x_dev, double *b_d
         launches += 6;
       }
     };
-    const bool use_graph = !dist && !profiling && s.north == 0 && N <= kGraphMaxRows && itmax > 1 &&
+    const bool use_graph = !dist && !profiling && s.north == 0 && N <= graph_max_rows() && itmax > 1 &&
                            !std::getenv("MF6GPU_NO_GRAPH");
     cudaGraphExec_t gexec = nullptr;
     int graph_launches = 0;

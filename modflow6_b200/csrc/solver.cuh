@@ -43,7 +43,7 @@ struct mf6gpu_solver {
   int ipc = 1;                            // 1 ILU0, 2 MILU0, 3 ILUT, 4 MILUT (ImsLinear.f90:178-185)
   std::unique_ptr<mf6::IlutPlan> ilut;    // IPC 3 / 4
   // z = M^-1 r with the active preconditioner; `dot` (fused rho) only with ILU0 / MILU0
-  int precond(const double *rin, double *d, const mf6::IluDotArgs *dot = nullptr);
+  int precond(const double *rin, double *d, cudaStream_t S, const mf6::IluDotArgs *dot = nullptr);
   cudaStream_t stream = 0;
   int n = 0;
   // work vectors (final numbering)

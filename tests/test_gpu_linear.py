@@ -208,8 +208,8 @@ def test_unsupported_options_fail_loudly(system):
     from modflow6_b200.linear import GpuLinearSolver, GpuMatrix
     m, a, b, x0 = system
     A = GpuMatrix(m.ia, m.ja, 0, 0)
-    with pytest.raises(Mf6GpuError, match="ILUT"):
-        GpuLinearSolver(A, T.ImsSettings.make(level=5, droptol=1e-4))
+    with pytest.raises(Mf6GpuError, match="PRECONDITIONER_LEVELS"):
+        GpuLinearSolver(A, T.ImsSettings.make(level=-1))
     with pytest.raises(Mf6GpuError):
         GpuLinearSolver(A, T.ImsSettings.make(ilinmeth=3))
     with pytest.raises(Mf6GpuError, match="diagonal first"):
