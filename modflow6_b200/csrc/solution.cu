@@ -1063,6 +1063,17 @@ void mf6gpu_solution::buildsystem(int inewton) {
     if (do_wd) {
       npf_wd_kernel<<<grid_for(n), kBlock, 0, stream>>>(M, x.p, ibound.p, ibound0.p, wd_flag.p);
       nl++;
+      if (halo.active()) {
+        // split-model path: the neighbours' copies of the cells that have just gone dry (ibound 0, head = HDRY)
+        // are refreshed before the conductances are formed -- what the reference re-synchronises per outer
+        // iteration for the interface model (GwfGwfConnection.f90:205-228, VirtualGwfModel ibound / x)
+        const int nh = n_ext - n;
+        i2d_kernel<<<grid_for(n), kBlock, 0, stream>>>(n, ibound.p, ibd_tmp.p);
+        halo.exchange(ibd_tmp.p, stream);
+        if (nh > 0) d2i_kernel<<<grid_for(nh), kBlock, 0, stream>>>(nh, ibd_tmp.p + n, ibound.p + n);
+        exchange_x();
+        nl += 4;
+      }
     }
     ModelView Me = M;
     Me.n = n_ext;  // saturation of the halo cells too
@@ -1512,15 +1523,14 @@ static void create_solution(const mf6gpu_gwf_model *m, const mf6gpu_sln_settings
       for (int i = 0; i < n; i++)
         if (m->icelltype[i] != 0) anyconv = true;
       o.all_confined = (!anyconv && m->iperched == 0 && m->inewton == 0) ? 1 : 0;
-      // cells can become / be inactive: wet-dry conversion (no NEWTON, convertible cells; not on the split-model
-      // path, where ibound of the halo is exchanged once per stress period) or IDOMAIN holes.  Recharge then needs
+      // cells can become / be inactive: wet-dry conversion (no NEWTON, convertible cells) or IDOMAIN holes.  Recharge then needs
       // the cell under every cell (highest_active walks the m > n vertical connections)
-      s->do_wd = (m->inewton == 0) && anyconv && !da;
+      s->do_wd = (m->inewton == 0) && anyconv;
       s->wd_flag.alloc_zero(1);
       bool anyinactive = false;
       for (int i = 0; i < n_own; i++)
         if (m->ibound && m->ibound[i] == 0) anyinactive = true;
-      if ((s->do_wd || anyinactive) && !da) {
+      if (s->do_wd || anyinactive) {  // (split-model path: a cell column never straddles two ranks)
         std::vector<int> bel((size_t)n_own, -1);
         for (int v = 0; v < n_own; v++)
           for (int p = m->ia[v] - base + 1; p < m->ia[v + 1] - base; p++) {

@@ -57,3 +57,17 @@ def test_two_rank_input_deck(tmp_path, shape, ordering):
         assert len(recs) == shp[0]
         for rec in recs:
             np.testing.assert_array_almost_equal(rec["data"], np.broadcast_to(first + np.arange(5.0), shp[1:]))
+
+
+@pytest.mark.parametrize("case,ordering", [("disv", 0), ("disv", 2), ("wetdry", 0), ("wetdry", 2)])
+def test_two_rank_generic_models(case, ordering):
+    """split-model path beyond DIS blocks: a hexagonal DISV model cut into stripes, and an unconfined model whose
+    top layer dries up (wet/dry conversion + recharge hand-down with per-outer ibound exchange); both against the
+    unsplit model solved on one GPU"""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29536", os.path.join(ROOT, "scripts", "dist_generic_check.py"), case,
+           str(ordering)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert "DIST_GENERIC PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
