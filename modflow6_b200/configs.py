@@ -67,13 +67,17 @@ def c1_npf01(case="b", gpu_ordering=T.ORDER_NATURAL):
     return SimConfig(f"npf01{case}_75x75", m, periods, sln, ims)
 
 
-# Inner closure of C2.  "survey" = the values SURVEY.md section 8(d) names (INNER_DVCLOSE 1e-6, INNER_RCLOSE 1e-2,
-# INNER_MAXIMUM 500): only a decade below OUTER_DVCLOSE 1e-5, and on the ill-conditioned 1e7-cell system the CG
-# step-size test then stops 1e-4 away from the converged heads -- two correct implementations that differ only in
-# the rounding of their dot products end 9e-6 apart (measured: device vs oracle on the same permuted system).
-# "tight" = INNER_DVCLOSE 1e-7, INNER_RCLOSE 1e-4, INNER_MAXIMUM 1000: the closure at which the north-star parity
-# bar (0.1 x OUTER_DVCLOSE) is meaningful; device vs oracle 4.5e-7 at full size.  bench.py times "tight".
-C2_CLOSURE = {"survey": (1e-6, 1e-2, 500), "tight": (1e-7, 1e-4, 1000)}
+# Inner closure of C2 (OUTER_DVCLOSE is 1e-5 throughout).
+#   "survey": INNER_DVCLOSE 1e-6, INNER_RCLOSE 1e-2, INNER_MAXIMUM 500 -- the values SURVEY.md section 8(d) names.
+#       Only a decade below the outer criterion; on the ill-conditioned 1e7-cell system the CG step-size test then
+#       stops ~1.5e-4 short of the converged heads.  Measured at full size: the oracle's own two orderings end
+#       5.7e-5 apart, device vs oracle on the SAME permuted system 8.7e-6 (dot-product rounding amplified by CG).
+#   "tight":  1e-7 / 1e-4 / 1000 -- device vs oracle on the same permuted system 4.5e-7 (bar 1e-6 met); the two
+#       orderings of the oracle still 9.6e-6 apart.
+#   "tight2": 1e-8 / 1e-5 / 1000 -- INNER_DVCLOSE three decades below OUTER_DVCLOSE: the orderings agree to 5.4e-7,
+#       i.e. the device's block ordering can be held to the north-star bar (0.1 x OUTER_DVCLOSE, budget within 1e-3)
+#       against the reference's OWN natural-order solve.  bench.py times this one.
+C2_CLOSURE = {"survey": (1e-6, 1e-2, 500), "tight": (1e-7, 1e-4, 1000), "tight2": (1e-8, 1e-5, 1000)}
 
 
 def c2_confined(nlay=10, nrow=1000, ncol=1000, gpu_ordering=T.ORDER_BLOCK_MULTICOLOR, inner_maximum=None,

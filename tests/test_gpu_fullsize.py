@@ -19,15 +19,18 @@ def _run(cfg, max_steps=None):
     return reps, x
 
 
-def test_c2_full_size_against_oracle_fixture(gpu):
-    """BASELINE config 2 (10 x 1000 x 1000, CG + ILU0, block ordering) with the inner closure bench.py times
-    (C2_CLOSURE["tight"]): 1e7 heads against the oracle's on the same permuted system, north-star bar"""
+@pytest.mark.parametrize("closure", ["tight2", "tight"])
+def test_c2_full_size_against_oracle_fixture(gpu, closure):
+    """BASELINE config 2 (10 x 1000 x 1000, CG + ILU0, block ordering): 1e7 heads against the oracle's on the same
+    permuted system, north-star bar (max |dhead| <= 0.1 x OUTER_DVCLOSE, budget within 1e-3), at the closure
+    bench.py times ("tight2") and one decade looser ("tight"); see configs.C2_CLOSURE"""
     from oracle import golden
-    if golden.load("c2_full_block_tight") is None:
+    tag = "c2_full_block_" + closure
+    if golden.load(tag) is None:
         pytest.skip("fixture missing")
-    cfg = configs.c2_confined(closure="tight")
+    cfg = configs.c2_confined(closure=closure)
     reps, x = _run(cfg)
-    c = golden.compare_heads("c2_full_block_tight", x, cfg.sln.dvclose)
+    c = golden.compare_heads(tag, x, cfg.sln.dvclose)
     assert reps[0]["converged"] == 1
     assert c["max_abs_dhead"] <= 0.1 * cfg.sln.dvclose, c
     if "max_abs_dblocksum" in c:
@@ -35,12 +38,14 @@ def test_c2_full_size_against_oracle_fixture(gpu):
     assert abs(reps[0]["pdiffr"] - c["oracle"]["pdiffr"]) <= 1e-3
     assert reps[0]["outer_iterations"] == c["oracle"]["outer_iterations"]
     assert abs(reps[0]["inner_iterations"] - c["oracle"]["inner_iterations"]) <= c["oracle"]["inner_iterations"] // 20
-    # the reference's own (natural) ordering at the same closure: same budget, heads within OUTER_DVCLOSE -- the
-    # two orderings are different convergence paths to the same answer (oracle block vs oracle natural: 9.6e-6)
-    n = golden.compare_heads("c2_full_natural_tight", x, cfg.sln.dvclose)
+    # the reference's own (natural) ordering at the same closure: a different convergence path to the same answer
+    n = golden.compare_heads("c2_full_natural_" + closure, x, cfg.sln.dvclose)
     if n is not None:
-        assert n["max_abs_dhead"] <= cfg.sln.dvclose
         assert abs(reps[0]["pdiffr"] - n["oracle"]["pdiffr"]) <= 1e-3
+        if closure == "tight2":      # the orderings themselves agree to 5.4e-7 here: the bar holds across them
+            assert n["max_abs_dhead"] <= 0.1 * cfg.sln.dvclose, n
+        else:                        # 9.6e-6 between the oracle's own two orderings at this closure
+            assert n["max_abs_dhead"] <= cfg.sln.dvclose, n
 
 
 def test_c2_full_size_survey_closure_slack(gpu):
