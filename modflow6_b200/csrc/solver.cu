@@ -23,11 +23,13 @@
 #include <cstring>
 
 namespace mf6 {
-// above this many rows an iteration is GPU-bound: plain launches (MF6GPU_GRAPH_MAX_ROWS overrides, for tuning)
+// The inner iteration replays a CUDA graph at every size: launch-bound small systems gain most (C1 0.090 -> 0.068 s),
+// but the 10 launches of an iteration still cost ~2 us of gaps each at 1e7 rows (measured: 1594 -> 1537 ms per C2
+// time step).  MF6GPU_GRAPH_MAX_ROWS lowers the limit for experiments.
 static int graph_max_rows() {
   static int v = [] {
     const char *e = std::getenv("MF6GPU_GRAPH_MAX_ROWS");
-    return e ? std::atoi(e) : 2000000;
+    return e ? std::atoi(e) : INT_MAX;
   }();
   return v;
 }
@@ -616,9 +618,25 @@ update_kernel(int n, double *__restrict__ x, double *__restrict__ d,
       rv = rv - alpha * qi;
       dout = rv;
     }
+    // running maxima: only the row index is tracked; its position in the reference's loop order (`ord`, the
+    // tie-breaker) is looked up on an exact tie and once at the end -- no index loads in the streaming loop
     const double atv = fabs(tv), arv = fabs(rv);
-    if (atv >= mx.a && atv > 0.0) maxloc_take(mx, tv, ord ? ord[i] : i, i);
-    if (arv >= mr.a && arv > 0.0) maxloc_take(mr, rv, ord ? ord[i] : i, i);
+    if (atv > mx.a) {
+      mx.a = atv;
+      mx.v = tv;
+      mx.idx = i;
+    } else if (atv == mx.a && atv > 0.0 && ord && ord[i] < ord[mx.idx]) {
+      mx.v = tv;
+      mx.idx = i;
+    }
+    if (arv > mr.a) {
+      mr.a = arv;
+      mr.v = rv;
+      mr.idx = i;
+    } else if (arv == mr.a && arv > 0.0 && ord && ord[i] < ord[mr.idx]) {
+      mr.v = rv;
+      mr.idx = i;
+    }
     ssq += rv * rv;
   };
   if (VEC2) {
@@ -678,6 +696,8 @@ update_kernel(int n, double *__restrict__ x, double *__restrict__ d,
       d[i] = dout;
     }
   }
+  if (mx.idx >= 0) mx.ord = ord ? ord[mx.idx] : mx.idx;
+  if (mr.idx >= 0) mr.ord = ord ? ord[mr.idx] : mr.idx;
   ssq = block_sum(ssq, sh);
   mx = block_maxloc(mx, shm);
   mr = block_maxloc(mr, shm);
