@@ -422,3 +422,41 @@ def test_models_with_different_options_are_refused(tmp_path):
     with pytest.raises(ValueError, match="inewton"):
         merge_models([a, b], [ex])
     merge_models([a, a], [ex])
+
+
+def test_npf05_anisotropy_and_drn_depth_from_decks(tmp_path):
+    """the deck reader hands K22 / K22OVERK / K33OVERK / ANGLEn (degrees -> radians) and the DRN AUXDEPTHNAME column
+    to the path: (1) autotest/test_gwf_npf05_anisotropy.py written as input files gives its literal head array;
+    (2) a strip along y with K22 and ANGLE1 = 90 equals the same strip along x (hy_eff)"""
+    import os
+    from tests.test_oracle_known_answers import NPF05_ANSWER
+    d = str(tmp_path / "a")
+    os.makedirs(d)
+    mf6_inputs.write_gwf(d, "npf", (2, 1, 5), 1.0, 1.0, 100.0, [50.0, 0.0], 5.0, strt=100.0,
+                         chd={1: [((1, 1, 1), 100.0), ((2, 1, 5), 110.0)]},
+                         extra_packages=[("RCH6", "rcha", "BEGIN options\n  READASARRAYS\nEND options\n\nBEGIN period 1\n"
+                                          "  RECHARGE\n    CONSTANT 0.01\nEND period 1\n")])
+    npf = (tmp_path / "a" / "npf.npf").read_text()
+    npf = npf.replace("SAVE_FLOWS", "SAVE_FLOWS\n  K22OVERK\n  K33OVERK").replace(
+        "END griddata", "  k22\n    CONSTANT 0.1\n  k33\n    CONSTANT 0.01\nEND griddata")
+    (tmp_path / "a" / "npf.npf").write_text(npf)
+    mf6_inputs.write_sim(d, ["npf"], [(1.0, 1, 1.0)],
+                         "BEGIN nonlinear\n  OUTER_DVCLOSE 1e-9\n  OUTER_MAXIMUM 100\n  UNDER_RELAXATION DBD\nEND nonlinear\n\n"
+                         "BEGIN linear\n  INNER_MAXIMUM 300\n  INNER_DVCLOSE 1e-9\n  INNER_RCLOSE 1e-3\n"
+                         "  LINEAR_ACCELERATION BICGSTAB\n  RELAXATION_FACTOR 0.97\nEND linear\n")
+    sim = mf6io.read_simulation(d)
+    m = sim.models[0].model
+    assert np.allclose(m.k22, 0.5) and np.allclose(m.k33, 0.05) and m.conn_nx is not None
+    out = simulate.run(d, ordering=T.ORDER_NATURAL, solution_class=oracle_class(), write_output=False)
+    assert np.allclose(out["heads"][0].ravel(), NPF05_ANSWER)
+    # DRN with a drainage-depth auxiliary column
+    d2 = str(tmp_path / "b")
+    os.makedirs(d2)
+    drn = ("BEGIN options\n  AUXILIARY ddrn\n  AUXDEPTHNAME ddrn\nEND options\n\nBEGIN dimensions\n  MAXBOUND 1\n"
+           "END dimensions\n\nBEGIN period 1\n  1 1 5  0.0  2.5  1.0\nEND period 1\n")
+    mf6_inputs.write_gwf(d2, "m", (1, 1, 5), 1.0, 1.0, 10.0, [0.0], 1.0, strt=5.0, icelltype=1,
+                         chd={1: [((1, 1, 1), 5.0)]}, extra_packages=[("DRN6", "drn", drn)])
+    mf6_inputs.write_sim(d2, ["m"], [(1.0, 1, 1.0)], "")
+    sp = [p for p in mf6io.read_simulation(d2).models[0].packages if p.ftype.upper().startswith("DRN")][0]
+    pk = sp.periods[1]
+    assert pk.b1.tolist() == [0.0] and pk.b2.tolist() == [2.5] and pk.b3.tolist() == [1.0] and pk.iflowred == 0
