@@ -89,27 +89,23 @@ __device__ __forceinline__ bool wait_flag(const unsigned long long *flag, unsign
   return false;
 }
 
-// small all-gather, push side: lane q writes this rank's record into rank q's mailbox, then the flag
+// small all-gather, push side: lane q writes this rank's record into rank q's mailbox (LL words, see comm.cuh)
 __global__ void p2p_small_push_kernel(char *const *__restrict__ peer, int nranks, int rank, size_t off,
                                       const double *__restrict__ in, int count, int cap,
                                       unsigned long long seq) {
   const int q = threadIdx.x;
   if (q >= nranks) return;
-  double *dst = reinterpret_cast<double *>(peer[q] + off);
-  for (int i = 0; i < count; i++) dst[i] = in[i];
-  __threadfence_system();
-  st_flag(reinterpret_cast<unsigned long long *>(dst + cap), seq);
+  ll_store(reinterpret_cast<unsigned long long *>(peer[q] + off), in, count, (unsigned int)seq);
 }
 
-// small all-gather, pull side: wait for every rank's flag, then copy the records out in rank order
+// small all-gather, pull side: wait for every rank's record, copy them out in rank order
 __global__ void p2p_small_pull_kernel(const char *__restrict__ mailbox, int nranks, size_t off0, size_t slot,
                                       double *__restrict__ out, int count, int cap, unsigned long long seq,
                                       int *err) {
   const int r = threadIdx.x;
   if (r >= nranks) return;
-  const double *src = reinterpret_cast<const double *>(mailbox + off0 + (size_t)r * slot);
-  wait_flag(reinterpret_cast<const unsigned long long *>(src + cap), seq, err);
-  for (int i = 0; i < count; i++) out[(size_t)r * count + i] = __ldcg(src + i);
+  ll_load_wait(reinterpret_cast<const unsigned long long *>(mailbox + off0 + (size_t)r * slot),
+               out + (size_t)r * count, count, (unsigned int)seq, err);
 }
 
 // halo, push side: gather the owned values every neighbour needs straight into THEIR mailbox; the last

@@ -20,7 +20,7 @@ struct P2PLayout {
   int nranks = 0;
   size_t small_doubles = 16;   // capacity of one small all-gather record
   size_t halo_doubles = 0;     // capacity of one halo message
-  size_t small_slot() const { return (small_doubles + 2) * sizeof(double); }              // data + flag + pad
+  size_t small_slot() const { return 2 * small_doubles * sizeof(double); }   // two tagged words per double (LL)
   size_t halo_slot() const { return (halo_doubles + 2) * sizeof(double); }
   size_t small_off(int parity, int src) const { return ((size_t)parity * nranks + src) * small_slot(); }
   size_t halo_base() const { return 2 * (size_t)nranks * small_slot(); }
@@ -152,23 +152,53 @@ __device__ __forceinline__ bool wait_seq(const unsigned long long *flag, unsigne
   *err = 1;
   return false;
 }
-// device side of SmallGather: block until rank r's record of this round has landed, return it
-__device__ __forceinline__ const double *small_gather_wait(const SmallGather &g, int r) {
-  const double *src = reinterpret_cast<const double *>(g.base + (size_t)r * g.slot);
-  wait_seq(reinterpret_cast<const unsigned long long *>(src + g.cap), g.seq, g.err);
-  return src;
+// Small records travel in a low-latency format: every double is split into two 8-byte words
+// {32 data bits | 32-bit round tag}.  An 8-byte store is atomic, so a word whose tag matches the round carries valid
+// data by itself -- no fence and no separate flag between data and "ready", i.e. one NVLink trip instead of a
+// store + system fence (round trip) + flag store.  (The protocol NCCL calls LL.)
+__device__ __forceinline__ void ll_store(unsigned long long *dst, const double *src, int count, unsigned int tag) {
+  for (int i = 0; i < count; i++) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(src[i]);
+    const unsigned long long lo = (b & 0xffffffffull) | ((unsigned long long)tag << 32);
+    const unsigned long long hi = (b >> 32) | ((unsigned long long)tag << 32);
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst + 2 * i), "l"(lo) : "memory");
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst + 2 * i + 1), "l"(hi) : "memory");
+  }
+}
+// waits until the first `count` doubles of the record carry this round's tag, returns them in out[]
+__device__ __forceinline__ bool ll_load_wait(const unsigned long long *src, double *out, int count, unsigned int tag,
+                                             int *err) {
+  for (int i = 0; i < count; i++) {
+    unsigned long long lo = 0, hi = 0;
+    bool ok = false;
+    for (unsigned int spin = 0; spin < (1u << 23); spin++) {
+      asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(lo) : "l"(src + 2 * i) : "memory");
+      asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(hi) : "l"(src + 2 * i + 1) : "memory");
+      if ((unsigned int)(lo >> 32) == tag && (unsigned int)(hi >> 32) == tag) {
+        ok = true;
+        break;
+      }
+      __nanosleep(spin < 4096 ? 20 : 1000);
+    }
+    if (!ok) {
+      *err = 1;
+      return false;
+    }
+    out[i] = __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
+  }
+  return true;
+}
+// device side of SmallGather: block until rank r's record of this round has landed, copy `count` doubles of it
+__device__ __forceinline__ void small_gather_read(const SmallGather &g, int r, double *out, int count) {
+  ll_load_wait(reinterpret_cast<const unsigned long long *>(g.base + (size_t)r * g.slot), out, count,
+               (unsigned int)g.seq, g.err);
 }
 // producer side of a fused round: lanes 0..nranks-1 of the first warp store the record (8 doubles, written by
-// this CTA before the call and made visible with __syncthreads) into the peers' mailboxes + the flag
+// this CTA before the call and made visible with __syncthreads) into the peers' mailboxes
 __device__ __forceinline__ void dist_push_record(const DistPush &P, const double *rec8) {
   const int q = threadIdx.x;
-  if (q < P.nranks) {
-    double *dst = reinterpret_cast<double *>(P.peer[q] + P.off);
-#pragma unroll
-    for (int i = 0; i < 8; i++) dst[i] = rec8[i];
-    __threadfence_system();
-    st_release_sys_u64(reinterpret_cast<unsigned long long *>(dst + P.cap), P.seq);
-  }
+  if (q < P.nranks)
+    ll_store(reinterpret_cast<unsigned long long *>(P.peer[q] + P.off), rec8, 8, (unsigned int)P.seq);
 }
 // value of halo column c (>= n_own) from the mailbox
 __device__ __forceinline__ double halo_load(const HaloSrc &H, int c) {

@@ -163,9 +163,10 @@ __device__ __forceinline__ void dist_combine(const SmallGather &g, double *sc) {
   if (threadIdx.x < 32) {
     double v0 = 0.0, v1 = 0.0;
     if ((int)threadIdx.x < g.nranks) {
-      const double *src = small_gather_wait(g, threadIdx.x);
-      v0 = __ldcg(src);
-      v1 = __ldcg(src + 1);
+      double v[2];
+      small_gather_read(g, threadIdx.x, v, 2);
+      v0 = v[0];
+      v1 = v[1];
     }
     double s0 = 0.0, s1 = 0.0;
     for (int r = 0; r < g.nranks; r++) {
@@ -808,11 +809,9 @@ __global__ void global_finalize_kernel(int mode, const RedRec *__restrict__ all_
   const bool krylov = !(mode == FIN_NRM_MAX || mode == FIN_NRM_SSQ);
   if (krylov && st->done) return;  // every rank takes the same decision: nobody pushed, nobody waits
   if (sg.base) {
-    if ((int)threadIdx.x < nranks) {
-      const double *src = small_gather_wait(sg, threadIdx.x);
-      double *dst = reinterpret_cast<double *>(&rec[threadIdx.x]);
-      for (int i = 0; i < (int)(sizeof(RedRec) / sizeof(double)); i++) dst[i] = __ldcg(src + i);
-    }
+    if ((int)threadIdx.x < nranks)
+      small_gather_read(sg, threadIdx.x, reinterpret_cast<double *>(&rec[threadIdx.x]),
+                        (int)(sizeof(RedRec) / sizeof(double)));
     __syncwarp();
     all = rec;
   }
