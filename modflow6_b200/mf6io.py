@@ -545,7 +545,10 @@ def read_gwf_model(name, nam_path, base_dir, warnings):
     count = {}
     for ft, fn, pn in stress:
         count[ft] = count.get(ft, 0) + 1
-        sp, _ = read_stress_package(fn, ft, pn or f"{ft[:-1]}-{count[ft]}", shape, inewton)
+        sp, naux = read_stress_package(fn, ft, pn or f"{ft[:-1]}-{count[ft]}", shape, inewton)
+        if naux > 0:
+            warnings.append(f"{name}: {sp.name}: AUXILIARY columns are read but not carried into the budget file "
+                            "records (only a DRN AUXDEPTHNAME column is used)")
         if gi.nodereduced is not None:          # user cellids -> reduced nodes; boundaries in removed cells are dropped
             for iper, p in sp.periods.items():
                 if p is None:
@@ -553,8 +556,10 @@ def read_gwf_model(name, nam_path, base_dir, warnings):
                 red = gi.nodereduced[p.nodelist]
                 keep = red >= 0
                 if not keep.all():
-                    warnings.append(f"{name}: {sp.name} period {iper}: {int((~keep).sum())} boundaries lie in cells "
-                                    "that IDOMAIN removes and are ignored")
+                    # the reference stops with an error for a boundary in a cell that IDOMAIN removes
+                    # (DiscretizationBase noder / "cell is outside active grid domain")
+                    raise Mf6InputError(f"{name}: {sp.name} period {iper}: {int((~keep).sum())} boundaries lie in "
+                                        "cells that IDOMAIN removes")
                 sp.periods[iper] = Package(p.type, red[keep], p.b1[keep], p.b2[keep], p.b3[keep],
                                            iflowred=p.iflowred, flowred=p.flowred)
         gi.packages.append(sp)

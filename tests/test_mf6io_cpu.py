@@ -381,14 +381,18 @@ def test_idomain_reduced_numbering_and_pass_through(tmp_path):
     idom[0, 2, 3] = 0                                      # a hole in the top layer
     chd3 = [((kk, i + 1, 1), 5.0) for kk in (1, 3) for i in range(nrow)] + \
            [((kk, i + 1, ncol), 2.0) for kk in (1, 3) for i in range(nrow)]
-    wel3 = [((3, 3, 3), -30.0), ((1, 3, 4), -10.0)]        # the second one sits in the hole: ignored with a warning
+    wel3 = [((3, 3, 3), -30.0)]
     a = tmp_path / "three"
     a.mkdir()
+    # a boundary in the hole is an input error, as in the reference (not silently dropped)
+    mf6_inputs.write_gwf(str(a), "m", (3, nrow, ncol), 20.0, 25.0, 0.0, [-4.0, -10.0, -18.0], k3, chd={1: chd3},
+                         wel={1: wel3 + [((1, 3, 4), -10.0)]}, strt=3.0, k33=0.2, idomain=idom)
+    mf6_inputs.write_sim(str(a), ["m"], [(1.0, 1, 1.0)], ims)
+    with pytest.raises(mf6io.Mf6InputError, match="IDOMAIN removes"):
+        mf6io.read_simulation(str(a))
     mf6_inputs.write_gwf(str(a), "m", (3, nrow, ncol), 20.0, 25.0, 0.0, [-4.0, -10.0, -18.0], k3, chd={1: chd3},
                          wel={1: wel3}, strt=3.0, k33=0.2, idomain=idom)
-    mf6_inputs.write_sim(str(a), ["m"], [(1.0, 1, 1.0)], ims)
     oa = simulate.run(str(a), ordering=T.ORDER_NATURAL, solution_class=oracle_class())
-    assert any("IDOMAIN removes" in w for w in oa["simulation"].warnings)
     gi = oa["simulation"].models[0]
     assert gi.model.nodes == 2 * nrow * ncol - 1 and gi.nodeuser.size == gi.model.nodes
     # the equivalent 2-layer model: thicknesses 4 and 8, same K per layer, the hole as idomain 0 again
