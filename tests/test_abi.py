@@ -81,3 +81,27 @@ def test_header_is_plain_c_and_a_c_host_links(tmp_path):
     assert "abi 1" in r.stdout
     if not torch.cuda.is_available():
         assert r.returncode == 3 and "no usable GPU" in r.stdout
+
+
+def test_host_only_elimination_order_entry_points():
+    """mf6gpu_model_elimination_order / mf6gpu_ordering_compute need no device: the block ordering of a DIS grid is
+    (checkerboard colour of the cell column, natural index), and the chains derived from the bare sparsity pattern
+    (what the LinearSolverBase seam has) are the same vertical columns"""
+    import ctypes as C
+    import numpy as np
+    from modflow6_b200 import ctypes_types as T, lib
+    from modflow6_b200.grid import build_dis_model
+    nlay, nrow, ncol = 3, 5, 7
+    m = build_dis_model(nlay, nrow, ncol, 1.0, 1.0, 0.0, [-1.0, -2.0, -3.0], 1.0)
+    perm = lib.model_elimination_order(m, T.ORDER_BLOCK_MULTICOLOR)
+    k, i, j = np.unravel_index(np.arange(m.nodes), (nlay, nrow, ncol))
+    want = np.lexsort((np.arange(m.nodes), (i + j) % 2))
+    assert np.array_equal(perm, want)
+    assert np.array_equal(lib.model_elimination_order(m, T.ORDER_NATURAL), np.arange(m.nodes))
+    p2 = np.empty(m.nodes, np.int32)
+    rc = lib.load().mf6gpu_ordering_compute(m.nodes, m.nodes, m.nja, T.ptr_i32(m.ia), T.ptr_i32(m.ja), 0,
+                                            T.ORDER_BLOCK_MULTICOLOR, None, T.ptr_i32(p2))
+    assert rc == 0 and np.array_equal(p2, perm)
+    # multicolour = red-black over cells
+    pm = lib.model_elimination_order(m, T.ORDER_MULTICOLOR)
+    assert np.array_equal(pm, np.lexsort((np.arange(m.nodes), (k + i + j) % 2)))
