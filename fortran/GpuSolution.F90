@@ -54,6 +54,9 @@ module GpuSolutionBindingsModule
     type(c_ptr) :: ibotnode
     type(c_ptr) :: ss, sy, iconvert
     integer(c_int32_t) :: istor_coef, iconf_ss, iorig_ss, reserved
+    ! NPF anisotropy (hy_eff, gwf-npf.f90:2280-2355): all c_null_ptr = K22 == K11, no rotation
+    type(c_ptr) :: k22, angle1, angle2, angle3
+    type(c_ptr) :: conn_nx, conn_ny !< unit normal of every connection (lower -> higher cell), [njas]
   end type mf6gpu_gwf_model
 
   type, bind(C) :: mf6gpu_bnd_package
@@ -160,6 +163,7 @@ module GpuNumericalSolutionModule
   use GhbModule, only: GhbType
   use DrnModule, only: DrnType
   use SimModule, only: store_error
+  use ConstantsModule, only: DZERO
   use TdisModule, only: kper, kstp, delt
   use Mf6GpuBindingsModule, only: mf6gpu_ims_settings, mf6gpu_check
   use GpuSolutionBindingsModule
@@ -171,7 +175,11 @@ module GpuNumericalSolutionModule
     type(c_ptr) :: handle = c_null_ptr !< mf6gpu_solution*
     class(GwfModelType), pointer :: gwf => null() !< the one model of this solution
     real(DP), dimension(:), allocatable :: simvals_all !< package rates, packages concatenated
+    real(DP), dimension(:), allocatable :: conn_nx !< x component of every connection's unit normal (lower -> higher cell)
+    real(DP), dimension(:), allocatable :: conn_ny !< y component
+    real(DP), dimension(:), allocatable :: ddrn !< contiguous copy of the DRN drainage-depth auxiliary column (one DRN package)
   contains
+    procedure :: fill_connection_normals => gpu_fill_connection_normals
     procedure :: sln_ar => gpu_sln_ar
     procedure :: sln_rp => gpu_sln_rp
     procedure :: sln_ca => gpu_sln_ca
@@ -217,6 +225,18 @@ contains
         m%istor_coef = 0; m%iconf_ss = 0; m%iorig_ss = 0
       end if
       m%reserved = 0
+      ! anisotropy: K22 and the rotation angles (already in radians, gwf-npf.f90:1689-1728); the connection normals
+      ! come from dis%connection_normal evaluated once per upper-triangle connection into this%conn_nx / conn_ny
+      m%k22 = c_null_ptr; m%angle1 = c_null_ptr; m%angle2 = c_null_ptr; m%angle3 = c_null_ptr
+      m%conn_nx = c_null_ptr; m%conn_ny = c_null_ptr
+      if (g%npf%ik22 > 0) m%k22 = c_loc(g%npf%k22)
+      if (g%npf%iangle1 > 0) m%angle1 = c_loc(g%npf%angle1)
+      if (g%npf%iangle2 > 0) m%angle2 = c_loc(g%npf%angle2)
+      if (g%npf%iangle3 > 0) m%angle3 = c_loc(g%npf%angle3)
+      if (g%npf%ik22 > 0 .or. g%npf%iangle1 > 0) then
+        call this%fill_connection_normals()
+        m%conn_nx = c_loc(this%conn_nx); m%conn_ny = c_loc(this%conn_ny)
+      end if
     end associate
     ! IMS NONLINEAR block, read by the inherited sln_ar
     s%dvclose = this%dvclose; s%mxiter = this%mxiter; s%nonmeth = this%nonmeth
@@ -270,6 +290,13 @@ contains
         pk(ip)%ptype = 5; pk(ip)%b1 = c_loc(b%bhead); pk(ip)%b2 = c_loc(b%cond)
       type is (DrnType)
         pk(ip)%ptype = 6; pk(ip)%b1 = c_loc(b%elev); pk(ip)%b2 = c_loc(b%cond)
+        ! drainage depth (AUXDEPTHNAME column, gwf-drn.f90:501-530) and cubic scaling (NEWTON / DEV_CUBIC_SCALING)
+        if (b%iauxddrncol > 0) then
+          if (.not. allocated(this%ddrn)) allocate (this%ddrn(b%maxbound))
+          this%ddrn(1:b%nbound) = b%auxvar(b%iauxddrncol, 1:b%nbound)
+          pk(ip)%b3 = c_loc(this%ddrn)
+        end if
+        pk(ip)%iflowred = b%icubic_scaling
       class default
         call store_error('package '//trim(b%packName)//' is outside the GPU path', terminate=.true.)
       end select
@@ -299,6 +326,28 @@ contains
     end if
     ! rep%term_in / term_out / term_id feed model_bdentry (Budget.f90) in package order
   end subroutine gpu_sln_ca
+
+  !> @brief unit normal of every upper-triangle connection, as hy_eff gets it from dis%connection_normal
+  !! (gwf-npf.f90:2318-2320; Dis.f90:1039-1085, Disv.f90:979-1018): evaluated once, the geometry is static
+  subroutine gpu_fill_connection_normals(this)
+    class(GpuNumericalSolutionType) :: this
+    integer(I4B) :: n, m, ipos, jj
+    real(DP) :: zc
+    associate (con => this%gwf%dis%con)
+      allocate (this%conn_nx(con%njas), this%conn_ny(con%njas))
+      this%conn_nx = DZERO
+      this%conn_ny = DZERO
+      do n = 1, this%gwf%dis%nodes
+        do ipos = con%ia(n) + 1, con%ia(n + 1) - 1
+          m = con%ja(ipos)
+          if (m < n) cycle
+          jj = con%jas(ipos)
+          if (con%ihc(jj) == 0) cycle
+          call this%gwf%dis%connection_normal(n, m, con%ihc(jj), this%conn_nx(jj), this%conn_ny(jj), zc, ipos)
+        end do
+      end do
+    end associate
+  end subroutine gpu_fill_connection_normals
 
   subroutine gpu_sln_da(this)
     class(GpuNumericalSolutionType) :: this
