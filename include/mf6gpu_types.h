@@ -115,6 +115,14 @@ typedef struct mf6gpu_gwf_model {
   const double *angle3;
   const double *conn_nx;
   const double *conn_ny;
+  /* NPF REWET (gwf-npf.f90 sgwf_npf_wetdry / rewet_check :2061-2223): wetdry [nodes] may be NULL (no rewetting);
+   * irewet 1 = REWET given; wetfct / iwetit / ihdwet as in the REWET record */
+  const double *wetdry;
+  double wetfct;
+  int32_t irewet;
+  int32_t iwetit;
+  int32_t ihdwet;
+  int32_t reserved2;
 } mf6gpu_gwf_model;
 
 /* ---- stress packages (BoundaryPackage.f90:47-166) ------------------------ */

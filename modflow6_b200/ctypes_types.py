@@ -115,6 +115,12 @@ class GwfModelStruct(C.Structure):
         ("angle3", p_f64),
         ("conn_nx", p_f64),
         ("conn_ny", p_f64),
+        ("wetdry", p_f64),
+        ("wetfct", c_f64),
+        ("irewet", c_i32),
+        ("iwetit", c_i32),
+        ("ihdwet", c_i32),
+        ("reserved2", c_i32),
     ]
 
 

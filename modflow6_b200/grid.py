@@ -92,6 +92,12 @@ class GwfModel:
     angle3: np.ndarray = None
     conn_nx: np.ndarray = None
     conn_ny: np.ndarray = None
+    # NPF REWET: wetdry [nodes] (None = no rewetting) and the REWET record
+    wetdry: np.ndarray = None
+    irewet: int = 0
+    wetfct: float = 1.0
+    iwetit: int = 1
+    ihdwet: int = 0
 
     def __post_init__(self):
         n = self.nodes
@@ -104,7 +110,7 @@ class GwfModel:
         self.ss = T.as_f64(self.ss) if self.ss is not None else np.zeros(n)
         self.sy = T.as_f64(self.sy) if self.sy is not None else np.zeros(n)
         self.iconvert = T.as_i32(self.iconvert) if self.iconvert is not None else np.zeros(n, np.int32)
-        for name in ("k22", "angle1", "angle2", "angle3", "conn_nx", "conn_ny"):
+        for name in ("k22", "angle1", "angle2", "angle3", "conn_nx", "conn_ny", "wetdry"):
             v = getattr(self, name)
             if v is not None:
                 size = self.ihc.size if name.startswith("conn_") else n
@@ -130,10 +136,11 @@ class GwfModel:
                      "istor_coef", "iconf_ss", "iorig_ss"):
             setattr(s, name, int(getattr(self, name)))
         s.ithickstrt = 0
-        for name in ("k22", "angle1", "angle2", "angle3", "conn_nx", "conn_ny"):
+        for name in ("k22", "angle1", "angle2", "angle3", "conn_nx", "conn_ny", "wetdry"):
             v = getattr(self, name)
             if v is not None:
                 setattr(s, name, T.ptr_f64(v))
+        s.irewet, s.iwetit, s.ihdwet, s.wetfct = int(self.irewet), int(self.iwetit), int(self.ihdwet), float(self.wetfct)
         return s
 
     def node(self, k, i, j):
@@ -263,7 +270,7 @@ def build_dis_model(nlay, nrow, ncol, delr, delc, top, botm, k11, k33=None, icel
     ibot = (np.arange(n, dtype=np.int64) % nrc + (nlay - 1) * nrc).astype(np.int32)
     # anisotropy: per-cell arrays + the connection normals of DisType%connection_normal (Dis.f90:1039-1085):
     # towards the next column (1, 0), towards the next row ("front") (0, -1), vertical (0, 0)
-    for name in ("k22", "angle1", "angle2", "angle3"):
+    for name in ("k22", "angle1", "angle2", "angle3", "wetdry"):
         if opts.get(name) is not None:
             opts[name] = _bcast(opts[name], shp)
     if opts.get("k22") is not None or opts.get("angle1") is not None:

@@ -59,6 +59,9 @@ struct orc_solution {
   orc_imslinear *ims;
   int isymmetric;
   int dry_chd; /* a constant-head cell went dry (fatal in the reference) */
+  /* REWET (gwf-npf.f90:2061-2223) */
+  double *wetdry, wetfct;
+  int irewet, iwetit, ihdwet, kiter_cur;
   /* cooley */
   double relaxold, bigchold, bigch;
   /* ptc */
@@ -359,10 +362,40 @@ static void calc_condsat(orc_solution *S) {
   }
 }
 
-/* sgwf_npf_wetdry without rewetting (gwf-npf.f90:2061-2158): a convertible cell whose saturated thickness
- * is gone becomes inactive for good, its head the dry value; a constant head going dry is fatal there */
+/* sgwf_npf_wetdry (gwf-npf.f90:2061-2158) with rewet_check (:2167-2223): first the sequential rewetting sweep (a
+ * dry wettable cell turns wet when a neighbour's head has reached its wetting elevation -- a cell wetted earlier in
+ * the same sweep, ibound 30000, already counts as a wet neighbour), then the drying of cells whose saturated
+ * thickness is gone (a constant head going dry is fatal there), then 30000 -> 1 */
 #define DHDRY (-1.0e30)
-static void npf_wd(orc_solution *S) {
+static void npf_wd(orc_solution *S, int kiter) {
+  if (S->irewet > 0 && S->wetdry && (kiter % S->iwetit) == 0) {
+    for (int n = 0; n < S->nodes; n++) {
+      for (int ii = S->ia[n] + 1; ii < S->ia[n + 1]; ii++) {
+        if (S->ibound[n] != 0 || S->wetdry[n] == 0.0) break; /* rewet_check returns at once for such a cell */
+        const int m = S->ja[ii];
+        const int ihc = S->ihc[S->jas[ii]];
+        const double hm = S->x[m];
+        const int ibdm = S->ibound[m];
+        const double bbot = S->bot[n], wd = S->wetdry[n];
+        double awd = wd;
+        if (wd < 0) awd = -wd;
+        const double turnon = bbot + awd;
+        int irewet = 0;
+        if (ihc == 0) {
+          if (ibdm > 0 && hm >= turnon) irewet = 1;
+        } else if (wd > 0.0) {
+          if (ibdm > 0 && hm >= turnon) irewet = 1;
+        }
+        if (irewet == 1) {
+          if (S->ihdwet == 0)
+            S->x[n] = bbot + S->wetfct * (hm - bbot);
+          else
+            S->x[n] = bbot + S->wetfct * awd;
+          S->ibound[n] = 30000;
+        }
+      }
+    }
+  }
   for (int n = 0; n < S->nodes; n++) {
     if (S->ibound[n] == 0 || S->icelltype[n] == 0) continue;
     double ttop = S->top[n];
@@ -374,13 +407,17 @@ static void npf_wd(orc_solution *S) {
       }
       S->x[n] = DHDRY;
       S->ibound[n] = 0;
-      S->ibound0[n] = 0; /* stays dry in later stress periods (no rewetting) */
     }
+  }
+  for (int n = 0; n < S->nodes; n++) {
+    if (S->ibound[n] == 30000) S->ibound[n] = 1;
+    /* what the next chd_rp restores: the cell's own state without the constant-head marks */
+    if (S->ibound[n] >= 0) S->ibound0[n] = S->ibound[n];
   }
 }
 
 static void npf_cf(orc_solution *S) {
-  if (!S->inewton) npf_wd(S); /* npf_cf :454-457 */
+  if (!S->inewton) npf_wd(S, S->kiter_cur); /* npf_cf :454-457 */
   for (int n = 0; n < S->nodes; n++) {
     if (S->icelltype[n] != 0) {
       double satn = (S->ibound[n] == 0) ? 0.0 : thksat(S, n, S->x[n]);
@@ -958,6 +995,13 @@ orc_solution *orc_sln_create(const mf6gpu_gwf_model *m,
   S->isymmetric = (ls->ilinmeth == 1) ? 1 : 0; /* NumericalSolution.f90:914-916 */
   calc_hyc(S, m);
   calc_condsat(S);
+  S->wetdry = m->wetdry ? dup_d(m->wetdry, n) : NULL;
+  S->irewet = (m->wetdry && m->irewet) ? 1 : 0;
+  S->wetfct = m->wetfct;
+  S->iwetit = m->iwetit > 0 ? m->iwetit : 1;
+  S->ihdwet = m->ihdwet;
+  /* prepcheck (gwf-npf.f90:1817-1821): without NEWTON the wet/dry routine runs once on the initial heads, kiter = 0 */
+  if (!S->inewton) npf_wd(S, 0);
   return S;
 }
 
@@ -979,7 +1023,7 @@ void orc_sln_destroy(orc_solution *S) {
   free_pkgs(S);
   free(S->ia); free(S->ja); free(S->jas); free(S->isym); free(S->ihc);
   free(S->cl1); free(S->cl2); free(S->hwva); free(S->top); free(S->bot);
-  free(S->area); free(S->k11); free(S->k33); free(S->ss); free(S->sy); free(S->hyc);
+  free(S->area); free(S->k11); free(S->k33); free(S->ss); free(S->sy); free(S->hyc); free(S->wetdry);
   free(S->icelltype); free(S->iconvert); free(S->ibound0); free(S->ibound);
   free(S->ibotnode); free(S->x); free(S->xold); free(S->sat); free(S->condsat);
   free(S->amat); free(S->rhs); free(S->xtemp); free(S->dxold); free(S->wsave);
@@ -990,6 +1034,10 @@ void orc_sln_destroy(orc_solution *S) {
 }
 
 void orc_sln_set_packages(orc_solution *S, int npkg, const mf6gpu_bnd_package *pk) {
+  /* chd_rp (gwf-chd.f90:124-141): the cells of the previous constant-head list become ordinary active cells */
+  for (int k = 0; k < S->npkg; k++)
+    if (S->pkg[k].type == MF6GPU_PKG_CHD)
+      for (int i = 0; i < S->pkg[k].nbound; i++) S->ibound0[S->pkg[k].nodelist[i]] = 1;
   free_pkgs(S);
   S->npkg = npkg;
   S->pkg = (pkg_t *)calloc((size_t)(npkg ? npkg : 1), sizeof(pkg_t));
@@ -1144,6 +1192,7 @@ static void ls_fixups(orc_solution *S, int kiter, int kstp, int kper, int iptc,
 void orc_sln_formulate(orc_solution *S, int kiter, double delt, int iss) {
   S->delt = delt;
   S->iss = iss;
+  S->kiter_cur = kiter;
   buildsystem(S, 1);
   int iptc;
   double ptcf;
@@ -1238,6 +1287,7 @@ static void get_dxmax(orc_solution *S, double *hncg, int *lrch) {
 /* sln_backtracking :2680-2776 (+ get_backtracking_flag / apply_backtracking :2790-2842) */
 static void backtracking(orc_solution *S, int kiter) {
   const mf6gpu_sln_settings *c = &S->ss_;
+  S->kiter_cur = kiter;
   buildsystem(S, 0);
   if (kiter == 1) {
     S->res_prev = l2norm_resid(S);
@@ -1277,6 +1327,7 @@ static void backtracking(orc_solution *S, int kiter) {
 static int solve_outer(orc_solution *S, int kiter, int kstp, int kper,
                        double *hncg, int *lrch) {
   double t0 = now_s();
+  S->kiter_cur = kiter;
   if (S->ss_.numtrack > 0) backtracking(S, kiter);
   buildsystem(S, 1);
   int iptc;
@@ -1322,6 +1373,13 @@ int orc_sln_timestep(orc_solution *S, int kper, int kstp, double delt, int iss,
   double tf0 = S->t_form, tl0 = S->t_ls;
   /* prepareSolve -> gwf_ad :396-442 ; chd_ad gwf-chd.f90:175-197 */
   for (int i = 0; i < S->nodes; i++) S->xold[i] = S->x[i];
+  /* npf_ad (gwf-npf.f90:393-408): a dry wettable cell starts the step with hold = bottom, hnew = HDRY */
+  if (S->irewet > 0)
+    for (int i = 0; i < S->nodes; i++) {
+      if (S->wetdry[i] == 0.0 || S->ibound[i] != 0) continue;
+      S->xold[i] = S->bot[i];
+      S->x[i] = DHDRY;
+    }
   for (int k = 0; k < S->npkg; k++) {
     pkg_t *p = &S->pkg[k];
     if (p->type != MF6GPU_PKG_CHD) continue;

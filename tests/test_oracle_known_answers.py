@@ -434,3 +434,66 @@ def test_ilut_known_answers():
     it0, cv0 = OracleIms(m.ia, m.ja, s0).solve(a, xz, b)
     assert cv5 == 1 and cv0 == 1 and it5 < it0
     assert np.abs(x5 - xz).max() < 1e-7
+
+
+NPF02_1LAY = np.array([
+    [1.000000000000000000e02, 9.491194679807708212e01, 8.963852725425633139e01, 8.415783778939784554e01,
+     7.844327180838388358e01, 7.246196989134719502e01, 6.617253575516674857e01, 5.952154961171697778e01,
+     5.243800230005604845e01, 4.482387907284233819e01, 3.653700567841701030e01, 2.735652405614735727e01,
+     1.690257501779389671e01, 4.399393234039389533e00, -4.000000000000000000e01],
+    [2.500000000000000000e01, 2.236586340188107513e01, 1.963190756499453116e01, 1.678583852445553148e01,
+     1.381261073936328998e01, 1.069347358389677538e01, 7.404548318470112633e00, 3.914611143252753056e00,
+     1.814550305069945468e-01, -3.854475465269350920e00, -8.282216319385574010e00, -1.324637250326845006e01,
+     -1.901458294740395516e01, -2.622133464488191024e01, -4.000000000000000000e01]])
+NPF02_3LAY = np.array([
+    [1.000000000000000000e02, 9.496635368428880497e01, 8.974621521357816789e01, 8.432145824563308167e01,
+     7.866533338822696919e01, 7.274409668492738490e01, 6.651345136714729733e01, 5.991038738691469945e01,
+     5.278755954306133447e01, 4.516004619735397796e01, 3.696996838160407606e01, 2.789393025475152399e01,
+     1.752424435308674333e01, 4.558574627023233461e00, -4.000000000000000000e01],
+    [2.500000000000000000e01, 2.237276762221516435e01, 1.964557102731594540e01, 1.680659328791805862e01,
+     1.384042482892330028e01, 1.072732402849822897e01, 7.440599125420748194e00, 3.939435701073743079e00,
+     9.093214618820914807e-02, -3.940381765174159057e00, -8.354930726606033531e00, -1.330380168293016219e01,
+     -1.905635937367108212e01, -2.625249959368398223e01, -4.000000000000000000e01]])
+
+
+def npf02_rewet_case(nlay):
+    """autotest/test_gwf_npf02_rewet.py:8-200 (cases a / c, one model): 10 rows x 15 columns, 1 or 3 convertible
+    layers, K 10, strt -40, REWET WETFCT 1 IWETIT 1 IHDWET 1, WETDRY -0.001, CHD 100 (period 2: 25) on the left
+    wherever the layer bottom lies below it and -40 on the right; CG + MILU0 (relax 1), closure 0.1 / 0.01.
+    Returns (model, [packages of period 1, of period 2], sln, ims)."""
+    nrow, ncol = 10, 15
+    delr, delc = 15.0 * 500.0 / ncol, 10.0 * 500.0 / nrow
+    botm = [-50.0] if nlay == 1 else [50.0, 0.0, -50.0]
+    m = build_dis_model(nlay, nrow, ncol, delr, delc, 150.0, botm, 10.0, icelltype=1, strt=-40.0,
+                        wetdry=-0.001, irewet=1, wetfct=1.0, iwetit=1, ihdwet=1)
+    def chd(vl):
+        left = [(k * nrow + i) * ncol for k in range(nlay) for i in range(nrow) if botm[k] < vl]
+        right = [(k * nrow + i) * ncol + ncol - 1 for k in range(nlay) for i in range(nrow) if botm[k] < -40.0]
+        return [Package(T.PKG_CHD, left, np.full(len(left), vl)), Package(T.PKG_CHD, right, np.full(len(right), -40.0))]
+    ims = T.ImsSettings.make(dvclose=1e-1, rclose=0.01, iter1=100, ilinmeth=1, relax=1.0)
+    sln = T.SlnSettings.make(dvclose=1e-1, mxiter=1000, nonmeth=0)
+    return m, [chd(100.0), chd(25.0)], sln, ims
+
+
+def npf02_profile(x, nlay):
+    """the test's own reduction: the head of the highest wet layer along the middle row (:281-303)"""
+    h = np.asarray(x).reshape(nlay, 10, 15)[:, 5, :]
+    ht = np.full(15, 1e30)
+    for k in range(nlay):
+        sel = (ht == 1e30) & (h[k] != -1e30)
+        ht[sel] = h[k][sel]
+    return ht
+
+
+@pytest.mark.parametrize("nlay", [1, 3])
+def test_npf02_rewet_literal_heads(nlay):
+    """autotest/test_gwf_npf02_rewet.py:203-327 -- the literal head profiles of both stress periods, to the
+    reference's own tolerance 1e-9: rewetting sweep (rewet_check) + drying + npf_ad + the chd_rp reset"""
+    m, periods, sln, ims = npf02_rewet_case(nlay)
+    S = OracleSolution(m, sln, ims)
+    want = NPF02_1LAY if nlay == 1 else NPF02_3LAY
+    for kper, pk in enumerate(periods, start=1):
+        S.set_packages(pk)
+        rep = S.timestep(kper, 1, 1.0, 1)
+        assert rep.converged == 1
+        assert np.abs(npf02_profile(S.x, nlay) - want[kper - 1]).max() < 1e-9
