@@ -57,6 +57,10 @@ module GpuSolutionBindingsModule
     ! NPF anisotropy (hy_eff, gwf-npf.f90:2280-2355): all c_null_ptr = K22 == K11, no rotation
     type(c_ptr) :: k22, angle1, angle2, angle3
     type(c_ptr) :: conn_nx, conn_ny !< unit normal of every connection (lower -> higher cell), [njas]
+    ! NPF REWET (sgwf_npf_wetdry / rewet_check, gwf-npf.f90:2061-2223)
+    type(c_ptr) :: wetdry
+    real(c_double) :: wetfct
+    integer(c_int32_t) :: irewet, iwetit, ihdwet, reserved2
   end type mf6gpu_gwf_model
 
   type, bind(C) :: mf6gpu_bnd_package
@@ -233,6 +237,11 @@ contains
       if (g%npf%iangle1 > 0) m%angle1 = c_loc(g%npf%angle1)
       if (g%npf%iangle2 > 0) m%angle2 = c_loc(g%npf%angle2)
       if (g%npf%iangle3 > 0) m%angle3 = c_loc(g%npf%angle3)
+      m%wetdry = c_null_ptr; m%irewet = 0; m%iwetit = 1; m%ihdwet = 0; m%wetfct = 1.0_DP; m%reserved2 = 0
+      if (g%npf%irewet > 0) then
+        m%wetdry = c_loc(g%npf%wetdry); m%irewet = 1
+        m%wetfct = g%npf%wetfct; m%iwetit = g%npf%iwetit; m%ihdwet = g%npf%ihdwet
+      end if
       if (g%npf%ik22 > 0 .or. g%npf%iangle1 > 0) then
         call this%fill_connection_normals()
         m%conn_nx = c_loc(this%conn_nx); m%conn_ny = c_loc(this%conn_ny)

@@ -119,6 +119,98 @@ __global__ void npf_wd_kernel(ModelView M, double *__restrict__ x, int *__restri
   }
 }
 
+// ---- rewetting (rewet_check, gwf-npf.f90:2167-2223, driven by the first loop of sgwf_npf_wetdry :2096-2107) ----------
+// The reference sweeps the cells in their natural order and a cell wetted earlier in the sweep (ibound 30000) already
+// counts as a wet neighbour, i.e. the outcome for cell n depends on the outcome for its lower-numbered dry neighbours.
+// Reproduced exactly in passes: a candidate (dry, WETDRY != 0) is evaluated in the first pass in which all its
+// lower-numbered neighbouring candidates have been decided in EARLIER passes; its neighbours are visited in ascending
+// original number like the reference's ja order and the first one that qualifies wets it.  Higher-numbered
+// neighbours are seen in their pre-sweep state (a 30000 there means "was dry").  state: 0 undecided, else the pass
+// in which the cell was decided (1 = not a candidate).
+__global__ void rewet_begin_kernel(int n, const double *__restrict__ wetdry, const int *__restrict__ ibound,
+                                   int *__restrict__ state) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x)
+    state[r] = (ibound[r] == 0 && wetdry[r] != 0.0) ? 0 : 1;
+}
+
+__global__ void rewet_pass_kernel(ModelView M, const int *__restrict__ orig, const double *__restrict__ wetdry,
+                                  double *x, int *ibound, int *state, int pass, double wetfct, int ihdwet,
+                                  int *__restrict__ pending) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < M.n; r += gridDim.x * blockDim.x) {
+    if (state[r] != 0) continue;
+    const long long base = (long long)M.slice_ptr[r >> 5] + (r & 31);
+    const int len = M.rowlen[r], o_r = orig[r];
+    // neighbours in ascending original number (insertion sort of at most 15 entries; longer rows keep the tail order)
+    int nb[16], no[16], nh[16], cnt = 0;
+    bool wait = false;
+    for (int k = 1; k < len && cnt < 16; k++) {
+      const int c = M.col[base + 32LL * k];
+      if (c >= M.n) continue;  // halo column (not on this path)
+      const int sc = M.slot_conn[base + 32LL * k];
+      if (sc < 0) continue;
+      const int o_c = orig[c];
+      if (o_c < o_r) {
+        const int stc = state[c];
+        if (stc == 0 || stc >= pass) wait = true;  // a lower-numbered candidate is not decided yet
+      }
+      int q = cnt++;
+      while (q > 0 && no[q - 1] > o_c) {
+        nb[q] = nb[q - 1];
+        no[q] = no[q - 1];
+        nh[q] = nh[q - 1];
+        q--;
+      }
+      nb[q] = c;
+      no[q] = o_c;
+      nh[q] = M.ihc[sc >> 1];
+    }
+    if (wait) {
+      *pending = 1;
+      continue;
+    }
+    const double bbot = M.bot[r], wd = wetdry[r];
+    const double awd = (wd < 0.0) ? -wd : wd;
+    const double turnon = bbot + awd;
+    for (int q = 0; q < cnt; q++) {
+      const int c = nb[q];
+      int ibd = ibound[c];
+      if (no[q] > o_r && ibd == 30000) ibd = 0;  // not reached yet by the reference's sweep: still dry
+      const double hm = x[c];
+      bool wet = false;
+      if (nh[q] == 0)
+        wet = (ibd > 0 && hm >= turnon);
+      else if (wd > 0.0)
+        wet = (ibd > 0 && hm >= turnon);
+      if (wet) {
+        x[r] = (ihdwet == 0) ? bbot + wetfct * (hm - bbot) : bbot + wetfct * awd;
+        ibound[r] = 30000;
+        break;
+      }
+    }
+    state[r] = pass;
+  }
+}
+
+// last loop of sgwf_npf_wetdry (:2150-2153) + what the next chd_rp restores (ibound0 = the cell's own state)
+__global__ void rewet_end_kernel(int n, int *__restrict__ ibound, int *__restrict__ ibound0) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    int ib = ibound[r];
+    if (ib == 30000) ibound[r] = ib = 1;
+    if (ib >= 0) ibound0[r] = ib;
+  }
+}
+
+// npf_ad (gwf-npf.f90:393-408): a dry wettable cell starts the time step with hold = bottom and hnew = HDRY
+__global__ void npf_ad_rewet_kernel(int n, const double *__restrict__ wetdry, const int *__restrict__ ibound,
+                                    const double *__restrict__ bot, double *__restrict__ x,
+                                    double *__restrict__ xold) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    if (wetdry[r] == 0.0 || ibound[r] != 0) continue;
+    xold[r] = bot[r];
+    x[r] = -1.0e30;
+  }
+}
+
 // npf_cf (gwf-npf.f90:444-470) + thksat (:775-794)
 __global__ void npf_cf_kernel(ModelView M, const double *__restrict__ h, double *__restrict__ sat) {
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < M.n; r += gridDim.x * blockDim.x) {
@@ -342,6 +434,12 @@ __global__ void chd_ad_kernel(BndView B, double *__restrict__ x, double *__restr
 __global__ void chd_ibound_kernel(BndView B, const int *__restrict__ pkgid, int *__restrict__ ibound) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B.nb; i += gridDim.x * blockDim.x)
     if (B.type[i] == MF6GPU_PKG_CHD) ibound[B.node[i]] = -(pkgid[i] + 1);
+}
+
+// chd_rp, first loop (gwf-chd.f90:134-138): "Reset previous CHDs to active cell"
+__global__ void chd_release_kernel(BndView B, int *__restrict__ ibound0) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B.nb; i += gridDim.x * blockDim.x)
+    if (B.type[i] == MF6GPU_PKG_CHD) ibound0[B.node[i]] = 1;
 }
 
 // calc_chd_rate (gwf-chd.f90:264-320)
@@ -920,7 +1018,13 @@ struct mf6gpu_solution {
   DevBuf<int> below;     // cell under every cell (final numbering); only when a cell can be inactive
   DevBuf<int> b_eff;     // [nb] cell every bound acts on
   DevBuf<int> wd_flag;   // [1] a constant-head cell went dry
-  bool do_wd = false;    // npf wet/dry conversion applies (no NEWTON, convertible cells, single process)
+  bool do_wd = false;    // npf wet/dry conversion applies (no NEWTON, convertible cells)
+  // REWET (rewet_check): wetdry per cell, the REWET record, pass bookkeeping
+  DevBuf<double> wetdry;
+  DevBuf<int> rw_state, rw_pending;
+  int irewet = 0, iwetit = 1, ihdwet = 0, kiter_cur = 1;
+  double wetfct = 1.0;
+  void wetdry_sweep(int kiter);  // sgwf_npf_wetdry: rewetting passes, drying, 30000 -> 1
   bool moving_rch = false;  // some RCH package without FIXED_CELL and cells that can be inactive
   DevBuf<int> slot_conn;
   DevBuf<double> slot_condsat, flowja;
@@ -1049,6 +1153,34 @@ static std::vector<T> permuted(const T *src, const std::vector<int> &perm, T dfl
   return out;
 }
 
+// sgwf_npf_wetdry (gwf-npf.f90:2061-2158): [rewetting sweep] + drying + [30000 -> 1]
+void mf6gpu_solution::wetdry_sweep(int kiter) {
+  const ModelView M = view();
+  const int G = grid_for(n);
+  const bool rewet = irewet > 0 && wetdry.n > 0 && (kiter % iwetit) == 0;
+  if (rewet) {
+    rewet_begin_kernel<<<G, kBlock, 0, stream>>>(n, wetdry.p, ibound.p, rw_state.p);
+    nl++;
+    for (int pass = 2; pass < n + 3; pass++) {
+      rw_pending.zero(stream);
+      rewet_pass_kernel<<<G, kBlock, 0, stream>>>(M, A->d_perm.p, wetdry.p, x.p, ibound.p, rw_state.p, pass, wetfct,
+                                                  ihdwet, rw_pending.p);
+      nl++;
+      int pend = 0;
+      MF6_CK(cudaMemcpyAsync(&pend, rw_pending.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+      MF6_CK(cudaStreamSynchronize(stream));
+      if (!pend) break;
+    }
+  }
+  npf_wd_kernel<<<G, kBlock, 0, stream>>>(M, x.p, ibound.p, ibound0.p, wd_flag.p);
+  nl++;
+  if (irewet > 0 && wetdry.n > 0) {
+    rewet_end_kernel<<<G, kBlock, 0, stream>>>(n, ibound.p, ibound0.p);
+    nl++;
+  }
+  MF6_CK(cudaGetLastError());
+}
+
 // sln_buildsystem (:1941-1991): sln_reset + gwf_cf + gwf_fc [+ Newton terms]
 void mf6gpu_solution::buildsystem(int inewton) {
   const ModelView M = view();
@@ -1061,8 +1193,7 @@ void mf6gpu_solution::buildsystem(int inewton) {
   if (inewton && o.inewton) nl += 1 + (nseg > 0 ? 1 : 0);
   if (!o.all_confined) {
     if (do_wd) {
-      npf_wd_kernel<<<grid_for(n), kBlock, 0, stream>>>(M, x.p, ibound.p, ibound0.p, wd_flag.p);
-      nl++;
+      wetdry_sweep(kiter_cur);
       if (halo.active()) {
         // split-model path: the neighbours' copies of the cells that have just gone dry (ibound 0, head = HDRY)
         // are refreshed before the conductances are formed -- what the reference re-synchronises per outer
@@ -1211,6 +1342,7 @@ int mf6gpu_solution::solve_outer(int kiter, int kstp, int kper, double &hncg, in
   const int G = grid_for(n);
   MF6_CK(cudaEventRecord(ev[0], stream));
   nvtxRangePushA("Formulate");
+  kiter_cur = kiter;
   if (ss.numtrack > 0) backtracking(kiter);
   buildsystem(1);
   int iptc;
@@ -1527,6 +1659,16 @@ static void create_solution(const mf6gpu_gwf_model *m, const mf6gpu_sln_settings
       // the cell under every cell (highest_active walks the m > n vertical connections)
       s->do_wd = (m->inewton == 0) && anyconv;
       s->wd_flag.alloc_zero(1);
+      if (m->wetdry && m->irewet) {
+        MF6_REQUIRE(!da, "solution_create: REWET is not available on the split-model path");
+        s->wetdry.upload(permuted(m->wetdry, perm, 0.0));
+        s->rw_state.alloc_zero((size_t)n_own);
+        s->rw_pending.alloc_zero(1);
+        s->irewet = 1;
+        s->iwetit = m->iwetit > 0 ? m->iwetit : 1;
+        s->ihdwet = m->ihdwet;
+        s->wetfct = m->wetfct;
+      }
       bool anyinactive = false;
       for (int i = 0; i < n_own; i++)
         if (m->ibound && m->ibound[i] == 0) anyinactive = true;
@@ -1650,6 +1792,12 @@ static void create_solution(const mf6gpu_gwf_model *m, const mf6gpu_sln_settings
         MF6_CK(cudaGetLastError());
         MF6_CK(cudaStreamSynchronize(s->stream));
       }
+      // prepcheck (gwf-npf.f90:1817-1821): without NEWTON the wet/dry routine runs once on the initial heads
+      // (kiter = 0); the split-model path does it in its first formulate, after the first halo exchange
+      if (s->do_wd && !da) {
+        s->wetdry_sweep(0);
+        MF6_CK(cudaStreamSynchronize(s->stream));
+      }
     } catch (const std::exception &e) {
       const std::string keep = e.what();
       mf6gpu_solution_destroy(s);
@@ -1691,6 +1839,12 @@ int mf6gpu_solution_set_packages(mf6gpu_solution *s, int32_t npkg, const mf6gpu_
   return guard([&] {
     MF6_REQUIRE(s && (npkg == 0 || pk), "solution_set_packages: null argument");
     MF6_REQUIRE(npkg <= MF6GPU_MAX_BUDGET_TERMS - 2, "solution_set_packages: too many packages");
+    // chd_rp (gwf-chd.f90:134-138): the cells of the PREVIOUS constant-head list become ordinary active cells
+    if (s->nb > 0) {
+      chd_release_kernel<<<grid_for(s->nb), kBlock, 0, s->stream>>>(s->bview(), s->ibound0.p);
+      MF6_CK(cudaGetLastError());
+      MF6_CK(cudaStreamSynchronize(s->stream));
+    }
     int nb = 0;
     for (int k = 0; k < npkg; k++) nb += pk[k].nbound;
     std::vector<unsigned char> type(nb), flag(nb);
@@ -1778,6 +1932,7 @@ int mf6gpu_solution_formulate(mf6gpu_solution *s, int32_t kiter, double delt, in
     MF6_REQUIRE(s, "solution_formulate: null argument");
     s->delt = delt;
     s->iss = iss;
+    s->kiter_cur = kiter;
     if (s->nb > 0) chd_ad_kernel<<<grid_for(s->nb), kBlock, 0, s->stream>>>(s->bview(), s->x.p, s->xold.p);
     s->buildsystem(1);
     int iptc;
@@ -1801,6 +1956,8 @@ int mf6gpu_solution_timestep(mf6gpu_solution *s, int32_t kper, int32_t kstp, dou
     s->nl = 2 + 4 + (s->nb > 0 ? 3 : 0);  // prepareSolve + finalizeSolve kernels (budget reductions not counted)
     // prepareSolve: gwf_ad (xold = x) ; chd_ad
     copy_d_kernel<<<G, kBlock, 0, st>>>(n, s->x.p, s->xold.p);
+    if (s->irewet > 0)
+      npf_ad_rewet_kernel<<<G, kBlock, 0, st>>>(n, s->wetdry.p, s->ibound.p, s->bot.p, s->x.p, s->xold.p);
     if (s->nb > 0) chd_ad_kernel<<<grid_for(s->nb), kBlock, 0, st>>>(s->bview(), s->x.p, s->xold.p);
     MF6_CK(cudaGetLastError());
     int kiter, inner_total = 0, lrch = -1;

@@ -468,18 +468,31 @@ def read_gwf_model(name, nam_path, base_dir, warnings):
     nb = read_blocks(files["NPF6"])
     nopt = _options(_block(nb, "OPTIONS", required=False))
     for k in nopt:
-        if k in ("THICKSTRT", "XT3D", "REWET", "TVK6"):
+        if k in ("THICKSTRT", "XT3D", "TVK6"):
             raise Mf6InputError(f"NPF option {k} is not supported on the GPU path")
     np_ = read_griddata(_block(nb, "GRIDDATA"), base_dir,
                         {"ICELLTYPE": (ashape, np.int32), "K": (ashape, np.float64), "K22": (ashape, np.float64),
                          "K33": (ashape, np.float64), "ANGLE1": (ashape, np.float64), "ANGLE2": (ashape, np.float64),
-                         "ANGLE3": (ashape, np.float64)})
+                         "ANGLE3": (ashape, np.float64), "WETDRY": (ashape, np.float64)})
     # K22OVERK / K33OVERK: the arrays hold ratios (gwf-npf.f90 prepcheck: k22 = k22 * k11, k33 = k33 * k11)
     if "K22OVERK" in nopt and "K22" in np_:
         np_["K22"] = np_["K22"] * np_["K"]
     if "K33OVERK" in nopt and "K33" in np_:
         np_["K33"] = np_["K33"] * np_["K"]
     kw = {}
+    if "REWET" in nopt:
+        # REWET WETFCT <wetfct> IWETIT <iwetit> IHDWET <ihdwet> (gwf-npf.dfn); needs the WETDRY array (:1677-1684)
+        r = [t.upper() for t in nopt["REWET"]]
+        if "WETDRY" not in np_:
+            raise Mf6InputError("NPF: REWET needs the WETDRY array")
+        if inewton:
+            raise Mf6InputError("NPF: REWET cannot be used with NEWTON")
+        if "IDOMAIN" in g and (g["IDOMAIN"] <= 0).any():
+            raise Mf6InputError("NPF: REWET on a grid with removed cells (IDOMAIN <= 0) is not supported on the GPU path")
+        kw.update(irewet=1, wetdry=np_["WETDRY"].reshape(-1),
+                  wetfct=float(r[r.index("WETFCT") + 1]) if "WETFCT" in r else 1.0,
+                  iwetit=int(r[r.index("IWETIT") + 1]) if "IWETIT" in r else 1,
+                  ihdwet=int(r[r.index("IHDWET") + 1]) if "IHDWET" in r else 0)
     aniso = ("K22" in np_ and not np.array_equal(np_["K22"], np_["K"])) or any(a in np_ for a in ("ANGLE1", "ANGLE2", "ANGLE3"))
     if aniso:
         # hy_eff (gwf-npf.f90:2280-2355); angles are given in degrees and stored in radians (:1213-1239)

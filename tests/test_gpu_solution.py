@@ -297,3 +297,31 @@ def test_k22_rotated_anisotropy_parity(gpu, ordering, angles):
     O0.set_packages(cfg.periods[0].packages)
     O0.timestep()
     assert np.abs(O0.x - b["head"]).max() > 1e-3
+
+
+@pytest.mark.parametrize("ordering", [T.ORDER_NATURAL, T.ORDER_BLOCK_MULTICOLOR])
+@pytest.mark.parametrize("nlay", [1, 3])
+def test_npf02_rewet_on_device(gpu, nlay, ordering):
+    """autotest/test_gwf_npf02_rewet.py on the device: the literal head profiles of both stress periods (the
+    reference's own tolerance, 1e-9) and the same wet / dry pattern and heads as the oracle -- the rewetting sweep
+    is order dependent in the reference (a cell wetted earlier in the sweep wets its successors), the device
+    reproduces it in dependency passes whatever the ILU ordering"""
+    from modflow6_b200.solution import GpuNumericalSolution
+    from oracle.oracle import OracleSolution
+    from tests.test_oracle_known_answers import NPF02_1LAY, NPF02_3LAY, npf02_profile, npf02_rewet_case
+    m, periods, sln, ims = npf02_rewet_case(nlay)
+    ims.gpu_ordering = ordering
+    G = GpuNumericalSolution(m, sln, ims)
+    O = OracleSolution(m, sln, ims, perm=None if ordering == T.ORDER_NATURAL else G.elimination_order())
+    want = NPF02_1LAY if nlay == 1 else NPF02_3LAY
+    for kper, pk in enumerate(periods, start=1):
+        G.set_packages(pk)
+        O.set_packages(pk)
+        rg, ro = G.timestep(kper, 1, 1.0, 1), O.timestep(kper, 1, 1.0, 1)
+        assert rg.converged == 1 and ro.converged == 1
+        xg, xo = G.x, np.array(O.x)
+        assert np.array_equal(xg == -1.0e30, xo == -1.0e30)
+        wet = xo != -1.0e30
+        assert np.abs(xg[wet] - xo[wet]).max() <= 0.1 * sln.dvclose
+        assert rg.outer_iterations == ro.outer_iterations
+        assert np.abs(npf02_profile(xg, nlay) - want[kper - 1]).max() < 1e-9

@@ -464,3 +464,28 @@ def test_npf05_anisotropy_and_drn_depth_from_decks(tmp_path):
     sp = [p for p in mf6io.read_simulation(d2).models[0].packages if p.ftype.upper().startswith("DRN")][0]
     pk = sp.periods[1]
     assert pk.b1.tolist() == [0.0] and pk.b2.tolist() == [2.5] and pk.b3.tolist() == [1.0] and pk.iflowred == 0
+
+
+def test_npf02_rewet_from_deck(tmp_path):
+    """autotest/test_gwf_npf02_rewet.py (case c: 3 layers) written as input files -- REWET record + WETDRY array
+    through the deck reader, two stress periods with a changing CHD list -- gives the reference's literal heads"""
+    from tests.test_oracle_known_answers import NPF02_3LAY, npf02_profile
+    d = str(tmp_path)
+    nlay, nrow, ncol = 3, 10, 15
+    botm = [50.0, 0.0, -50.0]
+    def chd(vl):
+        rows = [((k + 1, i + 1, 1), vl) for k in range(nlay) for i in range(nrow) if botm[k] < vl]
+        return rows + [((k + 1, i + 1, ncol), -40.0) for k in range(nlay) for i in range(nrow) if botm[k] < -40.0]
+    mf6_inputs.write_gwf(d, "m", (nlay, nrow, ncol), 500.0, 500.0, 150.0, botm, 10.0, strt=-40.0, icelltype=1,
+                         chd={1: chd(100.0), 2: chd(25.0)})
+    npf = (tmp_path / "m.npf").read_text()
+    npf = npf.replace("SAVE_FLOWS", "SAVE_FLOWS\n  REWET WETFCT 1.0 IWETIT 1 IHDWET 1").replace(
+        "END griddata", "  wetdry\n    CONSTANT -0.001\nEND griddata")
+    (tmp_path / "m.npf").write_text(npf)
+    mf6_inputs.write_sim(d, ["m"], [(1.0, 1, 1.0), (1.0, 1, 1.0)],
+                         "BEGIN nonlinear\n  OUTER_DVCLOSE 1e-1\n  OUTER_MAXIMUM 1000\nEND nonlinear\n\n"
+                         "BEGIN linear\n  INNER_MAXIMUM 100\n  INNER_DVCLOSE 1e-1\n  INNER_RCLOSE 0.01\n"
+                         "  LINEAR_ACCELERATION CG\n  RELAXATION_FACTOR 1.0\nEND linear\n")
+    out = simulate.run(d, ordering=T.ORDER_NATURAL, solution_class=oracle_class(), write_output=False)
+    assert all(r["converged"] for r in out["reports"])
+    assert np.abs(npf02_profile(out["heads"][0].ravel(), nlay) - NPF02_3LAY[1]).max() < 1e-9
