@@ -355,8 +355,8 @@ def merge_models(models, exchanges):
     # The merged system carries ONE set of NPF / STO options; the reference keeps them per model.  Models that
     # differ would be solved with model 0's options (silently wrong heads), so refuse them.
     for name in ("icellavg", "inewton", "inewtonur", "iperched", "ivarcv", "idewatcv", "insto", "istor_coef",
-                 "iconf_ss", "iorig_ss"):
-        vals = {int(getattr(m, name)) for m in models}
+                 "iconf_ss", "iorig_ss", "irewet", "iwetit", "ihdwet", "wetfct"):
+        vals = {float(getattr(m, name)) for m in models}
         if len(vals) > 1:
             raise ValueError(f"merge_models: the models differ in option `{name}` ({sorted(vals)}); one solution "
                              "matrix on the GPU path needs the same NPF / STO options in every model")
@@ -369,7 +369,9 @@ def merge_models(models, exchanges):
                     ss=cat("ss"), sy=cat("sy"), iconvert=cat("iconvert"), icellavg=m0.icellavg,
                     inewton=m0.inewton, inewtonur=m0.inewtonur, iperched=m0.iperched, ivarcv=m0.ivarcv,
                     idewatcv=m0.idewatcv, insto=m0.insto, istor_coef=m0.istor_coef, iconf_ss=m0.iconf_ss,
-                    iorig_ss=m0.iorig_ss, shape=None), offs
+                    iorig_ss=m0.iorig_ss, shape=None,
+                    wetdry=cat("wetdry") if m0.irewet else None, irewet=m0.irewet, iwetit=m0.iwetit, ihdwet=m0.ihdwet,
+                    wetfct=m0.wetfct), offs
 
 
 def build_disu_model(iac, ja, ihc, cl12, hwva, top, bot, area, k11, k33=None, icelltype=0, strt=0.0, ss=None,

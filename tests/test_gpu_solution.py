@@ -336,3 +336,19 @@ def test_npf02_rewet_on_device(gpu, nlay, ordering):
             assert np.abs(npf02_profile(xg, nlay) - want[kper - 1]).max() < 1e-9
         else:   # converged to 1e-4 instead of the deck's 0.1: close to the literal profile, not equal to it
             assert np.abs(npf02_profile(xg, nlay) - want[kper - 1]).max() < 0.5
+
+
+@pytest.mark.parametrize("nlay", [1, 3])
+def test_npf02_rewet_two_models_on_device(gpu, nlay):
+    """cases b / d of autotest/test_gwf_npf02_rewet.py on the device: two models + GWF-GWF exchange in one solution,
+    rewetting across the exchange, the reference's literal heads (1e-9)"""
+    from modflow6_b200.solution import GpuNumericalSolution
+    from tests.test_oracle_known_answers import (NPF02_1LAY, NPF02_3LAY, npf02_two_model_case,
+                                                 npf02_two_model_profile)
+    m, periods, sln, ims, offs, ncols = npf02_two_model_case(nlay)
+    G = GpuNumericalSolution(m, sln, ims)
+    want = NPF02_1LAY if nlay == 1 else NPF02_3LAY
+    for kper, pk in enumerate(periods, start=1):
+        G.set_packages(pk)
+        assert G.timestep(kper, 1, 1.0, 1).converged == 1
+        assert np.abs(npf02_two_model_profile(G.x, nlay, offs, ncols) - want[kper - 1]).max() < 1e-9

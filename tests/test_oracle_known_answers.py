@@ -497,3 +497,52 @@ def test_npf02_rewet_literal_heads(nlay):
         rep = S.timestep(kper, 1, 1.0, 1)
         assert rep.converged == 1
         assert np.abs(npf02_profile(S.x, nlay) - want[kper - 1]).max() < 1e-9
+
+
+def npf02_two_model_case(nlay):
+    """cases b / d of autotest/test_gwf_npf02_rewet.py: the same grid as two models (10 + 5 columns) joined by a
+    GWF-GWF exchange, in ONE solution.  Returns (merged model, [packages per period], sln, ims, offsets, ncols)."""
+    from modflow6_b200.grid import merge_models
+    nrow, ncols = 10, [10, 5]
+    botm = [-50.0] if nlay == 1 else [50.0, 0.0, -50.0]
+    ms = [build_dis_model(nlay, nrow, nc, 500.0, 500.0, 150.0, botm, 10.0, icelltype=1, strt=-40.0, wetdry=-0.001,
+                          irewet=1, wetfct=1.0, iwetit=1, ihdwet=1) for nc in ncols]
+    kk, ii = np.meshgrid(np.arange(nlay), np.arange(nrow), indexing="ij")
+    n1 = ((kk * nrow + ii) * ncols[0] + ncols[0] - 1).reshape(-1)
+    n2 = ((kk * nrow + ii) * ncols[1]).reshape(-1)
+    ex = dict(m1=0, m2=1, nodem1=n1, nodem2=n2, ihc=np.ones(n1.size, np.int32), cl1=np.full(n1.size, 250.0),
+              cl2=np.full(n1.size, 250.0), hwva=np.full(n1.size, 500.0))
+    merged, offs = merge_models(ms, [ex])
+    def chd(vl):
+        left = [int(offs[0]) + (k * nrow + i) * ncols[0] for k in range(nlay) for i in range(nrow) if botm[k] < vl]
+        right = [int(offs[1]) + (k * nrow + i) * ncols[1] + ncols[1] - 1 for k in range(nlay) for i in range(nrow)
+                 if botm[k] < -40.0]
+        return [Package(T.PKG_CHD, left, np.full(len(left), vl)), Package(T.PKG_CHD, right, np.full(len(right), -40.0))]
+    ims = T.ImsSettings.make(dvclose=1e-1, rclose=0.01, iter1=100, ilinmeth=1, relax=1.0)
+    sln = T.SlnSettings.make(dvclose=1e-1, mxiter=1000, nonmeth=0)
+    return merged, [chd(100.0), chd(25.0)], sln, ims, offs, ncols
+
+
+def npf02_two_model_profile(x, nlay, offs, ncols):
+    out = []
+    for j, nc in enumerate(ncols):
+        h = np.asarray(x)[int(offs[j]):int(offs[j + 1])].reshape(nlay, 10, nc)[:, 5, :]
+        ht = np.full(nc, 1e30)
+        for k in range(nlay):
+            sel = (ht == 1e30) & (h[k] != -1e30)
+            ht[sel] = h[k][sel]
+        out.append(ht)
+    return np.concatenate(out)
+
+
+@pytest.mark.parametrize("nlay", [1, 3])
+def test_npf02_rewet_two_models_literal_heads(nlay):
+    """cases b / d: rewetting across a GWF-GWF exchange (the exchange is an ordinary connection of the merged
+    system, so `rewet_check` sees the neighbour model's cells) -- the same literal heads, 1e-9"""
+    m, periods, sln, ims, offs, ncols = npf02_two_model_case(nlay)
+    S = OracleSolution(m, sln, ims)
+    want = NPF02_1LAY if nlay == 1 else NPF02_3LAY
+    for kper, pk in enumerate(periods, start=1):
+        S.set_packages(pk)
+        assert S.timestep(kper, 1, 1.0, 1).converged == 1
+        assert np.abs(npf02_two_model_profile(S.x, nlay, offs, ncols) - want[kper - 1]).max() < 1e-9
