@@ -82,6 +82,7 @@ class GwfModel:
     istor_coef: int = 0
     iconf_ss: int = 0
     iorig_ss: int = 0
+    ithickstrt: int = 0      # NPF THICKSTRT: cells with icelltype < 0 are confined with the thickness of their starting head
     shape: tuple = None
     meta: dict = field(default_factory=dict)
     # NPF anisotropy (all None = K22 == K, no rotation): k22 [nodes], angle1/2/3 [nodes] in radians, and the unit
@@ -135,7 +136,7 @@ class GwfModel:
         for name in ("icellavg", "inewton", "inewtonur", "iperched", "ivarcv", "idewatcv", "insto",
                      "istor_coef", "iconf_ss", "iorig_ss"):
             setattr(s, name, int(getattr(self, name)))
-        s.ithickstrt = 0
+        s.ithickstrt = int(self.ithickstrt)
         for name in ("k22", "angle1", "angle2", "angle3", "conn_nx", "conn_ny", "wetdry"):
             v = getattr(self, name)
             if v is not None:

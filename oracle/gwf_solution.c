@@ -59,6 +59,11 @@ struct orc_solution {
   orc_imslinear *ims;
   int isymmetric;
   int dry_chd; /* a constant-head cell went dry (fatal in the reference) */
+  /* THICKSTRT (gwf-npf.f90:1838-1882): initial saturation of every cell (1 unless flagged) */
+  double *sat0;
+  /* HFB (gwf-hfb.f90): barriers between cells noden / nodem, hydraulic characteristic */
+  int nhfb, *hfb_n, *hfb_m, *hfb_pos;
+  double *hfb_hydchr, *hfb_condsav, *hfb_csatsav;
   /* REWET (gwf-npf.f90:2061-2223) */
   double *wetdry, wetfct;
   int irewet, iwetit, ihdwet, kiter_cur;
@@ -351,9 +356,10 @@ static void calc_condsat(orc_solution *S) {
       double csat;
       if (ihc == 0) {
         csat = vcond(1, 1, 1, 1, 0, 1, 1, 1.0, botn, botm, S->hyc ? S->hyc[2 * jj] : S->k33[n],
-                     S->hyc ? S->hyc[2 * jj + 1] : S->k33[m], 1.0, 1.0, topn, topm, botn, botm, S->hwva[jj]);
+                     S->hyc ? S->hyc[2 * jj + 1] : S->k33[m], S->sat0[n], S->sat0[m], topn, topm, botn, botm,
+                     S->hwva[jj]);
       } else {
-        csat = hcond(1, 1, 1, 1, 0, ihc, S->icellavg, 1.0, topn, topm, 1.0, 1.0,
+        csat = hcond(1, 1, 1, 1, 0, ihc, S->icellavg, 1.0, topn, topm, S->sat0[n], S->sat0[m],
                      S->hyc ? S->hyc[2 * jj] : S->k11[n], S->hyc ? S->hyc[2 * jj + 1] : S->k11[m], topn, topm,
                      botn, botm, S->cl1[jj], S->cl2[jj], S->hwva[jj]);
       }
@@ -994,6 +1000,20 @@ orc_solution *orc_sln_create(const mf6gpu_gwf_model *m,
   S->ims = orc_ims_create(S->nodes, S->nja, S->ia, S->ja, ls, perm);
   S->isymmetric = (ls->ilinmeth == 1) ? 1 : 0; /* NumericalSolution.f90:914-916 */
   calc_hyc(S, m);
+  /* prepcheck (gwf-npf.f90:1838-1882): a negative ICELLTYPE means "convertible" without THICKSTRT; with THICKSTRT
+   * the cell is confined with the saturated thickness of its STARTING head (calc_initial_sat :2046-2057) */
+  S->sat0 = (double *)malloc(sizeof(double) * n);
+  for (size_t i = 0; i < n; i++) {
+    S->sat0[i] = 1.0;
+    if (S->icelltype[i] < 0) {
+      if (m->ithickstrt != 0) {
+        if (S->ibound[i] != 0) S->sat0[i] = thksat(S, (int)i, m->strt[i]);
+        S->icelltype[i] = 0;
+      } else {
+        S->icelltype[i] = 1;
+      }
+    }
+  }
   calc_condsat(S);
   S->wetdry = m->wetdry ? dup_d(m->wetdry, n) : NULL;
   S->irewet = (m->wetdry && m->irewet) ? 1 : 0;
@@ -1023,7 +1043,8 @@ void orc_sln_destroy(orc_solution *S) {
   free_pkgs(S);
   free(S->ia); free(S->ja); free(S->jas); free(S->isym); free(S->ihc);
   free(S->cl1); free(S->cl2); free(S->hwva); free(S->top); free(S->bot);
-  free(S->area); free(S->k11); free(S->k33); free(S->ss); free(S->sy); free(S->hyc); free(S->wetdry);
+  free(S->area); free(S->k11); free(S->k33); free(S->ss); free(S->sy); free(S->hyc); free(S->wetdry); free(S->sat0);
+  free(S->hfb_n); free(S->hfb_m); free(S->hfb_pos); free(S->hfb_hydchr); free(S->hfb_condsav); free(S->hfb_csatsav);
   free(S->icelltype); free(S->iconvert); free(S->ibound0); free(S->ibound);
   free(S->ibotnode); free(S->x); free(S->xold); free(S->sat); free(S->condsat);
   free(S->amat); free(S->rhs); free(S->xtemp); free(S->dxold); free(S->wsave);
@@ -1064,6 +1085,101 @@ void orc_sln_set_packages(orc_solution *S, int npkg, const mf6gpu_bnd_package *p
   }
 }
 
+/* ---- HFB (gwf-hfb.f90) ------------------------------------------------------------------- */
+static double hfb_faheight(const orc_solution *S, int n, int m, int jj, int use_heads) {
+  double topn = S->top[n], topm = S->top[m], botn = S->bot[n], botm = S->bot[m];
+  if (use_heads) {
+    if (S->icelltype[n] != 0 && S->x[n] < topn) topn = S->x[n];
+    if (S->icelltype[m] != 0 && S->x[m] < topm) topm = S->x[m];
+  }
+  if (S->ihc[jj] == 2) {
+    double t = topn < topm ? topn : topm, b = botn > botm ? botn : botm;
+    return t - b;
+  }
+  return 0.5 * ((topn - botn) + (topm - botm));
+}
+
+/* hfb_rp: condsat_reset + read_data + condsat_modify (:149-201, 770-832); nodes 0-based */
+void orc_sln_set_hfb(orc_solution *S, int nhfb, const int *noden, const int *nodem, const double *hydchr) {
+  for (int i = 0; i < S->nhfb; i++) S->condsat[S->jas[S->hfb_pos[i]]] = S->hfb_csatsav[i]; /* condsat_reset */
+  free(S->hfb_n); free(S->hfb_m); free(S->hfb_pos); free(S->hfb_hydchr); free(S->hfb_condsav); free(S->hfb_csatsav);
+  S->nhfb = nhfb;
+  size_t c = (size_t)(nhfb ? nhfb : 1);
+  S->hfb_n = (int *)calloc(c, sizeof(int));
+  S->hfb_m = (int *)calloc(c, sizeof(int));
+  S->hfb_pos = (int *)calloc(c, sizeof(int));
+  S->hfb_hydchr = (double *)calloc(c, sizeof(double));
+  S->hfb_condsav = (double *)calloc(c, sizeof(double));
+  S->hfb_csatsav = (double *)calloc(c, sizeof(double));
+  for (int i = 0; i < nhfb; i++) {
+    int n = noden[i], m = nodem[i], pos = -1;
+    for (int p = S->ia[n] + 1; p < S->ia[n + 1]; p++)
+      if (S->ja[p] == m) pos = p;
+    S->hfb_n[i] = n;
+    S->hfb_m[i] = m;
+    S->hfb_pos[i] = pos; /* idxloc: position of (n, m) in ja; < 0 = the cells are not connected (input error) */
+    S->hfb_hydchr[i] = hydchr[i];
+  }
+  for (int i = 0; i < nhfb; i++) { /* condsat_modify */
+    if (S->hfb_pos[i] < 0) continue;
+    int n = S->hfb_n[i], m = S->hfb_m[i], jj = S->jas[S->hfb_pos[i]];
+    double cond = S->condsat[jj];
+    S->hfb_csatsav[i] = cond;
+    if (S->inewton == 1 || (S->icelltype[n] == 0 && S->icelltype[m] == 0)) {
+      if (S->hfb_hydchr[i] > 0.0) {
+        double condhfb = S->hfb_hydchr[i] * S->hwva[jj] * hfb_faheight(S, n, m, jj, 0);
+        cond = cond * condhfb / (cond + condhfb);
+      } else {
+        cond = -cond * S->hfb_hydchr[i];
+      }
+      S->condsat[jj] = cond;
+    }
+  }
+}
+
+/* hfb_fc without XT3D (:296-345): Picard with a convertible cell on either side */
+static void hfb_fc(orc_solution *S) {
+  if (S->inewton != 0) return;
+  for (int i = 0; i < S->nhfb; i++) {
+    int ipos = S->hfb_pos[i];
+    if (ipos < 0) continue;
+    double aterm = S->amat[ipos];
+    int n = S->hfb_n[i], m = S->hfb_m[i];
+    if (S->ibound[n] == 0 || S->ibound[m] == 0) continue;
+    if (S->icelltype[n] != 0 || S->icelltype[m] != 0) {
+      int jj = S->jas[ipos];
+      double cond;
+      if (S->hfb_hydchr[i] > 0.0) {
+        double condhfb = S->hfb_hydchr[i] * 1.0 * S->hwva[jj] * hfb_faheight(S, n, m, jj, 1);
+        cond = aterm * condhfb / (aterm + condhfb);
+      } else {
+        cond = -aterm * S->hfb_hydchr[i];
+      }
+      S->hfb_condsav[i] = cond;
+      S->amat[S->ia[n]] += aterm - cond;
+      S->amat[ipos] = cond;
+      S->amat[S->ia[m]] += aterm - cond;
+      S->amat[S->isym[ipos]] = cond;
+    }
+  }
+}
+
+/* hfb_cq without XT3D (:432-449) */
+static void hfb_cq(orc_solution *S) {
+  if (S->inewton != 0) return;
+  for (int i = 0; i < S->nhfb; i++) {
+    int ipos = S->hfb_pos[i];
+    if (ipos < 0) continue;
+    int n = S->hfb_n[i], m = S->hfb_m[i];
+    if (S->ibound[n] == 0 || S->ibound[m] == 0) continue;
+    if (S->icelltype[n] != 0 || S->icelltype[m] != 0) {
+      double qnm = S->hfb_condsav[i] * (S->x[m] - S->x[n]);
+      S->flowja[ipos] = qnm;
+      S->flowja[S->isym[ipos]] = -qnm;
+    }
+  }
+}
+
 /* sln_buildsystem :1941-1991 (single model, no exchanges) */
 static void buildsystem(orc_solution *S, int inewton) {
   memset(S->amat, 0, sizeof(double) * (size_t)S->nja);
@@ -1073,6 +1189,7 @@ static void buildsystem(orc_solution *S, int inewton) {
   for (int k = 0; k < S->npkg; k++) bnd_cf(S, &S->pkg[k]);
   /* gwf_fc */
   npf_fc(S);
+  if (S->nhfb > 0) hfb_fc(S); /* gwf_fc: right after npf_fc (gwf.f90:500-506) */
   if (S->insto) sto_fc(S);
   for (int k = 0; k < S->npkg; k++) bnd_fc(S, &S->pkg[k]);
   if (inewton && S->inewton) {
@@ -1401,6 +1518,7 @@ int orc_sln_timestep(orc_solution *S, int kper, int kstp, double delt, int iss,
   /* finalizeSolve: gwf_cq :741-778 */
   memset(S->flowja, 0, sizeof(double) * (size_t)S->nja);
   npf_cq(S);
+  if (S->nhfb > 0) hfb_cq(S);
   if (S->insto) sto_cq(S);
   for (int k = 0; k < S->npkg; k++) {
     pkg_t *p = &S->pkg[k];

@@ -65,6 +65,7 @@ def lib():
         L.orc_sln_set_blocks.argtypes = [vp, T.p_i32]
         L.orc_ims_set_blocks.argtypes = [vp, T.p_i32]
         L.orc_sln_set_packages.argtypes = [vp, C.c_int, C.POINTER(T.BndPackageStruct)]
+        L.orc_sln_set_hfb.argtypes = [vp, C.c_int, T.p_i32, T.p_i32, T.p_f64]
         L.orc_sln_timestep.restype = C.c_int
         L.orc_sln_timestep.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(T.StepReport)]
         L.orc_sln_formulate.argtypes = [vp, C.c_int, C.c_double, C.c_int]
@@ -220,6 +221,11 @@ class OracleSolution:
         self._pkgs = list(pkgs)
         arr = package_array(pkgs)
         lib().orc_sln_set_packages(self.h, len(pkgs), arr)
+
+    def set_hfb(self, noden, nodem, hydchr):
+        """horizontal flow barriers between cells noden[i] / nodem[i] (0-based) with hydraulic characteristic"""
+        a, b, h = T.as_i32(noden), T.as_i32(nodem), T.as_f64(hydchr)
+        lib().orc_sln_set_hfb(self.h, a.size, T.ptr_i32(a), T.ptr_i32(b), T.ptr_f64(h))
 
     @property
     def simvals(self):
