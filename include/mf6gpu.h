@@ -192,6 +192,11 @@ int mf6gpu_solution_create_dist(const mf6gpu_gwf_model *model, const mf6gpu_sln_
                                 const int32_t *send_idx, const int32_t *recv_ptr,
                                 const int32_t *global_id, mf6gpu_solution **out);
 int mf6gpu_solution_destroy(mf6gpu_solution *s);
+/* HFB, horizontal flow barriers of the coming stress period(s) (hfb_rp / condsat_modify / hfb_fc / hfb_cq,
+ * gwf-hfb.f90:149-450, 770-832): barrier i lies between the connected cells noden[i], nodem[i] with hydraulic
+ * characteristic hydchr[i] (negative = multiplier of the conductance).  nhfb = 0 removes the barriers. */
+int mf6gpu_solution_set_hfb(mf6gpu_solution *s, int32_t nhfb, const int32_t *noden, const int32_t *nodem,
+                            const double *hydchr, int32_t index_base);
 /* bnd_rp: stress-period data of every package (copied to the device) */
 int mf6gpu_solution_set_packages(mf6gpu_solution *s, int32_t npkg,
                                  const mf6gpu_bnd_package *pk);

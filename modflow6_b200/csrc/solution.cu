@@ -68,19 +68,21 @@ __device__ __forceinline__ double conn_cond(const ModelView &M, int r, int c, in
 }
 
 // calc_condsat (gwf-npf.f90:1950-2037), upper triangle, no THICKSTRT (sat = 1)
+// sat0 (may be null = 1): initial saturation of a THICKSTRT cell (calc_initial_sat, gwf-npf.f90:2046-2057)
 __global__ void condsat_kernel(int njas, const int *__restrict__ conn_n,
-                               const int *__restrict__ conn_m, ModelView M,
+                               const int *__restrict__ conn_m, ModelView M, const double *__restrict__ sat0,
                                double *__restrict__ condsat) {
   for (int jj = blockIdx.x * blockDim.x + threadIdx.x; jj < njas; jj += gridDim.x * blockDim.x) {
     const int n = conn_n[jj], m = conn_m[jj];
     const int ihc = M.ihc[jj];
     const double topn = M.top[n], botn = M.bot[n], topm = M.top[m], botm = M.bot[m];
+    const double satn = sat0 ? sat0[n] : 1.0, satm = sat0 ? sat0[m] : 1.0;
     double csat;
     if (ihc == 0)
       csat = vcond(1, 1, 1, 1, 1, 1, 1.0, botn, botm, M.hyc ? M.hyc[2 * jj] : M.k33[n],
-                   M.hyc ? M.hyc[2 * jj + 1] : M.k33[m], 1.0, 1.0, topn, topm, botn, botm, M.hwva[jj]);
+                   M.hyc ? M.hyc[2 * jj + 1] : M.k33[m], satn, satm, topn, topm, botn, botm, M.hwva[jj]);
     else
-      csat = hcond(1, 1, 1, 1, 0, ihc, M.o.icellavg, 1.0, topn, topm, 1.0, 1.0,
+      csat = hcond(1, 1, 1, 1, 0, ihc, M.o.icellavg, 1.0, topn, topm, satn, satm,
                    M.hyc ? M.hyc[2 * jj] : M.k11[n], M.hyc ? M.hyc[2 * jj + 1] : M.k11[m], topn, topm, botn, botm,
                    M.cl1[jj], M.cl2[jj], M.hwva[jj]);
     condsat[jj] = csat;
@@ -94,6 +96,97 @@ __global__ void slot_condsat_kernel(long long nslots, const int *__restrict__ sl
        s += (long long)gridDim.x * blockDim.x) {
     const int c = slot_conn[s];
     slot_condsat[s] = (c >= 0) ? condsat[c >> 1] : 0.0;
+  }
+}
+
+// ---- HFB, horizontal flow barriers (gwf-hfb.f90) ------------------------------------------------------------------
+struct HfbView {
+  int nhfb;
+  const int *rn, *rm;        // final rows of noden / nodem
+  const int *jas;            // symmetric connection
+  const int *slot_nm, *slot_mn;  // SELL slots of the entries (n, m) and (m, n)
+  const double *hydchr;
+  double *csatsav, *condsav;
+};
+
+__device__ __forceinline__ double hfb_faheight(const ModelView &M, int n, int m, int jj, const double *h) {
+  double topn = M.top[n], topm = M.top[m];
+  const double botn = M.bot[n], botm = M.bot[m];
+  if (h) {
+    if (M.icelltype[n] != 0 && h[n] < topn) topn = h[n];
+    if (M.icelltype[m] != 0 && h[m] < topm) topm = h[m];
+  }
+  if (M.ihc[jj] == 2) return fmin(topn, topm) - fmax(botn, botm);
+  return 0.5 * ((topn - botn) + (topm - botm));
+}
+
+// condsat_modify (gwf-hfb.f90:789-832) / condsat_reset (:770-781): one thread per barrier
+__global__ void hfb_condsat_kernel(HfbView H, ModelView M, double *__restrict__ condsat,
+                                   double *__restrict__ slot_condsat, int reset) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H.nhfb; i += gridDim.x * blockDim.x) {
+    const int jj = H.jas[i], n = H.rn[i], m = H.rm[i];
+    double cond;
+    if (reset) {
+      cond = H.csatsav[i];
+    } else {
+      cond = condsat[jj];
+      H.csatsav[i] = cond;
+      if (M.o.inewton == 1 || (M.icelltype[n] == 0 && M.icelltype[m] == 0)) {
+        if (H.hydchr[i] > 0.0) {
+          const double condhfb = H.hydchr[i] * M.hwva[jj] * hfb_faheight(M, n, m, jj, nullptr);
+          cond = cond * condhfb / (cond + condhfb);
+        } else {
+          cond = -cond * H.hydchr[i];
+        }
+      }
+    }
+    condsat[jj] = cond;
+    slot_condsat[H.slot_nm[i]] = cond;
+    slot_condsat[H.slot_mn[i]] = cond;
+  }
+}
+
+// hfb_fc without XT3D (gwf-hfb.f90:296-345), Picard with a convertible cell on either side: one thread per DISTINCT
+// row walks the barriers of that row in barrier order (the reference's loop order): the row's own off-diagonal entry
+// becomes cond, its diagonal gains aterm - cond.  Both rows of a barrier compute the same cond from the same inputs.
+__global__ void hfb_fc_kernel(int nrows, const int *__restrict__ ev_row, const int *__restrict__ ev_ptr,
+                              const int *__restrict__ ev_hfb, HfbView H, ModelView M, const double *__restrict__ h,
+                              double *__restrict__ val) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nrows; e += gridDim.x * blockDim.x) {
+    const int row = ev_row[e];
+    const long long dslot = (long long)M.slice_ptr[row >> 5] + (row & 31);
+    double diag = val[dslot];
+    for (int q = ev_ptr[e]; q < ev_ptr[e + 1]; q++) {
+      const int i = ev_hfb[q];
+      const int n = H.rn[i], m = H.rm[i], jj = H.jas[i];
+      if (M.ibound[n] == 0 || M.ibound[m] == 0) continue;
+      if (M.icelltype[n] == 0 && M.icelltype[m] == 0) continue;
+      const int slot = (row == n) ? H.slot_nm[i] : H.slot_mn[i];
+      const double aterm = val[slot];
+      double cond;
+      if (H.hydchr[i] > 0.0) {
+        const double condhfb = H.hydchr[i] * 1.0 * M.hwva[jj] * hfb_faheight(M, n, m, jj, h);
+        cond = aterm * condhfb / (aterm + condhfb);
+      } else {
+        cond = -aterm * H.hydchr[i];
+      }
+      if (row == n) H.condsav[i] = cond;
+      diag = diag + (aterm - cond);
+      val[slot] = cond;
+    }
+    val[dslot] = diag;
+  }
+}
+
+// hfb_cq without XT3D (gwf-hfb.f90:432-449)
+__global__ void hfb_cq_kernel(HfbView H, ModelView M, const double *__restrict__ h, double *__restrict__ flowja) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H.nhfb; i += gridDim.x * blockDim.x) {
+    const int n = H.rn[i], m = H.rm[i];
+    if (M.ibound[n] == 0 || M.ibound[m] == 0) continue;
+    if (M.icelltype[n] == 0 && M.icelltype[m] == 0) continue;
+    const double qnm = H.condsav[i] * (h[m] - h[n]);
+    flowja[H.slot_nm[i]] = qnm;
+    flowja[H.slot_mn[i]] = -qnm;
   }
 }
 
@@ -1019,6 +1112,18 @@ struct mf6gpu_solution {
   DevBuf<int> b_eff;     // [nb] cell every bound acts on
   DevBuf<int> wd_flag;   // [1] a constant-head cell went dry
   bool do_wd = false;    // npf wet/dry conversion applies (no NEWTON, convertible cells)
+  // THICKSTRT: initial saturation per cell (empty = 1 everywhere)
+  DevBuf<double> sat0;
+  // HFB: barriers of the current period
+  int nhfb = 0, hfb_nrows = 0;
+  DevBuf<int> hfb_rn, hfb_rm, hfb_jas, hfb_slot_nm, hfb_slot_mn, hfb_ev_row, hfb_ev_ptr, hfb_ev_hfb;
+  DevBuf<double> hfb_hydchr, hfb_csatsav, hfb_condsav;
+  std::vector<int> h_ia, h_ja;   // host copy of the CSR pattern (barrier lookup)
+  int index_base = 0;
+  HfbView hview() const {
+    return HfbView{nhfb, hfb_rn.p, hfb_rm.p, hfb_jas.p, hfb_slot_nm.p, hfb_slot_mn.p, hfb_hydchr.p, hfb_csatsav.p,
+                   hfb_condsav.p};
+  }
   // REWET (rewet_check): wetdry per cell, the REWET record, pass bookkeeping
   DevBuf<double> wetdry;
   DevBuf<int> rw_state, rw_pending;
@@ -1215,6 +1320,13 @@ void mf6gpu_solution::buildsystem(int inewton) {
     assemble_rows_kernel<true><<<G, kBlock, 0, stream>>>(M, x.p, xold.p, sat.p, A->val.p, rhs.p, transient, tled);
   else
     assemble_rows_kernel<false><<<G, kBlock, 0, stream>>>(M, x.p, xold.p, sat.p, A->val.p, rhs.p, transient, tled);
+  if (nhfb > 0 && o.inewton == 0 && !o.all_confined) {
+    // gwf_fc: hfb_fc follows npf_fc (gwf.f90:500-506).  Here STO is already in the diagonal (fused into the row
+    // kernel), so with storage the diagonal is summed in another order than the reference's: last-bit only
+    hfb_fc_kernel<<<grid_for(hfb_nrows), kBlock, 0, stream>>>(hfb_nrows, hfb_ev_row.p, hfb_ev_ptr.p, hfb_ev_hfb.p,
+                                                              hview(), M, x.p, A->val.p);
+    nl++;
+  }
   if (nseg > 0)
     bnd_scatter_kernel<<<grid_for(nseg), kBlock, 0, stream>>>(nseg, seg_node.p, seg_ptr.p, seg_idx.p, B, M,
                                                               x.p, A->val.p, rhs.p, flowja.p, 0);
@@ -1520,7 +1632,6 @@ static std::vector<int32_t> model_column_blocks(const mf6gpu_gwf_model *m, int n
 static void create_solution(const mf6gpu_gwf_model *m, const mf6gpu_sln_settings *sln,
                             const mf6gpu_ims_settings *ims, const DistArgs *da, mf6gpu_solution **out) {
     MF6_REQUIRE(m && sln && ims && out, "solution_create: null argument");
-    MF6_REQUIRE(m->ithickstrt == 0, "solution_create: THICKSTRT is not supported on the GPU path");
     if (!da) MF6_REQUIRE(m->njas * 2 == m->nja - m->nodes, "solution_create: nja/njas/nodes are inconsistent");
     MF6_REQUIRE((long long)m->njas < (1LL << 30), "solution_create: too many connections for one GPU");
     MF6_REQUIRE(!(m->inewton != 0 && ims->ilinmeth == 1),
@@ -1651,9 +1762,45 @@ static void create_solution(const mf6gpu_gwf_model *m, const mf6gpu_sln_settings
       o.iconf_ss = m->iconf_ss;
       o.iorig_ss = m->iorig_ss;
       o.satomega = (m->inewton > 0) ? 1.0e-6 : 0.0;
+      // prepcheck (gwf-npf.f90:1838-1882): a negative ICELLTYPE means "convertible" without THICKSTRT; with THICKSTRT
+      // the cell is confined with the saturated thickness of its STARTING head (calc_initial_sat :2046-2057)
+      std::vector<int> ict(m->icelltype, m->icelltype + n);
+      std::vector<double> sat0;
+      for (int i = 0; i < n; i++) {
+        if (ict[i] >= 0) continue;
+        if (m->ithickstrt != 0) {
+          if (sat0.empty()) sat0.assign((size_t)n, 1.0);
+          if (!m->ibound || m->ibound[i] != 0) {
+            const double tp = m->top[i], bt = m->bot[i], hn = m->strt[i];
+            double sn = (hn >= tp) ? 1.0 : (hn - bt) / (tp - bt);
+            if (m->inewton != 0) {  // sQuadraticSaturation with satomega = 1e-6 (thksat, :775-794)
+              const double eps = 1.0e-6, b = tp - bt;
+              if (b > 0.0) {
+                const double br = (hn < bt) ? 0.0 : (hn > tp ? 1.0 : (hn - bt) / b);
+                const double av = 1.0 / (1.0 - eps), bri = 1.0 - br;
+                if (br < eps)
+                  sn = av * 0.5 * (br * br) / eps;
+                else if (br < (1.0 - eps))
+                  sn = av * br + 0.5 * (1.0 - av);
+                else if (br < 1.0)
+                  sn = 1.0 - ((av * 0.5 * (bri * bri)) / eps);
+                else
+                  sn = 1.0;
+              } else {
+                sn = (hn < bt) ? 0.0 : 1.0;
+              }
+            }
+            sat0[i] = sn;
+          }
+          ict[i] = 0;
+        } else {
+          ict[i] = 1;
+        }
+      }
+      if (!sat0.empty()) s->sat0.upload(permuted(sat0.data(), perm, 1.0));
       bool anyconv = false;
       for (int i = 0; i < n; i++)
-        if (m->icelltype[i] != 0) anyconv = true;
+        if (ict[i] != 0) anyconv = true;
       o.all_confined = (!anyconv && m->iperched == 0 && m->inewton == 0) ? 1 : 0;
       // cells can become / be inactive: wet-dry conversion (no NEWTON, convertible cells) or IDOMAIN holes.  Recharge then needs
       // the cell under every cell (highest_active walks the m > n vertical connections)
@@ -1692,7 +1839,7 @@ static void create_solution(const mf6gpu_gwf_model *m, const mf6gpu_sln_settings
       s->k33.upload(permuted(m->k33 ? m->k33 : m->k11, perm, 0.0));
       s->ssv.upload(permuted(m->ss, perm, 0.0));
       s->syv.upload(permuted(m->sy, perm, 0.0));
-      s->icelltype.upload(permuted(m->icelltype, perm, 0));
+      s->icelltype.upload(permuted(ict.data(), perm, 0));
       s->iconvert.upload(permuted(m->iconvert, perm, 0));
       s->ibound0.upload(permuted(m->ibound, perm, 1));
       s->ibound.upload(permuted(m->ibound, perm, 1));
@@ -1735,6 +1882,9 @@ static void create_solution(const mf6gpu_gwf_model *m, const mf6gpu_sln_settings
       std::vector<int> csr2sell((size_t)nja);
       A->csr2sell.download(csr2sell.data(), (size_t)nja);
       s->h_conn_jas.assign((size_t)nja, -1);
+      s->index_base = base;
+      s->h_ia.assign(m->ia, m->ia + n_own + 1);
+      s->h_ja.assign(m->ja, m->ja + nja);
       for (int v = 0; v < n_own; v++) {
         const int i0 = m->ia[v] - base, i1 = m->ia[v + 1] - base;
         for (int p = i0 + 1; p < i1; p++) {
@@ -1786,7 +1936,8 @@ static void create_solution(const mf6gpu_gwf_model *m, const mf6gpu_sln_settings
         DevBuf<int> dn, dm;
         dn.upload(conn_n);
         dm.upload(conn_m);
-        condsat_kernel<<<grid_for(njas), kBlock, 0, s->stream>>>(njas, dn.p, dm.p, s->view(), s->condsat.p);
+        condsat_kernel<<<grid_for(njas), kBlock, 0, s->stream>>>(njas, dn.p, dm.p, s->view(),
+                                                                 s->sat0.n ? s->sat0.p : nullptr, s->condsat.p);
         slot_condsat_kernel<<<grid_for(A->nslots), kBlock, 0, s->stream>>>(A->nslots, s->slot_conn.p,
                                                                            s->condsat.p, s->slot_condsat.p);
         MF6_CK(cudaGetLastError());
@@ -1832,6 +1983,73 @@ int mf6gpu_solution_destroy(mf6gpu_solution *s) {
     for (auto &e : s->ev)
       if (e) cudaEventDestroy(e);
     delete s;
+  });
+}
+
+// hfb_rp (gwf-hfb.f90:149-201): condsat_reset, the new barrier list, condsat_modify
+int mf6gpu_solution_set_hfb(mf6gpu_solution *s, int32_t nhfb, const int32_t *noden, const int32_t *nodem,
+                            const double *hydchr, int32_t index_base) {
+  return guard([&] {
+    MF6_REQUIRE(s && nhfb >= 0 && (nhfb == 0 || (noden && nodem && hydchr)), "solution_set_hfb: bad argument");
+    MF6_REQUIRE(!s->halo.active(), "solution_set_hfb: HFB is not available on the split-model path");
+    const ModelView M = s->view();
+    if (s->nhfb > 0) {
+      hfb_condsat_kernel<<<grid_for(s->nhfb), kBlock, 0, s->stream>>>(s->hview(), M, s->condsat.p,
+                                                                      s->slot_condsat.p, 1);
+      MF6_CK(cudaGetLastError());
+      MF6_CK(cudaStreamSynchronize(s->stream));
+    }
+    s->nhfb = nhfb;
+    if (nhfb == 0) return;
+    std::vector<int> csr2sell((size_t)s->nja);
+    s->A->csr2sell.download(csr2sell.data(), (size_t)s->nja);
+    const int b0 = s->index_base;
+    auto find = [&](int v, int u) {  // CSR position of (v, u)
+      for (int p = s->h_ia[v] - b0 + 1; p < s->h_ia[v + 1] - b0; p++)
+        if (s->h_ja[p] - b0 == u) return p;
+      return -1;
+    };
+    std::vector<int> rn(nhfb), rm(nhfb), jas(nhfb), snm(nhfb), smn(nhfb);
+    std::vector<double> hc(hydchr, hydchr + nhfb);
+    std::vector<std::pair<int, int>> ev;  // (row, barrier)
+    for (int i = 0; i < nhfb; i++) {
+      const int v = noden[i] - index_base, u = nodem[i] - index_base;
+      MF6_REQUIRE(v >= 0 && v < s->n && u >= 0 && u < s->n, "solution_set_hfb: cell out of range");
+      const int pnm = find(v, u), pmn = find(u, v);
+      MF6_REQUIRE(pnm >= 0 && pmn >= 0, "solution_set_hfb: the two cells of a barrier are not connected");
+      rn[i] = s->A->iperm[v];
+      rm[i] = s->A->iperm[u];
+      jas[i] = s->h_conn_jas[pnm];
+      snm[i] = csr2sell[pnm];
+      smn[i] = csr2sell[pmn];
+      ev.emplace_back(rn[i], i);
+      ev.emplace_back(rm[i], i);
+    }
+    std::sort(ev.begin(), ev.end());
+    std::vector<int> ev_row, ev_ptr, ev_hfb;
+    for (size_t e = 0; e < ev.size(); e++) {
+      if (e == 0 || ev[e].first != ev[e - 1].first) {
+        ev_row.push_back(ev[e].first);
+        ev_ptr.push_back((int)e);
+      }
+      ev_hfb.push_back(ev[e].second);
+    }
+    ev_ptr.push_back((int)ev.size());
+    s->hfb_nrows = (int)ev_row.size();
+    s->hfb_rn.upload(rn);
+    s->hfb_rm.upload(rm);
+    s->hfb_jas.upload(jas);
+    s->hfb_slot_nm.upload(snm);
+    s->hfb_slot_mn.upload(smn);
+    s->hfb_hydchr.upload(hc);
+    s->hfb_csatsav.alloc_zero((size_t)nhfb);
+    s->hfb_condsav.alloc_zero((size_t)nhfb);
+    s->hfb_ev_row.upload(ev_row);
+    s->hfb_ev_ptr.upload(ev_ptr);
+    s->hfb_ev_hfb.upload(ev_hfb);
+    hfb_condsat_kernel<<<grid_for(nhfb), kBlock, 0, s->stream>>>(s->hview(), M, s->condsat.p, s->slot_condsat.p, 0);
+    MF6_CK(cudaGetLastError());
+    MF6_CK(cudaStreamSynchronize(s->stream));
   });
 }
 
@@ -1981,6 +2199,8 @@ int mf6gpu_solution_timestep(mf6gpu_solution *s, int32_t kper, int32_t kstp, dou
     }
     flow_rows_kernel<<<G, kBlock, 0, st>>>(M, s->x.p, s->xold.p, s->sat.p, s->flowja.p, s->strgss.p,
                                            s->strgsy.p, transient, 1.0 / delt);
+    if (s->nhfb > 0 && s->o.inewton == 0 && !s->o.all_confined)
+      hfb_cq_kernel<<<grid_for(s->nhfb), kBlock, 0, st>>>(s->hview(), M, s->x.p, s->flowja.p);
     if (s->nb > 0) {
       bnd_cf_kernel<<<grid_for(s->nb), kBlock, 0, st>>>(B, M, s->x.p);
       bnd_scatter_kernel<<<grid_for(s->nseg), kBlock, 0, st>>>(s->nseg, s->seg_node.p, s->seg_ptr.p,

@@ -35,6 +35,11 @@ class GpuNumericalSolution:
         arr = package_array(self._pkgs)
         check(self._L.mf6gpu_solution_set_packages(self.h, len(self._pkgs), arr))
 
+    def set_hfb(self, noden, nodem, hydchr):
+        """hfb_rp: horizontal flow barriers between the connected cells noden[i] / nodem[i] (0-based)"""
+        a, b, h = T.as_i32(noden), T.as_i32(nodem), T.as_f64(hydchr)
+        check(self._L.mf6gpu_solution_set_hfb(self.h, a.size, T.ptr_i32(a), T.ptr_i32(b), T.ptr_f64(h), 0))
+
     # sln_ca for one time step
     def timestep(self, kper=1, kstp=1, delt=1.0, iss=1):
         rep = T.StepReport()

@@ -98,3 +98,34 @@ def drn_ddrn01_case(newton):
         f = np.where(sat < 0, 0.0, np.where(sat > 1, 1.0, f))
         return f * dcond * (delev - np.asarray(h))
     return cfg, analytic
+
+
+NPF_THICKSTRT = {"thickstrt": [False, True, True, False, False, False, True, False, False],
+                 "icelltype": [0, 0, -1, 1, -1, 0, -1, 1, -1],
+                 "hfb": [False, False, False, False, False, True, True, True, True]}
+
+
+def npf_thickstrt_case(idx):
+    """autotest/test_gwf_npf_thickstrt.py:8-127 literally: 1 x 1 x 6 strip, top 10, bottom 0, K 1, starting head 5,
+    constant heads 6 / 4 at the ends, one steady step; CG with relaxation 1 (MILU0), closures 1e-6, 10 outer x 5 inner
+    iterations.  The nine cases vary ICELLTYPE (0 / 1 / -1), THICKSTRT and one horizontal flow barrier between cells 3
+    and 4 (hydraulic characteristic 1e-4).  Returns (SimConfig, hfb or None, heads, CHD inflow) with the reference
+    test's literal answers (:140-194)."""
+    from modflow6_b200 import configs
+    m = build_dis_model(1, 1, 6, 1.0, 1.0, 10.0, [0.0], 1.0, icelltype=NPF_THICKSTRT["icelltype"][idx], strt=5.0,
+                        ithickstrt=1 if NPF_THICKSTRT["thickstrt"][idx] else 0)
+    chd = Package(T.PKG_CHD, [0, 5], [6.0, 4.0])
+    ims = T.ImsSettings.make(dvclose=1e-6, rclose=1e-6, iter1=5, ilinmeth=1, relax=1.0)
+    sln = T.SlnSettings.make(dvclose=1e-6, mxiter=10)
+    cfg = configs.SimConfig(f"npf_thickstrt{idx + 1:02d}", m, [configs.Period(1.0, 1, 1.0, True, [chd])], sln, ims)
+    hfb = ([2], [3], [1.0e-4]) if NPF_THICKSTRT["hfb"][idx] else None
+    linear = np.linspace(6, 4, 6)
+    water_table = np.array((6.0, 5.65716, 5.29206, 4.89969, 4.47276, 4.0))
+    confined_hfb = np.array((6.0, 5.9998, 5.9996, 4.0004, 4.0002, 4.0))
+    thickstrt_hfb = np.array((6.0, 5.9996004, 5.9992008, 4.0007992, 4.0003996, 4.0))
+    unconfined_hfb = np.array((6.0, 5.99983342, 5.99966683, 4.00049971, 4.00024986, 4.0))
+    heads = [linear, linear, linear, water_table, water_table, confined_hfb, thickstrt_hfb, unconfined_hfb,
+             unconfined_hfb][idx]
+    inflow = [4.0, 4.0, 2.0, 1.9965396769631871, 1.9965396769631871, 1.9990e-03, 1.9980e-03, 9.9949e-04,
+              9.9949e-04][idx]
+    return cfg, hfb, heads, inflow

@@ -352,3 +352,64 @@ def test_npf02_rewet_two_models_on_device(gpu, nlay):
         G.set_packages(pk)
         assert G.timestep(kper, 1, 1.0, 1).converged == 1
         assert np.abs(npf02_two_model_profile(G.x, nlay, offs, ncols) - want[kper - 1]).max() < 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("idx", range(9))
+def test_npf_thickstrt_hfb_on_device(gpu, idx):
+    """autotest/test_gwf_npf_thickstrt.py on the device: the reference's literal heads and CHD inflow for the nine
+    ICELLTYPE x THICKSTRT x HFB cases, and agreement with the oracle (heads, flowja) to round-off"""
+    from modflow6_b200.solution import GpuNumericalSolution
+    from oracle.oracle import OracleSolution
+    from tests.helpers import npf_thickstrt_case
+    cfg, hfb, heads, inflow = npf_thickstrt_case(idx)
+    cfg.ims.gpu_ordering = T.ORDER_NATURAL
+    G = GpuNumericalSolution(cfg.model, cfg.sln, cfg.ims)
+    O = OracleSolution(cfg.model, cfg.sln, cfg.ims)
+    for S in (G, O):
+        S.set_packages(cfg.periods[0].packages)
+        if hfb:
+            S.set_hfb(*hfb)
+        S.timestep(1, 1, 1.0, 1)
+    assert np.allclose(heads, G.x)
+    assert np.allclose(inflow, G.simvals[0][0])
+    assert np.abs(G.x - O.x).max() < 1e-10
+    assert np.abs(G.flowja - O.flowja).max() < 1e-10 * max(1.0, np.abs(O.flowja).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ordering", [T.ORDER_NATURAL, T.ORDER_BLOCK_MULTICOLOR])
+def test_hfb_many_barriers_parity(gpu, ordering):
+    """a wall of barriers through a 3-layer unconfined grid (positive hydraulic characteristic on two layers, a
+    negative one = conductance multiplier on the third), changed in the second stress period and removed in the
+    third: device == oracle on the same permuted system"""
+    from modflow6_b200.solution import GpuNumericalSolution
+    from oracle.oracle import OracleSolution
+    from tests.helpers import chd_west_east
+    nlay, nrow, ncol = 3, 12, 16
+    m = hetero_dis(nlay, nrow, ncol, seed=11, sigma=0.5, icelltype=1, top=30.0, dz=10.0)
+    m.strt[:] = 25.0
+    pk = [chd_west_east(m, 28.0, 12.0)]
+    ims = T.ImsSettings.make(dvclose=1e-9, rclose=1e-7, iter1=200, ilinmeth=1, gpu_ordering=ordering)
+    sln = T.SlnSettings.make(dvclose=1e-7, mxiter=100)
+    G = GpuNumericalSolution(m, sln, ims)
+    O = OracleSolution(m, sln, ims, perm=None if ordering == T.ORDER_NATURAL else G.elimination_order())
+    jc = 7
+    cells = np.array([(k * nrow + i) * ncol + jc for k in range(nlay) for i in range(nrow)])
+    hyd = np.repeat([1e-3, 5e-3, -0.1], nrow)
+    walls = [(cells, cells + 1, hyd), (cells[: 2 * nrow], cells[: 2 * nrow] + 1, hyd[: 2 * nrow] * 10.0),
+             (cells[:0], cells[:0], hyd[:0])]
+    prev = None
+    for kper, w in enumerate(walls, start=1):
+        for S in (G, O):
+            S.set_packages(pk)
+            S.set_hfb(*w)
+        rg, ro = G.timestep(kper, 1, 1.0, 1), O.timestep(kper, 1, 1.0, 1)
+        assert rg.converged == 1 and ro.converged == 1
+        assert rg.outer_iterations == ro.outer_iterations
+        assert np.abs(G.x - O.x).max() < 1e-7 * 0.1
+        assert abs(rg.pdiffr - ro.pdiffr) < 1e-3
+        assert np.abs(G.flowja - O.flowja).max() < 1e-6 * max(1.0, np.abs(O.flowja).max())
+        if prev is not None:
+            assert np.abs(G.x - prev).max() > 1e-3     # the changed wall changed the heads
+        prev = np.array(G.x, copy=True)

@@ -546,3 +546,20 @@ def test_npf02_rewet_two_models_literal_heads(nlay):
         S.set_packages(pk)
         assert S.timestep(kper, 1, 1.0, 1).converged == 1
         assert np.abs(npf02_two_model_profile(S.x, nlay, offs, ncols) - want[kper - 1]).max() < 1e-9
+
+
+@pytest.mark.parametrize("idx", range(9))
+def test_npf_thickstrt_hfb_literal_answers(idx):
+    """autotest/test_gwf_npf_thickstrt.py:129-194 -- the reference's own assertions (np.allclose on the six heads
+    and on the first CHD's inflow) for ICELLTYPE 0 / 1 / -1 x THICKSTRT x one horizontal flow barrier: prepcheck's
+    treatment of a negative ICELLTYPE, calc_initial_sat (gwf-npf.f90:1838-1882, 2046-2057), condsat_modify, hfb_fc
+    and hfb_cq (gwf-hfb.f90:149-450, 770-832)"""
+    from tests.helpers import npf_thickstrt_case
+    cfg, hfb, heads, inflow = npf_thickstrt_case(idx)
+    S = OracleSolution(cfg.model, cfg.sln, cfg.ims)
+    S.set_packages(cfg.periods[0].packages)
+    if hfb:
+        S.set_hfb(*hfb)
+    S.timestep(1, 1, 1.0, 1)
+    assert np.allclose(heads, S.x)
+    assert np.allclose(inflow, S.simvals[0][0])
