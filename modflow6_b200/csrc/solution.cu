@@ -1855,7 +1855,9 @@ static void create_solution(const mf6gpu_gwf_model *m, const mf6gpu_sln_settings
       s->strt.upload(permuted(m->strt, perm, 0.0));
       s->x.upload(permuted(m->strt, perm, 0.0));
       s->xold.upload(permuted(m->strt, perm, 0.0));
-      {
+      if (!sat0.empty()) {
+        s->sat.upload(permuted(sat0.data(), perm, 1.0));  // a THICKSTRT cell keeps its initial saturation (prepcheck)
+      } else {
         std::vector<double> ones((size_t)n, 1.0);
         s->sat.upload(ones);
       }
@@ -2192,11 +2194,7 @@ int mf6gpu_solution_timestep(mf6gpu_solution *s, int32_t kper, int32_t kstp, dou
     const BndView B = s->bview();
     const int transient = (iss == 0 && s->o.insto) ? 1 : 0;
     s->exchange_x();
-    if (!s->o.all_confined) {
-      ModelView Me = M;
-      Me.n = s->n_ext;
-      npf_cf_kernel<<<grid_for(s->n_ext), kBlock, 0, st>>>(Me, s->x.p, s->sat.p);
-    }
+    // npf_cq uses the saturation of the LAST formulate (this%sat is only updated in npf_cf, gwf-npf.f90:444-470)
     flow_rows_kernel<<<G, kBlock, 0, st>>>(M, s->x.p, s->xold.p, s->sat.p, s->flowja.p, s->strgss.p,
                                            s->strgsy.p, transient, 1.0 / delt);
     if (s->nhfb > 0 && s->o.inewton == 0 && !s->o.all_confined)

@@ -1008,6 +1008,7 @@ orc_solution *orc_sln_create(const mf6gpu_gwf_model *m,
     if (S->icelltype[i] < 0) {
       if (m->ithickstrt != 0) {
         if (S->ibound[i] != 0) S->sat0[i] = thksat(S, (int)i, m->strt[i]);
+        S->sat[i] = S->sat0[i]; /* npf_cf never touches a confined cell: this%sat keeps the initial saturation */
         S->icelltype[i] = 0;
       } else {
         S->icelltype[i] = 1;

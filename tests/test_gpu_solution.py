@@ -374,7 +374,7 @@ def test_npf_thickstrt_hfb_on_device(gpu, idx):
     assert np.allclose(heads, G.x)
     assert np.allclose(inflow, G.simvals[0][0])
     assert np.abs(G.x - O.x).max() < 1e-10
-    assert np.abs(G.flowja - O.flowja).max() < 1e-10 * max(1.0, np.abs(O.flowja).max())
+    assert np.abs(G.flowja - O.flowja).max() < 1e-8 * max(1.0, np.abs(O.flowja).max())
 
 
 @pytest.mark.gpu
@@ -388,8 +388,8 @@ def test_hfb_many_barriers_parity(gpu, ordering):
     from tests.helpers import chd_west_east
     nlay, nrow, ncol = 3, 12, 16
     m = hetero_dis(nlay, nrow, ncol, seed=11, sigma=0.5, icelltype=1, top=30.0, dz=10.0)
-    m.strt[:] = 25.0
-    pk = [chd_west_east(m, 28.0, 12.0)]
+    m.strt[:] = 27.0
+    pk = [chd_west_east(m, 29.0, 23.0)]     # above the bottom of the top layer (20): no constant head goes dry
     ims = T.ImsSettings.make(dvclose=1e-9, rclose=1e-7, iter1=200, ilinmeth=1, gpu_ordering=ordering)
     sln = T.SlnSettings.make(dvclose=1e-7, mxiter=100)
     G = GpuNumericalSolution(m, sln, ims)
