@@ -280,7 +280,7 @@ def extract_submodel(g, owner, rank, nranks):
                  ss=g.ss[sel], sy=g.sy[sel], iconvert=g.iconvert[sel],
                  icellavg=g.icellavg, inewton=g.inewton, inewtonur=g.inewtonur, iperched=g.iperched,
                  ivarcv=g.ivarcv, idewatcv=g.idewatcv, insto=g.insto, istor_coef=g.istor_coef,
-                 iconf_ss=g.iconf_ss, iorig_ss=g.iorig_ss, shape=None)
+                 iconf_ss=g.iconf_ss, iorig_ss=g.iorig_ss, ithickstrt=g.ithickstrt, shape=None)
     howner = owner[halo_g]
     nbrs = np.unique(howner)
     recv_ptr = np.concatenate([[0], np.cumsum([(howner == q).sum() for q in nbrs])]).astype(np.int32)

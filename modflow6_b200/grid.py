@@ -363,9 +363,14 @@ def merge_models(models, exchanges):
                              "matrix on the GPU path needs the same NPF / STO options in every model")
     if any(getattr(m, a) is not None for m in models for a in ("k22", "angle1", "angle2", "angle3")):
         raise ValueError("merge_models: K22 / ANGLE anisotropy is not supported in multi-model solutions")
+    # THICKSTRT is a per-model option: a model without it turns its negative ICELLTYPE into 1 (prepcheck,
+    # gwf-npf.f90:1838-1846), so doing that here lets the merged model carry THICKSTRT for the models that set it
+    ict = np.concatenate([m.icelltype if m.ithickstrt else np.where(m.icelltype < 0, 1, m.icelltype)
+                          for m in models]).astype(np.int32)
     return GwfModel(nodes=n, ia=ia, ja=ja, jas=jas, isym=isym, ihc=ihc, cl1=cl1, cl2=cl2, hwva=hw,
                     top=cat("top"), bot=cat("bot"), area=cat("area"), k11=cat("k11"), k33=cat("k33"),
-                    icelltype=cat("icelltype"), strt=cat("strt"), ibound=cat("ibound"),
+                    icelltype=ict, ithickstrt=max(int(m.ithickstrt) for m in models),
+                    strt=cat("strt"), ibound=cat("ibound"),
                     ibotnode=np.concatenate([m.ibotnode + offs[k] for k, m in enumerate(models)]),
                     ss=cat("ss"), sy=cat("sy"), iconvert=cat("iconvert"), icellavg=m0.icellavg,
                     inewton=m0.inewton, inewtonur=m0.inewtonur, iperched=m0.iperched, ivarcv=m0.ivarcv,

@@ -166,6 +166,7 @@ class GwfInput:
     head_file: str = None
     budget_file: str = None
     save: dict = field(default_factory=dict)          # iper -> list of (rtype, ocsetting tokens)
+    hfb: dict = field(default_factory=dict)           # iper -> (noden, nodem, hydchr), HFB6 barriers (0-based nodes)
     nodeuser: np.ndarray = None       # DIS with IDOMAIN <= 0 cells: reduced -> user node (model.nodes entries)
     nodereduced: np.ndarray = None    # user -> reduced node, -1 where no cell exists
 
@@ -396,6 +397,42 @@ def read_stress_package(path, ftype, name, shape, inewton=0):
     return StressPackage(ftype[:-1], name, periods, iflowred, flowred), naux
 
 
+def read_hfb(path, shape, nodereduced, model):
+    """HFB6 (gwf-hfb.dfn; hfb_rp / read_data / check_data, gwf-hfb.f90:149-201, 596-760): PERIOD blocks of
+    `cellid1 cellid2 hydchr`; a block replaces the whole barrier list, which then stays in force.  The two cells of
+    a barrier must be horizontally connected."""
+    b = read_blocks(path)
+    dim = _options(_block(b, "DIMENSIONS"))
+    maxhfb = int(dim["MAXHFB"][0])
+    row_of = np.repeat(np.arange(model.nodes), np.diff(model.ia))
+    conn = {(int(r), int(c)): int(j) for r, c, j in zip(row_of, model.ja, model.jas) if j >= 0}
+    periods = {}
+    for nm, num, lines in b:
+        if nm != "PERIOD":
+            continue
+        n1, n2, hc = [], [], []
+        for t in lines:
+            a, w = _cellid(t, shape)
+            c, w2 = _cellid(t[w:], shape)
+            if nodereduced is not None:
+                a, c = int(nodereduced[a]), int(nodereduced[c])
+                if a < 0 or c < 0:
+                    raise Mf6InputError(f"{path}: period {num}: a barrier lies in a cell that IDOMAIN removes")
+            j = conn.get((a, c))
+            if j is None:
+                raise Mf6InputError(f"{path}: period {num}: HFB cells {t[:w]} and {t[w:w + w2]} are not connected")
+            if model.ihc[j] == 0:
+                raise Mf6InputError(f"{path}: period {num}: HFB between vertically connected cells "
+                                    f"{t[:w]} and {t[w:w + w2]}")
+            n1.append(a)
+            n2.append(c)
+            hc.append(float(t[w + w2]))
+        if len(n1) > maxhfb:
+            raise Mf6InputError(f"{path}: period {num}: {len(n1)} barriers, MAXHFB is {maxhfb}")
+        periods[num] = (np.array(n1, dtype=np.int32), np.array(n2, dtype=np.int32), np.array(hc, dtype=np.float64))
+    return periods
+
+
 def read_gwf_model(name, nam_path, base_dir, warnings):
     b = read_blocks(nam_path)
     opt = _options(_block(b, "OPTIONS", required=False))
@@ -409,7 +446,7 @@ def read_gwf_model(name, nam_path, base_dir, warnings):
         pn = t[2] if len(t) > 2 else None
         if ft in _PKG_TYPE:
             stress.append((ft, fn, pn))
-        elif ft in ("DIS6", "DISV6", "DISU6", "IC6", "NPF6", "STO6", "OC6"):
+        elif ft in ("DIS6", "DISV6", "DISU6", "IC6", "NPF6", "STO6", "OC6", "HFB6"):
             files[ft] = fn
         else:
             raise Mf6InputError(f"{nam_path}: package {ft} is outside the GPU path (SURVEY.md section 8)")
@@ -468,7 +505,7 @@ def read_gwf_model(name, nam_path, base_dir, warnings):
     nb = read_blocks(files["NPF6"])
     nopt = _options(_block(nb, "OPTIONS", required=False))
     for k in nopt:
-        if k in ("THICKSTRT", "XT3D", "TVK6"):
+        if k in ("XT3D", "TVK6"):
             raise Mf6InputError(f"NPF option {k} is not supported on the GPU path")
     np_ = read_griddata(_block(nb, "GRIDDATA"), base_dir,
                         {"ICELLTYPE": (ashape, np.int32), "K": (ashape, np.float64), "K22": (ashape, np.float64),
@@ -506,6 +543,8 @@ def read_gwf_model(name, nam_path, base_dir, warnings):
         for a in ("ANGLE1", "ANGLE2", "ANGLE3"):
             if a in np_:
                 kw[a.lower()] = (np_[a] * (np.arctan(1.0) / 45.0)).reshape(shape)   # DPIO180, Constants.f90:130
+    if "THICKSTRT" in nopt:
+        kw["ithickstrt"] = 1
     avg = {"LOGARITHMIC": 1, "AMT-LMK": 2, "AMT-HMK": 3}
     if "ALTERNATIVE_CELL_AVERAGING" in nopt:
         kw["icellavg"] = avg[nopt["ALTERNATIVE_CELL_AVERAGING"][0].upper()]
@@ -576,6 +615,8 @@ def read_gwf_model(name, nam_path, base_dir, warnings):
                 sp.periods[iper] = Package(p.type, red[keep], p.b1[keep], p.b2[keep], p.b3[keep],
                                            iflowred=p.iflowred, flowred=p.flowred)
         gi.packages.append(sp)
+    if "HFB6" in files:
+        gi.hfb = read_hfb(files["HFB6"], shape, gi.nodereduced, m)
     if "OC6" in files:
         ob = read_blocks(files["OC6"])
         oopt = _block(ob, "OPTIONS", required=False)

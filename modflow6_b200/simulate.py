@@ -134,6 +134,7 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
     current = [[None] * len(gi.packages) for gi in sim.models]     # list in force per package
     saving = [dict() for _ in sim.models]                          # rtype -> settings in force
     reports, totim = [], 0.0
+    hfb_now = {}                                                   # model -> barrier list in force
     for kper in range(1, sim.nper + 1):
         perlen, nstp, tsmult = sim.perioddata[kper - 1]
         pkgs, owner = [], []
@@ -162,6 +163,15 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
             raise Mf6InputError(f"period {kper}: the models of the solution disagree on STEADY-STATE / TRANSIENT")
         iss = iss_of[0] if iss_of else 1
         S.set_packages(pkgs)
+        if any(kper in gi.hfb for gi in sim.models):   # hfb_rp: a PERIOD block replaces the model's barrier list
+            for k, gi in enumerate(sim.models):
+                if kper in gi.hfb:
+                    hfb_now[k] = gi.hfb[kper]
+            if rank is not None:
+                from .mf6io import Mf6InputError
+                raise Mf6InputError("HFB6 is not available in the split-model run")
+            lists = [(a + int(offs[k]), c + int(offs[k]), h) for k, (a, c, h) in sorted(hfb_now.items())]
+            S.set_hfb(*(np.concatenate([l[i] for l in lists]) for i in range(3)))
         pertim = 0.0
         for kstp, delt in enumerate(tdis_steps(perlen, nstp, tsmult), start=1):
             rep = S.timestep(kper, kstp, delt, iss)

@@ -489,3 +489,35 @@ def test_npf02_rewet_from_deck(tmp_path):
     out = simulate.run(d, ordering=T.ORDER_NATURAL, solution_class=oracle_class(), write_output=False)
     assert all(r["converged"] for r in out["reports"])
     assert np.abs(npf02_profile(out["heads"][0].ravel(), nlay) - NPF02_3LAY[1]).max() < 1e-9
+
+
+@pytest.mark.parametrize("idx", [2, 6, 8])
+def test_npf_thickstrt_and_hfb_from_decks(tmp_path, idx):
+    """autotest/test_gwf_npf_thickstrt.py from input FILES: NPF THICKSTRT with a negative ICELLTYPE and the HFB6
+    package (PERIOD list of cellid1 cellid2 hydchr) reach the reference's literal heads and CHD inflow"""
+    from tests.helpers import NPF_THICKSTRT, npf_thickstrt_case
+    _, hfb, heads, inflow = npf_thickstrt_case(idx)
+    d = str(tmp_path)
+    extra = []
+    if hfb:
+        extra.append(("HFB6", "hfb", "BEGIN options\n  PRINT_INPUT\nEND options\n\nBEGIN dimensions\n  MAXHFB 1\n"
+                      "END dimensions\n\nBEGIN period 1\n  1 1 3  1 1 4  1.0e-4\nEND period 1\n"))
+    mf6_inputs.write_gwf(d, "flow", (1, 1, 6), 1.0, 1.0, 10.0, [0.0], 1.0, icelltype=NPF_THICKSTRT["icelltype"][idx],
+                         chd={1: [((1, 1, 1), 6.0), ((1, 1, 6), 4.0)]}, strt=5.0, k33=1.0, extra_packages=extra)
+    if NPF_THICKSTRT["thickstrt"][idx]:
+        p = tmp_path / "flow.npf"
+        p.write_text(p.read_text().replace("  SAVE_FLOWS\n", "  SAVE_FLOWS\n  THICKSTRT\n"))
+    ims = ("BEGIN nonlinear\n  OUTER_DVCLOSE 1e-6\n  OUTER_MAXIMUM 10\n  UNDER_RELAXATION NONE\nEND nonlinear\n\n"
+           "BEGIN linear\n  INNER_MAXIMUM 5\n  INNER_DVCLOSE 1e-6\n  INNER_RCLOSE 1e-6\n  LINEAR_ACCELERATION CG\n"
+           "  SCALING_METHOD NONE\n  REORDERING_METHOD NONE\n  RELAXATION_FACTOR 1.0\nEND linear\n")
+    mf6_inputs.write_sim(d, ["flow"], [(1.0, 1, 1.0)], ims)
+    out = simulate.run(d, ordering=T.ORDER_NATURAL, solution_class=oracle_class())
+    assert np.allclose(heads, out["heads"][0].ravel())
+    cbc = read_budget_file(tmp_path / "flow.cbc")
+    assert cbc[1]["text"].strip() == "CHD" and np.allclose(inflow, cbc[1]["q"][0])
+    # a barrier between cells that are not connected is an input error (check_data, gwf-hfb.f90:714-766)
+    if hfb:
+        (tmp_path / "flow.hfb").write_text("BEGIN dimensions\n  MAXHFB 1\nEND dimensions\n\nBEGIN period 1\n"
+                                           "  1 1 2  1 1 4  1.0e-4\nEND period 1\n")
+        with pytest.raises(mf6io.Mf6InputError, match="not connected"):
+            simulate.run(d, ordering=T.ORDER_NATURAL, solution_class=oracle_class(), write_output=False)
