@@ -380,6 +380,57 @@ def merge_models(models, exchanges):
                     wetfct=m0.wetfct), offs
 
 
+def reduce_model(m, keep):
+    """Remove the cells with keep == False from any GwfModel the way the reference numbers a grid with IDOMAIN == 0
+    cells (reduced node numbers in user order, DiscretizationBase `nodereduced` / `nodeuser`; connections to a
+    removed cell do not exist, Connections.f90:463-700, 803-960).  The kept connections keep their relative order, so
+    the symmetric numbering stays the filljas one.  `meta` gets nodeuser / nodereduced like build_dis_model_idomain."""
+    import dataclasses
+    keep = np.asarray(keep, dtype=bool)
+    n_old = m.nodes
+    nodeuser = np.nonzero(keep)[0]
+    n = nodeuser.size
+    red = np.full(n_old, -1, dtype=np.int64)
+    red[nodeuser] = np.arange(n)
+    rows = np.repeat(np.arange(n_old), np.diff(m.ia))
+    kc = keep[rows] & keep[m.ja]                       # CSR entries that survive
+    keep_s = np.zeros(m.njas, dtype=bool)
+    keep_s[m.jas[kc & (m.jas >= 0)]] = True
+    jmap = np.full(m.njas, -1, dtype=np.int64)
+    jmap[keep_s] = np.arange(int(keep_s.sum()))
+    pos = np.full(m.nja, -1, dtype=np.int64)
+    pos[kc] = np.arange(int(kc.sum()))
+    ia = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(np.bincount(red[rows[kc]], minlength=n), out=ia[1:])
+    ja = red[m.ja[kc]]
+    jas = np.where(m.jas[kc] >= 0, jmap[np.maximum(m.jas[kc], 0)], -1)
+    isym = pos[m.isym[kc]]
+    # bottom of every vertical chain (gwf-npf.f90:1904-1940): walk down through the vertical connections
+    r2 = red[rows[kc]]
+    cand = (m.ihc[np.maximum(m.jas[kc], 0)] == 0) & (m.jas[kc] >= 0) & (ja > r2) & (m.bot[nodeuser][ja] < m.bot[nodeuser][r2])
+    below = np.full(n, -1, dtype=np.int64)
+    bb = np.full(n, np.inf)
+    for r, c in zip(r2[cand], ja[cand]):
+        if m.bot[nodeuser[c]] < bb[r]:
+            bb[r], below[r] = m.bot[nodeuser[c]], c
+    ibot = np.arange(n, dtype=np.int64)
+    for c in range(n - 1, -1, -1):
+        if below[c] >= 0:
+            ibot[c] = ibot[below[c]]
+    per_node = {f: getattr(m, f)[nodeuser] for f in ("top", "bot", "area", "k11", "k33", "icelltype", "strt", "ibound",
+                                                      "ss", "sy", "iconvert")}
+    for f in ("k22", "angle1", "angle2", "angle3", "wetdry"):
+        per_node[f] = None if getattr(m, f) is None else getattr(m, f)[nodeuser]
+    per_conn = {f: getattr(m, f)[keep_s] for f in ("ihc", "cl1", "cl2", "hwva")}
+    for f in ("conn_nx", "conn_ny"):
+        per_conn[f] = None if getattr(m, f) is None else getattr(m, f)[keep_s]
+    out = dataclasses.replace(m, nodes=n, ia=ia, ja=ja, jas=jas, isym=isym, ibotnode=ibot, meta=dict(m.meta),
+                              **per_node, **per_conn)
+    out.meta["nodeuser"] = nodeuser
+    out.meta["nodereduced"] = red
+    return out
+
+
 def build_disu_model(iac, ja, ihc, cl12, hwva, top, bot, area, k11, k33=None, icelltype=0, strt=0.0, ss=None,
                      sy=None, iconvert=None, **opts):
     """Unstructured (DISU) model from the CONNECTIONDATA block as the user writes it (gwf-disu.dfn): `iac` entries

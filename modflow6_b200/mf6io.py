@@ -23,7 +23,7 @@ import numpy as np
 
 from . import ctypes_types as T
 from .disv import build_disv_model, cell2d_from_vertices
-from .grid import Package, build_dis_model, build_dis_model_idomain, build_disu_model
+from .grid import Package, build_dis_model, build_dis_model_idomain, build_disu_model, reduce_model
 
 
 class Mf6InputError(ValueError):
@@ -588,10 +588,12 @@ def read_gwf_model(name, nam_path, base_dir, warnings):
                                 g["BOTM"].reshape(shape), np_["K"].reshape(shape), **common)
     else:
         m = build_disv_model(nlay, cell2d, g["TOP"], g["BOTM"].reshape(nlay, shape[1]), np_["K"], **common)
-    if "IDOMAIN" in g:
+    if "IDOMAIN" in g:       # DISV / DISU (the DIS branch consumed its IDOMAIN above)
         if (g["IDOMAIN"] < 0).any():
-            raise Mf6InputError("IDOMAIN < 0 (vertical pass-through cells) is not supported on the GPU path")
-        m.ibound = np.where(g["IDOMAIN"] > 0, 1, 0).astype(np.int32)
+            raise Mf6InputError("IDOMAIN < 0 (vertical pass-through cells) is supported on DIS grids only on the GPU path")
+        if (g["IDOMAIN"] == 0).any():
+            # reduced node numbering, like the reference: the removed cells and their connections do not exist
+            m = reduce_model(m, g["IDOMAIN"].reshape(-1) > 0)
     gi = GwfInput(name=name, model=m, shape=shape, sto_transient=sto_tr, nodeuser=m.meta.get("nodeuser"),
                   nodereduced=m.meta.get("nodereduced"))
     count = {}

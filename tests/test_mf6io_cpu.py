@@ -521,3 +521,50 @@ def test_npf_thickstrt_and_hfb_from_decks(tmp_path, idx):
                                            "  1 1 2  1 1 4  1.0e-4\nEND period 1\n")
         with pytest.raises(mf6io.Mf6InputError, match="not connected"):
             simulate.run(d, ordering=T.ORDER_NATURAL, solution_class=oracle_class(), write_output=False)
+
+
+def test_idomain_holes_on_disv_and_disu_decks_equal_the_dis_deck(tmp_path):
+    """IDOMAIN == 0 on DISV / DISU: reduced node numbering like on DIS (grid.reduce_model) -- the same rectangular
+    grid with the same holes written as DIS, DISV and DISU gives the same reduced connectivity, bottom nodes, heads
+    and FLOW-JA-FACE length; the head files carry 1e30 in the holes"""
+    rng = np.random.default_rng(21)
+    shape = (3, 4, 5)
+    k = np.exp(rng.normal(0.5, 0.6, shape))
+    idom = np.ones(shape, dtype=int)
+    idom[0, 1, 2] = idom[1, 1, 2] = idom[2, 3, 0] = idom[1, 0, 4] = 0
+    chd = [((kk + 1, i + 1, 1), 5.0) for kk in range(3) for i in range(4) if idom[kk, i, 0]] + \
+          [((kk + 1, i + 1, 5), 2.0) for kk in range(3) for i in range(4) if idom[kk, i, 4]]
+    wel = [((3, 3, 3), -40.0)]
+    ims = ("BEGIN nonlinear\n  OUTER_DVCLOSE 1e-9\n  OUTER_MAXIMUM 50\nEND nonlinear\n\n"
+           "BEGIN linear\n  INNER_MAXIMUM 200\n  INNER_DVCLOSE 1e-10\n  INNER_RCLOSE 1e-8\n  LINEAR_ACCELERATION CG\nEND linear\n")
+    outs = {}
+    for tag in ("dis", "disv", "disu"):
+        d = tmp_path / tag
+        d.mkdir()
+        mf6_inputs.write_gwf(str(d), "m", shape, 10.0, 12.0, 0.0, [-5.0, -12.0, -30.0], k, chd={1: chd},
+                             wel={1: wel}, strt=3.0, k33=0.3, disv=(tag == "disv"), disu=(tag == "disu"),
+                             idomain=idom if tag == "dis" else None)
+        if tag != "dis":
+            p = d / "m.dis"
+            arr = mf6_inputs._arr("idomain", idom.astype(float), layered=True) if tag == "disv" else \
+                mf6_inputs._arr("idomain", idom.astype(float).reshape(1, -1))
+            p.write_text(p.read_text().replace("END griddata\n", arr + "END griddata\n"))
+        mf6_inputs.write_sim(str(d), ["m"], [(1.0, 1, 1.0)], ims)
+        outs[tag] = simulate.run(str(d), ordering=T.ORDER_NATURAL, solution_class=oracle_class())
+    a = outs["dis"]["simulation"].models[0].model
+    assert a.nodes == idom.sum()
+    for tag in ("disv", "disu"):
+        gi = outs[tag]["simulation"].models[0]
+        b = gi.model
+        assert b.nodes == a.nodes and np.array_equal(gi.nodeuser, np.nonzero(idom.reshape(-1))[0])
+        for name in ("ia", "ja", "jas", "isym", "ihc", "ibotnode"):
+            assert np.array_equal(getattr(a, name), getattr(b, name)), (tag, name)
+        for name in ("cl1", "cl2", "hwva", "area", "top", "bot", "k11"):
+            assert np.allclose(getattr(a, name), getattr(b, name), rtol=1e-13), (tag, name)
+        ha, hb = outs["dis"]["heads"][0].ravel(), outs[tag]["heads"][0].ravel()
+        assert np.array_equal(ha == 1.0e30, hb == 1.0e30) and (hb == 1.0e30).sum() == 4
+        assert np.abs(ha - hb).max() < 1e-9
+        cbc = read_budget_file(tmp_path / tag / "m.cbc")
+        assert cbc[0]["flow"].size == a.nja
+        w = [r for r in cbc if r["text"].strip() == "WEL"][0]
+        assert w["node"].tolist() == [(2 * 4 + 2) * 5 + 3]          # USER node number
