@@ -80,6 +80,17 @@ def c1_npf01(case="b", gpu_ordering=T.ORDER_NATURAL):
 C2_CLOSURE = {"survey": (1e-6, 1e-2, 500), "tight": (1e-7, 1e-4, 1000), "tight2": (1e-8, 1e-5, 1000)}
 
 
+def tighten_inner_closure(cfg, level):
+    """INNER_DVCLOSE x 0.1^level, INNER_RCLOSE x 0.01 x 0.1^(level - 1), INNER_MAXIMUM >= 1000: what
+    tests/golden/make_golden_full.py --tight (1) / --tight2 (2) applies before the oracle run, so that a device run
+    of the same config is held against a fixture made at the same closure."""
+    if level:
+        cfg.ims.dvclose *= 0.1 ** level
+        cfg.ims.rclose *= 0.01 * 0.1 ** (level - 1)
+        cfg.ims.iter1 = max(cfg.ims.iter1, 1000)
+    return cfg
+
+
 def c2_confined(nlay=10, nrow=1000, ncol=1000, gpu_ordering=T.ORDER_BLOCK_MULTICOLOR, inner_maximum=None,
                 outer_maximum=50, seed=20260101, closure="survey"):
     """confined steady state, heterogeneous K = exp(N(ln 10, 1)), k33 = 0.1 k,

@@ -26,6 +26,13 @@ class Package:
     b3: np.ndarray = None
     iflowred: int = 0
     flowred: float = 0.1
+    auxnames: tuple = ()          # AUXILIARY variable names and their values [nbound, naux]: carried to the
+    aux: np.ndarray = None        # budget file records (save_print_model_flows), not used by the solve
+
+    def with_nodes(self, nodelist):
+        """the same boundaries at other node numbers (model offset in a merged solution, reduced -> user)"""
+        return Package(self.type, nodelist, self.b1, self.b2, self.b3, iflowred=self.iflowred, flowred=self.flowred,
+                       auxnames=self.auxnames, aux=self.aux)
 
     def __post_init__(self):
         self.nodelist = T.as_i32(self.nodelist)

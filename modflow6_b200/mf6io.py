@@ -354,7 +354,7 @@ def read_stress_package(path, ftype, name, shape, inewton=0):
             if nm_d not in auxnames:
                 raise Mf6InputError(f"{path}: AUXDEPTHNAME {nm_d} is not one of the AUXILIARY variables")
             depth_col = ncol + auxnames.index(nm_d)
-    nread = ncol + (naux if depth_col is not None else 0)
+    nread = ncol + naux
     periods = {}
     for nm, num, lines in b:
         if nm != "PERIOD":
@@ -391,7 +391,8 @@ def read_stress_package(path, ftype, name, shape, inewton=0):
             if depth_col is not None:
                 cols[2] = v[:, depth_col]
             periods[num] = Package(_PKG_TYPE[ftype], np.array(nodes), cols[0], cols[1], cols[2], iflowred=iflowred,
-                                   flowred=flowred)
+                                   flowred=flowred, auxnames=tuple(auxnames),
+                                   aux=v[:, ncol:ncol + naux].copy() if naux else None)
         else:
             periods[num] = None
     return StressPackage(ftype[:-1], name, periods, iflowred, flowred), naux
@@ -600,9 +601,6 @@ def read_gwf_model(name, nam_path, base_dir, warnings):
     for ft, fn, pn in stress:
         count[ft] = count.get(ft, 0) + 1
         sp, naux = read_stress_package(fn, ft, pn or f"{ft[:-1]}-{count[ft]}", shape, inewton)
-        if naux > 0:
-            warnings.append(f"{name}: {sp.name}: AUXILIARY columns are read but not carried into the budget file "
-                            "records (only a DRN AUXDEPTHNAME column is used)")
         if gi.nodereduced is not None:          # user cellids -> reduced nodes; boundaries in removed cells are dropped
             for iper, p in sp.periods.items():
                 if p is None:
@@ -614,8 +612,7 @@ def read_gwf_model(name, nam_path, base_dir, warnings):
                     # (DiscretizationBase noder / "cell is outside active grid domain")
                     raise Mf6InputError(f"{name}: {sp.name} period {iper}: {int((~keep).sum())} boundaries lie in "
                                         "cells that IDOMAIN removes")
-                sp.periods[iper] = Package(p.type, red[keep], p.b1[keep], p.b2[keep], p.b3[keep],
-                                           iflowred=p.iflowred, flowred=p.flowred)
+                sp.periods[iper] = p.with_nodes(red)
         gi.packages.append(sp)
     if "HFB6" in files:
         gi.hfb = read_hfb(files["HFB6"], shape, gi.nodereduced, m)

@@ -86,21 +86,28 @@ class BudgetFileWriter:
         self._header(kstp, kper, text, self.ncol, self.nrow, self.nlay, 1, delt, pertim, totim)
         self.f.write(values.tobytes())
 
-    def write_list(self, kstp, kper, delt, pertim, totim, text, package_name, nodes, q):
-        """save_print_model_flows: IMETH = 6 header, then (node, bound index, rate) per boundary.
+    def write_list(self, kstp, kper, delt, pertim, totim, text, package_name, nodes, q, auxname=(), aux=None):
+        """save_print_model_flows (BoundaryPackage.f90 / BudgetObject ubdsv06): IMETH = 6 header, the auxiliary
+        variable names, then (node, bound index, rate, auxiliary values) per boundary.
         `nodes` are 0-based cell numbers; entries with node < 0 (inactive) are skipped like node <= 0 there."""
         nodes = np.asarray(nodes)
         q = np.asarray(q, dtype=np.float64)
         keep = nodes >= 0
+        naux = len(auxname)
         self._header(kstp, kper, text, self.ncol, self.nrow, self.nlay, 6, delt, pertim, totim)
         self.f.write(self.model + _text16(package_name.upper(), right=False) + self.model
                      + _text16(package_name.upper(), right=False))
-        self.f.write(struct.pack("<i", 1))                      # naux + 1
+        self.f.write(struct.pack("<i", naux + 1))
+        for a in auxname:
+            self.f.write(_text16(a.upper(), right=False))
         self.f.write(struct.pack("<i", int(keep.sum())))        # nlist
-        rec = np.empty(int(keep.sum()), dtype=np.dtype([("n", "<i4"), ("n2", "<i4"), ("q", "<f8")]))
+        rec = np.empty(int(keep.sum()), dtype=np.dtype([("n", "<i4"), ("n2", "<i4"), ("q", "<f8"),
+                                                        ("aux", "<f8", (naux,))]))
         rec["n"] = nodes[keep] + 1
         rec["n2"] = np.nonzero(keep)[0] + 1
         rec["q"] = q[keep]
+        if naux:
+            rec["aux"] = np.asarray(aux, dtype=np.float64).reshape(nodes.size, naux)[keep]
         self.f.write(rec.tobytes())
 
     def write_exchange(self, kstp, kper, delt, pertim, totim, exchange_name, other_model, nodes, other_nodes, q,
@@ -150,7 +157,7 @@ class BudgetFileWriter:
             name = package_names[i] if package_names else f"{t}-{count[t]}"   # default package names, e.g. CHD-1
             nodes = p.nodelist if eff is None else eff[i]
             self.write_list(kstp, kper, delt, pertim, totim, t, name, nodes if nodeuser is None else nodeuser[nodes],
-                            sim[i])
+                            sim[i], auxname=getattr(p, "auxnames", ()) or (), aux=getattr(p, "aux", None))
         self.f.flush()
 
     def close(self):

@@ -144,8 +144,7 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
                     current[k][ip] = sp.periods[kper]
                 p = current[k][ip]
                 if p is not None:
-                    pkgs.append(Package(p.type, p.nodelist + int(offs[k]), p.b1, p.b2, p.b3, iflowred=p.iflowred,
-                                        flowred=p.flowred))
+                    pkgs.append(p.with_nodes(p.nodelist + int(offs[k])))
                     owner.append((k, ip))
             if kper in gi.save:
                 saving[k] = {}
@@ -192,7 +191,7 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
                 if bw and _should_save(saving[k].get("BUDGET", []), kstp, nstp):
                     mine = [i for i, (kk, _) in enumerate(owner) if kk == k]
                     view = S if len(models) == 1 else _ModelView(S, model, gi.model, offs[k], mine)
-                    local = [Package(pkgs[i].type, pkgs[i].nodelist - int(offs[k]), pkgs[i].b1) for i in mine]
+                    local = [pkgs[i].with_nodes(pkgs[i].nodelist - int(offs[k])) for i in mine]
                     bw.write_step(kstp, kper, delt, pertim, totim, view, local,
                                   [gi.packages[owner[i][1]].name for i in mine], nodeuser=gi.nodeuser)
             # exchange flows follow the models' own records (exg_ot after model_ot, mf6core.f90:755-771)

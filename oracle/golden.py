@@ -61,3 +61,29 @@ def compare_heads(tag, heads, dvclose, factor=0.1):
                      "linear_solve_s": sum(s["t_linsolve"] for s in meta["steps"]),
                      "formulate_s": sum(s["t_formulate"] for s in meta["steps"])}
     return out
+
+
+def nonlinear_residual(cfg, heads, kper=1):
+    """Size-independent property: how well `heads` satisfy the REFERENCE's discrete equations of the first time step
+    of stress period `kper` -- the oracle formulates the system AT these heads (npf_cf / npf_fc / npf_fn, STO, the
+    boundary packages; under NEWTON the Newton terms cancel at the linearisation point, the pseudo-transient terms
+    always do), and r = amat . h - rhs is the flow imbalance of every cell.  Needs no oracle solve, so it runs at
+    any size in seconds.  Returns max |r|, its L2 norm, the cell of the maximum and the sum over the active cells."""
+    from modflow6_b200.grid import tdis_steps
+    from .oracle import OracleSolution
+    per = cfg.periods[kper - 1]
+    delt = next(iter(tdis_steps(per.perlen, per.nstp, per.tsmult)))
+    O = OracleSolution(cfg.model, cfg.sln, cfg.ims)
+    O.set_packages(per.packages)
+    O.x[:] = np.asarray(heads, dtype=np.float64)
+    O.formulate(1, delt, 1 if per.steady else 0)
+    m = cfg.model
+    a, x = O.amat, O.x
+    ax = np.add.reduceat(a * x[m.ja], m.ia[:-1].astype(np.int64))
+    r = ax - O.rhs
+    act = np.asarray(m.ibound) > 0
+    r = np.where(act, r, 0.0)
+    out = {"max_abs": float(np.abs(r).max()), "l2": float(np.sqrt(np.dot(r, r))), "argmax_cell": int(np.abs(r).argmax()),
+           "sum": float(r.sum()), "cells": int(act.sum())}
+    O.destroy() if hasattr(O, "destroy") else None
+    return out

@@ -56,10 +56,7 @@ def main():
         cfg = configs.c3_newton(*(size or (5, 2000, 2000)), gpu_ordering=o)
     else:
         raise SystemExit("config must be c2 or c3")
-    if tight:
-        cfg.ims.dvclose *= 0.1 ** tight
-        cfg.ims.rclose *= 0.01 * 0.1 ** (tight - 1)
-        cfg.ims.iter1 = max(cfg.ims.iter1, 1000)
+    configs.tighten_inner_closure(cfg, tight)
     perm = None if o == T.ORDER_NATURAL else lib.model_elimination_order(cfg.model, o)
     t0 = time.perf_counter()
     O = OracleSolution(cfg.model, cfg.sln, cfg.ims, perm=perm)
@@ -76,6 +73,10 @@ def main():
             "stride": STRIDE, "block": BLOCK, "inner_dvclose": cfg.ims.dvclose, "inner_rclose": cfg.ims.rclose,
             "inner_maximum": cfg.ims.iter1, "outer_dvclose": cfg.sln.dvclose, "sha256": s["sha256"], "oracle_wall_s": wall, "steps": reps,
             "made_by": "tests/golden/make_golden_full.py " + " ".join(sys.argv[1:])}
+    if max_steps == 1:
+        # flow imbalance of every cell at the oracle's own heads, formulated by the oracle (oracle/golden.py)
+        from oracle import golden
+        meta["residual"] = golden.nonlinear_residual(cfg, heads)
     np.savez_compressed(os.path.join(HERE, tag + ".npz"), sample=s["sample"], block_sums=s["block_sums"],
                         meta=np.array(json.dumps(meta)))
     print(json.dumps({k: v for k, v in meta.items() if k != "steps"}))

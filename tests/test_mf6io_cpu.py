@@ -324,6 +324,11 @@ def test_chd02_binary_list_with_auxiliary(tmp_path):
         "BEGIN period 1\n  OPEN/CLOSE chd.bin (BINARY)\nEND period 1\n")
     out = simulate.run(str(tmp_path), ordering=T.ORDER_NATURAL, solution_class=oracle_class())
     assert np.allclose(CHD02_HEADS, out["heads"][0].ravel())
+    # the auxiliary columns travel into the CHD record of the budget file (save_print_model_flows: naux + 1, the
+    # names, one row of values per boundary)
+    chd = [r for r in read_budget_file(tmp_path / "chd02.cbc") if r["text"].strip() == "CHD"][-1]
+    assert [a.strip() for a in chd["auxtxt"]] == ["CONC", "SOMETHING"]
+    assert np.array_equal(chd["aux"], [[1.0, 100.0], [0.0, 100.0]]) and chd["node"].tolist() == [1, 10]
     # and the text flavour of OPEN/CLOSE
     (tmp_path / "chd.txt").write_text("1 1 1 10.0 1.0 100.0\n1 1 10 5.0 0.0 100.0\n")
     (tmp_path / "chd02.chd").write_text((tmp_path / "chd02.chd").read_text().replace("chd.bin (BINARY)", "chd.txt"))
