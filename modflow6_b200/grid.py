@@ -28,11 +28,17 @@ class Package:
     flowred: float = 0.1
     auxnames: tuple = ()          # AUXILIARY variable names and their values [nbound, naux]: carried to the
     aux: np.ndarray = None        # budget file records (save_print_model_flows), not used by the solve
+    bound_index: np.ndarray = None   # 0-based position of every boundary in the package's own list, when entries of
+                                     # that list do not exist in the model (array-based recharge over removed cells)
 
-    def with_nodes(self, nodelist):
-        """the same boundaries at other node numbers (model offset in a merged solution, reduced -> user)"""
-        return Package(self.type, nodelist, self.b1, self.b2, self.b3, iflowred=self.iflowred, flowred=self.flowred,
-                       auxnames=self.auxnames, aux=self.aux)
+    def with_nodes(self, nodelist, keep=None):
+        """the same boundaries at other node numbers (model offset in a merged solution, user -> reduced);
+        keep: boolean mask of the boundaries that exist (the others are dropped, their list positions remembered)"""
+        k = slice(None) if keep is None else np.asarray(keep, dtype=bool)
+        bi = self.bound_index if self.bound_index is not None else (None if keep is None else np.arange(self.nodelist.size))
+        return Package(self.type, np.asarray(nodelist)[k], self.b1[k], self.b2[k], self.b3[k], iflowred=self.iflowred,
+                       flowred=self.flowred, auxnames=self.auxnames, aux=None if self.aux is None else self.aux[k],
+                       bound_index=None if bi is None else np.asarray(bi)[k])
 
     def __post_init__(self):
         self.nodelist = T.as_i32(self.nodelist)

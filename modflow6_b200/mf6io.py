@@ -154,6 +154,7 @@ class StressPackage:
     periods: dict            # iper (1-based) -> Package or None (empty period block)
     iflowred: int = 0
     flowred: float = 0.1
+    from_arrays: bool = False     # READASARRAYS input: one boundary per 2-D cell, also over cells that do not exist
 
 
 @dataclass
@@ -326,7 +327,7 @@ def _read_rcha(blocks, name, shape, fixed_cell=0, base_dir=""):
             raise Mf6InputError(f"RCHA {name}: IRCH outside 1..{shape[0]}")
         nodes = (irch.astype(np.int64) - 1) * ncpl + np.arange(ncpl)
         periods[num] = Package(T.PKG_RCH, nodes, rech.copy(), iflowred=fixed_cell)
-    return StressPackage("RCH", name, periods, fixed_cell)
+    return StressPackage("RCH", name, periods, fixed_cell, from_arrays=True)
 
 
 def read_stress_package(path, ftype, name, shape, inewton=0):
@@ -607,12 +608,15 @@ def read_gwf_model(name, nam_path, base_dir, warnings):
                     continue
                 red = gi.nodereduced[p.nodelist]
                 keep = red >= 0
-                if not keep.all():
-                    # the reference stops with an error for a boundary in a cell that IDOMAIN removes
+                if not keep.all() and not sp.from_arrays:
+                    # the reference stops with an error for a LIST boundary in a cell that IDOMAIN removes
                     # (DiscretizationBase noder / "cell is outside active grid domain")
                     raise Mf6InputError(f"{name}: {sp.name} period {iper}: {int((~keep).sum())} boundaries lie in "
                                         "cells that IDOMAIN removes")
-                sp.periods[iper] = p.with_nodes(red)
+                # array input (nlarray_to_nodelist): such an entry gets node 0 -- no recharge, no hand-down to the
+                # layer below, no budget record; the others keep their position in the list as the bound number
+                # (autotest/test_gwf_rch02.py, test_gwf_rch03.py)
+                sp.periods[iper] = p.with_nodes(red, keep=None if keep.all() else keep)
         gi.packages.append(sp)
     if "HFB6" in files:
         gi.hfb = read_hfb(files["HFB6"], shape, gi.nodereduced, m)

@@ -86,7 +86,8 @@ class BudgetFileWriter:
         self._header(kstp, kper, text, self.ncol, self.nrow, self.nlay, 1, delt, pertim, totim)
         self.f.write(values.tobytes())
 
-    def write_list(self, kstp, kper, delt, pertim, totim, text, package_name, nodes, q, auxname=(), aux=None):
+    def write_list(self, kstp, kper, delt, pertim, totim, text, package_name, nodes, q, auxname=(), aux=None,
+                   bound_index=None):
         """save_print_model_flows (BoundaryPackage.f90 / BudgetObject ubdsv06): IMETH = 6 header, the auxiliary
         variable names, then (node, bound index, rate, auxiliary values) per boundary.
         `nodes` are 0-based cell numbers; entries with node < 0 (inactive) are skipped like node <= 0 there."""
@@ -104,7 +105,7 @@ class BudgetFileWriter:
         rec = np.empty(int(keep.sum()), dtype=np.dtype([("n", "<i4"), ("n2", "<i4"), ("q", "<f8"),
                                                         ("aux", "<f8", (naux,))]))
         rec["n"] = nodes[keep] + 1
-        rec["n2"] = np.nonzero(keep)[0] + 1
+        rec["n2"] = (np.nonzero(keep)[0] if bound_index is None else np.asarray(bound_index)[keep]) + 1
         rec["q"] = q[keep]
         if naux:
             rec["aux"] = np.asarray(aux, dtype=np.float64).reshape(nodes.size, naux)[keep]
@@ -157,7 +158,8 @@ class BudgetFileWriter:
             name = package_names[i] if package_names else f"{t}-{count[t]}"   # default package names, e.g. CHD-1
             nodes = p.nodelist if eff is None else eff[i]
             self.write_list(kstp, kper, delt, pertim, totim, t, name, nodes if nodeuser is None else nodeuser[nodes],
-                            sim[i], auxname=getattr(p, "auxnames", ()) or (), aux=getattr(p, "aux", None))
+                            sim[i], auxname=getattr(p, "auxnames", ()) or (), aux=getattr(p, "aux", None),
+                            bound_index=getattr(p, "bound_index", None))
         self.f.flush()
 
     def close(self):

@@ -83,6 +83,44 @@ def test_rch01_on_device(gpu, tmp_path, irch):
     assert g["reports"][0]["outer_iterations"] == c["reports"][0]["outer_iterations"]
 
 
+def test_rch03_on_device(gpu, tmp_path):
+    """autotest/test_gwf_rch03.py:130-146 on the device: the literal RCH budget records of array-based recharge with
+    IRCH over removed / pass-through / constant-head cells (reduced numbering, bound numbers kept)"""
+    from tests.test_mf6io_cpu import _write_rch0203
+    idom = np.array([[[0, 0, 0, 0, 0], [0, -1, 1, -1, 0], [0, -1, 1, -1, 0], [0, 0, 0, 0, 0]],
+                     [[1, 1, 1, 1, 1], [1, 1, 1, -1, 1], [1, 1, 1, 1, 1], [1, 1, 1, 1, 1]]])
+    irch = np.array([[1, 0, 0, 0, 0], [0, 1, 0, 1, 0], [0, 1, 0, 1, 0], [0, 0, 0, 0, 0]]) + 1
+    _write_rch0203(str(tmp_path), idom, irch)
+    g = simulate.run(str(tmp_path), ordering=T.ORDER_NATURAL)
+    assert g["reports"][0]["converged"] == 1
+    rec = [r for r in read_budget_file(tmp_path / "rch.cbc") if r["text"].strip() == "RCH"][0]
+    assert rec["node"].tolist() == [21, 27, 8, 32, 13, 34] and rec["node2"].tolist() == [1, 7, 8, 12, 13, 14]
+    assert np.allclose(rec["q"], [0.0, 7.0, 8.0, 12.0, 13.0, 14.0])
+
+
+@pytest.mark.parametrize("idx", [6, 8])
+def test_thickstrt_hfb_deck_on_device(gpu, tmp_path, idx):
+    """autotest/test_gwf_npf_thickstrt.py cases 7 and 9 from input FILES on the device (NPF THICKSTRT, HFB6)"""
+    from tests.helpers import NPF_THICKSTRT, npf_thickstrt_case
+    _, hfb, heads, inflow = npf_thickstrt_case(idx)
+    d = str(tmp_path)
+    extra = [("HFB6", "hfb", "BEGIN dimensions\n  MAXHFB 1\nEND dimensions\n\nBEGIN period 1\n"
+              "  1 1 3  1 1 4  1.0e-4\nEND period 1\n")]
+    mf6_inputs.write_gwf(d, "flow", (1, 1, 6), 1.0, 1.0, 10.0, [0.0], 1.0, icelltype=NPF_THICKSTRT["icelltype"][idx],
+                         chd={1: [((1, 1, 1), 6.0), ((1, 1, 6), 4.0)]}, strt=5.0, k33=1.0, extra_packages=extra)
+    if NPF_THICKSTRT["thickstrt"][idx]:
+        p = tmp_path / "flow.npf"
+        p.write_text(p.read_text().replace("  SAVE_FLOWS\n", "  SAVE_FLOWS\n  THICKSTRT\n"))
+    ims = ("BEGIN nonlinear\n  OUTER_DVCLOSE 1e-6\n  OUTER_MAXIMUM 10\n  UNDER_RELAXATION NONE\nEND nonlinear\n\n"
+           "BEGIN linear\n  INNER_MAXIMUM 5\n  INNER_DVCLOSE 1e-6\n  INNER_RCLOSE 1e-6\n  LINEAR_ACCELERATION CG\n"
+           "  SCALING_METHOD NONE\n  REORDERING_METHOD NONE\n  RELAXATION_FACTOR 1.0\nEND linear\n")
+    mf6_inputs.write_sim(d, ["flow"], [(1.0, 1, 1.0)], ims)
+    out = simulate.run(d, ordering=T.ORDER_NATURAL)
+    assert np.allclose(heads, out["heads"][0].ravel())
+    cbc = read_budget_file(tmp_path / "flow.cbc")
+    assert cbc[1]["text"].strip() == "CHD" and np.allclose(inflow, cbc[1]["q"][0])
+
+
 def test_ex_gwf_bump_on_device(gpu):
     """the head file MODFLOW 6 itself wrote for autotest/test_gwf_newton_under_relaxation.py (tests/golden):
     Newton-Raphson + Newton under-relaxation + BiCGSTAB on the device against the reference's own output,

@@ -573,3 +573,47 @@ def test_idomain_holes_on_disv_and_disu_decks_equal_the_dis_deck(tmp_path):
         assert cbc[0]["flow"].size == a.nja
         w = [r for r in cbc if r["text"].strip() == "WEL"][0]
         assert w["node"].tolist() == [(2 * 4 + 2) * 5 + 3]          # USER node number
+
+
+def _write_rch0203(d, idomain, irch):
+    """autotest/test_gwf_rch02.py:14-106 / test_gwf_rch03.py:14-128: 2 x 4 x 5 confined cells (top 100, bottoms 50 and
+    0, K 1), CHD 100 at (2, 1, 1), array-based recharge = 2-D cell number (1 .. 20), IDOMAIN with removed (0) and
+    pass-through (-1) cells in the top layer"""
+    per = "BEGIN period 1\n"
+    if irch is not None:
+        per += "  irch\n    INTERNAL FACTOR 1\n" + "".join("      " + " ".join(str(v) for v in row) + "\n" for row in irch)
+    per += "  recharge\n    INTERNAL FACTOR 1.0\n" + "".join(
+        "      " + " ".join(repr(float(v)) for v in row) + "\n" for row in np.arange(20).reshape(4, 5) + 1.0)
+    per += "END period 1\n"
+    mf6_inputs.write_gwf(d, "rch", (2, 4, 5), 1.0, 1.0, 100.0, [50.0, 0.0], 1.0, icelltype=0, strt=100.0,
+                         chd={1: [((2, 1, 1), 100.0)]}, idomain=idomain,
+                         extra_packages=[("RCH6", "rcha", "BEGIN options\n  READASARRAYS\nEND options\n\n" + per)])
+    mf6_inputs.write_sim(d, ["rch"], [(1.0, 1, 1.0)], RCH01_IMS)
+
+
+def test_rch02_array_recharge_over_pass_through_cells(tmp_path):
+    """autotest/test_gwf_rch02.py:109-122: recharge given for pass-through cells (IDOMAIN -1) goes nowhere; every
+    record that is written has node == node2 == q (the recharge array holds the 2-D cell numbers)"""
+    idom = np.ones((2, 4, 5), dtype=int)
+    idom[0, 1:3, 1:4] = -1
+    _write_rch0203(str(tmp_path), idom, None)
+    out = simulate.run(str(tmp_path), ordering=T.ORDER_NATURAL, solution_class=oracle_class())
+    assert out["reports"][0]["converged"] == 1
+    rec = [r for r in read_budget_file(tmp_path / "rch.cbc") if r["text"].strip() == "RCH"][0]
+    assert rec["node"].size == 14
+    assert np.allclose(rec["node"].astype(float), rec["q"]) and np.allclose(rec["node2"], rec["node"])
+
+
+def test_rch03_irch_and_idomain_literal_records(tmp_path):
+    """autotest/test_gwf_rch03.py:130-146: the literal RCH budget records (user nodes 21 27 8 32 13 34, bound
+    numbers 1 7 8 12 13 14, rates 0 7 8 12 13 14) of IRCH pointing at removed, pass-through and constant-head cells"""
+    idom = np.array([[[0, 0, 0, 0, 0], [0, -1, 1, -1, 0], [0, -1, 1, -1, 0], [0, 0, 0, 0, 0]],
+                     [[1, 1, 1, 1, 1], [1, 1, 1, -1, 1], [1, 1, 1, 1, 1], [1, 1, 1, 1, 1]]])
+    irch = np.array([[1, 0, 0, 0, 0], [0, 1, 0, 1, 0], [0, 1, 0, 1, 0], [0, 0, 0, 0, 0]]) + 1   # flopy writes 1-based
+    _write_rch0203(str(tmp_path), idom, irch)
+    out = simulate.run(str(tmp_path), ordering=T.ORDER_NATURAL, solution_class=oracle_class())
+    assert out["reports"][0]["converged"] == 1
+    rec = [r for r in read_budget_file(tmp_path / "rch.cbc") if r["text"].strip() == "RCH"][0]
+    assert rec["node"].tolist() == [21, 27, 8, 32, 13, 34]
+    assert rec["node2"].tolist() == [1, 7, 8, 12, 13, 14]
+    assert np.allclose(rec["q"], [0.0, 7.0, 8.0, 12.0, 13.0, 14.0])
