@@ -100,18 +100,25 @@ def test_c3_full_size_first_step_against_oracle_fixture(gpu, capsys):
         assert res["l2"] <= 3 * ores["l2"], (res, ores)
 
 
-def test_c3_reduced_size_tight_closure(gpu):
-    """config 3 at 5 x 500 x 500 (1.25e6 cells: the largest size at which the oracle finishes the tightly closed
-    Newton solve in reasonable time), inner closure two decades tighter (configs.tighten_inner_closure level 2):
-    the north-star bar, max |dhead| <= 0.1 x OUTER_DVCLOSE against the oracle on the same permuted system"""
+@pytest.mark.parametrize("size", [(5, 500, 500), (5, 1000, 1000)])
+def test_c3_tight_closure_against_oracle_fixture(gpu, size):
+    """config 3 (Newton, BiCGSTAB + ILU0, DBD, pseudo-transient continuation), steady first step, at 1.25e6 and 5e6
+    cells -- the sizes at which the oracle finishes the solve in minutes / an hour -- with the inner closure one decade
+    tighter (configs.tighten_inner_closure level 1: 1e-7 / 1e-7; the oracle's own two orderings then agree to 3.6e-7,
+    profiles/r02_c3_closure_study.json).  North-star bar: max |dhead| <= 0.1 x OUTER_DVCLOSE against the oracle on the
+    same permuted system AND against the reference's own natural-order solve, budget within 1e-3."""
     from oracle import golden
-    tag = "c3_5x500x500_block_tight2"
+    tag = "c3_%dx%dx%d_block_tight" % size
     if golden.load(tag) is None:
         pytest.skip("fixture missing")
-    cfg = configs.tighten_inner_closure(configs.c3_newton(5, 500, 500), 2)
+    cfg = configs.tighten_inner_closure(configs.c3_newton(*size), 1)
     reps, x = _run(cfg, max_steps=1)
     c = golden.compare_heads(tag, x, cfg.sln.dvclose)
     assert reps[0]["converged"] == 1
     assert c["max_abs_dhead"] <= 0.1 * cfg.sln.dvclose, c
     assert abs(reps[0]["pdiffr"] - c["oracle"]["pdiffr"]) <= 1e-3
     assert reps[0]["outer_iterations"] == c["oracle"]["outer_iterations"]
+    n = golden.compare_heads(tag.replace("block", "natural"), x, cfg.sln.dvclose)
+    if n is not None:
+        assert n["max_abs_dhead"] <= 0.1 * cfg.sln.dvclose, n
+        assert abs(reps[0]["pdiffr"] - n["oracle"]["pdiffr"]) <= 1e-3
