@@ -19,6 +19,7 @@ module GpuSolutionBindingsModule
   public :: mf6gpu_sln_settings, mf6gpu_gwf_model, mf6gpu_bnd_package, mf6gpu_step_report
   public :: MF6GPU_MAX_BUDGET_TERMS
   public :: mf6gpu_solution_create, mf6gpu_solution_destroy, mf6gpu_solution_set_packages
+  public :: mf6gpu_solution_set_hfb
   public :: mf6gpu_solution_timestep, mf6gpu_solution_get_x, mf6gpu_solution_set_x
   public :: mf6gpu_solution_get_flowja, mf6gpu_solution_get_simvals, mf6gpu_solution_get_storage
 
@@ -106,6 +107,16 @@ module GpuSolutionBindingsModule
       type(mf6gpu_bnd_package), intent(in) :: pkgs(*)
       integer(c_int) :: rc
     end function
+    function mf6gpu_solution_set_hfb(handle, nhfb, noden, nodem, hydchr, index_base) &
+      bind(C, name="mf6gpu_solution_set_hfb") result(rc)
+      import :: c_int, c_int32_t, c_double, c_ptr
+      type(c_ptr), value :: handle
+      integer(c_int32_t), value :: nhfb
+      integer(c_int32_t), intent(in) :: noden(*), nodem(*)
+      real(c_double), intent(in) :: hydchr(*)
+      integer(c_int32_t), value :: index_base
+      integer(c_int) :: rc
+    end function
     function mf6gpu_solution_timestep(handle, kper, kstp, delt, iss, report) &
       bind(C, name="mf6gpu_solution_timestep") result(rc)
       import :: c_int, c_int32_t, c_double, c_ptr, mf6gpu_step_report
@@ -181,7 +192,8 @@ module GpuNumericalSolutionModule
     real(DP), dimension(:), allocatable :: simvals_all !< package rates, packages concatenated
     real(DP), dimension(:), allocatable :: conn_nx !< x component of every connection's unit normal (lower -> higher cell)
     real(DP), dimension(:), allocatable :: conn_ny !< y component
-    real(DP), dimension(:), allocatable :: ddrn !< contiguous copy of the DRN drainage-depth auxiliary column (one DRN package)
+    integer(I4B), dimension(:), allocatable :: icelltype_user !< icelltype with THICKSTRT cells marked negative again
+    real(DP), dimension(:), allocatable, target :: ddrn !< contiguous copy of the DRN drainage-depth auxiliary column (one DRN package)
   contains
     procedure :: fill_connection_normals => gpu_fill_connection_normals
     procedure :: sln_ar => gpu_sln_ar
@@ -220,6 +232,13 @@ contains
       m%icellavg = g%npf%icellavg; m%inewton = g%inewton; m%inewtonur = g%inewtonur
       m%iperched = g%npf%iperched; m%ivarcv = g%npf%ivarcv; m%idewatcv = g%npf%idewatcv
       m%ithickstrt = g%npf%ithickstrt; m%insto = g%insto
+      ! prepcheck has already folded THICKSTRT into icelltype (0) and ithickstartflag (gwf-npf.f90:1851-1875); the
+      ! device derives the initial saturation itself from a NEGATIVE icelltype, so hand it the user's marking back
+      if (g%npf%ithickstrt /= 0) then
+        allocate (this%icelltype_user(g%dis%nodes))
+        this%icelltype_user = merge(-1, g%npf%icelltype, g%npf%ithickstartflag /= 0)
+        m%icelltype = c_loc(this%icelltype_user)
+      end if
       m%ibotnode = c_loc(g%npf%ibotnode)
       if (g%insto > 0) then
         m%ss = c_loc(g%sto%ss); m%sy = c_loc(g%sto%sy); m%iconvert = c_loc(g%sto%iconvert)
@@ -311,6 +330,13 @@ contains
       end select
     end do
     call mf6gpu_check(mf6gpu_solution_set_packages(this%handle, int(np, c_int32_t), pk))
+    ! horizontal flow barriers of this stress period (GwfHfbType keeps noden / nodem / hydchr, gwf-hfb.f90:33-36;
+    ! hfb_rp has read the list); the device does condsat_reset / condsat_modify, hfb_fc and hfb_cq itself
+    if (this%gwf%inhfb > 0) then
+      call mf6gpu_check(mf6gpu_solution_set_hfb(this%handle, int(this%gwf%hfb%nhfb, c_int32_t), &
+                                                this%gwf%hfb%noden, this%gwf%hfb%nodem, this%gwf%hfb%hydchr, &
+                                                1_c_int32_t))
+    end if
   end subroutine gpu_sln_rp
 
   !> @brief one time step on the device instead of prepareSolve / solve(kiter) loop / finalizeSolve
