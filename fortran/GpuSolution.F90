@@ -189,10 +189,10 @@ module GpuNumericalSolutionModule
   type, extends(NumericalSolutionType) :: GpuNumericalSolutionType
     type(c_ptr) :: handle = c_null_ptr !< mf6gpu_solution*
     class(GwfModelType), pointer :: gwf => null() !< the one model of this solution
-    real(DP), dimension(:), allocatable :: simvals_all !< package rates, packages concatenated
-    real(DP), dimension(:), allocatable :: conn_nx !< x component of every connection's unit normal (lower -> higher cell)
-    real(DP), dimension(:), allocatable :: conn_ny !< y component
-    integer(I4B), dimension(:), allocatable :: icelltype_user !< icelltype with THICKSTRT cells marked negative again
+    real(DP), dimension(:), allocatable, target :: simvals_all !< package rates, packages concatenated
+    real(DP), dimension(:), allocatable, target :: conn_nx !< x component of every connection's unit normal (lower -> higher cell)
+    real(DP), dimension(:), allocatable, target :: conn_ny !< y component
+    integer(I4B), dimension(:), allocatable, target :: icelltype_user !< icelltype with THICKSTRT cells marked negative again
     real(DP), dimension(:), allocatable, target :: ddrn !< contiguous copy of the DRN drainage-depth auxiliary column (one DRN package)
   contains
     procedure :: fill_connection_normals => gpu_fill_connection_normals
