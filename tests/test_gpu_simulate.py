@@ -83,6 +83,18 @@ def test_rch01_on_device(gpu, tmp_path, irch):
     assert g["reports"][0]["outer_iterations"] == c["reports"][0]["outer_iterations"]
 
 
+def test_pertim_zero_length_period_on_device(gpu, tmp_path):
+    """autotest/test_gwf_pertim.py:99-115 on the device: a steady period of length zero, two CHD packages with
+    BOUNDNAMES; literal canal inflow 99928.4941 and river outflow 99928.5036"""
+    from tests.test_mf6io_cpu import write_pertim
+    write_pertim(str(tmp_path))
+    out = simulate.run(str(tmp_path), ordering=T.ORDER_BLOCK_MULTICOLOR)
+    assert out["reports"][0]["converged"] == 1
+    canal, river = [r for r in read_budget_file(tmp_path / "gwf_pertim.cbc") if r["text"].strip() == "CHD"]
+    assert np.allclose([canal["q"][canal["q"] > 0].sum()], [99928.4941])
+    assert np.allclose([-river["q"][river["q"] < 0].sum()], [99928.5036])
+
+
 def test_rch03_on_device(gpu, tmp_path):
     """autotest/test_gwf_rch03.py:130-146 on the device: the literal RCH budget records of array-based recharge with
     IRCH over removed / pass-through / constant-head cells (reduced numbering, bound numbers kept)"""

@@ -617,3 +617,37 @@ def test_rch03_irch_and_idomain_literal_records(tmp_path):
     assert rec["node"].tolist() == [21, 27, 8, 32, 13, 34]
     assert rec["node2"].tolist() == [1, 7, 8, 12, 13, 14]
     assert np.allclose(rec["q"], [0.0, 7.0, 8.0, 12.0, 13.0, 14.0])
+
+
+def write_pertim(d):
+    """autotest/test_gwf_pertim.py:10-96: 3 x 21 x 20 confined cells (K 50 / 0.01 / 200, K33 10 / 0.01 / 20), two CHD
+    packages with BOUNDNAMES (canal 330 on the first column, river 320 on the last), ONE steady period of LENGTH 0,
+    IMS COMPLEXITY SIMPLE"""
+    nlay, nrow, ncol = 3, 21, 20
+    mf6_inputs.write_gwf(d, "gwf_pertim", (nlay, nrow, ncol), 500.0, 500.0, 330.0, [220.0, 200.0, 0.0],
+                         np.broadcast_to(np.array([50.0, 0.01, 200.0])[:, None, None], (nlay, nrow, ncol)),
+                         strt=330.0,
+                         k33=np.broadcast_to(np.array([10.0, 0.01, 20.0])[:, None, None], (nlay, nrow, ncol)))
+    for tag, col, head in (("canal", 1, 330.0), ("river", ncol, 320.0)):
+        with open(f"{d}/gwf_pertim_{tag}.chd", "w") as f:
+            f.write(f"BEGIN options\n  BOUNDNAMES\nEND options\n\nBEGIN dimensions\n  MAXBOUND {nrow}\nEND dimensions\n\n"
+                    "BEGIN period 1\n" + "".join(f"  1 {i + 1} {col} {head!r} {tag}\n" for i in range(nrow))
+                    + "END period 1\n")
+    nam = f"{d}/gwf_pertim.nam"
+    text = open(nam).read().replace("END packages", "  CHD6  gwf_pertim_canal.chd  CHD-CANAL\n"
+                                    "  CHD6  gwf_pertim_river.chd  CHD-RIVER\nEND packages")
+    open(nam, "w").write(text)
+    mf6_inputs.write_sim(d, ["gwf_pertim"], [(0.0, 1, 1.0)], "BEGIN options\n  COMPLEXITY SIMPLE\nEND options\n")
+
+
+def test_pertim_zero_length_period_literal_chd_flows(tmp_path):
+    """autotest/test_gwf_pertim.py:99-115: a steady stress period of length ZERO; the listing budget's CHD_IN
+    99928.4941 and CHD2_OUT 99928.5036 (np.allclose) = inflow through the canal, outflow through the river"""
+    write_pertim(str(tmp_path))
+    out = simulate.run(str(tmp_path), ordering=T.ORDER_NATURAL, solution_class=oracle_class())
+    assert out["reports"][0]["converged"] == 1
+    cbc = read_budget_file(tmp_path / "gwf_pertim.cbc")
+    canal, river = [r for r in cbc if r["text"].strip() == "CHD"]
+    assert canal["srcpackage"].strip() == "CHD-CANAL" and river["srcpackage"].strip() == "CHD-RIVER"
+    assert np.allclose([canal["q"][canal["q"] > 0].sum()], [99928.4941])
+    assert np.allclose([-river["q"][river["q"] < 0].sum()], [99928.5036])
