@@ -15,7 +15,7 @@ import sys
 import numpy as np
 
 from . import ctypes_types as T
-from .grid import Package, merge_models, tdis_steps
+from .grid import merge_models, tdis_steps
 from .mf6io import read_simulation
 from .output import BudgetFileWriter, HeadFileWriter
 

@@ -5,8 +5,6 @@ import sys
 import time
 
 sys.path.insert(0, ".")
-import numpy as np  # noqa: E402
-
 from modflow6_b200 import configs, ctypes_types as T, lib  # noqa: E402
 from modflow6_b200.solution import GpuNumericalSolution  # noqa: E402
 
