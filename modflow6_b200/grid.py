@@ -30,15 +30,49 @@ class Package:
     aux: np.ndarray = None        # budget file records (save_print_model_flows), not used by the solve
     bound_index: np.ndarray = None   # 0-based position of every boundary in the package's own list, when entries of
                                      # that list do not exist in the model (array-based recharge over removed cells)
+    # time series (TS6) and AUXMULTNAME of an input deck, resolved per time step by at_time():
+    ts_links: list = None            # [(target, row, SERIES NAME)], target = "b1" | "b2" | "b3" | ("aux", j)
+    series: dict = None              # {NAME: timeseries.TimeSeries}
+    mult: tuple = None               # (column "b1" | "b2", j): that column is multiplied by auxiliary variable j
 
     def with_nodes(self, nodelist, keep=None):
         """the same boundaries at other node numbers (model offset in a merged solution, user -> reduced);
         keep: boolean mask of the boundaries that exist (the others are dropped, their list positions remembered)"""
         k = slice(None) if keep is None else np.asarray(keep, dtype=bool)
         bi = self.bound_index if self.bound_index is not None else (None if keep is None else np.arange(self.nodelist.size))
+        links = self.ts_links
+        if links and keep is not None:
+            newrow = np.cumsum(k) - 1
+            links = [(t, int(newrow[r]), nm) for t, r, nm in links if k[r]]
         return Package(self.type, np.asarray(nodelist)[k], self.b1[k], self.b2[k], self.b3[k], iflowred=self.iflowred,
                        flowred=self.flowred, auxnames=self.auxnames, aux=None if self.aux is None else self.aux[k],
-                       bound_index=None if bi is None else np.asarray(bi)[k])
+                       bound_index=None if bi is None else np.asarray(bi)[k], ts_links=links, series=self.series,
+                       mult=self.mult)
+
+    @property
+    def time_dependent(self):
+        return bool(self.ts_links)
+
+    def at_time(self, time0, time1):
+        """the package as the solve sees it during the time step [time0, time1]: every entry linked to a time series
+        takes the series' value (tsmgr_ad, TimeSeriesManager.f90:134-260: auxiliary links first, because one of
+        them may be the multiplier), then the multiplier column is applied (bnd `*_mult` functions, e.g.
+        gwf-wel.f90 q_mult, gwf-chd.f90 head_mult, gwf-riv.f90 cond_mult)"""
+        if not self.ts_links and self.mult is None:
+            return self
+        cols = {"b1": self.b1.copy(), "b2": self.b2.copy(), "b3": self.b3.copy()}
+        aux = None if self.aux is None else self.aux.copy()
+        for target, row, name in self.ts_links or ():
+            val = self.series[name].value(time0, time1)
+            if isinstance(target, tuple):
+                aux[row, target[1]] = val
+            else:
+                cols[target][row] = val
+        if self.mult is not None:
+            col, j = self.mult
+            cols[col] = cols[col] * aux[:, j]
+        return Package(self.type, self.nodelist, cols["b1"], cols["b2"], cols["b3"], iflowred=self.iflowred,
+                       flowred=self.flowred, auxnames=self.auxnames, aux=aux, bound_index=self.bound_index)
 
     def __post_init__(self):
         self.nodelist = T.as_i32(self.nodelist)

@@ -23,6 +23,7 @@ import numpy as np
 
 from . import ctypes_types as T
 from .disv import build_disv_model, cell2d_from_vertices
+from .timeseries import TimeSeriesError, read_ts_file  # noqa: F401
 from .grid import Package, build_dis_model, build_dis_model_idomain, build_disu_model, reduce_model
 
 
@@ -336,7 +337,7 @@ def read_stress_package(path, ftype, name, shape, inewton=0):
     auxnames = [a.upper() for a in opt.get("AUXILIARY", opt.get("AUX", []))]
     naux = len(auxnames)
     for k in opt:
-        if k in ("TS6", "TAS6", "MOVER", "AUXMULTNAME") or (k == "READASARRAYS" and ftype != "RCH6"):
+        if k in ("TAS6", "MOVER") or (k == "READASARRAYS" and ftype != "RCH6"):
             raise Mf6InputError(f"{path}: option {k} is not supported on the GPU path")
     fixed_cell = 1 if (ftype == "RCH6" and "FIXED_CELL" in opt) else 0    # carried in Package.iflowred for RCH
     if "READASARRAYS" in opt:
@@ -356,11 +357,41 @@ def read_stress_package(path, ftype, name, shape, inewton=0):
                 raise Mf6InputError(f"{path}: AUXDEPTHNAME {nm_d} is not one of the AUXILIARY variables")
             depth_col = ncol + auxnames.index(nm_d)
     nread = ncol + naux
+    # TS6 FILEIN <file> (any number of them): entries of the list may name a time series instead of a number;
+    # AUXMULTNAME: the auxiliary variable that multiplies the rate / conductance / head column
+    series = {}
+    for ln in _block(b, "OPTIONS", required=False):
+        if ln[0].upper() == "TS6":
+            series.update(read_ts_file(os.path.join(os.path.dirname(path), ln[-1]), read_blocks))
+    mult = None
+    if "AUXMULTNAME" in opt:
+        nm_m = opt["AUXMULTNAME"][0].upper()
+        if nm_m not in auxnames:
+            raise Mf6InputError(f"{path}: AUXMULTNAME {nm_m} is not one of the AUXILIARY variables")
+        mult = ({"CHD6": "b1", "WEL6": "b1", "RCH6": "b1", "RIV6": "b2", "GHB6": "b2", "DRN6": "b2"}[ftype],
+                auxnames.index(nm_m))
+
+    def numbers(tokens, row, links):
+        out = []
+        for c, tok in enumerate(tokens):
+            try:
+                out.append(float(tok))
+            except ValueError:
+                if tok.upper() not in series:
+                    raise Mf6InputError(f"{path}: '{tok}' is neither a number nor a time series of this package") from None
+                if depth_col is not None and c == depth_col:
+                    target = "b3"
+                else:
+                    target = ("b1", "b2", "b3")[c] if c < ncol else ("aux", c - ncol)
+                links.append((target, row, tok.upper()))
+                out.append(0.0)
+        return out
+
     periods = {}
     for nm, num, lines in b:
         if nm != "PERIOD":
             continue
-        nodes, vals = [], []
+        nodes, vals, links = [], [], []
         for t in lines:
             if t[0].upper() == "OPEN/CLOSE":
                 # the list in an external file (ListReader.f90): text rows like the inline ones, or (BINARY)
@@ -381,11 +412,11 @@ def read_stress_package(path, ftype, name, shape, inewton=0):
                             if tt:
                                 node, w = _cellid(tt, shape)
                                 nodes.append(node)
-                                vals.append([float(v) for v in tt[w:w + nread]])
+                                vals.append(numbers(tt[w:w + nread], len(nodes) - 1, links))
                 continue
             node, w = _cellid(t, shape)
             nodes.append(node)
-            vals.append([float(v) for v in t[w:w + nread]])
+            vals.append(numbers(t[w:w + nread], len(nodes) - 1, links))
         if nodes:
             v = np.array(vals)
             cols = [v[:, c] if c < ncol else None for c in range(3)]
@@ -393,7 +424,8 @@ def read_stress_package(path, ftype, name, shape, inewton=0):
                 cols[2] = v[:, depth_col]
             periods[num] = Package(_PKG_TYPE[ftype], np.array(nodes), cols[0], cols[1], cols[2], iflowred=iflowred,
                                    flowred=flowred, auxnames=tuple(auxnames),
-                                   aux=v[:, ncol:ncol + naux].copy() if naux else None)
+                                   aux=v[:, ncol:ncol + naux].copy() if naux else None,
+                                   ts_links=links or None, series=series or None, mult=mult)
         else:
             periods[num] = None
     return StressPackage(ftype[:-1], name, periods, iflowred, flowred), naux

@@ -161,7 +161,13 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
             from .mf6io import Mf6InputError
             raise Mf6InputError(f"period {kper}: the models of the solution disagree on STEADY-STATE / TRANSIENT")
         iss = iss_of[0] if iss_of else 1
-        S.set_packages(pkgs)
+        # AUXMULTNAME without a time series is a constant factor; with time series (TS6) the lists are re-evaluated
+        # every time step (tsmgr_ad at the start of the step: begin = totim, end = totim + delt)
+        pkgs = [p if p.time_dependent else p.at_time(totim, totim) for p in pkgs]
+        timed = any(p.time_dependent for p in pkgs)
+        templates = pkgs
+        if not timed:
+            S.set_packages(pkgs)
         if any(kper in gi.hfb for gi in sim.models):   # hfb_rp: a PERIOD block replaces the model's barrier list
             for k, gi in enumerate(sim.models):
                 if kper in gi.hfb:
@@ -173,6 +179,9 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
             S.set_hfb(*(np.concatenate([l[i] for l in lists]) for i in range(3)))
         pertim = 0.0
         for kstp, delt in enumerate(tdis_steps(perlen, nstp, tsmult), start=1):
+            if timed:
+                pkgs = [p.at_time(totim, totim + delt) for p in templates]
+                S.set_packages(pkgs)
             rep = S.timestep(kper, kstp, delt, iss)
             pertim += delt
             totim += delt

@@ -651,3 +651,53 @@ def test_pertim_zero_length_period_literal_chd_flows(tmp_path):
     assert canal["srcpackage"].strip() == "CHD-CANAL" and river["srcpackage"].strip() == "CHD-RIVER"
     assert np.allclose([canal["q"][canal["q"] > 0].sum()], [99928.4941])
     assert np.allclose([-river["q"][river["q"] < 0].sum()], [99928.5036])
+
+
+def write_auxmult(d, idx):
+    """autotest/test_gwf_utl04_auxmult.py:14-160: 1 x 3 x 3 confined cells, CHD 1 at (1,1,1), one well at (1,3,3) whose
+    rate is a time series ("tsq", constant 1) or the number 1, multiplied by the auxiliary variable AUXMULT, which is
+    the time series "tsqfact" (0, 1, 0, 1 ... at t = 0, 0.1, ... 1, 2, 3, 4; LINEAREND); 10 + 1 + 1 + 1 time steps"""
+    wel = ("BEGIN options\n  AUXILIARY auxmult\n  AUXMULTNAME auxmult\n  PRINT_INPUT\n  TS6 FILEIN m.wel.ts\nEND options\n\n"
+           "BEGIN dimensions\n  MAXBOUND 1\nEND dimensions\n\nBEGIN period 1\n  1 3 3 "
+           + ("tsq" if idx == 0 else "1.0000000") + " tsqfact\nEND period 1\n")
+    mf6_inputs.write_gwf(d, "m", (1, 3, 3), 100.0, 100.0, 0.0, [-1.0], 1.0, chd={1: [((1, 1, 1), 1.0)]}, strt=0.0,
+                         k33=1.0, extra_packages=[("WEL6", "wel", wel)])
+    t = [0.1 * i for i in range(11)] + [2.0, 3.0, 4.0]
+    with open(f"{d}/m.wel.ts", "w") as f:
+        f.write("BEGIN attributes\n  NAMES tsqfact tsq\n  METHODS linearend linearend\nEND attributes\n\nBEGIN timeseries\n"
+                + "".join(f"  {tt!r}  {float(i % 2)!r}  1.0\n" for i, tt in enumerate(t)) + "END timeseries\n")
+    oc = f"{d}/m.oc"
+    text = open(oc).read().replace("SAVE BUDGET LAST", "SAVE BUDGET ALL")
+    open(oc, "w").write(text)
+    ims = ("BEGIN nonlinear\n  OUTER_DVCLOSE 1e-6\n  OUTER_MAXIMUM 100\n  UNDER_RELAXATION NONE\nEND nonlinear\n\n"
+           "BEGIN linear\n  INNER_MAXIMUM 300\n  INNER_DVCLOSE 1e-6\n  INNER_RCLOSE 1e-3\n  LINEAR_ACCELERATION CG\n"
+           "  SCALING_METHOD NONE\n  REORDERING_METHOD NONE\n  RELAXATION_FACTOR 1.0\nEND linear\n")
+    mf6_inputs.write_sim(d, ["m"], [(1.0, 10, 1.0), (1.0, 1, 1.0), (1.0, 1, 1.0), (1.0, 1, 1.0)], ims)
+
+
+@pytest.mark.parametrize("idx", [0, 1])
+def test_auxmult_with_time_series_literal_rates(tmp_path, idx):
+    """autotest/test_gwf_utl04_auxmult.py:163-182: the well rate of every time step in the budget file is
+    1, 0, 1, 0 ... 1 (13 steps) -- TS6 time series (LINEAREND = the value at the end of the step) and AUXMULTNAME"""
+    write_auxmult(str(tmp_path), idx)
+    simulate.run(str(tmp_path), ordering=T.ORDER_NATURAL, solution_class=oracle_class())
+    recs = [r for r in read_budget_file(tmp_path / "m.cbc") if r["text"].strip() == "WEL"]
+    q = np.array([r["q"][0] for r in recs])
+    assert np.allclose(q, np.array(7 * [1.0, 0.0])[:-1])
+    assert [a.strip() for a in recs[0]["auxtxt"]] == ["AUXMULT"]
+    assert np.allclose([r["aux"][0, 0] for r in recs], np.array(7 * [1.0, 0.0])[:-1])
+
+
+def test_time_series_interpolation_methods():
+    """TimeSeries.f90 GetValue: STEPWISE and LINEAR give the time-weighted average over the step, LINEAREND the value
+    at its end; a step beyond the last record is an error (no extension)"""
+    from modflow6_b200.timeseries import TimeSeries, TimeSeriesError
+    t, v = [0.0, 1.0, 3.0], [2.0, 4.0, 0.0]
+    sw, li, le = (TimeSeries("s", m, t, v) for m in ("STEPWISE", "LINEAR", "LINEAREND"))
+    assert sw.value(0.0, 1.0) == 2.0 and np.isclose(sw.value(0.5, 2.0), (0.5 * 2.0 + 1.0 * 4.0) / 1.5)
+    assert np.isclose(li.value(0.0, 1.0), 3.0) and np.isclose(li.value(0.5, 2.0), (0.5 * 3.5 + 1.0 * 3.0) / 1.5)
+    assert np.isclose(le.value(0.5, 2.0), 2.0) and le.value(0.0, 3.0) == 0.0
+    assert sw.value(1.0, 1.0) == 4.0 and np.isclose(li.value(2.0, 2.0), 2.0)
+    for s in (sw, li, le):
+        with pytest.raises(TimeSeriesError):
+            s.value(2.0, 3.5)
