@@ -95,6 +95,16 @@ def test_pertim_zero_length_period_on_device(gpu, tmp_path):
     assert np.allclose([-river["q"][river["q"] < 0].sum()], [99928.5036])
 
 
+def test_auxmult_time_series_on_device(gpu, tmp_path):
+    """autotest/test_gwf_utl04_auxmult.py:163-182 on the device: stress lists re-evaluated from their time series every
+    time step (set_packages per step), well rates 1, 0, 1, 0 ... 1"""
+    from tests.test_mf6io_cpu import write_auxmult
+    write_auxmult(str(tmp_path), 0)
+    simulate.run(str(tmp_path), ordering=T.ORDER_NATURAL)
+    q = np.array([r["q"][0] for r in read_budget_file(tmp_path / "m.cbc") if r["text"].strip() == "WEL"])
+    assert np.allclose(q, np.array(7 * [1.0, 0.0])[:-1])
+
+
 def test_rch03_on_device(gpu, tmp_path):
     """autotest/test_gwf_rch03.py:130-146 on the device: the literal RCH budget records of array-based recharge with
     IRCH over removed / pass-through / constant-head cells (reduced numbering, bound numbers kept)"""
