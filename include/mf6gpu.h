@@ -192,6 +192,13 @@ int mf6gpu_solution_create_dist(const mf6gpu_gwf_model *model, const mf6gpu_sln_
                                 const int32_t *send_idx, const int32_t *recv_ptr,
                                 const int32_t *global_id, mf6gpu_solution **out);
 int mf6gpu_solution_destroy(mf6gpu_solution *s);
+/* GNC, ghost node correction of the connections of a locally refined grid (GhostNode.f90: read_data :739-864,
+ * gnc_fc explicit branch :280-324, gnc_fn :340-443, gnc_cq :478-542).  Entry i corrects the connection between the
+ * connected cells noden[i], nodem[i]; nodesj[i * numj + k] are the contributing cells of noden's grid (a value below
+ * index_base = none) with weights alphasj[i * numj + k].  The correction is applied EXPLICITLY (right-hand side, one
+ * outer iteration behind): the matrix keeps its pattern and its symmetry.  ngnc = 0 removes the corrections. */
+int mf6gpu_solution_set_gnc(mf6gpu_solution *s, int32_t ngnc, int32_t numj, const int32_t *noden,
+                            const int32_t *nodem, const int32_t *nodesj, const double *alphasj, int32_t index_base);
 /* HFB, horizontal flow barriers of the coming stress period(s) (hfb_rp / condsat_modify / hfb_fc / hfb_cq,
  * gwf-hfb.f90:149-450, 770-832): barrier i lies between the connected cells noden[i], nodem[i] with hydraulic
  * characteristic hydchr[i] (negative = multiplier of the conductance).  nhfb = 0 removes the barriers. */

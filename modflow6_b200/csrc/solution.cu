@@ -190,6 +190,126 @@ __global__ void hfb_cq_kernel(HfbView H, ModelView M, const double *__restrict__
   }
 }
 
+// ---- GNC, ghost node correction, EXPLICIT variant (src/Exchange/GhostNode.f90) -------------------------------------
+struct GncView {
+  int ngnc, numj;
+  const int *rn, *rm;            // final rows of noden / nodem
+  const int *jas;                // symmetric connection (n, m)
+  const int *slot_nm, *slot_mn;  // SELL slots of the entries (n, m) and (m, n)
+  const int *rj;                 // [ngnc * numj] final rows of the contributing cells, < 0 = none
+  const double *alpha;           // [ngnc * numj]
+  double *cond;                  // conductance of (n, m) saved by the last formulate (gnc_fmsav :251-273)
+};
+
+// explicit branch of gnc_fc (:280-324): one thread per DISTINCT row walks the corrections of that row in list order;
+// row n loses rterm = alpha cond (h_n - h_j), row m gains it.  Both read the (n, m) entry npf_fc / hfb_fc left.
+__global__ void gnc_fc_kernel(int nrows, const int *__restrict__ ev_row, const int *__restrict__ ev_ptr,
+                              const int *__restrict__ ev_gnc, GncView Gv, ModelView M, const double *__restrict__ h,
+                              const double *__restrict__ val, double *__restrict__ rhs) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nrows; e += gridDim.x * blockDim.x) {
+    const int row = ev_row[e];
+    double r = rhs[row];
+    for (int q = ev_ptr[e]; q < ev_ptr[e + 1]; q++) {
+      const int i = ev_gnc[q];
+      const int n = Gv.rn[i], m = Gv.rm[i];
+      const double cond = val[Gv.slot_nm[i]];
+      if (row == n) Gv.cond[i] = cond;
+      if (M.ibound[n] == 0 || M.ibound[m] == 0) continue;
+      for (int k = 0; k < Gv.numj; k++) {
+        const int j = Gv.rj[i * Gv.numj + k];
+        if (j < 0) continue;
+        const double alpha = Gv.alpha[i * Gv.numj + k];
+        if (alpha == 0.0) continue;
+        const double aterm = alpha * cond;
+        const double rterm = aterm * (h[n] - h[j]);
+        r = (row == n) ? (r - rterm) : (r + rterm);
+      }
+    }
+    rhs[row] = r;
+  }
+}
+
+// gnc_fn (:340-443), single-model arguments (gwf.f90:521-528): row n owns its diagonal and the (n, m) entry, row m
+// its diagonal and (m, n)
+__global__ void gnc_fn_kernel(int nrows, const int *__restrict__ ev_row, const int *__restrict__ ev_ptr,
+                              const int *__restrict__ ev_gnc, GncView Gv, ModelView M, const double *__restrict__ h,
+                              double *__restrict__ val, double *__restrict__ rhs) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nrows; e += gridDim.x * blockDim.x) {
+    const int row = ev_row[e];
+    const long long dslot = (long long)M.slice_ptr[row >> 5] + (row & 31);
+    double r = rhs[row], diag = val[dslot];
+    for (int q = ev_ptr[e]; q < ev_ptr[e + 1]; q++) {
+      const int i = ev_gnc[q];
+      const int n = Gv.rn[i], m = Gv.rm[i], jj = Gv.jas[i];
+      if (M.ibound[n] == 0 || M.ibound[m] == 0) continue;
+      const int ihc = M.ihc[jj];
+      if (ihc == 0 && M.o.ivarcv == 0) continue;
+      const int iups = (h[m] > h[n]) ? 1 : 0;
+      const int up = iups ? m : n;
+      if (M.icelltype[up] == 0) continue;
+      double topup = M.top[up], botup = M.bot[up];
+      const double xup = h[up];
+      if (ihc == 2) {
+        topup = fmin(M.top[n], M.top[m]);
+        botup = fmax(M.bot[n], M.bot[m]);
+      }
+      const double csat = M.condsat[jj];
+      for (int k = 0; k < Gv.numj; k++) {
+        const int j = Gv.rj[i * Gv.numj + k];
+        if (j < 0) continue;
+        if (M.ibound[j] == 0) continue;
+        const double alpha = Gv.alpha[i * Gv.numj + k];
+        if (alpha == 0.0) continue;
+        const double consterm = csat * alpha * (h[n] - h[j]);
+        const double derv = sQuadraticSaturationDerivative(topup, botup, xup, 1.0e-6);
+        const double term = consterm * derv;
+        if (row == n) {
+          if (iups == 0) {
+            diag = diag + term;
+            r = r + term * h[n];
+          } else {
+            if (M.ibound[n] > 0) val[Gv.slot_nm[i]] = val[Gv.slot_nm[i]] + term;
+            r = r + term * h[m];
+          }
+        } else {
+          if (iups == 0) {
+            if (M.ibound[m] > 0) val[Gv.slot_mn[i]] = val[Gv.slot_mn[i]] + (-term);
+            r = r - term * h[n];
+          } else {
+            diag = diag + (-term);
+            r = r - term * h[m];
+          }
+        }
+      }
+    }
+    rhs[row] = r;
+    val[dslot] = diag;
+  }
+}
+
+// gnc_cq (:478-503) with deltaQgnc (:509-542)
+__global__ void gnc_cq_kernel(GncView Gv, ModelView M, const double *__restrict__ h, double *__restrict__ flowja) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Gv.ngnc; i += gridDim.x * blockDim.x) {
+    const int n = Gv.rn[i], m = Gv.rm[i];
+    double dq = 0.0;
+    if (M.ibound[n] != 0 && M.ibound[m] != 0) {
+      double sigalj = 0.0, hd = 0.0;
+      for (int k = 0; k < Gv.numj; k++) {
+        const int j = Gv.rj[i * Gv.numj + k];
+        if (j < 0) continue;
+        if (M.ibound[j] == 0) continue;
+        const double alpha = Gv.alpha[i * Gv.numj + k];
+        sigalj = sigalj + alpha;
+        hd = hd + alpha * h[j];
+      }
+      const double aterm = sigalj * h[n] - hd;
+      dq = aterm * Gv.cond[i];
+    }
+    flowja[Gv.slot_nm[i]] = flowja[Gv.slot_nm[i]] + dq;
+    flowja[Gv.slot_mn[i]] = flowja[Gv.slot_mn[i]] - dq;
+  }
+}
+
 // sgwf_npf_wetdry without rewetting (gwf-npf.f90:2061-2158), the first thing npf_cf does for a model without
 // NEWTON: a convertible cell whose saturated thickness is gone becomes inactive for good (ibound0 keeps it so in
 // later stress periods), its head the dry value; a constant-head cell going dry is fatal (flag)
@@ -1115,6 +1235,13 @@ struct mf6gpu_solution {
   // THICKSTRT: initial saturation per cell (empty = 1 everywhere)
   DevBuf<double> sat0;
   // HFB: barriers of the current period
+  int ngnc = 0, gnc_numj = 0, gnc_nrows = 0;
+  DevBuf<int> gnc_rn, gnc_rm, gnc_jas, gnc_slot_nm, gnc_slot_mn, gnc_rj, gnc_ev_row, gnc_ev_ptr, gnc_ev_gnc;
+  DevBuf<double> gnc_alpha, gnc_cond;
+  GncView gview() const {
+    return GncView{ngnc, gnc_numj, gnc_rn.p, gnc_rm.p, gnc_jas.p, gnc_slot_nm.p, gnc_slot_mn.p, gnc_rj.p, gnc_alpha.p,
+                   gnc_cond.p};
+  }
   int nhfb = 0, hfb_nrows = 0;
   DevBuf<int> hfb_rn, hfb_rm, hfb_jas, hfb_slot_nm, hfb_slot_mn, hfb_ev_row, hfb_ev_ptr, hfb_ev_hfb;
   DevBuf<double> hfb_hydchr, hfb_csatsav, hfb_condsav;
@@ -1327,6 +1454,11 @@ void mf6gpu_solution::buildsystem(int inewton) {
                                                               hview(), M, x.p, A->val.p);
     nl++;
   }
+  if (ngnc > 0) {  // gwf_fc: gnc_fc follows hfb_fc (gwf.f90:496)
+    gnc_fc_kernel<<<grid_for(gnc_nrows), kBlock, 0, stream>>>(gnc_nrows, gnc_ev_row.p, gnc_ev_ptr.p, gnc_ev_gnc.p,
+                                                              gview(), M, x.p, A->val.p, rhs.p);
+    nl++;
+  }
   if (nseg > 0)
     bnd_scatter_kernel<<<grid_for(nseg), kBlock, 0, stream>>>(nseg, seg_node.p, seg_ptr.p, seg_idx.p, B, M,
                                                               x.p, A->val.p, rhs.p, flowja.p, 0);
@@ -1336,6 +1468,11 @@ void mf6gpu_solution::buildsystem(int inewton) {
   }
   if (inewton && o.inewton) {
     newton_rows_kernel<<<G, kBlock, 0, stream>>>(M, x.p, A->val.p, rhs.p, transient, tled);
+    if (ngnc > 0) {
+      gnc_fn_kernel<<<grid_for(gnc_nrows), kBlock, 0, stream>>>(gnc_nrows, gnc_ev_row.p, gnc_ev_ptr.p, gnc_ev_gnc.p,
+                                                                gview(), M, x.p, A->val.p, rhs.p);
+      nl++;
+    }
     if (nseg > 0)
       bnd_scatter_kernel<<<grid_for(nseg), kBlock, 0, stream>>>(nseg, seg_node.p, seg_ptr.p, seg_idx.p, B,
                                                                 M, x.p, A->val.p, rhs.p, flowja.p, 1);
@@ -2055,6 +2192,71 @@ int mf6gpu_solution_set_hfb(mf6gpu_solution *s, int32_t nhfb, const int32_t *nod
   });
 }
 
+// GNC6 package data (GhostNode.f90 read_data :739-864), EXPLICIT correction only
+int mf6gpu_solution_set_gnc(mf6gpu_solution *s, int32_t ngnc, int32_t numj, const int32_t *noden,
+                            const int32_t *nodem, const int32_t *nodesj, const double *alphasj, int32_t index_base) {
+  return guard([&] {
+    MF6_REQUIRE(s && ngnc >= 0 && numj >= 0 && (ngnc == 0 || (noden && nodem)), "solution_set_gnc: bad argument");
+    MF6_REQUIRE(ngnc == 0 || numj == 0 || (nodesj && alphasj), "solution_set_gnc: bad argument");
+    MF6_REQUIRE(!s->halo.active(), "solution_set_gnc: GNC is not available on the split-model path");
+    s->ngnc = ngnc;
+    s->gnc_numj = numj;
+    if (ngnc == 0) return;
+    std::vector<int> csr2sell((size_t)s->nja);
+    s->A->csr2sell.download(csr2sell.data(), (size_t)s->nja);
+    const int b0 = s->index_base;
+    auto find = [&](int v, int u) {
+      for (int p = s->h_ia[v] - b0 + 1; p < s->h_ia[v + 1] - b0; p++)
+        if (s->h_ja[p] - b0 == u) return p;
+      return -1;
+    };
+    std::vector<int> rn(ngnc), rm(ngnc), jas(ngnc), snm(ngnc), smn(ngnc), rj((size_t)ngnc * std::max(numj, 1), -1);
+    std::vector<double> al((size_t)ngnc * std::max(numj, 1), 0.0);
+    std::vector<std::pair<int, int>> ev;
+    for (int i = 0; i < ngnc; i++) {
+      const int v = noden[i] - index_base, u = nodem[i] - index_base;
+      MF6_REQUIRE(v >= 0 && v < s->n && u >= 0 && u < s->n, "solution_set_gnc: cell out of range");
+      const int pnm = find(v, u), pmn = find(u, v);
+      MF6_REQUIRE(pnm >= 0 && pmn >= 0, "solution_set_gnc: GHOST NODE ERROR, the two cells are not connected");
+      rn[i] = s->A->iperm[v];
+      rm[i] = s->A->iperm[u];
+      jas[i] = s->h_conn_jas[pnm];
+      snm[i] = csr2sell[pnm];
+      smn[i] = csr2sell[pmn];
+      for (int k = 0; k < numj; k++) {
+        const int j = nodesj[(size_t)i * numj + k] - index_base;
+        MF6_REQUIRE(j < s->n, "solution_set_gnc: contributing cell out of range");
+        rj[(size_t)i * numj + k] = (j >= 0) ? s->A->iperm[j] : -1;
+        al[(size_t)i * numj + k] = alphasj[(size_t)i * numj + k];
+      }
+      ev.emplace_back(rn[i], i);
+      ev.emplace_back(rm[i], i);
+    }
+    std::sort(ev.begin(), ev.end());
+    std::vector<int> ev_row, ev_ptr, ev_gnc;
+    for (size_t e = 0; e < ev.size(); e++) {
+      if (e == 0 || ev[e].first != ev[e - 1].first) {
+        ev_row.push_back(ev[e].first);
+        ev_ptr.push_back((int)e);
+      }
+      ev_gnc.push_back(ev[e].second);
+    }
+    ev_ptr.push_back((int)ev.size());
+    s->gnc_nrows = (int)ev_row.size();
+    s->gnc_rn.upload(rn);
+    s->gnc_rm.upload(rm);
+    s->gnc_jas.upload(jas);
+    s->gnc_slot_nm.upload(snm);
+    s->gnc_slot_mn.upload(smn);
+    s->gnc_rj.upload(rj);
+    s->gnc_alpha.upload(al);
+    s->gnc_cond.alloc_zero((size_t)ngnc);
+    s->gnc_ev_row.upload(ev_row);
+    s->gnc_ev_ptr.upload(ev_ptr);
+    s->gnc_ev_gnc.upload(ev_gnc);
+  });
+}
+
 int mf6gpu_solution_set_packages(mf6gpu_solution *s, int32_t npkg, const mf6gpu_bnd_package *pk) {
   return guard([&] {
     MF6_REQUIRE(s && (npkg == 0 || pk), "solution_set_packages: null argument");
@@ -2199,6 +2401,7 @@ int mf6gpu_solution_timestep(mf6gpu_solution *s, int32_t kper, int32_t kstp, dou
                                            s->strgsy.p, transient, 1.0 / delt);
     if (s->nhfb > 0 && s->o.inewton == 0 && !s->o.all_confined)
       hfb_cq_kernel<<<grid_for(s->nhfb), kBlock, 0, st>>>(s->hview(), M, s->x.p, s->flowja.p);
+    if (s->ngnc > 0) gnc_cq_kernel<<<grid_for(s->ngnc), kBlock, 0, st>>>(s->gview(), M, s->x.p, s->flowja.p);
     if (s->nb > 0) {
       bnd_cf_kernel<<<grid_for(s->nb), kBlock, 0, st>>>(B, M, s->x.p);
       bnd_scatter_kernel<<<grid_for(s->nseg), kBlock, 0, st>>>(s->nseg, s->seg_node.p, s->seg_ptr.p,

@@ -32,7 +32,7 @@ SYMBOLS = [
     "mf6gpu_solution_get_simvals", "mf6gpu_solution_get_storage", "mf6gpu_solution_get_nodes",
     "mf6gpu_ordering_compute", "mf6gpu_model_elimination_order",
     "mf6gpu_solver_set_models", "mf6gpu_solver_get_model_summary",
-    "mf6gpu_host_register", "mf6gpu_host_unregister", "mf6gpu_solution_set_hfb",
+    "mf6gpu_host_register", "mf6gpu_host_unregister", "mf6gpu_solution_set_hfb", "mf6gpu_solution_set_gnc",
 ]
 
 _lib = None
@@ -113,6 +113,7 @@ def load():
     L.mf6gpu_solution_destroy.argtypes = [vp]
     L.mf6gpu_solution_set_packages.argtypes = [vp, i32, C.POINTER(T.BndPackageStruct)]
     L.mf6gpu_solution_set_hfb.argtypes = [vp, i32, pi32, pi32, pf64, i32]
+    L.mf6gpu_solution_set_gnc.argtypes = [vp, i32, i32, pi32, pi32, pi32, pf64, i32]
     L.mf6gpu_solution_timestep.argtypes = [vp, i32, i32, f64, i32, C.POINTER(T.StepReport)]
     L.mf6gpu_solution_formulate.argtypes = [vp, i32, f64, i32]
     for f in ("get_x", "set_x", "get_amat", "get_rhs", "get_flowja", "get_condsat"):

@@ -40,6 +40,15 @@ class GpuNumericalSolution:
         a, b, h = T.as_i32(noden), T.as_i32(nodem), T.as_f64(hydchr)
         check(self._L.mf6gpu_solution_set_hfb(self.h, a.size, T.ptr_i32(a), T.ptr_i32(b), T.ptr_f64(h), 0))
 
+    def set_gnc(self, noden, nodem, nodesj, alphasj):
+        """GNC6 (explicit): entry i corrects the connection noden[i] - nodem[i] with the contributing cells
+        nodesj[i, :] (< 0 = none) weighted by alphasj[i, :]; 0-based nodes"""
+        a, b = T.as_i32(noden), T.as_i32(nodem)
+        j = T.as_i32(np.asarray(nodesj).reshape(a.size, -1)) if a.size else T.as_i32(np.zeros((0, 0)))
+        al = T.as_f64(np.asarray(alphasj, dtype=np.float64).reshape(a.size, -1)) if a.size else T.as_f64(np.zeros(0))
+        check(self._L.mf6gpu_solution_set_gnc(self.h, a.size, j.shape[1] if a.size else 0, T.ptr_i32(a), T.ptr_i32(b),
+                                              T.ptr_i32(j.reshape(-1)), T.ptr_f64(al.reshape(-1)), 0))
+
     # sln_ca for one time step
     def timestep(self, kper=1, kstp=1, delt=1.0, iss=1):
         rep = T.StepReport()

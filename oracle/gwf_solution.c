@@ -62,6 +62,9 @@ struct orc_solution {
   /* THICKSTRT (gwf-npf.f90:1838-1882): initial saturation of every cell (1 unless flagged) */
   double *sat0;
   /* HFB (gwf-hfb.f90): barriers between cells noden / nodem, hydraulic characteristic */
+  /* GNC, ghost node correction (src/Exchange/GhostNode.f90), EXPLICIT variant */
+  int ngnc, gnc_numj, *gnc_n, *gnc_m, *gnc_j, *gnc_pos;
+  double *gnc_alpha, *gnc_cond;
   int nhfb, *hfb_n, *hfb_m, *hfb_pos;
   double *hfb_hydchr, *hfb_condsav, *hfb_csatsav;
   /* REWET (gwf-npf.f90:2061-2223) */
@@ -1046,6 +1049,7 @@ void orc_sln_destroy(orc_solution *S) {
   free(S->cl1); free(S->cl2); free(S->hwva); free(S->top); free(S->bot);
   free(S->area); free(S->k11); free(S->k33); free(S->ss); free(S->sy); free(S->hyc); free(S->wetdry); free(S->sat0);
   free(S->hfb_n); free(S->hfb_m); free(S->hfb_pos); free(S->hfb_hydchr); free(S->hfb_condsav); free(S->hfb_csatsav);
+  free(S->gnc_n); free(S->gnc_m); free(S->gnc_j); free(S->gnc_pos); free(S->gnc_alpha); free(S->gnc_cond);
   free(S->icelltype); free(S->iconvert); free(S->ibound0); free(S->ibound);
   free(S->ibotnode); free(S->x); free(S->xold); free(S->sat); free(S->condsat);
   free(S->amat); free(S->rhs); free(S->xtemp); free(S->dxold); free(S->wsave);
@@ -1181,6 +1185,118 @@ static void hfb_cq(orc_solution *S) {
   }
 }
 
+/* ---- GNC: ghost node correction, EXPLICIT (GhostNode.f90).  noden / nodem: the connected pair; nodesj[numj] per
+ * entry: the contributing cells of noden's grid (< 0 = none) with weights alphasj.  Nodes 0-based. ---- */
+void orc_sln_set_gnc(orc_solution *S, int ngnc, int numj, const int *noden, const int *nodem, const int *nodesj,
+                     const double *alphasj) {
+  free(S->gnc_n); free(S->gnc_m); free(S->gnc_j); free(S->gnc_pos); free(S->gnc_alpha); free(S->gnc_cond);
+  S->ngnc = ngnc;
+  S->gnc_numj = numj;
+  size_t c = (size_t)(ngnc ? ngnc : 1), cj = c * (size_t)(numj ? numj : 1);
+  S->gnc_n = (int *)calloc(c, sizeof(int));
+  S->gnc_m = (int *)calloc(c, sizeof(int));
+  S->gnc_pos = (int *)calloc(c, sizeof(int));
+  S->gnc_cond = (double *)calloc(c, sizeof(double));
+  S->gnc_j = (int *)calloc(cj, sizeof(int));
+  S->gnc_alpha = (double *)calloc(cj, sizeof(double));
+  for (int i = 0; i < ngnc; i++) {
+    int n = noden[i], m = nodem[i], pos = -1;
+    for (int p = S->ia[n] + 1; p < S->ia[n + 1]; p++)
+      if (S->ja[p] == m) pos = p;
+    S->gnc_n[i] = n;
+    S->gnc_m[i] = m;
+    S->gnc_pos[i] = pos; /* idxglo (gnc_mc :172-246); < 0 = not connected (input error there) */
+    for (int k = 0; k < numj; k++) {
+      S->gnc_j[i * numj + k] = nodesj[i * numj + k];
+      S->gnc_alpha[i * numj + k] = alphasj[i * numj + k];
+    }
+  }
+}
+
+/* gnc_fmsav :251-273 + the explicit branch of gnc_fc :280-324 */
+static void gnc_fc(orc_solution *S) {
+  for (int i = 0; i < S->ngnc; i++) S->gnc_cond[i] = (S->gnc_pos[i] >= 0) ? S->amat[S->gnc_pos[i]] : 0.0;
+  for (int i = 0; i < S->ngnc; i++) {
+    int n = S->gnc_n[i], m = S->gnc_m[i];
+    if (S->ibound[n] == 0 || S->ibound[m] == 0) continue;
+    double cond = S->gnc_cond[i];
+    for (int k = 0; k < S->gnc_numj; k++) {
+      int j = S->gnc_j[i * S->gnc_numj + k];
+      if (j < 0) continue;
+      double alpha = S->gnc_alpha[i * S->gnc_numj + k];
+      if (alpha == 0.0) continue;
+      double aterm = alpha * cond;
+      double rterm = aterm * (S->x[n] - S->x[j]);
+      S->rhs[n] = S->rhs[n] - rterm;
+      S->rhs[m] = S->rhs[m] + rterm;
+    }
+  }
+}
+
+/* gnc_fn :340-443 (single-model arguments of gwf_fc, gwf.f90:521-528) */
+static void gnc_fn(orc_solution *S) {
+  for (int i = 0; i < S->ngnc; i++) {
+    int n = S->gnc_n[i], m = S->gnc_m[i], ipos = S->gnc_pos[i];
+    if (S->ibound[n] == 0 || S->ibound[m] == 0 || ipos < 0) continue;
+    int jj = S->jas[ipos], ihc = S->ihc[jj];
+    double csat = S->condsat[jj];
+    if (ihc == 0 && S->ivarcv == 0) continue;
+    int iups = (S->x[m] > S->x[n]) ? 1 : 0;
+    int up = iups ? m : n;
+    double topup = S->top[up], botup = S->bot[up], xup = S->x[up];
+    if (S->icelltype[up] == 0) continue;
+    if (ihc == 2) {
+      topup = S->top[n] < S->top[m] ? S->top[n] : S->top[m];
+      botup = S->bot[n] > S->bot[m] ? S->bot[n] : S->bot[m];
+    }
+    for (int k = 0; k < S->gnc_numj; k++) {
+      int j = S->gnc_j[i * S->gnc_numj + k];
+      if (j < 0) continue;
+      if (S->ibound[j] == 0) continue;
+      double alpha = S->gnc_alpha[i * S->gnc_numj + k];
+      if (alpha == 0.0) continue;
+      double consterm = csat * alpha * (S->x[n] - S->x[j]);
+      double derv = sQuadraticSaturationDerivative(topup, botup, xup, DEM6);
+      double term = consterm * derv;
+      if (iups == 0) {
+        S->amat[S->ia[n]] += term;
+        if (S->ibound[m] > 0) S->amat[S->isym[ipos]] += -term;
+        S->rhs[n] = S->rhs[n] + term * S->x[n];
+        S->rhs[m] = S->rhs[m] - term * S->x[n];
+      } else {
+        S->amat[S->ia[m]] += -term;
+        if (S->ibound[n] > 0) S->amat[ipos] += term;
+        S->rhs[n] = S->rhs[n] + term * S->x[m];
+        S->rhs[m] = S->rhs[m] - term * S->x[m];
+      }
+    }
+  }
+}
+
+/* gnc_cq :478-503 with deltaQgnc :509-542 */
+static void gnc_cq(orc_solution *S) {
+  for (int i = 0; i < S->ngnc; i++) {
+    int n = S->gnc_n[i], m = S->gnc_m[i], ipos = S->gnc_pos[i];
+    double dq = 0.0;
+    if (S->ibound[n] != 0 && S->ibound[m] != 0) {
+      double sigalj = 0.0, hd = 0.0;
+      for (int k = 0; k < S->gnc_numj; k++) {
+        int j = S->gnc_j[i * S->gnc_numj + k];
+        if (j < 0) continue;
+        if (S->ibound[j] == 0) continue;
+        double alpha = S->gnc_alpha[i * S->gnc_numj + k];
+        sigalj = sigalj + alpha;
+        hd = hd + alpha * S->x[j];
+      }
+      double aterm = sigalj * S->x[n] - hd;
+      dq = aterm * S->gnc_cond[i];
+    }
+    if (ipos < 0) continue;
+    S->flowja[ipos] = S->flowja[ipos] + dq;
+    S->flowja[S->isym[ipos]] = S->flowja[S->isym[ipos]] - dq;
+  }
+}
+
 /* sln_buildsystem :1941-1991 (single model, no exchanges) */
 static void buildsystem(orc_solution *S, int inewton) {
   memset(S->amat, 0, sizeof(double) * (size_t)S->nja);
@@ -1191,10 +1307,12 @@ static void buildsystem(orc_solution *S, int inewton) {
   /* gwf_fc */
   npf_fc(S);
   if (S->nhfb > 0) hfb_fc(S); /* gwf_fc: right after npf_fc (gwf.f90:500-506) */
+  if (S->ngnc > 0) gnc_fc(S);
   if (S->insto) sto_fc(S);
   for (int k = 0; k < S->npkg; k++) bnd_fc(S, &S->pkg[k]);
   if (inewton && S->inewton) {
     npf_fn(S);
+    if (S->ngnc > 0) gnc_fn(S);
     if (S->insto) sto_fn(S);
     for (int k = 0; k < S->npkg; k++) bnd_fn(S, &S->pkg[k]);
   }
@@ -1520,6 +1638,7 @@ int orc_sln_timestep(orc_solution *S, int kper, int kstp, double delt, int iss,
   memset(S->flowja, 0, sizeof(double) * (size_t)S->nja);
   npf_cq(S);
   if (S->nhfb > 0) hfb_cq(S);
+  if (S->ngnc > 0) gnc_cq(S);
   if (S->insto) sto_cq(S);
   for (int k = 0; k < S->npkg; k++) {
     pkg_t *p = &S->pkg[k];

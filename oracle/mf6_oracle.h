@@ -155,6 +155,8 @@ void orc_sln_destroy(orc_solution *S);
 /* set stress data for the coming period(s); arrays are copied */
 void orc_sln_set_packages(orc_solution *S, int npkg, const mf6gpu_bnd_package *pk);
 /* HFB list of the coming period(s) (hfb_rp, gwf-hfb.f90:149-201); 0-based cells */
+void orc_sln_set_gnc(orc_solution *S, int ngnc, int numj, const int *noden, const int *nodem, const int *nodesj,
+                     const double *alphasj);
 void orc_sln_set_hfb(orc_solution *S, int nhfb, const int *noden, const int *nodem, const double *hydchr);
 /* one time step: prepareSolve + outer loop + finalizeSolve
  * (NumericalSolution.f90:1287-1327, 1437-1470, 1844-1938).

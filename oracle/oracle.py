@@ -66,6 +66,7 @@ def lib():
         L.orc_ims_set_blocks.argtypes = [vp, T.p_i32]
         L.orc_sln_set_packages.argtypes = [vp, C.c_int, C.POINTER(T.BndPackageStruct)]
         L.orc_sln_set_hfb.argtypes = [vp, C.c_int, T.p_i32, T.p_i32, T.p_f64]
+        L.orc_sln_set_gnc.argtypes = [vp, C.c_int, C.c_int, T.p_i32, T.p_i32, T.p_i32, T.p_f64]
         L.orc_sln_timestep.restype = C.c_int
         L.orc_sln_timestep.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(T.StepReport)]
         L.orc_sln_formulate.argtypes = [vp, C.c_int, C.c_double, C.c_int]
@@ -226,6 +227,15 @@ class OracleSolution:
         """horizontal flow barriers between cells noden[i] / nodem[i] (0-based) with hydraulic characteristic"""
         a, b, h = T.as_i32(noden), T.as_i32(nodem), T.as_f64(hydchr)
         lib().orc_sln_set_hfb(self.h, a.size, T.ptr_i32(a), T.ptr_i32(b), T.ptr_f64(h))
+
+    def set_gnc(self, noden, nodem, nodesj, alphasj):
+        """ghost node correction (EXPLICIT): entry i corrects the connection noden[i] - nodem[i] with the contributing
+        cells nodesj[i, :] (< 0 = none) and weights alphasj[i, :]; 0-based nodes"""
+        a, b = T.as_i32(noden), T.as_i32(nodem)
+        j = T.as_i32(np.asarray(nodesj).reshape(a.size, -1))
+        al = T.as_f64(np.asarray(alphasj, dtype=np.float64).reshape(a.size, -1))
+        lib().orc_sln_set_gnc(self.h, a.size, j.shape[1] if a.size else 0, T.ptr_i32(a), T.ptr_i32(b),
+                              T.ptr_i32(j.reshape(-1)), T.ptr_f64(al.reshape(-1)))
 
     @property
     def simvals(self):

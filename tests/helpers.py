@@ -129,3 +129,66 @@ def npf_thickstrt_case(idx):
     inflow = [4.0, 4.0, 2.0, 1.9965396769631871, 1.9965396769631871, 1.9990e-03, 1.9980e-03, 9.9949e-04,
               9.9949e-04][idx]
     return cfg, hfb, heads, inflow
+
+
+def nested_grid_case():
+    """A locally refined 2-D grid as ONE DISU model, the textbook case for the ghost node correction: 3 x 4 coarse
+    cells of 2 x 2 (x 0..6) next to 4 x 8 fine cells of 1 x 1 (x 6..10), one confined layer, K = 1.  Every coarse cell
+    of the last coarse column touches TWO fine cells whose centres sit 0.5 above / below its own, so the plain
+    two-point flux is wrong for any head field with a y-gradient; the ghost node on the coarse side, interpolated
+    between the coarse cell and its neighbour above / below with alpha = 0.5 / 2, removes that error exactly for a
+    LINEAR field.  All boundary cells are constant heads on h = 10 + 0.7 x + 0.3 y.
+    Returns (model, chd package, gnc tuple (noden, nodem, nodesj, alphasj), exact heads)."""
+    from modflow6_b200.grid import build_disu_model
+    ncx, ncy, nfx, nfy = 3, 4, 4, 8
+    nc = ncx * ncy
+    n = nc + nfx * nfy
+    cid = lambda r, c: r * ncx + c                      # noqa: E731
+    fid = lambda r, c: nc + r * nfx + c                 # noqa: E731
+    x, y, size = np.zeros(n), np.zeros(n), np.zeros(n)
+    for r in range(ncy):
+        for c in range(ncx):
+            x[cid(r, c)], y[cid(r, c)], size[cid(r, c)] = 2 * c + 1.0, 2 * r + 1.0, 2.0
+    for r in range(nfy):
+        for c in range(nfx):
+            x[fid(r, c)], y[fid(r, c)], size[fid(r, c)] = 6.5 + c, r + 0.5, 1.0
+    nbr = [dict() for _ in range(n)]                    # node -> {neighbour: (cl of this side, width)}
+
+    def link(a, b, cla, clb, w):
+        nbr[a][b] = (cla, w)
+        nbr[b][a] = (clb, w)
+    for r in range(ncy):
+        for c in range(ncx):
+            if c + 1 < ncx:
+                link(cid(r, c), cid(r, c + 1), 1.0, 1.0, 2.0)
+            if r + 1 < ncy:
+                link(cid(r, c), cid(r + 1, c), 1.0, 1.0, 2.0)
+    for r in range(nfy):
+        for c in range(nfx):
+            if c + 1 < nfx:
+                link(fid(r, c), fid(r, c + 1), 0.5, 0.5, 1.0)
+            if r + 1 < nfy:
+                link(fid(r, c), fid(r + 1, c), 0.5, 0.5, 1.0)
+    gn, gm, gj, ga = [], [], [], []
+    for r in range(ncy):
+        for half in (0, 1):
+            a, b = cid(r, ncx - 1), fid(2 * r + half, 0)
+            link(a, b, 1.0, 0.5, 1.0)
+            rj = r + (1 if half else -1)                # the coarse neighbour on the side of the fine cell's centre
+            if 0 <= rj < ncy:
+                gn.append(a); gm.append(b); gj.append([cid(rj, ncx - 1)]); ga.append([0.25])
+    iac, ja, ihc, cl12, hwva = [], [], [], [], []
+    for a in range(n):
+        cols = sorted(nbr[a])
+        iac.append(1 + len(cols))
+        ja += [a] + cols
+        ihc += [1] * (1 + len(cols))
+        cl12 += [0.0] + [nbr[a][b][0] for b in cols]
+        hwva += [0.0] + [nbr[a][b][1] for b in cols]
+    exact = 10.0 + 0.7 * x + 0.3 * y
+    m = build_disu_model(np.array(iac), np.array(ja), np.array(ihc), np.array(cl12), np.array(hwva), 1.0, 0.0,
+                         size * size, 1.0, icelltype=0, strt=10.0)
+    edge = [a for a in range(n) if (x[a] - size[a] / 2 <= 0 or x[a] + size[a] / 2 >= 10
+                                    or y[a] - size[a] / 2 <= 0 or y[a] + size[a] / 2 >= 8)]
+    chd = Package(T.PKG_CHD, edge, exact[edge])
+    return m, chd, (np.array(gn), np.array(gm), np.array(gj), np.array(ga)), exact

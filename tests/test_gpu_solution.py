@@ -413,3 +413,51 @@ def test_hfb_many_barriers_parity(gpu, ordering):
         if prev is not None:
             assert np.abs(G.x - prev).max() > 1e-3     # the changed wall changed the heads
         prev = np.array(G.x, copy=True)
+
+
+@pytest.mark.parametrize("ordering", [T.ORDER_NATURAL, T.ORDER_BLOCK_MULTICOLOR])
+def test_gnc_nested_grid_on_device(gpu, ordering):
+    """ghost node correction (explicit) on the device: the linear head field on the locally refined DISU grid is
+    restored to 1e-8 (the uncorrected run is centimetres off), heads and corrected flows equal the oracle's"""
+    from modflow6_b200.solution import GpuNumericalSolution
+    from oracle.oracle import OracleSolution
+    from tests.helpers import nested_grid_case
+    m, chd, gnc, exact = nested_grid_case()
+    ims = T.ImsSettings.make(dvclose=1e-12, rclose=1e-12, iter1=200, ilinmeth=1, gpu_ordering=ordering)
+    sln = T.SlnSettings.make(dvclose=1e-10, mxiter=200)
+    G = GpuNumericalSolution(m, sln, ims)
+    O = OracleSolution(m, sln, ims, perm=None if ordering == T.ORDER_NATURAL else G.elimination_order())
+    for S in (G, O):
+        S.set_packages([chd])
+        S.set_gnc(*gnc)
+    rg, ro = G.timestep(1, 1, 1.0, 1), O.timestep(1, 1, 1.0, 1)
+    assert rg.converged == 1 and ro.converged == 1 and rg.outer_iterations == ro.outer_iterations
+    assert np.abs(G.x - exact).max() < 1e-8
+    assert np.abs(G.x - O.x).max() < 1e-9
+    assert np.abs(G.flowja - O.flowja).max() < 1e-8
+    assert abs(rg.pdiffr) < 1e-6
+    G.set_gnc(np.zeros(0, int), np.zeros(0, int), np.zeros((0, 1), int), np.zeros((0, 1)))     # remove them again
+    G.timestep(1, 2, 1.0, 1)
+    assert np.abs(G.x - exact).max() > 1e-2
+
+
+@pytest.mark.parametrize("newton", [0, 1])
+def test_gnc_unconfined_nested_grid_parity(gpu, newton):
+    """the nested grid with a water table, Picard (gnc_fc) and NEWTON (gnc_fc + gnc_fn): device == oracle, same
+    outer iteration count"""
+    from modflow6_b200.solution import GpuNumericalSolution
+    from oracle.oracle import OracleSolution
+    from tests.helpers import nested_grid_case
+    m, chd, gnc, _ = nested_grid_case()
+    m.top[:], m.icelltype[:], m.inewton = 25.0, 1, newton
+    ims = T.ImsSettings.make(dvclose=1e-12, rclose=1e-10, iter1=200, ilinmeth=2, gpu_ordering=T.ORDER_NATURAL)
+    sln = T.SlnSettings.make(dvclose=1e-10, mxiter=300)
+    G, O = GpuNumericalSolution(m, sln, ims), OracleSolution(m, sln, ims)
+    for S in (G, O):
+        S.set_packages([chd])
+        S.set_gnc(*gnc)
+    rg, ro = G.timestep(1, 1, 1.0, 1), O.timestep(1, 1, 1.0, 1)
+    assert rg.converged == 1 and ro.converged == 1 and rg.outer_iterations == ro.outer_iterations
+    assert np.abs(G.x - O.x).max() < 1e-9
+    assert np.abs(G.flowja - O.flowja).max() < 1e-8
+    assert abs(rg.pdiffr - ro.pdiffr) < 1e-6

@@ -563,3 +563,54 @@ def test_npf_thickstrt_hfb_literal_answers(idx):
     S.timestep(1, 1, 1.0, 1)
     assert np.allclose(heads, S.x)
     assert np.allclose(inflow, S.simvals[0][0])
+
+
+def test_gnc_restores_the_linear_field_on_a_nested_grid():
+    """Ghost node correction (GhostNode.f90 gnc_fc explicit branch :280-324, gnc_cq :478-542).  The reference has no
+    GNC case with literal answers in autotest/, so the pin is the property the method is built on (Panday and
+    Langevin 2012): with the ghost nodes interpolated correctly a LINEAR head field satisfies the discrete equations
+    of a locally refined grid exactly; without them it does not"""
+    from tests.helpers import nested_grid_case
+    m, chd, gnc, exact = nested_grid_case()
+    ims = T.ImsSettings.make(dvclose=1e-12, rclose=1e-12, iter1=200, ilinmeth=1)
+    sln = T.SlnSettings.make(dvclose=1e-10, mxiter=200)
+    plain = OracleSolution(m, sln, ims)
+    plain.set_packages([chd])
+    assert plain.timestep(1, 1, 1.0, 1).converged == 1
+    assert np.abs(plain.x - exact).max() > 1e-2             # the two-point flux is wrong across the refinement
+    S = OracleSolution(m, sln, ims)
+    S.set_packages([chd])
+    S.set_gnc(*gnc)
+    rep = S.timestep(1, 1, 1.0, 1)
+    assert rep.converged == 1 and rep.outer_iterations > 2   # explicit: the correction lags one outer iteration
+    assert np.abs(S.x - exact).max() < 1e-8
+    # flowja carries the correction: every free cell's flows balance, and the interface flows are the exact Darcy
+    # fluxes K * 0.7 * (face width 1) into the fine cells
+    row = np.repeat(np.arange(m.nodes), np.diff(m.ia))
+    for a, b in zip(gnc[0], gnc[1]):
+        q = S.flowja[(row == b) & (m.ja == a)][0]
+        assert abs(q - (-0.7)) < 1e-7 or abs(q - 0.7) < 1e-7
+    assert abs(rep.pdiffr) < 1e-6
+
+
+def test_gnc_on_an_unconfined_nested_grid_picard_and_newton():
+    """the nested grid unconfined (water table between 10 and 20 in cells from 0 to 25), Picard (gnc_fc) and NEWTON
+    (gnc_fc + gnc_fn, :340-443): both converge, the correction moves the heads by centimetres in both formulations,
+    and the corrected interface flows balance (budget closes).  The two formulations discretise the saturated
+    thickness differently (averaged vs upstream), so they are not compared with each other."""
+    from tests.helpers import nested_grid_case
+    for newton in (0, 1):
+        out = {}
+        for use_gnc in (True, False):
+            m, chd, gnc, _ = nested_grid_case()
+            m.top[:], m.icelltype[:], m.inewton = 25.0, 1, newton
+            ims = T.ImsSettings.make(dvclose=1e-12, rclose=1e-10, iter1=200, ilinmeth=2)
+            sln = T.SlnSettings.make(dvclose=1e-10, mxiter=300)
+            S = OracleSolution(m, sln, ims)
+            S.set_packages([chd])
+            if use_gnc:
+                S.set_gnc(*gnc)
+            rep = S.timestep(1, 1, 1.0, 1)
+            assert rep.converged == 1 and abs(rep.pdiffr) < 1e-6, (newton, use_gnc)
+            out[use_gnc] = S.x.copy()
+        assert 1e-3 < np.abs(out[True] - out[False]).max() < 0.1
