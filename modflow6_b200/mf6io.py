@@ -168,6 +168,7 @@ class GwfInput:
     head_file: str = None
     budget_file: str = None
     save: dict = field(default_factory=dict)          # iper -> list of (rtype, ocsetting tokens)
+    gnc: tuple = None                                 # GNC6: (noden, nodem, nodesj, alphasj), reduced 0-based nodes
     hfb: dict = field(default_factory=dict)           # iper -> (noden, nodem, hydchr), HFB6 barriers (0-based nodes)
     nodeuser: np.ndarray = None       # DIS with IDOMAIN <= 0 cells: reduced -> user node (model.nodes entries)
     nodereduced: np.ndarray = None    # user -> reduced node, -1 where no cell exists
@@ -480,7 +481,7 @@ def read_gwf_model(name, nam_path, base_dir, warnings):
         pn = t[2] if len(t) > 2 else None
         if ft in _PKG_TYPE:
             stress.append((ft, fn, pn))
-        elif ft in ("DIS6", "DISV6", "DISU6", "IC6", "NPF6", "STO6", "OC6", "HFB6"):
+        elif ft in ("DIS6", "DISV6", "DISU6", "IC6", "NPF6", "STO6", "OC6", "HFB6", "GNC6"):
             files[ft] = fn
         else:
             raise Mf6InputError(f"{nam_path}: package {ft} is outside the GPU path (SURVEY.md section 8)")
@@ -652,6 +653,8 @@ def read_gwf_model(name, nam_path, base_dir, warnings):
         gi.packages.append(sp)
     if "HFB6" in files:
         gi.hfb = read_hfb(files["HFB6"], shape, gi.nodereduced, m)
+    if "GNC6" in files:
+        gi.gnc = _reduce_gnc(read_gnc(files["GNC6"], shape, shape, warnings), gi.nodereduced, gi.nodereduced, name)
     if "OC6" in files:
         ob = read_blocks(files["OC6"])
         oopt = _block(ob, "OPTIONS", required=False)
@@ -666,11 +669,57 @@ def read_gwf_model(name, nam_path, base_dir, warnings):
     return gi
 
 
+def read_gnc(path, shape_n, shape_m, warnings):
+    """GNC6 (gwf-gnc.dfn; GhostNode.f90 read_options / read_dimensions / read_data :637-864): GNCDATA rows of
+    cellidn cellidm cellidsj(numalphaj) alphasj(numalphaj); cellidn and the contributing cells belong to the first
+    grid, cellidm to the second (the same grid for the single-model package); an all-zero cellid = no cell.
+    Returns user node numbers (0-based): (noden, nodem, nodesj[ngnc, numj] with -1 = none, alphasj)."""
+    b = read_blocks(path)
+    opt = _options(_block(b, "OPTIONS", required=False))
+    if "EXPLICIT" not in opt:
+        warnings.append(f"{os.path.basename(path)}: the ghost node correction is applied EXPLICITLY on the GPU path "
+                        "(right-hand side; the same converged heads as the implicit variant, more outer iterations)")
+    dim = _options(_block(b, "DIMENSIONS"))
+    ngnc, numj = int(dim["NUMGNC"][0]), int(dim["NUMALPHAJ"][0])
+    wn = len(shape_n) if len(shape_n) > 1 else 1
+    noden, nodem, nodesj, alphasj = [], [], [], []
+    for t in _block(b, "GNCDATA"):
+        a, w = _cellid(t, shape_n)
+        c, w2 = _cellid(t[w:], shape_m)
+        pos = w + w2
+        js = []
+        for _ in range(numj):
+            tok = t[pos:pos + wn]
+            js.append(-1 if all(int(v) == 0 for v in tok) else _cellid(tok, shape_n)[0])
+            pos += wn
+        noden.append(a)
+        nodem.append(c)
+        nodesj.append(js)
+        alphasj.append([float(v) for v in t[pos:pos + numj]])
+    if len(noden) != ngnc:
+        raise Mf6InputError(f"{path}: NUMGNC is {ngnc}, GNCDATA holds {len(noden)} entries")
+    return (np.array(noden, dtype=np.int64), np.array(nodem, dtype=np.int64),
+            np.array(nodesj, dtype=np.int64).reshape(ngnc, numj), np.array(alphasj).reshape(ngnc, numj))
+
+
+def _reduce_gnc(gnc, red_n, red_m, what):
+    """user -> reduced node numbers of a grid with removed cells"""
+    noden, nodem, nodesj, alphasj = gnc
+    if red_n is not None:
+        noden = red_n[noden]
+        nodesj = np.where(nodesj >= 0, red_n[np.maximum(nodesj, 0)], -1)
+    if red_m is not None:
+        nodem = red_m[nodem]
+    if (noden < 0).any() or (nodem < 0).any():
+        raise Mf6InputError(f"{what}: a ghost node correction names a cell that IDOMAIN removes")
+    return noden, nodem, nodesj, alphasj
+
+
 def read_exchange(path, m1, m2, shape1, shape2, exg_id=1):
     b = read_blocks(path)
     opt = _options(_block(b, "OPTIONS", required=False))
     for k in opt:
-        if k in ("GNC6", "MVR6", "XT3D", "CELL_AVERAGING", "VARIABLECV", "DEWATERED"):
+        if k in ("MVR6", "XT3D", "CELL_AVERAGING", "VARIABLECV", "DEWATERED"):
             raise Mf6InputError(f"{path}: exchange option {k} is not supported on the GPU path")
     auxname = [a.upper() for a in opt.get("AUXILIARY", opt.get("AUX", []))]
     n1, n2, ihc, cl1, cl2, hw, aux = [], [], [], [], [], [], []
@@ -685,7 +734,8 @@ def read_exchange(path, m1, m2, shape1, shape2, exg_id=1):
     return dict(m1=m1, m2=m2, nodem1=np.array(n1), nodem2=np.array(n2), ihc=np.array(ihc, dtype=np.int32),
                 cl1=np.array(cl1), cl2=np.array(cl2), hwva=np.array(hw), name=f"GWF-GWF_{exg_id}",
                 save_flows="SAVE_FLOWS" in opt, auxname=auxname,
-                aux=np.array(aux, dtype=np.float64).reshape(len(n1), len(auxname)))
+                aux=np.array(aux, dtype=np.float64).reshape(len(n1), len(auxname)),
+                gnc_file=os.path.join(os.path.dirname(path), opt["GNC6"][-1]) if "GNC6" in opt else None)
 
 
 def read_simulation(sim_dir):
@@ -709,6 +759,10 @@ def read_simulation(sim_dir):
         e = read_exchange(os.path.join(sim_dir, t[1]), i1, i2, models[i1].shape, models[i2].shape,
                           exg_id=len(exchanges) + 1)
         e["usernodem1"], e["usernodem2"] = e["nodem1"], e["nodem2"]
+        e["gnc"] = None
+        if e["gnc_file"]:
+            g = read_gnc(e["gnc_file"], models[i1].shape, models[i2].shape, warnings)
+            e["gnc"] = _reduce_gnc(g, models[i1].nodereduced, models[i2].nodereduced, t[1])
         for key, gi in (("nodem1", models[i1]), ("nodem2", models[i2])):
             if gi.nodereduced is not None:
                 e[key] = gi.nodereduced[e[key]]

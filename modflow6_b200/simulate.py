@@ -120,6 +120,25 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
         if solution_class is None:
             from .solution import GpuNumericalSolution as solution_class
         S = solution_class(model, sim.sln, sim.ims)
+    # ghost node corrections of the models (GNC6 in a name file) and of the exchanges (GNC6 FILEIN in a GWF-GWF
+    # exchange: cellidn and the contributing cells in model 1, cellidm in model 2), in merged node numbers
+    gncs = []
+    for k, gi in enumerate(sim.models):
+        if gi.gnc is not None:
+            n_, m_, j_, a_ = gi.gnc
+            gncs.append((n_ + offs[k], m_ + offs[k], np.where(j_ >= 0, j_ + offs[k], -1), a_))
+    for e in sim.exchanges:
+        if e.get("gnc") is not None:
+            n_, m_, j_, a_ = e["gnc"]
+            gncs.append((n_ + offs[e["m1"]], m_ + offs[e["m2"]], np.where(j_ >= 0, j_ + offs[e["m1"]], -1), a_))
+    if gncs:
+        if rank is not None:
+            from .mf6io import Mf6InputError
+            raise Mf6InputError("GNC6 is not available in the split-model run")
+        numj = max(g[2].shape[1] for g in gncs)
+        pad = lambda a, fill: np.pad(a, ((0, 0), (0, numj - a.shape[1])), constant_values=fill)   # noqa: E731
+        S.set_gnc(np.concatenate([g[0] for g in gncs]), np.concatenate([g[1] for g in gncs]),
+                  np.concatenate([pad(g[2], -1) for g in gncs]), np.concatenate([pad(g[3], 0.0) for g in gncs]))
     writers = []
     for k, gi in enumerate(sim.models):
         mine = rank is None or rank == k

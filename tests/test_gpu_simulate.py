@@ -105,6 +105,18 @@ def test_auxmult_time_series_on_device(gpu, tmp_path):
     assert np.allclose(q, np.array(7 * [1.0, 0.0])[:-1])
 
 
+@pytest.mark.parametrize("ordering", [T.ORDER_NATURAL, T.ORDER_BLOCK_MULTICOLOR])
+def test_lgr_exchange_with_ghost_nodes_on_device(gpu, tmp_path, ordering):
+    """parent + refined child model + GWF-GWF exchange + GNC6 from input files on the device: the linear head
+    field to 1e-8"""
+    from tests.test_mf6io_cpu import write_lgr_gnc
+    hp, hc = write_lgr_gnc(str(tmp_path), True)
+    out = simulate.run(str(tmp_path), ordering=ordering)
+    assert out["reports"][0]["converged"] == 1
+    assert np.abs(out["heads"][0].reshape(4, 3) - hp).max() < 1e-8
+    assert np.abs(out["heads"][1].reshape(8, 4) - hc).max() < 1e-8
+
+
 def test_rch03_on_device(gpu, tmp_path):
     """autotest/test_gwf_rch03.py:130-146 on the device: the literal RCH budget records of array-based recharge with
     IRCH over removed / pass-through / constant-head cells (reduced numbering, bound numbers kept)"""

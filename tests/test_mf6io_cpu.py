@@ -701,3 +701,47 @@ def test_time_series_interpolation_methods():
     for s in (sw, li, le):
         with pytest.raises(TimeSeriesError):
             s.value(2.0, 3.5)
+
+
+def write_lgr_gnc(d, gnc=True):
+    """local grid refinement the way MODFLOW 6 decks do it: a parent DIS model (4 x 3 cells of 2 x 2) and a child DIS
+    model (8 x 4 cells of 1 x 1) joined by a GWF-GWF exchange with a GNC6 file (one contributing parent cell per
+    connection, alpha 0.25); constant heads on h = 10 + 0.7 x + 0.3 y along the outer boundary.
+    Returns the exact heads of both models."""
+    hp = np.array([[10 + 0.7 * (2 * j - 1) + 0.3 * (9 - 2 * i) for j in range(1, 4)] for i in range(1, 5)])
+    hc = np.array([[10 + 0.7 * (5.5 + j) + 0.3 * (8.5 - i) for j in range(1, 5)] for i in range(1, 9)])
+    chd_p = [((1, i, j), float(hp[i - 1, j - 1])) for i in range(1, 5) for j in range(1, 4) if j == 1 or i in (1, 4)]
+    chd_c = [((1, i, j), float(hc[i - 1, j - 1])) for i in range(1, 9) for j in range(1, 5) if j == 4 or i in (1, 8)]
+    mf6_inputs.write_gwf(d, "parent", (1, 4, 3), 2.0, 2.0, 1.0, [0.0], 1.0, chd={1: chd_p}, strt=10.0)
+    mf6_inputs.write_gwf(d, "child", (1, 8, 4), 1.0, 1.0, 1.0, [0.0], 1.0, chd={1: chd_c}, strt=10.0)
+    rows, gncrows = [], []
+    for i in range(1, 5):
+        for ic, ij in ((2 * i - 1, i - 1), (2 * i, i + 1)):      # upper / lower child row, parent row on that side
+            rows.append(((1, i, 3), (1, ic, 1), 1, 1.0, 0.5, 1.0))
+            if 1 <= ij <= 4:
+                gncrows.append(f"  1 {i} 3  1 {ic} 1  1 {ij} 3  0.25\n")
+    ims = ("BEGIN nonlinear\n  OUTER_DVCLOSE 1e-10\n  OUTER_MAXIMUM 200\nEND nonlinear\n\n"
+           "BEGIN linear\n  INNER_MAXIMUM 200\n  INNER_DVCLOSE 1e-12\n  INNER_RCLOSE 1e-12\n  LINEAR_ACCELERATION CG\nEND linear\n")
+    mf6_inputs.write_sim(d, ["parent", "child"], [(1.0, 1, 1.0)], ims, exchanges=[("lgr", "parent", "child", rows)])
+    if gnc:
+        p = f"{d}/lgr.gwfgwf"
+        text = open(p).read().replace("  SAVE_FLOWS\n", "  SAVE_FLOWS\n  GNC6 FILEIN lgr.gnc\n")
+        open(p, "w").write(text)
+        with open(f"{d}/lgr.gnc", "w") as f:
+            f.write("BEGIN options\n  EXPLICIT\nEND options\n\nBEGIN dimensions\n"
+                    f"  NUMGNC {len(gncrows)}\n  NUMALPHAJ 1\nEND dimensions\n\nBEGIN gncdata\n" + "".join(gncrows)
+                    + "END gncdata\n")
+    return hp, hc
+
+
+def test_lgr_exchange_with_ghost_nodes_from_decks(tmp_path):
+    """parent + refined child model + GWF-GWF exchange + GNC6 from input FILES: the linear head field is reproduced
+    exactly with the ghost nodes and is centimetres off without them"""
+    for tag, gnc in (("gnc", True), ("plain", False)):
+        d = tmp_path / tag
+        d.mkdir()
+        hp, hc = write_lgr_gnc(str(d), gnc)
+        out = simulate.run(str(d), ordering=T.ORDER_NATURAL, solution_class=oracle_class())
+        assert out["reports"][0]["converged"] == 1
+        err = max(np.abs(out["heads"][0].reshape(4, 3) - hp).max(), np.abs(out["heads"][1].reshape(8, 4) - hc).max())
+        assert (err < 1e-8) if gnc else (err > 1e-2)
