@@ -19,7 +19,7 @@ module GpuSolutionBindingsModule
   public :: mf6gpu_sln_settings, mf6gpu_gwf_model, mf6gpu_bnd_package, mf6gpu_step_report
   public :: MF6GPU_MAX_BUDGET_TERMS
   public :: mf6gpu_solution_create, mf6gpu_solution_destroy, mf6gpu_solution_set_packages
-  public :: mf6gpu_solution_set_hfb
+  public :: mf6gpu_solution_set_hfb, mf6gpu_solution_set_gnc
   public :: mf6gpu_solution_timestep, mf6gpu_solution_get_x, mf6gpu_solution_set_x
   public :: mf6gpu_solution_get_flowja, mf6gpu_solution_get_simvals, mf6gpu_solution_get_storage
 
@@ -114,6 +114,16 @@ module GpuSolutionBindingsModule
       integer(c_int32_t), value :: nhfb
       integer(c_int32_t), intent(in) :: noden(*), nodem(*)
       real(c_double), intent(in) :: hydchr(*)
+      integer(c_int32_t), value :: index_base
+      integer(c_int) :: rc
+    end function
+    function mf6gpu_solution_set_gnc(handle, ngnc, numj, noden, nodem, nodesj, alphasj, index_base) &
+      bind(C, name="mf6gpu_solution_set_gnc") result(rc)
+      import :: c_int, c_int32_t, c_double, c_ptr
+      type(c_ptr), value :: handle
+      integer(c_int32_t), value :: ngnc, numj
+      integer(c_int32_t), intent(in) :: noden(*), nodem(*), nodesj(*)
+      real(c_double), intent(in) :: alphasj(*)
       integer(c_int32_t), value :: index_base
       integer(c_int) :: rc
     end function
@@ -281,6 +291,15 @@ contains
     l%gpu_ordering = 2 ! MF6GPU_ORDER_BLOCK_MULTICOLOR
     l%reserved = 0
     call mf6gpu_check(mf6gpu_solution_create(m, s, c_loc(l), this%handle))
+    ! single-model ghost node correction (GhostNodeType: nodem1, nodem2, nodesj(numjs, nexg), alphasj(numjs, nexg),
+    ! GhostNode.f90:25-50): Fortran's (numjs, nexg) storage IS the row-major [nexg][numjs] layout the C side reads;
+    ! a nodesj of 0 = no cell, which index_base 1 maps to "none".  Applied explicitly on the device.
+    if (this%gwf%ingnc > 0) then
+      call mf6gpu_check(mf6gpu_solution_set_gnc(this%handle, int(this%gwf%gnc%nexg, c_int32_t), &
+                                                int(this%gwf%gnc%numjs, c_int32_t), this%gwf%gnc%nodem1, &
+                                                this%gwf%gnc%nodem2, this%gwf%gnc%nodesj, this%gwf%gnc%alphasj, &
+                                                1_c_int32_t))
+    end if
   end subroutine gpu_sln_ar
 
   !> @brief stress period data of every boundary package (after the packages' bnd_rp)
