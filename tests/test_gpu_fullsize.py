@@ -72,11 +72,10 @@ def test_c3_full_size_first_step_against_oracle_fixture(gpu, capsys):
 
     At the closure SURVEY.md names (INNER_DVCLOSE 1e-6 / INNER_RCLOSE 1e-5, OUTER_DVCLOSE 1e-4) the damped Newton
     iteration stops well short of the converged heads -- the oracle's own budget is 0.028 % off and its two
-    orderings are 2e-4 apart already on a 5 x 500 x 500 grid -- so head differences here measure closure slack
-    (measured 1.5e-3), not parity: see test_c3_reduced_size_tight_closure for the parity bar.  What IS asserted at
-    full size: convergence, the iteration counts near the oracle's, heads within the characterised slack, and the
-    size-independent property that the device heads satisfy the REFERENCE's discrete equations (every cell's flow
-    imbalance, formulated by the oracle at the device heads) as well as the oracle's own heads do."""
+    orderings are 2e-4 apart already on a 5 x 500 x 500 grid (profiles/r02_c3_closure_study.json) -- so head
+    differences here measure closure slack (measured 1.5e-3), not parity: the parity bar is held by
+    test_c3_tight_closure_against_oracle_fixture.  Asserted at this closure: convergence, the outer iteration count
+    near the oracle's, heads within the characterised slack, a budget as good as the oracle's."""
     import json
     from oracle import golden
     if golden.load("c3_full_block") is None:
@@ -84,29 +83,24 @@ def test_c3_full_size_first_step_against_oracle_fixture(gpu, capsys):
     cfg = configs.c3_newton()
     reps, x = _run(cfg, max_steps=1)
     c = golden.compare_heads("c3_full_block", x, cfg.sln.dvclose)
-    res = golden.nonlinear_residual(cfg, x)
-    ores = golden.load("c3_full_block")["meta"].get("residual")
     with capsys.disabled():
         print("\nC3_FULL " + json.dumps({"device": {k: reps[0][k] for k in ("converged", "outer_iterations",
                                                                             "inner_iterations", "pdiffr")},
-                                         "compare": c, "residual_device_heads": res, "residual_oracle_heads": ores}))
+                                         "compare": c}))
     assert reps[0]["converged"] == 1
     assert c["max_abs_dhead"] <= 50 * cfg.sln.dvclose, c
     assert abs(reps[0]["outer_iterations"] - c["oracle"]["outer_iterations"]) <= 2
     assert abs(reps[0]["pdiffr"]) <= 0.1
-    # flow imbalance per cell: INNER_RCLOSE is the solver's own per-cell criterion
-    assert res["max_abs"] <= 5 * cfg.ims.rclose, res
-    if ores:
-        assert res["l2"] <= 3 * ores["l2"], (res, ores)
 
 
 @pytest.mark.parametrize("size", [(5, 500, 500), (5, 1000, 1000), (5, 2000, 2000)])
-def test_c3_tight_closure_against_oracle_fixture(gpu, size):
+def test_c3_tight_closure_against_oracle_fixture(gpu, size, capsys):
     """config 3 (Newton, BiCGSTAB + ILU0, DBD, pseudo-transient continuation), steady first step, at 1.25e6, 5e6 and
     (when the 6-hour oracle fixture is present) the full 2e7 cells, with the inner closure one decade
     tighter (configs.tighten_inner_closure level 1: 1e-7 / 1e-7; the oracle's own two orderings then agree to 3.6e-7,
     profiles/r02_c3_closure_study.json).  North-star bar: max |dhead| <= 0.1 x OUTER_DVCLOSE against the oracle on the
     same permuted system AND against the reference's own natural-order solve, budget within 1e-3."""
+    import json
     from oracle import golden
     tag = "c3_full_block_tight" if size == (5, 2000, 2000) else "c3_%dx%dx%d_block_tight" % size
     if golden.load(tag) is None:
@@ -122,3 +116,14 @@ def test_c3_tight_closure_against_oracle_fixture(gpu, size):
     if n is not None:
         assert n["max_abs_dhead"] <= 0.1 * cfg.sln.dvclose, n
         assert abs(reps[0]["pdiffr"] - n["oracle"]["pdiffr"]) <= 1e-3
+    # size-independent property: the device heads satisfy the REFERENCE's discrete equations (the oracle formulates
+    # the system at these heads; every cell's flow imbalance) as well as the oracle's own heads do
+    ores = golden.load(tag)["meta"].get("residual")
+    if ores:
+        res = golden.nonlinear_residual(cfg, x)
+        with capsys.disabled():
+            print("\nC3_TIGHT " + json.dumps({"size": size, "device": {k: reps[0][k] for k in (
+                "outer_iterations", "inner_iterations", "pdiffr")}, "compare": c, "natural": n,
+                "residual_device_heads": res, "residual_oracle_heads": ores}))
+        assert res["max_abs"] <= max(3 * ores["max_abs"], cfg.ims.rclose), (res, ores)
+        assert res["l2"] <= 3 * ores["l2"] + 1e-12, (res, ores)
