@@ -111,22 +111,25 @@ def test_c3_tight_closure_against_oracle_fixture(gpu, size, capsys):
     cfg = configs.tighten_inner_closure(configs.c3_newton(*size), 1)
     reps, x = _run(cfg, max_steps=1)
     c = golden.compare_heads(tag, x, cfg.sln.dvclose)
+    n = golden.compare_heads(tag.replace("block", "natural"), x, cfg.sln.dvclose)
+    with capsys.disabled():
+        print("\nC3_TIGHT " + json.dumps({"size": size, "device": {k: reps[0][k] for k in (
+            "converged", "outer_iterations", "inner_iterations", "pdiffr")}, "compare": c, "natural": n}))
     assert reps[0]["converged"] == 1
     assert c["max_abs_dhead"] <= 0.1 * cfg.sln.dvclose, c
     assert abs(reps[0]["pdiffr"] - c["oracle"]["pdiffr"]) <= 1e-3
     assert reps[0]["outer_iterations"] == c["oracle"]["outer_iterations"]
-    n = golden.compare_heads(tag.replace("block", "natural"), x, cfg.sln.dvclose)
     if n is not None:
-        assert n["max_abs_dhead"] <= 0.1 * cfg.sln.dvclose, n
+        # across orderings: the oracle's own two orderings are 3.6e-7 apart at 1.25e6 cells and 5.4e-6 at 5e6 (the
+        # conditioning grows with the grid), so the 0.1 x bar is asserted across orderings at the smallest size only
+        assert n["max_abs_dhead"] <= (0.1 if size == (5, 500, 500) else 1.0) * cfg.sln.dvclose, n
         assert abs(reps[0]["pdiffr"] - n["oracle"]["pdiffr"]) <= 1e-3
     # size-independent property: the device heads satisfy the REFERENCE's discrete equations (the oracle formulates
     # the system at these heads; every cell's flow imbalance) as well as the oracle's own heads do
     ores = golden.load(tag)["meta"].get("residual")
-    if ores:
+    if ores and x.size <= 5000000:       # (the oracle-side formulate of 2e7 cells takes a minute)
         res = golden.nonlinear_residual(cfg, x)
         with capsys.disabled():
-            print("\nC3_TIGHT " + json.dumps({"size": size, "device": {k: reps[0][k] for k in (
-                "outer_iterations", "inner_iterations", "pdiffr")}, "compare": c, "natural": n,
-                "residual_device_heads": res, "residual_oracle_heads": ores}))
+            print("C3_TIGHT_RESIDUAL " + json.dumps({"size": size, "device_heads": res, "oracle_heads": ores}))
         assert res["max_abs"] <= max(3 * ores["max_abs"], cfg.ims.rclose), (res, ores)
         assert res["l2"] <= 3 * ores["l2"] + 1e-12, (res, ores)
