@@ -614,3 +614,41 @@ def test_gnc_on_an_unconfined_nested_grid_picard_and_newton():
             assert rep.converged == 1 and abs(rep.pdiffr) < 1e-6, (newton, use_gnc)
             out[use_gnc] = S.x.copy()
         assert 1e-3 < np.abs(out[True] - out[False]).max() < 0.1
+
+
+@pytest.mark.parametrize("newton", [False, True])
+def test_sto03_storage_is_invariant_under_an_elevation_offset(newton):
+    """autotest/test_gwf_sto03.py:13-255 -- ONE convertible cell (top 0, bottom -100, ss 1e-5, sy 0) filled and
+    emptied by a well in alternating stress periods (6 periods x 50 steps x 1.1), Picard (CG, SIMPLE under-relaxation
+    0.95) and NEWTON UNDER_RELAXATION (BiCGSTAB).  The reference's own criteria: the heads of the same model lifted by
+    15999.1 are the same once the offset is removed (atol 1e-6), the head reached at the end of every filling period
+    is the same (t = 1, 3, 5), and the STO-SS rates of the two models agree -- the convertible-cell specific-storage
+    formulation (SsTerms, gwf-sto.f90 / GwfStorageUtils.f90) must not depend on the datum."""
+    from modflow6_b200 import configs
+    from modflow6_b200.grid import tdis_steps
+    ss, off = 1e-5, 15999.1
+    absrate = 1.1 * ss * 100.0 * 90.0
+    out = {}
+    for tag, offset in (("base", 0.0), ("offset", off)):
+        m = build_dis_model(1, 1, 1, 1.0, 1.0, 0.0 + offset, [-100.0 + offset], 1.0, icelltype=1,
+                            strt=-100.0 + 1e-7 + offset, ss=ss, sy=0.0, iconvert=1, inewton=1 if newton else 0,
+                            inewtonur=1 if newton else 0)
+        ims = T.ImsSettings.make(dvclose=1e-9, rclose=1e-6, iter1=300, ilinmeth=2 if newton else 1, relax=1.0)
+        sln = T.SlnSettings.make(dvclose=1e-9, mxiter=500, nonmeth=1, gamma=1.0 if newton else 0.95)
+        S = OracleSolution(m, sln, ims)
+        heads, rates, ends = [], [], []
+        for kper in range(1, 7):
+            S.set_packages([Package(T.PKG_WEL, [0], [absrate if kper % 2 == 1 else -absrate])])
+            for kstp, delt in enumerate(tdis_steps(1.0, 50, 1.1), start=1):
+                rep = S.timestep(kper, kstp, delt, 0)
+                assert rep.converged == 1, (tag, kper, kstp)
+                heads.append(S.x[0])
+                rates.append(S.storage_rates[0][0])
+            ends.append(S.x[0])
+        out[tag] = (np.array(heads), np.array(rates), np.array(ends))
+    hb, rb, eb = out["base"]
+    ho, ro, eo = out["offset"]
+    assert np.allclose(hb, ho - off, atol=1e-6)
+    assert np.allclose(rb, ro)
+    assert np.allclose(eb[[0, 2, 4]], eb[0]) and np.allclose(eo[[0, 2, 4]], eo[0])
+    assert eb[0] > -100.0 + 1.0                    # the cell did fill (the test is not vacuous)
