@@ -29,14 +29,14 @@ def _arr(name, a, layered=False):
         "      " + " ".join(repr(float(v)) for v in row) for row in a.reshape(-1, a.shape[-1])) + "\n"
 
 
-def _disv_text(shape, delr, delc, top, botm):
+def _disv_text(shape, delr, delc, top, botm, xoff=0.0, yoff=0.0):
     """the rectangular grid as a DISV package: vertices row by row from the top-left corner, cells clockwise
     from their top-left vertex (what flopy's structured-to-vertex conversion writes)"""
     nlay, nrow, ncol = shape
     delr = np.broadcast_to(np.asarray(delr, dtype=float), (ncol,))
     delc = np.broadcast_to(np.asarray(delc, dtype=float), (nrow,))
-    xe = np.concatenate([[0.0], np.cumsum(delr)])
-    ye = delc.sum() - np.concatenate([[0.0], np.cumsum(delc)])
+    xe = xoff + np.concatenate([[0.0], np.cumsum(delr)])
+    ye = yoff + delc.sum() - np.concatenate([[0.0], np.cumsum(delc)])
     s = (f"BEGIN options\nEND options\n\nBEGIN dimensions\n  NLAY {nlay}\n  NCPL {nrow * ncol}\n"
          f"  NVERT {(nrow + 1) * (ncol + 1)}\nEND dimensions\n\nBEGIN griddata\n" + _arr("top", top)
          + _arr("botm", botm, layered=np.ndim(botm) > 0) + "END griddata\n\nBEGIN vertices\n")

@@ -745,3 +745,39 @@ def test_lgr_exchange_with_ghost_nodes_from_decks(tmp_path):
         assert out["reports"][0]["converged"] == 1
         err = max(np.abs(out["heads"][0].reshape(4, 3) - hp).max(), np.abs(out["heads"][1].reshape(8, 4) - hc).max())
         assert (err < 1e-8) if gnc else (err > 1e-2)
+
+
+@pytest.mark.parametrize("grid", ["disv", "disu"])
+def test_disv_disu_connectivity_with_an_inactive_cell(tmp_path, grid):
+    """autotest/test_gwf_disv.py:56-72 and test_gwf_disu.py:56-72, case b: a 3 x 3 x 3 grid of 10 x 10 x 10 cells
+    (DISV with vertex coordinates offset by 1e8) whose cell 2 has IDOMAIN 0 -- the reference asserts the connectivity
+    of its binary grid file in USER numbering: ia[0:4] = 1 4 4 7 (the removed cell's row is empty), ja[:6] =
+    1 4 10 3 6 12, ia[-1] = 127, 28 / 126 entries.  Rebuilt here from the reduced model and nodeuser."""
+    shape = (3, 3, 3)
+    d = str(tmp_path)
+    mf6_inputs.write_gwf(d, "m", shape, 10.0, 10.0, 0.0, [-10.0, -20.0, -30.0], 1.0, strt=0.0,
+                         chd={1: [((1, 1, 1), 1.0), ((1, 3, 3), 0.0)]}, disv=(grid == "disv"), disu=(grid == "disu"))
+    idom = np.ones(shape)
+    idom[0, 0, 1] = 0
+    p = tmp_path / "m.dis"
+    if grid == "disv":
+        p.write_text("# test\n" + mf6_inputs._disv_text(shape, 10.0, 10.0, 0.0, [-10.0, -20.0, -30.0], 1.0e8, 1.0e8))
+        arr = mf6_inputs._arr("idomain", idom, layered=True)
+    else:
+        arr = mf6_inputs._arr("idomain", idom.reshape(1, -1))
+    p.write_text(p.read_text().replace("END griddata\n", arr + "END griddata\n"))
+    mf6_inputs.write_sim(d, ["m"], [(1.0, 1, 1.0)], "BEGIN options\n  PRINT_OPTION SUMMARY\nEND options\n")
+    gi = mf6io.read_simulation(d).models[0]
+    m, nodeuser = gi.model, gi.nodeuser
+    assert m.nodes == 26 and np.allclose(m.area, 100.0, rtol=1e-12)     # the 1e8 offsets do not hurt the areas
+    ia = np.zeros(28, dtype=int)
+    ja = []
+    for r in range(m.nodes):
+        row = nodeuser[m.ja[m.ia[r]:m.ia[r + 1]]] + 1
+        ja += [int(row[0])] + sorted(int(v) for v in row[1:])
+        ia[nodeuser[r] + 1] = m.ia[r + 1] - m.ia[r]
+    ia = 1 + np.concatenate([[0], np.cumsum(ia[1:])])
+    assert np.array_equal(ia[0:4], [1, 4, 4, 7]) and ia[-1] == 127 and ia.shape[0] == 28
+    assert ja[:6] == [1, 4, 10, 3, 6, 12] and len(ja) == 126
+    out = simulate.run(d, ordering=T.ORDER_NATURAL, solution_class=oracle_class(), write_output=False)
+    assert out["reports"][0]["converged"] == 1
