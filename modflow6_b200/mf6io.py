@@ -168,6 +168,7 @@ class GwfInput:
     head_file: str = None
     budget_file: str = None
     save: dict = field(default_factory=dict)          # iper -> list of (rtype, ocsetting tokens)
+    grid: dict = None                                 # what the binary grid file records (output.write_grb)
     gnc: tuple = None                                 # GNC6: (noden, nodem, nodesj, alphasj), reduced 0-based nodes
     hfb: dict = field(default_factory=dict)           # iper -> (noden, nodem, hydchr), HFB6 barriers (0-based nodes)
     nodeuser: np.ndarray = None       # DIS with IDOMAIN <= 0 cells: reduced -> user node (model.nodes entries)
@@ -533,6 +534,24 @@ def read_gwf_model(name, nam_path, base_dir, warnings):
         if any(c is None for c in cells):
             raise Mf6InputError(f"{files['DISV6']}: CELL2D does not list every cell")
         cell2d = cell2d_from_vertices(verts, cells)
+    # what the binary grid file (.grb) records about the grid, in USER numbering
+    dopt = _options(_block(d, "OPTIONS", required=False))
+    grid = dict(xorigin=float(dopt["XORIGIN"][0]) if "XORIGIN" in dopt else 0.0,
+                yorigin=float(dopt["YORIGIN"][0]) if "YORIGIN" in dopt else 0.0,
+                angrot=float(dopt["ANGROT"][0]) if "ANGROT" in dopt else 0.0,
+                nogrb="NOGRB" in dopt,
+                file=os.path.join(base_dir, dopt["GRB6"][-1]) if "GRB6" in dopt else None)
+    if disu is not None:
+        grid.update(kind="DISU", nodes=nodes, top=g["TOP"].reshape(-1), bot=g["BOT"].reshape(-1),
+                    default=files["DISU6"] + ".grb")
+    elif cell2d is None:
+        grid.update(kind="DIS", nlay=nlay, nrow=nrow, ncol=ncol, delr=g["DELR"].reshape(-1), delc=g["DELC"].reshape(-1),
+                    top=g["TOP"].reshape(-1), botm=g["BOTM"].reshape(-1), default=files["DIS6"] + ".grb")
+    else:
+        grid.update(kind="DISV", nlay=nlay, ncpl=ncpl, vertices=verts, cells=cells, top=g["TOP"].reshape(-1),
+                    botm=g["BOTM"].reshape(-1), default=files["DISV6"] + ".grb")
+    grid["idomain"] = (g["IDOMAIN"].reshape(-1).astype(np.int32) if "IDOMAIN" in g
+                       else np.ones(int(np.prod(shape)), dtype=np.int32))
     # READARRAY layout (LAYERED = one control record per layer)
     ashape = shape if len(shape) == 3 else ((nlay, 1, shape[1]) if len(shape) == 2 else shape)
     # IC / NPF / STO
@@ -629,7 +648,8 @@ def read_gwf_model(name, nam_path, base_dir, warnings):
         if (g["IDOMAIN"] == 0).any():
             # reduced node numbering, like the reference: the removed cells and their connections do not exist
             m = reduce_model(m, g["IDOMAIN"].reshape(-1) > 0)
-    gi = GwfInput(name=name, model=m, shape=shape, sto_transient=sto_tr, nodeuser=m.meta.get("nodeuser"),
+    grid["icelltype"] = np_["ICELLTYPE"].reshape(-1).astype(np.int32)      # as read, user numbering (dis_ar)
+    gi = GwfInput(name=name, model=m, shape=shape, grid=grid, sto_transient=sto_tr, nodeuser=m.meta.get("nodeuser"),
                   nodereduced=m.meta.get("nodereduced"))
     count = {}
     for ft, fn, pn in stress:

@@ -166,6 +166,101 @@ class BudgetFileWriter:
         self.f.close()
 
 
+def _grb_line(text, n):
+    return (text[:n - 1].ljust(n - 1) + "\n").encode("ascii")
+
+
+def write_grb(path, grid, model, nodeuser=None):
+    """Binary grid file, what post-processors need to interpret FLOW-JA-FACE (`write_grb` of Dis.f90:547-659,
+    Disv.f90:709-850, Disu.f90:908-1030): four 50-byte header lines (GRID <type>, VERSION 1, NTXT, LENTXT 100), one
+    100-byte definition line per variable, then the data in that order.  IA / JA are the connectivity in USER
+    numbering (`iajausr`, Connections.f90:1112-1160: a removed cell has an empty row), 1-based, every row = the cell
+    itself followed by its neighbours.  `grid` is GwfInput.grid, `model` the (reduced) GwfModel."""
+    kind = grid["kind"]
+    nodesuser = int(grid["idomain"].size)
+    nu = np.arange(nodesuser) if nodeuser is None else np.asarray(nodeuser)
+    cnt = np.zeros(nodesuser, dtype=np.int64)
+    cnt[nu] = np.diff(model.ia)
+    iausr = (1 + np.concatenate([[0], np.cumsum(cnt)])).astype("<i4")
+    jausr = (nu[model.ja] + 1).astype("<i4")
+    nja = int(model.nja)
+    f8 = lambda a: np.ascontiguousarray(a, dtype="<f8").tobytes()      # noqa: E731
+    i4 = lambda a: np.ascontiguousarray(a, dtype="<i4").tobytes()      # noqa: E731
+    g25 = lambda v: f"{v:24.15E}"                                      # noqa: E731
+    defs, data = [], []
+
+    def scalar_i(name, v):
+        defs.append(f"{name} INTEGER NDIM 0 # {int(v)}")
+        data.append(struct.pack("<i", int(v)))
+
+    def scalar_d(name, v):
+        defs.append(f"{name} DOUBLE NDIM 0 # {g25(float(v))}")
+        data.append(struct.pack("<d", float(v)))
+
+    def arr_d(name, a, dims=None):
+        a = np.asarray(a, dtype=np.float64)
+        defs.append(f"{name} DOUBLE NDIM {dims or ('1 %d' % a.size)}")
+        data.append(f8(a))
+
+    def arr_i(name, a):
+        a = np.asarray(a)
+        defs.append(f"{name} INTEGER NDIM 1 {a.size}")
+        data.append(i4(a))
+
+    if kind == "DIS":
+        scalar_i("NCELLS", nodesuser); scalar_i("NLAY", grid["nlay"]); scalar_i("NROW", grid["nrow"])
+        scalar_i("NCOL", grid["ncol"]); scalar_i("NJA", nja)
+        scalar_d("XORIGIN", grid["xorigin"]); scalar_d("YORIGIN", grid["yorigin"]); scalar_d("ANGROT", grid["angrot"])
+        arr_d("DELR", grid["delr"]); arr_d("DELC", grid["delc"]); arr_d("TOP", grid["top"]); arr_d("BOTM", grid["botm"])
+    elif kind == "DISV":
+        verts = np.asarray(grid["vertices"], dtype=np.float64)
+        iav, jav = [1], []
+        for _, _, iv in grid["cells"]:
+            iv = list(iv)
+            if iv[0] != iv[-1]:
+                iv.append(iv[0])             # the polygon is stored closed (Disv.f90 source_cell2d)
+            jav += [v + 1 for v in iv]
+            iav.append(len(jav) + 1)
+        scalar_i("NCELLS", nodesuser); scalar_i("NLAY", grid["nlay"]); scalar_i("NCPL", grid["ncpl"])
+        scalar_i("NVERT", verts.shape[0]); scalar_i("NJAVERT", len(jav)); scalar_i("NJA", nja)
+        scalar_d("XORIGIN", grid["xorigin"]); scalar_d("YORIGIN", grid["yorigin"]); scalar_d("ANGROT", grid["angrot"])
+        arr_d("TOP", grid["top"]); arr_d("BOTM", grid["botm"])
+        arr_d("VERTICES", verts.reshape(-1), dims=f"2 2 {verts.shape[0]}")
+        arr_d("CELLX", [c[0] for c in grid["cells"]]); arr_d("CELLY", [c[1] for c in grid["cells"]])
+        arr_i("IAVERT", iav); arr_i("JAVERT", jav)
+    elif kind == "DISU":
+        scalar_i("NODES", nodesuser); scalar_i("NJA", nja)
+        scalar_d("XORIGIN", grid["xorigin"]); scalar_d("YORIGIN", grid["yorigin"]); scalar_d("ANGROT", grid["angrot"])
+        arr_d("TOP", grid["top"]); arr_d("BOT", grid["bot"])
+    else:
+        raise ValueError(f"write_grb: unknown grid kind {kind}")
+    arr_i("IA", iausr); arr_i("JA", jausr); arr_i("IDOMAIN", grid["idomain"]); arr_i("ICELLTYPE", grid["icelltype"])
+    with open(path, "wb") as f:
+        for t in (f"GRID {kind}", "VERSION 1", f"NTXT {len(defs)}", "LENTXT 100"):
+            f.write(_grb_line(t, 50))
+        for t in defs:
+            f.write(_grb_line(t, 100))
+        for b in data:
+            f.write(b)
+
+
+def read_grb(path):
+    """the self-describing binary grid file -> dict(GRID=..., NAME=value or array)"""
+    out = {}
+    with open(path, "rb") as f:
+        hdr = [f.read(50).decode("ascii").strip() for _ in range(4)]
+        out["GRID"] = hdr[0].split()[1]
+        ntxt, lentxt = int(hdr[2].split()[1]), int(hdr[3].split()[1])
+        defs = [f.read(lentxt).decode("ascii").split("#")[0].split() for _ in range(ntxt)]
+        for d in defs:
+            name, typ, ndim = d[0], d[1], int(d[3])
+            n = int(np.prod([int(v) for v in d[4:4 + ndim]])) if ndim else 1
+            dt = "<i4" if typ == "INTEGER" else "<f8"
+            a = np.frombuffer(f.read(n * int(dt[-1])), dtype=dt)
+            out[name] = a[0].item() if ndim == 0 else a.copy()
+    return out
+
+
 def read_head_file(path):
     """list of dicts (kstp, kper, pertim, totim, text, ncol, nrow, ilay, data[nrow, ncol])"""
     out = []

@@ -17,7 +17,7 @@ import numpy as np
 from . import ctypes_types as T
 from .grid import merge_models, tdis_steps
 from .mf6io import read_simulation
-from .output import BudgetFileWriter, HeadFileWriter
+from .output import BudgetFileWriter, HeadFileWriter, write_grb
 
 DHNOFLO = 1.0e30   # Constants.f90: head written for cells outside the active domain
 
@@ -142,6 +142,8 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
     writers = []
     for k, gi in enumerate(sim.models):
         mine = rank is None or rank == k
+        if write_output and mine and gi.grid is not None and not gi.grid["nogrb"]:
+            write_grb(gi.grid["file"] or gi.grid["default"], gi.grid, gi.model, gi.nodeuser)   # dis_ar
         hw = HeadFileWriter(gi.head_file, gi.shape) if (write_output and gi.head_file and mine) else None
         bw = None
         if write_output and gi.budget_file and mine:

@@ -779,5 +779,17 @@ def test_disv_disu_connectivity_with_an_inactive_cell(tmp_path, grid):
     ia = 1 + np.concatenate([[0], np.cumsum(ia[1:])])
     assert np.array_equal(ia[0:4], [1, 4, 4, 7]) and ia[-1] == 127 and ia.shape[0] == 28
     assert ja[:6] == [1, 4, 10, 3, 6, 12] and len(ja) == 126
-    out = simulate.run(d, ordering=T.ORDER_NATURAL, solution_class=oracle_class(), write_output=False)
+    out = simulate.run(d, ordering=T.ORDER_NATURAL, solution_class=oracle_class())
     assert out["reports"][0]["converged"] == 1
+    # the binary grid file the run writes (write_grb): exactly what the reference test reads back
+    from modflow6_b200.output import read_grb
+    grb = read_grb(tmp_path / "m.dis.grb")
+    assert grb["GRID"] == grid.upper() and grb["NJA"] == 126
+    assert np.array_equal(grb["IA"][0:4], [1, 4, 4, 7]) and grb["IA"][-1] == 127 and grb["IA"].shape[0] == 28
+    assert np.array_equal(grb["JA"][:6], [1, 4, 10, 3, 6, 12]) and grb["JA"].shape[0] == 126
+    assert np.array_equal(grb["IDOMAIN"], [1, 0] + 25 * [1]) and grb["ICELLTYPE"].shape[0] == 27
+    if grid == "disv":
+        assert grb["NCPL"] == 9 and grb["NVERT"] == 16 and grb["IAVERT"][-1] == grb["NJAVERT"] + 1 == 46
+        assert grb["VERTICES"].shape[0] == 32 and grb["VERTICES"].min() >= 1.0e8
+    raw = open(tmp_path / "m.dis.grb", "rb").read()
+    assert raw[:50] == (f"GRID {grid.upper()}".ljust(49) + "\n").encode() and raw[50:100].startswith(b"VERSION 1")

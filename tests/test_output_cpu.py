@@ -119,3 +119,34 @@ def test_oracle_run_writes_consistent_files(tmp_path):
     assert texts == ["STO-SS", "STO-SY", "FLOW-JA-FACE", "CHD", "WEL"]
     assert np.allclose(hds[-1]["data"].ravel(), O.x)
     check_water_balance(cfg, hds, cbc)
+
+
+def test_binary_grid_file_of_a_dis_grid(tmp_path):
+    """write_grb (Dis.f90:547-659): header lines, the sixteen variables in the reference's order, DELR / DELC / TOP /
+    BOTM and the user-numbered connectivity of a DIS grid with a removed and a pass-through cell"""
+    import numpy as np
+    from modflow6_b200 import mf6io
+    from modflow6_b200.output import read_grb, write_grb
+    from tests import mf6_inputs
+    idom = np.ones((2, 3, 4), dtype=int)
+    idom[0, 1, 1] = 0
+    idom[0, 2, 2] = -1
+    mf6_inputs.write_gwf(str(tmp_path), "m", (2, 3, 4), [10.0, 20.0, 30.0, 40.0], [5.0, 6.0, 7.0], 3.0, [-1.0, -4.0], 1.0,
+                         chd={1: [((1, 1, 1), 1.0)]}, strt=0.0, idomain=idom)
+    mf6_inputs.write_sim(str(tmp_path), ["m"], [(1.0, 1, 1.0)], "BEGIN options\nEND options\n")
+    gi = mf6io.read_simulation(str(tmp_path)).models[0]
+    write_grb(tmp_path / "g.grb", gi.grid, gi.model, gi.nodeuser)
+    g = read_grb(tmp_path / "g.grb")
+    assert list(g)[:1] == ["GRID"] and g["GRID"] == "DIS"
+    assert list(g)[1:] == ["NCELLS", "NLAY", "NROW", "NCOL", "NJA", "XORIGIN", "YORIGIN", "ANGROT", "DELR", "DELC", "TOP",
+                           "BOTM", "IA", "JA", "IDOMAIN", "ICELLTYPE"]
+    assert (g["NCELLS"], g["NLAY"], g["NROW"], g["NCOL"]) == (24, 2, 3, 4) and g["NJA"] == gi.model.nja
+    assert np.array_equal(g["DELR"], [10, 20, 30, 40]) and np.array_equal(g["DELC"], [5, 6, 7])
+    assert g["TOP"].size == 12 and g["BOTM"].size == 24 and np.array_equal(g["IDOMAIN"], idom.reshape(-1))
+    ia, ja = g["IA"], g["JA"]
+    assert ia[0] == 1 and ia[-1] == gi.model.nja + 1 and ja.size == gi.model.nja
+    assert ia[5] == ia[6] and ia[10] == ia[11]                       # the removed / pass-through cells: empty rows
+    row = lambda n: ja[ia[n - 1] - 1:ia[n] - 1].tolist()             # noqa: E731
+    assert row(1) == [1, 2, 5, 13]                                   # itself, right, front, below
+    assert row(23)[0] == 23 and 11 not in row(23)                    # below the pass-through cell: nothing above
+    assert row(18)[0] == 18 and 6 not in row(18)                     # below the hole
