@@ -168,6 +168,8 @@ class GwfInput:
     head_file: str = None
     budget_file: str = None
     save: dict = field(default_factory=dict)          # iper -> list of (rtype, ocsetting tokens)
+    printrec: dict = field(default_factory=dict)      # the same for the OC PRINT records
+    list_file: str = None                             # model listing file (name file LIST option or <name file>.lst)
     grid: dict = None                                 # what the binary grid file records (output.write_grb)
     gnc: tuple = None                                 # GNC6: (noden, nodem, nodesj, alphasj), reduced 0-based nodes
     hfb: dict = field(default_factory=dict)           # iper -> (noden, nodem, hydchr), HFB6 barriers (0-based nodes)
@@ -189,6 +191,7 @@ class Simulation:
     sln: object
     ims: object
     warnings: list = field(default_factory=list)
+    time_units: str = None
 
 
 _PKG_TYPE = {"CHD6": T.PKG_CHD, "WEL6": T.PKG_WEL, "RIV6": T.PKG_RIV, "RCH6": T.PKG_RCH, "GHB6": T.PKG_GHB,
@@ -205,6 +208,11 @@ def read_tdis(path):
     if len(pd) != nper:
         raise Mf6InputError(f"{path}: PERIODDATA has {len(pd)} rows, NPER = {nper}")
     return nper, pd
+
+
+def read_time_units(path):
+    opt = _options(_block(read_blocks(path), "OPTIONS", required=False))
+    return opt["TIME_UNITS"][0].upper() if opt.get("TIME_UNITS") else None
 
 
 def read_ims(path, warnings):
@@ -474,6 +482,7 @@ def read_gwf_model(name, nam_path, base_dir, warnings):
     opt = _options(_block(b, "OPTIONS", required=False))
     inewton = 1 if "NEWTON" in opt else 0
     inewtonur = 1 if inewton and opt["NEWTON"] and opt["NEWTON"][0].upper() == "UNDER_RELAXATION" else 0
+    list_file = os.path.join(base_dir, opt["LIST"][0]) if opt.get("LIST") else os.path.splitext(nam_path)[0] + ".lst"
     files = {}
     stress = []
     for t in _block(b, "PACKAGES"):
@@ -671,6 +680,7 @@ def read_gwf_model(name, nam_path, base_dir, warnings):
                 # (autotest/test_gwf_rch02.py, test_gwf_rch03.py)
                 sp.periods[iper] = p.with_nodes(red, keep=None if keep.all() else keep)
         gi.packages.append(sp)
+    gi.list_file = list_file
     if "HFB6" in files:
         gi.hfb = read_hfb(files["HFB6"], shape, gi.nodereduced, m)
     if "GNC6" in files:
@@ -686,6 +696,8 @@ def read_gwf_model(name, nam_path, base_dir, warnings):
         for nm, num, lines in ob:
             if nm == "PERIOD":
                 gi.save[num] = [(t[1].upper(), [x.upper() for x in t[2:]]) for t in lines if t[0].upper() == "SAVE"]
+                gi.printrec[num] = [(t[1].upper(), [x.upper() for x in t[2:]]) for t in lines
+                                    if t[0].upper() == "PRINT"]
     return gi
 
 
@@ -796,4 +808,5 @@ def read_simulation(sim_dir):
     if sorted(x.upper() for x in sl[2:]) != sorted(index):
         raise Mf6InputError("every model must belong to the one IMS solution")
     sln, ims = read_ims(os.path.join(sim_dir, sl[1]), warnings)
-    return Simulation(sim_dir, nper, pd, models, exchanges, sln, ims, warnings)
+    return Simulation(sim_dir, nper, pd, models, exchanges, sln, ims, warnings,
+                      time_units=read_time_units(os.path.join(sim_dir, tim[0][1])))

@@ -166,6 +166,125 @@ class BudgetFileWriter:
         self.f.close()
 
 
+def fortran_g(x, w, d):
+    """Fortran `1P, Gw.d` editing (what tdis_ot prints its times with): F editing with d significant digits and four
+    trailing blanks while 0.1 <= |x| < 10**d, else 1PEw.d (one digit before the point, d after)"""
+    ax = abs(x)
+    if ax == 0.0:
+        return f"{x:{w - 4}.{d - 1}f}" + "    "
+    if 0.1 - 0.5 * 10.0 ** (-d - 1) <= ax < 10.0 ** d - 0.5:
+        n = 0
+        while ax >= 10.0 ** n - 0.5 * 10.0 ** (n - d):
+            n += 1
+        return f"{x:#{w - 4}.{d - n}f}" + "    "
+    return f"{x:{w}.{d}E}"
+
+
+def _budget_value(v, big):
+    """Budget.f90 value_to_string :150-170"""
+    a = abs(v)
+    if v != 0.0 and (a >= big or a < 0.1):
+        return f"{v:17.4E}"
+    return f"{v:17.4f}"
+
+
+class ListingFileWriter:
+    """The part of a model listing file (.lst) that post-processors parse: the VOLUME BUDGET table of `budget_ot`
+    (Budget.f90:178-311, labelled variant: formats 261 / 266 / 276 / 286 / 287 / 298 / 299 / 300) followed by the TIME
+    SUMMARY of `tdis_ot` (tdis.f90:273-340), written for every time step whose budget OC asks to PRINT.  Entries are
+    (text, rate in, rate out, package name); the cumulative volumes accumulate rate * delt like `addentry`."""
+
+    _SECONDS = {"SECONDS": 1.0, "MINUTES": 60.0, "HOURS": 3600.0, "DAYS": 86400.0, "YEARS": 31557600.0}
+
+    def __init__(self, path, model_name, time_units=None):
+        self.f = open(path, "w")
+        self.f.write(f"                                   MODFLOW 6 (mf6-b200 GPU path)\n\n"
+                     f" GROUNDWATER FLOW MODEL ({model_name.upper()})\n")
+        self.cnv = self._SECONDS.get((time_units or "").upper(), 0.0)
+        self.vol = {}
+
+    def write_budget(self, kstp, kper, delt, pertim, totim, entries):
+        w = self.f.write
+        rows = []
+        for i, (text, rin, rout, label) in enumerate(entries):
+            vin, vout = self.vol.get((i, text), (0.0, 0.0))
+            vin, vout = vin + rin * delt, vout + rout * delt
+            self.vol[(i, text)] = (vin, vout)
+            rows.append((f"{text.upper():>16s}"[:16], vin, vout, rin, rout, label))
+        totrin, totrot = sum(r[3] for r in rows), sum(r[4] for r in rows)
+        totvin, totvot = sum(r[1] for r in rows), sum(r[2] for r in rows)
+        big1, big2 = 9.99999e11, 9.99999e10
+        w(f"\n\n  VOLUME BUDGET FOR ENTIRE MODEL AT END OF TIME STEP{kstp:5d}, STRESS PERIOD{kper:4d}\n  " + 99 * "-" + "\n")
+        w(" \n     CUMULATIVE VOLUME      L**3       RATES FOR THIS TIME STEP      L**3/T          "
+          + f"{'PACKAGE NAME':<16s}\n     " + 18 * "-" + 17 * " " + 24 * "-" + 21 * " " + 16 * "-" + "\n\n"
+          + 11 * " " + "IN:" + 38 * " " + "IN:\n" + 11 * " " + "---" + 38 * " " + "---\n")
+        for nm, vin, _, rin, _, label in rows:
+            w(f"    {nm} ={_budget_value(vin, big1)}      {nm} ={_budget_value(rin, big1)}     {label}\n")
+        w(" \n" + 12 * " " + f"TOTAL IN ={_budget_value(totvin, big1)}" + 14 * " " + f"TOTAL IN ={_budget_value(totrin, big1)}\n")
+        w(" \n" + 10 * " " + "OUT:" + 37 * " " + "OUT:\n" + 10 * " " + "----" + 37 * " " + "----\n")
+        for nm, _, vout, _, rout, label in rows:
+            w(f"    {nm} ={_budget_value(vout, big1)}      {nm} ={_budget_value(rout, big1)}     {label}\n")
+        w(" \n" + 11 * " " + f"TOTAL OUT ={_budget_value(totvot, big1)}" + 13 * " " + f"TOTAL OUT ={_budget_value(totrot, big1)}\n")
+        diffr, diffv = totrin - totrot, totvin - totvot
+        pdiffr = 100.0 * diffr / ((totrin + totrot) / 2.0) if (totrin + totrot) != 0.0 else 0.0
+        pdiffv = 100.0 * diffv / ((totvin + totvot) / 2.0) if (totvin + totvot) != 0.0 else 0.0
+        w(" \n" + 12 * " " + f"IN - OUT ={_budget_value(diffv, big2)}" + 14 * " " + f"IN - OUT ={_budget_value(diffr, big2)}\n")
+        w(f" \n PERCENT DISCREPANCY ={pdiffv:15.2f}     PERCENT DISCREPANCY ={pdiffr:15.2f}\n\n")
+        # tdis_ot
+        w(" \n\n\n" + 9 * " " + f"TIME SUMMARY AT END OF TIME STEP{kstp:5d} IN STRESS PERIOD {kper:4d}\n")
+        if self.cnv == 0.0:
+            w(21 * " " + f"     TIME STEP LENGTH ={delt:15.6G}\n" + 21 * " " + f"   STRESS PERIOD TIME ={pertim:15.6G}\n"
+              + 21 * " " + f"TOTAL SIMULATION TIME ={totim:15.6G}\n")
+        else:
+            w(19 * " " + " SECONDS     MINUTES      HOURS" + 7 * " " + "DAYS        YEARS\n" + 20 * " " + 59 * "-" + "\n")
+            for label, t in (("  TIME STEP LENGTH", delt), ("STRESS PERIOD TIME", pertim), ("        TOTAL TIME", totim)):
+                sec = self.cnv * t
+                vals = (sec, sec / 60.0, sec / 3600.0, sec / 86400.0, sec / 86400.0 / 365.25)
+                w(" " + label + "".join(fortran_g(v, 12, 5) for v in vals) + "\n")
+            w("\n")
+        self.f.flush()
+        return pdiffr
+
+    def close(self):
+        self.f.close()
+
+
+def read_listing_budgets(path):
+    """the budget tables of a listing file -> list of dicts(kstp, kper, totim, IN / OUT rates and cumulative volumes
+    per (text, package), totals, percent discrepancy): the parsing a list-budget post-processor does"""
+    out, cur, side = [], None, None
+    with open(path) as f:
+        for line in f:
+            if "BUDGET FOR ENTIRE MODEL AT END OF TIME STEP" in line:
+                t = line.replace(",", " ").split()
+                cur = dict(kstp=int(t[t.index("STEP") + 1]), kper=int(t[t.index("PERIOD") + 1]), rates_in={},
+                           rates_out={}, volumes_in={}, volumes_out={})
+                out.append(cur)
+                side = None
+            elif cur is None:
+                continue
+            elif line.strip().startswith("IN:"):
+                side = "in"
+            elif line.strip().startswith("OUT:"):
+                side = "out"
+            elif "TOTAL IN =" in line or "TOTAL OUT =" in line:
+                v = line.split("=")
+                key = "total_in" if "TOTAL IN" in line else "total_out"
+                cur[key + "_volume"], cur[key] = float(v[1].split()[0]), float(v[2].split()[0])
+            elif "PERCENT DISCREPANCY =" in line:
+                cur["pdiffr"] = float(line.split("=")[2].split()[0])
+            elif "TOTAL TIME" in line and "totim" not in cur:
+                cur["totim_seconds"] = float(line.split("TIME")[1].split()[0])
+            elif "TOTAL SIMULATION TIME =" in line:
+                cur["totim"] = float(line.split("=")[1])
+            elif side and line.count("=") == 2:
+                a, b, c = line.split("=")
+                name, vol, rate, label = a.strip(), float(b.split()[0]), float(c.split()[0]), " ".join(c.split()[1:])
+                cur["volumes_" + side][(name, label)] = vol
+                cur["rates_" + side][(name, label)] = rate
+    return out
+
+
 def _grb_line(text, n):
     return (text[:n - 1].ljust(n - 1) + "\n").encode("ascii")
 

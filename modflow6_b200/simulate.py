@@ -17,7 +17,7 @@ import numpy as np
 from . import ctypes_types as T
 from .grid import merge_models, tdis_steps
 from .mf6io import read_simulation
-from .output import BudgetFileWriter, HeadFileWriter, write_grb
+from .output import PKG_TEXT, BudgetFileWriter, HeadFileWriter, ListingFileWriter, write_grb
 
 DHNOFLO = 1.0e30   # Constants.f90: head written for cells outside the active domain
 
@@ -151,9 +151,14 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
                 log(f"warning: {gi.name}: budget files are not written by the split-model run")
             else:
                 bw = BudgetFileWriter(gi.budget_file, gi.shape, gi.name)
-        writers.append((hw, bw))
+        lw = None
+        if write_output and gi.list_file and mine and rank is None and any(
+                r[0] == "BUDGET" for recs in gi.printrec.values() for r in recs):
+            lw = ListingFileWriter(gi.list_file, gi.name, sim.time_units)
+        writers.append((hw, bw, lw))
     current = [[None] * len(gi.packages) for gi in sim.models]     # list in force per package
     saving = [dict() for _ in sim.models]                          # rtype -> settings in force
+    printing = [dict() for _ in sim.models]
     reports, totim = [], 0.0
     hfb_now = {}                                                   # model -> barrier list in force
     for kper in range(1, sim.nper + 1):
@@ -171,6 +176,10 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
                 saving[k] = {}
                 for rtype, st in gi.save[kper]:
                     saving[k].setdefault(rtype, []).append(st)
+            if kper in gi.printrec:
+                printing[k] = {}
+                for rtype, st in gi.printrec[kper]:
+                    printing[k].setdefault(rtype, []).append(st)
         # a model without STO is steady; with STO the period keeps the last STEADY-STATE / TRANSIENT keyword,
         # TRANSIENT before any PERIOD block (gwf-sto.f90:170-182, 756)
         iss_of = []
@@ -213,7 +222,7 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
                 f"converged {d['converged']} budget discrepancy {d['pdiffr']:.3e} %")
             x = S.x                      # split-model run: the owned cells = this rank's model
             for k, gi in enumerate(sim.models):
-                hw, bw = writers[k]
+                hw, bw, lw = writers[k]
                 if hw and _should_save(saving[k].get("HEAD", []), kstp, nstp):
                     h = (x if rank is not None else x[offs[k]:offs[k] + gi.model.nodes]).copy()
                     h[gi.model.ibound == 0] = DHNOFLO
@@ -224,6 +233,31 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
                     local = [pkgs[i].with_nodes(pkgs[i].nodelist - int(offs[k])) for i in mine]
                     bw.write_step(kstp, kper, delt, pertim, totim, view, local,
                                   [gi.packages[owner[i][1]].name for i in mine], nodeuser=gi.nodeuser)
+            # the model budget table of the listing file (gwf_ot_bdsummary -> budget_ot, then tdis_ot)
+            exq = {}
+            for k, gi in enumerate(sim.models):
+                lw = writers[k][2]
+                if not (lw and _should_save(printing[k].get("BUDGET", []), kstp, nstp)):
+                    continue
+                mine = [i for i, (kk, _) in enumerate(owner) if kk == k]
+                view = S if len(models) == 1 else _ModelView(S, model, gi.model, offs[k], mine)
+                acc = lambda v: (float(v[v > 0].sum()), float(-v[v < 0].sum()))     # noqa: E731  rate_accumulator
+                entries = []
+                if gi.model.insto:
+                    ss_, sy_ = view.storage_rates
+                    entries.append(("STO-SS",) + acc(ss_) + ("STORAGE",))
+                    if gi.model.iconvert is not None and np.any(gi.model.iconvert):
+                        entries.append(("STO-SY",) + acc(sy_) + ("STORAGE",))
+                sv = view.simvals
+                for n_, i in enumerate(mine):
+                    entries.append((PKG_TEXT[pkgs[i].type],) + acc(np.asarray(sv[n_])) + (gi.packages[owner[i][1]].name.upper(),))
+                for e in sim.exchanges:            # gwf_gwf_bd: the exchange is a FLOW-JA-FACE entry of both budgets
+                    if k in (e["m1"], e["m2"]):
+                        if id(e) not in exq:
+                            exq[id(e)] = _exchange_rates(model, S.flowja, offs, e)
+                        q = exq[id(e)] if k == e["m1"] else -exq[id(e)]
+                        entries.append(("FLOW-JA-FACE",) + acc(q) + (e["name"].upper(),))
+                lw.write_budget(kstp, kper, delt, pertim, totim, entries)
             # exchange flows follow the models' own records (exg_ot after model_ot, mf6core.f90:755-771)
             for e in sim.exchanges:
                 if not e["save_flows"]:
@@ -237,11 +271,10 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
                             q = _exchange_rates(model, S.flowja, offs, e)
                         bw.write_exchange(kstp, kper, delt, pertim, totim, e["name"], sim.models[other].name,
                                           e["user" + mine], e["user" + theirs], sign * q, e["auxname"], e["aux"])
-    for hw, bw in writers:
-        if hw:
-            hw.close()
-        if bw:
-            bw.close()
+    for ws in writers:
+        for w_ in ws:
+            if w_:
+                w_.close()
     xf = np.array(S.x, copy=True)      # (a solution class may hand out a view of memory it owns)
     if rank is not None:
         heads = [_user_grid(sim.models[rank], xf).reshape(sim.models[rank].shape)]

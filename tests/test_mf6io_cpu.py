@@ -637,6 +637,9 @@ def write_pertim(d):
     text = open(nam).read().replace("END packages", "  CHD6  gwf_pertim_canal.chd  CHD-CANAL\n"
                                     "  CHD6  gwf_pertim_river.chd  CHD-RIVER\nEND packages")
     open(nam, "w").write(text)
+    oc = f"{d}/gwf_pertim.oc"
+    text = open(oc).read().replace("  PRINT HEAD LAST\n", "  PRINT HEAD LAST\n  PRINT BUDGET ALL\n")
+    open(oc, "w").write(text)
     mf6_inputs.write_sim(d, ["gwf_pertim"], [(0.0, 1, 1.0)], "BEGIN options\n  COMPLEXITY SIMPLE\nEND options\n")
 
 
@@ -651,6 +654,15 @@ def test_pertim_zero_length_period_literal_chd_flows(tmp_path):
     assert canal["srcpackage"].strip() == "CHD-CANAL" and river["srcpackage"].strip() == "CHD-RIVER"
     assert np.allclose([canal["q"][canal["q"] > 0].sum()], [99928.4941])
     assert np.allclose([-river["q"][river["q"] < 0].sum()], [99928.5036])
+    # and where the reference test reads them: the VOLUME BUDGET table of the model listing file (CHD_IN of the
+    # first CHD package, CHD2_OUT of the second)
+    from modflow6_b200.output import read_listing_budgets
+    bud = read_listing_budgets(tmp_path / "gwf_pertim.lst")
+    assert len(bud) == 1 and (bud[0]["kstp"], bud[0]["kper"]) == (1, 1)
+    assert np.allclose([bud[0]["rates_in"][("CHD", "CHD-CANAL")]], [99928.4941])
+    assert np.allclose([bud[0]["rates_out"][("CHD", "CHD-RIVER")]], [99928.5036])
+    assert bud[0]["volumes_in"][("CHD", "CHD-CANAL")] == 0.0          # a period of length zero moves no volume
+    assert abs(bud[0]["pdiffr"]) < 0.01 and bud[0]["totim_seconds"] == 0.0
 
 
 def write_auxmult(d, idx):
@@ -793,3 +805,27 @@ def test_disv_disu_connectivity_with_an_inactive_cell(tmp_path, grid):
         assert grb["VERTICES"].shape[0] == 32 and grb["VERTICES"].min() >= 1.0e8
     raw = open(tmp_path / "m.dis.grb", "rb").read()
     assert raw[:50] == (f"GRID {grid.upper()}".ljust(49) + "\n").encode() and raw[50:100].startswith(b"VERSION 1")
+
+
+def test_listing_budget_of_two_models_with_an_exchange(tmp_path):
+    """the model listing files of a two-model simulation (par_gwf01): each model's VOLUME BUDGET carries its CHD
+    package and the GWF-GWF exchange as a FLOW-JA-FACE entry (gwf_gwf_bd), what leaves the left model through the
+    exchange enters the right one, and each budget closes"""
+    from modflow6_b200.output import read_listing_budgets
+    mf6_inputs.write_par_gwf01(str(tmp_path), (1, 5, 5))
+    for m in ("leftmodel", "rightmodel"):
+        p = tmp_path / f"{m}.oc"
+        text = p.read_text()
+        assert "PRINT" not in text.upper() or "PRINT BUDGET" not in text.upper()
+        p.write_text(text.replace("END period 1", "  PRINT BUDGET ALL\nEND period 1").replace("END period  1", "  PRINT BUDGET ALL\nEND period  1"))
+    out = simulate.run(str(tmp_path), ordering=T.ORDER_NATURAL, solution_class=oracle_class())
+    assert all(r["converged"] for r in out["reports"])
+    left, right = (read_listing_budgets(tmp_path / f"{m}.lst")[-1] for m in ("leftmodel", "rightmodel"))
+    ex_l = [k for k in left["rates_out"] if k[0] == "FLOW-JA-FACE"]
+    ex_r = [k for k in right["rates_in"] if k[0] == "FLOW-JA-FACE"]
+    assert len(ex_l) == 1 and ex_l == ex_r and ex_l[0][1].startswith("GWF-GWF")
+    # heads fall from the right model's CHD (10) to the left model's (1): water crosses the exchange right -> left
+    q = right["rates_out"][ex_r[0]]
+    assert q > 0 and np.isclose(left["rates_in"][ex_l[0]], q, rtol=1e-9)
+    assert np.isclose(left["total_in"], left["total_out"], rtol=1e-6) and abs(left["pdiffr"]) < 0.01
+    assert any(k[0] == "CHD" for k in left["rates_out"]) and any(k[0] == "CHD" for k in right["rates_in"])

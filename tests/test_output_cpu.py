@@ -150,3 +150,30 @@ def test_binary_grid_file_of_a_dis_grid(tmp_path):
     assert row(1) == [1, 2, 5, 13]                                   # itself, right, front, below
     assert row(23)[0] == 23 and 11 not in row(23)                    # below the pass-through cell: nothing above
     assert row(18)[0] == 18 and 6 not in row(18)                     # below the hole
+
+
+def test_listing_file_budget_table_and_time_summary(tmp_path):
+    """ListingFileWriter against the formats of budget_ot (Budget.f90:292-310) and tdis_ot (tdis.f90:283-297): fixed
+    columns, F17.4 / 1PE17.4 switching of value_to_string, cumulative volumes = rate x delt summed, 1P G12.5 times"""
+    from modflow6_b200.output import ListingFileWriter, fortran_g, read_listing_budgets
+    w = ListingFileWriter(tmp_path / "m.lst", "m", "DAYS")
+    e = [("STO-SS", 0.0, 0.05, "STORAGE"), ("WEL", 0.0, 2500.0, "WEL_0"), ("CHD", 2500.05, 1.0e12, "CHD_0")]
+    w.write_budget(1, 1, 0.5, 0.5, 0.5, e)
+    w.write_budget(2, 1, 1.0, 1.5, 1.5, e)
+    w.close()
+    lines = open(tmp_path / "m.lst").read().split("\n")
+    hdr = [i for i, ln in enumerate(lines) if "VOLUME BUDGET" in ln]
+    assert lines[hdr[0]] == "  VOLUME BUDGET FOR ENTIRE MODEL AT END OF TIME STEP    1, STRESS PERIOD   1"
+    assert lines[hdr[0] + 1] == "  " + 99 * "-"
+    assert lines[hdr[0] + 3].startswith("     CUMULATIVE VOLUME      L**3       RATES FOR THIS TIME STEP      L**3/T")
+    row = [ln for ln in lines if ln.startswith("                 WEL =")]
+    assert row[1] == "                 WEL =        1250.0000                   WEL =        2500.0000     WEL_0"
+    assert "          STO-SS =       2.5000E-02" in "\n".join(lines)            # below 0.1: exponent form
+    assert "             CHD =       1.0000E+12" in "\n".join(lines)            # above 9.99999e11 too
+    b = read_listing_budgets(tmp_path / "m.lst")
+    assert [x["kstp"] for x in b] == [1, 2]
+    assert b[1]["volumes_out"][("WEL", "WEL_0")] == 2500.0 * 1.5 and b[1]["rates_in"][("CHD", "CHD_0")] == 2500.05
+    assert b[0]["totim_seconds"] == 43200.0 and b[1]["totim_seconds"] == 129600.0
+    assert " STRESS PERIOD TIME 1.29600E+05  2160.0      36.000      1.5000     4.10678E-03" in lines
+    assert "         TIME SUMMARY AT END OF TIME STEP    2 IN STRESS PERIOD    1" in lines
+    assert [fortran_g(v, 12, 5) for v in (86400.0, 24.0, 0.0)] == ["  86400.    ", "  24.000    ", "  0.0000    "]
