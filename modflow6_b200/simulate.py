@@ -16,7 +16,7 @@ import numpy as np
 
 from . import ctypes_types as T
 from .grid import merge_models, tdis_steps
-from .mf6io import read_simulation
+from .mf6io import Mf6InputError, TimeSeriesError, read_simulation
 from .output import PKG_TEXT, BudgetFileWriter, HeadFileWriter, ListingFileWriter, write_grb
 
 DHNOFLO = 1.0e30   # Constants.f90: head written for cells outside the active domain
@@ -105,7 +105,6 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
         try:
             model, offs = merge_models(models, sim.exchanges)
         except ValueError as e:
-            from .mf6io import Mf6InputError
             raise Mf6InputError(str(e)) from None
     sim.ims.gpu_ordering = ordering
     rank = None
@@ -133,7 +132,6 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
             gncs.append((n_ + offs[e["m1"]], m_ + offs[e["m2"]], np.where(j_ >= 0, j_ + offs[e["m1"]], -1), a_))
     if gncs:
         if rank is not None:
-            from .mf6io import Mf6InputError
             raise Mf6InputError("GNC6 is not available in the split-model run")
         numj = max(g[2].shape[1] for g in gncs)
         pad = lambda a, fill: np.pad(a, ((0, 0), (0, numj - a.shape[1])), constant_values=fill)   # noqa: E731
@@ -188,7 +186,6 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
                 upto = [p for p in gi.sto_transient if p <= kper]
                 iss_of.append(0 if (not upto or gi.sto_transient[max(upto)]) else 1)
         if len(set(iss_of)) > 1:     # one solution matrix carries one steady / transient state (see merge_models)
-            from .mf6io import Mf6InputError
             raise Mf6InputError(f"period {kper}: the models of the solution disagree on STEADY-STATE / TRANSIENT")
         iss = iss_of[0] if iss_of else 1
         # AUXMULTNAME without a time series is a constant factor; with time series (TS6) the lists are re-evaluated
@@ -203,14 +200,16 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
                 if kper in gi.hfb:
                     hfb_now[k] = gi.hfb[kper]
             if rank is not None:
-                from .mf6io import Mf6InputError
                 raise Mf6InputError("HFB6 is not available in the split-model run")
             lists = [(a + int(offs[k]), c + int(offs[k]), h) for k, (a, c, h) in sorted(hfb_now.items())]
             S.set_hfb(*(np.concatenate([l[i] for l in lists]) for i in range(3)))
         pertim = 0.0
         for kstp, delt in enumerate(tdis_steps(perlen, nstp, tsmult), start=1):
             if timed:
-                pkgs = [p.at_time(totim, totim + delt) for p in templates]
+                try:
+                    pkgs = [p.at_time(totim, totim + delt) for p in templates]
+                except TimeSeriesError as e:         # e.g. a series that ends before the simulation does
+                    raise Mf6InputError(f"period {kper} step {kstp}: {e}") from None
                 S.set_packages(pkgs)
             rep = S.timestep(kper, kstp, delt, iss)
             pertim += delt
