@@ -829,3 +829,14 @@ def test_listing_budget_of_two_models_with_an_exchange(tmp_path):
     assert q > 0 and np.isclose(left["rates_in"][ex_l[0]], q, rtol=1e-9)
     assert np.isclose(left["total_in"], left["total_out"], rtol=1e-6) and abs(left["pdiffr"]) < 0.01
     assert any(k[0] == "CHD" for k in left["rates_out"]) and any(k[0] == "CHD" for k in right["rates_in"])
+
+
+def test_time_series_that_ends_early_is_an_input_error(tmp_path):
+    """TimeSeries.f90 get_value_at_time / get_integrated_value stop the run when a step reaches past the last record
+    of a series (no extension to the end of the simulation for stress packages)"""
+    write_auxmult(str(tmp_path), 0)
+    p = tmp_path / "m.wel.ts"
+    rows = p.read_text().split("\n")
+    p.write_text("\n".join(r for r in rows if not r.strip().startswith(("3.0", "4.0"))))
+    with pytest.raises(mf6io.Mf6InputError, match="period 3 step 1"):
+        simulate.run(str(tmp_path), ordering=T.ORDER_NATURAL, solution_class=oracle_class(), write_output=False)
