@@ -192,6 +192,7 @@ class Simulation:
     ims: object
     warnings: list = field(default_factory=list)
     time_units: str = None
+    continue_: bool = False      # mfsim.nam CONTINUE: go on after a time step that did not converge
 
 
 _PKG_TYPE = {"CHD6": T.PKG_CHD, "WEL6": T.PKG_WEL, "RIV6": T.PKG_RIV, "RCH6": T.PKG_RCH, "GHB6": T.PKG_GHB,
@@ -809,4 +810,5 @@ def read_simulation(sim_dir):
         raise Mf6InputError("every model must belong to the one IMS solution")
     sln, ims = read_ims(os.path.join(sim_dir, sl[1]), warnings)
     return Simulation(sim_dir, nper, pd, models, exchanges, sln, ims, warnings,
-                      time_units=read_time_units(os.path.join(sim_dir, tim[0][1])))
+                      time_units=read_time_units(os.path.join(sim_dir, tim[0][1])),
+                      continue_="CONTINUE" in _options(_block(b, "OPTIONS", required=False)))

@@ -159,6 +159,7 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
     printing = [dict() for _ in sim.models]
     reports, totim = [], 0.0
     hfb_now = {}                                                   # model -> barrier list in force
+    stopped = False
     for kper in range(1, sim.nper + 1):
         perlen, nstp, tsmult = sim.perioddata[kper - 1]
         pkgs, owner = [], []
@@ -270,6 +271,14 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
                             q = _exchange_rates(model, S.flowja, offs, e)
                         bw.write_exchange(kstp, kper, delt, pertim, totim, e["name"], sim.models[other].name,
                                           e["user" + mine], e["user" + theirs], sign * q, e["auxname"], e["aux"])
+            # converge_check (Sim.f90:401-433): without CONTINUE in mfsim.nam a time step that did not converge ends
+            # the simulation after its output has been written
+            if not d["converged"] and not sim.continue_:
+                log("Simulation convergence failure. Simulation will terminate after output and deallocation.")
+                stopped = True
+                break
+        if stopped:
+            break
     for ws in writers:
         for w_ in ws:
             if w_:

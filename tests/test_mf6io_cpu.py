@@ -840,3 +840,21 @@ def test_time_series_that_ends_early_is_an_input_error(tmp_path):
     p.write_text("\n".join(r for r in rows if not r.strip().startswith(("3.0", "4.0"))))
     with pytest.raises(mf6io.Mf6InputError, match="period 3 step 1"):
         simulate.run(str(tmp_path), ordering=T.ORDER_NATURAL, solution_class=oracle_class(), write_output=False)
+
+
+def test_convergence_failure_stops_the_simulation_unless_continue(tmp_path):
+    """converge_check (Sim.f90:401-433): a time step that does not converge ends the simulation after its output --
+    unless mfsim.nam says CONTINUE"""
+    d = str(tmp_path)
+    mf6_inputs.write_gwf(d, "m", (1, 1, 10), 1.0, 1.0, 10.0, [0.0], 1.0, icelltype=1, strt=10.0,
+                         chd={1: [((1, 1, 1), 10.0), ((1, 1, 10), 5.0)]})
+    ims = ("BEGIN nonlinear\n  OUTER_DVCLOSE 1e-9\n  OUTER_MAXIMUM 1\nEND nonlinear\n\n"
+           "BEGIN linear\n  INNER_MAXIMUM 50\n  INNER_DVCLOSE 1e-10\n  INNER_RCLOSE 1e-8\nEND linear\n")
+    mf6_inputs.write_sim(d, ["m"], [(3.0, 3, 1.0)], ims)
+    out = simulate.run(d, ordering=T.ORDER_NATURAL, solution_class=oracle_class())
+    assert len(out["reports"]) == 1 and out["reports"][0]["converged"] == 0
+    assert len(read_head_file(tmp_path / "m.hds")) == 1                  # the failed step's output is written
+    nam = tmp_path / "mfsim.nam"
+    nam.write_text(nam.read_text().replace("BEGIN options\n", "BEGIN options\n  CONTINUE\n", 1))
+    out = simulate.run(d, ordering=T.ORDER_NATURAL, solution_class=oracle_class())
+    assert len(out["reports"]) == 3 and out["simulation"].continue_
