@@ -120,8 +120,21 @@ class _ArrayReader:
         elif key == "OPEN/CLOSE":
             fn = os.path.join(self.dir, ctl[1])
             if "(BINARY)" in up:
-                raise Mf6InputError("OPEN/CLOSE (BINARY) arrays are not supported")
-            a = np.loadtxt(fn).reshape(-1)[:n].astype(np.float64)
+                # records of a 52-byte header (kstp, kper, pertim, totim, text, m1, m2, m3) followed by m1 * m2
+                # values, one record per layer of a 3-D array (ArrayReaders.f90 read_binary_header :1029-1067)
+                item = 8 if dtype == np.float64 else 4
+                raw = open(fn, "rb").read()
+                vals, off = [], 0
+                while sum(v.size for v in vals) < n:
+                    if off + 52 > len(raw):
+                        raise Mf6InputError(f"{fn}: binary array file is shorter than the grid")
+                    m1, m2, _ = np.frombuffer(raw, dtype="<i4", count=3, offset=off + 40)
+                    cnt = int(m1) * int(m2)
+                    vals.append(np.frombuffer(raw, dtype="<f8" if item == 8 else "<i4", count=cnt, offset=off + 52))
+                    off += 52 + cnt * item
+                a = np.concatenate(vals)[:n].astype(np.float64)
+            else:
+                a = np.loadtxt(fn).reshape(-1)[:n].astype(np.float64)
         else:
             raise Mf6InputError(f"array control record {ctl[0]} is not supported")
         a = a * factor

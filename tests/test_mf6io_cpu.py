@@ -120,6 +120,18 @@ def test_array_control_records(tmp_path):
     g = mf6io.read_griddata(lines, str(tmp_path), {"K": ((2, 2, 3), np.float64), "ICELLTYPE": ((1, 2, 3), np.int32)})
     assert g["K"].tolist() == [2.5] * 6 + [2.0, 4.0, 6.0, 8.0, 10.0, 12.0]
     assert g["ICELLTYPE"].tolist() == [1, 2, 3, 4, 5, 6] and g["ICELLTYPE"].dtype == np.int32
+    # OPEN/CLOSE (BINARY): one 52-byte header + m1 x m2 values per layer, doubles or 4-byte integers -- a head file
+    # written by HeadFileWriter has exactly that layout, which is how the reference restarts from saved heads
+    from modflow6_b200.output import HeadFileWriter
+    hw = HeadFileWriter(str(tmp_path / "h.bin"), (2, 2, 3))
+    hw.write(1, 1, 1.0, 1.0, np.arange(12.0))
+    hw.close()
+    import struct
+    with open(tmp_path / "i.bin", "wb") as f:
+        f.write(struct.pack("<iidd16siii", 1, 1, 1.0, 1.0, b"         IDOMAIN", 3, 2, 1) + np.arange(6, dtype="<i4").tobytes())
+    lines = [["strt"], ["OPEN/CLOSE", "h.bin", "(BINARY)", "FACTOR", "2.0"], ["idomain"], ["OPEN/CLOSE", "i.bin", "(BINARY)"]]
+    g = mf6io.read_griddata(lines, str(tmp_path), {"STRT": ((2, 2, 3), np.float64), "IDOMAIN": ((1, 2, 3), np.int32)})
+    assert g["STRT"].tolist() == (2.0 * np.arange(12.0)).tolist() and g["IDOMAIN"].tolist() == [0, 1, 2, 3, 4, 5]
     assert mf6io._tokens("  SAVE  HEAD, 'my file.hds'  # trailing") == ["SAVE", "HEAD", "my file.hds"]
     assert mf6io._tokens("! comment") == [] and mf6io._tokens("// c") == []
 
