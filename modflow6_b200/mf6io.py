@@ -182,6 +182,7 @@ class GwfInput:
     budget_file: str = None
     save: dict = field(default_factory=dict)          # iper -> list of (rtype, ocsetting tokens)
     printrec: dict = field(default_factory=dict)      # the same for the OC PRINT records
+    budgetcsv_file: str = None                        # OC BUDGETCSV FILEOUT
     list_file: str = None                             # model listing file (name file LIST option or <name file>.lst)
     grid: dict = None                                 # what the binary grid file records (output.write_grb)
     gnc: tuple = None                                 # GNC6: (noden, nodem, nodesj, alphasj), reduced 0-based nodes
@@ -707,6 +708,8 @@ def read_gwf_model(name, nam_path, base_dir, warnings):
                 gi.head_file = os.path.join(base_dir, t[2])
             elif t[0].upper() == "BUDGET" and t[1].upper() == "FILEOUT":
                 gi.budget_file = os.path.join(base_dir, t[2])
+            elif t[0].upper() == "BUDGETCSV" and t[1].upper() == "FILEOUT":
+                gi.budgetcsv_file = os.path.join(base_dir, t[2])
         for nm, num, lines in ob:
             if nm == "PERIOD":
                 gi.save[num] = [(t[1].upper(), [x.upper() for x in t[2:]]) for t in lines if t[0].upper() == "SAVE"]

@@ -249,6 +249,30 @@ class ListingFileWriter:
         self.f.close()
 
 
+class BudgetCsvWriter:
+    """OC `BUDGETCSV FILEOUT <file>`: one line per time step (Budget.f90 writecsv :671-718, header :726-757):
+    time, every entry's inflow rate, every entry's outflow rate, TOTAL_IN, TOTAL_OUT, PERCENT_DIFFERENCE"""
+
+    def __init__(self, path):
+        self.f = open(path, "w")
+        self.header = False
+
+    def write(self, totim, entries):
+        if not self.header:
+            names = [f"{t.strip().upper()}({lab.strip()})" for t, _, _, lab in entries]
+            self.f.write("time," + "".join(n + "_IN," for n in names) + "".join(n + "_OUT," for n in names)
+                         + "TOTAL_IN,TOTAL_OUT,PERCENT_DIFFERENCE\n")
+            self.header = True
+        rin, rout = [e[1] for e in entries], [e[2] for e in entries]
+        tin, tout = sum(rin), sum(rout)
+        pd = 100.0 * (tin - tout) / ((tin + tout) / 2.0) if (tin + tout) != 0.0 else 0.0
+        self.f.write(",".join(repr(float(v)) for v in [totim] + rin + rout + [tin, tout, pd]) + "\n")
+        self.f.flush()
+
+    def close(self):
+        self.f.close()
+
+
 def read_listing_budgets(path):
     """the budget tables of a listing file -> list of dicts(kstp, kper, totim, IN / OUT rates and cumulative volumes
     per (text, package), totals, percent discrepancy): the parsing a list-budget post-processor does"""

@@ -17,7 +17,7 @@ import numpy as np
 from . import ctypes_types as T
 from .grid import merge_models, tdis_steps
 from .mf6io import Mf6InputError, TimeSeriesError, read_simulation
-from .output import PKG_TEXT, BudgetFileWriter, HeadFileWriter, ListingFileWriter, write_grb
+from .output import PKG_TEXT, BudgetCsvWriter, BudgetFileWriter, HeadFileWriter, ListingFileWriter, write_grb
 
 DHNOFLO = 1.0e30   # Constants.f90: head written for cells outside the active domain
 
@@ -153,7 +153,8 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
         if write_output and gi.list_file and mine and rank is None and any(
                 r[0] == "BUDGET" for recs in gi.printrec.values() for r in recs):
             lw = ListingFileWriter(gi.list_file, gi.name, sim.time_units)
-        writers.append((hw, bw, lw))
+        cw = BudgetCsvWriter(gi.budgetcsv_file) if (write_output and gi.budgetcsv_file and mine and rank is None) else None
+        writers.append((hw, bw, lw, cw))
     current = [[None] * len(gi.packages) for gi in sim.models]     # list in force per package
     saving = [dict() for _ in sim.models]                          # rtype -> settings in force
     printing = [dict() for _ in sim.models]
@@ -222,7 +223,7 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
                 f"converged {d['converged']} budget discrepancy {d['pdiffr']:.3e} %")
             x = S.x                      # split-model run: the owned cells = this rank's model
             for k, gi in enumerate(sim.models):
-                hw, bw, lw = writers[k]
+                hw, bw = writers[k][:2]
                 if hw and _should_save(saving[k].get("HEAD", []), kstp, nstp):
                     h = (x if rank is not None else x[offs[k]:offs[k] + gi.model.nodes]).copy()
                     h[gi.model.ibound == 0] = DHNOFLO
@@ -236,8 +237,10 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
             # the model budget table of the listing file (gwf_ot_bdsummary -> budget_ot, then tdis_ot)
             exq = {}
             for k, gi in enumerate(sim.models):
-                lw = writers[k][2]
+                lw, cw = writers[k][2:]
                 if not (lw and _should_save(printing[k].get("BUDGET", []), kstp, nstp)):
+                    lw = None
+                if not (lw or cw):
                     continue
                 mine = [i for i, (kk, _) in enumerate(owner) if kk == k]
                 view = S if len(models) == 1 else _ModelView(S, model, gi.model, offs[k], mine)
@@ -257,7 +260,10 @@ def run(sim_dir, ordering=T.ORDER_BLOCK_MULTICOLOR, write_output=True, log=None,
                             exq[id(e)] = _exchange_rates(model, S.flowja, offs, e)
                         q = exq[id(e)] if k == e["m1"] else -exq[id(e)]
                         entries.append(("FLOW-JA-FACE",) + acc(q) + (e["name"].upper(),))
-                lw.write_budget(kstp, kper, delt, pertim, totim, entries)
+                if lw:
+                    lw.write_budget(kstp, kper, delt, pertim, totim, entries)
+                if cw:
+                    cw.write(totim, entries)             # every time step (gwf_ot_bdsummary)
             # exchange flows follow the models' own records (exg_ot after model_ot, mf6core.f90:755-771)
             for e in sim.exchanges:
                 if not e["save_flows"]:

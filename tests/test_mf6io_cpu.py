@@ -870,3 +870,19 @@ def test_convergence_failure_stops_the_simulation_unless_continue(tmp_path):
     nam.write_text(nam.read_text().replace("BEGIN options\n", "BEGIN options\n  CONTINUE\n", 1))
     out = simulate.run(d, ordering=T.ORDER_NATURAL, solution_class=oracle_class())
     assert len(out["reports"]) == 3 and out["simulation"].continue_
+
+
+def test_budget_csv_file(tmp_path):
+    """OC BUDGETCSV FILEOUT: header and one row per time step in the layout of Budget.f90 writecsv / write_csv_header"""
+    write_auxmult(str(tmp_path), 0)
+    p = tmp_path / "m.oc"
+    p.write_text(p.read_text().replace("  BUDGET FILEOUT m.cbc\n", "  BUDGET FILEOUT m.cbc\n  BUDGETCSV FILEOUT m.bud.csv\n"))
+    simulate.run(str(tmp_path), ordering=T.ORDER_NATURAL, solution_class=oracle_class())
+    rows = (tmp_path / "m.bud.csv").read_text().strip().split("\n")
+    assert rows[0] == ("time,CHD(CHD_0)_IN,WEL(WEL_0)_IN,CHD(CHD_0)_OUT,WEL(WEL_0)_OUT,"
+                       "TOTAL_IN,TOTAL_OUT,PERCENT_DIFFERENCE")
+    data = np.array([[float(v) for v in r.split(",")] for r in rows[1:]])
+    assert data.shape == (13, 8) and np.allclose(data[:, 0], [0.1 * i for i in range(1, 11)] + [2.0, 3.0, 4.0])
+    assert np.allclose(data[:, 2], np.array(7 * [1.0, 0.0])[:-1])           # the well injects 1, 0, 1, ...
+    on = data[:, 2] > 0.5                                                   # (idle steps: in and out are round-off)
+    assert np.allclose(data[:, 5], data[:, 6], atol=1e-6) and np.abs(data[on, 7]).max() < 1e-3
