@@ -585,6 +585,9 @@ def read_gwf_model(name, nam_path, base_dir, warnings):
     for k in nopt:
         if k in ("XT3D", "TVK6"):
             raise Mf6InputError(f"NPF option {k} is not supported on the GPU path")
+        if k in ("SAVE_SPECIFIC_DISCHARGE", "SAVE_SATURATION"):
+            warnings.append(f"{name}: NPF {k}: the DATA-{'SPDIS' if 'SPEC' in k else 'SAT'} record is not written to the "
+                            "budget file by this path")
     np_ = read_griddata(_block(nb, "GRIDDATA"), base_dir,
                         {"ICELLTYPE": (ashape, np.int32), "K": (ashape, np.float64), "K22": (ashape, np.float64),
                          "K33": (ashape, np.float64), "ANGLE1": (ashape, np.float64), "ANGLE2": (ashape, np.float64),
