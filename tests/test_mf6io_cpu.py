@@ -886,3 +886,20 @@ def test_budget_csv_file(tmp_path):
     assert np.allclose(data[:, 2], np.array(7 * [1.0, 0.0])[:-1])           # the well injects 1, 0, 1, ...
     on = data[:, 2] > 0.5                                                   # (idle steps: in and out are round-off)
     assert np.allclose(data[:, 5], data[:, 6], atol=1e-6) and np.abs(data[on, 7]).max() < 1e-3
+
+
+def test_time_series_average_equals_quadrature():
+    """STEPWISE / LINEAR values over a step are time-weighted averages: compared with a fine midpoint quadrature of
+    the pointwise interpolant (get_value_at_time) on seeded random series and intervals"""
+    from modflow6_b200.timeseries import TimeSeries
+    rng = np.random.default_rng(7)
+    for method in ("STEPWISE", "LINEAR"):
+        for _ in range(20):
+            t = np.cumsum(rng.uniform(0.1, 2.0, 8))
+            s = TimeSeries("x", method, t, rng.normal(size=8))
+            a, b = np.sort(rng.uniform(t[0], t[-1], 2))
+            if b - a < 1e-3:
+                continue
+            mid = a + (np.arange(20000) + 0.5) * (b - a) / 20000
+            quad = np.mean([s.value_at(x) for x in mid])
+            assert abs(s.value(a, b) - quad) < 2e-3, (method, a, b)
